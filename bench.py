@@ -1,0 +1,409 @@
+#!/usr/bin/env python
+"""Benchmark of the boundary-element hot path (BASELINE.json: "G+K entries/sec
+(fp64) and CG GEMV GB/s ... vs host-CPU reference").
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # reference CPU path
+
+One step = one pass of the hot path on a synthetic refined UV sphere
+(SURVEY.md section 8d): fused G+K assembly (diagonal + off-diagonal kernels) into
+resident HBM buffers, then the dense CG solve of G sigma = -v to a relative
+residual of 1e-13.  N=1 runs config C2 (19,880 triangles); for N>1 the mesh is
+refined so that the N^2 matrix work per GPU stays fixed ("weak" scaling), rows
+block-sharded over the ranks, NCCL only inside the CG.
+
+value   = G+K entries per second over the whole step = 2*N^2 / ms_per_step
+e2e     = same metric through the public Python API (LaplaceSolver on a host
+          polydata -> host response), host<->device copies inside the timed region
+roofline= dominant kernel (fused G+K off-diagonal assembly) against the FP64 FMA
+          rate measured on this GPU in the same run; roofline_gemv = CG GEMV against
+          MEASURED_PEAKS.json's HBM copy bandwidth
+cpu_baseline = the reference's own C++ (oracle/_ref/libicqref.so, unmodified
+          sources) or, when that was not built, the C restatement, on a bounded
+          sub-mesh sample, 1 thread (the reference ships single-threaded).
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = 'G+K entries/sec (fp64)'
+UNIT = 'entries/s'
+EXPR_V = '1./sqrt(x**2 + (y-2.)**2 + (z-4.)**2)'   # CMakeLists.txt:487 of the reference
+FLOP_PER_EVAL_G = 12.0
+FLOP_PER_EVAL_GK = 18.0    # + 1/r^3 (2 mul) and two weighted accumulations (2 fma), DESIGN.md
+
+
+def workload(ngpus, name):
+    """(label, n_theta, n_phi) of the UV sphere for this GPU count."""
+    if name == 'c2' or (name == 'auto' and ngpus == 1):
+        return 'uv_sphere_142x71_N19880 (config C2)', 142, 71
+    if name == 'c5':
+        return 'uv_sphere_448x224_N199808 (config C5)', 448, 224
+    if name == 'c3':
+        return 'uv_sphere_318x159_N100488 (size of config C3)', 318, 159
+    if name == 'small':
+        return 'uv_sphere_48x24_N2208 (smoke size)', 48, 24
+    # weak scaling from C2: N^2/P fixed  ->  n_theta ~ 142 * P^(1/4)
+    nt = int(round(142 * ngpus ** 0.25 / 2.0)) * 2
+    return 'uv_sphere_{0}x{1}_N{2} (C2 scaled to {3} GPUs, N^2/GPU fixed)'.format(
+        nt, nt // 2, 2 * nt * (nt // 2 - 1), ngpus), nt, nt // 2
+
+
+def centroid_potential(xyz, tri):
+    cen = (xyz[tri[:, 0]] + xyz[tri[:, 1]] + xyz[tri[:, 2]]) / 3.
+    return 1. / numpy.sqrt(cen[:, 0] ** 2 + (cen[:, 1] - 2.) ** 2 + (cen[:, 2] - 4.) ** 2)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    QUERY = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+             'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+             'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        threading.Thread.__init__(self, daemon=True)
+        self.index = index
+        self.samples = []
+        self.stop_flag = False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.QUERY,
+                                      '--format=csv,noheader,nounits'], capture_output=True,
+                                     text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([f.strip() for f in out.split(',')])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        sm = [float(s[0]) for s in self.samples if s[0].replace('.', '').isdigit()]
+        mx = [float(s[1]) for s in self.samples if s[1].replace('.', '').isdigit()]
+        reasons = set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for s in self.samples:
+            for k, nm in enumerate(names):
+                if len(s) > 3 + k and s[3 + k].lower().startswith('active'):
+                    reasons.add(nm)
+        return {'sm_mhz': float(numpy.median(sm)) if sm else None,
+                'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(self.samples)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f), 'measured (MEASURED_PEAKS.json)'
+    return {'hbm_gbs': 6650.0}, 'fallback (B200_PROFILING.md)'
+
+
+# ---------------------------------------------------------------------------------------
+# reference arm / cpu baseline
+# ---------------------------------------------------------------------------------------
+
+def _ref_worker(args):
+    xyz, tri, order, use_ref = args
+    from oracle import oracle
+    t0 = time.perf_counter()
+    if use_ref:
+        g = oracle.ref_offdiag(xyz, tri)
+    else:
+        g = oracle.offdiag(xyz, tri)
+    g[numpy.diag_indices_from(g)] = oracle.diag(xyz, tri, order)
+    return time.perf_counter() - t0, float(g[0, 1])
+
+
+def cpu_assembly_sample(xyz, tri, ns, workers, order=5):
+    """Each worker assembles G for its own ns-triangle sub-mesh of the workload with
+    the reference's C++ (off-diagonal) and the restated self term.  Returns
+    (seconds wall, entries, kind)."""
+    from oracle import oracle
+    oracle.build()
+    use_ref = oracle.have_reference()
+    n = tri.shape[0]
+    jobs = []
+    for w in range(workers):
+        start = (w * ns) % max(1, n - ns)
+        jobs.append((xyz, tri[start:start + ns], order, use_ref))
+    t0 = time.perf_counter()
+    if workers == 1:
+        _ref_worker(jobs[0])
+    else:
+        import multiprocessing
+        with multiprocessing.get_context('fork').Pool(workers) as pool:
+            pool.map(_ref_worker, jobs)
+    wall = time.perf_counter() - t0
+    return wall, workers * ns * ns, 'reference' if use_ref else 'port'
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    label, nt, nph = workload(args.gpus, args.workload)
+    from icqsol_b200.mesh.generators import uvSphere
+    xyz, tri = uvSphere(1.0, nt, nph)
+    cores = os.cpu_count() or 1
+    ns = args.cpu_sample
+    times = []
+    kind = 'port'
+    for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        wall, entries, kind = cpu_assembly_sample(xyz, tri, ns, cores)
+        # the reference's solve: LU on the sample system (bem/icqLaplaceSolver.py:36)
+        from oracle import oracle
+        g = oracle.green_matrix(xyz, tri[:ns], 5, threads=True) if it == 0 else g
+        v = centroid_potential(xyz, tri[:ns])
+        oracle.laplace_response(g, v)
+        dt = time.perf_counter() - t0
+        if it >= args.warmup:
+            times.append((dt, entries))
+    total_t = sum(t for t, _ in times)
+    total_e = sum(e for _, e in times)
+    value = total_e / total_t
+    sample = ('{0} processes x G of a {1}-triangle sub-mesh of the workload (reference C++ '
+              'off-diagonal + restated self term) + one numpy LU solve of that size; the reference '
+              'has no K, entries counted are G entries'.format(cores, ns))
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * total_t / len(times),
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+        'data': 'synthetic', 'config': {'workload': label, 'sample': sample},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': kind, 'sample': sample},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------
+# CUDA arm
+# ---------------------------------------------------------------------------------------
+
+def run_b200(args):
+    import ctypes
+    import torch
+    import torch.distributed as dist
+    from icqsol_b200 import _lib
+    from icqsol_b200.bem import icqRowPartition as rowPartition
+    from icqsol_b200.bem.icqBaseLaplaceSolver import leadingDimension
+    from icqsol_b200.mesh.generators import uvSphere
+    from icqsol_b200.mesh.polydata import PolyData, DataArray
+    from icqsol_b200.bem.icqLaplaceSolver import LaplaceSolver
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise RuntimeError('bench.py: no CUDA device; the CUDA path has no CPU fallback')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+    if world != args.gpus and rank == 0:
+        print('warning: --gpus {0} but WORLD_SIZE {1}'.format(args.gpus, world), file=sys.stderr)
+
+    label, nt, nph = workload(world, args.workload)
+    xyz, tri = uvSphere(1.0, nt, nph)
+    n = tri.shape[0]
+    v = centroid_potential(xyz, tri)
+
+    # ---- resident set-up (not timed): context, mesh in HBM, matrix buffers ----------------
+    ctx = _lib.Context(local)
+    lib = ctx.lib
+    stream = torch.cuda.Stream(device=dev)
+    ctx.check(lib.icqb_set_stream(ctx.handle, stream.cuda_stream))
+    if world > 1:
+        uid = ctypes.create_string_buffer(128)
+        if rank == 0:
+            ctx.check(lib.icqb_comm_unique_id(uid))
+        raw = rowPartition.broadcastBytes(uid.raw, 128, src=0)
+        ctx.check(lib.icqb_comm_init(ctx.handle, ctypes.create_string_buffer(raw, 128), rank, world))
+    ctx.check(lib.icqb_set_mesh(ctx.handle, xyz.ctypes.data_as(_lib.c_double_p), xyz.shape[0],
+                                tri.ctypes.data_as(_lib.c_int64_p), n))
+    r0, r1 = rowPartition.rowRange(n, rank, world)
+    ctx.check(lib.icqb_set_rows(ctx.handle, r0, r1))
+    rows = r1 - r0
+    ld = leadingDimension(n)
+    gbuf = torch.empty((max(rows, 1), ld), dtype=torch.float64, device=dev)
+    kbuf = torch.empty((max(rows, 1), ld), dtype=torch.float64, device=dev)
+    bdev = torch.from_numpy(v[r0:r1].copy()).to(dev)
+    xdev = torch.zeros(max(rows, 1), dtype=torch.float64, device=dev)
+    area2 = lib.icqb_area2_dev(ctx.handle) + 8 * r0
+    torch.cuda.synchronize(dev)
+
+    phase = {'assembly_ms': [], 'offdiag_ms': [], 'diag_ms': [], 'solve_ms': [], 'gemv_ms': [],
+             'iters': [], 'resid': []}
+
+    def step(record):
+        with torch.cuda.stream(stream):
+            xdev.zero_()
+        t0 = time.perf_counter()
+        ctx.check(lib.icqb_assemble_dev(ctx.handle, 5, gbuf.data_ptr(), kbuf.data_ptr(), ld))
+        t1 = time.perf_counter()
+        iters = ctypes.c_int64(0)
+        r2 = ctypes.c_double(0.)
+        rinf = ctypes.c_double(0.)
+        ctx.check(lib.icqb_cg_solve_dev(ctx.handle, gbuf.data_ptr(), n, ld, area2, 0,
+                                        bdev.data_ptr(), xdev.data_ptr(), 1e-13, 1, -1,
+                                        ctypes.byref(iters), ctypes.byref(r2), ctypes.byref(rinf)))
+        if record:
+            phase['assembly_ms'].append(1e3 * (t1 - t0))
+            phase['offdiag_ms'].append(ctx.last_ms(1))
+            phase['diag_ms'].append(ctx.last_ms(2))
+            phase['solve_ms'].append(ctx.last_ms(4))
+            phase['gemv_ms'].append(ctx.last_ms(3))
+            phase['iters'].append(iters.value)
+            phase['resid'].append(r2.value)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        step(False)
+    sampler = ClockSampler(local)
+    launches0 = ctx.launch_count()
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step(True)
+    e1.record(stream)
+    barrier()
+    sampler.stop_flag = True
+    ms_total = e0.elapsed_time(e1)
+    launches = ctx.launch_count() - launches0
+    if world > 1:
+        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_per_step = ms_total / args.steps
+    value = 2.0 * n * n / (ms_per_step * 1e-3)
+
+    # ---- fp64 peak of this GPU, measured in-run -------------------------------------------
+    peak = ctypes.c_double(0.)
+    ctx.check(lib.icqb_measure_fp64_peak(ctx.handle, ctypes.byref(peak)))
+
+    # ---- e2e through the public Python API (host polydata in, host response out) ----------
+    e2e_times = []
+    h2d = xyz.nbytes + tri.nbytes + v.nbytes
+    d2h = 8 * n
+    for it in range(1 + args.e2e_steps):
+        pd = PolyData.from_arrays(xyz, tri, dtype=numpy.float64)
+        pd.GetCellData().AddArray(DataArray('v', v))
+        barrier()
+        t0 = time.perf_counter()
+        solver = LaplaceSolver(pd, float('inf'), 5, computeK=True, device=local)
+        rsp = solver.computeResponseField()
+        torch.cuda.synchronize(dev)
+        dt = time.perf_counter() - t0
+        if it > 0:
+            e2e_times.append(dt)
+        del solver
+    e2e_s = max(e2e_times) if world == 1 else None
+    if world > 1:
+        t = torch.tensor([numpy.mean(e2e_times)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    else:
+        e2e_s = float(numpy.mean(e2e_times))
+    backward = None
+    if rank == 0:
+        backward = float(numpy.abs(rsp).max())
+
+    if rank == 0:
+        peaks, peak_src = measured_peaks()
+        off_ms = float(numpy.mean(phase['offdiag_ms']))
+        gemv_ms = float(numpy.mean(phase['gemv_ms']))
+        # algorithmic flop of this rank's off-diagonal launch: symmetric block + direct columns
+        pairs_local = rows * (rows - 1) / 2.0 + rows * (n - rows)
+        flop = pairs_local * 256.0 * FLOP_PER_EVAL_GK
+        achieved = flop / (off_ms * 1e-3) / 1e12
+        gemv_bytes = 8.0 * rows * n
+        gemv_gbs = gemv_bytes / (gemv_ms * 1e-3) / 1e9 if gemv_ms > 0 else 0.0
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': label, 'triangles': n, 'diag_order': 5, 'offdiag_order': 8,
+                       'step': 'fused G+K assembly + CG solve (rel. residual 1e-13)',
+                       'rows_per_gpu': rows, 'parallelism': 'row-block x{0}'.format(world),
+                       'l2': 'inputs larger than L2 (matrix {0:.1f} GB per GPU)'.format(
+                           2 * 8.0 * rows * ld / 1e9)},
+            'phases': {'assembly_ms': float(numpy.mean(phase['assembly_ms'])),
+                       'offdiag_kernel_ms': off_ms,
+                       'diag_kernel_ms': float(numpy.mean(phase['diag_ms'])),
+                       'assembly_entries_per_s': 2.0 * n * n / (numpy.mean(phase['assembly_ms']) * 1e-3),
+                       'solve_ms': float(numpy.mean(phase['solve_ms'])),
+                       'cg_iters': int(numpy.mean(phase['iters'])),
+                       'cg_residual2': float(numpy.max(phase['resid'])),
+                       'gemv_ms': gemv_ms, 'gemv_gbs_per_gpu': gemv_gbs,
+                       'gemv_gbs_aggregate': gemv_gbs * world},
+            'roofline': {'bound': 'fp64', 'kernel': 'k_offdiag<G+K>', 'achieved': achieved,
+                         'peak': peak.value, 'unit': 'TFLOP/s', 'frac': achieved / peak.value,
+                         'traffic': None,
+                         'peak_source': 'DFMA loop measured in this run (icqb_measure_fp64_peak)',
+                         'flop_per_evaluation': FLOP_PER_EVAL_GK,
+                         'fp64_instr_per_evaluation': 16,
+                         'issue_frac': (pairs_local * 256.0 * 16 * 2 / (off_ms * 1e-3) / 1e12) / peak.value},
+            'roofline_gemv': {'bound': 'hbm', 'kernel': 'k_gemv', 'achieved': gemv_gbs,
+                              'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
+                              'frac': gemv_gbs / peaks['hbm_gbs'], 'traffic': None,
+                              'peak_source': peak_src},
+            'e2e': {'value': 2.0 * n * n / e2e_s, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d),
+                    'd2h_bytes_per_step': int(d2h), 'ms_per_step': 1e3 * e2e_s,
+                    'api': 'LaplaceSolver(pdata, inf, 5, computeK=True).computeResponseField()'},
+            'gpu_launches': int(launches),
+            'clocks': sampler.summary(),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            wall, entries, kind = cpu_assembly_sample(xyz, tri, args.cpu_sample, 1)
+            line['cpu_baseline'] = {
+                'value': entries / wall, 'unit': UNIT, 'cores': 1, 'kind': kind,
+                'sample': 'G (no K in the reference) of the first {0} triangles of the workload: '
+                          'reference C++ off-diagonal + restated self term, {1:.1f} s'.format(
+                              args.cpu_sample, wall)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--workload', default='auto', choices=['auto', 'c2', 'c3', 'c5', 'small'])
+    ap.add_argument('--cpu-sample', type=int, default=2400,
+                    help='triangles of the CPU baseline sub-mesh (2400 -> ~9 s single core)')
+    ap.add_argument('--e2e-steps', type=int, default=2)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == '__main__':
+    main()

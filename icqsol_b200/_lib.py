@@ -1,0 +1,121 @@
+"""ctypes binding of include/icqb.h (the counterpart of
+``cdll.LoadLibrary(getSharedLibraryName('icqLaplaceMatricesCpp'))`` at
+bem/icqBaseLaplaceSolver.py:26-27, with explicit argtypes/restype)."""
+import ctypes
+from ctypes import (POINTER, byref, c_char_p, c_double, c_int, c_int64, c_uint64,
+                    c_void_p)
+
+from icqsol_b200.util.icqSharedLibraryUtils import getSharedLibraryName
+
+LIB_NAME = 'libicqLaplaceMatricesB200'
+
+ICQB_OK = 0
+ICQB_ECUDA = -1
+ICQB_EARG = -2
+ICQB_EORDER = -3
+ICQB_ESTATE = -4
+ICQB_ECOMM = -5
+
+c_double_p = POINTER(c_double)
+c_int64_p = POINTER(c_int64)
+
+# (name, restype, argtypes) for every symbol include/icqb.h declares
+SIGNATURES = [
+    ('icqb_create', c_int, [POINTER(c_void_p), c_int]),
+    ('icqb_destroy', c_int, [c_void_p]),
+    ('icqb_last_error', c_char_p, [c_void_p]),
+    ('icqb_device', c_int, [c_void_p]),
+    ('icqb_stream', c_uint64, [c_void_p]),
+    ('icqb_set_stream', c_int, [c_void_p, c_uint64]),
+    ('icqb_synchronize', c_int, [c_void_p]),
+    ('icqb_set_mesh', c_int, [c_void_p, c_double_p, c_int64, c_int64_p, c_int64]),
+    ('icqb_num_triangles', c_int64, [c_void_p]),
+    ('icqb_set_rows', c_int, [c_void_p, c_int64, c_int64]),
+    ('icqb_get_rows', c_int, [c_void_p, c_int64_p, c_int64_p]),
+    ('icqb_area2_dev', c_uint64, [c_void_p]),
+    ('icqb_assemble_dev', c_int, [c_void_p, c_int, c_uint64, c_uint64, c_int64]),
+    ('icqb_assemble_host', c_int, [c_void_p, c_int, c_double_p, c_double_p]),
+    ('icqb_diagonal_host', c_int, [c_void_p, c_int, c_double_p]),
+    ('computeOffDiagonalTermsArrays', c_int, [c_double_p, c_int64, c_int64_p, c_int64, c_double_p]),
+    ('icqb_gemv_dev', c_int, [c_void_p, c_uint64, c_int64, c_int64, c_int64, c_uint64, c_uint64,
+                              c_uint64, c_uint64]),
+    ('icqb_gemv_host', c_int, [c_void_p, c_uint64, c_int64, c_int64, c_int64, c_double_p,
+                               c_double_p]),
+    ('icqb_cg_solve_dev', c_int, [c_void_p, c_uint64, c_int64, c_int64, c_uint64, c_uint64,
+                                  c_uint64, c_uint64, c_double, c_int, c_int64, c_int64_p,
+                                  c_double_p, c_double_p]),
+    ('icqb_comm_unique_id', c_int, [c_void_p]),
+    ('icqb_comm_init', c_int, [c_void_p, c_void_p, c_int, c_int]),
+    ('icqb_comm_rank', c_int, [c_void_p, POINTER(c_int), POINTER(c_int)]),
+    ('icqb_last_ms', c_double, [c_void_p, c_int]),
+    ('icqb_launch_count', c_int64, [c_void_p]),
+    ('icqb_measure_fp64_peak', c_int, [c_void_p, c_double_p]),
+    ('icqQuadratureInit', None, [POINTER(c_void_p)]),
+    ('icqQuadratureSetObserver', None, [POINTER(c_void_p), c_double_p]),
+    ('icqQuadratureGetMaxOrder', c_int, [POINTER(c_void_p)]),
+    ('icqQuadratureEvaluate', c_double, [POINTER(c_void_p), c_int, c_double_p, c_double_p,
+                                         c_double_p]),
+    ('icqQuadratureEvaluateDouble', c_double, [POINTER(c_void_p), c_int] + [c_double_p] * 6),
+    ('icqQuadratureDel', None, [POINTER(c_void_p)]),
+]
+
+_lib = None
+
+
+def load():
+    """Load the CUDA library (raises RuntimeError when it has not been built)."""
+    global _lib
+    if _lib is None:
+        lib = ctypes.CDLL(getSharedLibraryName(LIB_NAME))
+        for name, restype, argtypes in SIGNATURES:
+            fn = getattr(lib, name)
+            fn.restype = restype
+            fn.argtypes = argtypes
+        _lib = lib
+    return _lib
+
+
+def check(ctx, status):
+    """Turn a status code into the exception the reference would raise:
+    KeyError for a diagonal order outside 1..5 (bem/icqQuadrature1D.py:38),
+    RuntimeError otherwise."""
+    if status == ICQB_OK:
+        return
+    msg = load().icqb_last_error(ctx)
+    msg = msg.decode() if msg else 'status {0}'.format(status)
+    if status == ICQB_EORDER:
+        raise KeyError(msg)
+    raise RuntimeError('icqb error {0}: {1}'.format(status, msg))
+
+
+class Context:
+    """Owns one ``icqb_ctx`` (one GPU, one rank)."""
+
+    def __init__(self, device=0):
+        self.lib = load()
+        self.handle = c_void_p()
+        st = self.lib.icqb_create(byref(self.handle), int(device))
+        if st != ICQB_OK:
+            msg = self.lib.icqb_last_error(None)
+            raise RuntimeError('icqb_create failed ({0}): {1}'.format(st, msg.decode() if msg else ''))
+        self.device = int(device)
+
+    def check(self, status):
+        check(self.handle, status)
+
+    def close(self):
+        if self.handle:
+            self.lib.icqb_destroy(self.handle)
+            self.handle = c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def last_ms(self, which):
+        return float(self.lib.icqb_last_ms(self.handle, int(which)))
+
+    def launch_count(self):
+        return int(self.lib.icqb_launch_count(self.handle))

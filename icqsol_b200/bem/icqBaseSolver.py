@@ -1,0 +1,188 @@
+"""Mesh intake and field plumbing shared by the BEM solvers.
+
+Same public surface as the reference's ``BaseSolver`` (bem/icqBaseSolver.py:9-157):
+constructor ``(pdata, max_edge_length, order=5)``, ``getVtkPolyData``,
+``getPoints``, ``getCells``, ``setResponseFieldName``, ``setSourceFieldName``,
+``getSourceArrayIndex``, ``getSourceArray``, ``addResponseField``,
+``setSourceFromExpression``.  ``pdata`` is duck-typed: a real ``vtkPolyData`` or
+the in-repo stand-in (icqsol_b200.mesh.polydata.PolyData).
+
+Differences, all forced by the image (no VTK, no pytriangle):
+  * polygons are split into triangles by a fan and edges longer than
+    ``max_edge_length`` by uniform per-triangle subdivision, instead of
+    RefineSurface's constrained Delaunay step (shapes/icqRefineSurface.py:46-177);
+    a mesh that is already triangulated and fine enough passes through untouched;
+  * ``getCells`` returns int64 (the reference's ``numpy.int`` no longer exists).
+"""
+import numpy
+
+from icqsol_b200.mesh import generators
+from icqsol_b200.mesh.polydata import (PolyData, DataArray, extract_mesh, new_double_array,
+                                       new_id_list)
+
+
+def _findArray(data, name):
+    # bem ... util/icqDataFetcher.py:7-21
+    for i in range(data.GetNumberOfArrays()):
+        if data.GetArray(i).GetName() == name:
+            return i
+    return -1
+
+
+class BaseSolver:
+
+    def __init__(self, pdata, max_edge_length, order=5):
+        """
+        Constructor
+        @param pdata polydata (vtkPolyData or stand-in)
+        @param max_edge_length maximum edge length, used to turn
+                               polygons into triangles
+        @param order order of the self-term integration (1..5)
+        """
+        xyz, cells = extract_mesh(pdata)
+        isTriangulated = all(len(c) == 3 for c in cells)
+        tri = generators.fanSplit(cells)
+        refXyz, refTri = generators.refineToMaxEdge(xyz, tri, max_edge_length)
+        if isTriangulated and refTri.shape[0] == tri.shape[0]:
+            self.pdata = pdata
+        else:
+            # new polydata, as RefineSurface.getVtkPolyData() hands back
+            self.pdata = PolyData.from_arrays(refXyz, refTri)
+            if refXyz.shape[0] == xyz.shape[0]:
+                src = pdata.GetPointData()
+                for i in range(src.GetNumberOfArrays()):
+                    arr = src.GetArray(i)
+                    nc = arr.GetNumberOfComponents()
+                    vals = [[arr.GetComponent(k, j) for j in range(nc)]
+                            for k in range(xyz.shape[0])]
+                    self.pdata.GetPointData().AddArray(DataArray(arr.GetName(), vals))
+            xyz, tri = self.pdata.GetPoints().as_float64(), refTri
+
+        # point ids of each cell
+        assert tri.ndim == 2 and tri.shape[1] == 3
+        self.ptIdList = tri.tolist()
+        self._xyz = numpy.ascontiguousarray(xyz, numpy.float64)
+        self._tri = numpy.ascontiguousarray(tri, numpy.int64)
+
+        self.points = self.pdata.GetPoints()
+        self.polys = self.pdata.GetPolys()
+        self.numTriangles = self.polys.GetNumberOfCells()
+        assert self.numTriangles == self._tri.shape[0]
+
+        # order of the integration, method dependent
+        self.order = order
+
+        # set in the derived classes
+        self.responseName = 'NO-SET'
+        self.sourceName = 'NOT-SET'
+
+    def getVtkPolyData(self):
+        """
+        Get the (modified) polydata object
+        @return object
+        """
+        return self.pdata
+
+    def getPoints(self):
+        """
+        Get grid points
+        @return float64[numPoints, 3]
+        """
+        return self._xyz.copy()
+
+    def getCells(self):
+        """
+        Get cell connectivity
+        @return int64[numTriangles, 3]
+        """
+        return self._tri.copy()
+
+    def setResponseFieldName(self, name):
+        self.responseName = name
+
+    def setSourceFieldName(self, name):
+        self.sourceName = name
+
+    def getSourceArrayIndex(self):
+        """
+        Index of the source cell array; a point array of that name is first
+        projected onto the cells by averaging the three vertex values
+        (util/icqDataFetcher.py:23-62).
+        """
+        cellData = self.pdata.GetCellData()
+        srcIndex = _findArray(cellData, self.sourceName)
+        if srcIndex < 0:
+            pointData = self.pdata.GetPointData()
+            index2 = _findArray(pointData, self.sourceName)
+            if index2 >= 0:
+                pointArr = pointData.GetArray(index2)
+                cellArr = new_double_array(self.pdata)
+                cellArr.SetName(self.sourceName)
+                cellArr.SetNumberOfComponents(1)
+                cellArr.SetNumberOfTuples(self.numTriangles)
+                for i, (ia, ib, ic) in enumerate(self.ptIdList):
+                    va = pointArr.GetComponent(ia, 0)
+                    vb = pointArr.GetComponent(ib, 0)
+                    vc = pointArr.GetComponent(ic, 0)
+                    cellArr.SetComponent(i, 0, (va + vb + vc) / 3.)
+                cellData.AddArray(cellArr)
+                srcIndex = _findArray(cellData, self.sourceName)
+        if srcIndex < 0:
+            msg = 'ERROR: could not find any cell field named {0}!'.format(self.sourceName)
+            raise RuntimeError(msg)
+        return srcIndex
+
+    def getSourceArray(self, srcIndex):
+        """
+        Source values, one per triangle
+        @param srcIndex source array index
+        @return float64[numTriangles]
+        """
+        srcArray = self.pdata.GetCellData().GetArray(srcIndex)
+        n = self.pdata.GetNumberOfPolys()
+        if hasattr(srcArray, 'as_numpy'):
+            return srcArray.as_numpy()[:n, 0].astype(numpy.float64)
+        src = numpy.zeros((n,), numpy.float64)
+        for i in range(n):
+            src[i] = srcArray.GetComponent(i, 0)
+        return src
+
+    def addResponseField(self, rsp):
+        """
+        Attach the response to the polydata as a named cell array
+        @param rsp response numpy array
+        """
+        n = len(rsp)
+        rspData = new_double_array(self.pdata)
+        rspData.SetNumberOfComponents(1)
+        rspData.SetNumberOfTuples(n)
+        rspData.SetName(self.responseName)
+        if hasattr(rspData, 'as_numpy'):
+            rspData.as_numpy()[:, 0] = rsp
+        else:
+            for i in range(n):
+                rspData.SetTuple(i, [rsp[i]])
+        self.pdata.GetCellData().AddArray(rspData)
+
+    def setSourceFromExpression(self, expression):
+        """
+        Set the source from expression, evaluated at each triangle's centroid
+        @param expression expression of x, y, and z
+        """
+        from math import sqrt, pi, sin, cos, tan, log, exp  # noqa: F401 (names for eval)
+
+        n = self.pdata.GetNumberOfPolys()
+        sourceData = new_double_array(self.pdata)
+        sourceData.SetNumberOfComponents(1)
+        sourceData.SetNumberOfTuples(n)
+        sourceData.SetName(self.sourceName)
+        a, b, c = (self._xyz[self._tri[:, k]] for k in range(3))
+        mid = a.copy()
+        mid += b
+        mid += c
+        mid /= 3.0
+        for i in range(n):
+            x, y, z = mid[i]
+            v = eval(expression)
+            sourceData.SetTuple(i, [v])
+        self.pdata.GetCellData().AddArray(sourceData)

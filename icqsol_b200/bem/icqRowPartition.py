@@ -1,0 +1,96 @@
+"""Row-block partition of the dense matrices over the ranks of one box, and the
+few host-side collectives the solvers need around the CUDA library
+(SURVEY.md section 8e).  The reference is single-process; this is new.
+
+torch.distributed is plumbing only: it carries the NCCL unique id to the ranks
+(the library then talks NCCL itself) and gathers result vectors.  Works with
+the ``nccl`` backend on GPUs and with ``gloo`` on CPU (tests).
+"""
+import numpy
+
+
+def worldInfo():
+    """(rank, world_size) of the default process group, (0, 1) without one."""
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank(), dist.get_world_size()
+    except ImportError:
+        pass
+    return 0, 1
+
+
+def rowChunk(n, nranks):
+    """Rows per rank: ceil(n / nranks) (the slot size of the all-gathered vectors)."""
+    return (int(n) + int(nranks) - 1) // int(nranks)
+
+
+def rowRange(n, rank, nranks):
+    """Observer rows [r0, r1) owned by ``rank``: consecutive blocks of
+    ceil(n/nranks) rows; trailing ranks may own fewer (or no) rows.  Must match
+    the partition icqb_cg_solve_dev assumes."""
+    chunk = rowChunk(n, nranks)
+    r0 = min(int(n), int(rank) * chunk)
+    r1 = min(int(n), r0 + chunk)
+    return r0, r1
+
+
+def _backendDevice():
+    import torch
+    import torch.distributed as dist
+    if dist.get_backend() == 'nccl':
+        return torch.device('cuda', torch.cuda.current_device())
+    return torch.device('cpu')
+
+
+def broadcastBytes(payload, nbytes, src=0):
+    """Broadcast ``nbytes`` bytes (a bytes object on ``src``, ignored elsewhere)."""
+    rank, nranks = worldInfo()
+    if nranks == 1:
+        return bytes(payload)
+    import torch
+    import torch.distributed as dist
+    if rank == src:
+        buf = torch.tensor(list(bytes(payload)), dtype=torch.uint8)
+    else:
+        buf = torch.zeros(nbytes, dtype=torch.uint8)
+    buf = buf.to(_backendDevice())
+    dist.broadcast(buf, src=src)
+    return bytes(buf.cpu().numpy().tobytes())
+
+
+def allGatherRows(local, n):
+    """Concatenate the per-rank row slices (numpy float64[m_rank]) into float64[n]."""
+    rank, nranks = worldInfo()
+    local = numpy.ascontiguousarray(local, numpy.float64)
+    if nranks == 1:
+        return local.copy()
+    import torch
+    import torch.distributed as dist
+    chunk = rowChunk(n, nranks)
+    dev = _backendDevice()
+    send = torch.zeros(chunk, dtype=torch.float64)
+    send[:local.shape[0]] = torch.from_numpy(local)
+    send = send.to(dev)
+    recv = torch.empty(chunk * nranks, dtype=torch.float64, device=dev)
+    dist.all_gather_into_tensor(recv, send)
+    return recv.cpu().numpy()[:n].copy()
+
+
+def allGatherMatrixRows(localRows, n):
+    """Gather row blocks float64[m_rank, ncols] into float64[n, ncols] on every rank."""
+    rank, nranks = worldInfo()
+    localRows = numpy.ascontiguousarray(localRows, numpy.float64)
+    if nranks == 1:
+        return localRows
+    import torch
+    import torch.distributed as dist
+    chunk = rowChunk(n, nranks)
+    ncols = localRows.shape[1]
+    dev = _backendDevice()
+    send = torch.zeros((chunk, ncols), dtype=torch.float64)
+    send[:localRows.shape[0]] = torch.from_numpy(localRows)
+    send = send.to(dev)
+    recv = torch.empty((chunk * nranks, ncols), dtype=torch.float64, device=dev)
+    dist.all_gather_into_tensor(recv, send)
+    return recv.cpu().numpy()[:n].copy()

@@ -1,0 +1,150 @@
+// NCCL plumbing for the row-sharded solve: the CG iterate is all-gathered and the
+// dot products all-reduced (the reference has no multi-process code at all;
+// SURVEY.md section 8e).  NCCL is bound at run time with dlopen so that the library
+// resolves to the libnccl the host process already carries (PyTorch's bundled
+// 2.28.9 when driven from the Python layer) and has no link-time dependency.
+#include <dlfcn.h>
+#include <string.h>
+
+#include "icqb_internal.cuh"
+
+namespace icqb {
+
+namespace {
+
+// the slice of the NCCL ABI used here (stable since NCCL 2.0)
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef int ncclResult_t;
+constexpr int ncclFloat64 = 8;
+constexpr int ncclSum = 0;
+
+struct Api {
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    std::string error;
+};
+
+Api& api() {
+    static Api a;
+    if (a.handle || !a.error.empty()) return a;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+        a.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (a.handle) break;
+    }
+    if (!a.handle) {
+        a.error = std::string("cannot load libnccl: ") + dlerror();
+        return a;
+    }
+#define ICQB_SYM(field, name)                                              \
+    a.field = reinterpret_cast<decltype(a.field)>(dlsym(a.handle, name)); \
+    if (!a.field) a.error = std::string("libnccl lacks ") + name;
+    ICQB_SYM(GetUniqueId, "ncclGetUniqueId")
+    ICQB_SYM(CommInitRank, "ncclCommInitRank")
+    ICQB_SYM(CommDestroy, "ncclCommDestroy")
+    ICQB_SYM(AllGather, "ncclAllGather")
+    ICQB_SYM(AllReduce, "ncclAllReduce")
+    ICQB_SYM(GetErrorString, "ncclGetErrorString")
+#undef ICQB_SYM
+    return a;
+}
+
+}  // namespace
+
+struct Comm {
+    ncclComm_t comm = nullptr;
+    int rank = 0, nranks = 1;
+};
+
+int comm_nranks(const icqb_ctx* ctx) { return ctx->comm ? ctx->comm->nranks : 1; }
+int comm_rank(const icqb_ctx* ctx) { return ctx->comm ? ctx->comm->rank : 0; }
+
+static int nccl_check(icqb_ctx* ctx, ncclResult_t r, const char* what) {
+    if (r == 0) return ICQB_OK;
+    return set_error(ctx, ICQB_ECOMM, std::string(what) + ": " + api().GetErrorString(r));
+}
+
+int comm_allgather(icqb_ctx* ctx, const double* send, double* recv, int64_t count_per_rank,
+                   cudaStream_t stream) {
+    if (comm_nranks(ctx) == 1) {
+        if (send != recv)
+            return check_cuda(ctx,
+                              cudaMemcpyAsync(recv, send, sizeof(double) * count_per_rank,
+                                              cudaMemcpyDeviceToDevice, stream),
+                              "allgather(self)");
+        return ICQB_OK;
+    }
+    return nccl_check(ctx,
+                      api().AllGather(send, recv, (size_t)count_per_rank, ncclFloat64,
+                                      ctx->comm->comm, stream),
+                      "ncclAllGather");
+}
+
+int comm_allreduce_sum(icqb_ctx* ctx, double* buf, int64_t count, cudaStream_t stream) {
+    if (comm_nranks(ctx) == 1) return ICQB_OK;
+    return nccl_check(ctx,
+                      api().AllReduce(buf, buf, (size_t)count, ncclFloat64, ncclSum,
+                                      ctx->comm->comm, stream),
+                      "ncclAllReduce");
+}
+
+void comm_destroy(icqb_ctx* ctx) {
+    if (!ctx->comm) return;
+    if (ctx->comm->comm) api().CommDestroy(ctx->comm->comm);
+    delete ctx->comm;
+    ctx->comm = nullptr;
+}
+
+}  // namespace icqb
+
+using namespace icqb;
+
+extern "C" {
+
+int icqb_comm_unique_id(void* unique_id_128) {
+    if (!unique_id_128) return ICQB_EARG;
+    Api& a = api();
+    if (!a.error.empty()) return set_error(nullptr, ICQB_ECOMM, a.error);
+    ncclUniqueId id;
+    ncclResult_t r = a.GetUniqueId(&id);
+    if (r != 0) return set_error(nullptr, ICQB_ECOMM, std::string("ncclGetUniqueId: ") + a.GetErrorString(r));
+    memcpy(unique_id_128, &id, sizeof(id));
+    return ICQB_OK;
+}
+
+int icqb_comm_init(icqb_ctx* ctx, const void* unique_id_128, int rank, int nranks) {
+    if (!ctx || !unique_id_128 || nranks < 1 || rank < 0 || rank >= nranks)
+        return set_error(ctx, ICQB_EARG, "icqb_comm_init: bad arguments");
+    comm_destroy(ctx);
+    if (nranks == 1) return ICQB_OK;
+    Api& a = api();
+    if (!a.error.empty()) return set_error(ctx, ICQB_ECOMM, a.error);
+    ICQB_CUDA(ctx, cudaSetDevice(ctx->device));
+    ncclUniqueId id;
+    memcpy(&id, unique_id_128, sizeof(id));
+    Comm* c = new Comm();
+    c->rank = rank;
+    c->nranks = nranks;
+    ncclResult_t r = a.CommInitRank(&c->comm, nranks, id, rank);
+    if (r != 0) {
+        delete c;
+        return set_error(ctx, ICQB_ECOMM, std::string("ncclCommInitRank: ") + a.GetErrorString(r));
+    }
+    ctx->comm = c;
+    return ICQB_OK;
+}
+
+int icqb_comm_rank(const icqb_ctx* ctx, int* rank, int* nranks) {
+    if (!ctx) return ICQB_EARG;
+    if (rank) *rank = comm_rank(ctx);
+    if (nranks) *nranks = comm_nranks(ctx);
+    return ICQB_OK;
+}
+
+}  // extern "C"

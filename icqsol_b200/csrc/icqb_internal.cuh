@@ -1,0 +1,83 @@
+// Internal declarations shared by the translation units of
+// libicqLaplaceMatricesB200.so.  The public surface is include/icqb.h.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/icqb.h"
+
+namespace icqb {
+
+constexpr int kNq = 16;          // nodes of the order-8 triangle rule
+constexpr int kQpStride = 48;    // doubles per triangle in the quadrature-point tables
+constexpr int kPad = 128;        // triangle count is padded to a multiple of this
+
+// phases for icqb_last_ms
+enum Phase { kPrepare = 0, kOffDiag = 1, kDiag = 2, kGemv = 3, kCg = 4, kNumPhases = 5 };
+
+struct Comm;  // NCCL state, comm.cu
+
+}  // namespace icqb
+
+struct icqb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;      // stream in use
+    cudaStream_t own_stream = nullptr;  // created with the context
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int num_sms = 0;
+
+    int64_t npts = 0, ntri = 0, ntri_pad = 0;
+    int64_t r0 = 0, r1 = 0;
+
+    // mesh and per-triangle tables (device)
+    double* d_xyz = nullptr;     // [npts][3]
+    int64_t* d_tri = nullptr;    // [ntri][3]
+    double* d_verts = nullptr;   // [ntri][9]  gathered vertices a,b,c
+    double* d_qp_soa = nullptr;  // [48][ntri_pad]   component-major: observer side
+    double* d_qp_aos = nullptr;  // [ntri_pad][48]   triangle-major: source side (bulk-copied tiles)
+    double* d_area2 = nullptr;   // [ntri_pad]  |db x dc|
+    double* d_nrm = nullptr;     // [ntri_pad][4]  unit normal, n . pa
+
+    // CG work space (device), sized on demand
+    double* d_work = nullptr;
+    int64_t work_doubles = 0;
+    double* h_pinned = nullptr;  // small pinned scratch for scalar read-back
+
+    icqb::Comm* comm = nullptr;
+
+    double last_ms[icqb::kNumPhases] = {0, 0, 0, 0, 0};
+    int64_t launches = 0;
+    std::string err;
+};
+
+namespace icqb {
+
+int set_error(icqb_ctx* ctx, int code, const std::string& msg);
+int check_cuda(icqb_ctx* ctx, cudaError_t e, const char* what);
+int ensure_work(icqb_ctx* ctx, int64_t doubles);
+
+// kernels' host launchers (each returns ICQB_OK or sets the context error)
+int launch_prepare(icqb_ctx* ctx);
+int launch_offdiag(icqb_ctx* ctx, double* dG, double* dK, int64_t ld);
+int launch_diag(icqb_ctx* ctx, int order, double* dOut, int64_t stride);
+int launch_gemv(icqb_ctx* ctx, const double* dA, int64_t nrows, int64_t ncols, int64_t ld,
+                const double* dx, double* dy, const double* drowscale, cudaStream_t stream);
+
+// NCCL plumbing (comm.cu); all no-ops for a single rank
+int comm_nranks(const icqb_ctx* ctx);
+int comm_rank(const icqb_ctx* ctx);
+int comm_allgather(icqb_ctx* ctx, const double* send, double* recv, int64_t count_per_rank,
+                   cudaStream_t stream);
+int comm_allreduce_sum(icqb_ctx* ctx, double* buf, int64_t count, cudaStream_t stream);
+void comm_destroy(icqb_ctx* ctx);
+
+}  // namespace icqb
+
+#define ICQB_CUDA(ctx, call)                                              \
+    do {                                                                  \
+        int _st = icqb::check_cuda((ctx), (call), #call);                 \
+        if (_st != ICQB_OK) return _st;                                   \
+    } while (0)

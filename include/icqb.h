@@ -1,0 +1,169 @@
+/*
+ * icqb.h -- C ABI of libicqLaplaceMatricesB200.so, the B200 (sm_100a) replacement
+ * for icqsol's boundary-element hot path.
+ *
+ * The reference's FFI for this path is the ctypes binding in
+ * bem/icqBaseLaplaceSolver.py:26-27,68-72 onto
+ *     void computeOffDiagonalTerms(vtkPolyData*, double* gMat)   bem/icqLaplaceMatrices.h:6-7
+ * plus the quadrature handle API of bem/icqQuadrature.h:19-40.  A vtkPolyData*
+ * cannot cross a VTK-free ABI, so the mesh crosses as plain arrays
+ * (points double[npts][3], triangles int64[ntri][3]); everything else is plain
+ * pointers and sizes.  Device pointers are passed as uint64_t (what
+ * torch.Tensor.data_ptr() / cudaMalloc return); streams as uint64_t
+ * (cudaStream_t; 0 = the context's own stream).
+ *
+ * Conventions copied from the reference:
+ *   - G is row-major, G[N*obs + src]; "area" = |db x dc| = twice the area;
+ *   - off-diagonal entries always use the 16-point (order 8) triangle rule
+ *     (bem/icqLaplaceMatrices.cpp:42,94); `diag_order` (1..5) only drives the
+ *     self term (bem/icqBaseLaplaceSolver.py:34-66);
+ *   - no guards against coincident / zero-area triangles: inf/nan propagate.
+ *
+ * Every function returns ICQB_OK (0) or a negative status; the message is
+ * available from icqb_last_error().  There is no CPU fallback: without a
+ * usable CUDA device icqb_create fails.
+ */
+#ifndef ICQB_H
+#define ICQB_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ICQB_OK 0
+#define ICQB_ECUDA (-1)    /* CUDA runtime error                                  */
+#define ICQB_EARG (-2)     /* bad argument                                        */
+#define ICQB_EORDER (-3)   /* diagonal order outside 1..5 (reference: KeyError,   */
+                           /* bem/icqQuadrature1D.py:38)                          */
+#define ICQB_ESTATE (-4)   /* call sequence error (no mesh, no matrix ...)        */
+#define ICQB_ECOMM (-5)    /* NCCL error / NCCL not loadable                      */
+
+typedef struct icqb_ctx icqb_ctx;
+
+/* ---- context ---------------------------------------------------------------
+ * One context per process and GPU (one rank).  Owns the mesh copy, the
+ * quadrature-point tables, CG work vectors and (optionally) the NCCL
+ * communicator.  Replaces the icqQuadratureInit/Del pair wrapped around the
+ * assembly at bem/icqLaplaceMatrices.cpp:40-41,103. */
+int icqb_create(icqb_ctx** ctx, int device);
+int icqb_destroy(icqb_ctx* ctx);
+const char* icqb_last_error(const icqb_ctx* ctx); /* ctx may be NULL: last create error */
+int icqb_device(const icqb_ctx* ctx);
+uint64_t icqb_stream(const icqb_ctx* ctx);
+/* Run all subsequent work of this context on the caller's stream (a cudaStream_t,
+ * e.g. torch.cuda.current_stream().cuda_stream); 0 restores the context's own. */
+int icqb_set_stream(icqb_ctx* ctx, uint64_t stream);
+int icqb_synchronize(icqb_ctx* ctx);
+
+/* ---- mesh ------------------------------------------------------------------
+ * Host arrays, copied.  Replaces the vtkPoints/vtkCellArray traversal at
+ * bem/icqLaplaceMatrices.cpp:54-71 (connectivity) and :81-91 (GetPoint).
+ * Also precomputes, per triangle, the 16 order-8 quadrature points with the
+ * reference's rounding (pa + xi*db + eta*dc, bem/icqQuadrature.cpp:233-239),
+ * |db x dc| and the unit normal. */
+int icqb_set_mesh(icqb_ctx* ctx, const double* xyz, int64_t npts, const int64_t* tri,
+                  int64_t ntri);
+int64_t icqb_num_triangles(const icqb_ctx* ctx);
+/* observer rows [r0, r1) this context assembles / multiplies (default: all). */
+int icqb_set_rows(icqb_ctx* ctx, int64_t r0, int64_t r1);
+int icqb_get_rows(const icqb_ctx* ctx, int64_t* r0, int64_t* r1);
+/* |db x dc| of every triangle (device pointer, double[ntri]). */
+uint64_t icqb_area2_dev(const icqb_ctx* ctx);
+
+/* ---- assembly ----------------------------------------------------------------
+ * Fills rows [r0, r1) of G -- and of K when dK != 0 -- into caller-owned device
+ * buffers: dG[(r - r0)*ld + c], c in [0, ntri), ld >= ntri.
+ *   off-diagonal: bem/icqLaplaceMatrices.cpp:75-101 + bem/icqQuadrature.cpp:208-246
+ *                 + bem/icqLaplaceFunctor.cpp:4-10, one fused kernel;
+ *   diagonal:     bem/icqBaseLaplaceSolver.py:34-66 (+ icqPotentialIntegrals.py,
+ *                 icqReferenceTriangle.py, icqQuadrature1D.py), `diag_order` in 1..5;
+ *                 diag_order == 0 leaves the diagonal untouched (the contract of
+ *                 computeOffDiagonalTerms itself).
+ * K is the double-layer matrix (NOT in the reference snapshot; definition in
+ * DESIGN.md); K[i,i] = 0.  Asynchronous on the context stream. */
+int icqb_assemble_dev(icqb_ctx* ctx, int diag_order, uint64_t dG, uint64_t dK, int64_t ld);
+
+/* Host-buffer forms (blocking; host<->device copies inside the call).
+ * gMat/kMat: row-major double[(r1-r0)*ntri]; kMat may be NULL. */
+int icqb_assemble_host(icqb_ctx* ctx, int diag_order, double* gMat, double* kMat);
+/* self terms only: double[r1-r0] (bem/icqBaseLaplaceSolver.py:34-66). */
+int icqb_diagonal_host(icqb_ctx* ctx, int diag_order, double* diag);
+
+/* Drop-in for computeOffDiagonalTerms (bem/icqLaplaceMatrices.h:6-7) with the
+ * polydata replaced by arrays: fills the off-diagonal of the caller's row-major
+ * ntri x ntri host matrix and leaves its diagonal untouched.  Returns status
+ * (the reference returns void). */
+int computeOffDiagonalTermsArrays(const double* xyz, int64_t npts, const int64_t* tri,
+                                  int64_t ntri, double* gMat);
+
+/* ---- dense apply / solve ---------------------------------------------------------
+ * y = A x for a row-major device matrix (numpy.dot at bem/icqPoissonSolver.py:36,
+ * solvers/icqConjugateGradient.py:57,66,74).  If drowscale != 0, y[i] *= rowscale[i].
+ * Bandwidth-bound streaming kernel; asynchronous on `stream`. */
+int icqb_gemv_dev(icqb_ctx* ctx, uint64_t dA, int64_t nrows, int64_t ncols, int64_t ld,
+                  uint64_t dx, uint64_t dy, uint64_t drowscale, uint64_t stream);
+/* Host-vector form on a device matrix: x double[ncols] -> y double[nrows]. */
+int icqb_gemv_host(icqb_ctx* ctx, uint64_t dA, int64_t nrows, int64_t ncols, int64_t ld,
+                   const double* x, double* y);
+
+/* Jacobi-preconditioned conjugate gradient (solvers/icqConjugateGradient.py:49-79)
+ * on the system  diag(rowscale) A x = diag(rowscale) b.
+ *   dA       rows [r0, r1) of the n x n matrix, row-major, leading dimension ld;
+ *   drowscale double[r1-r0] or 0 (no scaling: plain CG on A, as the reference class);
+ *            for the Green matrix pass the local slice of icqb_area2_dev(): G is not
+ *            symmetric (G[j,i] = G[i,j] A_i/A_j, bem/icqLaplaceMatrices.cpp:97-98)
+ *            but diag(area) G is;
+ *   dprecond double[r1-r0] diagonal preconditioner of the UNSCALED matrix
+ *            (icqConjugateGradient.py:19) or 0 = use diag(A);
+ *   db, dx   local slices double[r1-r0]; dx holds x0 on entry, the solution on exit;
+ *   tol      stop when ||b - A x||_2 <= tol (absolute, :64) ; if rel != 0 the
+ *            threshold is tol*||b||_2;
+ *   maxit    iteration cap (:16 defaults to n);
+ *   outputs  iters, final true residual ||b - A x||_2 and max norm.
+ * With nranks > 1 (icqb_comm_init) the iterate is all-gathered and the dot
+ * products all-reduced over NCCL. Blocking. */
+int icqb_cg_solve_dev(icqb_ctx* ctx, uint64_t dA, int64_t n, int64_t ld, uint64_t drowscale,
+                      uint64_t dprecond, uint64_t db, uint64_t dx, double tol, int rel,
+                      int64_t maxit, int64_t* iters, double* resid2, double* residinf);
+
+/* ---- multi-GPU plumbing -----------------------------------------------------------
+ * One rank per process.  `unique_id` is the 128-byte ncclUniqueId produced by
+ * icqb_comm_unique_id on rank 0 and broadcast by the caller (torch.distributed
+ * in the Python host layer). */
+int icqb_comm_unique_id(void* unique_id_128);
+int icqb_comm_init(icqb_ctx* ctx, const void* unique_id_128, int rank, int nranks);
+int icqb_comm_rank(const icqb_ctx* ctx, int* rank, int* nranks);
+
+/* ---- instrumentation ----------------------------------------------------------------
+ * Milliseconds (CUDA events on the context stream) of the last call of each phase:
+ * which = 0 prepare, 1 off-diagonal, 2 diagonal, 3 last gemv, 4 last cg solve;
+ * icqb_launch_count: kernels launched by this context since creation. */
+double icqb_last_ms(const icqb_ctx* ctx, int which);
+int64_t icqb_launch_count(const icqb_ctx* ctx);
+/* Sustained FP64 FMA rate of the device, TFLOP/s (register-resident DFMA loop):
+ * the measured denominator of the assembly roofline. */
+int icqb_measure_fp64_peak(icqb_ctx* ctx, double* tflops);
+
+/* ---- quadrature handle API (bem/icqQuadrature.h:19-40) --------------------------------
+ * Same names, argument order and meaning as the reference; each Evaluate call
+ * runs the device code on one CUDA block so that testQuadratureCpp-style
+ * known-answer tests exercise the GPU arithmetic.  icqQuadratureSetFunctor takes
+ * a C++ object in the reference and is not reproducible across a C ABI: omitted
+ * (the functor is always the Laplace kernel of bem/icqLaplaceFunctor.cpp:4-10). */
+typedef struct icqQuadratureType icqQuadratureType;
+void icqQuadratureInit(icqQuadratureType** self);
+void icqQuadratureSetObserver(icqQuadratureType** self, const double* pObs);
+int icqQuadratureGetMaxOrder(icqQuadratureType** self);
+double icqQuadratureEvaluate(icqQuadratureType** self, int order, const double* pa,
+                             const double* pb, const double* pc);
+double icqQuadratureEvaluateDouble(icqQuadratureType** self, int order, const double* pa0,
+                                   const double* pb0, const double* pc0, const double* pa1,
+                                   const double* pb1, const double* pc1);
+void icqQuadratureDel(icqQuadratureType** self);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ICQB_H */

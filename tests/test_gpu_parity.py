@@ -1,0 +1,395 @@
+"""Parity of the CUDA path against the oracle (CPU restatement of the reference)
+and the committed golden vectors (outputs of the reference's own code).
+All calls go through the C ABI (ctypes) or the Python classes on top of it.
+
+Tolerances: north_star demands 1e-12 relative for every G entry and for GEMV
+outputs in fp64; solution vectors are checked by backward error <= 1e-12 and
+forward difference vs LU <= 50*cond(G)*eps.
+"""
+import ctypes
+
+import numpy
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TOL_ENTRY = 1e-12
+EPS = numpy.finfo(numpy.float64).eps
+
+
+def dp(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+
+
+def lp(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_int64))
+
+
+@pytest.fixture()
+def ctx(gpu_lib):
+    from icqsol_b200 import _lib
+    c = _lib.Context(0)
+    yield c
+    c.close()
+
+
+def assemble(ctx, xyz, tri, order=5, with_k=False, rows=None):
+    xyz = numpy.ascontiguousarray(xyz, numpy.float64)
+    tri = numpy.ascontiguousarray(tri, numpy.int64)
+    n = tri.shape[0]
+    ctx.check(ctx.lib.icqb_set_mesh(ctx.handle, dp(xyz), xyz.shape[0], lp(tri), n))
+    r0, r1 = (0, n) if rows is None else rows
+    ctx.check(ctx.lib.icqb_set_rows(ctx.handle, r0, r1))
+    g = numpy.full((r1 - r0, n), numpy.nan)
+    k = numpy.full((r1 - r0, n), numpy.nan) if with_k else None
+    ctx.check(ctx.lib.icqb_assemble_host(ctx.handle, order, dp(g), dp(k) if with_k else None))
+    return (g, k) if with_k else g
+
+
+def relerr(a, b):
+    return numpy.abs(a - b).max() / numpy.abs(b).max() if b.size else 0.0
+
+
+def max_entry_relerr(a, b):
+    return numpy.abs(a / b - 1.0).max()
+
+
+# ---- G: golden vectors produced by the reference's own C++ and Python ------------------
+
+@pytest.mark.parametrize('name', ['twotri', 'tet', 'sphere4x2', 'createSphere', 'square'])
+@pytest.mark.parametrize('order', [1, 2, 3, 4, 5])
+def test_green_small_golden(ctx, golden, name, order):
+    xyz, tri = golden.mesh(name)
+    g = assemble(ctx, xyz, tri, order)
+    ref = golden['green_small'][name + '_offdiag'].copy()
+    ref[numpy.diag_indices_from(ref)] = golden['green_small']['%s_diag%d' % (name, order)]
+    assert max_entry_relerr(g, ref) < TOL_ENTRY
+
+
+def test_survey_known_values(ctx, golden):
+    """Values printed in SURVEY.md section 8c (run of the reference during the survey)."""
+    g = assemble(ctx, *golden.mesh('twotri'), 5)
+    assert abs(g[0, 0] / -0.15959645874363654 - 1) < TOL_ENTRY
+    assert abs(g[1, 0] / -0.03637297439435873 - 1) < TOL_ENTRY
+    g = assemble(ctx, *golden.mesh('tet'), 5)
+    assert abs(g[0, 1] / -0.08250452568311496 - 1) < TOL_ENTRY
+    assert abs(g[0, 3] / -0.16292331240300845 - 1) < TOL_ENTRY
+    assert abs(g[3, 0] / -0.09406381827314243 - 1) < TOL_ENTRY
+    assert abs(g[3, 3] / -0.21436428380303485 - 1) < TOL_ENTRY
+    g = assemble(ctx, *golden.mesh('square'), 5)
+    assert abs(g[1, 0] / -0.08186618508970281 - 1) < TOL_ENTRY
+
+
+@pytest.mark.parametrize('name', ['sphere', 'boltFine'])
+def test_green_real_meshes_golden(ctx, golden, name):
+    """data/sphere.vtk (960 triangles after the fan split) and
+    test_results/testBoltFine.vtk (2350 triangles, areas spanning 1500x)."""
+    xyz, tri = golden.mesh(name)
+    g = assemble(ctx, xyz, tri, 5)
+    big = golden['green_sampled']
+    rows = big[name + '_rows']
+    assert max_entry_relerr(g[rows, :], big[name + '_G_rows']) < TOL_ENTRY
+    assert max_entry_relerr(g[:, rows], big[name + '_G_cols']) < TOL_ENTRY
+    assert max_entry_relerr(numpy.diag(g), big[name + '_diag5']) < TOL_ENTRY
+    assert max_entry_relerr(g.sum(axis=1), big[name + '_rowsum']) < TOL_ENTRY
+    assert max_entry_relerr(g.sum(axis=0), big[name + '_colsum']) < TOL_ENTRY
+
+
+def test_green_vs_oracle_every_entry(ctx, golden, oracle_mod):
+    xyz, tri = golden.mesh('boltFine')
+    g = assemble(ctx, xyz, tri, 5)
+    ref = oracle_mod.green_matrix(xyz, tri, 5, threads=True)
+    assert max_entry_relerr(g, ref) < TOL_ENTRY
+
+
+@pytest.mark.parametrize('n_theta,n_phi', [(5, 3), (16, 9), (33, 17), (64, 30)])
+def test_green_uv_spheres_vs_oracle(ctx, oracle_mod, n_theta, n_phi):
+    """Sizes around the 128-triangle tile boundary: 20, 256, 1056, 3712 triangles."""
+    from icqsol_b200.mesh.generators import uvSphere
+    xyz, tri = uvSphere(1.0, n_theta, n_phi)
+    g = assemble(ctx, xyz, tri, 5)
+    ref = oracle_mod.green_matrix(xyz, tri, 5, threads=True)
+    assert max_entry_relerr(g, ref) < TOL_ENTRY
+
+
+@pytest.mark.parametrize('n', [1, 2, 127, 128, 129, 255, 257])
+def test_green_ragged_sizes(ctx, golden, oracle_mod, n):
+    xyz, tri = golden.mesh('boltFine')
+    tri = tri[500:500 + n]
+    g = assemble(ctx, xyz, tri, 3)
+    ref = oracle_mod.green_matrix(xyz, tri, 3)
+    assert max_entry_relerr(g, ref) < TOL_ENTRY
+
+
+def test_empty_mesh(ctx):
+    xyz = numpy.zeros((0, 3))
+    tri = numpy.zeros((0, 3), numpy.int64)
+    ctx.check(ctx.lib.icqb_set_mesh(ctx.handle, dp(xyz), 0, lp(tri), 0))
+    assert ctx.lib.icqb_num_triangles(ctx.handle) == 0
+    ctx.check(ctx.lib.icqb_assemble_host(ctx.handle, 5, dp(numpy.zeros(1)), None))
+
+
+def test_bad_vertex_index_rejected(ctx):
+    xyz = numpy.zeros((3, 3))
+    tri = numpy.array([[0, 1, 3]], numpy.int64)
+    st = ctx.lib.icqb_set_mesh(ctx.handle, dp(xyz), 3, lp(tri), 1)
+    assert st == -2
+    with pytest.raises(RuntimeError):
+        ctx.check(st)
+
+
+@pytest.mark.parametrize('order', [0 + 6, 7, 8, -1])
+def test_diag_order_out_of_range_is_keyerror(ctx, golden, order):
+    """bem/icqQuadrature1D.py:38 raises KeyError for order > 5 (tests/testLaplace.py:30)."""
+    xyz, tri = golden.mesh('tet')
+    with pytest.raises(KeyError):
+        assemble(ctx, xyz, tri, order)
+
+
+def test_offdiag_dropin_keeps_diagonal(gpu_lib, golden):
+    """computeOffDiagonalTermsArrays: the contract of computeOffDiagonalTerms
+    (bem/icqLaplaceMatrices.cpp:37-105) -- off-diagonal filled, diagonal untouched."""
+    xyz, tri = golden.mesh('createSphere')
+    n = tri.shape[0]
+    g = numpy.zeros((n, n))
+    g[numpy.diag_indices(n)] = 7.25
+    st = gpu_lib.computeOffDiagonalTermsArrays(dp(numpy.ascontiguousarray(xyz)), xyz.shape[0],
+                                               lp(numpy.ascontiguousarray(tri)), n, dp(g))
+    assert st == 0
+    ref = golden['green_small']['createSphere_offdiag']
+    mask = ~numpy.eye(n, dtype=bool)
+    assert (numpy.diag(g) == 7.25).all()
+    assert numpy.abs(g[mask] / ref[mask] - 1).max() < TOL_ENTRY
+
+
+def test_mirror_rule(ctx, golden):
+    """G[j,i] = G[i,j] * A_i / A_j (bem/icqLaplaceMatrices.cpp:97-98)."""
+    xyz, tri = golden.mesh('boltFine')
+    g = assemble(ctx, xyz, tri, 5)
+    a, b, c = xyz[tri[:, 0]], xyz[tri[:, 1]], xyz[tri[:, 2]]
+    area = numpy.linalg.norm(numpy.cross(b - a, c - a), axis=1)
+    s = area[:, None] * g
+    off = ~numpy.eye(len(tri), dtype=bool)
+    assert numpy.abs(s - s.T)[off].max() / numpy.abs(s).max() < 1e-14
+
+
+def test_row_block_assembly_matches_full(ctx, golden):
+    """Row-sharded assembly (what each rank does) reproduces the full matrix."""
+    xyz, tri = golden.mesh('sphere')
+    n = tri.shape[0]
+    full = assemble(ctx, xyz, tri, 5)
+    for (r0, r1) in [(0, 240), (240, 480), (480, 961 - 1), (100, 101), (130, 389), (960, 960)]:
+        part = assemble(ctx, xyz, tri, 5, rows=(r0, r1))
+        assert part.shape == (r1 - r0, n)
+        if r1 > r0:
+            assert max_entry_relerr(part, full[r0:r1]) < 1e-14
+
+
+# ---- K (double layer; not in the reference: parity unpinned, oracle = definition) ----
+
+def test_k_matches_definition_oracle(ctx, golden, oracle_mod):
+    xyz, tri = golden.mesh('createSphere')
+    n = tri.shape[0]
+    g, k = assemble(ctx, xyz, tri, 5, with_k=True)
+    ref = oracle_mod.k_block(xyz, tri, 0, n, 0, n)
+    assert numpy.abs(k - ref).max() / numpy.abs(ref).max() < 1e-12
+    assert (numpy.diag(k) == 0).all()
+    gref = golden['green_small']['createSphere_offdiag'].copy()
+    gref[numpy.diag_indices(n)] = golden['green_small']['createSphere_diag5']
+    assert max_entry_relerr(g, gref) < TOL_ENTRY     # G unchanged by the fused K path
+
+
+def test_k_row_sums_closed_surface(ctx):
+    """sum_j K[i,j] -> 1/2 on a closed outward-oriented surface (solid angle 2 pi)."""
+    from icqsol_b200.mesh.generators import uvSphere
+    xyz, tri = uvSphere(1.0, 48, 24)
+    g, k = assemble(ctx, xyz, tri, 5, with_k=True)
+    rs = k.sum(axis=1)
+    assert numpy.abs(rs - 0.5).max() < 0.02
+
+
+def test_k_row_block_and_sampled_oracle(ctx, golden, oracle_mod):
+    xyz, tri = golden.mesh('boltFine')
+    g, k = assemble(ctx, xyz, tri, 5, with_k=True, rows=(1000, 1300))
+    ref = oracle_mod.k_block(xyz, tri, 1000, 1300, 0, tri.shape[0])
+    assert numpy.abs(k - ref).max() / numpy.abs(ref).max() < 1e-11
+    gref = oracle_mod.block(xyz, tri, 1000, 1300, 0, tri.shape[0], 5)
+    assert max_entry_relerr(g, gref) < TOL_ENTRY
+
+
+# ---- quadrature handle API (tests/testQuadratureCpp.py) ----------------------------------
+
+def test_quadrature_handle_api(gpu_lib, golden):
+    kat = golden['known_answers']
+    h = ctypes.c_void_p()
+    gpu_lib.icqQuadratureInit(ctypes.byref(h))
+    assert h.value
+    assert gpu_lib.icqQuadratureGetMaxOrder(ctypes.byref(h)) == int(kat['max_order']) == 8
+    tris, obs = kat['corner_tris'], kat['single_obs']
+    for i in range(tris.shape[0]):
+        gpu_lib.icqQuadratureSetObserver(ctypes.byref(h), dp(numpy.ascontiguousarray(obs[i])))
+        t = numpy.ascontiguousarray(tris[i])
+        for order in range(10):
+            v = gpu_lib.icqQuadratureEvaluate(ctypes.byref(h), order, dp(t[0]), dp(t[1]), dp(t[2]))
+            ref = kat['single_vals'][i, order]
+            assert abs(v - ref) <= 1e-13 * abs(ref)      # unknown orders: exactly 0
+    pairs = kat['double_pairs']
+    for i in range(pairs.shape[0]):
+        a = numpy.ascontiguousarray(pairs[i, 0])
+        b = numpy.ascontiguousarray(pairs[i, 1])
+        for order in range(10):
+            v = gpu_lib.icqQuadratureEvaluateDouble(ctypes.byref(h), order, dp(a[0]), dp(a[1]),
+                                                    dp(a[2]), dp(b[0]), dp(b[1]), dp(b[2]))
+            ref = kat['double_vals'][i, order]
+            assert abs(v - ref) <= 1e-13 * abs(ref)
+    # zero-area triangle -> 0 (bem/icqQuadrature.cpp:185)
+    z = numpy.zeros(3)
+    assert gpu_lib.icqQuadratureEvaluate(ctypes.byref(h), 5, dp(z), dp(z), dp(z)) == 0.0
+    gpu_lib.icqQuadratureDel(ctypes.byref(h))
+
+
+def test_quadrature_cpp_style(gpu_lib, golden):
+    """tests/testQuadratureCpp.py:33-53: device quadrature == triangleQuadrature formula
+    (observer at the origin, -1/(4 pi r)) for orders 1..8, tolerance 1e-10 as in the reference."""
+    tables = golden['tables']
+    pa, pb, pc = numpy.array([0., 0., 1.]), numpy.array([1., 0., 1.]), numpy.array([0., 1., 1.])
+    h = ctypes.c_void_p()
+    gpu_lib.icqQuadratureInit(ctypes.byref(h))
+    for order in range(1, 9):
+        xi, eta, w = tables['tri%d' % order]
+        p = pa[None, :] + xi[:, None] * (pb - pa)[None, :] + eta[:, None] * (pc - pa)[None, :]
+        area = numpy.linalg.norm(numpy.cross(pb - pa, pc - pa))
+        expected = 0.5 * area * (w * (-1. / (4. * numpy.pi * numpy.linalg.norm(p, axis=1)))).sum()
+        v = gpu_lib.icqQuadratureEvaluate(ctypes.byref(h), order, dp(pa), dp(pb), dp(pc))
+        assert abs(v - expected) < 1e-10
+    gpu_lib.icqQuadratureDel(ctypes.byref(h))
+
+
+# ---- GEMV / CG / solver classes -----------------------------------------------------------
+
+@pytest.mark.parametrize('nrows,ncols', [(1, 1), (3, 5), (4, 512), (127, 1023), (960, 960),
+                                         (1001, 2350)])
+def test_gemv_vs_numpy(ctx, nrows, ncols):
+    import torch
+    rng = numpy.random.default_rng(nrows * 7919 + ncols)
+    a = rng.normal(size=(nrows, ncols))
+    x = rng.normal(size=ncols)
+    for ld in (ncols, (ncols + 15) // 16 * 16):
+        dev = torch.zeros((nrows, ld), dtype=torch.float64, device='cuda:0')
+        dev[:, :ncols] = torch.from_numpy(a).cuda()
+        y = numpy.zeros(nrows)
+        ctx.check(ctx.lib.icqb_gemv_host(ctx.handle, dev.data_ptr(), nrows, ncols, ld, dp(x), dp(y)))
+        ref = a.dot(x)
+        scale = numpy.abs(a).dot(numpy.abs(x))
+        assert (numpy.abs(y - ref) <= 1e-13 * scale).all()
+
+
+def test_poisson_response_golden(golden):
+    """PoissonSolver on the reference's meshes: v = G.charge vs numpy.dot on the
+    reference G (bem/icqPoissonSolver.py:36), 1e-12 relative."""
+    from icqsol_b200.mesh.polydata import PolyData
+    from icqsol_b200.bem.icqPoissonSolver import PoissonSolver
+    big = golden['green_sampled']
+    for name in ('sphere', 'boltFine'):
+        xyz, tri = golden.mesh(name)
+        solver = PoissonSolver(PolyData.from_arrays(xyz, tri, dtype=numpy.float64), float('inf'))
+        solver.setSourceFromExpression('1.0')
+        rsp = solver.computeResponseField()
+        assert numpy.abs(rsp / big[name + '_poisson_rsp_one'] - 1).max() < 1e-12
+        solver.setSourceFromExpression('x')
+        rsp = solver.computeResponseField()
+        ref = big[name + '_poisson_rsp_x']
+        assert numpy.abs(rsp - ref).max() / numpy.abs(ref).max() < 1e-12
+        arr = solver.getVtkPolyData().GetCellData().GetArray('v')
+        assert arr is not None and arr.GetNumberOfTuples() == len(tri)
+
+
+def test_laplace_response_golden(golden):
+    """LaplaceSolver: sigma = -G^-1 v.  Reference = LU (bem/icqLaplaceSolver.py:36).
+    Backward error <= 1e-12; forward difference vs LU bounded by the conditioning."""
+    from icqsol_b200.mesh.polydata import PolyData
+    from icqsol_b200.bem.icqLaplaceSolver import LaplaceSolver
+    big = golden['green_sampled']
+    for name in ('sphere', 'boltFine'):
+        xyz, tri = golden.mesh(name)
+        solver = LaplaceSolver(PolyData.from_arrays(xyz, tri, dtype=numpy.float64), float('inf'), 5)
+        solver.setSourceFromExpression('1./sqrt(x**2 + (y-2.)**2 + (z-4.)**2)')
+        v = solver.getSourceArray(solver.getSourceArrayIndex())
+        assert numpy.abs(v / big[name + '_v'] - 1).max() < 1e-14
+        rsp = solver.computeResponseField()
+        ref = big[name + '_laplace_rsp']
+        g = solver.getGreenMatrix()
+        backward = numpy.abs(v + g.dot(rsp)).max() / numpy.abs(v).max()
+        assert backward < 1e-12
+        cond = float(big[name + '_cond'])
+        assert numpy.abs(rsp - ref).max() / numpy.abs(ref).max() < 50 * cond * EPS
+        assert solver.lastSolveInfo['iterations'] < len(tri)
+        arr = solver.getVtkPolyData().GetCellData().GetArray('normal_electric_field_jump')
+        assert arr is not None
+
+
+def test_conjugate_gradient_class_golden(golden):
+    """ConjugateGradient on the symmetrised system of a UV sphere vs the reference
+    class's own run (tests/golden/cg.npz) and LU."""
+    from icqsol_b200.mesh.generators import uvSphere
+    from icqsol_b200.solvers.icqConjugateGradient import ConjugateGradient
+    from oracle import oracle
+    cg = golden['cg']
+    for name in ('uv16x8', 'uv40x20'):
+        nt, npz = cg[name + '_nt_np']
+        xyz, tri = uvSphere(1.0, int(nt), int(npz))
+        g = oracle.green_matrix(xyz, tri, 5, threads=True)
+        a2 = oracle.area2(xyz, tri)
+        cen = (xyz[tri[:, 0]] + xyz[tri[:, 1]] + xyz[tri[:, 2]]) / 3.
+        v = 1. / numpy.sqrt(cen[:, 0] ** 2 + (cen[:, 1] - 2.) ** 2 + (cen[:, 2] - 4.) ** 2)
+        # (1) exactly the reference's usage: explicit symmetrised matrix
+        s = a2[:, None] * g
+        solver = ConjugateGradient(s, a2 * v)
+        solver.setTolerance(1.e-13)
+        x, err, k = solver.solve(numpy.zeros(len(v)))
+        assert err <= 1.e-13
+        assert abs(k - int(cg[name + '_iters'])) <= 3
+        assert numpy.abs(x - cg[name + '_x']).max() / numpy.abs(x).max() < 1e-9
+        assert abs(solver.getSolutionError(x) - err) < 1e-13
+        # (2) raw G with row scaling
+        solver = ConjugateGradient(g, v)
+        solver.setRowScaling(a2)
+        solver.setTolerance(1.e-12)
+        x2, err2, k2 = solver.solve(numpy.zeros(len(v)))
+        assert err2 <= 1.e-12
+        lu = cg[name + '_lu']
+        assert numpy.abs(x2 - lu).max() / numpy.abs(lu).max() < 1e-8
+
+
+def test_cg_nonzero_start_and_maxiter(golden):
+    from icqsol_b200.solvers.icqConjugateGradient import ConjugateGradient
+    rng = numpy.random.default_rng(3)
+    q = rng.normal(size=(300, 300))
+    a = q.dot(q.T) + 300 * numpy.eye(300)
+    xt = rng.normal(size=300)
+    b = a.dot(xt)
+    solver = ConjugateGradient(a, b)
+    x, err, k = solver.solve(rng.normal(size=300))
+    assert err <= 1e-10 and numpy.abs(x - xt).max() < 1e-10 and 0 < k < 300
+    solver.setMaxNumberOfIterations(3)
+    x, err, k = solver.solve(numpy.zeros(300))
+    assert k == 3 and err > 1e-10
+    # already converged start: zero iterations (while-condition at icqConjugateGradient.py:64)
+    solver.setMaxNumberOfIterations(300)
+    x, err, k = solver.solve(xt)
+    assert k == 0
+
+
+def test_point_data_projection_and_missing_source(golden):
+    from icqsol_b200.mesh.polydata import PolyData, DataArray
+    from icqsol_b200.bem.icqPoissonSolver import PoissonSolver
+    xyz, tri = golden.mesh('tet')
+    pd = PolyData.from_arrays(xyz, tri)
+    solver = PoissonSolver(pd, float('inf'))
+    with pytest.raises(RuntimeError):
+        solver.computeResponseField()
+    pd.GetPointData().AddArray(DataArray('charge', [1., 2., 3., 4.]))
+    rsp = solver.computeResponseField()
+    cellCharge = numpy.array([(1 + 2 + 4) / 3., (1 + 3 + 2) / 3., (1 + 4 + 3) / 3., (2 + 3 + 4) / 3.])
+    g = solver.getGreenMatrix()
+    assert numpy.abs(rsp - g.dot(cellCharge)).max() < 1e-14
