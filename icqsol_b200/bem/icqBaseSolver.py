@@ -40,6 +40,9 @@ class BaseSolver:
         @param order order of the self-term integration (1..5)
         """
         xyz, cells = extract_mesh(pdata)
+        # every cell must be a polygon that can be turned into triangles
+        # (the reference asserts 3 ids per refined cell, bem/icqBaseSolver.py:31)
+        assert all(len(c) >= 3 for c in cells)
         isTriangulated = all(len(c) == 3 for c in cells)
         tri = generators.fanSplit(cells)
         refXyz, refTri = generators.refineToMaxEdge(xyz, tri, max_edge_length)

@@ -1,0 +1,230 @@
+"""Host-side logic that needs no GPU: mesh stand-in, legacy VTK I/O, generators,
+solver field plumbing, the row partition (incl. a world_size-2 gloo run), and
+that the C-ABI library loads and exports every symbol include/icqb.h declares."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    import __graft_entry__ as entry
+    entry.build()
+    from icqsol_b200 import _lib
+    from icqsol_b200.util.icqSharedLibraryUtils import getSharedLibraryName
+    path = getSharedLibraryName(_lib.LIB_NAME)
+    assert os.path.dirname(path) == os.path.join(ROOT, 'icqsol_b200')
+    hdr = open(os.path.join(ROOT, 'include', 'icqb.h')).read()
+    hdr = re.sub(r'/\*.*?\*/', '', hdr, flags=re.S)
+    declared = set(re.findall(r'\b(icqb_\w+|icqQuadrature(?!Type)\w+|computeOffDiagonalTermsArrays)\s*\(', hdr))
+    assert len(declared) >= 30
+    lib = ctypes.CDLL(path)
+    for name in declared:
+        assert hasattr(lib, name), name
+    bound = {name for name, _, _ in _lib.SIGNATURES}
+    assert bound == declared
+    # sm_100a code, TMA bulk copies and the fp64 reciprocal-sqrt unit are really in there
+    sass = subprocess.run(['cuobjdump', '-sass', path], capture_output=True, text=True).stdout
+    if sass:
+        assert 'sm_100a' in sass and 'UBLKCP' in sass and 'MUFU.RSQ64H' in sass and 'DFMA' in sass
+
+
+def test_no_cpu_fallback_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('CUDA present')
+    from icqsol_b200 import _lib
+    with pytest.raises(RuntimeError):
+        _lib.Context(0)
+    from icqsol_b200.mesh.polydata import PolyData
+    from icqsol_b200.mesh.generators import uvSphere
+    from icqsol_b200.bem.icqLaplaceSolver import LaplaceSolver
+    with pytest.raises(RuntimeError):
+        LaplaceSolver(PolyData.from_arrays(*uvSphere(1.0, 6, 4)), float('inf'))
+    from icqsol_b200.solvers.icqConjugateGradient import ConjugateGradient
+    with pytest.raises(RuntimeError):
+        ConjugateGradient(numpy.eye(3), numpy.ones(3))
+
+
+def test_product_does_not_import_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, 'icqsol_b200')):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.h')):
+                text = open(os.path.join(dirpath, f)).read()
+                assert 'oracle' not in text.lower().replace('not import the oracle', ''), f
+
+
+def test_vtk_reader_on_golden_meshes(golden, tmp_path):
+    from icqsol_b200.mesh.polydata import PolyData, DataArray, extract_mesh
+    from icqsol_b200.mesh.vtk_legacy_io import readVtkPolyData, writeVtkPolyData
+    xyz, tri = golden.mesh('boltFine')
+    pd = PolyData.from_arrays(xyz, tri)
+    pd.GetCellData().AddArray(DataArray('v', numpy.arange(len(tri)) * 0.5))
+    pd.GetPointData().AddArray(DataArray('Normals', numpy.ones((len(xyz), 3))))
+    path = str(tmp_path / 'bolt.vtk')
+    writeVtkPolyData(pd, path)
+    back = readVtkPolyData(path)
+    xyz2, cells2 = extract_mesh(back)
+    assert (xyz2 == xyz).all()           # float32 values survive the ASCII round trip
+    assert (numpy.array(cells2) == tri).all()
+    assert back.GetCellData().GetArray('v').GetComponent(7, 0) == 3.5
+    assert back.GetPointData().GetArray('Normals').GetNumberOfComponents() == 3
+
+
+def test_vtk_reader_binary_and_ascii(tmp_path):
+    from icqsol_b200.mesh.vtk_legacy_io import readVtkPolyData
+    pts = numpy.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0.5]], '>f4')
+    polys = numpy.array([4, 0, 1, 2, 3, 3, 0, 2, 3], '>i4')
+    nrm = numpy.ones((4, 3), '>f4')
+    path = str(tmp_path / 'b.vtk')
+    with open(path, 'wb') as f:
+        f.write(b'# vtk DataFile Version 3.0\nvtk output\nBINARY\nDATASET POLYDATA\nPOINTS 4 float\n')
+        f.write(pts.tobytes() + b'\nPOLYGONS 2 9\n' + polys.tobytes())
+        f.write(b'\nPOINT_DATA 4\nNORMALS Normals float\n' + nrm.tobytes() + b'\n')
+    pd = readVtkPolyData(path)
+    assert pd.GetNumberOfPoints() == 4 and pd.GetNumberOfPolys() == 2
+    assert pd.GetPoints().GetPoint(3) == (0.0, 1.0, 0.5)
+    ids = type(pd.GetPolys()).__mro__ and __import__('icqsol_b200.mesh.polydata', fromlist=['IdList']).IdList()
+    pd.GetPolys().InitTraversal()
+    pd.GetPolys().GetNextCell(ids)
+    assert [ids.GetId(k) for k in range(ids.GetNumberOfIds())] == [0, 1, 2, 3]
+    with open(path, 'w') as f:
+        f.write('# vtk DataFile Version 3.0\nx\nASCII\nDATASET UNSTRUCTURED_GRID\n')
+    with pytest.raises(ValueError):
+        readVtkPolyData(path)
+
+
+def test_generators():
+    from icqsol_b200.mesh import generators as gen
+    xyz, tri = gen.uvSphere(1.0, 142, 71)
+    assert tri.shape == (19880, 3) and xyz.shape == (9942, 3)
+    a, b, c = xyz[tri[:, 0]], xyz[tri[:, 1]], xyz[tri[:, 2]]
+    nrm = numpy.cross(b - a, c - a)
+    assert ((nrm * (a + b + c)).sum(axis=1) > 0).all()          # outward
+    assert abs(0.5 * numpy.linalg.norm(nrm, axis=1).sum() / (4 * numpy.pi) - 1) < 1e-3
+    assert (xyz == xyz.astype(numpy.float32)).all()              # float32-representable
+    assert gen.uvSphere(1.0, 448, 224)[1].shape[0] == 199808
+    assert gen.hollowSphere()[1].shape[0] == 49400
+    xi, ti = gen.uvSphere(1.0, 8, 4, outward=False)
+    a, b, c = xi[ti[:, 0]], xi[ti[:, 1]], xi[ti[:, 2]]
+    assert ((numpy.cross(b - a, c - a) * (a + b + c)).sum(axis=1) < 0).all()
+    # fan split and subdivision
+    assert gen.fanSplit([(0, 1, 2, 3), (4, 5, 6)]).tolist() == [[0, 1, 2], [0, 2, 3], [4, 5, 6]]
+    x0, t0 = gen.uvSphere(1.0, 8, 4, float32_points=False)
+    x6, t6 = gen.subdivide(x0, t0, 6, float32_points=False)
+    assert t6.shape[0] == 36 * t0.shape[0]
+
+    def area(x, t):
+        return 0.5 * numpy.linalg.norm(numpy.cross(x[t[:, 1]] - x[t[:, 0]], x[t[:, 2]] - x[t[:, 0]]), axis=1).sum()
+    assert abs(area(x6, t6) / area(x0, t0) - 1) < 1e-13
+    xr, tr = gen.refineToMaxEdge(x0, t0, 0.3)
+    e = numpy.sqrt(((xr[tr[:, 1]] - xr[tr[:, 0]]) ** 2).sum(1))
+    assert e.max() <= 0.3 + 1e-6 and abs(area(xr, tr) / area(x0, t0) - 1) < 1e-6
+    same = gen.refineToMaxEdge(x0, t0, float('inf'))
+    assert same[1] is not None and same[1].shape == t0.shape
+
+
+def test_base_solver_plumbing(golden):
+    """BaseSolver API (bem/icqBaseSolver.py:47-157) on the stand-in polydata."""
+    from icqsol_b200.mesh.polydata import PolyData, DataArray
+    from icqsol_b200.bem.icqBaseSolver import BaseSolver
+    xyz, tri = golden.mesh('tet')
+    pd = PolyData.from_arrays(xyz, tri)
+    s = BaseSolver(pd, float('inf'), order=3)
+    assert s.getVtkPolyData() is pd and s.numTriangles == 4 and s.order == 3
+    assert (s.getPoints() == xyz).all() and (s.getCells() == tri).all()
+    assert s.getCells().dtype == numpy.int64
+    s.setSourceFieldName('src')
+    s.setResponseFieldName('rsp')
+    with pytest.raises(RuntimeError):
+        s.getSourceArrayIndex()
+    s.setSourceFromExpression('x + 2*y + sin(z)')
+    src = s.getSourceArray(s.getSourceArrayIndex())
+    cen = (xyz[tri[:, 0]] + xyz[tri[:, 1]] + xyz[tri[:, 2]]) / 3.
+    assert numpy.abs(src - (cen[:, 0] + 2 * cen[:, 1] + numpy.sin(cen[:, 2]))).max() < 1e-15
+    s.addResponseField(numpy.array([1., 2., 3., 4.]))
+    assert pd.GetCellData().GetArray('rsp').GetComponent(2, 0) == 3.0
+    # point data -> cell data by vertex averaging (util/icqDataFetcher.py:57)
+    pd.GetPointData().AddArray(DataArray('pt', [3., 6., 9., 12.]))
+    s.setSourceFieldName('pt')
+    vals = s.getSourceArray(s.getSourceArrayIndex())
+    assert numpy.allclose(vals, [(3 + 6 + 12) / 3., (3 + 9 + 6) / 3., (3 + 12 + 9) / 3., (6 + 9 + 12) / 3.])
+    # polygons are fan-split into a new polydata; long edges are subdivided
+    xyzs, cells = golden.mesh('sphere')
+    quad = PolyData.from_arrays(numpy.array([[0., 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0]]), [(0, 1, 2, 3)])
+    s2 = BaseSolver(quad, float('inf'))
+    assert s2.numTriangles == 2 and s2.getVtkPolyData() is not quad
+    s3 = BaseSolver(quad, 0.5)
+    assert s3.numTriangles > 2
+    with pytest.raises(AssertionError):
+        BaseSolver(PolyData.from_arrays(numpy.zeros((2, 3)), [(0, 1)]), float('inf'))
+
+
+def test_row_partition():
+    from icqsol_b200.bem import icqRowPartition as rp
+    for n in (0, 1, 7, 19880, 199808):
+        for p in (1, 2, 3, 4, 8):
+            ranges = [rp.rowRange(n, r, p) for r in range(p)]
+            assert ranges[0][0] == 0 and ranges[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+            chunk = rp.rowChunk(n, p)
+            assert all(0 <= r1 - r0 <= chunk for r0, r1 in ranges)
+            assert all(r0 == min(n, r * chunk) for r, (r0, r1) in enumerate(ranges))
+    assert rp.worldInfo() == (0, 1)
+    assert rp.broadcastBytes(b'abc', 3) == b'abc'
+    assert (rp.allGatherRows(numpy.arange(5.), 5) == numpy.arange(5.)).all()
+
+
+GLOO_WORKER = r'''
+import os, sys
+sys.path.insert(0, {root!r})
+import numpy, torch.distributed as dist
+from icqsol_b200.bem import icqRowPartition as rp
+dist.init_process_group('gloo')
+rank, world = rp.worldInfo()
+assert world == 2
+payload = bytes(range(128)) if rank == 0 else b''
+got = rp.broadcastBytes(payload, 128, src=0)
+assert got == bytes(range(128)), got
+n = 11
+r0, r1 = rp.rowRange(n, rank, world)
+full = rp.allGatherRows(numpy.arange(r0, r1, dtype=float) * 2.0, n)
+assert (full == numpy.arange(n) * 2.0).all(), full
+mat = rp.allGatherMatrixRows(numpy.arange(r0, r1, dtype=float)[:, None] * numpy.ones((1, 3)), n)
+assert mat.shape == (n, 3) and (mat[:, 1] == numpy.arange(n)).all()
+# empty trailing rank
+r0, r1 = rp.rowRange(1, rank, world)
+full = rp.allGatherRows(numpy.ones(r1 - r0) * 5.0, 1)
+assert full.tolist() == [5.0]
+dist.barrier()
+dist.destroy_process_group()
+print('rank', rank, 'ok')
+'''
+
+
+def test_row_partition_gloo_world2(tmp_path):
+    script = tmp_path / 'worker.py'
+    script.write_text(GLOO_WORKER.format(root=ROOT))
+    env = dict(os.environ, MASTER_ADDR='127.0.0.1', CUDA_VISIBLE_DEVICES='')
+    out = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1',
+                          '--nproc-per-node', '2', '--master-addr', '127.0.0.1', '--master-port',
+                          '29533', str(script)], capture_output=True, text=True, env=env, timeout=240)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.count('ok') == 2
+
+
+def test_bench_reference_arm_runs():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference',
+                          '--steps', '1', '--warmup', '0', '--cpu-sample', '200'],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    import json
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line['impl'] == 'reference' and line['value'] > 0 and line['unit'] == 'entries/s'
+    assert line['cpu_baseline']['kind'] in ('reference', 'port')
