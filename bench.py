@@ -228,12 +228,7 @@ def run_b200(args):
     lib = ctx.lib
     stream = torch.cuda.Stream(device=dev)
     ctx.check(lib.icqb_set_stream(ctx.handle, stream.cuda_stream))
-    if world > 1:
-        uid = ctypes.create_string_buffer(128)
-        if rank == 0:
-            ctx.check(lib.icqb_comm_unique_id(uid))
-        raw = rowPartition.broadcastBytes(uid.raw, 128, src=0)
-        ctx.check(lib.icqb_comm_init(ctx.handle, ctypes.create_string_buffer(raw, 128), rank, world))
+    _lib.attachCommunicator(ctx, rank, world, rowPartition.broadcastBytes)
     ctx.check(lib.icqb_set_mesh(ctx.handle, xyz.ctypes.data_as(_lib.c_double_p), xyz.shape[0],
                                 tri.ctypes.data_as(_lib.c_int64_p), n))
     r0, r1 = rowPartition.rowRange(n, rank, world)

@@ -46,6 +46,7 @@ SIGNATURES = [
                                   c_double_p, c_double_p]),
     ('icqb_comm_unique_id', c_int, [c_void_p]),
     ('icqb_comm_init', c_int, [c_void_p, c_void_p, c_int, c_int]),
+    ('icqb_comm_share', c_int, [c_void_p, c_void_p]),
     ('icqb_comm_rank', c_int, [c_void_p, POINTER(c_int), POINTER(c_int)]),
     ('icqb_last_ms', c_double, [c_void_p, c_int]),
     ('icqb_launch_count', c_int64, [c_void_p]),
@@ -119,3 +120,25 @@ class Context:
 
     def launch_count(self):
         return int(self.lib.icqb_launch_count(self.handle))
+
+
+_comm_owner = {}
+
+
+def attachCommunicator(ctx, rank, nranks, broadcastBytes):
+    """Give ``ctx`` the process-wide NCCL communicator for its device, creating it
+    on first use: rank 0 draws the ncclUniqueId, ``broadcastBytes(payload, nbytes, src)``
+    (torch.distributed in the host layer) carries it to the other ranks."""
+    if nranks <= 1:
+        return
+    owner = _comm_owner.get(ctx.device)
+    if owner is None:
+        owner = Context(ctx.device)
+        uid = ctypes.create_string_buffer(128)
+        if rank == 0:
+            owner.check(owner.lib.icqb_comm_unique_id(uid))
+        raw = broadcastBytes(uid.raw, 128, 0)
+        owner.check(owner.lib.icqb_comm_init(owner.handle, ctypes.create_string_buffer(raw, 128),
+                                             int(rank), int(nranks)))
+        _comm_owner[ctx.device] = owner
+    ctx.check(ctx.lib.icqb_comm_share(ctx.handle, owner.handle))

@@ -64,13 +64,8 @@ class BaseLaplaceSolver(BaseSolver):
         self.lib = self.ctx.lib
 
         self.rank, self.numRanks = rowPartition.worldInfo()
-        if self.numRanks > 1:
-            uid = ctypes.create_string_buffer(128)
-            if self.rank == 0:
-                self.ctx.check(self.lib.icqb_comm_unique_id(uid))
-            raw = rowPartition.broadcastBytes(uid.raw, 128, src=0)
-            uid = ctypes.create_string_buffer(raw, 128)
-            self.ctx.check(self.lib.icqb_comm_init(self.ctx.handle, uid, self.rank, self.numRanks))
+        # one NCCL communicator per process, shared by every solver
+        _lib.attachCommunicator(self.ctx, self.rank, self.numRanks, rowPartition.broadcastBytes)
 
         n = self.numTriangles
         self.ctx.check(self.lib.icqb_set_mesh(

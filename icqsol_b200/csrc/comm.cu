@@ -60,6 +60,7 @@ Api& api() {
 struct Comm {
     ncclComm_t comm = nullptr;
     int rank = 0, nranks = 1;
+    int refs = 1;   // contexts sharing this communicator (icqb_comm_share)
 };
 
 int comm_nranks(const icqb_ctx* ctx) { return ctx->comm ? ctx->comm->nranks : 1; }
@@ -96,8 +97,10 @@ int comm_allreduce_sum(icqb_ctx* ctx, double* buf, int64_t count, cudaStream_t s
 
 void comm_destroy(icqb_ctx* ctx) {
     if (!ctx->comm) return;
-    if (ctx->comm->comm) api().CommDestroy(ctx->comm->comm);
-    delete ctx->comm;
+    if (--ctx->comm->refs == 0) {
+        if (ctx->comm->comm) api().CommDestroy(ctx->comm->comm);
+        delete ctx->comm;
+    }
     ctx->comm = nullptr;
 }
 
@@ -137,6 +140,18 @@ int icqb_comm_init(icqb_ctx* ctx, const void* unique_id_128, int rank, int nrank
         return set_error(ctx, ICQB_ECOMM, std::string("ncclCommInitRank: ") + a.GetErrorString(r));
     }
     ctx->comm = c;
+    return ICQB_OK;
+}
+
+int icqb_comm_share(icqb_ctx* ctx, icqb_ctx* owner) {
+    if (!ctx || !owner) return ICQB_EARG;
+    if (ctx->device != owner->device)
+        return set_error(ctx, ICQB_EARG, "icqb_comm_share: contexts live on different devices");
+    comm_destroy(ctx);
+    if (owner->comm) {
+        ctx->comm = owner->comm;
+        ctx->comm->refs += 1;
+    }
     return ICQB_OK;
 }
 

@@ -134,6 +134,9 @@ int icqb_cg_solve_dev(icqb_ctx* ctx, uint64_t dA, int64_t n, int64_t ld, uint64_
  * in the Python host layer). */
 int icqb_comm_unique_id(void* unique_id_128);
 int icqb_comm_init(icqb_ctx* ctx, const void* unique_id_128, int rank, int nranks);
+/* Reuse the communicator of another context of the same process and device
+ * (communicator creation costs ~1 s; solvers are created many times). */
+int icqb_comm_share(icqb_ctx* ctx, icqb_ctx* owner);
 int icqb_comm_rank(const icqb_ctx* ctx, int* rank, int* nranks);
 
 /* ---- instrumentation ----------------------------------------------------------------

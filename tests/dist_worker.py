@@ -1,0 +1,65 @@
+"""Multi-rank parity worker, launched by tests/test_gpu_multi.py under torchrun
+(one rank per GPU, NCCL).  Row-sharded assembly + NCCL CG vs the oracle."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy  # noqa: E402
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+
+def main():
+    local = int(os.environ['LOCAL_RANK'])
+    torch.cuda.set_device(local)
+    dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    rank, world = dist.get_rank(), dist.get_world_size()
+    from oracle import oracle
+    from icqsol_b200.mesh.generators import uvSphere
+    from icqsol_b200.mesh.polydata import PolyData
+    from icqsol_b200.bem.icqLaplaceSolver import LaplaceSolver
+    from icqsol_b200.bem.icqPoissonSolver import PoissonSolver
+
+    for nt, npz in ((40, 20), (64, 30), (7, 4)):
+        xyz, tri = uvSphere(1.0, nt, npz)
+        n = tri.shape[0]
+        solver = LaplaceSolver(PolyData.from_arrays(xyz, tri), float('inf'), 5, computeK=True)
+        r0, r1 = solver.getRowRange()
+        assert solver.numRanks == world
+        gloc = solver.getGreenMatrixDevice().cpu().numpy()
+        ref = oracle.block(xyz, tri, r0, r1, 0, n, 5)
+        if r1 > r0:
+            assert numpy.abs(gloc / ref - 1).max() < 1e-12, 'G rows'
+            kref = oracle.k_block(xyz, tri, r0, r1, 0, n)
+            kloc = solver.getNormalDerivativeGreenMatrixDevice().cpu().numpy()
+            assert numpy.abs(kloc - kref).max() / numpy.abs(kref).max() < 1e-9, 'K rows'
+        g = solver.getGreenMatrix()          # gathered on every rank
+        gref = oracle.green_matrix(xyz, tri, 5, threads=True)
+        assert numpy.abs(g / gref - 1).max() < 1e-12, 'G gathered'
+        solver.setSourceFromExpression('1./sqrt(x**2 + (y-2.)**2 + (z-4.)**2)')
+        v = solver.getSourceArray(solver.getSourceArrayIndex())
+        rsp = solver.computeResponseField()
+        backward = numpy.abs(v + gref.dot(rsp)).max() / numpy.abs(v).max()
+        assert backward < 1e-12, backward
+        lu = oracle.laplace_response(gref, v)
+        assert numpy.abs(rsp - lu).max() / numpy.abs(lu).max() < 1e-8
+        info = solver.lastSolveInfo
+        psolver = PoissonSolver(PolyData.from_arrays(xyz, tri), float('inf'), 5)
+        psolver.setSourceFromExpression('x + 1.0')
+        prsp = psolver.computeResponseField()
+        cen = (xyz[tri[:, 0]] + xyz[tri[:, 1]] + xyz[tri[:, 2]]) / 3.
+        pref = gref.dot(cen[:, 0] + 1.0)
+        assert numpy.abs(prsp - pref).max() / numpy.abs(pref).max() < 1e-12
+        if rank == 0:
+            print('N={0} ranks={1}: CG iters {2}, backward {3:.2e}'.format(
+                n, world, info['iterations'], backward))
+        del solver, psolver
+    dist.barrier()
+    dist.destroy_process_group()
+    print('rank {0} ok'.format(rank))
+
+
+if __name__ == '__main__':
+    main()
