@@ -13,6 +13,8 @@ refined so that the N^2 matrix work per GPU stays fixed ("weak" scaling), rows
 block-sharded over the ranks, NCCL only inside the CG.
 
 value   = G+K entries per second over the whole step = 2*N^2 / ms_per_step
+          (N^2 entries per matrix are DEFINED by a step in either storage: in 'lower'
+          storage the upper half is the mirror rule applied on read)
 e2e     = same metric through the public Python API (LaplaceSolver on a host
           polydata -> host response), host<->device copies inside the timed region
 roofline= dominant kernel (fused G+K off-diagonal assembly) against the FP64 FMA
@@ -231,15 +233,36 @@ def run_b200(args):
     _lib.attachCommunicator(ctx, rank, world, rowPartition.broadcastBytes)
     ctx.check(lib.icqb_set_mesh(ctx.handle, xyz.ctypes.data_as(_lib.c_double_p), xyz.shape[0],
                                 tri.ctypes.data_as(_lib.c_int64_p), n))
-    r0, r1 = rowPartition.rowRange(n, rank, world)
-    ctx.check(lib.icqb_set_rows(ctx.handle, r0, r1))
-    rows = r1 - r0
+    lower = args.storage == 'lower'
+    if lower:
+        blocks = rowPartition.foldedBlocks(n, rank, world)
+        ctx.check(lib.icqb_set_row_blocks(ctx.handle, *blocks))
+    else:
+        r0, r1 = rowPartition.rowRange(n, rank, world)
+        blocks = (r0, r1, r1, r1)
+        ctx.check(lib.icqb_set_rows(ctx.handle, r0, r1))
+    rows = (blocks[1] - blocks[0]) + (blocks[3] - blocks[2])
     ld = leadingDimension(n)
     gbuf = torch.empty((max(rows, 1), ld), dtype=torch.float64, device=dev)
     kbuf = torch.empty((max(rows, 1), ld), dtype=torch.float64, device=dev)
-    bdev = torch.from_numpy(v[r0:r1].copy()).to(dev)
-    xdev = torch.zeros(max(rows, 1), dtype=torch.float64, device=dev)
-    area2 = lib.icqb_area2_dev(ctx.handle) + 8 * r0
+    kubuf = torch.empty((max(rows, 1), ld), dtype=torch.float64, device=dev) if lower else None
+    bdev = torch.from_numpy(v).to(dev)
+    xdev = torch.zeros(n, dtype=torch.float64, device=dev)
+    area2 = lib.icqb_area2_dev(ctx.handle)
+    # pairs of triangles this rank evaluates, stored entries it streams per product
+    if lower:
+        tiles = 0
+        pairs_local = 0.0
+        stored = 0.0
+        for (b, e) in ((blocks[0], blocks[1]), (blocks[2], blocks[3])):
+            for t0 in range(b, e, 128):
+                h = min(128, e - t0)
+                w_diag = min(128, n - t0)
+                pairs_local += h * t0 + h * (w_diag - 1)      # below the diagonal tile + inside it
+                stored += h * t0 + h * w_diag
+    else:
+        pairs_local = rows * (rows - 1) / 2.0 + rows * (n - rows)
+        stored = float(rows) * n
     torch.cuda.synchronize(dev)
 
     phase = {'assembly_ms': [], 'offdiag_ms': [], 'diag_ms': [], 'solve_ms': [], 'gemv_ms': [],
@@ -249,12 +272,16 @@ def run_b200(args):
         with torch.cuda.stream(stream):
             xdev.zero_()
         t0 = time.perf_counter()
-        ctx.check(lib.icqb_assemble_dev(ctx.handle, 5, gbuf.data_ptr(), kbuf.data_ptr(), ld))
+        if lower:
+            ctx.check(lib.icqb_assemble_lower_dev(ctx.handle, 5, gbuf.data_ptr(), kbuf.data_ptr(),
+                                                  kubuf.data_ptr(), ld))
+        else:
+            ctx.check(lib.icqb_assemble_dev(ctx.handle, 5, gbuf.data_ptr(), kbuf.data_ptr(), ld))
         t1 = time.perf_counter()
         iters = ctypes.c_int64(0)
         r2 = ctypes.c_double(0.)
         rinf = ctypes.c_double(0.)
-        ctx.check(lib.icqb_cg_solve_dev(ctx.handle, gbuf.data_ptr(), n, ld, area2, 0,
+        ctx.check(lib.icqb_cg_solve_dev(ctx.handle, gbuf.data_ptr(), n, ld, 1 if lower else 0, area2, 0,
                                         bdev.data_ptr(), xdev.data_ptr(), 1e-13, 1, -1,
                                         ctypes.byref(iters), ctypes.byref(r2), ctypes.byref(rinf)))
         if record:
@@ -306,7 +333,8 @@ def run_b200(args):
         pd.GetCellData().AddArray(DataArray('v', v))
         barrier()
         t0 = time.perf_counter()
-        solver = LaplaceSolver(pd, float('inf'), 5, computeK=True, device=local)
+        solver = LaplaceSolver(pd, float('inf'), 5, computeK=True, device=local,
+                               storage=args.storage)
         rsp = solver.computeResponseField()
         torch.cuda.synchronize(dev)
         dt = time.perf_counter() - t0
@@ -328,11 +356,10 @@ def run_b200(args):
         peaks, peak_src = measured_peaks()
         off_ms = float(numpy.mean(phase['offdiag_ms']))
         gemv_ms = float(numpy.mean(phase['gemv_ms']))
-        # algorithmic flop of this rank's off-diagonal launch: symmetric block + direct columns
-        pairs_local = rows * (rows - 1) / 2.0 + rows * (n - rows)
+        # algorithmic flop of this rank's off-diagonal launch (pairs it evaluates x 256 x 18)
         flop = pairs_local * 256.0 * FLOP_PER_EVAL_GK
         achieved = flop / (off_ms * 1e-3) / 1e12
-        gemv_bytes = 8.0 * rows * n
+        gemv_bytes = 8.0 * stored     # bytes of matrix this rank streams per product
         gemv_gbs = gemv_bytes / (gemv_ms * 1e-3) / 1e9 if gemv_ms > 0 else 0.0
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
@@ -340,9 +367,11 @@ def run_b200(args):
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
             'config': {'workload': label, 'triangles': n, 'diag_order': 5, 'offdiag_order': 8,
                        'step': 'fused G+K assembly + CG solve (rel. residual 1e-13)',
-                       'rows_per_gpu': rows, 'parallelism': 'row-block x{0}'.format(world),
-                       'l2': 'inputs larger than L2 (matrix {0:.1f} GB per GPU)'.format(
-                           2 * 8.0 * rows * ld / 1e9)},
+                       'rows_per_gpu': rows, 'storage': args.storage,
+                       'parallelism': ('folded row blocks, lower storage x{0}' if lower
+                                       else 'row-block x{0}').format(world),
+                       'l2': 'inputs larger than L2 ({0:.2f} GB of G streamed per product per GPU)'.format(
+                           gemv_bytes / 1e9)},
             'phases': {'assembly_ms': float(numpy.mean(phase['assembly_ms'])),
                        'offdiag_kernel_ms': off_ms,
                        'diag_kernel_ms': float(numpy.mean(phase['diag_ms'])),
@@ -351,7 +380,9 @@ def run_b200(args):
                        'cg_iters': int(numpy.mean(phase['iters'])),
                        'cg_residual2': float(numpy.max(phase['resid'])),
                        'gemv_ms': gemv_ms, 'gemv_gbs_per_gpu': gemv_gbs,
-                       'gemv_gbs_aggregate': gemv_gbs * world},
+                       'gemv_gbs_aggregate': gemv_gbs * world,
+                       'gemv_equivalent_dense_gbs_aggregate': 8.0 * n * n / (gemv_ms * 1e-3) / 1e9
+                       if gemv_ms > 0 else 0.0},
             'roofline': {'bound': 'fp64', 'kernel': 'k_offdiag<G+K>', 'achieved': achieved,
                          'peak': peak.value, 'unit': 'TFLOP/s', 'frac': achieved / peak.value,
                          'traffic': None,
@@ -359,7 +390,8 @@ def run_b200(args):
                          'flop_per_evaluation': FLOP_PER_EVAL_GK,
                          'fp64_instr_per_evaluation': 16,
                          'issue_frac': (pairs_local * 256.0 * 16 * 2 / (off_ms * 1e-3) / 1e12) / peak.value},
-            'roofline_gemv': {'bound': 'hbm', 'kernel': 'k_gemv', 'achieved': gemv_gbs,
+            'roofline_gemv': {'bound': 'hbm', 'kernel': 'k_symv+k_symv_reduce' if lower else 'k_gemv',
+                              'achieved': gemv_gbs,
                               'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
                               'frac': gemv_gbs / peaks['hbm_gbs'], 'traffic': None,
                               'peak_source': peak_src},
@@ -392,6 +424,9 @@ def main():
     ap.add_argument('--cpu-sample', type=int, default=2400,
                     help='triangles of the CPU baseline sub-mesh (2400 -> ~9 s single core)')
     ap.add_argument('--e2e-steps', type=int, default=2)
+    ap.add_argument('--storage', default='lower', choices=['lower', 'full'],
+                    help="'lower': each pair entry stored once (mirror rule), symmetric product; "
+                         "'full': complete row blocks, row-major GEMV")
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':

@@ -32,8 +32,12 @@ SIGNATURES = [
     ('icqb_num_triangles', c_int64, [c_void_p]),
     ('icqb_set_rows', c_int, [c_void_p, c_int64, c_int64]),
     ('icqb_get_rows', c_int, [c_void_p, c_int64_p, c_int64_p]),
+    ('icqb_set_row_blocks', c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64]),
     ('icqb_area2_dev', c_uint64, [c_void_p]),
+    ('icqb_area2_host', c_int, [c_void_p, c_double_p]),
     ('icqb_assemble_dev', c_int, [c_void_p, c_int, c_uint64, c_uint64, c_int64]),
+    ('icqb_assemble_lower_dev', c_int, [c_void_p, c_int, c_uint64, c_uint64, c_uint64, c_int64]),
+    ('icqb_symv_dev', c_int, [c_void_p, c_uint64, c_int64, c_uint64, c_uint64, c_int]),
     ('icqb_assemble_host', c_int, [c_void_p, c_int, c_double_p, c_double_p]),
     ('icqb_diagonal_host', c_int, [c_void_p, c_int, c_double_p]),
     ('computeOffDiagonalTermsArrays', c_int, [c_double_p, c_int64, c_int64_p, c_int64, c_double_p]),
@@ -41,7 +45,7 @@ SIGNATURES = [
                               c_uint64, c_uint64]),
     ('icqb_gemv_host', c_int, [c_void_p, c_uint64, c_int64, c_int64, c_int64, c_double_p,
                                c_double_p]),
-    ('icqb_cg_solve_dev', c_int, [c_void_p, c_uint64, c_int64, c_int64, c_uint64, c_uint64,
+    ('icqb_cg_solve_dev', c_int, [c_void_p, c_uint64, c_int64, c_int64, c_int, c_uint64, c_uint64,
                                   c_uint64, c_uint64, c_double, c_int, c_int64, c_int64_p,
                                   c_double_p, c_double_p]),
     ('icqb_comm_unique_id', c_int, [c_void_p]),

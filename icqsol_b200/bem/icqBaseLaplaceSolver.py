@@ -5,10 +5,12 @@ Same role and accessors as the reference's ``BaseLaplaceSolver``
 (:26-27), allocates the response matrix (:29-30) and fills its diagonal and
 off-diagonal terms (:74-77); ``getGreenMatrix`` returns it (:79-84).
 
-Here the matrix lives in HBM (a torch float64 buffer, row-block sharded when
-torch.distributed is initialised: rank g owns observer rows
-[g*ceil(N/P), (g+1)*ceil(N/P)) x all N columns) and both kinds of terms are
-computed by the CUDA library (include/icqb.h).  ``getGreenMatrix()`` still
+Here the matrix lives in HBM (torch float64 buffers, sharded by observer rows over
+the ranks when torch.distributed is initialised) and both kinds of terms are
+computed by the CUDA library (include/icqb.h).  Two storages:
+'lower' (default) keeps each pair entry once -- the upper part is the reference's
+own mirror rule -- with row blocks g and 2P-1-g on rank g; 'full' keeps complete
+rows [g*ceil(N/P), (g+1)*ceil(N/P)) on rank g.  ``getGreenMatrix()`` still
 returns a ``numpy.float64[N,N]`` (materialised on demand); ``getGreenMatrixDevice()``
 returns the resident local row block.  ``getNormalDerivativeGreenMatrix()`` is
 the double-layer matrix K (not in the reference snapshot).
@@ -41,7 +43,8 @@ def leadingDimension(n):
 
 class BaseLaplaceSolver(BaseSolver):
 
-    def __init__(self, pdata, max_edge_length, order=5, computeK=False, device=None):
+    def __init__(self, pdata, max_edge_length, order=5, computeK=False, device=None,
+                 storage='lower'):
         """
         Constructor
         @param pdata polydata (vtkPolyData or stand-in)
@@ -50,8 +53,14 @@ class BaseLaplaceSolver(BaseSolver):
         @param order order of the self-term integration (1..5)
         @param computeK also assemble the double-layer matrix K
         @param device CUDA device index (default: LOCAL_RANK, else current device)
+        @param storage 'lower': block-lower-triangular, each pair entry stored once, the
+                       upper part given by the mirror rule G[j,i] = G[i,j] A_i/A_j
+                       (bem/icqLaplaceMatrices.cpp:97-98); 'full': complete row blocks
         """
         BaseSolver.__init__(self, pdata, max_edge_length, order)
+        if storage not in ('lower', 'full'):
+            raise ValueError("storage must be 'lower' or 'full'")
+        self.storage = storage
 
         torch = _requireTorchCuda()
         if device is None:
@@ -71,15 +80,27 @@ class BaseLaplaceSolver(BaseSolver):
         self.ctx.check(self.lib.icqb_set_mesh(
             self.ctx.handle, self._xyz.ctypes.data_as(_lib.c_double_p), self._xyz.shape[0],
             self._tri.ctypes.data_as(_lib.c_int64_p), n))
-        self.rowBegin, self.rowEnd = rowPartition.rowRange(n, self.rank, self.numRanks)
-        self.ctx.check(self.lib.icqb_set_rows(self.ctx.handle, self.rowBegin, self.rowEnd))
+        if storage == 'lower':
+            self.rowBlocks = rowPartition.foldedBlocks(n, self.rank, self.numRanks)
+            self.ctx.check(self.lib.icqb_set_row_blocks(self.ctx.handle, *self.rowBlocks))
+        else:
+            r0, r1 = rowPartition.rowRange(n, self.rank, self.numRanks)
+            self.rowBlocks = (r0, r1, r1, r1)
+            self.ctx.check(self.lib.icqb_set_rows(self.ctx.handle, r0, r1))
+        self.rowBegin, self.rowEnd = self.rowBlocks[0], self.rowBlocks[1]
+        self.numLocalRows = (self.rowBlocks[1] - self.rowBlocks[0]) + \
+            (self.rowBlocks[3] - self.rowBlocks[2])
 
         self.ld = leadingDimension(n)
-        rows = max(self.rowEnd - self.rowBegin, 1)
+        rows = max(self.numLocalRows, 1)
         dev = torch.device('cuda', self.device)
         self.gMatDevice = torch.empty((rows, self.ld), dtype=torch.float64, device=dev)
-        self.kMatDevice = torch.empty((rows, self.ld), dtype=torch.float64, device=dev) \
-            if computeK else None
+        self.kMatDevice = None
+        self.kMatUpperDevice = None
+        if computeK:
+            self.kMatDevice = torch.empty((rows, self.ld), dtype=torch.float64, device=dev)
+            if storage == 'lower':
+                self.kMatUpperDevice = torch.empty((rows, self.ld), dtype=torch.float64, device=dev)
         self.gMat = None   # host copy, made on demand
         self.kMat = None
 
@@ -88,18 +109,35 @@ class BaseLaplaceSolver(BaseSolver):
     def __computeResponseMatrix(self):
         # diagonal (self) terms and off-diagonal terms, one library call
         kPtr = self.kMatDevice.data_ptr() if self.kMatDevice is not None else 0
-        self.ctx.check(self.lib.icqb_assemble_dev(self.ctx.handle, int(self.order),
-                                                  self.gMatDevice.data_ptr(), kPtr, self.ld))
+        if self.storage == 'lower':
+            kuPtr = self.kMatUpperDevice.data_ptr() if self.kMatUpperDevice is not None else 0
+            self.ctx.check(self.lib.icqb_assemble_lower_dev(
+                self.ctx.handle, int(self.order), self.gMatDevice.data_ptr(), kPtr, kuPtr, self.ld))
+        else:
+            self.ctx.check(self.lib.icqb_assemble_dev(self.ctx.handle, int(self.order),
+                                                      self.gMatDevice.data_ptr(), kPtr, self.ld))
         self.ctx.check(self.lib.icqb_synchronize(self.ctx.handle))
         self.assemblyMilliseconds = {'diagonal': self.ctx.last_ms(2),
                                      'offDiagonal': self.ctx.last_ms(1),
                                      'prepare': self.ctx.last_ms(0)}
 
-    def __toHost(self, devMat):
+    def getTriangleAreas2(self):
+        """|db x dc| of every triangle (twice the area), the weights of the mirror rule."""
+        out = numpy.zeros(self.numTriangles, numpy.float64)
+        self.ctx.check(self.lib.icqb_area2_host(self.ctx.handle, out.ctypes.data_as(_lib.c_double_p)))
+        return out
+
+    def __gatherStored(self, devMat):
         n = self.numTriangles
-        rows = self.rowEnd - self.rowBegin
-        local = devMat[:rows, :n].cpu().numpy()
+        local = devMat[:self.numLocalRows, :n].cpu().numpy()
+        if self.storage == 'lower':
+            return rowPartition.gatherFoldedRows(local, n)
         return rowPartition.allGatherMatrixRows(local, n)
+
+    def __tileMask(self):
+        """True where the lower storage holds an entry: tile(col) <= tile(row)."""
+        t = numpy.arange(self.numTriangles) // rowPartition.TILE
+        return t[None, :] <= t[:, None]
 
     def getGreenMatrix(self):
         """
@@ -107,7 +145,16 @@ class BaseLaplaceSolver(BaseSolver):
         @return matrix, numpy float64[N, N]
         """
         if self.gMat is None:
-            self.gMat = self.__toHost(self.gMatDevice)
+            g = self.__gatherStored(self.gMatDevice)
+            if self.storage == 'lower':
+                # upper part by the reference's mirror rule (icqLaplaceMatrices.cpp:97-98):
+                # G[j,i] = G[i,j] * area_i / area_j
+                stored = self.__tileMask()
+                g = numpy.where(stored, g, 0.0)
+                a2 = self.getTriangleAreas2()
+                mirrored = (g * a2[:, None]).T / a2[:, None]
+                g = numpy.where(stored, g, mirrored)
+            self.gMat = g
         return self.gMat
 
     def getNormalDerivativeGreenMatrix(self):
@@ -118,41 +165,58 @@ class BaseLaplaceSolver(BaseSolver):
         if self.kMatDevice is None:
             raise RuntimeError('ERROR: K was not assembled; construct the solver with computeK=True')
         if self.kMat is None:
-            self.kMat = self.__toHost(self.kMatDevice)
+            k = self.__gatherStored(self.kMatDevice)
+            if self.storage == 'lower':
+                stored = self.__tileMask()
+                ku = self.__gatherStored(self.kMatUpperDevice)
+                k = numpy.where(stored, k, numpy.where(stored, ku, 0.0).T)
+            self.kMat = k
         return self.kMat
 
     def getGreenMatrixDevice(self):
-        """Local row block of G in HBM: torch float64[rowEnd-rowBegin, N] (a view)."""
-        return self.gMatDevice[:self.rowEnd - self.rowBegin, :self.numTriangles]
+        """Locally stored rows of G in HBM, torch float64[numLocalRows, N] (a view).
+        storage='full': rows [rowBegin, rowEnd) complete.  storage='lower': the rows of
+        getRowBlocks() one after the other, valid up to and including each row's
+        diagonal 128-column tile."""
+        return self.gMatDevice[:self.numLocalRows, :self.numTriangles]
 
     def getNormalDerivativeGreenMatrixDevice(self):
         if self.kMatDevice is None:
             raise RuntimeError('ERROR: K was not assembled; construct the solver with computeK=True')
-        return self.kMatDevice[:self.rowEnd - self.rowBegin, :self.numTriangles]
+        return self.kMatDevice[:self.numLocalRows, :self.numTriangles]
 
     def getRowRange(self):
-        """Observer rows [begin, end) owned by this rank."""
+        """First block of observer rows [begin, end) owned by this rank."""
         return self.rowBegin, self.rowEnd
+
+    def getRowBlocks(self):
+        """(r0, r1, q0, q1): this rank stores observer rows [r0,r1) and [q0,q1)."""
+        return self.rowBlocks
 
     # -- dense apply / solve on the resident matrix ---------------------------------
 
-    def _localSlice(self, vec):
+    def _toDevice(self, vec):
         torch = _requireTorchCuda()
         v = numpy.ascontiguousarray(vec, numpy.float64)
-        return torch.from_numpy(v[self.rowBegin:self.rowEnd].copy()).to(self.gMatDevice.device)
+        return torch.from_numpy(v).to(self.gMatDevice.device)
 
     def applyGreenMatrix(self, src):
-        """G . src with the GEMV kernel (numpy.dot at bem/icqPoissonSolver.py:36).
+        """G . src (numpy.dot at bem/icqPoissonSolver.py:36) on the resident matrix.
         @param src float64[N] on the host
         @return float64[N] on the host"""
         torch = _requireTorchCuda()
         n = self.numTriangles
-        rows = self.rowEnd - self.rowBegin
-        x = torch.from_numpy(numpy.ascontiguousarray(src, numpy.float64)).to(self.gMatDevice.device)
-        y = torch.empty(max(rows, 1), dtype=torch.float64, device=self.gMatDevice.device)
-        stream = self.lib.icqb_stream(self.ctx.handle)
-        self.ctx.check(self.lib.icqb_synchronize(self.ctx.handle))
+        x = self._toDevice(src)
         torch.cuda.current_stream().synchronize()
+        if self.storage == 'lower':
+            y = torch.empty(n, dtype=torch.float64, device=x.device)
+            self.ctx.check(self.lib.icqb_symv_dev(self.ctx.handle, self.gMatDevice.data_ptr(),
+                                                  self.ld, x.data_ptr(), y.data_ptr(), 0))
+            self.ctx.check(self.lib.icqb_synchronize(self.ctx.handle))
+            return y.cpu().numpy()
+        rows = self.rowEnd - self.rowBegin
+        y = torch.empty(max(rows, 1), dtype=torch.float64, device=x.device)
+        stream = self.lib.icqb_stream(self.ctx.handle)
         self.ctx.check(self.lib.icqb_gemv_dev(self.ctx.handle, self.gMatDevice.data_ptr(), rows, n,
                                               self.ld, x.data_ptr(), y.data_ptr(), 0, stream))
         self.ctx.check(self.lib.icqb_synchronize(self.ctx.handle))
@@ -165,25 +229,20 @@ class BaseLaplaceSolver(BaseSolver):
         @return x float64[N]; details in self.lastSolveInfo"""
         torch = _requireTorchCuda()
         n = self.numTriangles
-        rows = self.rowEnd - self.rowBegin
-        dev = self.gMatDevice.device
-        b = self._localSlice(rhs)
-        x = self._localSlice(x0) if x0 is not None else torch.zeros(rows, dtype=torch.float64,
-                                                                    device=dev)
-        if rows == 0:
-            b = torch.zeros(1, dtype=torch.float64, device=dev)
-            x = torch.zeros(1, dtype=torch.float64, device=dev)
+        b = self._toDevice(rhs)
+        x = self._toDevice(x0) if x0 is not None else torch.zeros(n, dtype=torch.float64,
+                                                                  device=b.device)
         torch.cuda.current_stream().synchronize()
-        area2 = self.lib.icqb_area2_dev(self.ctx.handle) + 8 * self.rowBegin
         iters = ctypes.c_int64(0)
         r2 = ctypes.c_double(0.)
         rinf = ctypes.c_double(0.)
         maxit = -1 if maxNumIters is None else int(maxNumIters)
         self.ctx.check(self.lib.icqb_cg_solve_dev(
-            self.ctx.handle, self.gMatDevice.data_ptr(), n, self.ld, area2, 0, b.data_ptr(),
-            x.data_ptr(), float(tol), 1, maxit, ctypes.byref(iters), ctypes.byref(r2),
-            ctypes.byref(rinf)))
+            self.ctx.handle, self.gMatDevice.data_ptr(), n, self.ld,
+            1 if self.storage == 'lower' else 0, self.lib.icqb_area2_dev(self.ctx.handle), 0,
+            b.data_ptr(), x.data_ptr(), float(tol), 1, maxit, ctypes.byref(iters),
+            ctypes.byref(r2), ctypes.byref(rinf)))
         self.lastSolveInfo = {'iterations': iters.value, 'residual2': r2.value,
                               'residualInf': rinf.value, 'milliseconds': self.ctx.last_ms(4),
                               'gemvMilliseconds': self.ctx.last_ms(3)}
-        return rowPartition.allGatherRows(x[:rows].cpu().numpy(), n)
+        return x.cpu().numpy()

@@ -35,6 +35,58 @@ def rowRange(n, rank, nranks):
     return r0, r1
 
 
+TILE = 128
+
+
+def foldedBlocks(n, rank, nranks):
+    """Row blocks (r0, r1, q0, q1) of ``rank`` for the block-lower-triangular storage:
+    the rows are cut into 2*nranks blocks of c = 128*ceil(n / (256*nranks)) rows and
+    rank g owns blocks g and 2*nranks-1-g.  A row of block b stores ~(b + 1/2)*c
+    columns, so every rank stores (and assembles, and streams) the same amount."""
+    n, rank, nranks = int(n), int(rank), int(nranks)
+    c = (n + 2 * nranks * TILE - 1) // (2 * nranks * TILE) * TILE
+    c = max(c, TILE)
+    b0, b1 = rank, 2 * nranks - 1 - rank
+    r0, r1 = min(n, b0 * c), min(n, (b0 + 1) * c)
+    q0, q1 = min(n, b1 * c), min(n, (b1 + 1) * c)
+    if q0 == q1:
+        q0 = q1 = r1
+    return r0, r1, q0, q1
+
+
+def foldedBlockSize(n, nranks):
+    n, nranks = int(n), int(nranks)
+    return max(TILE, (n + 2 * nranks * TILE - 1) // (2 * nranks * TILE) * TILE)
+
+
+def gatherFoldedRows(localRows, n):
+    """Stored rows float64[len0+len1, ncols] of every rank -> float64[n, ncols] in
+    global row order, on every rank."""
+    rank, nranks = worldInfo()
+    localRows = numpy.ascontiguousarray(localRows, numpy.float64)
+    if nranks == 1:
+        return localRows[:n]
+    import torch
+    import torch.distributed as dist
+    c = foldedBlockSize(n, nranks)
+    ncols = localRows.shape[1]
+    r0, r1, q0, q1 = foldedBlocks(n, rank, nranks)
+    dev = _backendDevice()
+    send = torch.zeros((2 * c, ncols), dtype=torch.float64)
+    send[:r1 - r0] = torch.from_numpy(localRows[:r1 - r0])
+    send[c:c + (q1 - q0)] = torch.from_numpy(localRows[r1 - r0:r1 - r0 + (q1 - q0)])
+    send = send.to(dev)
+    recv = torch.empty((2 * c * nranks, ncols), dtype=torch.float64, device=dev)
+    dist.all_gather_into_tensor(recv, send)
+    recv = recv.cpu().numpy()
+    out = numpy.zeros((n, ncols), numpy.float64)
+    for g in range(nranks):
+        a0, a1, b0, b1 = foldedBlocks(n, g, nranks)
+        out[a0:a1] = recv[2 * c * g:2 * c * g + (a1 - a0)]
+        out[b0:b1] = recv[2 * c * g + c:2 * c * g + c + (b1 - b0)]
+    return out
+
+
 def _backendDevice():
     import torch
     import torch.distributed as dist

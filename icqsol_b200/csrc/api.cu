@@ -21,6 +21,18 @@ __global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters) {
     out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
 }
 
+__global__ void k_reciprocal(const double* a, double* out, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x)
+        out[i] = 1.0 / a[i];
+}
+
+int launch_reciprocal(icqb_ctx* ctx, const double* a, double* out, long long n) {
+    k_reciprocal<<<128, 256, 0, ctx->stream>>>(a, out, n);
+    ctx->launches += 1;
+    return check_cuda(ctx, cudaGetLastError(), "k_reciprocal launch");
+}
+
 int finish_phase(icqb_ctx* ctx, int phase) {
     ICQB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     float ms = 0;
@@ -55,6 +67,63 @@ int icqb_assemble_dev(icqb_ctx* ctx, int diag_order, uint64_t dG, uint64_t dK, i
     int st = launch_offdiag(ctx, G, K, ld);
     if (st != ICQB_OK) return st;
     return finish_phase(ctx, kOffDiag);
+}
+
+int icqb_assemble_lower_dev(icqb_ctx* ctx, int diag_order, uint64_t dG, uint64_t dKl, uint64_t dKu,
+                            int64_t ld) {
+    if (!ctx) return ICQB_EARG;
+    if (ctx->ntri == 0) return ICQB_OK;
+    if (!ctx->d_qp_aos) return set_error(ctx, ICQB_ESTATE, "icqb_assemble_lower_dev: no mesh set");
+    if (!dG || ld < ctx->ntri || (ld & 1))
+        return set_error(ctx, ICQB_EARG, "icqb_assemble_lower_dev: null G, ld < ntri or odd ld");
+    if ((dKl == 0) != (dKu == 0))
+        return set_error(ctx, ICQB_EARG, "icqb_assemble_lower_dev: pass both K buffers or neither");
+    if (diag_order != 0 && (diag_order < 1 || diag_order > 5))
+        return set_error(ctx, ICQB_EORDER,
+                         "diagonal order must be in 1..5 (KeyError in the reference)");
+    ICQB_CUDA(ctx, cudaSetDevice(ctx->device));
+    double* G = reinterpret_cast<double*>(dG);
+    if (diag_order != 0) {
+        cudaEventRecord(ctx->ev0, ctx->stream);
+        int st = launch_diag_rows(ctx, diag_order, ctx->r0, ctx->r1, G + ctx->r0, ld + 1);
+        if (st == ICQB_OK)
+            st = launch_diag_rows(ctx, diag_order, ctx->q0, ctx->q1,
+                                  G + (ctx->r1 - ctx->r0) * ld + ctx->q0, ld + 1);
+        cudaEventRecord(ctx->ev1, ctx->stream);
+        if (st != ICQB_OK) return st;
+        st = finish_phase(ctx, kDiag);
+        if (st != ICQB_OK) return st;
+    }
+    int st = launch_offdiag_lower(ctx, G, reinterpret_cast<double*>(dKl),
+                                  reinterpret_cast<double*>(dKu), ld);
+    if (st != ICQB_OK) return st;
+    return finish_phase(ctx, kOffDiag);
+}
+
+int icqb_symv_dev(icqb_ctx* ctx, uint64_t dA, int64_t ld, uint64_t dx, uint64_t dy, int scaled) {
+    if (!ctx) return ICQB_EARG;
+    if (!dA || !dx || !dy) return set_error(ctx, ICQB_EARG, "icqb_symv_dev: null pointer");
+    if (!ctx->d_area2) return set_error(ctx, ICQB_ESTATE, "icqb_symv_dev: no mesh set");
+    ICQB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int64_t n = ctx->ntri;
+    double* inv = nullptr;
+    if (!scaled) {
+        int st = ensure_work(ctx, n + 64);
+        if (st != ICQB_OK) return st;
+        inv = ctx->d_work;
+        st = launch_reciprocal(ctx, ctx->d_area2, inv, n);
+        if (st != ICQB_OK) return st;
+    }
+    cudaEventRecord(ctx->ev0, ctx->stream);
+    int st = launch_symv(ctx, reinterpret_cast<const double*>(dA), ld,
+                         reinterpret_cast<const double*>(dx), ctx->d_area2,
+                         scaled ? ctx->d_area2 : nullptr, scaled ? nullptr : inv,
+                         reinterpret_cast<double*>(dy), ctx->stream);
+    cudaEventRecord(ctx->ev1, ctx->stream);
+    if (st != ICQB_OK) return st;
+    st = comm_allreduce_sum(ctx, reinterpret_cast<double*>(dy), n, ctx->stream);
+    if (st != ICQB_OK) return st;
+    return finish_phase(ctx, kGemv);
 }
 
 int icqb_assemble_host(icqb_ctx* ctx, int diag_order, double* gMat, double* kMat) {
@@ -114,6 +183,15 @@ int computeOffDiagonalTermsArrays(const double* xyz, int64_t npts, const int64_t
     if (st != ICQB_OK) set_error(nullptr, st, ctx->err);
     icqb_destroy(ctx);
     return st;
+}
+
+int icqb_area2_host(icqb_ctx* ctx, double* out) {
+    if (!ctx || !out) return ICQB_EARG;
+    if (ctx->ntri == 0) return ICQB_OK;
+    ICQB_CUDA(ctx, cudaSetDevice(ctx->device));
+    ICQB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ICQB_CUDA(ctx, cudaMemcpy(out, ctx->d_area2, sizeof(double) * ctx->ntri, cudaMemcpyDeviceToHost));
+    return ICQB_OK;
 }
 
 int icqb_gemv_dev(icqb_ctx* ctx, uint64_t dA, int64_t nrows, int64_t ncols, int64_t ld,

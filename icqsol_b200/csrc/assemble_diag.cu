@@ -92,18 +92,25 @@ __global__ void __launch_bounds__(128) k_diag(const double* __restrict__ verts, 
 
 }  // namespace
 
-int launch_diag(icqb_ctx* ctx, int order, double* dOut, int64_t stride) {
+// self terms of global rows [g0, g1): out[(t - g0)*stride]
+int launch_diag_rows(icqb_ctx* ctx, int order, long long g0, long long g1, double* dOut,
+                     int64_t stride) {
     if (order < 1 || order > kLineMaxOrder)
         return set_error(ctx, ICQB_EORDER, "diagonal order must be in 1..5 (KeyError in the reference)");
-    const long long rows = ctx->r1 - ctx->r0;
+    const long long rows = g1 - g0;
     if (rows <= 0) return ICQB_OK;
     const int threads = 128;
     const unsigned blocks = (unsigned)((rows * 8 + threads - 1) / threads);
-    cudaEventRecord(ctx->ev0, ctx->stream);
-    k_diag<<<blocks, threads, 0, ctx->stream>>>(ctx->d_verts, ctx->r0, ctx->r1, order, dOut, stride);
-    cudaEventRecord(ctx->ev1, ctx->stream);
+    k_diag<<<blocks, threads, 0, ctx->stream>>>(ctx->d_verts, g0, g1, order, dOut, stride);
     ctx->launches += 1;
     return check_cuda(ctx, cudaGetLastError(), "k_diag launch");
+}
+
+int launch_diag(icqb_ctx* ctx, int order, double* dOut, int64_t stride) {
+    cudaEventRecord(ctx->ev0, ctx->stream);
+    const int st = launch_diag_rows(ctx, order, ctx->r0, ctx->r1, dOut, stride);
+    cudaEventRecord(ctx->ev1, ctx->stream);
+    return st;
 }
 
 }  // namespace icqb

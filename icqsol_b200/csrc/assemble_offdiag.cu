@@ -47,10 +47,14 @@ struct OffDiagParams {
     const double* verts;    // [ntri][9]
     double* G;
     double* K;
+    double* Ku;             // lower mode only: Ku[i,j] = K[j,i] at the position of (i,j)
     long long ld;
     long long n, npad;
-    long long r0, r1;
-    long long nObsTiles, nLeft, nRight;  // tile counts: local rows, columns < r0, columns >= r1
+    long long r0, r1;       // full mode: the row block; lower mode: first row block
+    long long q0, q1;       // lower mode: second row block (may be empty)
+    long long nObsTiles, nLeft, nRight;  // full mode tile counts: local rows, columns < r0, >= r1
+    long long nTiles0;      // lower mode: observer tiles of the first block
+    int lower;              // 1 = block-lower-triangular storage
 };
 
 __device__ __forceinline__ double rsqrt_1ulp(double x) {
@@ -110,13 +114,35 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 // left and right of it.
 struct Tile {
     long long obs0;   // first observer triangle (global index)
+    long long obsEnd; // one past the last observer triangle of the row block
+    long long lrow0;  // local (storage) row of obs0
     long long src0;   // first source triangle
     long long srcEnd; // one past the last valid source triangle of this tile's range
-    int kind;         // 0 = diagonal tile, 1 = mirrored (I > J inside the block), 2 = direct only
+    int kind;         // 0 = diagonal tile, 1 = mirrored (I > J inside the block), 2 = direct only,
+                      // 3 = lower storage, strictly below the diagonal tile
+                      // -1 = nothing to do
 };
 
 __device__ __forceinline__ Tile decode_tile(const OffDiagParams& P, long long task) {
     Tile t;
+    if (P.lower) {
+        // 2-D grid: x = global source tile J, y = local observer tile; only J <= I is stored
+        const long long lt = blockIdx.y;
+        if (lt < P.nTiles0) {
+            t.obs0 = P.r0 + lt * kTileObs;
+            t.obsEnd = P.r1;
+            t.lrow0 = lt * kTileObs;
+        } else {
+            t.obs0 = P.q0 + (lt - P.nTiles0) * kTileObs;
+            t.obsEnd = P.q1;
+            t.lrow0 = (P.r1 - P.r0) + (lt - P.nTiles0) * kTileObs;
+        }
+        const long long I = t.obs0 / kTileObs, J = blockIdx.x;
+        t.src0 = J * kTileSrc;
+        t.srcEnd = (J == I) ? min(P.n, t.src0 + kTileSrc) : t.src0 + kTileSrc;
+        t.kind = (J > I) ? -1 : (J == I ? 0 : 3);
+        return t;
+    }
     const long long nT = P.nObsTiles;
     const long long nTri = nT * (nT + 1) / 2;
     if (task < nTri) {
@@ -126,6 +152,8 @@ __device__ __forceinline__ Tile decode_tile(const OffDiagParams& P, long long ta
         while ((I + 1) * (I + 2) / 2 <= task) ++I;
         long long J = task - I * (I + 1) / 2;
         t.obs0 = P.r0 + I * kTileObs;
+        t.obsEnd = P.r1;
+        t.lrow0 = I * kTileObs;
         t.src0 = P.r0 + J * kTileSrc;
         t.srcEnd = P.r1;
         t.kind = (I == J) ? 0 : 1;
@@ -135,6 +163,8 @@ __device__ __forceinline__ Tile decode_tile(const OffDiagParams& P, long long ta
     const long long nSide = P.nLeft + P.nRight;
     long long I = task / nSide, J = task - I * nSide;
     t.obs0 = P.r0 + I * kTileObs;
+    t.obsEnd = P.r1;
+    t.lrow0 = I * kTileObs;
     t.kind = 2;
     if (J < P.nLeft) {
         t.src0 = J * kTileSrc;
@@ -153,6 +183,7 @@ __global__ void __launch_bounds__(kTileObs) k_offdiag(const OffDiagParams P) {
 
     const int tid = threadIdx.x;
     const Tile T = decode_tile(P, blockIdx.x);
+    if (T.kind < 0) return;  // lower storage: tile above the diagonal (whole CTA exits)
 
     if (tid == 0) {
         mbar_init(&s_bar[0], 1);
@@ -178,8 +209,8 @@ __global__ void __launch_bounds__(kTileObs) k_offdiag(const OffDiagParams P) {
 
     // observer triangle of this thread
     const long long iObs = T.obs0 + tid;
-    const bool obsValid = iObs < P.r1;
-    const long long iLoad = obsValid ? iObs : (P.r1 - 1);
+    const bool obsValid = iObs < T.obsEnd;
+    const long long iLoad = obsValid ? iObs : (T.obsEnd - 1);
     double ox[kNq], oy[kNq], oz[kNq];
 #pragma unroll
     for (int k = 0; k < kNq; ++k) {
@@ -201,8 +232,11 @@ __global__ void __launch_bounds__(kTileObs) k_offdiag(const OffDiagParams P) {
         paz = __ldg(P.verts + 9 * iLoad + 2);
     }
 
-    double* gRow = P.G + (iLoad - P.r0) * P.ld;
-    double* kRow = WITH_K ? (P.K + (iLoad - P.r0) * P.ld) : nullptr;
+    // storage row of this observer (clamped lanes never store)
+    const long long lrow = T.lrow0 + (obsValid ? tid : 0);
+    double* gRow = P.G + lrow * P.ld;
+    double* kRow = WITH_K ? (P.K + lrow * P.ld) : nullptr;
+    double* kuRow = (WITH_K && P.lower) ? (P.Ku + lrow * P.ld) : nullptr;
 
     for (int sub = 0; sub < nSubTiles; ++sub) {
         const int stage = sub & 1;
@@ -284,9 +318,11 @@ __global__ void __launch_bounds__(kTileObs) k_offdiag(const OffDiagParams P) {
                     }
                     kRow[j] = (cG * a2Src) * accK;
                     if (T.kind == 1) P.K[(j - P.r0) * P.ld + iObs] = (cG * a2Obs) * accKm;
+                    if (P.lower) kuRow[j] = (cG * a2Obs) * accKm;   // K[j,i] kept next to K[i,j]
                 }
             } else if (obsValid && WITH_K) {
                 kRow[j] = 0.0;  // K[i,i] = 0 (flat panel, principal value)
+                if (P.lower) kuRow[j] = 0.0;
             }
         }
 
@@ -305,9 +341,53 @@ __global__ void __launch_bounds__(kTileObs) k_offdiag(const OffDiagParams P) {
 
 }  // namespace
 
+int launch_offdiag_lower(icqb_ctx* ctx, double* dG, double* dK, double* dKu, int64_t ld) {
+    if (ctx->ntri == 0) return ICQB_OK;
+    OffDiagParams P;
+    P.qp_soa = ctx->d_qp_soa;
+    P.qp_aos = ctx->d_qp_aos;
+    P.area2 = ctx->d_area2;
+    P.nrm = ctx->d_nrm;
+    P.verts = ctx->d_verts;
+    P.G = dG;
+    P.K = dK;
+    P.Ku = dKu;
+    P.ld = ld;
+    P.n = ctx->ntri;
+    P.npad = ctx->ntri_pad;
+    P.r0 = ctx->r0;
+    P.r1 = ctx->r1;
+    P.q0 = ctx->q0;
+    P.q1 = ctx->q1;
+    P.nObsTiles = P.nLeft = P.nRight = 0;
+    P.lower = 1;
+    if ((P.r1 > P.r0 && (P.r0 % kTileObs) != 0) || (P.q1 > P.q0 && (P.q0 % kTileObs) != 0))
+        return set_error(ctx, ICQB_EARG, "lower storage: row blocks must start on multiples of 128");
+    P.nTiles0 = (P.r1 - P.r0 + kTileObs - 1) / kTileObs;
+    const long long nTiles1 = (P.q1 - P.q0 + kTileObs - 1) / kTileObs;
+    const long long lastRow = (P.q1 > P.q0) ? P.q1 : P.r1;
+    const long long nLocal = P.nTiles0 + nTiles1;
+    if (nLocal == 0) return ICQB_OK;
+    const long long nSrcTiles = (lastRow + kTileSrc - 1) / kTileSrc;   // J <= I for every local I
+    if (nLocal > 65535) return set_error(ctx, ICQB_EARG, "too many observer tiles for one launch");
+    dim3 grid((unsigned)nSrcTiles, (unsigned)nLocal);
+    cudaEventRecord(ctx->ev0, ctx->stream);
+    if (dK)
+        k_offdiag<true><<<grid, kTileObs, 0, ctx->stream>>>(P);
+    else
+        k_offdiag<false><<<grid, kTileObs, 0, ctx->stream>>>(P);
+    cudaEventRecord(ctx->ev1, ctx->stream);
+    ctx->launches += 1;
+    return check_cuda(ctx, cudaGetLastError(), "k_offdiag(lower) launch");
+}
+
 int launch_offdiag(icqb_ctx* ctx, double* dG, double* dK, int64_t ld) {
     if (ctx->ntri == 0 || ctx->r1 <= ctx->r0) return ICQB_OK;
     OffDiagParams P;
+    P.Ku = nullptr;
+    P.q0 = P.q1 = 0;
+    P.nTiles0 = 0;
+    P.lower = 0;
     P.qp_soa = ctx->d_qp_soa;
     P.qp_aos = ctx->d_qp_aos;
     P.area2 = ctx->d_area2;

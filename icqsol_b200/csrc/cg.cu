@@ -28,14 +28,16 @@ namespace {
 constexpr int kNB = 128;       // blocks of every vector kernel == partials per dot product
 constexpr int kVT = 256;       // threads per block
 
+// every vector is full length (n) and replicated on all ranks: the ranks execute the
+// same vector kernels on identical data, only the matrix product is distributed
 struct CgBuf {
-    double *pfull, *xfull, *r, *w, *z, *minv, *s;
+    double *p, *r, *w, *z, *minv, *s, *d;
     double *pz;        // [kNB]
     double *rw;        // [2][kNB]
     double *res;       // [kNB]  sum (r/s)^2  (recurrence residual of the unscaled system)
     double *tru;       // [kNB]  sum (b - A x)^2
     double *bb;        // [kNB]  sum b^2
-    double *mx;        // [nranks] max |b - A x| per rank
+    double *mx;        // [kNB]  max |b - A x| per block
 };
 
 __device__ __forceinline__ double block_sum(double v, double* s_red) {
@@ -73,24 +75,30 @@ __device__ __forceinline__ double sum_partials(const double* part) {
     return t;
 }
 
-// r = s*(b - A x0) given z = s*(A x0); minv = 1/(s*precond); w = r*minv; p = 0
-__global__ void __launch_bounds__(kVT) k_cg_init(long long m, long long r0, const double* A,
-                                                 long long ld, const double* b,
+// diag(A) of the locally stored rows into a zeroed full-length vector
+__global__ void __launch_bounds__(kVT) k_cg_diag(const double* A, long long ld, long long g0,
+                                                 long long g1, long long lrow0, double* d) {
+    for (long long i = g0 + (long long)blockIdx.x * kVT + threadIdx.x; i < g1;
+         i += (long long)kNB * kVT)
+        d[i] = A[(lrow0 + (i - g0)) * ld + i];
+}
+
+// r = s*b - z (z = s*(A x0)); minv = 1/(s*precond); w = r*minv; p = 0
+__global__ void __launch_bounds__(kVT) k_cg_init(long long n, const double* b,
                                                  const double* scale, const double* precond,
                                                  CgBuf B) {
     __shared__ double s_red[kVT / 32];
     double rw = 0.0, rs = 0.0, bb = 0.0;
-    for (long long i = (long long)blockIdx.x * kVT + threadIdx.x; i < m; i += (long long)kNB * kVT) {
+    for (long long i = (long long)blockIdx.x * kVT + threadIdx.x; i < n; i += (long long)kNB * kVT) {
         const double s = scale ? scale[i] : 1.0;
-        const double d = precond ? precond[i] : A[i * ld + r0 + i];
         const double r = s * b[i] - B.z[i];
-        const double mi = 1.0 / (s * d);
+        const double mi = 1.0 / (s * precond[i]);
         const double w = r * mi;
         B.s[i] = s;
         B.minv[i] = mi;
         B.r[i] = r;
         B.w[i] = w;
-        B.pfull[r0 + i] = 0.0;
+        B.p[i] = 0.0;
         rw = fma(r, w, rw);
         const double ru = r / s;
         rs = fma(ru, ru, rs);
@@ -105,33 +113,32 @@ __global__ void __launch_bounds__(kVT) k_cg_init(long long m, long long r0, cons
 }
 
 // p = w + beta p, beta = rho_k / rho_{k-1} (0 on the first iteration)
-__global__ void __launch_bounds__(kVT) k_cg_dir(long long m, long long r0, int k, CgBuf B) {
+__global__ void __launch_bounds__(kVT) k_cg_dir(long long n, int k, CgBuf B) {
     double beta = 0.0;
     if (k > 0) beta = sum_partials(B.rw + (k & 1) * kNB) / sum_partials(B.rw + ((k - 1) & 1) * kNB);
-    for (long long i = (long long)blockIdx.x * kVT + threadIdx.x; i < m; i += (long long)kNB * kVT)
-        B.pfull[r0 + i] = fma(beta, B.pfull[r0 + i], B.w[i]);
+    for (long long i = (long long)blockIdx.x * kVT + threadIdx.x; i < n; i += (long long)kNB * kVT)
+        B.p[i] = fma(beta, B.p[i], B.w[i]);
 }
 
-// partial p.z over the local rows
-__global__ void __launch_bounds__(kVT) k_cg_dot(long long m, long long r0, CgBuf B) {
+// partial p.z
+__global__ void __launch_bounds__(kVT) k_cg_dot(long long n, CgBuf B) {
     __shared__ double s_red[kVT / 32];
     double acc = 0.0;
-    for (long long i = (long long)blockIdx.x * kVT + threadIdx.x; i < m; i += (long long)kNB * kVT)
-        acc = fma(B.pfull[r0 + i], B.z[i], acc);
+    for (long long i = (long long)blockIdx.x * kVT + threadIdx.x; i < n; i += (long long)kNB * kVT)
+        acc = fma(B.p[i], B.z[i], acc);
     const double t = block_sum(acc, s_red);
     if (threadIdx.x == 0) B.pz[blockIdx.x] = t;
 }
 
 // alpha = rho_k / (p.z); x += alpha p; r -= alpha z; w = r/M; partial rho_{k+1}, |r/s|^2
-__global__ void __launch_bounds__(kVT) k_cg_update(long long m, long long r0, int k, double* x,
-                                                   CgBuf B) {
+__global__ void __launch_bounds__(kVT) k_cg_update(long long n, int k, double* x, CgBuf B) {
     __shared__ double s_red[kVT / 32];
     const double alpha = sum_partials(B.rw + (k & 1) * kNB) / sum_partials(B.pz);
     double rw = 0.0, rs = 0.0;
-    for (long long i = (long long)blockIdx.x * kVT + threadIdx.x; i < m; i += (long long)kNB * kVT) {
+    for (long long i = (long long)blockIdx.x * kVT + threadIdx.x; i < n; i += (long long)kNB * kVT) {
         const double r = fma(-alpha, B.z[i], B.r[i]);
         const double w = r * B.minv[i];
-        x[i] = fma(alpha, B.pfull[r0 + i], x[i]);
+        x[i] = fma(alpha, B.p[i], x[i]);
         B.r[i] = r;
         B.w[i] = w;
         rw = fma(r, w, rw);
@@ -145,11 +152,11 @@ __global__ void __launch_bounds__(kVT) k_cg_update(long long m, long long r0, in
 }
 
 // true residual t = b - A x given z = A x (unscaled); optionally replace r, w, rho
-__global__ void __launch_bounds__(kVT) k_cg_true(long long m, int rank, int nranks, int replace,
-                                                 int knext, const double* b, CgBuf B) {
+__global__ void __launch_bounds__(kVT) k_cg_true(long long n, int replace, int knext,
+                                                 const double* b, CgBuf B) {
     __shared__ double s_red[kVT / 32];
     double tt = 0.0, mx = 0.0, rw = 0.0;
-    for (long long i = (long long)blockIdx.x * kVT + threadIdx.x; i < m; i += (long long)kNB * kVT) {
+    for (long long i = (long long)blockIdx.x * kVT + threadIdx.x; i < n; i += (long long)kNB * kVT) {
         const double t = b[i] - B.z[i];
         tt = fma(t, t, tt);
         mx = fmax(mx, fabs(t));
@@ -168,16 +175,13 @@ __global__ void __launch_bounds__(kVT) k_cg_true(long long m, int rank, int nran
         if (threadIdx.x == 0) B.rw[(knext & 1) * kNB + blockIdx.x] = t;
     }
     t = block_max(mx, s_red);
-    if (threadIdx.x == 0) {
-        // per-rank maxima live in a [nranks] array that is sum-all-reduced:
-        // a rank only ever contributes to its own slot
-        if (blockIdx.x == 0)
-            for (int q = 0; q < nranks; ++q)
-                if (q != rank) B.mx[q] = 0.0;
-        // combine blocks through an ordered integer max (values are >= 0)
-        atomicMax(reinterpret_cast<unsigned long long*>(B.mx + rank),
-                  (unsigned long long)__double_as_longlong(t));
-    }
+    if (threadIdx.x == 0) B.mx[blockIdx.x] = t;
+}
+
+__global__ void k_recip(const double* a, double* out, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x)
+        out[i] = 1.0 / a[i];
 }
 
 __global__ void k_zero(double* p, long long n) {
@@ -188,37 +192,66 @@ __global__ void k_zero(double* p, long long n) {
 
 }  // namespace
 
-// full[off .. off+m) = local, then all-gather the chunk-sized slots in place
-static int gather_local(icqb_ctx* ctx, const double* local, long long m, double* full,
-                        long long off, long long chunk, cudaStream_t st) {
-    if (m > 0)
-        ICQB_CUDA(ctx, cudaMemcpyAsync(full + off, local, sizeof(double) * m,
-                                       cudaMemcpyDeviceToDevice, st));
-    if (comm_nranks(ctx) > 1) return comm_allgather(ctx, full + off, full, chunk, st);
-    return ICQB_OK;
-}
-
-static int read_sum(icqb_ctx* ctx, const double* dpart, int count, double* out) {
+static int read_partials(icqb_ctx* ctx, const double* dpart, int count, bool take_max,
+                         double* out) {
     ICQB_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, dpart, sizeof(double) * count,
                                    cudaMemcpyDeviceToHost, ctx->stream));
     ICQB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     double t = 0.0;
-    for (int k = 0; k < count; ++k) t += ctx->h_pinned[k];
+    for (int k = 0; k < count; ++k) t = take_max ? std::max(t, ctx->h_pinned[k]) : t + ctx->h_pinned[k];
     *out = t;
     return ICQB_OK;
 }
+
+// The distributed product: out = diag(scale) A v on every rank (scale may be null).
+//   storage 0: rank g multiplies its row block and the slices are all-gathered;
+//   storage 1: block-lower-triangular rows, symmetric product, partial vectors all-reduced.
+struct MatVec {
+    icqb_ctx* ctx;
+    const double* A;
+    long long n, ld;
+    int storage;
+    long long r0, r1, chunk;   // storage 0: this rank's rows and the all-gather slot size
+    const double* area;        // storage 1: |db x dc| (mirror rule weights), full length
+    const double* inv_area;    // storage 1: 1/area (for the unscaled product)
+    double* gathered;          // storage 0: [nranks*chunk] staging for the all-gather
+
+    // scaled != 0: out = diag(area or scale) A v ; scaled == 0: out = A v
+    int apply(const double* v, double* out, const double* scale, cudaStream_t st) {
+        int rc;
+        if (storage == 1) {
+            rc = launch_symv(ctx, A, ld, v, area, scale ? area : nullptr,
+                             scale ? nullptr : inv_area, out, st);
+            if (rc != ICQB_OK) return rc;
+            return comm_allreduce_sum(ctx, out, n, st);
+        }
+        const int P = comm_nranks(ctx);
+        double* dst = (P == 1) ? out : gathered + (long long)comm_rank(ctx) * chunk;
+        rc = launch_gemv(ctx, A, r1 - r0, n, ld, v, dst, scale ? scale + r0 : nullptr, st);
+        if (rc != ICQB_OK || P == 1) return rc;
+        rc = comm_allgather(ctx, dst, gathered, chunk, st);
+        if (rc != ICQB_OK) return rc;
+        return check_cuda(ctx, cudaMemcpyAsync(out, gathered, sizeof(double) * n,
+                                               cudaMemcpyDeviceToDevice, st), "gather copy");
+    }
+};
 
 }  // namespace icqb
 
 using namespace icqb;
 
-extern "C" int icqb_cg_solve_dev(icqb_ctx* ctx, uint64_t dA_, int64_t n, int64_t ld,
+extern "C" int icqb_cg_solve_dev(icqb_ctx* ctx, uint64_t dA_, int64_t n, int64_t ld, int storage,
                                  uint64_t drowscale_, uint64_t dprecond_, uint64_t db_,
                                  uint64_t dx_, double tol, int rel, int64_t maxit, int64_t* iters,
                                  double* resid2, double* residinf) {
     if (!ctx) return ICQB_EARG;
     if (!dA_ || !db_ || !dx_ || n <= 0 || ld < n)
         return set_error(ctx, ICQB_EARG, "icqb_cg_solve_dev: null pointer or bad sizes");
+    if (storage != 0 && storage != 1)
+        return set_error(ctx, ICQB_EARG, "icqb_cg_solve_dev: storage must be 0 (row blocks) or 1 (lower)");
+    if (storage == 1 && (ctx->ntri != n || !ctx->d_area2))
+        return set_error(ctx, ICQB_ESTATE,
+                         "icqb_cg_solve_dev: lower storage needs the mesh of this matrix in the context");
     ICQB_CUDA(ctx, cudaSetDevice(ctx->device));
     const double* A = reinterpret_cast<const double*>(dA_);
     const double* scale = reinterpret_cast<const double*>(drowscale_);
@@ -227,33 +260,47 @@ extern "C" int icqb_cg_solve_dev(icqb_ctx* ctx, uint64_t dA_, int64_t n, int64_t
     double* x = reinterpret_cast<double*>(dx_);
     const int P = comm_nranks(ctx), rank = comm_rank(ctx);
     const long long chunk = (n + P - 1) / P;
-    const long long r0 = std::min<long long>(n, (long long)rank * chunk);
-    const long long r1 = std::min<long long>(n, r0 + chunk);
-    const long long m = r1 - r0;
-    const long long off = (long long)rank * chunk;  // slot of this rank in the gathered vectors
     if (maxit < 0) maxit = n;
     cudaStream_t st = ctx->stream;
 
     // work space
     const long long nfull = chunk * P;
-    const long long need = 2 * nfull + 5 * chunk + 6 * kNB + P + 64;
+    const long long need = 8 * n + nfull + 7 * kNB + 64;
     int rc = ensure_work(ctx, need);
     if (rc != ICQB_OK) return rc;
     CgBuf B;
     double* wp = ctx->d_work;
-    B.pfull = wp; wp += nfull;
-    B.xfull = wp; wp += nfull;
-    B.r = wp; wp += chunk;
-    B.w = wp; wp += chunk;
-    B.z = wp; wp += chunk;
-    B.minv = wp; wp += chunk;
-    B.s = wp; wp += chunk;
+    B.p = wp; wp += n;
+    B.r = wp; wp += n;
+    B.w = wp; wp += n;
+    B.z = wp; wp += n;
+    B.minv = wp; wp += n;
+    B.s = wp; wp += n;
+    B.d = wp; wp += n;
+    double* inv_area = wp; wp += n;
+    double* gathered = wp; wp += nfull;
     B.pz = wp; wp += kNB;
     B.rw = wp; wp += 2 * kNB;
     B.res = wp; wp += kNB;
     B.tru = wp; wp += kNB;
     B.bb = wp; wp += kNB;
-    B.mx = wp; wp += P;
+    B.mx = wp; wp += kNB;
+
+    MatVec mv;
+    mv.ctx = ctx;
+    mv.A = A;
+    mv.n = n;
+    mv.ld = ld;
+    mv.storage = storage;
+    mv.chunk = chunk;
+    mv.r0 = std::min<long long>(n, (long long)rank * chunk);
+    mv.r1 = std::min<long long>(n, mv.r0 + chunk);
+    mv.area = ctx->d_area2;
+    mv.inv_area = inv_area;
+    mv.gathered = gathered;
+    if (storage == 1 && scale && scale != ctx->d_area2)
+        return set_error(ctx, ICQB_EARG,
+                         "icqb_cg_solve_dev: with lower storage the row scaling must be icqb_area2_dev()");
 
     cudaEvent_t evTotal0 = ctx->ev0, evTotal1 = ctx->ev1;
     cudaEvent_t evg0, evg1;
@@ -271,73 +318,67 @@ extern "C" int icqb_cg_solve_dev(icqb_ctx* ctx, uint64_t dA_, int64_t n, int64_t
 
     {
         CG_CUDA(cudaEventRecord(evTotal0, st));
-        k_zero<<<kNB, kVT, 0, st>>>(B.pfull, 2 * nfull + 5 * chunk + 6 * kNB + P);
+        k_zero<<<kNB, kVT, 0, st>>>(ctx->d_work, need);
         ctx->launches += 1;
+        if (storage == 1) {
+            k_recip<<<kNB, kVT, 0, st>>>(ctx->d_area2, inv_area, n);
+            ctx->launches += 1;
+        }
+        // preconditioner: diag(A) unless given
+        if (!precond) {
+            if (storage == 1) {
+                if (ctx->r1 > ctx->r0)
+                    k_cg_diag<<<kNB, kVT, 0, st>>>(A, ld, ctx->r0, ctx->r1, 0, B.d);
+                if (ctx->q1 > ctx->q0)
+                    k_cg_diag<<<kNB, kVT, 0, st>>>(A, ld, ctx->q0, ctx->q1, ctx->r1 - ctx->r0, B.d);
+            } else if (mv.r1 > mv.r0) {
+                k_cg_diag<<<kNB, kVT, 0, st>>>(A, ld, mv.r0, mv.r1, 0, B.d);
+            }
+            ctx->launches += 2;
+            CG_TRY(comm_allreduce_sum(ctx, B.d, n, st));
+            precond = B.d;
+        }
         // z = s * (A x0)
-        CG_TRY(gather_local(ctx, x, m, B.xfull, off, chunk, st));
-        CG_TRY(launch_gemv(ctx, A, m, n, ld, B.xfull, B.z, scale, st));
-        k_cg_init<<<kNB, kVT, 0, st>>>(m, r0, A, ld, b, scale, precond, B);
+        CG_TRY(mv.apply(x, B.z, scale, st));
+        k_cg_init<<<kNB, kVT, 0, st>>>(n, b, scale, precond, B);
         ctx->launches += 1;
         CG_CUDA(cudaGetLastError());
-        CG_TRY(comm_allreduce_sum(ctx, B.rw, 2 * kNB + kNB, st));       // rw[0..1], res (contiguous)
-        CG_TRY(comm_allreduce_sum(ctx, B.bb, kNB, st));
 
         double res2 = 0.0, bb = 0.0;
-        CG_TRY(read_sum(ctx, B.res, kNB, &res2));
-        CG_TRY(read_sum(ctx, B.bb, kNB, &bb));
+        CG_TRY(read_partials(ctx, B.res, kNB, false, &res2));
+        CG_TRY(read_partials(ctx, B.bb, kNB, false, &bb));
         const double thr = rel ? tol * sqrt(bb) : tol;
         double err = sqrt(res2);
         long long k = 0;
         int replacements = 0;
-        bool converged = false;
         double true2 = err, trueinf = 0.0;
 
         while (true) {
             if (err <= thr || k >= maxit) {
                 // confirm with the true residual b - A x (and stop, or replace r)
-                CG_TRY(gather_local(ctx, x, m, B.xfull, off, chunk, st));
-                CG_TRY(launch_gemv(ctx, A, m, n, ld, B.xfull, B.z, nullptr, st));
+                CG_TRY(mv.apply(x, B.z, nullptr, st));
                 const bool last = (k >= maxit) || replacements >= 8;
-                k_cg_true<<<kNB, kVT, 0, st>>>(m, rank, P, last ? 0 : 1, (int)(k & 1), b, B);
+                k_cg_true<<<kNB, kVT, 0, st>>>(n, last ? 0 : 1, (int)(k & 1), b, B);
                 ctx->launches += 1;
                 CG_CUDA(cudaGetLastError());
-                CG_TRY(comm_allreduce_sum(ctx, B.tru, kNB, st));
-                CG_TRY(comm_allreduce_sum(ctx, B.mx, P, st));
-                if (!last) CG_TRY(comm_allreduce_sum(ctx, B.rw + (k & 1) * kNB, kNB, st));
                 double t2 = 0.0;
-                CG_TRY(read_sum(ctx, B.tru, kNB, &t2));
-                CG_CUDA(cudaMemcpyAsync(ctx->h_pinned, B.mx, sizeof(double) * P,
-                                        cudaMemcpyDeviceToHost, st));
-                CG_CUDA(cudaStreamSynchronize(st));
-                trueinf = 0.0;
-                for (int q = 0; q < P; ++q) trueinf = std::max(trueinf, ctx->h_pinned[q]);
+                CG_TRY(read_partials(ctx, B.tru, kNB, false, &t2));
+                CG_TRY(read_partials(ctx, B.mx, kNB, true, &trueinf));
                 true2 = sqrt(t2);
-                // reset the per-rank max slot for a later pass
-                k_zero<<<1, 32, 0, st>>>(B.mx, P);
-                ctx->launches += 1;
-                if (true2 <= thr) converged = true;
-                if (converged || last) break;
+                if (true2 <= thr || last) break;
                 ++replacements;
                 err = true2;  // r was replaced by the true residual; iterate on
-                if (err <= thr) { converged = true; break; }
             }
-            k_cg_dir<<<kNB, kVT, 0, st>>>(m, r0, (int)k, B);
+            k_cg_dir<<<kNB, kVT, 0, st>>>(n, (int)k, B);
             ctx->launches += 1;
-            if (P > 1) CG_TRY(comm_allgather(ctx, B.pfull + off, B.pfull, chunk, st));
             CG_CUDA(cudaEventRecord(evg0, st));
-            CG_TRY(launch_gemv(ctx, A, m, n, ld, B.pfull, B.z, scale, st));
+            CG_TRY(mv.apply(B.p, B.z, scale ? scale : nullptr, st));
             CG_CUDA(cudaEventRecord(evg1, st));
-            k_cg_dot<<<kNB, kVT, 0, st>>>(m, r0, B);
-            ctx->launches += 1;
-            CG_TRY(comm_allreduce_sum(ctx, B.pz, kNB, st));
-            k_cg_update<<<kNB, kVT, 0, st>>>(m, r0, (int)k, x, B);
-            ctx->launches += 1;
+            k_cg_dot<<<kNB, kVT, 0, st>>>(n, B);
+            k_cg_update<<<kNB, kVT, 0, st>>>(n, (int)k, x, B);
+            ctx->launches += 2;
             CG_CUDA(cudaGetLastError());
-            if (P > 1) {
-                CG_TRY(comm_allreduce_sum(ctx, B.rw + ((k + 1) & 1) * kNB, kNB, st));
-                CG_TRY(comm_allreduce_sum(ctx, B.res, kNB, st));
-            }
-            CG_TRY(read_sum(ctx, B.res, kNB, &res2));
+            CG_TRY(read_partials(ctx, B.res, kNB, false, &res2));
             float gms = 0;
             cudaEventElapsedTime(&gms, evg0, evg1);
             gemv_ms += gms;

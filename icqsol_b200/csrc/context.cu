@@ -181,6 +181,7 @@ int icqb_destroy(icqb_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     comm_destroy(ctx);
+    symv_plan_free(ctx);
     free_mesh(ctx);
     cudaFree(ctx->d_work);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
@@ -226,11 +227,13 @@ int icqb_set_mesh(icqb_ctx* ctx, const double* xyz, int64_t npts, const int64_t*
             return set_error(ctx, ICQB_EARG, "icqb_set_mesh: vertex index out of range");
     ICQB_CUDA(ctx, cudaSetDevice(ctx->device));
     free_mesh(ctx);
+    symv_plan_free(ctx);
     ctx->npts = npts;
     ctx->ntri = ntri;
     ctx->ntri_pad = (ntri + kPad - 1) / kPad * kPad;
     ctx->r0 = 0;
     ctx->r1 = ntri;
+    ctx->q0 = ctx->q1 = 0;
     if (ntri == 0) return ICQB_OK;
     const int64_t nalloc = ctx->ntri_pad + kPad;
     ICQB_CUDA(ctx, cudaMalloc(&ctx->d_xyz, sizeof(double) * 3 * (npts > 0 ? npts : 1)));
@@ -255,6 +258,21 @@ int icqb_set_rows(icqb_ctx* ctx, int64_t r0, int64_t r1) {
         return set_error(ctx, ICQB_EARG, "icqb_set_rows: need 0 <= r0 <= r1 <= ntri");
     ctx->r0 = r0;
     ctx->r1 = r1;
+    ctx->q0 = ctx->q1 = 0;
+    return ICQB_OK;
+}
+
+int icqb_set_row_blocks(icqb_ctx* ctx, int64_t r0, int64_t r1, int64_t q0, int64_t q1) {
+    if (!ctx) return ICQB_EARG;
+    if (r0 < 0 || r1 < r0 || r1 > ctx->ntri || q0 < r1 || q1 < q0 || q1 > ctx->ntri)
+        return set_error(ctx, ICQB_EARG,
+                         "icqb_set_row_blocks: need 0 <= r0 <= r1 <= q0 <= q1 <= ntri");
+    if ((r1 > r0 && (r0 % 128) != 0) || (q1 > q0 && (q0 % 128) != 0))
+        return set_error(ctx, ICQB_EARG, "icqb_set_row_blocks: blocks must start on multiples of 128");
+    ctx->r0 = r0;
+    ctx->r1 = r1;
+    ctx->q0 = q0;
+    ctx->q1 = q1;
     return ICQB_OK;
 }
 

@@ -18,7 +18,8 @@ constexpr int kPad = 128;        // triangle count is padded to a multiple of th
 // phases for icqb_last_ms
 enum Phase { kPrepare = 0, kOffDiag = 1, kDiag = 2, kGemv = 3, kCg = 4, kNumPhases = 5 };
 
-struct Comm;  // NCCL state, comm.cu
+struct Comm;      // NCCL state, comm.cu
+struct SymvPlan;  // task table + workspace of the symmetric product, symv.cu
 
 }  // namespace icqb
 
@@ -30,7 +31,8 @@ struct icqb_ctx {
     int num_sms = 0;
 
     int64_t npts = 0, ntri = 0, ntri_pad = 0;
-    int64_t r0 = 0, r1 = 0;
+    int64_t r0 = 0, r1 = 0;   // observer rows owned by this context (first block)
+    int64_t q0 = 0, q1 = 0;   // second row block (block-lower-triangular storage only)
 
     // mesh and per-triangle tables (device)
     double* d_xyz = nullptr;     // [npts][3]
@@ -47,6 +49,7 @@ struct icqb_ctx {
     double* h_pinned = nullptr;  // small pinned scratch for scalar read-back
 
     icqb::Comm* comm = nullptr;
+    icqb::SymvPlan* symv = nullptr;
 
     double last_ms[icqb::kNumPhases] = {0, 0, 0, 0, 0};
     int64_t launches = 0;
@@ -62,6 +65,12 @@ int ensure_work(icqb_ctx* ctx, int64_t doubles);
 // kernels' host launchers (each returns ICQB_OK or sets the context error)
 int launch_prepare(icqb_ctx* ctx);
 int launch_offdiag(icqb_ctx* ctx, double* dG, double* dK, int64_t ld);
+int launch_offdiag_lower(icqb_ctx* ctx, double* dG, double* dK, double* dKu, int64_t ld);
+int launch_diag_rows(icqb_ctx* ctx, int order, long long g0, long long g1, double* dOut,
+                     int64_t stride);
+int launch_symv(icqb_ctx* ctx, const double* dA, int64_t ld, const double* dx,
+                const double* dgamma, const double* dalpha, const double* dbeta, double* dz,
+                cudaStream_t stream);
 int launch_diag(icqb_ctx* ctx, int order, double* dOut, int64_t stride);
 int launch_gemv(icqb_ctx* ctx, const double* dA, int64_t nrows, int64_t ncols, int64_t ld,
                 const double* dx, double* dy, const double* drowscale, cudaStream_t stream);
@@ -73,6 +82,7 @@ int comm_allgather(icqb_ctx* ctx, const double* send, double* recv, int64_t coun
                    cudaStream_t stream);
 int comm_allreduce_sum(icqb_ctx* ctx, double* buf, int64_t count, cudaStream_t stream);
 void comm_destroy(icqb_ctx* ctx);
+void symv_plan_free(icqb_ctx* ctx);
 
 }  // namespace icqb
 

@@ -86,7 +86,7 @@ class ConjugateGradient:
         r2 = ctypes.c_double(0.)
         rinf = ctypes.c_double(0.)
         self.ctx.check(self.lib.icqb_cg_solve_dev(
-            self.ctx.handle, self.mat.data_ptr(), self.n, self.ld,
+            self.ctx.handle, self.mat.data_ptr(), self.n, self.ld, 0,
             self.rowScaling.data_ptr() if self.rowScaling is not None else 0,
             self.precond.data_ptr() if self.precond is not None else 0,
             self.b.data_ptr(), x.data_ptr(), float(self.tol), 0, int(self.maxNumIters),

@@ -69,8 +69,15 @@ int64_t icqb_num_triangles(const icqb_ctx* ctx);
 /* observer rows [r0, r1) this context assembles / multiplies (default: all). */
 int icqb_set_rows(icqb_ctx* ctx, int64_t r0, int64_t r1);
 int icqb_get_rows(const icqb_ctx* ctx, int64_t* r0, int64_t* r1);
+/* Block-lower-triangular storage ("lower"): this context owns the
+ * observer rows [r0, r1) and [q0, q1) (second block may be empty; blocks start on
+ * multiples of 128) and stores, for each row, only the 128-wide column tiles up to and
+ * including the diagonal tile.  The upper part follows from the reference's own mirror
+ * rule G[j,i] = G[i,j] * area_i / area_j (bem/icqLaplaceMatrices.cpp:97-98). */
+int icqb_set_row_blocks(icqb_ctx* ctx, int64_t r0, int64_t r1, int64_t q0, int64_t q1);
 /* |db x dc| of every triangle (device pointer, double[ntri]). */
 uint64_t icqb_area2_dev(const icqb_ctx* ctx);
+int icqb_area2_host(icqb_ctx* ctx, double* out); /* same values, host double[ntri] */
 
 /* ---- assembly ----------------------------------------------------------------
  * Fills rows [r0, r1) of G -- and of K when dK != 0 -- into caller-owned device
@@ -84,6 +91,18 @@ uint64_t icqb_area2_dev(const icqb_ctx* ctx);
  * K is the double-layer matrix (NOT in the reference snapshot; definition in
  * DESIGN.md); K[i,i] = 0.  Asynchronous on the context stream. */
 int icqb_assemble_dev(icqb_ctx* ctx, int diag_order, uint64_t dG, uint64_t dK, int64_t ld);
+
+/* Lower storage: rows of the two blocks are stored one after the other (local row =
+ * position in [r0,r1) ++ [q0,q1)), pitch ld (even).  Only tiles J <= I are written; every
+ * pair of triangles is evaluated exactly once over the whole set of ranks and nothing is
+ * mirrored.  dKl[i,j] = K[i,j] and dKu[i,j] = K[j,i] for the stored positions (both 0 or
+ * both non-zero). */
+int icqb_assemble_lower_dev(icqb_ctx* ctx, int diag_order, uint64_t dG, uint64_t dKl, uint64_t dKu,
+                            int64_t ld);
+/* y = G x (scaled == 0) or diag(area) G x (scaled != 0) from the lower storage: streams
+ * each stored entry once (4 N^2 bytes instead of 8 N^2) and all-reduces the partial
+ * vectors over the ranks.  x, y: device double[ntri], replicated.  Blocking. */
+int icqb_symv_dev(icqb_ctx* ctx, uint64_t dA, int64_t ld, uint64_t dx, uint64_t dy, int scaled);
 
 /* Host-buffer forms (blocking; host<->device copies inside the call).
  * gMat/kMat: row-major double[(r1-r0)*ntri]; kMat may be NULL. */
@@ -110,23 +129,28 @@ int icqb_gemv_host(icqb_ctx* ctx, uint64_t dA, int64_t nrows, int64_t ncols, int
 
 /* Jacobi-preconditioned conjugate gradient (solvers/icqConjugateGradient.py:49-79)
  * on the system  diag(rowscale) A x = diag(rowscale) b.
- *   dA       rows [r0, r1) of the n x n matrix, row-major, leading dimension ld;
- *   drowscale double[r1-r0] or 0 (no scaling: plain CG on A, as the reference class);
- *            for the Green matrix pass the local slice of icqb_area2_dev(): G is not
- *            symmetric (G[j,i] = G[i,j] A_i/A_j, bem/icqLaplaceMatrices.cpp:97-98)
- *            but diag(area) G is;
- *   dprecond double[r1-r0] diagonal preconditioner of the UNSCALED matrix
+ *   dA       the locally stored rows of the n x n matrix, pitch ld:
+ *              storage 0: rank g of P holds rows [g*ceil(n/P), (g+1)*ceil(n/P)), all columns;
+ *              storage 1: lower storage of the context's row blocks (icqb_set_row_blocks),
+ *                         the context must hold the mesh the matrix was assembled from;
+ *   drowscale double[n] or 0 (no scaling: plain CG on A, as the reference class);
+ *            for the Green matrix pass icqb_area2_dev(): G is not symmetric
+ *            (G[j,i] = G[i,j] A_i/A_j, bem/icqLaplaceMatrices.cpp:97-98) but diag(area) G is;
+ *            storage 1 requires exactly that vector;
+ *   dprecond double[n] diagonal preconditioner of the UNSCALED matrix
  *            (icqConjugateGradient.py:19) or 0 = use diag(A);
- *   db, dx   local slices double[r1-r0]; dx holds x0 on entry, the solution on exit;
- *   tol      stop when ||b - A x||_2 <= tol (absolute, :64) ; if rel != 0 the
+ *   db, dx   double[n], replicated on every rank; dx holds x0 on entry, the solution on exit;
+ *   tol      stop when ||b - A x||_2 <= tol (absolute, :64); if rel != 0 the
  *            threshold is tol*||b||_2;
- *   maxit    iteration cap (:16 defaults to n);
+ *   maxit    iteration cap (:16 defaults to n; pass -1 for n);
  *   outputs  iters, final true residual ||b - A x||_2 and max norm.
- * With nranks > 1 (icqb_comm_init) the iterate is all-gathered and the dot
- * products all-reduced over NCCL. Blocking. */
-int icqb_cg_solve_dev(icqb_ctx* ctx, uint64_t dA, int64_t n, int64_t ld, uint64_t drowscale,
-                      uint64_t dprecond, uint64_t db, uint64_t dx, double tol, int rel,
-                      int64_t maxit, int64_t* iters, double* resid2, double* residinf);
+ * All vectors are replicated and every rank runs the same vector kernels; only the
+ * matrix product is distributed: one NCCL collective per iteration (all-gather of the
+ * product's row slices for storage 0, all-reduce of the partial products for storage 1).
+ * Blocking. */
+int icqb_cg_solve_dev(icqb_ctx* ctx, uint64_t dA, int64_t n, int64_t ld, int storage,
+                      uint64_t drowscale, uint64_t dprecond, uint64_t db, uint64_t dx, double tol,
+                      int rel, int64_t maxit, int64_t* iters, double* resid2, double* residinf);
 
 /* ---- multi-GPU plumbing -----------------------------------------------------------
  * One rank per process.  `unique_id` is the 128-byte ncclUniqueId produced by

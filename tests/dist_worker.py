@@ -14,7 +14,9 @@ import torch.distributed as dist  # noqa: E402
 def main():
     local = int(os.environ['LOCAL_RANK'])
     torch.cuda.set_device(local)
-    dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    import datetime
+    dist.init_process_group('nccl', device_id=torch.device('cuda', local),
+                            timeout=datetime.timedelta(seconds=90))
     rank, world = dist.get_rank(), dist.get_world_size()
     from oracle import oracle
     from icqsol_b200.mesh.generators import uvSphere
@@ -22,19 +24,27 @@ def main():
     from icqsol_b200.bem.icqLaplaceSolver import LaplaceSolver
     from icqsol_b200.bem.icqPoissonSolver import PoissonSolver
 
-    for nt, npz in ((40, 20), (64, 30), (7, 4)):
+    for nt, npz, storage in ((40, 20, 'full'), (40, 20, 'lower'), (64, 30, 'lower'), (64, 30, 'full'),
+                             (7, 4, 'full'), (7, 4, 'lower')):
         xyz, tri = uvSphere(1.0, nt, npz)
         n = tri.shape[0]
-        solver = LaplaceSolver(PolyData.from_arrays(xyz, tri), float('inf'), 5, computeK=True)
-        r0, r1 = solver.getRowRange()
+        print('rank', rank, 'case', nt, npz, storage, flush=True)
+        solver = LaplaceSolver(PolyData.from_arrays(xyz, tri), float('inf'), 5, computeK=True,
+                               storage=storage)
         assert solver.numRanks == world
-        gloc = solver.getGreenMatrixDevice().cpu().numpy()
-        ref = oracle.block(xyz, tri, r0, r1, 0, n, 5)
-        if r1 > r0:
-            assert numpy.abs(gloc / ref - 1).max() < 1e-12, 'G rows'
-            kref = oracle.k_block(xyz, tri, r0, r1, 0, n)
-            kloc = solver.getNormalDerivativeGreenMatrixDevice().cpu().numpy()
-            assert numpy.abs(kloc - kref).max() / numpy.abs(kref).max() < 1e-9, 'K rows'
+        if storage == 'full':
+            r0, r1 = solver.getRowRange()
+            gloc = solver.getGreenMatrixDevice().cpu().numpy()
+            ref = oracle.block(xyz, tri, r0, r1, 0, n, 5)
+            if r1 > r0:
+                assert numpy.abs(gloc / ref - 1).max() < 1e-12, 'G rows'
+                kref = oracle.k_block(xyz, tri, r0, r1, 0, n)
+                kloc = solver.getNormalDerivativeGreenMatrixDevice().cpu().numpy()
+                assert numpy.abs(kloc - kref).max() / numpy.abs(kref).max() < 1e-9, 'K rows'
+        else:
+            kfull = solver.getNormalDerivativeGreenMatrix()
+            kref = oracle.k_block(xyz, tri, 0, n, 0, n)
+            assert numpy.abs(kfull - kref).max() / numpy.abs(kref).max() < 1e-9, 'K lower'
         g = solver.getGreenMatrix()          # gathered on every rank
         gref = oracle.green_matrix(xyz, tri, 5, threads=True)
         assert numpy.abs(g / gref - 1).max() < 1e-12, 'G gathered'
@@ -46,15 +56,15 @@ def main():
         lu = oracle.laplace_response(gref, v)
         assert numpy.abs(rsp - lu).max() / numpy.abs(lu).max() < 1e-8
         info = solver.lastSolveInfo
-        psolver = PoissonSolver(PolyData.from_arrays(xyz, tri), float('inf'), 5)
+        psolver = PoissonSolver(PolyData.from_arrays(xyz, tri), float('inf'), 5, storage=storage)
         psolver.setSourceFromExpression('x + 1.0')
         prsp = psolver.computeResponseField()
         cen = (xyz[tri[:, 0]] + xyz[tri[:, 1]] + xyz[tri[:, 2]]) / 3.
         pref = gref.dot(cen[:, 0] + 1.0)
         assert numpy.abs(prsp - pref).max() / numpy.abs(pref).max() < 1e-12
         if rank == 0:
-            print('N={0} ranks={1}: CG iters {2}, backward {3:.2e}'.format(
-                n, world, info['iterations'], backward))
+            print('N={0} ranks={1} {4}: CG iters {2}, backward {3:.2e}'.format(
+                n, world, info['iterations'], backward, storage))
         del solver, psolver
     dist.barrier()
     dist.destroy_process_group()

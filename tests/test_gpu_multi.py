@@ -20,6 +20,6 @@ def test_sharded_assembly_and_cg(nranks):
                           '--nproc-per-node', str(nranks), '--master-addr', '127.0.0.1',
                           '--master-port', str(29600 + nranks),
                           os.path.join(ROOT, 'tests', 'dist_worker.py')],
-                         capture_output=True, text=True, env=env, timeout=900)
+                         capture_output=True, text=True, env=env, timeout=420)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert out.stdout.count(' ok') == nranks

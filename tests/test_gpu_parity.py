@@ -289,7 +289,8 @@ def test_gemv_vs_numpy(ctx, nrows, ncols):
         assert (numpy.abs(y - ref) <= 1e-13 * scale).all()
 
 
-def test_poisson_response_golden(golden):
+@pytest.mark.parametrize('storage', ['lower', 'full'])
+def test_poisson_response_golden(golden, storage):
     """PoissonSolver on the reference's meshes: v = G.charge vs numpy.dot on the
     reference G (bem/icqPoissonSolver.py:36), 1e-12 relative."""
     from icqsol_b200.mesh.polydata import PolyData
@@ -297,7 +298,8 @@ def test_poisson_response_golden(golden):
     big = golden['green_sampled']
     for name in ('sphere', 'boltFine'):
         xyz, tri = golden.mesh(name)
-        solver = PoissonSolver(PolyData.from_arrays(xyz, tri, dtype=numpy.float64), float('inf'))
+        solver = PoissonSolver(PolyData.from_arrays(xyz, tri, dtype=numpy.float64), float('inf'),
+                               storage=storage)
         solver.setSourceFromExpression('1.0')
         rsp = solver.computeResponseField()
         assert numpy.abs(rsp / big[name + '_poisson_rsp_one'] - 1).max() < 1e-12
@@ -309,7 +311,8 @@ def test_poisson_response_golden(golden):
         assert arr is not None and arr.GetNumberOfTuples() == len(tri)
 
 
-def test_laplace_response_golden(golden):
+@pytest.mark.parametrize('storage', ['lower', 'full'])
+def test_laplace_response_golden(golden, storage):
     """LaplaceSolver: sigma = -G^-1 v.  Reference = LU (bem/icqLaplaceSolver.py:36).
     Backward error <= 1e-12; forward difference vs LU bounded by the conditioning."""
     from icqsol_b200.mesh.polydata import PolyData
@@ -317,7 +320,12 @@ def test_laplace_response_golden(golden):
     big = golden['green_sampled']
     for name in ('sphere', 'boltFine'):
         xyz, tri = golden.mesh(name)
-        solver = LaplaceSolver(PolyData.from_arrays(xyz, tri, dtype=numpy.float64), float('inf'), 5)
+        solver = LaplaceSolver(PolyData.from_arrays(xyz, tri, dtype=numpy.float64), float('inf'), 5,
+                               storage=storage)
+        big_rows = big[name + '_rows']
+        gfull = solver.getGreenMatrix()
+        assert max_entry_relerr(gfull[big_rows, :], big[name + '_G_rows']) < TOL_ENTRY
+        assert max_entry_relerr(gfull[:, big_rows], big[name + '_G_cols']) < TOL_ENTRY
         solver.setSourceFromExpression('1./sqrt(x**2 + (y-2.)**2 + (z-4.)**2)')
         v = solver.getSourceArray(solver.getSourceArrayIndex())
         assert numpy.abs(v / big[name + '_v'] - 1).max() < 1e-14
@@ -398,3 +406,81 @@ def test_point_data_projection_and_missing_source(golden):
     cellCharge = numpy.array([(1 + 2 + 4) / 3., (1 + 3 + 2) / 3., (1 + 4 + 3) / 3., (2 + 3 + 4) / 3.])
     g = solver.getGreenMatrix()
     assert numpy.abs(rsp - g.dot(cellCharge)).max() < 1e-14
+
+
+# ---- block-lower-triangular storage -----------------------------------------------------------
+
+def lower_assemble(ctx, xyz, tri, blocks, order=5, with_k=False):
+    import torch
+    xyz = numpy.ascontiguousarray(xyz, numpy.float64)
+    tri = numpy.ascontiguousarray(tri, numpy.int64)
+    n = tri.shape[0]
+    ctx.check(ctx.lib.icqb_set_mesh(ctx.handle, dp(xyz), xyz.shape[0], lp(tri), n))
+    ctx.check(ctx.lib.icqb_set_row_blocks(ctx.handle, *blocks))
+    rows = (blocks[1] - blocks[0]) + (blocks[3] - blocks[2])
+    ld = (n + 15) // 16 * 16
+    bufs = [torch.full((max(rows, 1), ld), float('nan'), dtype=torch.float64, device='cuda:0')
+            for _ in range(3 if with_k else 1)]
+    ctx.check(ctx.lib.icqb_assemble_lower_dev(ctx.handle, order, bufs[0].data_ptr(),
+                                              bufs[1].data_ptr() if with_k else 0,
+                                              bufs[2].data_ptr() if with_k else 0, ld))
+    ctx.check(ctx.lib.icqb_synchronize(ctx.handle))
+    return bufs, ld, rows
+
+
+@pytest.mark.parametrize('blocks', [(0, 960, 960, 960), (0, 256, 768, 960), (256, 512, 512, 768),
+                                    (128, 128, 384, 500), (0, 0, 0, 0)])
+def test_lower_storage_tiles_vs_oracle(ctx, golden, oracle_mod, blocks):
+    """Every stored tile (J <= I) of arbitrary row blocks equals the oracle; tiles above
+    the diagonal tile are never written; KL/KU hold K[i,j] / K[j,i]."""
+    xyz, tri = golden.mesh('sphere')
+    n = tri.shape[0]
+    bufs, ld, rows = lower_assemble(ctx, xyz, tri, blocks, 5, with_k=True)
+    g, kl, ku = [b.cpu().numpy() for b in bufs]
+    ref = oracle_mod.green_matrix(xyz, tri, 5, threads=True)
+    kref = oracle_mod.k_block(xyz, tri, 0, n, 0, n)
+    glob = list(range(blocks[0], blocks[1])) + list(range(blocks[2], blocks[3]))
+    assert len(glob) == rows
+    kmax = numpy.abs(kref).max()
+    for lrow, i in enumerate(glob):
+        cend = min(n, (i // 128 + 1) * 128)
+        assert numpy.abs(g[lrow, :cend] / ref[i, :cend] - 1).max() < TOL_ENTRY
+        assert numpy.isnan(g[lrow, cend:n]).all()          # never written
+        assert numpy.abs(kl[lrow, :cend] - kref[i, :cend]).max() < K_TOL * kmax
+        assert numpy.abs(ku[lrow, :cend] - kref[:cend, i]).max() < K_TOL * kmax
+
+
+@pytest.mark.parametrize('name', ['tet', 'sphere', 'boltFine'])
+def test_lower_storage_solver_matrices(golden, oracle_mod, name):
+    """getGreenMatrix()/getNormalDerivativeGreenMatrix() rebuilt from the lower storage
+    (mirror rule on read) equal the oracle entry by entry."""
+    from icqsol_b200.mesh.polydata import PolyData
+    from icqsol_b200.bem.icqLaplaceSolver import LaplaceSolver
+    xyz, tri = golden.mesh(name)
+    n = tri.shape[0]
+    solver = LaplaceSolver(PolyData.from_arrays(xyz, tri, dtype=numpy.float64), float('inf'), 5,
+                           computeK=True, storage='lower')
+    ref = oracle_mod.green_matrix(xyz, tri, 5, threads=True)
+    assert max_entry_relerr(solver.getGreenMatrix(), ref) < TOL_ENTRY
+    kref = oracle_mod.k_block(xyz, tri, 0, n, 0, n)
+    assert numpy.abs(solver.getNormalDerivativeGreenMatrix() - kref).max() < K_TOL * numpy.abs(kref).max()
+    a2 = solver.getTriangleAreas2()
+    assert (a2 == oracle_mod.area2(xyz, tri)).all() or numpy.abs(a2 / oracle_mod.area2(xyz, tri) - 1).max() < 1e-15
+
+
+@pytest.mark.parametrize('nt,nph', [(7, 4), (16, 9), (33, 17), (64, 30)])
+def test_symmetric_product_vs_numpy(oracle_mod, nt, nph):
+    """icqb_symv_dev (streams the stored half once) == numpy.dot with the full oracle G."""
+    from icqsol_b200.mesh.generators import uvSphere
+    from icqsol_b200.mesh.polydata import PolyData
+    from icqsol_b200.bem.icqPoissonSolver import PoissonSolver
+    xyz, tri = uvSphere(1.0, nt, nph)
+    n = tri.shape[0]
+    solver = PoissonSolver(PolyData.from_arrays(xyz, tri), float('inf'), 5, storage='lower')
+    ref = oracle_mod.green_matrix(xyz, tri, 5, threads=True)
+    rng = numpy.random.default_rng(n)
+    for _ in range(2):
+        x = rng.normal(size=n)
+        y = solver.applyGreenMatrix(x)
+        scale = numpy.abs(ref).dot(numpy.abs(x))
+        assert (numpy.abs(y - ref.dot(x)) <= 1e-13 * scale).all()
