@@ -42,8 +42,12 @@ class BaseSolver:
         xyz, cells = extract_mesh(pdata)
         # every cell must be a polygon that can be turned into triangles
         # (the reference asserts 3 ids per refined cell, bem/icqBaseSolver.py:31)
-        assert all(len(c) >= 3 for c in cells)
-        isTriangulated = all(len(c) == 3 for c in cells)
+        if isinstance(cells, numpy.ndarray):
+            assert cells.shape[1] >= 3
+            isTriangulated = cells.shape[1] == 3
+        else:
+            assert all(len(c) >= 3 for c in cells)
+            isTriangulated = all(len(c) == 3 for c in cells)
         tri = generators.fanSplit(cells)
         refXyz, refTri = generators.refineToMaxEdge(xyz, tri, max_edge_length)
         if isTriangulated and refTri.shape[0] == tri.shape[0]:
@@ -63,7 +67,7 @@ class BaseSolver:
 
         # point ids of each cell
         assert tri.ndim == 2 and tri.shape[1] == 3
-        self.ptIdList = tri.tolist()
+        self._ptIdList = None
         self._xyz = numpy.ascontiguousarray(xyz, numpy.float64)
         self._tri = numpy.ascontiguousarray(tri, numpy.int64)
 
@@ -78,6 +82,13 @@ class BaseSolver:
         # set in the derived classes
         self.responseName = 'NO-SET'
         self.sourceName = 'NOT-SET'
+
+    @property
+    def ptIdList(self):
+        """Point ids of each triangle as nested lists (bem/icqBaseSolver.py:24-35)."""
+        if self._ptIdList is None:
+            self._ptIdList = self._tri.tolist()
+        return self._ptIdList
 
     def getVtkPolyData(self):
         """

@@ -28,6 +28,18 @@ namespace {
 constexpr int kNB = 128;       // blocks of every vector kernel == partials per dot product
 constexpr int kVT = 256;       // threads per block
 
+// Loop state kept on the device so that iterations can be enqueued ahead of the
+// host: once the recurrence residual meets the threshold every later kernel of the
+// batch returns immediately, and `iters` stops counting -- the iteration count is the
+// one a per-iteration host test would give (solvers/icqConjugateGradient.py:64).
+struct CgState {
+    int done;
+    unsigned int ticket;
+    long long iters;
+    double thr2;       // squared stopping threshold
+    double res2;       // squared recurrence residual after the last counted iteration
+};
+
 // every vector is full length (n) and replicated on all ranks: the ranks execute the
 // same vector kernels on identical data, only the matrix product is distributed
 struct CgBuf {
@@ -38,6 +50,7 @@ struct CgBuf {
     double *tru;       // [kNB]  sum (b - A x)^2
     double *bb;        // [kNB]  sum b^2
     double *mx;        // [kNB]  max |b - A x| per block
+    CgState *state;    // device-side loop state (see below)
 };
 
 __device__ __forceinline__ double block_sum(double v, double* s_red) {
@@ -114,6 +127,7 @@ __global__ void __launch_bounds__(kVT) k_cg_init(long long n, const double* b,
 
 // p = w + beta p, beta = rho_k / rho_{k-1} (0 on the first iteration)
 __global__ void __launch_bounds__(kVT) k_cg_dir(long long n, int k, CgBuf B) {
+    if (B.state->done) return;
     double beta = 0.0;
     if (k > 0) beta = sum_partials(B.rw + (k & 1) * kNB) / sum_partials(B.rw + ((k - 1) & 1) * kNB);
     for (long long i = (long long)blockIdx.x * kVT + threadIdx.x; i < n; i += (long long)kNB * kVT)
@@ -123,6 +137,7 @@ __global__ void __launch_bounds__(kVT) k_cg_dir(long long n, int k, CgBuf B) {
 // partial p.z
 __global__ void __launch_bounds__(kVT) k_cg_dot(long long n, CgBuf B) {
     __shared__ double s_red[kVT / 32];
+    if (B.state->done) return;
     double acc = 0.0;
     for (long long i = (long long)blockIdx.x * kVT + threadIdx.x; i < n; i += (long long)kNB * kVT)
         acc = fma(B.p[i], B.z[i], acc);
@@ -133,6 +148,8 @@ __global__ void __launch_bounds__(kVT) k_cg_dot(long long n, CgBuf B) {
 // alpha = rho_k / (p.z); x += alpha p; r -= alpha z; w = r/M; partial rho_{k+1}, |r/s|^2
 __global__ void __launch_bounds__(kVT) k_cg_update(long long n, int k, double* x, CgBuf B) {
     __shared__ double s_red[kVT / 32];
+    __shared__ bool s_last;
+    if (B.state->done) return;
     const double alpha = sum_partials(B.rw + (k & 1) * kNB) / sum_partials(B.pz);
     double rw = 0.0, rs = 0.0;
     for (long long i = (long long)blockIdx.x * kVT + threadIdx.x; i < n; i += (long long)kNB * kVT) {
@@ -148,7 +165,24 @@ __global__ void __launch_bounds__(kVT) k_cg_update(long long n, int k, double* x
     double t = block_sum(rw, s_red);
     if (threadIdx.x == 0) B.rw[((k + 1) & 1) * kNB + blockIdx.x] = t;
     t = block_sum(rs, s_red);
-    if (threadIdx.x == 0) B.res[blockIdx.x] = t;
+    if (threadIdx.x == 0) {
+        B.res[blockIdx.x] = t;
+        __threadfence();
+        s_last = (atomicAdd(&B.state->ticket, 1u) == kNB - 1);
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+        // the last block to finish closes the iteration: fixed-order sum of the partials
+        __threadfence();
+        const volatile double* part = B.res;
+        double res2 = 0.0;
+        for (int q = 0; q < kNB; ++q) res2 += part[q];
+        B.state->res2 = res2;
+        B.state->iters += 1;
+        B.state->ticket = 0;
+        if (res2 <= B.state->thr2) B.state->done = 1;
+        __threadfence();
+    }
 }
 
 // true residual t = b - A x given z = A x (unscaled); optionally replace r, w, rho
@@ -176,6 +210,13 @@ __global__ void __launch_bounds__(kVT) k_cg_true(long long n, int replace, int k
     }
     t = block_max(mx, s_red);
     if (threadIdx.x == 0) B.mx[blockIdx.x] = t;
+}
+
+__global__ void k_cg_state(CgState* s, int done, long long iters, double thr2, int set_iters) {
+    s->done = done;
+    s->ticket = 0;
+    s->thr2 = thr2;
+    if (set_iters) s->iters = iters;
 }
 
 __global__ void k_recip(const double* a, double* out, long long n) {
@@ -217,17 +258,18 @@ struct MatVec {
     double* gathered;          // storage 0: [nranks*chunk] staging for the all-gather
 
     // scaled != 0: out = diag(area or scale) A v ; scaled == 0: out = A v
-    int apply(const double* v, double* out, const double* scale, cudaStream_t st) {
+    int apply(const double* v, double* out, const double* scale, cudaStream_t st,
+              const int* skip = nullptr) {
         int rc;
         if (storage == 1) {
             rc = launch_symv(ctx, A, ld, v, area, scale ? area : nullptr,
-                             scale ? nullptr : inv_area, out, st);
+                             scale ? nullptr : inv_area, out, st, skip);
             if (rc != ICQB_OK) return rc;
             return comm_allreduce_sum(ctx, out, n, st);
         }
         const int P = comm_nranks(ctx);
         double* dst = (P == 1) ? out : gathered + (long long)comm_rank(ctx) * chunk;
-        rc = launch_gemv(ctx, A, r1 - r0, n, ld, v, dst, scale ? scale + r0 : nullptr, st);
+        rc = launch_gemv(ctx, A, r1 - r0, n, ld, v, dst, scale ? scale + r0 : nullptr, st, skip);
         if (rc != ICQB_OK || P == 1) return rc;
         rc = comm_allgather(ctx, dst, gathered, chunk, st);
         if (rc != ICQB_OK) return rc;
@@ -265,7 +307,7 @@ extern "C" int icqb_cg_solve_dev(icqb_ctx* ctx, uint64_t dA_, int64_t n, int64_t
 
     // work space
     const long long nfull = chunk * P;
-    const long long need = 8 * n + nfull + 7 * kNB + 64;
+    const long long need = 8 * n + nfull + 7 * kNB + 8 + 64;
     int rc = ensure_work(ctx, need);
     if (rc != ICQB_OK) return rc;
     CgBuf B;
@@ -285,6 +327,7 @@ extern "C" int icqb_cg_solve_dev(icqb_ctx* ctx, uint64_t dA_, int64_t n, int64_t
     B.tru = wp; wp += kNB;
     B.bb = wp; wp += kNB;
     B.mx = wp; wp += kNB;
+    B.state = reinterpret_cast<CgState*>(wp); wp += 8;
 
     MatVec mv;
     mv.ctx = ctx;
@@ -352,6 +395,12 @@ extern "C" int icqb_cg_solve_dev(icqb_ctx* ctx, uint64_t dA_, int64_t n, int64_t
         long long k = 0;
         int replacements = 0;
         double true2 = err, trueinf = 0.0;
+        const int* skip = reinterpret_cast<const int*>(B.state);   // &state->done
+        k_cg_state<<<1, 1, 0, st>>>(B.state, 0, 0, thr * thr, 1);
+        ctx->launches += 1;
+        // iterations are enqueued `batch` at a time; the device decides when to stop
+        // (CgState), the host only polls -- no host round trip per iteration
+        const long long batch = 8;
 
         while (true) {
             if (err <= thr || k >= maxit) {
@@ -368,23 +417,30 @@ extern "C" int icqb_cg_solve_dev(icqb_ctx* ctx, uint64_t dA_, int64_t n, int64_t
                 if (true2 <= thr || last) break;
                 ++replacements;
                 err = true2;  // r was replaced by the true residual; iterate on
+                k_cg_state<<<1, 1, 0, st>>>(B.state, 0, 0, thr * thr, 0);
+                ctx->launches += 1;
             }
-            k_cg_dir<<<kNB, kVT, 0, st>>>(n, (int)k, B);
-            ctx->launches += 1;
-            CG_CUDA(cudaEventRecord(evg0, st));
-            CG_TRY(mv.apply(B.p, B.z, scale ? scale : nullptr, st));
-            CG_CUDA(cudaEventRecord(evg1, st));
-            k_cg_dot<<<kNB, kVT, 0, st>>>(n, B);
-            k_cg_update<<<kNB, kVT, 0, st>>>(n, (int)k, x, B);
-            ctx->launches += 2;
+            const long long nb = std::min<long long>(batch, maxit - k);
+            for (long long i = 0; i < nb; ++i) {
+                const int kk = (int)((k + i) & 0x3fffffff);
+                k_cg_dir<<<kNB, kVT, 0, st>>>(n, kk, B);
+                if (i == 0) CG_CUDA(cudaEventRecord(evg0, st));
+                CG_TRY(mv.apply(B.p, B.z, scale ? scale : nullptr, st, skip));
+                if (i == 0) CG_CUDA(cudaEventRecord(evg1, st));
+                k_cg_dot<<<kNB, kVT, 0, st>>>(n, B);
+                k_cg_update<<<kNB, kVT, 0, st>>>(n, kk, x, B);
+                ctx->launches += 3;
+            }
             CG_CUDA(cudaGetLastError());
-            CG_TRY(read_partials(ctx, B.res, kNB, false, &res2));
+            CG_CUDA(cudaMemcpyAsync(ctx->h_pinned, B.state, sizeof(CgState), cudaMemcpyDeviceToHost, st));
+            CG_CUDA(cudaStreamSynchronize(st));
+            const CgState hs = *reinterpret_cast<const CgState*>(ctx->h_pinned);
             float gms = 0;
             cudaEventElapsedTime(&gms, evg0, evg1);
             gemv_ms += gms;
             ++gemv_count;
-            err = sqrt(res2);
-            ++k;
+            k = hs.iters;
+            err = sqrt(hs.res2);
             if (!(err == err)) {  // NaN: breakdown (singular / indefinite system)
                 true2 = err;
                 break;

@@ -33,8 +33,10 @@ __global__ void __launch_bounds__(kThreads) k_gemv(const double* __restrict__ A,
                                                    long long ncols, long long ld,
                                                    const double* __restrict__ x,
                                                    double* __restrict__ y,
-                                                   const double* __restrict__ rowscale) {
+                                                   const double* __restrict__ rowscale,
+                                                   const int* __restrict__ skip) {
     __shared__ double s_part[kRows][kThreads / 32];
+    if (skip && *skip) return;
     const int tid = threadIdx.x;
     const long long row0 = (long long)blockIdx.x * kRows;
     const double* a[kRows];
@@ -114,16 +116,17 @@ __global__ void __launch_bounds__(kThreads) k_gemv(const double* __restrict__ A,
 }  // namespace
 
 int launch_gemv(icqb_ctx* ctx, const double* dA, int64_t nrows, int64_t ncols, int64_t ld,
-                const double* dx, double* dy, const double* drowscale, cudaStream_t stream) {
+                const double* dx, double* dy, const double* drowscale, cudaStream_t stream,
+                const int* skip) {
     if (nrows <= 0) return ICQB_OK;
     if (ncols < 0 || ld < ncols) return set_error(ctx, ICQB_EARG, "gemv: need ld >= ncols >= 0");
     const unsigned blocks = (unsigned)((nrows + kRows - 1) / kRows);
     const bool aligned = ((reinterpret_cast<uintptr_t>(dA) & 15) == 0) && ((ld & 1) == 0) &&
                          ((reinterpret_cast<uintptr_t>(dx) & 15) == 0);
     if (aligned)
-        k_gemv<true><<<blocks, kThreads, 0, stream>>>(dA, nrows, ncols, ld, dx, dy, drowscale);
+        k_gemv<true><<<blocks, kThreads, 0, stream>>>(dA, nrows, ncols, ld, dx, dy, drowscale, skip);
     else
-        k_gemv<false><<<blocks, kThreads, 0, stream>>>(dA, nrows, ncols, ld, dx, dy, drowscale);
+        k_gemv<false><<<blocks, kThreads, 0, stream>>>(dA, nrows, ncols, ld, dx, dy, drowscale, skip);
     ctx->launches += 1;
     return check_cuda(ctx, cudaGetLastError(), "k_gemv launch");
 }

@@ -70,10 +70,11 @@ int launch_diag_rows(icqb_ctx* ctx, int order, long long g0, long long g1, doubl
                      int64_t stride);
 int launch_symv(icqb_ctx* ctx, const double* dA, int64_t ld, const double* dx,
                 const double* dgamma, const double* dalpha, const double* dbeta, double* dz,
-                cudaStream_t stream);
+                cudaStream_t stream, const int* skip = nullptr);
 int launch_diag(icqb_ctx* ctx, int order, double* dOut, int64_t stride);
 int launch_gemv(icqb_ctx* ctx, const double* dA, int64_t nrows, int64_t ncols, int64_t ld,
-                const double* dx, double* dy, const double* drowscale, cudaStream_t stream);
+                const double* dx, double* dy, const double* drowscale, cudaStream_t stream,
+                const int* skip = nullptr);
 
 // NCCL plumbing (comm.cu); all no-ops for a single rank
 int comm_nranks(const icqb_ctx* ctx);

@@ -35,7 +35,7 @@ constexpr int kT = 128;          // tile edge
 constexpr int kWarps = 8;
 constexpr int kThreads = kWarps * 32;
 constexpr int kRowsPerWarp = kT / kWarps;   // 16
-constexpr int kChunk = 8;        // tiles per task
+constexpr int kChunk = 4;        // tiles per task (512 KB of matrix)
 
 struct SymvTask {
     int lt;        // local strip (tile row) index
@@ -48,6 +48,7 @@ struct SymvParams {
     long long r0, r1, q0, q1;   // row blocks (multiples of 128 at the start)
     int nTiles0, nLocal;        // strips of the first block / all local strips
     const SymvTask* tasks;
+    const int* order;           // launch order: longest tasks first
     const int* taskBegin;       // [nLocal+1] first task of each strip
     const double* x;            // [n]
     const double* gamma;        // [n] or null
@@ -57,6 +58,7 @@ struct SymvParams {
     double* Wr;                 // [nTasks][128]  row partials per task
     long long wcols;
     double* z;                  // [n]
+    const int* skip;            // when non-null and *skip != 0 the kernels return at once
 };
 
 __device__ __forceinline__ double2 ld_stream2(const double* p) {
@@ -84,8 +86,10 @@ __global__ void __launch_bounds__(kThreads, 2) k_symv(const SymvParams P) {
     __shared__ double s_u[kT];                    // gamma . x for the strip's rows
     __shared__ double s_col[2][kWarps][kT];       // column partials, double buffered
 
+    if (P.skip && *P.skip) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const SymvTask task = P.tasks[blockIdx.x];
+    const int taskId = P.order[blockIdx.x];
+    const SymvTask task = P.tasks[taskId];
     long long obs0, obsEnd, lrow0;
     strip_of(P, task.lt, &obs0, &obsEnd, &lrow0);
     const int I = (int)(obs0 / kT);
@@ -183,12 +187,13 @@ __global__ void __launch_bounds__(kThreads, 2) k_symv(const SymvParams P) {
         double v = rowacc[k];
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-        if (lane == 0) P.Wr[(long long)blockIdx.x * kT + warp + kWarps * k] = v;
+        if (lane == 0) P.Wr[(long long)taskId * kT + warp + kWarps * k] = v;
     }
 }
 
 // z[j] = alpha_j * (sum of row partials of j's strip) + beta_j * (sum over strips below of Wc)
 __global__ void __launch_bounds__(256) k_symv_reduce(const SymvParams P) {
+    if (P.skip && *P.skip) return;
     const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= P.n) return;
     const int J = (int)(j / kT);
@@ -220,6 +225,7 @@ struct SymvPlan {
     int nTiles0 = 0, nLocal = 0, nTasks = 0;
     long long wcols = 0;
     SymvTask* d_tasks = nullptr;
+    int* d_order = nullptr;
     int* d_taskBegin = nullptr;
     double* d_Wc = nullptr;
     double* d_Wr = nullptr;
@@ -229,6 +235,7 @@ void symv_plan_free(icqb_ctx* ctx) {
     SymvPlan* p = ctx->symv;
     if (!p) return;
     cudaFree(p->d_tasks);
+    cudaFree(p->d_order);
     cudaFree(p->d_taskBegin);
     cudaFree(p->d_Wc);
     cudaFree(p->d_Wr);
@@ -265,6 +272,14 @@ static int symv_plan(icqb_ctx* ctx) {
     begin[p->nLocal] = (int)tasks.size();
     p->nTasks = (int)tasks.size();
     if (p->nTasks == 0) return ICQB_OK;
+    std::vector<int> order(tasks.size());
+    for (size_t t = 0; t < order.size(); ++t) order[t] = (int)t;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+        return (tasks[a].j1 - tasks[a].j0) > (tasks[b].j1 - tasks[b].j0);
+    });
+    ICQB_CUDA(ctx, cudaMalloc(&p->d_order, sizeof(int) * order.size()));
+    ICQB_CUDA(ctx, cudaMemcpy(p->d_order, order.data(), sizeof(int) * order.size(),
+                              cudaMemcpyHostToDevice));
     ICQB_CUDA(ctx, cudaMalloc(&p->d_tasks, sizeof(SymvTask) * tasks.size()));
     ICQB_CUDA(ctx, cudaMalloc(&p->d_taskBegin, sizeof(int) * begin.size()));
     ICQB_CUDA(ctx, cudaMalloc(&p->d_Wc, sizeof(double) * (size_t)p->nLocal * p->wcols));
@@ -278,7 +293,7 @@ static int symv_plan(icqb_ctx* ctx) {
 
 int launch_symv(icqb_ctx* ctx, const double* dA, int64_t ld, const double* dx,
                 const double* dgamma, const double* dalpha, const double* dbeta, double* dz,
-                cudaStream_t stream) {
+                cudaStream_t stream, const int* skip) {
     if (ctx->ntri == 0) return ICQB_OK;
     if ((reinterpret_cast<uintptr_t>(dA) & 15) != 0 || (ld & 1) != 0 || ld < ctx->ntri)
         return set_error(ctx, ICQB_EARG, "symv: matrix must be 16-byte aligned with an even ld >= n");
@@ -293,6 +308,7 @@ int launch_symv(icqb_ctx* ctx, const double* dA, int64_t ld, const double* dx,
     P.nTiles0 = p->nTiles0;
     P.nLocal = p->nLocal;
     P.tasks = p->d_tasks;
+    P.order = p->d_order;
     P.taskBegin = p->d_taskBegin;
     P.x = dx;
     P.gamma = dgamma;
@@ -302,6 +318,7 @@ int launch_symv(icqb_ctx* ctx, const double* dA, int64_t ld, const double* dx,
     P.Wr = p->d_Wr;
     P.wcols = p->wcols;
     P.z = dz;
+    P.skip = skip;
     if (p->nTasks > 0) {
         k_symv<<<p->nTasks, kThreads, 0, stream>>>(P);
         ctx->launches += 1;

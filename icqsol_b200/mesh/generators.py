@@ -62,6 +62,11 @@ def fanSplit(cells):
     (v0,v1,v2),(v0,v2,v3),...  The reference triangulates with pytriangle
     (shapes/icqRefineSurface.py:204-306), which is not available here; for
     triangles this is the identity, for convex polygons it is a valid split."""
+    if isinstance(cells, numpy.ndarray) and cells.ndim == 2:
+        k = cells.shape[1]
+        if k == 3:
+            return numpy.ascontiguousarray(cells, numpy.int64)
+        return numpy.stack([cells[:, [0, j, j + 1]] for j in range(1, k - 1)], 1).reshape(-1, 3)
     out = []
     for c in cells:
         for k in range(1, len(c) - 1):

@@ -85,22 +85,49 @@ class Points:
 
 
 class CellArray:
-    """vtkCellArray subset; cells are stored as a list of id tuples."""
+    """vtkCellArray subset.  Cells of one size (the usual all-triangles case) are kept
+    as an int64[ncells, k] array; mixed polygons as a list of id tuples."""
 
     def __init__(self, cells=None):
-        self._cells = [tuple(int(v) for v in c) for c in cells] if cells is not None else []
+        self._array = None
+        self._list = None
+        if cells is None:
+            self._list = []
+        elif isinstance(cells, numpy.ndarray) and cells.ndim == 2:
+            self._array = numpy.ascontiguousarray(cells, numpy.int64)
+        else:
+            self._list = [tuple(int(v) for v in c) for c in cells]
         self._cur = 0
 
+    @property
+    def _cells(self):
+        """Cells as a list of id tuples (materialised on demand)."""
+        if self._list is None:
+            self._list = [tuple(row) for row in self._array.tolist()]
+            self._array = None
+        return self._list
+
+    def as_array(self):
+        """int64[ncells, k] when every cell has k vertices, else None."""
+        if self._array is not None:
+            return self._array
+        if self._list and len(set(len(c) for c in self._list)) == 1:
+            return numpy.asarray(self._list, numpy.int64)
+        return None
+
     def GetNumberOfCells(self):
-        return len(self._cells)
+        return self._array.shape[0] if self._array is not None else len(self._list)
 
     def InitTraversal(self):
         self._cur = 0
 
     def GetNextCell(self, idList):
-        if self._cur >= len(self._cells):
+        if self._cur >= self.GetNumberOfCells():
             return 0
-        idList._assign(self._cells[self._cur])
+        if self._array is not None:
+            idList._assign(self._array[self._cur])
+        else:
+            idList._assign(self._list[self._cur])
         self._cur += 1
         return 1
 
@@ -111,7 +138,7 @@ class CellArray:
             else:
                 ids = arg
         self._cells.append(tuple(int(v) for v in ids))
-        return len(self._cells) - 1
+        return len(self._list) - 1
 
 
 class DataArray:
@@ -241,13 +268,15 @@ def new_double_array(pdata):
 
 
 def extract_mesh(pdata):
-    """Points float64[Np,3] and polygons (list of id tuples) of a duck-typed polydata.
+    """Points float64[Np,3] and polygons of a duck-typed polydata: an int64[ncells,k]
+    array when every cell has k vertices (stand-in only), else a list of id tuples.
 
     Mirrors the traversal at bem/icqBaseSolver.py:25-38 and
     bem/icqLaplaceMatrices.cpp:54-71.
     """
     if isinstance(pdata, PolyData):
-        return pdata._points.as_float64(), list(pdata._polys._cells)
+        arr = pdata._polys.as_array()
+        return pdata._points.as_float64(), (arr if arr is not None else list(pdata._polys._cells))
     points = pdata.GetPoints()
     npts = points.GetNumberOfPoints()
     xyz = numpy.zeros((npts, 3), numpy.float64)
