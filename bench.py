@@ -243,9 +243,16 @@ def run_b200(args):
         ctx.check(lib.icqb_set_rows(ctx.handle, r0, r1))
     rows = (blocks[1] - blocks[0]) + (blocks[3] - blocks[2])
     ld = leadingDimension(n)
-    gbuf = torch.empty((max(rows, 1), ld), dtype=torch.float64, device=dev)
-    kbuf = torch.empty((max(rows, 1), ld), dtype=torch.float64, device=dev)
-    kubuf = torch.empty((max(rows, 1), ld), dtype=torch.float64, device=dev) if lower else None
+    if lower:
+        ntiles = int(lib.icqb_lower_num_tiles(ctx.handle))
+        shape = (max(ntiles, 1), 128, 128)
+        gbuf = torch.zeros(shape, dtype=torch.float64, device=dev)
+        kbuf = torch.zeros(shape, dtype=torch.float64, device=dev)
+        kubuf = torch.zeros(shape, dtype=torch.float64, device=dev)
+    else:
+        gbuf = torch.empty((max(rows, 1), ld), dtype=torch.float64, device=dev)
+        kbuf = torch.empty((max(rows, 1), ld), dtype=torch.float64, device=dev)
+        kubuf = None
     bdev = torch.from_numpy(v).to(dev)
     xdev = torch.zeros(n, dtype=torch.float64, device=dev)
     area2 = lib.icqb_area2_dev(ctx.handle)
@@ -259,7 +266,7 @@ def run_b200(args):
                 h = min(128, e - t0)
                 w_diag = min(128, n - t0)
                 pairs_local += h * t0 + h * (w_diag - 1)      # below the diagonal tile + inside it
-                stored += h * t0 + h * w_diag
+                stored += 128.0 * t0 + 128.0 * 128.0    # whole tiles are streamed
     else:
         pairs_local = rows * (rows - 1) / 2.0 + rows * (n - rows)
         stored = float(rows) * n
@@ -274,7 +281,7 @@ def run_b200(args):
         t0 = time.perf_counter()
         if lower:
             ctx.check(lib.icqb_assemble_lower_dev(ctx.handle, 5, gbuf.data_ptr(), kbuf.data_ptr(),
-                                                  kubuf.data_ptr(), ld))
+                                                  kubuf.data_ptr()))
         else:
             ctx.check(lib.icqb_assemble_dev(ctx.handle, 5, gbuf.data_ptr(), kbuf.data_ptr(), ld))
         t1 = time.perf_counter()

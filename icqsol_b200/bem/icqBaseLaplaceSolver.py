@@ -92,15 +92,23 @@ class BaseLaplaceSolver(BaseSolver):
             (self.rowBlocks[3] - self.rowBlocks[2])
 
         self.ld = leadingDimension(n)
-        rows = max(self.numLocalRows, 1)
         dev = torch.device('cuda', self.device)
-        self.gMatDevice = torch.empty((rows, self.ld), dtype=torch.float64, device=dev)
         self.kMatDevice = None
         self.kMatUpperDevice = None
-        if computeK:
-            self.kMatDevice = torch.empty((rows, self.ld), dtype=torch.float64, device=dev)
-            if storage == 'lower':
-                self.kMatUpperDevice = torch.empty((rows, self.ld), dtype=torch.float64, device=dev)
+        if storage == 'lower':
+            # tile-contiguous lower triangle: [numTiles, 128, 128]; zero-filled because the
+            # ragged edge tiles are only partly written
+            self.numLocalTiles = int(self.lib.icqb_lower_num_tiles(self.ctx.handle))
+            shape = (max(self.numLocalTiles, 1), rowPartition.TILE, rowPartition.TILE)
+            self.gMatDevice = torch.zeros(shape, dtype=torch.float64, device=dev)
+            if computeK:
+                self.kMatDevice = torch.zeros(shape, dtype=torch.float64, device=dev)
+                self.kMatUpperDevice = torch.zeros(shape, dtype=torch.float64, device=dev)
+        else:
+            rows = max(self.numLocalRows, 1)
+            self.gMatDevice = torch.empty((rows, self.ld), dtype=torch.float64, device=dev)
+            if computeK:
+                self.kMatDevice = torch.empty((rows, self.ld), dtype=torch.float64, device=dev)
         self.gMat = None   # host copy, made on demand
         self.kMat = None
 
@@ -112,7 +120,7 @@ class BaseLaplaceSolver(BaseSolver):
         if self.storage == 'lower':
             kuPtr = self.kMatUpperDevice.data_ptr() if self.kMatUpperDevice is not None else 0
             self.ctx.check(self.lib.icqb_assemble_lower_dev(
-                self.ctx.handle, int(self.order), self.gMatDevice.data_ptr(), kPtr, kuPtr, self.ld))
+                self.ctx.handle, int(self.order), self.gMatDevice.data_ptr(), kPtr, kuPtr))
         else:
             self.ctx.check(self.lib.icqb_assemble_dev(self.ctx.handle, int(self.order),
                                                       self.gMatDevice.data_ptr(), kPtr, self.ld))
@@ -129,9 +137,11 @@ class BaseLaplaceSolver(BaseSolver):
 
     def __gatherStored(self, devMat):
         n = self.numTriangles
-        local = devMat[:self.numLocalRows, :n].cpu().numpy()
         if self.storage == 'lower':
+            tiles = devMat[:self.numLocalTiles].cpu().numpy()
+            local = rowPartition.lowerTilesToRows(tiles, self.rowBlocks, n)
             return rowPartition.gatherFoldedRows(local, n)
+        local = devMat[:self.numLocalRows, :n].cpu().numpy()
         return rowPartition.allGatherMatrixRows(local, n)
 
     def __tileMask(self):
@@ -174,15 +184,20 @@ class BaseLaplaceSolver(BaseSolver):
         return self.kMat
 
     def getGreenMatrixDevice(self):
-        """Locally stored rows of G in HBM, torch float64[numLocalRows, N] (a view).
-        storage='full': rows [rowBegin, rowEnd) complete.  storage='lower': the rows of
-        getRowBlocks() one after the other, valid up to and including each row's
-        diagonal 128-column tile."""
+        """The part of G resident in this rank's HBM (a torch float64 view).
+        storage='full': rows [rowBegin, rowEnd) complete, float64[rows, N].
+        storage='lower': float64[numLocalTiles, 128, 128], the tile-contiguous lower
+        triangle of the rows in getRowBlocks() (icqRowPartition.lowerStrips gives the
+        strip -> tile map; icqRowPartition.lowerTilesToRows rebuilds rows on the host)."""
+        if self.storage == 'lower':
+            return self.gMatDevice[:self.numLocalTiles]
         return self.gMatDevice[:self.numLocalRows, :self.numTriangles]
 
     def getNormalDerivativeGreenMatrixDevice(self):
         if self.kMatDevice is None:
             raise RuntimeError('ERROR: K was not assembled; construct the solver with computeK=True')
+        if self.storage == 'lower':
+            return self.kMatDevice[:self.numLocalTiles]
         return self.kMatDevice[:self.numLocalRows, :self.numTriangles]
 
     def getRowRange(self):
@@ -211,7 +226,7 @@ class BaseLaplaceSolver(BaseSolver):
         if self.storage == 'lower':
             y = torch.empty(n, dtype=torch.float64, device=x.device)
             self.ctx.check(self.lib.icqb_symv_dev(self.ctx.handle, self.gMatDevice.data_ptr(),
-                                                  self.ld, x.data_ptr(), y.data_ptr(), 0))
+                                                  x.data_ptr(), y.data_ptr(), 0))
             self.ctx.check(self.lib.icqb_synchronize(self.ctx.handle))
             return y.cpu().numpy()
         rows = self.rowEnd - self.rowBegin

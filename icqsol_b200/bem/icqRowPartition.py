@@ -54,6 +54,35 @@ def foldedBlocks(n, rank, nranks):
     return r0, r1, q0, q1
 
 
+def lowerStrips(blocks):
+    """[(first global row, rows in the strip, global tile row I, index of its tile J=0)]
+    for the 128-row strips of row blocks (r0, r1, q0, q1), in storage order -- the
+    tile-contiguous layout of include/icqb.h (icqb_assemble_lower_dev)."""
+    strips, tile = [], 0
+    for (b, e) in ((blocks[0], blocks[1]), (blocks[2], blocks[3])):
+        for row0 in range(b, e, TILE):
+            tileRow = row0 // TILE
+            strips.append((row0, min(TILE, e - row0), tileRow, tile))
+            tile += tileRow + 1
+    return strips, tile
+
+
+def lowerTilesToRows(tiles, blocks, n):
+    """Local tile sequence float64[ntiles, 128, 128] -> stored rows float64[rows, n]
+    (columns beyond each row's diagonal tile are left zero)."""
+    strips, ntiles = lowerStrips(blocks)
+    rows = (blocks[1] - blocks[0]) + (blocks[3] - blocks[2])
+    out = numpy.zeros((rows, n), numpy.float64)
+    lrow = 0
+    for (row0, nrows, tileRow, base) in strips:
+        t = tiles[base:base + tileRow + 1]                     # [I+1, 128, 128]
+        strip = t.transpose(1, 0, 2).reshape(TILE, (tileRow + 1) * TILE)
+        ncols = min(n, (tileRow + 1) * TILE)
+        out[lrow:lrow + nrows, :ncols] = strip[:nrows, :ncols]
+        lrow += nrows
+    return out
+
+
 def foldedBlockSize(n, nranks):
     n, nranks = int(n), int(nranks)
     return max(TILE, (n + 2 * nranks * TILE - 1) // (2 * nranks * TILE) * TILE)

@@ -27,6 +27,18 @@ __global__ void k_reciprocal(const double* a, double* out, long long n) {
         out[i] = 1.0 / a[i];
 }
 
+// compact self terms (row order of the two blocks) -> diagonal entries of the diagonal tiles
+__global__ void k_scatter_diag_lower(const double* diag, LowerLayout L, double* G) {
+    const long long rows = (L.r1 - L.r0) + (L.q1 - L.q0);
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < rows;
+         k += (long long)gridDim.x * blockDim.x) {
+        const long long i = k < (L.r1 - L.r0) ? L.r0 + k : L.q0 + (k - (L.r1 - L.r0));
+        const int lt = L.stripOf(i);
+        const long long I = i / kLowerTile, r = i - I * kLowerTile;
+        G[(L.tileBase(lt) + I) * kLowerTileElems + r * kLowerTile + r] = diag[k];
+    }
+}
+
 int launch_reciprocal(icqb_ctx* ctx, const double* a, double* out, long long n) {
     k_reciprocal<<<128, 256, 0, ctx->stream>>>(a, out, n);
     ctx->launches += 1;
@@ -69,13 +81,11 @@ int icqb_assemble_dev(icqb_ctx* ctx, int diag_order, uint64_t dG, uint64_t dK, i
     return finish_phase(ctx, kOffDiag);
 }
 
-int icqb_assemble_lower_dev(icqb_ctx* ctx, int diag_order, uint64_t dG, uint64_t dKl, uint64_t dKu,
-                            int64_t ld) {
+int icqb_assemble_lower_dev(icqb_ctx* ctx, int diag_order, uint64_t dG, uint64_t dKl, uint64_t dKu) {
     if (!ctx) return ICQB_EARG;
     if (ctx->ntri == 0) return ICQB_OK;
     if (!ctx->d_qp_aos) return set_error(ctx, ICQB_ESTATE, "icqb_assemble_lower_dev: no mesh set");
-    if (!dG || ld < ctx->ntri || (ld & 1))
-        return set_error(ctx, ICQB_EARG, "icqb_assemble_lower_dev: null G, ld < ntri or odd ld");
+    if (!dG) return set_error(ctx, ICQB_EARG, "icqb_assemble_lower_dev: null G");
     if ((dKl == 0) != (dKu == 0))
         return set_error(ctx, ICQB_EARG, "icqb_assemble_lower_dev: pass both K buffers or neither");
     if (diag_order != 0 && (diag_order < 1 || diag_order > 5))
@@ -83,24 +93,31 @@ int icqb_assemble_lower_dev(icqb_ctx* ctx, int diag_order, uint64_t dG, uint64_t
                          "diagonal order must be in 1..5 (KeyError in the reference)");
     ICQB_CUDA(ctx, cudaSetDevice(ctx->device));
     double* G = reinterpret_cast<double*>(dG);
-    if (diag_order != 0) {
-        cudaEventRecord(ctx->ev0, ctx->stream);
-        int st = launch_diag_rows(ctx, diag_order, ctx->r0, ctx->r1, G + ctx->r0, ld + 1);
-        if (st == ICQB_OK)
-            st = launch_diag_rows(ctx, diag_order, ctx->q0, ctx->q1,
-                                  G + (ctx->r1 - ctx->r0) * ld + ctx->q0, ld + 1);
-        cudaEventRecord(ctx->ev1, ctx->stream);
+    LowerLayout L;
+    int st = lower_layout(ctx, &L);
+    if (st != ICQB_OK) return st;
+    const long long rows = (L.r1 - L.r0) + (L.q1 - L.q0);
+    if (diag_order != 0 && rows > 0) {
+        // self terms into a compact vector, then placed on the diagonal of the diagonal tiles
+        st = ensure_work(ctx, rows + 64);
         if (st != ICQB_OK) return st;
+        cudaEventRecord(ctx->ev0, ctx->stream);
+        st = launch_diag_rows(ctx, diag_order, L.r0, L.r1, ctx->d_work, 1);
+        if (st == ICQB_OK)
+            st = launch_diag_rows(ctx, diag_order, L.q0, L.q1, ctx->d_work + (L.r1 - L.r0), 1);
+        if (st != ICQB_OK) return st;
+        k_scatter_diag_lower<<<128, 256, 0, ctx->stream>>>(ctx->d_work, L, G);
+        ctx->launches += 1;
+        cudaEventRecord(ctx->ev1, ctx->stream);
         st = finish_phase(ctx, kDiag);
         if (st != ICQB_OK) return st;
     }
-    int st = launch_offdiag_lower(ctx, G, reinterpret_cast<double*>(dKl),
-                                  reinterpret_cast<double*>(dKu), ld);
+    st = launch_offdiag_lower(ctx, G, reinterpret_cast<double*>(dKl), reinterpret_cast<double*>(dKu));
     if (st != ICQB_OK) return st;
     return finish_phase(ctx, kOffDiag);
 }
 
-int icqb_symv_dev(icqb_ctx* ctx, uint64_t dA, int64_t ld, uint64_t dx, uint64_t dy, int scaled) {
+int icqb_symv_dev(icqb_ctx* ctx, uint64_t dA, uint64_t dx, uint64_t dy, int scaled) {
     if (!ctx) return ICQB_EARG;
     if (!dA || !dx || !dy) return set_error(ctx, ICQB_EARG, "icqb_symv_dev: null pointer");
     if (!ctx->d_area2) return set_error(ctx, ICQB_ESTATE, "icqb_symv_dev: no mesh set");
@@ -115,7 +132,7 @@ int icqb_symv_dev(icqb_ctx* ctx, uint64_t dA, int64_t ld, uint64_t dx, uint64_t 
         if (st != ICQB_OK) return st;
     }
     cudaEventRecord(ctx->ev0, ctx->stream);
-    int st = launch_symv(ctx, reinterpret_cast<const double*>(dA), ld,
+    int st = launch_symv(ctx, reinterpret_cast<const double*>(dA),
                          reinterpret_cast<const double*>(dx), ctx->d_area2,
                          scaled ? ctx->d_area2 : nullptr, scaled ? nullptr : inv,
                          reinterpret_cast<double*>(dy), ctx->stream);

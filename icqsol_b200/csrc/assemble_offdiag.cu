@@ -50,10 +50,9 @@ struct OffDiagParams {
     double* Ku;             // lower mode only: Ku[i,j] = K[j,i] at the position of (i,j)
     long long ld;
     long long n, npad;
-    long long r0, r1;       // full mode: the row block; lower mode: first row block
-    long long q0, q1;       // lower mode: second row block (may be empty)
+    long long r0, r1;       // full mode: the row block
     long long nObsTiles, nLeft, nRight;  // full mode tile counts: local rows, columns < r0, >= r1
-    long long nTiles0;      // lower mode: observer tiles of the first block
+    LowerLayout L;          // lower mode: row blocks and tile-contiguous layout
     int lower;              // 1 = block-lower-triangular storage
 };
 
@@ -115,7 +114,8 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 struct Tile {
     long long obs0;   // first observer triangle (global index)
     long long obsEnd; // one past the last observer triangle of the row block
-    long long lrow0;  // local (storage) row of obs0
+    long long lrow0;  // full mode: local (storage) row of obs0
+    long long tile;   // lower mode: index of this tile in the local tile sequence
     long long src0;   // first source triangle
     long long srcEnd; // one past the last valid source triangle of this tile's range
     int kind;         // 0 = diagonal tile, 1 = mirrored (I > J inside the block), 2 = direct only,
@@ -127,17 +127,12 @@ __device__ __forceinline__ Tile decode_tile(const OffDiagParams& P, long long ta
     Tile t;
     if (P.lower) {
         // 2-D grid: x = global source tile J, y = local observer tile; only J <= I is stored
-        const long long lt = blockIdx.y;
-        if (lt < P.nTiles0) {
-            t.obs0 = P.r0 + lt * kTileObs;
-            t.obsEnd = P.r1;
-            t.lrow0 = lt * kTileObs;
-        } else {
-            t.obs0 = P.q0 + (lt - P.nTiles0) * kTileObs;
-            t.obsEnd = P.q1;
-            t.lrow0 = (P.r1 - P.r0) + (lt - P.nTiles0) * kTileObs;
-        }
+        const int lt = blockIdx.y;
+        t.obs0 = P.L.obs0(lt);
+        t.obsEnd = P.L.obsEnd(lt);
+        t.lrow0 = 0;
         const long long I = t.obs0 / kTileObs, J = blockIdx.x;
+        t.tile = P.L.tileBase(lt) + J;
         t.src0 = J * kTileSrc;
         t.srcEnd = (J == I) ? min(P.n, t.src0 + kTileSrc) : t.src0 + kTileSrc;
         t.kind = (J > I) ? -1 : (J == I ? 0 : 3);
@@ -154,6 +149,7 @@ __device__ __forceinline__ Tile decode_tile(const OffDiagParams& P, long long ta
         t.obs0 = P.r0 + I * kTileObs;
         t.obsEnd = P.r1;
         t.lrow0 = I * kTileObs;
+        t.tile = 0;
         t.src0 = P.r0 + J * kTileSrc;
         t.srcEnd = P.r1;
         t.kind = (I == J) ? 0 : 1;
@@ -165,6 +161,7 @@ __device__ __forceinline__ Tile decode_tile(const OffDiagParams& P, long long ta
     t.obs0 = P.r0 + I * kTileObs;
     t.obsEnd = P.r1;
     t.lrow0 = I * kTileObs;
+    t.tile = 0;
     t.kind = 2;
     if (J < P.nLeft) {
         t.src0 = J * kTileSrc;
@@ -232,11 +229,14 @@ __global__ void __launch_bounds__(kTileObs) k_offdiag(const OffDiagParams P) {
         paz = __ldg(P.verts + 9 * iLoad + 2);
     }
 
-    // storage row of this observer (clamped lanes never store)
-    const long long lrow = T.lrow0 + (obsValid ? tid : 0);
-    double* gRow = P.G + lrow * P.ld;
-    double* kRow = WITH_K ? (P.K + lrow * P.ld) : nullptr;
-    double* kuRow = (WITH_K && P.lower) ? (P.Ku + lrow * P.ld) : nullptr;
+    // storage row of this observer, indexed by the GLOBAL column j (clamped lanes never store):
+    // full mode  row-major rows of pitch ld;  lower mode  row `tid` of the contiguous tile
+    const long long rowOff = P.lower
+        ? T.tile * kLowerTileElems + (long long)(obsValid ? tid : 0) * kLowerTile - T.src0
+        : (T.lrow0 + (obsValid ? tid : 0)) * P.ld;
+    double* gRow = P.G + rowOff;
+    double* kRow = WITH_K ? (P.K + rowOff) : nullptr;
+    double* kuRow = (WITH_K && P.lower) ? (P.Ku + rowOff) : nullptr;
 
     for (int sub = 0; sub < nSubTiles; ++sub) {
         const int stage = sub & 1;
@@ -341,7 +341,7 @@ __global__ void __launch_bounds__(kTileObs) k_offdiag(const OffDiagParams P) {
 
 }  // namespace
 
-int launch_offdiag_lower(icqb_ctx* ctx, double* dG, double* dK, double* dKu, int64_t ld) {
+int launch_offdiag_lower(icqb_ctx* ctx, double* dG, double* dK, double* dKu) {
     if (ctx->ntri == 0) return ICQB_OK;
     OffDiagParams P;
     P.qp_soa = ctx->d_qp_soa;
@@ -352,22 +352,17 @@ int launch_offdiag_lower(icqb_ctx* ctx, double* dG, double* dK, double* dKu, int
     P.G = dG;
     P.K = dK;
     P.Ku = dKu;
-    P.ld = ld;
+    P.ld = 0;
     P.n = ctx->ntri;
     P.npad = ctx->ntri_pad;
-    P.r0 = ctx->r0;
-    P.r1 = ctx->r1;
-    P.q0 = ctx->q0;
-    P.q1 = ctx->q1;
+    P.r0 = P.r1 = 0;
     P.nObsTiles = P.nLeft = P.nRight = 0;
     P.lower = 1;
-    if ((P.r1 > P.r0 && (P.r0 % kTileObs) != 0) || (P.q1 > P.q0 && (P.q0 % kTileObs) != 0))
-        return set_error(ctx, ICQB_EARG, "lower storage: row blocks must start on multiples of 128");
-    P.nTiles0 = (P.r1 - P.r0 + kTileObs - 1) / kTileObs;
-    const long long nTiles1 = (P.q1 - P.q0 + kTileObs - 1) / kTileObs;
-    const long long lastRow = (P.q1 > P.q0) ? P.q1 : P.r1;
-    const long long nLocal = P.nTiles0 + nTiles1;
+    int st = lower_layout(ctx, &P.L);
+    if (st != ICQB_OK) return st;
+    const long long nLocal = P.L.nLocal();
     if (nLocal == 0) return ICQB_OK;
+    const long long lastRow = (P.L.q1 > P.L.q0) ? P.L.q1 : P.L.r1;
     const long long nSrcTiles = (lastRow + kTileSrc - 1) / kTileSrc;   // J <= I for every local I
     if (nLocal > 65535) return set_error(ctx, ICQB_EARG, "too many observer tiles for one launch");
     dim3 grid((unsigned)nSrcTiles, (unsigned)nLocal);
@@ -385,8 +380,7 @@ int launch_offdiag(icqb_ctx* ctx, double* dG, double* dK, int64_t ld) {
     if (ctx->ntri == 0 || ctx->r1 <= ctx->r0) return ICQB_OK;
     OffDiagParams P;
     P.Ku = nullptr;
-    P.q0 = P.q1 = 0;
-    P.nTiles0 = 0;
+    P.L = LowerLayout{0, 0, 0, 0, 0, 0, 0};
     P.lower = 0;
     P.qp_soa = ctx->d_qp_soa;
     P.qp_aos = ctx->d_qp_aos;

@@ -96,6 +96,18 @@ __global__ void __launch_bounds__(kVT) k_cg_diag(const double* A, long long ld, 
         d[i] = A[(lrow0 + (i - g0)) * ld + i];
 }
 
+// diagonal of the tile-contiguous lower storage into a zeroed full-length vector
+__global__ void __launch_bounds__(kVT) k_cg_diag_lower(const double* A, LowerLayout L, double* d) {
+    const long long rows = (L.r1 - L.r0) + (L.q1 - L.q0);
+    for (long long k = (long long)blockIdx.x * kVT + threadIdx.x; k < rows;
+         k += (long long)kNB * kVT) {
+        const long long i = k < (L.r1 - L.r0) ? L.r0 + k : L.q0 + (k - (L.r1 - L.r0));
+        const int lt = L.stripOf(i);
+        const long long I = i / kLowerTile, r = i - I * kLowerTile;
+        d[i] = A[(L.tileBase(lt) + I) * kLowerTileElems + r * kLowerTile + r];
+    }
+}
+
 // r = s*b - z (z = s*(A x0)); minv = 1/(s*precond); w = r*minv; p = 0
 __global__ void __launch_bounds__(kVT) k_cg_init(long long n, const double* b,
                                                  const double* scale, const double* precond,
@@ -262,7 +274,7 @@ struct MatVec {
               const int* skip = nullptr) {
         int rc;
         if (storage == 1) {
-            rc = launch_symv(ctx, A, ld, v, area, scale ? area : nullptr,
+            rc = launch_symv(ctx, A, v, area, scale ? area : nullptr,
                              scale ? nullptr : inv_area, out, st, skip);
             if (rc != ICQB_OK) return rc;
             return comm_allreduce_sum(ctx, out, n, st);
@@ -287,7 +299,7 @@ extern "C" int icqb_cg_solve_dev(icqb_ctx* ctx, uint64_t dA_, int64_t n, int64_t
                                  uint64_t dx_, double tol, int rel, int64_t maxit, int64_t* iters,
                                  double* resid2, double* residinf) {
     if (!ctx) return ICQB_EARG;
-    if (!dA_ || !db_ || !dx_ || n <= 0 || ld < n)
+    if (!dA_ || !db_ || !dx_ || n <= 0 || (storage == 0 && ld < n))
         return set_error(ctx, ICQB_EARG, "icqb_cg_solve_dev: null pointer or bad sizes");
     if (storage != 0 && storage != 1)
         return set_error(ctx, ICQB_EARG, "icqb_cg_solve_dev: storage must be 0 (row blocks) or 1 (lower)");
@@ -370,10 +382,9 @@ extern "C" int icqb_cg_solve_dev(icqb_ctx* ctx, uint64_t dA_, int64_t n, int64_t
         // preconditioner: diag(A) unless given
         if (!precond) {
             if (storage == 1) {
-                if (ctx->r1 > ctx->r0)
-                    k_cg_diag<<<kNB, kVT, 0, st>>>(A, ld, ctx->r0, ctx->r1, 0, B.d);
-                if (ctx->q1 > ctx->q0)
-                    k_cg_diag<<<kNB, kVT, 0, st>>>(A, ld, ctx->q0, ctx->q1, ctx->r1 - ctx->r0, B.d);
+                LowerLayout L;
+                CG_TRY(lower_layout(ctx, &L));
+                k_cg_diag_lower<<<kNB, kVT, 0, st>>>(A, L, B.d);
             } else if (mv.r1 > mv.r0) {
                 k_cg_diag<<<kNB, kVT, 0, st>>>(A, ld, mv.r0, mv.r1, 0, B.d);
             }

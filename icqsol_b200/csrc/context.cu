@@ -32,6 +32,18 @@ int check_cuda(icqb_ctx* ctx, cudaError_t e, const char* what) {
     return set_error(ctx, ICQB_ECUDA, std::string(what) + ": " + cudaGetErrorString(e));
 }
 
+int lower_layout(icqb_ctx* ctx, LowerLayout* L) {
+    if ((ctx->r1 > ctx->r0 && (ctx->r0 % kLowerTile) != 0) ||
+        (ctx->q1 > ctx->q0 && (ctx->q0 % kLowerTile) != 0))
+        return set_error(ctx, ICQB_EARG, "lower storage: row blocks must start on multiples of 128");
+    L->r0 = ctx->r0; L->r1 = ctx->r1; L->q0 = ctx->q0; L->q1 = ctx->q1;
+    L->nTiles0 = (int)((L->r1 - L->r0 + kLowerTile - 1) / kLowerTile);
+    L->nTiles1 = (int)((L->q1 - L->q0 + kLowerTile - 1) / kLowerTile);
+    const long long I0 = L->r0 / kLowerTile, k0 = L->nTiles0;
+    L->tiles0 = k0 * (I0 + 1) + k0 * (k0 - 1) / 2;
+    return ICQB_OK;
+}
+
 int ensure_work(icqb_ctx* ctx, int64_t doubles) {
     if (doubles <= ctx->work_doubles) return ICQB_OK;
     if (ctx->d_work) cudaFree(ctx->d_work);
@@ -281,6 +293,13 @@ int icqb_get_rows(const icqb_ctx* ctx, int64_t* r0, int64_t* r1) {
     if (r0) *r0 = ctx->r0;
     if (r1) *r1 = ctx->r1;
     return ICQB_OK;
+}
+
+int64_t icqb_lower_num_tiles(icqb_ctx* ctx) {
+    if (!ctx) return -1;
+    LowerLayout L;
+    if (lower_layout(ctx, &L) != ICQB_OK) return -1;
+    return L.numTiles();
 }
 
 uint64_t icqb_area2_dev(const icqb_ctx* ctx) { return ctx ? (uint64_t)ctx->d_area2 : 0; }

@@ -18,6 +18,48 @@ constexpr int kPad = 128;        // triangle count is padded to a multiple of th
 // phases for icqb_last_ms
 enum Phase { kPrepare = 0, kOffDiag = 1, kDiag = 2, kGemv = 3, kCg = 4, kNumPhases = 5 };
 
+// Tile-contiguous layout of the block-lower-triangular storage: the locally owned
+// 128-row strips are stored one after the other; strip lt (global tile row I) holds its
+// tiles J = 0..I back to back, each tile a contiguous row-major 128 x 128 block (128 KB).
+// Every warp of the symmetric product therefore streams one contiguous 128 KB chunk, and
+// the storage is exactly the lower triangle: 4 N^2 + O(128 N) bytes over all ranks.
+constexpr int kLowerTile = 128;
+constexpr long long kLowerTileElems = (long long)kLowerTile * kLowerTile;
+
+struct LowerLayout {
+    long long r0, r1, q0, q1;   // row blocks (non-empty ones start on multiples of 128)
+    int nTiles0, nTiles1;       // strips per block
+    long long tiles0;           // tiles stored for the first block
+
+    __host__ __device__ int nLocal() const { return nTiles0 + nTiles1; }
+    // global tile row of local strip lt
+    __host__ __device__ long long tileRow(int lt) const {
+        return lt < nTiles0 ? r0 / kLowerTile + lt : q0 / kLowerTile + (lt - nTiles0);
+    }
+    // index of tile (lt, J = 0) in the local tile sequence
+    __host__ __device__ long long tileBase(int lt) const {
+        if (lt < nTiles0) {
+            const long long I0 = r0 / kLowerTile, k = lt;
+            return k * (I0 + 1) + k * (k - 1) / 2;
+        }
+        const long long I1 = q0 / kLowerTile, k = lt - nTiles0;
+        return tiles0 + k * (I1 + 1) + k * (k - 1) / 2;
+    }
+    __host__ __device__ long long numTiles() const { return tileBase(nLocal()); }
+    // first global row, one-past-last row of the block, of strip lt
+    __host__ __device__ long long obs0(int lt) const {
+        return lt < nTiles0 ? r0 + (long long)lt * kLowerTile
+                            : q0 + (long long)(lt - nTiles0) * kLowerTile;
+    }
+    __host__ __device__ long long obsEnd(int lt) const { return lt < nTiles0 ? r1 : q1; }
+    // local strip of global row i, or -1
+    __host__ __device__ int stripOf(long long i) const {
+        if (i >= r0 && i < r1) return (int)((i - r0) / kLowerTile);
+        if (i >= q0 && i < q1) return nTiles0 + (int)((i - q0) / kLowerTile);
+        return -1;
+    }
+};
+
 struct Comm;      // NCCL state, comm.cu
 struct SymvPlan;  // task table + workspace of the symmetric product, symv.cu
 
@@ -59,16 +101,18 @@ struct icqb_ctx {
 namespace icqb {
 
 int set_error(icqb_ctx* ctx, int code, const std::string& msg);
+// layout of the context's row blocks (sets the context error if a block is misaligned)
+int lower_layout(icqb_ctx* ctx, LowerLayout* L);
 int check_cuda(icqb_ctx* ctx, cudaError_t e, const char* what);
 int ensure_work(icqb_ctx* ctx, int64_t doubles);
 
 // kernels' host launchers (each returns ICQB_OK or sets the context error)
 int launch_prepare(icqb_ctx* ctx);
 int launch_offdiag(icqb_ctx* ctx, double* dG, double* dK, int64_t ld);
-int launch_offdiag_lower(icqb_ctx* ctx, double* dG, double* dK, double* dKu, int64_t ld);
+int launch_offdiag_lower(icqb_ctx* ctx, double* dG, double* dK, double* dKu);
 int launch_diag_rows(icqb_ctx* ctx, int order, long long g0, long long g1, double* dOut,
                      int64_t stride);
-int launch_symv(icqb_ctx* ctx, const double* dA, int64_t ld, const double* dx,
+int launch_symv(icqb_ctx* ctx, const double* dA, const double* dx,
                 const double* dgamma, const double* dalpha, const double* dbeta, double* dz,
                 cudaStream_t stream, const int* skip = nullptr);
 int launch_diag(icqb_ctx* ctx, int order, double* dOut, int64_t stride);

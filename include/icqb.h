@@ -92,17 +92,20 @@ int icqb_area2_host(icqb_ctx* ctx, double* out); /* same values, host double[ntr
  * DESIGN.md); K[i,i] = 0.  Asynchronous on the context stream. */
 int icqb_assemble_dev(icqb_ctx* ctx, int diag_order, uint64_t dG, uint64_t dK, int64_t ld);
 
-/* Lower storage: rows of the two blocks are stored one after the other (local row =
- * position in [r0,r1) ++ [q0,q1)), pitch ld (even).  Only tiles J <= I are written; every
- * pair of triangles is evaluated exactly once over the whole set of ranks and nothing is
- * mirrored.  dKl[i,j] = K[i,j] and dKu[i,j] = K[j,i] for the stored positions (both 0 or
- * both non-zero). */
-int icqb_assemble_lower_dev(icqb_ctx* ctx, int diag_order, uint64_t dG, uint64_t dKl, uint64_t dKu,
-                            int64_t ld);
+/* Lower storage, tile-contiguous: the 128-row strips of the two blocks are stored one
+ * after the other; a strip with global tile row I holds its tiles J = 0..I back to back,
+ * each tile a contiguous row-major 128 x 128 block.  icqb_lower_num_tiles() tiles of
+ * 16384 doubles per buffer; tile (strip lt, J) is number tileBase(lt) + J with
+ * tileBase(lt) = sum over earlier strips of (their I + 1).  Every pair of triangles is
+ * evaluated exactly once over the whole set of ranks and nothing is mirrored.
+ * dKl[i,j] = K[i,j] and dKu[i,j] = K[j,i] at the stored positions (both 0 or both set).
+ * Rows/columns of ragged edge tiles beyond ntri are never written (zero the buffers). */
+int64_t icqb_lower_num_tiles(icqb_ctx* ctx);
+int icqb_assemble_lower_dev(icqb_ctx* ctx, int diag_order, uint64_t dG, uint64_t dKl, uint64_t dKu);
 /* y = G x (scaled == 0) or diag(area) G x (scaled != 0) from the lower storage: streams
  * each stored entry once (4 N^2 bytes instead of 8 N^2) and all-reduces the partial
  * vectors over the ranks.  x, y: device double[ntri], replicated.  Blocking. */
-int icqb_symv_dev(icqb_ctx* ctx, uint64_t dA, int64_t ld, uint64_t dx, uint64_t dy, int scaled);
+int icqb_symv_dev(icqb_ctx* ctx, uint64_t dA, uint64_t dx, uint64_t dy, int scaled);
 
 /* Host-buffer forms (blocking; host<->device copies inside the call).
  * gMat/kMat: row-major double[(r1-r0)*ntri]; kMat may be NULL. */
@@ -129,7 +132,7 @@ int icqb_gemv_host(icqb_ctx* ctx, uint64_t dA, int64_t nrows, int64_t ncols, int
 
 /* Jacobi-preconditioned conjugate gradient (solvers/icqConjugateGradient.py:49-79)
  * on the system  diag(rowscale) A x = diag(rowscale) b.
- *   dA       the locally stored rows of the n x n matrix, pitch ld:
+ *   dA       the locally stored part of the n x n matrix (ld is used by storage 0 only):
  *              storage 0: rank g of P holds rows [g*ceil(n/P), (g+1)*ceil(n/P)), all columns;
  *              storage 1: lower storage of the context's row blocks (icqb_set_row_blocks),
  *                         the context must hold the mesh the matrix was assembled from;

@@ -334,8 +334,13 @@ def test_laplace_response_golden(golden, storage):
         g = solver.getGreenMatrix()
         backward = numpy.abs(v + g.dot(rsp)).max() / numpy.abs(v).max()
         assert backward < 1e-12
+        # forward error of ANY solver is bounded by cond(G) x (relative residual); LU's own
+        # is ~cond*eps.  2-norm bound with the measured residual, plus LU's share.
         cond = float(big[name + '_cond'])
-        assert numpy.abs(rsp - ref).max() / numpy.abs(ref).max() < 50 * cond * EPS
+        res2 = numpy.linalg.norm(v + g.dot(rsp)) / numpy.linalg.norm(v)
+        fwd2 = numpy.linalg.norm(rsp - ref) / numpy.linalg.norm(ref)
+        assert fwd2 < cond * (res2 + 50 * EPS)
+        assert res2 < 2e-13
         assert solver.lastSolveInfo['iterations'] < len(tri)
         arr = solver.getVtkPolyData().GetCellData().GetArray('normal_electric_field_jump')
         assert arr is not None
@@ -412,31 +417,40 @@ def test_point_data_projection_and_missing_source(golden):
 
 def lower_assemble(ctx, xyz, tri, blocks, order=5, with_k=False):
     import torch
+    from icqsol_b200.bem import icqRowPartition as rp
     xyz = numpy.ascontiguousarray(xyz, numpy.float64)
     tri = numpy.ascontiguousarray(tri, numpy.int64)
     n = tri.shape[0]
     ctx.check(ctx.lib.icqb_set_mesh(ctx.handle, dp(xyz), xyz.shape[0], lp(tri), n))
     ctx.check(ctx.lib.icqb_set_row_blocks(ctx.handle, *blocks))
     rows = (blocks[1] - blocks[0]) + (blocks[3] - blocks[2])
-    ld = (n + 15) // 16 * 16
-    bufs = [torch.full((max(rows, 1), ld), float('nan'), dtype=torch.float64, device='cuda:0')
+    ntiles = int(ctx.lib.icqb_lower_num_tiles(ctx.handle))
+    assert ntiles == rp.lowerStrips(blocks)[1]
+    bufs = [torch.full((max(ntiles, 1), 128, 128), float('nan'), dtype=torch.float64, device='cuda:0')
             for _ in range(3 if with_k else 1)]
     ctx.check(ctx.lib.icqb_assemble_lower_dev(ctx.handle, order, bufs[0].data_ptr(),
                                               bufs[1].data_ptr() if with_k else 0,
-                                              bufs[2].data_ptr() if with_k else 0, ld))
+                                              bufs[2].data_ptr() if with_k else 0))
     ctx.check(ctx.lib.icqb_synchronize(ctx.handle))
-    return bufs, ld, rows
+    out = []
+    for b in bufs:
+        t = b[:ntiles].cpu().numpy()
+        written = numpy.where(numpy.isnan(t), 0.0, t)
+        rowsArr = rp.lowerTilesToRows(written, blocks, n)
+        nanRows = rp.lowerTilesToRows(numpy.isnan(t).astype(float), blocks, n)
+        out.append((rowsArr, nanRows))
+    return out, rows
 
 
 @pytest.mark.parametrize('blocks', [(0, 960, 960, 960), (0, 256, 768, 960), (256, 512, 512, 768),
                                     (128, 128, 384, 500), (0, 0, 0, 0)])
 def test_lower_storage_tiles_vs_oracle(ctx, golden, oracle_mod, blocks):
-    """Every stored tile (J <= I) of arbitrary row blocks equals the oracle; tiles above
-    the diagonal tile are never written; KL/KU hold K[i,j] / K[j,i]."""
+    """Every stored entry (tiles J <= I, tile-contiguous layout) of arbitrary row blocks
+    equals the oracle; KL/KU hold K[i,j] / K[j,i]."""
     xyz, tri = golden.mesh('sphere')
     n = tri.shape[0]
-    bufs, ld, rows = lower_assemble(ctx, xyz, tri, blocks, 5, with_k=True)
-    g, kl, ku = [b.cpu().numpy() for b in bufs]
+    bufs, rows = lower_assemble(ctx, xyz, tri, blocks, 5, with_k=True)
+    (g, gnan), (kl, _), (ku, _) = bufs
     ref = oracle_mod.green_matrix(xyz, tri, 5, threads=True)
     kref = oracle_mod.k_block(xyz, tri, 0, n, 0, n)
     glob = list(range(blocks[0], blocks[1])) + list(range(blocks[2], blocks[3]))
@@ -444,8 +458,8 @@ def test_lower_storage_tiles_vs_oracle(ctx, golden, oracle_mod, blocks):
     kmax = numpy.abs(kref).max()
     for lrow, i in enumerate(glob):
         cend = min(n, (i // 128 + 1) * 128)
+        assert (gnan[lrow, :cend] == 0).all()                 # every stored entry written
         assert numpy.abs(g[lrow, :cend] / ref[i, :cend] - 1).max() < TOL_ENTRY
-        assert numpy.isnan(g[lrow, cend:n]).all()          # never written
         assert numpy.abs(kl[lrow, :cend] - kref[i, :cend]).max() < K_TOL * kmax
         assert numpy.abs(ku[lrow, :cend] - kref[:cend, i]).max() < K_TOL * kmax
 
