@@ -7,8 +7,8 @@
 
 One step = one pass of the hot path on a synthetic refined UV sphere
 (SURVEY.md section 8d): fused G+K assembly (diagonal + off-diagonal kernels) into
-resident HBM buffers, then the dense CG solve of G sigma = -v to a relative
-residual of 1e-13.  N=1 runs config C2 (19,880 triangles); for N>1 the mesh is
+resident HBM buffers, then the dense CG solve of G sigma = -v to a backward error
+max|v + G sigma| <= 5e-13 max|v| (inside the 1e-12 parity criterion).  N=1 runs config C2 (19,880 triangles); for N>1 the mesh is
 refined so that the N^2 matrix work per GPU stays fixed ("weak" scaling), rows
 block-sharded over the ranks, NCCL only inside the CG.
 
@@ -289,7 +289,7 @@ def run_b200(args):
         r2 = ctypes.c_double(0.)
         rinf = ctypes.c_double(0.)
         ctx.check(lib.icqb_cg_solve_dev(ctx.handle, gbuf.data_ptr(), n, ld, 1 if lower else 0, area2, 0,
-                                        bdev.data_ptr(), xdev.data_ptr(), 1e-13, 1, -1,
+                                        bdev.data_ptr(), xdev.data_ptr(), 5e-13, 2, -1,
                                         ctypes.byref(iters), ctypes.byref(r2), ctypes.byref(rinf)))
         if record:
             phase['assembly_ms'].append(1e3 * (t1 - t0))
@@ -373,7 +373,7 @@ def run_b200(args):
             'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
             'config': {'workload': label, 'triangles': n, 'diag_order': 5, 'offdiag_order': 8,
-                       'step': 'fused G+K assembly + CG solve (rel. residual 1e-13)',
+                       'step': 'fused G+K assembly + CG solve (max|v+G sigma| <= 5e-13 max|v|)',
                        'rows_per_gpu': rows, 'storage': args.storage,
                        'parallelism': ('folded row blocks, lower storage x{0}' if lower
                                        else 'row-block x{0}').format(world),

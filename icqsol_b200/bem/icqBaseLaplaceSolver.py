@@ -72,6 +72,11 @@ class BaseLaplaceSolver(BaseSolver):
         self.ctx = _lib.Context(self.device)
         self.lib = self.ctx.lib
 
+        # run the library on torch's current stream: buffer initialisation (torch) and the
+        # kernels (library) are then ordered without extra synchronisation
+        self.ctx.check(self.lib.icqb_set_stream(self.ctx.handle,
+                                                torch.cuda.current_stream().cuda_stream or 1))
+
         self.rank, self.numRanks = rowPartition.worldInfo()
         # one NCCL communicator per process, shared by every solver
         _lib.attachCommunicator(self.ctx, self.rank, self.numRanks, rowPartition.broadcastBytes)
@@ -237,10 +242,10 @@ class BaseLaplaceSolver(BaseSolver):
         self.ctx.check(self.lib.icqb_synchronize(self.ctx.handle))
         return rowPartition.allGatherRows(y[:rows].cpu().numpy(), n)
 
-    def solveGreenSystem(self, rhs, tol=1.e-13, maxNumIters=None, x0=None):
+    def solveGreenSystem(self, rhs, tol=1.e-12, maxNumIters=None, x0=None):
         """Solve G x = rhs by CG on the area-symmetrised system
         diag(A) G x = diag(A) rhs  (G[j,i] = G[i,j] A_i/A_j, so diag(A) G is symmetric).
-        Stops when ||rhs - G x||_2 <= tol*||rhs||_2.
+        Stops when max|rhs - G x| <= tol*max|rhs| (backward error in the max norm).
         @return x float64[N]; details in self.lastSolveInfo"""
         torch = _requireTorchCuda()
         n = self.numTriangles
@@ -255,7 +260,7 @@ class BaseLaplaceSolver(BaseSolver):
         self.ctx.check(self.lib.icqb_cg_solve_dev(
             self.ctx.handle, self.gMatDevice.data_ptr(), n, self.ld,
             1 if self.storage == 'lower' else 0, self.lib.icqb_area2_dev(self.ctx.handle), 0,
-            b.data_ptr(), x.data_ptr(), float(tol), 1, maxit, ctypes.byref(iters),
+            b.data_ptr(), x.data_ptr(), float(tol), 2, maxit, ctypes.byref(iters),
             ctypes.byref(r2), ctypes.byref(rinf)))
         self.lastSolveInfo = {'iterations': iters.value, 'residual2': r2.value,
                               'residualInf': rinf.value, 'milliseconds': self.ctx.last_ms(4),

@@ -21,11 +21,12 @@ class LaplaceSolver(BaseLaplaceSolver):
         BaseLaplaceSolver.__init__(self, pdata, max_edge_length, order, **kwargs)
         self.responseName = 'normal_electric_field_jump'
         self.sourceName = 'v'
-        self.solverTolerance = 1.e-13
+        self.solverTolerance = 5.e-13
         self.solverMaxNumIters = None
 
     def setSolverTolerance(self, tol):
-        """Relative residual ||v - G sigma||_2 / ||v||_2 at which the CG stops."""
+        """Backward error max|v + G sigma| / max|v| at which the CG stops (default 5e-13,
+        inside the 1e-12 parity criterion)."""
         self.solverTolerance = tol
 
     def setSolverMaxNumberOfIterations(self, maxNumIters):

@@ -36,8 +36,11 @@ struct CgState {
     int done;
     unsigned int ticket;
     long long iters;
-    double thr2;       // squared stopping threshold
-    double res2;       // squared recurrence residual after the last counted iteration
+    double thr2;       // stopping threshold: squared 2-norm, or max norm (use_max)
+    double res2;       // squared 2-norm of the recurrence residual after the last iteration
+    double resmax;     // its max norm
+    int use_max;       // 1: the stopping test is on the max norm
+    int pad;
 };
 
 // every vector is full length (n) and replicated on all ranks: the ranks execute the
@@ -50,6 +53,8 @@ struct CgBuf {
     double *tru;       // [kNB]  sum (b - A x)^2
     double *bb;        // [kNB]  sum b^2
     double *mx;        // [kNB]  max |b - A x| per block
+    double *rmx;       // [kNB]  max |r/s| per block (recurrence residual)
+    double *bmx;       // [kNB]  max |b| per block
     CgState *state;    // device-side loop state (see below)
 };
 
@@ -113,7 +118,7 @@ __global__ void __launch_bounds__(kVT) k_cg_init(long long n, const double* b,
                                                  const double* scale, const double* precond,
                                                  CgBuf B) {
     __shared__ double s_red[kVT / 32];
-    double rw = 0.0, rs = 0.0, bb = 0.0;
+    double rw = 0.0, rs = 0.0, bb = 0.0, rm = 0.0, bm = 0.0;
     for (long long i = (long long)blockIdx.x * kVT + threadIdx.x; i < n; i += (long long)kNB * kVT) {
         const double s = scale ? scale[i] : 1.0;
         const double r = s * b[i] - B.z[i];
@@ -127,7 +132,9 @@ __global__ void __launch_bounds__(kVT) k_cg_init(long long n, const double* b,
         rw = fma(r, w, rw);
         const double ru = r / s;
         rs = fma(ru, ru, rs);
+        rm = fmax(rm, fabs(ru));
         bb = fma(b[i], b[i], bb);
+        bm = fmax(bm, fabs(b[i]));
     }
     double t = block_sum(rw, s_red);
     if (threadIdx.x == 0) B.rw[blockIdx.x] = t;
@@ -135,6 +142,10 @@ __global__ void __launch_bounds__(kVT) k_cg_init(long long n, const double* b,
     if (threadIdx.x == 0) B.res[blockIdx.x] = t;
     t = block_sum(bb, s_red);
     if (threadIdx.x == 0) B.bb[blockIdx.x] = t;
+    t = block_max(rm, s_red);
+    if (threadIdx.x == 0) B.rmx[blockIdx.x] = t;
+    t = block_max(bm, s_red);
+    if (threadIdx.x == 0) B.bmx[blockIdx.x] = t;
 }
 
 // p = w + beta p, beta = rho_k / rho_{k-1} (0 on the first iteration)
@@ -163,7 +174,7 @@ __global__ void __launch_bounds__(kVT) k_cg_update(long long n, int k, double* x
     __shared__ bool s_last;
     if (B.state->done) return;
     const double alpha = sum_partials(B.rw + (k & 1) * kNB) / sum_partials(B.pz);
-    double rw = 0.0, rs = 0.0;
+    double rw = 0.0, rs = 0.0, rm = 0.0;
     for (long long i = (long long)blockIdx.x * kVT + threadIdx.x; i < n; i += (long long)kNB * kVT) {
         const double r = fma(-alpha, B.z[i], B.r[i]);
         const double w = r * B.minv[i];
@@ -173,12 +184,15 @@ __global__ void __launch_bounds__(kVT) k_cg_update(long long n, int k, double* x
         rw = fma(r, w, rw);
         const double ru = r / B.s[i];
         rs = fma(ru, ru, rs);
+        rm = fmax(rm, fabs(ru));
     }
     double t = block_sum(rw, s_red);
     if (threadIdx.x == 0) B.rw[((k + 1) & 1) * kNB + blockIdx.x] = t;
+    const double tm = block_max(rm, s_red);
     t = block_sum(rs, s_red);
     if (threadIdx.x == 0) {
         B.res[blockIdx.x] = t;
+        B.rmx[blockIdx.x] = tm;
         __threadfence();
         s_last = (atomicAdd(&B.state->ticket, 1u) == kNB - 1);
     }
@@ -187,12 +201,17 @@ __global__ void __launch_bounds__(kVT) k_cg_update(long long n, int k, double* x
         // the last block to finish closes the iteration: fixed-order sum of the partials
         __threadfence();
         const volatile double* part = B.res;
-        double res2 = 0.0;
-        for (int q = 0; q < kNB; ++q) res2 += part[q];
+        const volatile double* pmax = B.rmx;
+        double res2 = 0.0, resmax = 0.0;
+        for (int q = 0; q < kNB; ++q) {
+            res2 += part[q];
+            resmax = fmax(resmax, pmax[q]);
+        }
         B.state->res2 = res2;
+        B.state->resmax = resmax;
         B.state->iters += 1;
         B.state->ticket = 0;
-        if (res2 <= B.state->thr2) B.state->done = 1;
+        if ((B.state->use_max ? resmax : res2) <= B.state->thr2) B.state->done = 1;
         __threadfence();
     }
 }
@@ -224,10 +243,12 @@ __global__ void __launch_bounds__(kVT) k_cg_true(long long n, int replace, int k
     if (threadIdx.x == 0) B.mx[blockIdx.x] = t;
 }
 
-__global__ void k_cg_state(CgState* s, int done, long long iters, double thr2, int set_iters) {
+__global__ void k_cg_state(CgState* s, int done, long long iters, double thr2, int use_max,
+                           int set_iters) {
     s->done = done;
     s->ticket = 0;
     s->thr2 = thr2;
+    s->use_max = use_max;
     if (set_iters) s->iters = iters;
 }
 
@@ -319,7 +340,7 @@ extern "C" int icqb_cg_solve_dev(icqb_ctx* ctx, uint64_t dA_, int64_t n, int64_t
 
     // work space
     const long long nfull = chunk * P;
-    const long long need = 8 * n + nfull + 7 * kNB + 8 + 64;
+    const long long need = 8 * n + nfull + 9 * kNB + 8 + 64;
     int rc = ensure_work(ctx, need);
     if (rc != ICQB_OK) return rc;
     CgBuf B;
@@ -339,6 +360,8 @@ extern "C" int icqb_cg_solve_dev(icqb_ctx* ctx, uint64_t dA_, int64_t n, int64_t
     B.tru = wp; wp += kNB;
     B.bb = wp; wp += kNB;
     B.mx = wp; wp += kNB;
+    B.rmx = wp; wp += kNB;
+    B.bmx = wp; wp += kNB;
     B.state = reinterpret_cast<CgState*>(wp); wp += 8;
 
     MatVec mv;
@@ -401,13 +424,20 @@ extern "C" int icqb_cg_solve_dev(icqb_ctx* ctx, uint64_t dA_, int64_t n, int64_t
         double res2 = 0.0, bb = 0.0;
         CG_TRY(read_partials(ctx, B.res, kNB, false, &res2));
         CG_TRY(read_partials(ctx, B.bb, kNB, false, &bb));
-        const double thr = rel ? tol * sqrt(bb) : tol;
-        double err = sqrt(res2);
+        // stopping test (rel): 0 absolute 2-norm (the reference class), 1 relative 2-norm,
+        // 2 relative max norm  max|b - A x| <= tol * max|b|  (the backward-error criterion)
+        const bool use_max = (rel == 2);
+        double bmax = 0.0, rmax0 = 0.0;
+        CG_TRY(read_partials(ctx, B.bmx, kNB, true, &bmax));
+        CG_TRY(read_partials(ctx, B.rmx, kNB, true, &rmax0));
+        const double thr = use_max ? tol * bmax : (rel ? tol * sqrt(bb) : tol);
+        const double thr_dev = use_max ? thr : thr * thr;
+        double err = use_max ? rmax0 : sqrt(res2);
         long long k = 0;
         int replacements = 0;
-        double true2 = err, trueinf = 0.0;
+        double true2 = sqrt(res2), trueinf = rmax0, prev_true = -1.0;
         const int* skip = reinterpret_cast<const int*>(B.state);   // &state->done
-        k_cg_state<<<1, 1, 0, st>>>(B.state, 0, 0, thr * thr, 1);
+        k_cg_state<<<1, 1, 0, st>>>(B.state, 0, 0, thr_dev, use_max ? 1 : 0, 1);
         ctx->launches += 1;
         // iterations are enqueued `batch` at a time; the device decides when to stop
         // (CgState), the host only polls -- no host round trip per iteration
@@ -425,10 +455,15 @@ extern "C" int icqb_cg_solve_dev(icqb_ctx* ctx, uint64_t dA_, int64_t n, int64_t
                 CG_TRY(read_partials(ctx, B.tru, kNB, false, &t2));
                 CG_TRY(read_partials(ctx, B.mx, kNB, true, &trueinf));
                 true2 = sqrt(t2);
-                if (true2 <= thr || last) break;
+                const double truem = use_max ? trueinf : true2;
+                if (truem <= thr || last) break;
+                // attainable accuracy reached: the true residual no longer follows the
+                // recurrence (it did not even halve since the last replacement)
+                if (prev_true >= 0.0 && truem > 0.5 * prev_true) break;
+                prev_true = truem;
                 ++replacements;
-                err = true2;  // r was replaced by the true residual; iterate on
-                k_cg_state<<<1, 1, 0, st>>>(B.state, 0, 0, thr * thr, 0);
+                err = truem;  // r was replaced by the true residual; iterate on
+                k_cg_state<<<1, 1, 0, st>>>(B.state, 0, 0, thr_dev, use_max ? 1 : 0, 0);
                 ctx->launches += 1;
             }
             const long long nb = std::min<long long>(batch, maxit - k);
@@ -451,7 +486,7 @@ extern "C" int icqb_cg_solve_dev(icqb_ctx* ctx, uint64_t dA_, int64_t n, int64_t
             gemv_ms += gms;
             ++gemv_count;
             k = hs.iters;
-            err = sqrt(hs.res2);
+            err = use_max ? hs.resmax : sqrt(hs.res2);
             if (!(err == err)) {  // NaN: breakdown (singular / indefinite system)
                 true2 = err;
                 break;

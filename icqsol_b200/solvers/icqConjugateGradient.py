@@ -37,6 +37,9 @@ class ConjugateGradient:
         self.device = torch.device('cuda', int(device))
         self.ctx = _lib.Context(int(device))
         self.lib = self.ctx.lib
+        torch.cuda.set_device(self.device)
+        self.ctx.check(self.lib.icqb_set_stream(self.ctx.handle,
+                                                torch.cuda.current_stream().cuda_stream or 1))
         n = len(b)
         self.n = n
         if isinstance(mat, torch.Tensor) and mat.is_cuda:

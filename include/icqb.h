@@ -53,7 +53,8 @@ const char* icqb_last_error(const icqb_ctx* ctx); /* ctx may be NULL: last creat
 int icqb_device(const icqb_ctx* ctx);
 uint64_t icqb_stream(const icqb_ctx* ctx);
 /* Run all subsequent work of this context on the caller's stream (a cudaStream_t,
- * e.g. torch.cuda.current_stream().cuda_stream); 0 restores the context's own. */
+ * e.g. torch.cuda.current_stream().cuda_stream; pass 1 = cudaStreamLegacy for the legacy
+ * default stream); 0 restores the context's own. */
 int icqb_set_stream(icqb_ctx* ctx, uint64_t stream);
 int icqb_synchronize(icqb_ctx* ctx);
 
@@ -143,8 +144,13 @@ int icqb_gemv_host(icqb_ctx* ctx, uint64_t dA, int64_t nrows, int64_t ncols, int
  *   dprecond double[n] diagonal preconditioner of the UNSCALED matrix
  *            (icqConjugateGradient.py:19) or 0 = use diag(A);
  *   db, dx   double[n], replicated on every rank; dx holds x0 on entry, the solution on exit;
- *   tol      stop when ||b - A x||_2 <= tol (absolute, :64); if rel != 0 the
- *            threshold is tol*||b||_2;
+ *   tol, rel stopping test on the residual b - A x:
+ *              rel 0: ||.||_2 <= tol (absolute, icqConjugateGradient.py:64);
+ *              rel 1: ||.||_2 <= tol*||b||_2;
+ *              rel 2: max|.| <= tol*max|b| (the backward-error criterion of the parity tests);
+ *            the recurrence residual drives the loop, the true residual confirms it; if the
+ *            true residual stops improving (attainable accuracy) the solve ends early and
+ *            the returned residuals say so;
  *   maxit    iteration cap (:16 defaults to n; pass -1 for n);
  *   outputs  iters, final true residual ||b - A x||_2 and max norm.
  * All vectors are replicated and every rank runs the same vector kernels; only the
