@@ -113,6 +113,17 @@ def measured_peaks():
     return {'hbm_gbs': 6650.0}, 'fallback (B200_PROFILING.md)'
 
 
+def traffic_of(kernel, storage, n):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of `kernel` from
+    the committed ncu --set full capture of this workload (profiles/traffic.json), or None."""
+    path = os.path.join(ROOT, 'profiles', 'traffic.json')
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        table = json.load(f)
+    return table.get('{0}|{1}|N{2}'.format(kernel, storage, n))
+
+
 # ---------------------------------------------------------------------------------------
 # reference arm / cpu baseline
 # ---------------------------------------------------------------------------------------
@@ -231,6 +242,7 @@ def run_b200(args):
     stream = torch.cuda.Stream(device=dev)
     ctx.check(lib.icqb_set_stream(ctx.handle, stream.cuda_stream))
     _lib.attachCommunicator(ctx, rank, world, rowPartition.broadcastBytes)
+    ctx.check(lib.icqb_cg_set_preconditioner(ctx.handle, 1 if args.preconditioner == 'block' else 0))
     ctx.check(lib.icqb_set_mesh(ctx.handle, xyz.ctypes.data_as(_lib.c_double_p), xyz.shape[0],
                                 tri.ctypes.data_as(_lib.c_int64_p), n))
     lower = args.storage == 'lower'
@@ -273,7 +285,7 @@ def run_b200(args):
     torch.cuda.synchronize(dev)
 
     phase = {'assembly_ms': [], 'offdiag_ms': [], 'diag_ms': [], 'solve_ms': [], 'gemv_ms': [],
-             'iters': [], 'resid': []}
+             'iters': [], 'resid': [], 'residinf': []}
 
     def step(record):
         with torch.cuda.stream(stream):
@@ -299,6 +311,7 @@ def run_b200(args):
             phase['gemv_ms'].append(ctx.last_ms(3))
             phase['iters'].append(iters.value)
             phase['resid'].append(r2.value)
+            phase['residinf'].append(rinf.value)
 
     def barrier():
         if world > 1:
@@ -335,30 +348,26 @@ def run_b200(args):
     e2e_times = []
     h2d = xyz.nbytes + tri.nbytes + v.nbytes
     d2h = 8 * n
-    for it in range(1 + args.e2e_steps):
+    for it in range(1 + args.e2e_steps if args.e2e_steps > 0 else 0):
         pd = PolyData.from_arrays(xyz, tri, dtype=numpy.float64)
         pd.GetCellData().AddArray(DataArray('v', v))
         barrier()
         t0 = time.perf_counter()
         solver = LaplaceSolver(pd, float('inf'), 5, computeK=True, device=local,
-                               storage=args.storage)
+                               storage=args.storage, preconditioner=args.preconditioner)
         rsp = solver.computeResponseField()
         torch.cuda.synchronize(dev)
         dt = time.perf_counter() - t0
         if it > 0:
             e2e_times.append(dt)
         del solver
-    e2e_s = max(e2e_times) if world == 1 else None
-    if world > 1:
-        t = torch.tensor([numpy.mean(e2e_times)], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    else:
+    e2e_s = None
+    if e2e_times:
         e2e_s = float(numpy.mean(e2e_times))
-    backward = None
-    if rank == 0:
-        backward = float(numpy.abs(rsp).max())
-
+        if world > 1:
+            t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_s = float(t.item())
     if rank == 0:
         peaks, peak_src = measured_peaks()
         off_ms = float(numpy.mean(phase['offdiag_ms']))
@@ -368,6 +377,7 @@ def run_b200(args):
         achieved = flop / (off_ms * 1e-3) / 1e12
         gemv_bytes = 8.0 * stored     # bytes of matrix this rank streams per product
         gemv_gbs = gemv_bytes / (gemv_ms * 1e-3) / 1e9 if gemv_ms > 0 else 0.0
+        iters_mean = float(numpy.mean(phase['iters']))
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True,
@@ -375,6 +385,7 @@ def run_b200(args):
             'config': {'workload': label, 'triangles': n, 'diag_order': 5, 'offdiag_order': 8,
                        'step': 'fused G+K assembly + CG solve (max|v+G sigma| <= 5e-13 max|v|)',
                        'rows_per_gpu': rows, 'storage': args.storage,
+                       'preconditioner': args.preconditioner,
                        'parallelism': ('folded row blocks, lower storage x{0}' if lower
                                        else 'row-block x{0}').format(world),
                        'l2': 'inputs larger than L2 ({0:.2f} GB of G streamed per product per GPU)'.format(
@@ -386,28 +397,40 @@ def run_b200(args):
                        'solve_ms': float(numpy.mean(phase['solve_ms'])),
                        'cg_iters': int(numpy.mean(phase['iters'])),
                        'cg_residual2': float(numpy.max(phase['resid'])),
+                       'cg_backward_error_max_norm': float(numpy.max(phase['residinf']) / numpy.abs(v).max()),
                        'gemv_ms': gemv_ms, 'gemv_gbs_per_gpu': gemv_gbs,
                        'gemv_gbs_aggregate': gemv_gbs * world,
                        'gemv_equivalent_dense_gbs_aggregate': 8.0 * n * n / (gemv_ms * 1e-3) / 1e9
                        if gemv_ms > 0 else 0.0},
-            'roofline': {'bound': 'fp64', 'kernel': 'k_offdiag<G+K>', 'achieved': achieved,
-                         'peak': peak.value, 'unit': 'TFLOP/s', 'frac': achieved / peak.value,
-                         'traffic': None,
-                         'peak_source': 'DFMA loop measured in this run (icqb_measure_fp64_peak)',
-                         'flop_per_evaluation': FLOP_PER_EVAL_GK,
-                         'fp64_instr_per_evaluation': 16,
-                         'issue_frac': (pairs_local * 256.0 * 16 * 2 / (off_ms * 1e-3) / 1e12) / peak.value},
-            'roofline_gemv': {'bound': 'hbm', 'kernel': 'k_symv+k_symv_reduce' if lower else 'k_gemv',
-                              'achieved': gemv_gbs,
-                              'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
-                              'frac': gemv_gbs / peaks['hbm_gbs'], 'traffic': None,
-                              'peak_source': peak_src},
-            'e2e': {'value': 2.0 * n * n / e2e_s, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d),
-                    'd2h_bytes_per_step': int(d2h), 'ms_per_step': 1e3 * e2e_s,
-                    'api': 'LaplaceSolver(pdata, inf, 5, computeK=True).computeResponseField()'},
+            'roofline': None,
+            'roofline_assembly': {
+                'bound': 'fp64', 'kernel': 'k_offdiag<G+K>', 'achieved': achieved,
+                'peak': peak.value, 'unit': 'TFLOP/s', 'frac': achieved / peak.value,
+                'traffic': traffic_of('k_offdiag', args.storage, n),
+                'peak_source': 'DFMA loop measured in this run (icqb_measure_fp64_peak)',
+                'flop_per_evaluation': FLOP_PER_EVAL_GK, 'fp64_instr_per_evaluation': 16,
+                'issue_frac': (pairs_local * 256.0 * 16 * 2 / (off_ms * 1e-3) / 1e12) / peak.value,
+                'launches_per_step': 1, 'ms_per_launch': off_ms,
+                'share_of_step': off_ms / ms_per_step},
+            'roofline_gemv': {
+                'bound': 'hbm', 'kernel': 'k_symv+k_symv_reduce' if lower else 'k_gemv',
+                'achieved': gemv_gbs, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
+                'frac': gemv_gbs / peaks['hbm_gbs'],
+                'traffic': traffic_of('k_symv' if lower else 'k_gemv', args.storage, n),
+                'peak_source': peak_src, 'algorithmic_bytes_per_launch': gemv_bytes,
+                'launches_per_step': iters_mean + 2, 'ms_per_launch': gemv_ms,
+                'share_of_step': (iters_mean + 2) * gemv_ms / ms_per_step},
+            'e2e': None if e2e_s is None else {
+                'value': 2.0 * n * n / e2e_s, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d),
+                'd2h_bytes_per_step': int(d2h), 'ms_per_step': 1e3 * e2e_s,
+                'api': 'LaplaceSolver(pdata, inf, 5, computeK=True).computeResponseField()'},
             'gpu_launches': int(launches),
             'clocks': sampler.summary(),
         }
+        # `roofline` = the kernel with the larger share of the step
+        dom = 'roofline_gemv' if line['roofline_gemv']['share_of_step'] > \
+            line['roofline_assembly']['share_of_step'] else 'roofline_assembly'
+        line['roofline'] = dict(line[dom])
         if world == 1 and not args.no_cpu_baseline:
             wall, entries, kind = cpu_assembly_sample(xyz, tri, args.cpu_sample, 1)
             line['cpu_baseline'] = {
@@ -428,12 +451,14 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--workload', default='auto', choices=['auto', 'c2', 'c3', 'c5', 'small'])
-    ap.add_argument('--cpu-sample', type=int, default=2400,
-                    help='triangles of the CPU baseline sub-mesh (2400 -> ~9 s single core)')
+    ap.add_argument('--cpu-sample', type=int, default=3600,
+                    help='triangles of the CPU baseline sub-mesh (3600 -> 10-20 s single core)')
     ap.add_argument('--e2e-steps', type=int, default=2)
     ap.add_argument('--storage', default='lower', choices=['lower', 'full'],
                     help="'lower': each pair entry stored once (mirror rule), symmetric product; "
                          "'full': complete row blocks, row-major GEMV")
+    ap.add_argument('--preconditioner', default='block', choices=['block', 'diagonal'],
+                    help="CG preconditioner: inverse 128x128 diagonal blocks, or 1/diag")
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':

@@ -49,6 +49,7 @@ SIGNATURES = [
     ('icqb_cg_solve_dev', c_int, [c_void_p, c_uint64, c_int64, c_int64, c_int, c_uint64, c_uint64,
                                   c_uint64, c_uint64, c_double, c_int, c_int64, c_int64_p,
                                   c_double_p, c_double_p]),
+    ('icqb_cg_set_preconditioner', c_int, [c_void_p, c_int]),
     ('icqb_comm_unique_id', c_int, [c_void_p]),
     ('icqb_comm_init', c_int, [c_void_p, c_void_p, c_int, c_int]),
     ('icqb_comm_share', c_int, [c_void_p, c_void_p]),

@@ -44,7 +44,7 @@ def leadingDimension(n):
 class BaseLaplaceSolver(BaseSolver):
 
     def __init__(self, pdata, max_edge_length, order=5, computeK=False, device=None,
-                 storage='lower'):
+                 storage='lower', preconditioner='block'):
         """
         Constructor
         @param pdata polydata (vtkPolyData or stand-in)
@@ -56,11 +56,17 @@ class BaseLaplaceSolver(BaseSolver):
         @param storage 'lower': block-lower-triangular, each pair entry stored once, the
                        upper part given by the mirror rule G[j,i] = G[i,j] A_i/A_j
                        (bem/icqLaplaceMatrices.cpp:97-98); 'full': complete row blocks
+        @param preconditioner of the CG solve: 'block' = inverse 128 x 128 diagonal blocks of
+                       diag(A) G, 'diagonal' = 1/diag (the reference CG class's default,
+                       solvers/icqConjugateGradient.py:19)
         """
         BaseSolver.__init__(self, pdata, max_edge_length, order)
         if storage not in ('lower', 'full'):
             raise ValueError("storage must be 'lower' or 'full'")
+        if preconditioner not in ('block', 'diagonal'):
+            raise ValueError("preconditioner must be 'block' or 'diagonal'")
         self.storage = storage
+        self.preconditioner = preconditioner
 
         torch = _requireTorchCuda()
         if device is None:
@@ -76,6 +82,9 @@ class BaseLaplaceSolver(BaseSolver):
         # kernels (library) are then ordered without extra synchronisation
         self.ctx.check(self.lib.icqb_set_stream(self.ctx.handle,
                                                 torch.cuda.current_stream().cuda_stream or 1))
+
+        self.ctx.check(self.lib.icqb_cg_set_preconditioner(
+            self.ctx.handle, 1 if preconditioner == 'block' else 0))
 
         self.rank, self.numRanks = rowPartition.worldInfo()
         # one NCCL communicator per process, shared by every solver

@@ -63,6 +63,36 @@ struct LowerLayout {
 struct Comm;      // NCCL state, comm.cu
 struct SymvPlan;  // task table + workspace of the symmetric product, symv.cu
 
+// Loop state of the conjugate gradient, kept on the device so that iterations can be
+// enqueued ahead of the host (cg.cu).  The last CTA of a reducing kernel writes the
+// scalars; the next kernel in the stream reads them.
+struct CgState {
+    int done;                  // recurrence residual met the threshold: later kernels return at once
+    int use_max;               // stopping test on the max norm instead of the 2-norm
+    unsigned int ticket_dot;   // "last CTA" counters of the two reducing kernels
+    unsigned int ticket_res;
+    long long iters;           // iterations completed (stops counting once done)
+    double thr;                // threshold: squared 2-norm, or max norm (use_max)
+    double res2, resmax;       // recurrence residual of the unscaled system
+    double rho[2];             // r.w of iteration k at rho[k & 1]
+    double pz;                 // p.(A p)
+    double beta;               // rho_{k+1}/rho_k for the next direction
+    double bb, bmax;           // |b|_2^2, max|b|
+    double tru2, trumax;       // true residual |b - A x|_2^2, max norm
+};
+
+// Conjugate-gradient work fused into the symmetric product (single rank, lower storage):
+// the multiplied vector is the new direction p = w + beta * p_old, formed on the fly by
+// k_symv and stored by k_symv_reduce, which also leaves p.(A p) in *pz.
+struct SymvFuse {
+    const double* w = nullptr;       // null: plain product of x
+    const double* beta = nullptr;    // device scalar
+    double* p = nullptr;             // the vector x itself, writable
+    double* pz_part = nullptr;       // [ceil(n/128)] partials; null: no fused dot product
+    double* pz = nullptr;
+    unsigned int* ticket = nullptr;
+};
+
 }  // namespace icqb
 
 struct icqb_ctx {
@@ -93,6 +123,8 @@ struct icqb_ctx {
     icqb::Comm* comm = nullptr;
     icqb::SymvPlan* symv = nullptr;
 
+    int precond_kind = 0;   // CG preconditioner when none is passed: 0 diag(A), 1 inverse 128x128 diagonal blocks
+
     double last_ms[icqb::kNumPhases] = {0, 0, 0, 0, 0};
     int64_t launches = 0;
     std::string err;
@@ -114,7 +146,7 @@ int launch_diag_rows(icqb_ctx* ctx, int order, long long g0, long long g1, doubl
                      int64_t stride);
 int launch_symv(icqb_ctx* ctx, const double* dA, const double* dx,
                 const double* dgamma, const double* dalpha, const double* dbeta, double* dz,
-                cudaStream_t stream, const int* skip = nullptr);
+                cudaStream_t stream, const int* skip = nullptr, const SymvFuse* fuse = nullptr);
 int launch_diag(icqb_ctx* ctx, int order, double* dOut, int64_t stride);
 int launch_gemv(icqb_ctx* ctx, const double* dA, int64_t nrows, int64_t ncols, int64_t ld,
                 const double* dx, double* dy, const double* drowscale, cudaStream_t stream,

@@ -14,29 +14,43 @@
 // Algorithmic traffic: 8 bytes per STORED entry = 4 N^2 + O(128 N) per product,
 // half of the row-major GEMV.
 //
-// Mapping: one WARP per 128x128 tile, four independent warps per CTA, no shared
-// memory and no barriers.  The 32 lanes cover the tile's 128 columns as 4
-// consecutive doubles each (a 1 KB contiguous segment per row, two 16-byte streaming
-// loads per lane) and walk the 128 rows eight at a time (16 loads in flight per
-// lane, 128 KB per SM at 16 resident warps).  Column sums are complete inside the
-// warp (each lane owns its 4 columns over all rows); a row's partial is reduced over
-// the lanes by a shuffle butterfly and kept by lane (row mod 32).  Each tile stores
-// 128 row partials and 128 column partials (2 KB per 128 KB streamed); a second
-// kernel adds them per global index in a fixed order (no atomics: results are
-// reproducible) and applies alpha/beta.
+// Mapping (k_symv): the stored tiles of a rank are ONE contiguous array, cut into
+// 8 KB chunks (8 rows x 128 columns of a tile).  A persistent grid of one CTA per SM,
+// 8 warps each, divides the chunk sequence evenly: every warp owns one contiguous
+// span, so there is no tail and no tile-size granularity.  Each warp is its own
+// pipeline: lane 0 keeps kDepth bulk copies (cp.async.bulk ... mbarrier::complete_tx,
+// SASS UBLKCP, L2 evict-first) in flight into the warp's private shared-memory ring
+// -- 192 KB of loads outstanding per SM without holding a register -- and the 32
+// lanes consume a landed chunk from shared memory: lane l owns columns
+// {2l, 2l+1, 64+2l, 65+2l} (conflict-free 16-byte reads), column sums stay in its
+// registers for the whole tile, the eight row sums of a chunk are reduced across the
+// lanes with a transposed butterfly (9 shuffles per 8 rows instead of 40).
+// Per tile a warp stores 128 row partials; column partials go to the tile's slot when
+// the warp began the tile and to a per-warp "head" slot when its span starts inside the
+// tile (the host knows the partition and tells the reduce kernel which head slots belong
+// to which tile).  k_symv_reduce adds the partials per global index in a fixed order
+// (no atomics: results are reproducible) and applies alpha/beta.  Inside the CG it also
+// forms the new search direction and p.(A p) (SymvFuse, icqb_internal.cuh).
 #include <algorithm>
 #include <vector>
 
 #include "icqb_internal.cuh"
+#include "reduce_util.cuh"
 
 namespace icqb {
 
 namespace {
 
-constexpr int kT = 128;          // tile edge
-constexpr int kWarpsPerCta = 4;
-constexpr int kThreads = kWarpsPerCta * 32;
-constexpr int kRowsInFlight = 8;
+constexpr int kT = 128;                               // tile edge
+constexpr int kChunkRows = 8;
+constexpr int kChunksPerTile = kT / kChunkRows;       // 16
+constexpr int kChunkElems = kChunkRows * kT;          // 1024 doubles
+constexpr int kChunkBytes = kChunkElems * 8;          // 8 KB
+constexpr int kWarps = 8;                             // independent pipelines per CTA
+constexpr int kDepth = 3;                             // chunks in flight per warp
+constexpr int kThreads = kWarps * 32;
+constexpr int kSmemBytes =
+    kWarps * kDepth * kChunkBytes + kWarps * kT * 8 + kWarps * kDepth * 8;   // 204,992 B
 
 struct SymvTask {
     int lt;        // local strip (tile row) index
@@ -47,128 +61,271 @@ struct SymvParams {
     const double* A;            // tile-contiguous lower storage (LowerLayout)
     long long n;
     LowerLayout L;
-    int nTasks;                 // == number of stored tiles; task t works on tile t
+    int nTasks;                 // == number of stored tiles; task t describes tile t
     const SymvTask* tasks;
     const double* x;            // [n]
     const double* gamma;        // [n] or null
     const double* alpha;        // [n] or null
     const double* beta;         // [n] or null
-    double* Wc;                 // [nLocal][wcols] column partials per strip
+    double* Wc;                 // [nLocal][wcols] column partials of the warp that began a tile
     double* Wr;                 // [nTasks][128]  row partials per tile
+    double* Wh;                 // [head slots][128] column partials of spans starting inside a tile
+    const int* headSlot;        // [warps] slot of the warp's head segment, -1: none
+    const int* headBegin;       // [nTasks] first head slot of the tile
+    const int* headCount;       // [nTasks] number of head slots of the tile
     long long wcols;
     double* z;                  // [n]
     const int* skip;            // when non-null and *skip != 0 the kernels return at once
+    SymvFuse F;                 // CG fusion (all null: plain product)
 };
 
-__device__ __forceinline__ double2 ld_stream2(const double* p) {
-    double2 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];"
-                 : "=d"(v.x), "=d"(v.y)
-                 : "l"(p));
-    return v;
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
-__global__ void __launch_bounds__(kThreads, 4) k_symv(const SymvParams P) {
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+
+// global -> shared bulk copy, completion counted in bytes on `bar`; the matrix is read
+// once per product, so its lines are marked evict-first in L2 (the vectors, partial
+// arrays and the preconditioner blocks of the CG stay resident)
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar,
+                                         uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+        "[%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
+
+// entry c of the multiplied vector: x, or the CG direction w + beta * p_old
+__device__ __forceinline__ double vec_at(const SymvParams& P, double cgBeta, long long c) {
+    const double xv = __ldg(P.x + c);
+    return P.F.w ? fma(cgBeta, xv, __ldg(P.F.w + c)) : xv;
+}
+
+__global__ void __launch_bounds__(kThreads, 1) k_symv(const SymvParams P) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     if (P.skip && *P.skip) return;
-    const int lane = threadIdx.x & 31;
-    const int taskId = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
-    if (taskId >= P.nTasks) return;
-    const SymvTask task = P.tasks[taskId];
-    const long long obs0 = P.L.obs0(task.lt), obsEnd = P.L.obsEnd(task.lt);
-    const int I = (int)(obs0 / kT), J = task.J;
-    const int nrows = (int)min((long long)kT, obsEnd - obs0);
-    const bool diagTile = (J == I);
+    double* s_ring = reinterpret_cast<double*>(smem_raw);            // [kWarps][kDepth][kChunkElems]
+    double* s_mul = s_ring + kWarps * kDepth * kChunkElems;          // [kWarps][kT]
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_mul + kWarps * kT);   // [kWarps][kDepth]
 
-    const long long c0 = (long long)J * kT + lane * 4;
-    // valid columns: tiles below the diagonal tile are complete; the diagonal tile ends at n
-    const long long cEnd = diagTile ? min(P.n, (long long)(J + 1) * kT) : (long long)(J + 1) * kT;
-    const bool full4 = (c0 + 4 <= cEnd);
-    double x0 = 0, x1 = 0, x2 = 0, x3 = 0;
-    if (c0 < cEnd) x0 = __ldg(P.x + c0);
-    if (c0 + 1 < cEnd) x1 = __ldg(P.x + c0 + 1);
-    if (c0 + 2 < cEnd) x2 = __ldg(P.x + c0 + 2);
-    if (c0 + 3 < cEnd) x3 = __ldg(P.x + c0 + 3);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long gw = (long long)blockIdx.x * kWarps + warp;
+    const long long nW = (long long)gridDim.x * kWarps;
+    const long long total = (long long)P.nTasks * kChunksPerTile;
+    const long long c0 = total * gw / nW, c1 = total * (gw + 1) / nW;   // this warp's chunks
+    const long long nCh = c1 - c0;
+    if (nCh <= 0) return;
 
-    double ca0 = 0, ca1 = 0, ca2 = 0, ca3 = 0;      // column sums of this lane's 4 columns
-    double rowacc[kT / 32] = {0, 0, 0, 0};          // rows lane, lane+32, lane+64, lane+96
-    // the tile is one contiguous 128 KB block: row r starts at r*128
-    const double* aBase = P.A + (long long)taskId * kLowerTileElems + lane * 4;
-
+    double* ring = s_ring + warp * kDepth * kChunkElems;
+    double* mul = s_mul + warp * kT;
+    uint64_t* bar = s_bar + warp * kDepth;
+    uint64_t policy = 0;
+    if (lane == 0) {
 #pragma unroll
-    for (int q = 0; q < kT / 32; ++q) {
-#pragma unroll 1
-        for (int rb = 0; rb < 32; rb += kRowsInFlight) {
-            const int rbase = q * 32 + rb;
-            if (rbase >= nrows) break;   // uniform across the warp
-            double2 lo[kRowsInFlight], hi[kRowsInFlight];
-#pragma unroll
-            for (int u = 0; u < kRowsInFlight; ++u) {
-                const int r = rbase + u;
-                const double* ap = aBase + r * kT;
-                lo[u] = make_double2(0.0, 0.0);
-                hi[u] = make_double2(0.0, 0.0);
-                if (r < nrows) {
-                    if (full4) {
-                        lo[u] = ld_stream2(ap);
-                        hi[u] = ld_stream2(ap + 2);
-                    } else {
-                        if (c0 < cEnd) lo[u].x = __ldg(ap);
-                        if (c0 + 1 < cEnd) lo[u].y = __ldg(ap + 1);
-                        if (c0 + 2 < cEnd) hi[u].x = __ldg(ap + 2);
-                    }
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < kRowsInFlight; ++u) {
-                const int r = rbase + u;
-                double part = lo[u].x * x0;
-                part = fma(lo[u].y, x1, part);
-                part = fma(hi[u].x, x2, part);
-                part = fma(hi[u].y, x3, part);
-                if (!diagTile && r < nrows) {
-                    const long long i = obs0 + r;
-                    double ur = __ldg(P.x + i);            // uniform address: broadcast
-                    if (P.gamma) ur *= __ldg(P.gamma + i);
-                    ca0 = fma(lo[u].x, ur, ca0);
-                    ca1 = fma(lo[u].y, ur, ca1);
-                    ca2 = fma(hi[u].x, ur, ca2);
-                    ca3 = fma(hi[u].y, ur, ca3);
-                }
-#pragma unroll
-                for (int off = 16; off > 0; off >>= 1)
-                    part += __shfl_xor_sync(0xffffffffu, part, off);
-                if (lane == rb + u) rowacc[q] = part;      // row (q*32 + lane) of the tile
-            }
+        for (int s = 0; s < kDepth; ++s) mbar_init(&bar[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        policy = policy_evict_first();
+    }
+    __syncwarp();
+    if (lane == 0) {
+        const int pre = (int)min((long long)kDepth, nCh);
+        for (int s = 0; s < pre; ++s) {
+            mbar_expect_tx(&bar[s], kChunkBytes);
+            bulk_g2s(ring + s * kChunkElems, P.A + (c0 + s) * kChunkElems, kChunkBytes, &bar[s],
+                     policy);
         }
     }
 
-    double* wr = P.Wr + (long long)taskId * kT;
-#pragma unroll
-    for (int q = 0; q < kT / 32; ++q) wr[q * 32 + lane] = rowacc[q];
-    if (!diagTile) {
-        double* wc = P.Wc + (long long)task.lt * P.wcols + c0;
+    const double cgBeta = P.F.w ? *P.F.beta : 0.0;
+
+    // state of the tile being processed
+    long long curTile = -1;
+    bool diagTile = false, ragged = false, ownsStart = false;
+    bool v0 = true, v1 = true, v2 = true, v3 = true;
+    int nrows = 0, curLt = 0;
+    long long colA = 0;
+    double x0 = 0, x1 = 0, x2 = 0, x3 = 0;
+    double ca0 = 0, ca1 = 0, ca2 = 0, ca3 = 0;
+
+    // column partials of the finished segment: to the tile's slot when this warp began
+    // the tile, else to the warp's head slot
+    auto flush = [&]() {
+        if (curTile < 0 || diagTile) return;
+        double* wc = ownsStart ? P.Wc + (long long)curLt * P.wcols + colA
+                               : P.Wh + (long long)__ldg(P.headSlot + gw) * kT + 2 * lane;
         reinterpret_cast<double2*>(wc)[0] = make_double2(ca0, ca1);
-        reinterpret_cast<double2*>(wc)[1] = make_double2(ca2, ca3);
+        reinterpret_cast<double2*>(wc + 64)[0] = make_double2(ca2, ca3);
+    };
+
+    for (long long i = 0; i < nCh; ++i) {
+        const long long ch = c0 + i;
+        const long long tile = ch / kChunksPerTile;
+        const int rbase = (int)(ch % kChunksPerTile) * kChunkRows;
+
+        if (tile != curTile) {
+            flush();
+            curTile = tile;
+            ownsStart = (tile * kChunksPerTile >= c0);
+            const SymvTask task = P.tasks[tile];
+            curLt = task.lt;
+            const long long obs0 = P.L.obs0(task.lt), obsEnd = P.L.obsEnd(task.lt);
+            const long long I = obs0 / kT, J = task.J;
+            nrows = (int)min((long long)kT, obsEnd - obs0);
+            diagTile = (J == I);
+            // valid columns: tiles below the diagonal tile are complete; the diagonal tile ends at n
+            const long long cEnd = diagTile ? min(P.n, (J + 1) * kT) : (J + 1) * kT;
+            ragged = cEnd < (J + 1) * kT;
+            colA = J * kT + 2 * lane;
+            const long long colB = colA + 64;
+            v0 = colA < cEnd;
+            v1 = colA + 1 < cEnd;
+            v2 = colB < cEnd;
+            v3 = colB + 1 < cEnd;
+            x0 = v0 ? vec_at(P, cgBeta, colA) : 0.0;
+            x1 = v1 ? vec_at(P, cgBeta, colA + 1) : 0.0;
+            x2 = v2 ? vec_at(P, cgBeta, colB) : 0.0;
+            x3 = v3 ? vec_at(P, cgBeta, colB + 1) : 0.0;
+            ca0 = ca1 = ca2 = ca3 = 0.0;
+            if (!diagTile) {
+                // multipliers of the mirrored entries: gamma_i x_i for the tile's 128 rows
+                __syncwarp();
+#pragma unroll
+                for (int q = 0; q < kT / 32; ++q) {
+                    const int r = q * 32 + lane;
+                    double m = 0.0;
+                    if (r < nrows) {
+                        m = vec_at(P, cgBeta, obs0 + r);
+                        if (P.gamma) m *= __ldg(P.gamma + obs0 + r);
+                    }
+                    mul[r] = m;
+                }
+                __syncwarp();
+            }
+        }
+
+        const int s = (int)(i % kDepth);
+        mbar_wait(&bar[s], (uint32_t)((i / kDepth) & 1));
+        const double* sp = ring + s * kChunkElems + 2 * lane;
+
+        double part[kChunkRows];
+#pragma unroll
+        for (int u = 0; u < kChunkRows; ++u) {
+            const int r = rbase + u;
+            part[u] = 0.0;
+            if (r < nrows) {   // uniform across the warp
+                double2 a01 = *reinterpret_cast<const double2*>(sp + u * kT);
+                double2 a23 = *reinterpret_cast<const double2*>(sp + u * kT + 64);
+                if (ragged) {   // columns beyond n were never written: mask them
+                    if (!v0) a01.x = 0.0;
+                    if (!v1) a01.y = 0.0;
+                    if (!v2) a23.x = 0.0;
+                    if (!v3) a23.y = 0.0;
+                }
+                part[u] = fma(a23.y, x3, fma(a23.x, x2, fma(a01.y, x1, a01.x * x0)));
+                if (!diagTile) {
+                    const double m = mul[r];   // same address on every lane: broadcast
+                    ca0 = fma(a01.x, m, ca0);
+                    ca1 = fma(a01.y, m, ca1);
+                    ca2 = fma(a23.x, m, ca2);
+                    ca3 = fma(a23.y, m, ca3);
+                }
+            }
+        }
+        // every lane has read its part of the stage: lane 0 may refill it
+        __syncwarp();
+        if (lane == 0 && i + kDepth < nCh) {
+            mbar_expect_tx(&bar[s], kChunkBytes);
+            bulk_g2s(ring + s * kChunkElems, P.A + (ch + kDepth) * kChunkElems, kChunkBytes, &bar[s],
+                     policy);
+        }
+
+        // transposed butterfly: 8 row sums over 32 lanes in 4+2+1+1+1 shuffles; row
+        // (lane >> 2) of the chunk ends up on the four lanes of its group
+        const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const double send = b4 ? part[q] : part[q + 4];
+            const double keep = b4 ? part[q + 4] : part[q];
+            part[q] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const double send = b3 ? part[q] : part[q + 2];
+            const double keep = b3 ? part[q + 2] : part[q];
+            part[q] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+        {
+            const double send = b2 ? part[0] : part[1];
+            const double keep = b2 ? part[1] : part[0];
+            part[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+        part[0] += __shfl_xor_sync(0xffffffffu, part[0], 2);
+        part[0] += __shfl_xor_sync(0xffffffffu, part[0], 1);
+        if ((lane & 3) == 0) P.Wr[tile * kT + rbase + (lane >> 2)] = part[0];
     }
+    flush();
 }
 
 // z[j] = alpha_j * (row partials of j's strip over its tiles) + beta_j * (column partials of
 // the strips below).  One CTA per 128 global indices, 4 thread groups split the two sums and
-// are combined in a fixed order.
+// are combined in a fixed order.  With SymvFuse the CTA also stores the new direction
+// p_j = w_j + beta p_j and leaves its share of p.z; the last CTA adds the shares.
 __global__ void __launch_bounds__(512) k_symv_reduce(const SymvParams P) {
     __shared__ double s_row[4][kT], s_col[4][kT];
+    __shared__ double s_dot[4];
+    __shared__ double s_fin[512];
+    __shared__ int s_last;
     if (P.skip && *P.skip) return;
     const int T = blockIdx.x, c = threadIdx.x, g = threadIdx.y;
+    const int tid = g * kT + c;
     const long long j = (long long)T * kT + c;
     const long long jl = min(j, P.n - 1);       // clamp: lanes beyond n never store
     double col = 0.0, row = 0.0;
     // strips strictly below tile row T, first block then second block
-    {
-        const long long first = max(0LL, (long long)T + 1 - P.L.r0 / kT);
-        for (long long lt = first + g; lt < P.L.nTiles0; lt += 4) col += P.Wc[lt * P.wcols + jl];
-        const long long first1 = max(0LL, (long long)T + 1 - P.L.q0 / kT);
-        for (long long lt = P.L.nTiles0 + first1 + g; lt < P.L.nLocal(); lt += 4)
+    for (int blk = 0; blk < 2; ++blk) {
+        const long long b0 = blk == 0 ? P.L.r0 : P.L.q0;
+        const long long ltBeg = blk == 0 ? 0 : P.L.nTiles0;
+        const long long ltEnd = blk == 0 ? P.L.nTiles0 : P.L.nLocal();
+        const long long first = max(0LL, (long long)T + 1 - b0 / kT);
+        for (long long lt = ltBeg + first + g; lt < ltEnd; lt += 4) {
             col += P.Wc[lt * P.wcols + jl];
+            const long long tile = P.L.tileBase((int)lt) + T;
+            const int hc = __ldg(P.headCount + tile);
+            if (hc) {
+                const int hb = __ldg(P.headBegin + tile);
+                for (int q = 0; q < hc; ++q) col += P.Wh[(long long)(hb + q) * kT + c];
+            }
+        }
     }
     // this tile row, if it is stored here
     const int lt = P.L.stripOf((long long)T * kT);
@@ -179,12 +336,37 @@ __global__ void __launch_bounds__(512) k_symv_reduce(const SymvParams P) {
     s_row[g][c] = row;
     s_col[g][c] = col;
     __syncthreads();
+    double pzv = 0.0;
     if (g == 0 && j < P.n) {
         row = (s_row[0][c] + s_row[1][c]) + (s_row[2][c] + s_row[3][c]);
         col = (s_col[0][c] + s_col[1][c]) + (s_col[2][c] + s_col[3][c]);
         if (P.alpha) row *= P.alpha[j];
         if (P.beta) col *= P.beta[j];
-        P.z[j] = row + col;
+        const double zj = row + col;
+        P.z[j] = zj;
+        if (P.F.w) {
+            const double pj = fma(*P.F.beta, P.F.p[j], P.F.w[j]);   // same arithmetic as vec_at
+            P.F.p[j] = pj;
+            pzv = pj * zj;
+        }
+    }
+    if (P.F.pz_part) {   // uniform
+        if (g == 0) warp_part<false>(pzv, s_dot, tid);
+        __syncthreads();
+        if (tid == 0) {
+            P.F.pz_part[T] = join4<false>(s_dot);
+            s_last = take_ticket(P.F.ticket, gridDim.x) ? 1 : 0;
+        }
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            const double pz = final_reduce<false>(P.F.pz_part, (int)gridDim.x, s_fin, tid, 512);
+            if (tid == 0) {
+                *P.F.pz = pz;
+                *P.F.ticket = 0;
+                __threadfence();
+            }
+        }
     }
 }
 
@@ -195,10 +377,15 @@ struct SymvPlan {
     long long n = -1;
     LowerLayout L{0, 0, 0, 0, 0, 0, 0};
     int nTasks = 0;
+    int grid = 0;
     long long wcols = 0;
     SymvTask* d_tasks = nullptr;
     double* d_Wc = nullptr;
     double* d_Wr = nullptr;
+    double* d_Wh = nullptr;
+    int* d_headSlot = nullptr;
+    int* d_headBegin = nullptr;
+    int* d_headCount = nullptr;
 };
 
 void symv_plan_free(icqb_ctx* ctx) {
@@ -207,6 +394,10 @@ void symv_plan_free(icqb_ctx* ctx) {
     cudaFree(p->d_tasks);
     cudaFree(p->d_Wc);
     cudaFree(p->d_Wr);
+    cudaFree(p->d_Wh);
+    cudaFree(p->d_headSlot);
+    cudaFree(p->d_headBegin);
+    cudaFree(p->d_headCount);
     delete p;
     ctx->symv = nullptr;
 }
@@ -225,6 +416,7 @@ static int symv_plan(icqb_ctx* ctx) {
     p->n = ctx->ntri;
     p->L = L;
     p->wcols = (p->n + kT - 1) / kT * kT;
+    p->grid = ctx->num_sms > 0 ? ctx->num_sms : 148;
     std::vector<SymvTask> tasks;
     for (int lt = 0; lt < L.nLocal(); ++lt) {
         const int I = (int)L.tileRow(lt);
@@ -234,17 +426,49 @@ static int symv_plan(icqb_ctx* ctx) {
     if ((long long)p->nTasks != L.numTiles())
         return set_error(ctx, ICQB_ESTATE, "symv: tile enumeration does not match the layout");
     if (p->nTasks == 0) return ICQB_OK;
+
+    // the static partition of the chunk sequence over the warps (same arithmetic as the
+    // kernel): a span that starts inside an off-diagonal tile owns a head slot
+    const long long nW = (long long)p->grid * kWarps;
+    const long long total = (long long)p->nTasks * kChunksPerTile;
+    std::vector<int> headSlot((size_t)nW, -1), headBegin((size_t)p->nTasks, 0),
+        headCount((size_t)p->nTasks, 0);
+    int slots = 0;
+    for (long long gw = 0; gw < nW; ++gw) {
+        const long long c0 = total * gw / nW, c1 = total * (gw + 1) / nW;
+        if (c1 <= c0 || c0 % kChunksPerTile == 0) continue;
+        const long long tile = c0 / kChunksPerTile;
+        const SymvTask& t = tasks[(size_t)tile];
+        if (t.J == (int)L.tileRow(t.lt)) continue;   // diagonal tile: no column part
+        if (headCount[(size_t)tile] == 0) headBegin[(size_t)tile] = slots;
+        headCount[(size_t)tile] += 1;
+        headSlot[(size_t)gw] = slots++;
+    }
     ICQB_CUDA(ctx, cudaMalloc(&p->d_tasks, sizeof(SymvTask) * tasks.size()));
     ICQB_CUDA(ctx, cudaMalloc(&p->d_Wc, sizeof(double) * (size_t)L.nLocal() * p->wcols));
     ICQB_CUDA(ctx, cudaMalloc(&p->d_Wr, sizeof(double) * (size_t)p->nTasks * kT));
+    ICQB_CUDA(ctx, cudaMalloc(&p->d_Wh, sizeof(double) * (size_t)std::max(slots, 1) * kT));
+    ICQB_CUDA(ctx, cudaMalloc(&p->d_headSlot, sizeof(int) * headSlot.size()));
+    ICQB_CUDA(ctx, cudaMalloc(&p->d_headBegin, sizeof(int) * headBegin.size()));
+    ICQB_CUDA(ctx, cudaMalloc(&p->d_headCount, sizeof(int) * headCount.size()));
     ICQB_CUDA(ctx, cudaMemcpy(p->d_tasks, tasks.data(), sizeof(SymvTask) * tasks.size(),
                               cudaMemcpyHostToDevice));
+    ICQB_CUDA(ctx, cudaMemcpy(p->d_headSlot, headSlot.data(), sizeof(int) * headSlot.size(),
+                              cudaMemcpyHostToDevice));
+    ICQB_CUDA(ctx, cudaMemcpy(p->d_headBegin, headBegin.data(), sizeof(int) * headBegin.size(),
+                              cudaMemcpyHostToDevice));
+    ICQB_CUDA(ctx, cudaMemcpy(p->d_headCount, headCount.data(), sizeof(int) * headCount.size(),
+                              cudaMemcpyHostToDevice));
+    // (every stored off-diagonal tile is begun by exactly one warp, which always writes the
+    // tile's Wc slot, so Wc needs no initialisation)
+    ICQB_CUDA(ctx, cudaFuncSetAttribute(k_symv, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        kSmemBytes));
     return ICQB_OK;
 }
 
 int launch_symv(icqb_ctx* ctx, const double* dA, const double* dx, const double* dgamma,
                 const double* dalpha, const double* dbeta, double* dz, cudaStream_t stream,
-                const int* skip) {
+                const int* skip, const SymvFuse* fuse) {
     if (ctx->ntri == 0) return ICQB_OK;
     if ((reinterpret_cast<uintptr_t>(dA) & 15) != 0)
         return set_error(ctx, ICQB_EARG, "symv: matrix must be 16-byte aligned");
@@ -263,11 +487,16 @@ int launch_symv(icqb_ctx* ctx, const double* dA, const double* dx, const double*
     P.beta = dbeta;
     P.Wc = p->d_Wc;
     P.Wr = p->d_Wr;
+    P.Wh = p->d_Wh;
+    P.headSlot = p->d_headSlot;
+    P.headBegin = p->d_headBegin;
+    P.headCount = p->d_headCount;
     P.wcols = p->wcols;
     P.z = dz;
     P.skip = skip;
+    if (fuse) P.F = *fuse;
     if (p->nTasks > 0) {
-        k_symv<<<(p->nTasks + kWarpsPerCta - 1) / kWarpsPerCta, kThreads, 0, stream>>>(P);
+        k_symv<<<p->grid, kThreads, kSmemBytes, stream>>>(P);
         ctx->launches += 1;
     }
     k_symv_reduce<<<(unsigned)((p->n + kT - 1) / kT), dim3(kT, 4), 0, stream>>>(P);

@@ -72,6 +72,12 @@ class ConjugateGradient:
         import torch
         self.precond = torch.from_numpy(numpy.ascontiguousarray(precond, numpy.float64)).to(self.device)
 
+    def setBlockPreconditioner(self, on=True):
+        """Extension: precondition with the inverse 128 x 128 diagonal blocks of the
+        (row-scaled) matrix instead of 1/diag; ignored once setDiagonalPreconditioner
+        has been called."""
+        self.ctx.check(self.lib.icqb_cg_set_preconditioner(self.ctx.handle, 1 if on else 0))
+
     def setRowScaling(self, scale):
         import torch
         self.rowScaling = torch.from_numpy(numpy.ascontiguousarray(scale, numpy.float64)).to(self.device)

@@ -498,3 +498,107 @@ def test_symmetric_product_vs_numpy(oracle_mod, nt, nph):
         y = solver.applyGreenMatrix(x)
         scale = numpy.abs(ref).dot(numpy.abs(x))
         assert (numpy.abs(y - ref.dot(x)) <= 1e-13 * scale).all()
+
+
+@pytest.mark.parametrize('n,blocks', [(6000, None), (2500, (0, 640, 1920, 2500)), (130, None)])
+def test_symmetric_product_synthetic_matrix(ctx, n, blocks):
+    """k_symv on a synthetic matrix obeying the mirror rule G[j,i] = G[i,j] A_i/A_j, written
+    straight into the tile-contiguous lower storage: sizes where tiles are split between
+    warps (head slots), spans cover whole tiles, and ragged last tiles.  The unstored
+    remainder of ragged tiles is NaN-filled: it must never reach the result."""
+    import torch
+    from icqsol_b200.bem import icqRowPartition as rp
+    from icqsol_b200.mesh.generators import uvSphere
+    nt = 2
+    while 2 * nt * (nt // 2 - 1) < n:
+        nt += 2
+    xyz, tri = uvSphere(1.0, nt, nt // 2)
+    tri = numpy.ascontiguousarray(tri[:n])
+    ctx.check(ctx.lib.icqb_set_mesh(ctx.handle, dp(xyz), xyz.shape[0], lp(tri), n))
+    if blocks is None:
+        blocks = (0, n, n, n)
+    ctx.check(ctx.lib.icqb_set_row_blocks(ctx.handle, *blocks))
+    a2 = numpy.zeros(n)
+    ctx.check(ctx.lib.icqb_area2_host(ctx.handle, dp(a2)))
+    rng = numpy.random.default_rng(n)
+    s = rng.normal(size=(n, n))
+    s = s + s.T
+    g = s * a2[None, :]
+    strips, ntiles = rp.lowerStrips(blocks)
+    assert ntiles == ctx.lib.icqb_lower_num_tiles(ctx.handle)
+    tiles = numpy.full((ntiles, 128, 128), numpy.nan)
+    for (row0, nrows, tileRow, base) in strips:
+        for J in range(tileRow + 1):
+            ce = min(n, (J + 1) * 128)
+            tiles[base + J, :nrows, :ce - J * 128] = g[row0:row0 + nrows, J * 128:ce]
+    dev = torch.device('cuda', 0)
+    dA = torch.from_numpy(tiles).to(dev)
+    glob = numpy.array(list(range(blocks[0], blocks[1])) + list(range(blocks[2], blocks[3])), int)
+    # the rows this context stores define the operator: entries (i,j) and (j,i) with i stored, j<=tile(i)
+    mask = numpy.zeros((n, n), bool)
+    for i in glob:
+        ce = min(n, (i // 128 + 1) * 128)
+        mask[i, :ce] = True
+    tI = numpy.arange(n) // 128
+    lowerPart = mask & (tI[None, :] < tI[:, None])      # strictly below the diagonal tiles
+    full = numpy.where(mask, g, 0.0) + numpy.where(lowerPart, g, 0.0).T * (a2[None, :] / a2[:, None])
+    for scaled in (0, 1):
+        x = rng.normal(size=n)
+        dx = torch.from_numpy(x).to(dev)
+        dy = torch.zeros(n, dtype=torch.float64, device=dev)
+        ctx.check(ctx.lib.icqb_symv_dev(ctx.handle, dA.data_ptr(), dx.data_ptr(), dy.data_ptr(), scaled))
+        y = dy.cpu().numpy()
+        ref = full.dot(x)
+        bound = numpy.abs(full).dot(numpy.abs(x))
+        if scaled:
+            ref = a2 * ref
+            bound = a2 * bound
+        assert numpy.isfinite(y).all()
+        assert (numpy.abs(y - ref) <= 1e-13 * bound + 1e-300).all()
+
+
+def test_block_preconditioner_cuts_iterations():
+    """LaplaceSolver with the inverse-diagonal-block preconditioner needs fewer CG
+    iterations than 1/diag (the reference class's default) and gives the same response."""
+    from icqsol_b200.mesh.generators import uvSphere
+    from icqsol_b200.mesh.polydata import PolyData
+    from icqsol_b200.bem.icqLaplaceSolver import LaplaceSolver
+    xyz, tri = uvSphere(1.0, 48, 24)
+    out = {}
+    for storage in ('lower', 'full'):
+        for kind in ('diagonal', 'block'):
+            solver = LaplaceSolver(PolyData.from_arrays(xyz, tri), float('inf'), 5, storage=storage,
+                                   preconditioner=kind)
+            solver.setSourceFromExpression('1./sqrt(x**2 + (y-2.)**2 + (z-4.)**2)')
+            v = solver.getSourceArray(solver.getSourceArrayIndex())
+            rsp = solver.computeResponseField()
+            g = solver.getGreenMatrix()
+            assert numpy.abs(v + g.dot(rsp)).max() / numpy.abs(v).max() < 1e-12
+            out[storage, kind] = (rsp, solver.lastSolveInfo['iterations'])
+        assert out[storage, 'block'][1] < out[storage, 'diagonal'][1]
+        # two solutions with backward error <= 5e-13 differ by <= cond(G) * 1e-12 (cond ~ 1e3..1e4)
+        assert relerr(out[storage, 'block'][0], out[storage, 'diagonal'][0]) < 1e-6
+    # the same arithmetic in both storages up to summation order
+    assert abs(out['lower', 'block'][1] - out['full', 'block'][1]) <= 3
+    assert relerr(out['lower', 'block'][0], out['full', 'block'][0]) < 1e-6
+
+
+@pytest.mark.parametrize('n', [300, 128, 517])
+def test_conjugate_gradient_block_preconditioner(n):
+    """ConjugateGradient.setBlockPreconditioner on a dense SPD matrix whose size is not a
+    multiple of the block (identity padding of the last block)."""
+    from icqsol_b200.solvers.icqConjugateGradient import ConjugateGradient
+    rng = numpy.random.default_rng(n)
+    q = rng.normal(size=(n, n))
+    a = q.dot(q.T) + n * numpy.eye(n)
+    xt = rng.normal(size=n)
+    b = a.dot(xt)
+    ref = ConjugateGradient(a, b)
+    x0, err0, k0 = ref.solve(numpy.zeros(n))
+    solver = ConjugateGradient(a, b)
+    solver.setBlockPreconditioner()
+    x, err, k = solver.solve(numpy.zeros(n))
+    assert err <= 1e-10 and numpy.abs(x - xt).max() < 1e-10
+    assert 0 < k <= k0
+    if n <= 128:
+        assert k <= 2     # one block: the preconditioner is the inverse
