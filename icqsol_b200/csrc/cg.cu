@@ -41,8 +41,10 @@ namespace icqb {
 namespace {
 
 constexpr int kT = 128;                      // rows per CTA of the vector kernels == preconditioner block
-constexpr int kGroups = 4;                   // thread groups of the block preconditioner product
-constexpr int kVThreads = kT * kGroups;      // 512
+constexpr int kGroups = 8;                   // thread groups of the block preconditioner product
+constexpr int kGroupRows = kT / kGroups;     // 16 rows of the inverse block per group
+constexpr int kVThreads = kT * kGroups;      // 1024
+static_assert(kGroups == 8, "k_cg_resid joins exactly eight groups");
 constexpr long long kBlockElems = (long long)kT * kT;
 constexpr int kInvThreads = 1024;
 constexpr int kInvLd = kT + 1;               // padded row of the in-shared-memory inversion
@@ -212,7 +214,7 @@ __global__ void __launch_bounds__(kVThreads) k_cg_resid(int mode, int k, int rep
     __shared__ double s_r[kT];
     __shared__ double s_acc[kGroups][kT];
     __shared__ double s_w4[5][4];
-    __shared__ double s_fin[kVThreads];
+    __shared__ double s_fin[3 * kVThreads];
     __shared__ int s_last;
     CgState* S = B.state;
     if (mode == kUpdate && S->done) return;
@@ -221,6 +223,16 @@ __global__ void __launch_bounds__(kVThreads) k_cg_resid(int mode, int k, int rep
     const long long i = T * kT + c;
     const bool own = (g == 0) && (i < B.n);
     double r = 0.0, ru = 0.0, a1 = 0.0, a2 = 0.0, w = 0.0;
+    const bool needW = (mode != kTrue) || replace;   // uniform
+    // the inverse block is symmetric: column c of rows 16g..16g+15, coalesced over c; all
+    // sixteen loads of a thread are issued before anything else so that they overlap the
+    // vector update
+    double m[kGroupRows];
+    if (needW && B.Minv) {
+        const double* M = B.Minv + T * kBlockElems + (long long)(g * kGroupRows) * kT + c;
+#pragma unroll
+        for (int rr = 0; rr < kGroupRows; ++rr) m[rr] = __ldg(M + rr * kT);
+    }
     if (own) {
         if (mode == kUpdate) {
             const double alpha = S->rho[k & 1] / S->pz;
@@ -250,19 +262,18 @@ __global__ void __launch_bounds__(kVThreads) k_cg_resid(int mode, int k, int rep
             }
         }
     }
-    const bool needW = (mode != kTrue) || replace;   // uniform
     if (needW) {
         if (B.Minv) {
             if (g == 0) s_r[c] = r;   // zero beyond n
             __syncthreads();
-            // the inverse block is symmetric: column c of rows 32g..32g+31, coalesced over c
-            const double* M = B.Minv + T * kBlockElems + (long long)(g * 32) * kT + c;
             double acc = 0.0;
-#pragma unroll 8
-            for (int rr = 0; rr < 32; ++rr) acc = fma(__ldg(M + rr * kT), s_r[g * 32 + rr], acc);
+#pragma unroll
+            for (int rr = 0; rr < kGroupRows; ++rr) acc = fma(m[rr], s_r[g * kGroupRows + rr], acc);
             s_acc[g][c] = acc;
             __syncthreads();
-            if (own) w = (s_acc[0][c] + s_acc[1][c]) + (s_acc[2][c] + s_acc[3][c]);
+            if (own)
+                w = ((s_acc[0][c] + s_acc[1][c]) + (s_acc[2][c] + s_acc[3][c])) +
+                    ((s_acc[4][c] + s_acc[5][c]) + (s_acc[6][c] + s_acc[7][c]));
         } else if (own) {
             w = r * B.minv[i];
         }
@@ -295,10 +306,11 @@ __global__ void __launch_bounds__(kVThreads) k_cg_resid(int mode, int k, int rep
     __threadfence();
     const int nP = (int)gridDim.x;
     double rho = 0.0, res2 = 0.0, resmax = 0.0, fa = 0.0, fb = 0.0;
-    if (needW) rho = final_reduce<false>(B.part_rw, nP, s_fin, tid, kVThreads);
     if (mode != kTrue) {
-        res2 = final_reduce<false>(B.part_res, nP, s_fin, tid, kVThreads);
-        resmax = final_reduce<true>(B.part_rmx, nP, s_fin, tid, kVThreads);
+        final_reduce3(B.part_rw, B.part_res, B.part_rmx, nP, s_fin, tid, kVThreads, &rho, &res2,
+                      &resmax);
+    } else if (replace) {
+        rho = final_reduce<false>(B.part_rw, nP, s_fin, tid, kVThreads);
     }
     if (mode != kUpdate) {
         fa = final_reduce<false>(B.part_a, nP, s_fin, tid, kVThreads);

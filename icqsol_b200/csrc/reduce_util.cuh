@@ -30,7 +30,7 @@ __device__ __forceinline__ double join4(const double* s4) {
 
 // Whole-CTA reduction of `count` partials from global memory (written by other CTAs
 // before their ticket): thread t takes partials t, t+T, ... in order, then a binary tree
-// over the T threads.  T = blockDim (power of two, <= 512); s_buf holds T doubles.
+// over the T threads.  T = blockDim (power of two); s_buf holds T doubles.
 // Every thread of the CTA must call; the result is returned on all threads.
 template <bool MAX>
 __device__ __forceinline__ double final_reduce(const double* part, int count, double* s_buf,
@@ -53,6 +53,42 @@ __device__ __forceinline__ double final_reduce(const double* part, int count, do
     const double out = s_buf[0];
     __syncthreads();
     return out;
+}
+
+// Three reductions at once (sum, sum, max) -- the closing step of a CG iteration needs
+// rho, |r|^2 and max|r| and should pay the tree's barriers once.  s_buf holds 3*T doubles.
+__device__ __forceinline__ void final_reduce3(const double* sumA, const double* sumB,
+                                              const double* maxC, int count, double* s_buf,
+                                              int tid, int nthreads, double* outA, double* outB,
+                                              double* outC) {
+    const volatile double* pa = sumA;
+    const volatile double* pb = sumB;
+    const volatile double* pc = maxC;
+    double a = 0.0, b = 0.0, c = 0.0;
+    for (int q = tid; q < count; q += nthreads) {
+        a += pa[q];
+        b += pb[q];
+        c = fmax(c, pc[q]);
+    }
+    double* sa = s_buf;
+    double* sb = s_buf + nthreads;
+    double* sc = s_buf + 2 * nthreads;
+    sa[tid] = a;
+    sb[tid] = b;
+    sc[tid] = c;
+    __syncthreads();
+    for (int off = nthreads >> 1; off > 0; off >>= 1) {
+        if (tid < off) {
+            sa[tid] += sa[tid + off];
+            sb[tid] += sb[tid + off];
+            sc[tid] = fmax(sc[tid], sc[tid + off]);
+        }
+        __syncthreads();
+    }
+    *outA = sa[0];
+    *outB = sb[0];
+    *outC = sc[0];
+    __syncthreads();
 }
 
 // Ticket of the "last CTA" pattern: thread 0 publishes this CTA's partials (already

@@ -49,6 +49,9 @@ constexpr int kChunkBytes = kChunkElems * 8;          // 8 KB
 constexpr int kWarps = 8;                             // independent pipelines per CTA
 constexpr int kDepth = 3;                             // chunks in flight per warp
 constexpr int kThreads = kWarps * 32;
+constexpr int kRedGroups = 8;                         // thread groups of the reduce kernel
+constexpr int kRedThreads = kT * kRedGroups;          // 1024
+static_assert(kRedGroups == 8, "k_symv_reduce joins exactly eight groups");
 constexpr int kSmemBytes =
     kWarps * kDepth * kChunkBytes + kWarps * kT * 8 + kWarps * kDepth * 8;   // 204,992 B
 
@@ -71,8 +74,8 @@ struct SymvParams {
     double* Wr;                 // [nTasks][128]  row partials per tile
     double* Wh;                 // [head slots][128] column partials of spans starting inside a tile
     const int* headSlot;        // [warps] slot of the warp's head segment, -1: none
-    const int* headBegin;       // [nTasks] first head slot of the tile
-    const int* headCount;       // [nTasks] number of head slots of the tile
+    const int* headColBegin;    // [column tiles + 1] CSR over column tiles J ...
+    const int* headColSlots;    // ... of the head slots whose tile lies in column tile J
     long long wcols;
     double* z;                  // [n]
     const int* skip;            // when non-null and *skip != 0 the kernels return at once
@@ -297,13 +300,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_symv(const SymvParams P) {
 }
 
 // z[j] = alpha_j * (row partials of j's strip over its tiles) + beta_j * (column partials of
-// the strips below).  One CTA per 128 global indices, 4 thread groups split the two sums and
-// are combined in a fixed order.  With SymvFuse the CTA also stores the new direction
+// the strips below).  One CTA per 128 global indices, kRedGroups thread groups split the two
+// sums (many independent loads in flight: the kernel is latency bound) and are combined in a
+// fixed order.  With SymvFuse the CTA also stores the new direction
 // p_j = w_j + beta p_j and leaves its share of p.z; the last CTA adds the shares.
-__global__ void __launch_bounds__(512) k_symv_reduce(const SymvParams P) {
-    __shared__ double s_row[4][kT], s_col[4][kT];
+__global__ void __launch_bounds__(kRedThreads) k_symv_reduce(const SymvParams P) {
+    __shared__ double s_row[kRedGroups][kT], s_col[kRedGroups][kT];
     __shared__ double s_dot[4];
-    __shared__ double s_fin[512];
+    __shared__ double s_fin[kRedThreads];
     __shared__ int s_last;
     if (P.skip && *P.skip) return;
     const int T = blockIdx.x, c = threadIdx.x, g = threadIdx.y;
@@ -317,29 +321,32 @@ __global__ void __launch_bounds__(512) k_symv_reduce(const SymvParams P) {
         const long long ltBeg = blk == 0 ? 0 : P.L.nTiles0;
         const long long ltEnd = blk == 0 ? P.L.nTiles0 : P.L.nLocal();
         const long long first = max(0LL, (long long)T + 1 - b0 / kT);
-        for (long long lt = ltBeg + first + g; lt < ltEnd; lt += 4) {
+#pragma unroll 4
+        for (long long lt = ltBeg + first + g; lt < ltEnd; lt += kRedGroups)
             col += P.Wc[lt * P.wcols + jl];
-            const long long tile = P.L.tileBase((int)lt) + T;
-            const int hc = __ldg(P.headCount + tile);
-            if (hc) {
-                const int hb = __ldg(P.headBegin + tile);
-                for (int q = 0; q < hc; ++q) col += P.Wh[(long long)(hb + q) * kT + c];
-            }
-        }
+    }
+    // column partials of the spans that started inside a tile of this column tile
+    if (P.headColBegin) {
+        const int hEnd = __ldg(P.headColBegin + T + 1);
+        for (int q = __ldg(P.headColBegin + T) + g; q < hEnd; q += kRedGroups)
+            col += P.Wh[(long long)__ldg(P.headColSlots + q) * kT + c];
     }
     // this tile row, if it is stored here
     const int lt = P.L.stripOf((long long)T * kT);
     if (lt >= 0) {
         const long long base = P.L.tileBase(lt);
-        for (int Jt = g; Jt <= T; Jt += 4) row += P.Wr[(base + Jt) * kT + c];
+#pragma unroll 4
+        for (int Jt = g; Jt <= T; Jt += kRedGroups) row += P.Wr[(base + Jt) * kT + c];
     }
     s_row[g][c] = row;
     s_col[g][c] = col;
     __syncthreads();
     double pzv = 0.0;
     if (g == 0 && j < P.n) {
-        row = (s_row[0][c] + s_row[1][c]) + (s_row[2][c] + s_row[3][c]);
-        col = (s_col[0][c] + s_col[1][c]) + (s_col[2][c] + s_col[3][c]);
+        row = ((s_row[0][c] + s_row[1][c]) + (s_row[2][c] + s_row[3][c])) +
+              ((s_row[4][c] + s_row[5][c]) + (s_row[6][c] + s_row[7][c]));
+        col = ((s_col[0][c] + s_col[1][c]) + (s_col[2][c] + s_col[3][c])) +
+              ((s_col[4][c] + s_col[5][c]) + (s_col[6][c] + s_col[7][c]));
         if (P.alpha) row *= P.alpha[j];
         if (P.beta) col *= P.beta[j];
         const double zj = row + col;
@@ -360,7 +367,8 @@ __global__ void __launch_bounds__(512) k_symv_reduce(const SymvParams P) {
         __syncthreads();
         if (s_last) {
             __threadfence();
-            const double pz = final_reduce<false>(P.F.pz_part, (int)gridDim.x, s_fin, tid, 512);
+            const double pz =
+                final_reduce<false>(P.F.pz_part, (int)gridDim.x, s_fin, tid, kRedThreads);
             if (tid == 0) {
                 *P.F.pz = pz;
                 *P.F.ticket = 0;
@@ -384,8 +392,8 @@ struct SymvPlan {
     double* d_Wr = nullptr;
     double* d_Wh = nullptr;
     int* d_headSlot = nullptr;
-    int* d_headBegin = nullptr;
-    int* d_headCount = nullptr;
+    int* d_headColBegin = nullptr;
+    int* d_headColSlots = nullptr;
 };
 
 void symv_plan_free(icqb_ctx* ctx) {
@@ -396,8 +404,8 @@ void symv_plan_free(icqb_ctx* ctx) {
     cudaFree(p->d_Wr);
     cudaFree(p->d_Wh);
     cudaFree(p->d_headSlot);
-    cudaFree(p->d_headBegin);
-    cudaFree(p->d_headCount);
+    cudaFree(p->d_headColBegin);
+    cudaFree(p->d_headColSlots);
     delete p;
     ctx->symv = nullptr;
 }
@@ -431,34 +439,40 @@ static int symv_plan(icqb_ctx* ctx) {
     // kernel): a span that starts inside an off-diagonal tile owns a head slot
     const long long nW = (long long)p->grid * kWarps;
     const long long total = (long long)p->nTasks * kChunksPerTile;
-    std::vector<int> headSlot((size_t)nW, -1), headBegin((size_t)p->nTasks, 0),
-        headCount((size_t)p->nTasks, 0);
-    int slots = 0;
+    const int nCols = (int)((p->n + kT - 1) / kT);
+    std::vector<int> headSlot((size_t)nW, -1), slotCol;
     for (long long gw = 0; gw < nW; ++gw) {
         const long long c0 = total * gw / nW, c1 = total * (gw + 1) / nW;
         if (c1 <= c0 || c0 % kChunksPerTile == 0) continue;
-        const long long tile = c0 / kChunksPerTile;
-        const SymvTask& t = tasks[(size_t)tile];
+        const SymvTask& t = tasks[(size_t)(c0 / kChunksPerTile)];
         if (t.J == (int)L.tileRow(t.lt)) continue;   // diagonal tile: no column part
-        if (headCount[(size_t)tile] == 0) headBegin[(size_t)tile] = slots;
-        headCount[(size_t)tile] += 1;
-        headSlot[(size_t)gw] = slots++;
+        headSlot[(size_t)gw] = (int)slotCol.size();
+        slotCol.push_back(t.J);
+    }
+    const int slots = (int)slotCol.size();
+    // CSR of the head slots by column tile (counting sort: slots stay in ascending order)
+    std::vector<int> headColBegin((size_t)nCols + 1, 0), headColSlots((size_t)std::max(slots, 1), 0);
+    for (int sidx = 0; sidx < slots; ++sidx) headColBegin[(size_t)slotCol[sidx] + 1] += 1;
+    for (int J = 0; J < nCols; ++J) headColBegin[(size_t)J + 1] += headColBegin[(size_t)J];
+    {
+        std::vector<int> fill(headColBegin.begin(), headColBegin.end() - 1);
+        for (int sidx = 0; sidx < slots; ++sidx) headColSlots[(size_t)fill[(size_t)slotCol[sidx]]++] = sidx;
     }
     ICQB_CUDA(ctx, cudaMalloc(&p->d_tasks, sizeof(SymvTask) * tasks.size()));
     ICQB_CUDA(ctx, cudaMalloc(&p->d_Wc, sizeof(double) * (size_t)L.nLocal() * p->wcols));
     ICQB_CUDA(ctx, cudaMalloc(&p->d_Wr, sizeof(double) * (size_t)p->nTasks * kT));
     ICQB_CUDA(ctx, cudaMalloc(&p->d_Wh, sizeof(double) * (size_t)std::max(slots, 1) * kT));
     ICQB_CUDA(ctx, cudaMalloc(&p->d_headSlot, sizeof(int) * headSlot.size()));
-    ICQB_CUDA(ctx, cudaMalloc(&p->d_headBegin, sizeof(int) * headBegin.size()));
-    ICQB_CUDA(ctx, cudaMalloc(&p->d_headCount, sizeof(int) * headCount.size()));
+    ICQB_CUDA(ctx, cudaMalloc(&p->d_headColBegin, sizeof(int) * headColBegin.size()));
+    ICQB_CUDA(ctx, cudaMalloc(&p->d_headColSlots, sizeof(int) * headColSlots.size()));
     ICQB_CUDA(ctx, cudaMemcpy(p->d_tasks, tasks.data(), sizeof(SymvTask) * tasks.size(),
                               cudaMemcpyHostToDevice));
     ICQB_CUDA(ctx, cudaMemcpy(p->d_headSlot, headSlot.data(), sizeof(int) * headSlot.size(),
                               cudaMemcpyHostToDevice));
-    ICQB_CUDA(ctx, cudaMemcpy(p->d_headBegin, headBegin.data(), sizeof(int) * headBegin.size(),
-                              cudaMemcpyHostToDevice));
-    ICQB_CUDA(ctx, cudaMemcpy(p->d_headCount, headCount.data(), sizeof(int) * headCount.size(),
-                              cudaMemcpyHostToDevice));
+    ICQB_CUDA(ctx, cudaMemcpy(p->d_headColBegin, headColBegin.data(),
+                              sizeof(int) * headColBegin.size(), cudaMemcpyHostToDevice));
+    ICQB_CUDA(ctx, cudaMemcpy(p->d_headColSlots, headColSlots.data(),
+                              sizeof(int) * headColSlots.size(), cudaMemcpyHostToDevice));
     // (every stored off-diagonal tile is begun by exactly one warp, which always writes the
     // tile's Wc slot, so Wc needs no initialisation)
     ICQB_CUDA(ctx, cudaFuncSetAttribute(k_symv, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -489,8 +503,8 @@ int launch_symv(icqb_ctx* ctx, const double* dA, const double* dx, const double*
     P.Wr = p->d_Wr;
     P.Wh = p->d_Wh;
     P.headSlot = p->d_headSlot;
-    P.headBegin = p->d_headBegin;
-    P.headCount = p->d_headCount;
+    P.headColBegin = p->d_headColBegin;
+    P.headColSlots = p->d_headColSlots;
     P.wcols = p->wcols;
     P.z = dz;
     P.skip = skip;
@@ -499,7 +513,7 @@ int launch_symv(icqb_ctx* ctx, const double* dA, const double* dx, const double*
         k_symv<<<p->grid, kThreads, kSmemBytes, stream>>>(P);
         ctx->launches += 1;
     }
-    k_symv_reduce<<<(unsigned)((p->n + kT - 1) / kT), dim3(kT, 4), 0, stream>>>(P);
+    k_symv_reduce<<<(unsigned)((p->n + kT - 1) / kT), dim3(kT, kRedGroups), 0, stream>>>(P);
     ctx->launches += 1;
     return check_cuda(ctx, cudaGetLastError(), "k_symv launch");
 }

@@ -173,37 +173,53 @@ def readVtkPolyData(filename):
     return pdata
 
 
-def _write_arrays(f, fieldData):
+def _write_arrays(f, fieldData, binary):
     n = fieldData.GetNumberOfArrays()
     if n == 0:
         return
-    f.write('FIELD FieldData {0}\n'.format(n))
+    f.write('FIELD FieldData {0}\n'.format(n).encode('latin-1'))
     for i in range(n):
         arr = fieldData.GetArray(i)
         data = arr.as_numpy()
-        f.write('{0} {1} {2} double\n'.format(arr.GetName(), data.shape[1], data.shape[0]))
+        f.write('{0} {1} {2} double\n'.format(arr.GetName(), data.shape[1],
+                                              data.shape[0]).encode('latin-1'))
         flat = data.reshape(-1)
-        for k in range(0, flat.size, 9):
-            f.write(' '.join(repr(float(v)) for v in flat[k:k + 9]) + '\n')
+        if binary:
+            f.write(flat.astype('>f8').tobytes() + b'\n')
+        else:
+            for k in range(0, flat.size, 9):
+                f.write((' '.join(repr(float(v)) for v in flat[k:k + 9]) + '\n').encode('latin-1'))
 
 
-def writeVtkPolyData(pdata, filename):
-    """Write an ASCII legacy POLYDATA file (points, polygons, cell/point arrays)."""
+def writeVtkPolyData(pdata, filename, binary=False):
+    """Write a legacy POLYDATA file (points, polygons, cell/point arrays), ASCII or -- like
+    the reference's default, shapes/icqShapeManager.py:725-751 -- big-endian BINARY."""
     xyz = pdata.GetPoints().as_float64()
     cells = pdata.GetPolys()._cells
-    with open(filename, 'w') as f:
-        f.write('# vtk DataFile Version 3.0\nvtk output\nASCII\nDATASET POLYDATA\n')
-        typ = 'double' if pdata.GetPoints()._xyz.dtype == numpy.float64 else 'float'
-        f.write('POINTS {0} {1}\n'.format(xyz.shape[0], typ))
-        for p in xyz:
-            f.write('{0!r} {1!r} {2!r}\n'.format(float(p[0]), float(p[1]), float(p[2])))
+    with open(filename, 'wb') as f:
+        f.write('# vtk DataFile Version 3.0\nvtk output\n{0}\nDATASET POLYDATA\n'.format(
+            'BINARY' if binary else 'ASCII').encode('latin-1'))
+        isDouble = pdata.GetPoints()._xyz.dtype == numpy.float64
+        f.write('POINTS {0} {1}\n'.format(xyz.shape[0], 'double' if isDouble else 'float').encode('latin-1'))
+        if binary:
+            f.write(xyz.astype('>f8' if isDouble else '>f4').tobytes() + b'\n')
+        else:
+            for p in xyz:
+                f.write('{0!r} {1!r} {2!r}\n'.format(float(p[0]), float(p[1]), float(p[2])).encode('latin-1'))
         size = sum(len(c) + 1 for c in cells)
-        f.write('POLYGONS {0} {1}\n'.format(len(cells), size))
-        for c in cells:
-            f.write('{0} {1}\n'.format(len(c), ' '.join(str(v) for v in c)))
+        f.write('POLYGONS {0} {1}\n'.format(len(cells), size).encode('latin-1'))
+        if binary:
+            flat = []
+            for c in cells:
+                flat.append(len(c))
+                flat.extend(c)
+            f.write(numpy.asarray(flat, '>i4').tobytes() + b'\n')
+        else:
+            for c in cells:
+                f.write('{0} {1}\n'.format(len(c), ' '.join(str(v) for v in c)).encode('latin-1'))
         if pdata.GetCellData().GetNumberOfArrays():
-            f.write('CELL_DATA {0}\n'.format(len(cells)))
-            _write_arrays(f, pdata.GetCellData())
+            f.write('CELL_DATA {0}\n'.format(len(cells)).encode('latin-1'))
+            _write_arrays(f, pdata.GetCellData(), binary)
         if pdata.GetPointData().GetNumberOfArrays():
-            f.write('POINT_DATA {0}\n'.format(xyz.shape[0]))
-            _write_arrays(f, pdata.GetPointData())
+            f.write('POINT_DATA {0}\n'.format(xyz.shape[0]).encode('latin-1'))
+            _write_arrays(f, pdata.GetPointData(), binary)

@@ -602,3 +602,37 @@ def test_conjugate_gradient_block_preconditioner(n):
     assert 0 < k <= k0
     if n <= 128:
         assert k <= 2     # one block: the preconditioner is the inverse
+
+
+def test_example_solve_laplace_cli(tmp_path, oracle_mod, capsys):
+    """examples/solveLaplace.py (the reference's CLI, config C1 style): legacy VTK in, binary
+    legacy VTK out with the response as a named cell field; the field solves G sigma = -v for
+    the oracle's G."""
+    import importlib.util
+    import os
+    from icqsol_b200.mesh.generators import uvSphere
+    from icqsol_b200.mesh.polydata import PolyData, extract_mesh
+    from icqsol_b200.mesh.vtk_legacy_io import readVtkPolyData, writeVtkPolyData
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location('solveLaplace',
+                                                  os.path.join(root, 'examples', 'solveLaplace.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    xyz, tri = uvSphere(1.0, 24, 12)
+    src = str(tmp_path / 'in.vtk')
+    dst = str(tmp_path / 'out.vtk')
+    writeVtkPolyData(PolyData.from_arrays(xyz, tri), src)
+    assert mod.main(['--input', src, '--output', dst, '--verbose',
+                     '--dirichlet', 'sin(pi*x)*cos(pi*y)*z']) == 0
+    assert 'normal electric field jump min/avg/max' in capsys.readouterr().out
+    assert mod.main([]) == 3
+    back = readVtkPolyData(dst)
+    xyz2, cells2 = extract_mesh(back)
+    assert (xyz2 == xyz).all() and (numpy.array(cells2) == tri).all()
+    sigma = back.GetCellData().GetArray('normal_electric_field').as_numpy()[:, 0]
+    v = back.GetCellData().GetArray('voltage').as_numpy()[:, 0]
+    cen = (xyz[tri[:, 0]] + xyz[tri[:, 1]] + xyz[tri[:, 2]]) / 3.
+    vref = numpy.sin(numpy.pi * cen[:, 0]) * numpy.cos(numpy.pi * cen[:, 1]) * cen[:, 2]
+    assert numpy.abs(v - vref).max() < 1e-14
+    g = oracle_mod.green_matrix(xyz, tri, 5, threads=True)
+    assert numpy.abs(v + g.dot(sigma)).max() / numpy.abs(v).max() < 1e-12

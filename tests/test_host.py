@@ -77,6 +77,26 @@ def test_vtk_reader_on_golden_meshes(golden, tmp_path):
     assert back.GetPointData().GetArray('Normals').GetNumberOfComponents() == 3
 
 
+def test_vtk_writer_binary_round_trip(golden, tmp_path):
+    """BINARY output (the reference's default, shapes/icqShapeManager.py:725-751) reads back
+    bit-identical: float32 points, polygons, double cell and point arrays."""
+    from icqsol_b200.mesh.polydata import PolyData, DataArray, extract_mesh
+    from icqsol_b200.mesh.vtk_legacy_io import readVtkPolyData, writeVtkPolyData
+    xyz, tri = golden.mesh('sphere')
+    pd = PolyData.from_arrays(xyz, tri)
+    vals = numpy.random.default_rng(0).normal(size=len(tri))
+    pd.GetCellData().AddArray(DataArray('normal_electric_field', vals))
+    pd.GetPointData().AddArray(DataArray('w', numpy.arange(3. * len(xyz)).reshape(-1, 3)))
+    path = str(tmp_path / 'sphere_bin.vtk')
+    writeVtkPolyData(pd, path, binary=True)
+    assert open(path, 'rb').read(200).split(b'\n')[2] == b'BINARY'
+    back = readVtkPolyData(path)
+    xyz2, cells2 = extract_mesh(back)
+    assert (xyz2 == xyz).all() and (numpy.array(cells2) == tri).all()
+    assert (back.GetCellData().GetArray('normal_electric_field').as_numpy()[:, 0] == vals).all()
+    assert back.GetPointData().GetArray('w').GetComponent(5, 2) == 17.0
+
+
 def test_vtk_reader_binary_and_ascii(tmp_path):
     from icqsol_b200.mesh.vtk_legacy_io import readVtkPolyData
     pts = numpy.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0.5]], '>f4')
