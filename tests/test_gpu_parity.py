@@ -636,3 +636,89 @@ def test_example_solve_laplace_cli(tmp_path, oracle_mod, capsys):
     assert numpy.abs(v - vref).max() < 1e-14
     g = oracle_mod.green_matrix(xyz, tri, 5, threads=True)
     assert numpy.abs(v + g.dot(sigma)).max() / numpy.abs(v).max() < 1e-12
+
+
+# ---- BASELINE.json configurations at (or near) full size: sampled oracle rows/columns and
+# ---- size-independent properties (the oracle cannot build a whole matrix of this size) ----
+
+def _sampled_checks(solver, xyz, tri, oracle_mod, rows, rsp=None, v=None):
+    """Column j of G by the device product G e_j (stored and mirrored entries) against the
+    oracle's column; rows of the oracle against the device solution."""
+    n = tri.shape[0]
+    for j in rows:
+        e = numpy.zeros(n)
+        e[j] = 1.0
+        col = solver.applyGreenMatrix(e)
+        ref = oracle_mod.block(xyz, tri, 0, n, j, j + 1, 5)[:, 0]
+        assert numpy.abs(col / ref - 1.).max() < TOL_ENTRY, j
+    if rsp is not None:
+        vmax = numpy.abs(v).max()
+        for i in rows:
+            grow = oracle_mod.block(xyz, tri, i, i + 1, 0, n, 5)[0]
+            assert abs(v[i] + grow.dot(rsp)) < 1e-12 * vmax, i
+
+
+def test_config_c2_full_size(oracle_mod):
+    """Config C2 (19,880-triangle UV sphere, BASELINE.json configs[1]): sampled columns of G
+    equal the oracle to 1e-12; the response satisfies the oracle's rows of G sigma = -v to
+    1e-12 max|v|; the product is linear; the device's own backward error agrees."""
+    from icqsol_b200.mesh.generators import uvSphere
+    from icqsol_b200.mesh.polydata import PolyData
+    from icqsol_b200.bem.icqLaplaceSolver import LaplaceSolver
+    xyz, tri = uvSphere(1.0, 142, 71)
+    n = tri.shape[0]
+    assert n == 19880
+    solver = LaplaceSolver(PolyData.from_arrays(xyz, tri), float('inf'), 5)
+    solver.setSourceFromExpression('1./sqrt(x**2 + (y-2.)**2 + (z-4.)**2)')
+    v = solver.getSourceArray(solver.getSourceArrayIndex())
+    rsp = solver.computeResponseField()
+    assert solver.lastSolveInfo['iterations'] < 400
+    assert solver.lastSolveInfo['residualInf'] <= 5e-13 * numpy.abs(v).max()
+    _sampled_checks(solver, xyz, tri, oracle_mod, [0, 141, 9999, 19751, 19879], rsp, v)
+    back = solver.applyGreenMatrix(rsp)
+    assert numpy.abs(v + back).max() < 1e-12 * numpy.abs(v).max()
+    rng = numpy.random.default_rng(5)
+    x, y = rng.normal(size=n), rng.normal(size=n)
+    lin = solver.applyGreenMatrix(2.0 * x - 3.0 * y) - (2.0 * solver.applyGreenMatrix(x) -
+                                                        3.0 * solver.applyGreenMatrix(y))
+    assert numpy.abs(lin).max() < 1e-12 * numpy.abs(solver.applyGreenMatrix(numpy.abs(x) + numpy.abs(y))).max()
+
+
+def test_config_c3_refined_bolt(golden, oracle_mod):
+    """Config C3's geometry at a size one GPU test can afford: test_results/testBoltFine.vtk
+    with every triangle split in 4 (9,400 triangles, areas down to 2e-7)."""
+    from icqsol_b200.mesh.generators import subdivide
+    from icqsol_b200.mesh.polydata import PolyData
+    from icqsol_b200.bem.icqLaplaceSolver import LaplaceSolver
+    xyz0, tri0 = golden.mesh('boltFine')
+    xyz, tri = subdivide(xyz0, tri0, 2)
+    n = tri.shape[0]
+    assert n == 4 * tri0.shape[0]
+    solver = LaplaceSolver(PolyData.from_arrays(xyz, tri), float('inf'), 5)
+    solver.setSourceFromExpression('1./sqrt(x**2 + (y-2.)**2 + (z-4.)**2)')
+    v = solver.getSourceArray(solver.getSourceArrayIndex())
+    rsp = solver.computeResponseField()
+    assert solver.lastSolveInfo['iterations'] < n
+    _sampled_checks(solver, xyz, tri, oracle_mod, [0, 4701, n - 1], rsp, v)
+
+
+def test_config_c4_hollow_sphere_poisson(oracle_mod):
+    """Config C4's geometry (tests/testHollowSphere.py: outer shell plus an inward-oriented
+    inner shell of doubled resolution), PoissonSolver v = G.charge against the oracle."""
+    from icqsol_b200.mesh.generators import hollowSphere
+    from icqsol_b200.mesh.polydata import PolyData
+    from icqsol_b200.bem.icqPoissonSolver import PoissonSolver
+    xyz, tri = hollowSphere(2.0, 1.0, 20, 10)
+    n = tri.shape[0]
+    for storage in ('lower', 'full'):
+        solver = PoissonSolver(PolyData.from_arrays(xyz, tri), float('inf'), 5, storage=storage)
+        solver.setSourceFromExpression('x + 2.0')
+        rsp = solver.computeResponseField()
+        g = oracle_mod.green_matrix(xyz, tri, 5, threads=True)
+        cen = (xyz[tri[:, 0]] + xyz[tri[:, 1]] + xyz[tri[:, 2]]) / 3.
+        ref = g.dot(cen[:, 0] + 2.0)
+        assert numpy.abs(rsp - ref).max() < 1e-12 * numpy.abs(ref).max()
+    xyz, tri = hollowSphere(2.0, 1.0, 100, 50)
+    assert tri.shape[0] == 49400      # the full-size C4 mesh of SURVEY.md section 8(d)
+    solver = PoissonSolver(PolyData.from_arrays(xyz, tri), float('inf'), 5)
+    _sampled_checks(solver, xyz, tri, oracle_mod, [0, 9800, 49399])
