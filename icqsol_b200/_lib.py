@@ -50,6 +50,7 @@ SIGNATURES = [
                                   c_uint64, c_uint64, c_double, c_int, c_int64, c_int64_p,
                                   c_double_p, c_double_p]),
     ('icqb_cg_set_preconditioner', c_int, [c_void_p, c_int]),
+    ('icqb_cg_last_stats', c_int, [c_void_p, c_int64_p, c_int64_p]),
     ('icqb_comm_unique_id', c_int, [c_void_p]),
     ('icqb_comm_init', c_int, [c_void_p, c_void_p, c_int, c_int]),
     ('icqb_comm_share', c_int, [c_void_p, c_void_p]),
@@ -123,6 +124,12 @@ class Context:
 
     def last_ms(self, which):
         return float(self.lib.icqb_last_ms(self.handle, int(which)))
+
+    def cg_stats(self):
+        """(residual replacements, matrix products enqueued) of the last CG solve."""
+        rep, prod = c_int64(0), c_int64(0)
+        self.check(self.lib.icqb_cg_last_stats(self.handle, byref(rep), byref(prod)))
+        return rep.value, prod.value
 
     def launch_count(self):
         return int(self.lib.icqb_launch_count(self.handle))

@@ -274,4 +274,6 @@ class BaseLaplaceSolver(BaseSolver):
         self.lastSolveInfo = {'iterations': iters.value, 'residual2': r2.value,
                               'residualInf': rinf.value, 'milliseconds': self.ctx.last_ms(4),
                               'gemvMilliseconds': self.ctx.last_ms(3)}
+        self.lastSolveInfo['residualReplacements'], self.lastSolveInfo['products'] = \
+            self.ctx.cg_stats()
         return x.cpu().numpy()

@@ -23,11 +23,12 @@
 //     of the host in batches, two batches in flight, so the GPU never waits for the
 //     host between iterations.
 //
-// Kernels per iteration, lower storage on one rank: k_symv (forms p = w + beta p on the
-// fly), k_symv_reduce (stores p, z = A p and p.z), k_cg_resid (x, r, w = M^-1 r, rho,
-// residual norms, beta, stopping flag).  With several ranks the partial products are
-// all-reduced and p.z becomes its own kernel; with row-block storage p = w + beta p is
-// its own kernel too.
+// Kernels per iteration, lower storage: k_symv (forms p = w + beta p on the fly),
+// k_symv_reduce (stores p, z = A p and p.z), k_cg_resid (x, r, w = M^-1 r, rho, residual
+// norms, beta, stopping flag).  With several ranks one NCCL all-reduce follows
+// k_symv_reduce: it sums the partial products and, in the slot behind them, the ranks'
+// p.z_g.  With row-block storage p = w + beta p and p.z are kernels of their own and the
+// product's row slices are all-gathered.
 #include <math.h>
 
 #include <algorithm>
@@ -59,6 +60,7 @@ struct CgBuf {
     const double* Minv;    // [nT][128][128] inverse diagonal blocks of diag(s) A; null: diagonal
     double *part_rw, *part_res, *part_rmx, *part_a, *part_b, *part_pz;   // [nT] CTA partials
     CgState* state;
+    const double* pz;      // p.(A p): &state->pz, or the slot behind z that the ranks all-reduce
     long long n;
 };
 
@@ -235,7 +237,7 @@ __global__ void __launch_bounds__(kVThreads) k_cg_resid(int mode, int k, int rep
     }
     if (own) {
         if (mode == kUpdate) {
-            const double alpha = S->rho[k & 1] / S->pz;
+            const double alpha = S->rho[k & 1] / *B.pz;
             r = fma(-alpha, B.z[i], B.r[i]);
             x[i] = fma(alpha, B.p[i], x[i]);
             B.r[i] = r;
@@ -388,16 +390,19 @@ struct MatVec {
     const double* area;        // storage 1: |db x dc| (mirror rule weights), full length
     const double* inv_area;    // storage 1: 1/area (for the unscaled product)
     double* gathered;          // storage 0: [nranks*chunk] staging for the all-gather
+    long long products = 0;    // products enqueued (iterations enqueued behind `done` included)
 
-    // scale != null: out = diag(area or scale) A v ; null: out = A v
+    // scale != null: out = diag(area or scale) A v ; null: out = A v.
+    // `extra` doubles behind out[n] ride along in the all-reduce (the fused p.z).
     int apply(const double* v, double* out, const double* scale, cudaStream_t st,
-              const int* skip = nullptr, const SymvFuse* fuse = nullptr) {
+              const int* skip = nullptr, const SymvFuse* fuse = nullptr, int extra = 0) {
         int rc;
+        ++products;
         if (storage == 1) {
             rc = launch_symv(ctx, A, v, area, scale ? area : nullptr,
                              scale ? nullptr : inv_area, out, st, skip, fuse);
             if (rc != ICQB_OK) return rc;
-            return comm_allreduce_sum(ctx, out, n, st);
+            return comm_allreduce_sum(ctx, out, n + extra, st);
         }
         const int P = comm_nranks(ctx);
         double* dst = (P == 1) ? out : gathered + (long long)comm_rank(ctx) * chunk;
@@ -419,6 +424,13 @@ extern "C" int icqb_cg_set_preconditioner(icqb_ctx* ctx, int kind) {
     if (kind != 0 && kind != 1)
         return set_error(ctx, ICQB_EARG, "icqb_cg_set_preconditioner: kind must be 0 (diagonal) or 1 (blocks)");
     ctx->precond_kind = kind;
+    return ICQB_OK;
+}
+
+extern "C" int icqb_cg_last_stats(const icqb_ctx* ctx, int64_t* replacements, int64_t* products) {
+    if (!ctx) return ICQB_EARG;
+    if (replacements) *replacements = ctx->cg_replacements;
+    if (products) *products = ctx->cg_products;
     return ICQB_OK;
 }
 
@@ -458,7 +470,7 @@ extern "C" int icqb_cg_solve_dev(icqb_ctx* ctx, uint64_t dA_, int64_t n, int64_t
                          "multiples of 128 (or at n)");
     const long long nfull = chunk * P;
     const long long stateDoubles = (sizeof(CgState) + 7) / 8;
-    const long long small = 8 * n + nfull + 6 * nT + stateDoubles;
+    const long long small = 8 * n + 8 + nfull + 6 * nT + stateDoubles;
     const long long need = small + (blockPrec ? nT * kBlockElems : 0) + 64;
     int rc = ensure_work(ctx, need);
     if (rc != ICQB_OK) return rc;
@@ -467,7 +479,7 @@ extern "C" int icqb_cg_solve_dev(icqb_ctx* ctx, uint64_t dA_, int64_t n, int64_t
     B.p = wp; wp += n;
     B.r = wp; wp += n;
     B.w = wp; wp += n;
-    B.z = wp; wp += n;
+    B.z = wp; wp += n + 8;   // + the all-reduced p.z slot of the multi-rank lower storage
     B.minv = wp; wp += n;
     B.s = wp; wp += n;
     double* diagA = wp; wp += n;
@@ -497,19 +509,19 @@ extern "C" int icqb_cg_solve_dev(icqb_ctx* ctx, uint64_t dA_, int64_t n, int64_t
     mv.inv_area = inv_area;
     mv.gathered = gathered;
 
-    // fusion of the direction update and of p.z into the symmetric product
+    // fusion of the direction update and of p.z into the symmetric product.  With several
+    // ranks every rank forms p.(its partial product) and the sum over the ranks rides in the
+    // all-reduce of the partial products, one slot behind z: p.z = sum_g p.z_g.
     SymvFuse fuse;
     const bool fuseDir = (storage == 1);
-    const bool fuseDot = fuseDir && P == 1;
+    B.pz = (fuseDir && P > 1) ? B.z + n : &B.state->pz;
     if (fuseDir) {
         fuse.w = B.w;
         fuse.beta = &B.state->beta;
         fuse.p = B.p;
-        if (fuseDot) {
-            fuse.pz_part = B.part_pz;
-            fuse.pz = &B.state->pz;
-            fuse.ticket = &B.state->ticket_dot;
-        }
+        fuse.pz_part = B.part_pz;
+        fuse.pz = const_cast<double*>(B.pz);
+        fuse.ticket = &B.state->ticket_dot;
     }
 
     cudaEvent_t evTotal0 = ctx->ev0, evTotal1 = ctx->ev1;
@@ -536,10 +548,10 @@ extern "C" int icqb_cg_solve_dev(icqb_ctx* ctx, uint64_t dA_, int64_t n, int64_t
                 ctx->launches += 1;
             }
             if (i == 0) ICQB_CUDA(ctx, cudaEventRecord(evg0[slot], st));
-            int r2 = mv.apply(B.p, B.z, scale, st, skip, fuseDir ? &fuse : nullptr);
+            int r2 = mv.apply(B.p, B.z, scale, st, skip, fuseDir ? &fuse : nullptr, fuseDir ? 1 : 0);
             if (r2 != ICQB_OK) return r2;
             if (i == 0) ICQB_CUDA(ctx, cudaEventRecord(evg1[slot], st));
-            if (!fuseDot) {
+            if (!fuseDir) {
                 k_cg_dot<<<vgrid, kT, 0, st>>>(B);
                 ctx->launches += 1;
             }
@@ -665,7 +677,7 @@ extern "C" int icqb_cg_solve_dev(icqb_ctx* ctx, uint64_t dA_, int64_t n, int64_t
                 --inflight;
                 k = hs.iters;
                 err = use_max ? hs.resmax : sqrt(hs.res2);
-                if (!(hs.res2 == hs.res2) || !(hs.pz == hs.pz)) breakdown = true;   // NaN
+                if (!(hs.res2 == hs.res2)) breakdown = true;   // NaN
                 if (hs.done || breakdown) stop = true;   // later batches are no-ops: drain them
             }
             if (breakdown) {  // singular / indefinite system
@@ -679,6 +691,8 @@ extern "C" int icqb_cg_solve_dev(icqb_ctx* ctx, uint64_t dA_, int64_t n, int64_t
         cudaEventElapsedTime(&ms, evTotal0, evTotal1);
         ctx->last_ms[kCg] = ms;
         if (gemv_count) ctx->last_ms[kGemv] = gemv_ms / (double)gemv_count;
+        ctx->cg_replacements = replacements;
+        ctx->cg_products = mv.products;
         if (iters) *iters = k;
         if (resid2) *resid2 = true2;
         if (residinf) *residinf = trueinf;

@@ -124,6 +124,7 @@ struct icqb_ctx {
     icqb::SymvPlan* symv = nullptr;
 
     int precond_kind = 0;   // CG preconditioner when none is passed: 0 diag(A), 1 inverse 128x128 diagonal blocks
+    int64_t cg_replacements = 0, cg_products = 0;   // statistics of the last solve
 
     double last_ms[icqb::kNumPhases] = {0, 0, 0, 0, 0};
     int64_t launches = 0;

@@ -170,6 +170,11 @@ int icqb_cg_solve_dev(icqb_ctx* ctx, uint64_t dA, int64_t n, int64_t ld, int sto
  *           hold the strongest couplings: 2-3x fewer iterations on the refined spheres.
  * A new context uses kind 0.  The solver classes of the Python layer select kind 1. */
 int icqb_cg_set_preconditioner(icqb_ctx* ctx, int kind);
+/* Statistics of the last icqb_cg_solve_dev: how often the recurrence residual was replaced
+ * by the true residual b - A x (0 = the first confirmation passed), and how many matrix
+ * products were enqueued (iterations + confirmations + the ones skipped behind the stop
+ * flag). */
+int icqb_cg_last_stats(const icqb_ctx* ctx, int64_t* replacements, int64_t* products);
 
 /* ---- multi-GPU plumbing -----------------------------------------------------------
  * One rank per process.  `unique_id` is the 128-byte ncclUniqueId produced by
