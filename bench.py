@@ -68,41 +68,84 @@ def centroid_potential(xyz, tri):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """SM clock and throttle reasons during the timed region: NVML polled every 5 ms
+    (nvidia_ml_py), or -- when NVML cannot be opened -- nvidia-smi in a loop (the recipe's
+    clocks line, ~10 samples per second)."""
     QUERY = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
              'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
              'clocks_event_reasons.sw_power_cap')
+    # nvmlClocksThrottleReason* bits
+    REASON_BITS = (('sw_power_cap', 0x4), ('hw_slowdown', 0x8), ('sw_thermal_slowdown', 0x20),
+                   ('hw_thermal_slowdown', 0x40))
 
     def __init__(self, index):
         threading.Thread.__init__(self, daemon=True)
         self.index = index
-        self.samples = []
+        self.sm = []
+        self.max_mhz = None
+        self.reasons = set()
+        self.source = None
         self.stop_flag = False
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(int(index))
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            pynvml.nvmlDeviceGetClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+            self.nvml = pynvml
+            self.source = 'nvml'
+        except Exception:
+            self.nvml = None
+            self.source = 'nvidia-smi'
+
+    def _sample_nvml(self):
+        nv = self.nvml
+        self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)))
+        try:
+            mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+        except Exception:
+            mask = 0
+        for name, bit in self.REASON_BITS:
+            if mask & bit:
+                self.reasons.add(name)
+
+    def _sample_smi(self):
+        out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.QUERY,
+                              '--format=csv,noheader,nounits'], capture_output=True,
+                             text=True, timeout=5).stdout.strip()
+        if not out:
+            return
+        f = [t.strip() for t in out.split(',')]
+        if f[0].replace('.', '').isdigit():
+            self.sm.append(float(f[0]))
+        if f[1].replace('.', '').isdigit():
+            self.max_mhz = max(self.max_mhz or 0., float(f[1]))
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for k, nm in enumerate(names):
+            if len(f) > 3 + k and f[3 + k].lower().startswith('active'):
+                self.reasons.add(nm)
 
     def run(self):
         while not self.stop_flag:
             try:
-                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.QUERY,
-                                      '--format=csv,noheader,nounits'], capture_output=True,
-                                     text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([f.strip() for f in out.split(',')])
+                if self.nvml is not None:
+                    self._sample_nvml()
+                    time.sleep(0.005)
+                else:
+                    self._sample_smi()
+                    time.sleep(0.05)
             except Exception:
-                pass
-            time.sleep(0.1)
+                if self.nvml is not None:   # NVML went wrong mid-run: fall back
+                    self.nvml = None
+                    self.source = 'nvidia-smi'
+                else:
+                    time.sleep(0.05)
 
     def summary(self):
-        sm = [float(s[0]) for s in self.samples if s[0].replace('.', '').isdigit()]
-        mx = [float(s[1]) for s in self.samples if s[1].replace('.', '').isdigit()]
-        reasons = set()
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for s in self.samples:
-            for k, nm in enumerate(names):
-                if len(s) > 3 + k and s[3 + k].lower().startswith('active'):
-                    reasons.add(nm)
-        return {'sm_mhz': float(numpy.median(sm)) if sm else None,
-                'sm_max_mhz': max(mx) if mx else None,
-                'reasons': sorted(reasons), 'samples': len(self.samples)}
+        return {'sm_mhz': float(numpy.median(self.sm)) if self.sm else None,
+                'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons),
+                'samples': len(self.sm), 'source': self.source}
 
 
 def measured_peaks():
@@ -301,7 +344,7 @@ def run_b200(args):
         r2 = ctypes.c_double(0.)
         rinf = ctypes.c_double(0.)
         ctx.check(lib.icqb_cg_solve_dev(ctx.handle, gbuf.data_ptr(), n, ld, 1 if lower else 0, area2, 0,
-                                        bdev.data_ptr(), xdev.data_ptr(), 5e-13, 2, -1,
+                                        bdev.data_ptr(), xdev.data_ptr(), 5e-13, 2, args.max_iters,
                                         ctypes.byref(iters), ctypes.byref(r2), ctypes.byref(rinf)))
         if record:
             phase['assembly_ms'].append(1e3 * (t1 - t0))
@@ -358,6 +401,7 @@ def run_b200(args):
         t0 = time.perf_counter()
         solver = LaplaceSolver(pd, float('inf'), 5, computeK=True, device=local,
                                storage=args.storage, preconditioner=args.preconditioner)
+        solver.setSolverMaxNumberOfIterations(args.max_iters)
         rsp = solver.computeResponseField()
         torch.cuda.synchronize(dev)
         dt = time.perf_counter() - t0
@@ -403,6 +447,7 @@ def run_b200(args):
                        'cg_iters': int(numpy.mean(phase['iters'])),
                        'cg_residual_replacements': int(numpy.max(phase['replacements'])),
                        'cg_products_enqueued': int(numpy.mean(phase['products'])),
+                       'cg_converged': bool(numpy.max(phase['residinf']) <= 1e-12 * numpy.abs(v).max()),
                        'cg_residual2': float(numpy.max(phase['resid'])),
                        'cg_backward_error_max_norm': float(numpy.max(phase['residinf']) / numpy.abs(v).max()),
                        'gemv_ms': gemv_ms, 'gemv_gbs_per_gpu': gemv_gbs,
@@ -466,6 +511,8 @@ def main():
                          "'full': complete row blocks, row-major GEMV")
     ap.add_argument('--preconditioner', default='block', choices=['block', 'diagonal'],
                     help="CG preconditioner: inverse 128x128 diagonal blocks, or 1/diag")
+    ap.add_argument('--max-iters', type=int, default=4000,
+                    help='CG iteration cap (a solve that needs more is reported as not converged)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':

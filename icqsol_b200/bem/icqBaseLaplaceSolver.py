@@ -276,4 +276,15 @@ class BaseLaplaceSolver(BaseSolver):
                               'gemvMilliseconds': self.ctx.last_ms(3)}
         self.lastSolveInfo['residualReplacements'], self.lastSolveInfo['products'] = \
             self.ctx.cg_stats()
+        # the reference's LU (bem/icqLaplaceSolver.py:36) cannot "not converge"; say so loudly
+        # when the iteration stopped short of the requested backward error (iteration cap,
+        # attainable accuracy, or a matrix the quadrature left too indefinite for CG)
+        bmax = float(numpy.abs(numpy.asarray(rhs, numpy.float64)).max()) if n else 0.
+        reached = rinf.value <= 2. * float(tol) * bmax or bmax == 0.
+        self.lastSolveInfo['converged'] = bool(reached)
+        if not reached:
+            import warnings
+            warnings.warn('icqsol_b200: CG stopped after {0} iterations with max|rhs - G x| = {1:.3e} '
+                          '(requested {2:.3e})'.format(iters.value, rinf.value, float(tol) * bmax),
+                          RuntimeWarning)
         return x.cpu().numpy()
