@@ -58,13 +58,15 @@ class BaseLaplaceSolver(BaseSolver):
                        (bem/icqLaplaceMatrices.cpp:97-98); 'full': complete row blocks
         @param preconditioner of the CG solve: 'block' = inverse 128 x 128 diagonal blocks of
                        diag(A) G, 'diagonal' = 1/diag (the reference CG class's default,
-                       solvers/icqConjugateGradient.py:19)
+                       solvers/icqConjugateGradient.py:19), 'block+caps' = EXPERIMENTAL: blocks,
+                       with one dense block over the leading and one over the trailing run of
+                       tiles that hold sliver triangles (icqRowPartition.sliverCapTiles)
         """
         BaseSolver.__init__(self, pdata, max_edge_length, order)
         if storage not in ('lower', 'full'):
             raise ValueError("storage must be 'lower' or 'full'")
-        if preconditioner not in ('block', 'diagonal'):
-            raise ValueError("preconditioner must be 'block' or 'diagonal'")
+        if preconditioner not in ('block', 'diagonal', 'block+caps'):
+            raise ValueError("preconditioner must be 'block', 'diagonal' or 'block+caps'")
         self.storage = storage
         self.preconditioner = preconditioner
 
@@ -84,7 +86,11 @@ class BaseLaplaceSolver(BaseSolver):
                                                 torch.cuda.current_stream().cuda_stream or 1))
 
         self.ctx.check(self.lib.icqb_cg_set_preconditioner(
-            self.ctx.handle, 1 if preconditioner == 'block' else 0))
+            self.ctx.handle, {'diagonal': 0, 'block': 1, 'block+caps': 2}[preconditioner]))
+        self.capTiles = (0, 0)
+        if preconditioner == 'block+caps':
+            self.capTiles = rowPartition.sliverCapTiles(self._xyz, self._tri)
+            self.ctx.check(self.lib.icqb_cg_set_cap_tiles(self.ctx.handle, *self.capTiles))
 
         self.rank, self.numRanks = rowPartition.worldInfo()
         # one NCCL communicator per process, shared by every solver

@@ -83,6 +83,37 @@ def lowerTilesToRows(tiles, blocks, n):
     return out
 
 
+def sliverCapTiles(xyz, tri, threshold=30., maxTiles=32):
+    """(head_tiles, tail_tiles) for the experimental 'block+caps' preconditioner: how many
+    leading (trailing) 128-triangle tiles to merge into one dense block so that every sliver
+    -- a triangle whose aspect Lmax^2 / |db x dc| exceeds ``threshold`` -- among the first
+    (last) ``maxTiles`` tiles is inside it.  Neighbouring slivers make diag(area) G
+    indefinite; on the UV spheres they are the fan at each pole and
+    every other triangle of the next band(s), i.e. they sit at the two ends of the triangle
+    list (aspect 51 at n_theta = 318, 26 for the rest of the first band, below 30 from the
+    second band on), and the block has to span the whole band to restore convergence.
+    Slivers in the middle of the list are not covered."""
+    xyz = numpy.asarray(xyz, numpy.float64)
+    tri = numpy.asarray(tri, numpy.int64)
+    n = tri.shape[0]
+    if n == 0:
+        return 0, 0
+    a, b, c = xyz[tri[:, 0]], xyz[tri[:, 1]], xyz[tri[:, 2]]
+    e2 = numpy.maximum.reduce([((b - a) ** 2).sum(1), ((c - b) ** 2).sum(1), ((a - c) ** 2).sum(1)])
+    area2 = numpy.sqrt((numpy.cross(b - a, c - a) ** 2).sum(1))
+    sliver = e2 > threshold * area2
+    nT = (n + TILE - 1) // TILE
+    flagged = numpy.zeros(nT, bool)
+    numpy.logical_or.at(flagged, numpy.arange(n) // TILE, sliver)
+    w = min(int(maxTiles), nT)
+    lead = numpy.nonzero(flagged[:w])[0]
+    head = int(lead[-1]) + 1 if lead.size else 0
+    w = min(int(maxTiles), nT - head)
+    trail = numpy.nonzero(flagged[nT - w:][::-1])[0] if w > 0 else numpy.zeros(0, int)
+    tail = int(trail[-1]) + 1 if trail.size else 0
+    return head, tail
+
+
 def foldedBlockSize(n, nranks):
     n, nranks = int(n), int(nranks)
     return max(TILE, (n + 2 * nranks * TILE - 1) // (2 * nranks * TILE) * TILE)

@@ -1,0 +1,569 @@
+// EXPERIMENTAL (written without GPU access at the end of round 1; not reachable unless the
+// caller selects preconditioner kind 2 AND sets cap tiles; its tests run only with
+// ICQB_EXPERIMENTAL=1): conjugate gradient with DENSE CAP BLOCKS in the block
+// preconditioner.
+//
+// Why: neighbouring sliver triangles (the two rings at each pole of a UV sphere) make the
+// reference's diag(A) G indefinite -- the wrong-sign eigenvectors live entirely on those
+// rings (tools/experiments/spectrum_sliver_sphere.py).  The CG of
+// cg.cu with 128 x 128 diagonal blocks then does not converge; with ONE dense diagonal block
+// over the leading sliver tiles and one over the trailing ones it converges in ~110
+// iterations in the numpy model (tools/experiments/pcg_cap_blocks.py).
+//
+// Same algorithm, state and product kernels as cg.cu (solvers/icqConjugateGradient.py:49-79);
+// what differs is the preconditioner step w = M^-1 r:
+//   * tile rows [0, head) and [nT - tail, nT) each form one dense block of diag(s) A,
+//     extracted from the stored tiles (lower storage: symmetric fill), all-reduced over the
+//     ranks, inverted in global memory by an unblocked Gauss-Jordan (2 small kernels per
+//     pivot: once per solve) and symmetrised;
+//   * per iteration the residual kernel is split in two so that the caps can be applied
+//     with the validated streaming GEMV in between:
+//         k_cg_vec    x += alpha p, r -= alpha z            (all rows)
+//         k_gemv      w_cap = C^-1 r_cap                    (one launch per cap)
+//         k_cg_close  w = M^-1 r on the other tiles, rho, norms, beta, stopping flag.
+#include "cg_kernels.cuh"
+
+namespace icqb {
+
+namespace {
+
+struct Cap {
+    long long t0 = 0, tiles = 0;   // tile rows [t0, t0 + tiles)
+    long long m = 0;               // 128 * tiles: order of the dense block
+    long long valid = 0;           // rows of the block below n
+    double* inv = nullptr;         // [m][m] row-major
+};
+
+// dense block of diag(scale) A over tile rows [t0, t0 + m/128) from the lower storage:
+// tiles J <= I are copied (rows this rank stores), tiles J < I also mirrored -- diag(s) A is
+// symmetric.  The buffer is zeroed before; identity beyond n.
+__global__ void __launch_bounds__(256) k_cap_extract_lower(const double* A, LowerLayout L,
+                                                           const double* scale, long long n,
+                                                           long long t0, long long m, double* out) {
+    const long long I = t0 + blockIdx.y, J = t0 + blockIdx.x;
+    if (J > I) return;
+    const int lt = L.stripOf(I * kT);
+    if (lt < 0) return;
+    const double* a = A + (L.tileBase(lt) + J) * kLowerTileElems;
+    for (int e = threadIdx.x; e < kT * kT; e += blockDim.x) {
+        const int r = e >> 7, c = e & (kT - 1);
+        const long long i = I * kT + r, j = J * kT + c;
+        double v;
+        if (i < n && j < n)
+            v = (scale ? scale[i] : 1.0) * a[e];
+        else
+            v = (I == J && r == c) ? 1.0 : 0.0;
+        const long long lr = (I - t0) * kT + r, lc = (J - t0) * kT + c;
+        out[lr * m + lc] = v;
+        if (J < I) out[lc * m + lr] = v;
+    }
+}
+
+// the same block from row-block storage (every tile of the block, rows this rank holds)
+__global__ void __launch_bounds__(256) k_cap_extract_full(const double* A, long long ld,
+                                                          long long r0, long long r1,
+                                                          const double* scale, long long n,
+                                                          long long t0, long long m, double* out) {
+    const long long I = t0 + blockIdx.y, J = t0 + blockIdx.x;
+    const bool ownsLast = (n - 1 >= r0 && n - 1 < r1);
+    for (int e = threadIdx.x; e < kT * kT; e += blockDim.x) {
+        const int r = e >> 7, c = e & (kT - 1);
+        const long long i = I * kT + r, j = J * kT + c;
+        double v = 0.0;
+        if (i < n) {
+            if (i >= r0 && i < r1 && j < n) v = (scale ? scale[i] : 1.0) * A[(i - r0) * ld + j];
+        } else if (ownsLast) {
+            v = (I == J && r == c) ? 1.0 : 0.0;
+        }
+        out[((I - t0) * kT + r) * m + (J - t0) * kT + c] = v;
+    }
+}
+
+// Gauss-Jordan without pivoting, pivot k, in global memory: first the pivot row and column
+// are saved (no writes), then every entry is updated from them.
+__global__ void __launch_bounds__(256) k_gj_pivot(const double* a, long long m, long long k,
+                                                  double* colk, double* rowk) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= m) return;
+    const double pivinv = 1.0 / a[k * m + k];
+    colk[t] = a[t * m + k];
+    rowk[t] = (t == k) ? pivinv : a[k * m + t] * pivinv;
+}
+
+__global__ void __launch_bounds__(kT) k_gj_update(double* a, long long m, long long k,
+                                                  const double* colk, const double* rowk) {
+    const long long i = blockIdx.y;
+    const long long j = (long long)blockIdx.x * kT + threadIdx.x;
+    const double pivinv = rowk[k];
+    double v = a[i * m + j];
+    if (i == k)
+        v = rowk[j];
+    else if (j == k)
+        v = -colk[i] * pivinv;
+    else
+        v = fma(-colk[i], rowk[j], v);
+    a[i * m + j] = v;
+}
+
+__global__ void __launch_bounds__(kT) k_cap_symmetrise(double* a, long long m) {
+    const long long i = blockIdx.y;
+    const long long j = (long long)blockIdx.x * kT + threadIdx.x;
+    if (j <= i) return;
+    const double avg = 0.5 * (a[i * m + j] + a[j * m + i]);
+    a[i * m + j] = avg;
+    a[j * m + i] = avg;
+}
+
+// first half of k_cg_resid: the vector update only
+__global__ void __launch_bounds__(kT) k_cg_vec(int mode, int k, int replace, const double* b,
+                                               const double* scale, double* x, CgBuf B) {
+    CgState* S = B.state;
+    if (mode == kUpdate && S->done) return;
+    const long long i = (long long)blockIdx.x * kT + threadIdx.x;
+    if (i >= B.n) return;
+    if (mode == kUpdate) {
+        const double alpha = S->rho[k & 1] / *B.pz;
+        B.r[i] = fma(-alpha, B.z[i], B.r[i]);
+        x[i] = fma(alpha, B.p[i], x[i]);
+    } else if (mode == kInit) {
+        const double s = scale ? scale[i] : 1.0;
+        B.s[i] = s;
+        B.r[i] = s * b[i] - B.z[i];
+        B.p[i] = 0.0;
+    } else if (replace) {
+        B.r[i] = B.s[i] * (b[i] - B.z[i]);
+    }
+}
+
+// second half of k_cg_resid: w = M^-1 r (cap tiles: already written by the cap GEMV),
+// partials, and the closing step by the last CTA -- the same arithmetic as k_cg_resid
+__global__ void __launch_bounds__(kVThreads) k_cg_close(int mode, int k, int replace,
+                                                        const double* b, CgBuf B,
+                                                        long long capHeadRows, long long capTailRow0) {
+    __shared__ double s_r[kT];
+    __shared__ double s_acc[kGroups][kT];
+    __shared__ double s_w4[5][4];
+    __shared__ double s_fin[3 * kVThreads];
+    __shared__ int s_last;
+    CgState* S = B.state;
+    if (mode == kUpdate && S->done) return;
+    const int c = threadIdx.x, g = threadIdx.y, tid = g * kT + c;
+    const long long T = blockIdx.x;
+    const long long i = T * kT + c;
+    const bool own = (g == 0) && (i < B.n);
+    const bool capTile = (T * kT < capHeadRows) || (T * kT >= capTailRow0);   // uniform
+    const bool needW = (mode != kTrue) || replace;                           // uniform
+    double r = 0.0, ru = 0.0, a1 = 0.0, a2 = 0.0, w = 0.0;
+    double m[kGroupRows];
+    if (needW && !capTile) {
+        const double* M = B.Minv + T * kBlockElems + (long long)(g * kGroupRows) * kT + c;
+#pragma unroll
+        for (int rr = 0; rr < kGroupRows; ++rr) m[rr] = __ldg(M + rr * kT);
+    }
+    if (own) {
+        if (mode == kTrue) {
+            const double t = b[i] - B.z[i];
+            a1 = t * t;
+            a2 = fabs(t);
+            if (replace) {
+                r = B.r[i];
+                ru = t;
+            }
+        } else {
+            r = B.r[i];
+            ru = r / B.s[i];
+            if (mode == kInit) {
+                const double bi = b[i];
+                a1 = bi * bi;
+                a2 = fabs(bi);
+            }
+        }
+    }
+    if (needW) {
+        if (!capTile) {
+            if (g == 0) s_r[c] = r;   // zero beyond n
+            __syncthreads();
+            double acc = 0.0;
+#pragma unroll
+            for (int rr = 0; rr < kGroupRows; ++rr) acc = fma(m[rr], s_r[g * kGroupRows + rr], acc);
+            s_acc[g][c] = acc;
+            __syncthreads();
+            if (own) {
+                w = ((s_acc[0][c] + s_acc[1][c]) + (s_acc[2][c] + s_acc[3][c])) +
+                    ((s_acc[4][c] + s_acc[5][c]) + (s_acc[6][c] + s_acc[7][c]));
+                B.w[i] = w;
+            }
+        } else if (own) {
+            w = B.w[i];   // C^-1 r of this cap, written by the GEMV before this kernel
+        }
+    }
+    if (g == 0) {
+        warp_part<false>(r * w, s_w4[0], tid);
+        warp_part<false>(ru * ru, s_w4[1], tid);
+        warp_part<true>(fabs(ru), s_w4[2], tid);
+        warp_part<false>(a1, s_w4[3], tid);
+        warp_part<true>(a2, s_w4[4], tid);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        if (needW) B.part_rw[T] = join4<false>(s_w4[0]);
+        if (mode != kTrue) {
+            B.part_res[T] = join4<false>(s_w4[1]);
+            B.part_rmx[T] = join4<true>(s_w4[2]);
+        }
+        if (mode != kUpdate) {
+            B.part_a[T] = join4<false>(s_w4[3]);
+            B.part_b[T] = join4<true>(s_w4[4]);
+        }
+        s_last = take_ticket(&S->ticket_res, gridDim.x) ? 1 : 0;
+    }
+    __syncthreads();
+    if (!s_last) return;
+
+    __threadfence();
+    const int nP = (int)gridDim.x;
+    double rho = 0.0, res2 = 0.0, resmax = 0.0, fa = 0.0, fb = 0.0;
+    if (mode != kTrue) {
+        final_reduce3(B.part_rw, B.part_res, B.part_rmx, nP, s_fin, tid, kVThreads, &rho, &res2,
+                      &resmax);
+    } else if (replace) {
+        rho = final_reduce<false>(B.part_rw, nP, s_fin, tid, kVThreads);
+    }
+    if (mode != kUpdate) {
+        fa = final_reduce<false>(B.part_a, nP, s_fin, tid, kVThreads);
+        fb = final_reduce<true>(B.part_b, nP, s_fin, tid, kVThreads);
+    }
+    if (tid == 0) {
+        if (mode == kUpdate) {
+            S->rho[(k + 1) & 1] = rho;
+            S->beta = rho / S->rho[k & 1];
+            S->res2 = res2;
+            S->resmax = resmax;
+            S->iters += 1;
+            if ((S->use_max ? resmax : res2) <= S->thr) S->done = 1;
+        } else if (mode == kInit) {
+            S->rho[0] = rho;
+            S->beta = 0.0;
+            S->res2 = res2;
+            S->resmax = resmax;
+            S->bb = fa;
+            S->bmax = fb;
+        } else {
+            S->tru2 = fa;
+            S->trumax = fb;
+            if (replace) {
+                S->rho[k & 1] = rho;
+                S->beta = (k > 0) ? rho / S->rho[(k - 1) & 1] : 0.0;
+            }
+        }
+        S->ticket_res = 0;
+        __threadfence();
+    }
+}
+
+}  // namespace
+
+int cg_solve_caps(icqb_ctx* ctx, uint64_t dA_, int64_t n, int64_t ld, int storage,
+                  uint64_t drowscale_, uint64_t db_, uint64_t dx_, double tol, int rel,
+                  int64_t maxit, int64_t* iters, double* resid2, double* residinf) {
+    // (arguments were validated by icqb_cg_solve_dev)
+    ICQB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const double* A = reinterpret_cast<const double*>(dA_);
+    const double* scale = reinterpret_cast<const double*>(drowscale_);
+    const double* b = reinterpret_cast<const double*>(db_);
+    double* x = reinterpret_cast<double*>(dx_);
+    const int P = comm_nranks(ctx), rank = comm_rank(ctx);
+    const long long chunk = (n + P - 1) / P;
+    if (maxit < 0) maxit = n;
+    cudaStream_t st = ctx->stream;
+    const long long nT = (n + kT - 1) / kT;
+    if (storage == 1 &&
+        ((ctx->r1 % kT != 0 && ctx->r1 != n) || (ctx->q1 > ctx->q0 && ctx->q1 % kT != 0 && ctx->q1 != n)))
+        return set_error(ctx, ICQB_EARG,
+                         "icqb_cg_solve_dev: the block preconditioner needs row blocks that end on "
+                         "multiples of 128 (or at n)");
+
+    // the two caps (clipped so that they do not overlap)
+    Cap cap[2];
+    cap[0].t0 = 0;
+    cap[0].tiles = std::min<long long>(std::max<long long>(ctx->cap_head_tiles, 0), nT);
+    cap[1].tiles = std::min<long long>(std::max<long long>(ctx->cap_tail_tiles, 0), nT - cap[0].tiles);
+    cap[1].t0 = nT - cap[1].tiles;
+    long long capDoubles = 0, mMax = 0;
+    for (int q = 0; q < 2; ++q) {
+        cap[q].m = cap[q].tiles * kT;
+        cap[q].valid = std::max<long long>(0, std::min<long long>(n, (cap[q].t0 + cap[q].tiles) * kT) -
+                                                  cap[q].t0 * kT);
+        capDoubles += cap[q].m * cap[q].m;
+        mMax = std::max(mMax, cap[q].m);
+    }
+    const long long capHeadRows = cap[0].m;
+    const long long capTailRow0 = cap[1].tiles > 0 ? cap[1].t0 * kT : nT * kT;
+
+    // work space
+    const long long nfull = chunk * P;
+    const long long stateDoubles = (sizeof(CgState) + 7) / 8;
+    const long long small = 8 * n + 8 + nfull + 6 * nT + stateDoubles;
+    const long long need = small + nT * kBlockElems + capDoubles + 2 * mMax + 64;
+    int rc = ensure_work(ctx, need);
+    if (rc != ICQB_OK) return rc;
+    CgBuf B;
+    double* wp = ctx->d_work;
+    B.p = wp; wp += n;
+    B.r = wp; wp += n;
+    B.w = wp; wp += n;
+    B.z = wp; wp += n + 8;
+    B.minv = wp; wp += n;
+    B.s = wp; wp += n;
+    wp += n;   // (diag(A) slot of cg.cu, unused here)
+    double* inv_area = wp; wp += n;
+    double* gathered = wp; wp += nfull;
+    B.part_rw = wp; wp += nT;
+    B.part_res = wp; wp += nT;
+    B.part_rmx = wp; wp += nT;
+    B.part_a = wp; wp += nT;
+    B.part_b = wp; wp += nT;
+    B.part_pz = wp; wp += nT;
+    B.state = reinterpret_cast<CgState*>(wp); wp += stateDoubles;
+    double* blocks = wp; wp += nT * kBlockElems;
+    cap[0].inv = wp; wp += cap[0].m * cap[0].m;
+    cap[1].inv = wp; wp += cap[1].m * cap[1].m;
+    double* gjCol = wp; wp += mMax;
+    double* gjRow = wp; wp += mMax;
+    B.Minv = blocks;
+    B.n = n;
+
+    MatVec mv;
+    mv.ctx = ctx;
+    mv.A = A;
+    mv.n = n;
+    mv.ld = ld;
+    mv.storage = storage;
+    mv.chunk = chunk;
+    mv.r0 = std::min<long long>(n, (long long)rank * chunk);
+    mv.r1 = std::min<long long>(n, mv.r0 + chunk);
+    mv.area = ctx->d_area2;
+    mv.inv_area = inv_area;
+    mv.gathered = gathered;
+
+    SymvFuse fuse;
+    const bool fuseDir = (storage == 1);
+    B.pz = (fuseDir && P > 1) ? B.z + n : &B.state->pz;
+    if (fuseDir) {
+        fuse.w = B.w;
+        fuse.beta = &B.state->beta;
+        fuse.p = B.p;
+        fuse.pz_part = B.part_pz;
+        fuse.pz = const_cast<double*>(B.pz);
+        fuse.ticket = &B.state->ticket_dot;
+    }
+
+    cudaEvent_t evTotal0 = ctx->ev0, evTotal1 = ctx->ev1;
+    cudaEvent_t evg0[2] = {nullptr, nullptr}, evg1[2] = {nullptr, nullptr}, evb[2] = {nullptr, nullptr};
+    for (int q = 0; q < 2; ++q) {
+        ICQB_CUDA(ctx, cudaEventCreate(&evg0[q]));
+        ICQB_CUDA(ctx, cudaEventCreate(&evg1[q]));
+        ICQB_CUDA(ctx, cudaEventCreateWithFlags(&evb[q], cudaEventDisableTiming));
+    }
+    double gemv_ms = 0.0;
+    long long gemv_count = 0;
+    int status = ICQB_OK;
+    const dim3 vblock(kT, kGroups);
+    const unsigned vgrid = (unsigned)nT;
+    const int* skip = reinterpret_cast<const int*>(B.state);   // &state->done
+    CgState* hslot = reinterpret_cast<CgState*>(ctx->h_pinned);
+
+    // w = M^-1 r and the closing step, after r has been updated by k_cg_vec
+    auto precondition = [&](int mode, int kk, int replace, const int* skipFlag) -> int {
+        const bool needW = (mode != kTrue) || replace;
+        if (needW) {
+            for (int q = 0; q < 2; ++q) {
+                if (cap[q].valid <= 0) continue;
+                const long long row0 = cap[q].t0 * kT;
+                int r2 = launch_gemv(ctx, cap[q].inv, cap[q].valid, cap[q].valid, cap[q].m,
+                                     B.r + row0, B.w + row0, nullptr, st, skipFlag);
+                if (r2 != ICQB_OK) return r2;
+            }
+        }
+        k_cg_close<<<vgrid, vblock, 0, st>>>(mode, kk, replace, b, B, capHeadRows, capTailRow0);
+        ctx->launches += 1;
+        return check_cuda(ctx, cudaGetLastError(), "k_cg_close launch");
+    };
+
+    auto enqueue_batch = [&](long long kstart, long long nb, int slot) -> int {
+        for (long long i = 0; i < nb; ++i) {
+            const int kk = (int)((kstart + i) & 0x3fffffff);
+            if (!fuseDir) {
+                k_cg_dir<<<128, 256, 0, st>>>(B);
+                ctx->launches += 1;
+            }
+            if (i == 0) ICQB_CUDA(ctx, cudaEventRecord(evg0[slot], st));
+            int r2 = mv.apply(B.p, B.z, scale, st, skip, fuseDir ? &fuse : nullptr, fuseDir ? 1 : 0);
+            if (r2 != ICQB_OK) return r2;
+            if (i == 0) ICQB_CUDA(ctx, cudaEventRecord(evg1[slot], st));
+            if (!fuseDir) {
+                k_cg_dot<<<vgrid, kT, 0, st>>>(B);
+                ctx->launches += 1;
+            }
+            k_cg_vec<<<vgrid, kT, 0, st>>>(kUpdate, kk, 0, b, scale, x, B);
+            ctx->launches += 1;
+            r2 = precondition(kUpdate, kk, 0, skip);
+            if (r2 != ICQB_OK) return r2;
+        }
+        ICQB_CUDA(ctx, cudaGetLastError());
+        ICQB_CUDA(ctx, cudaMemcpyAsync(&hslot[slot], B.state, sizeof(CgState), cudaMemcpyDeviceToHost, st));
+        ICQB_CUDA(ctx, cudaEventRecord(evb[slot], st));
+        return ICQB_OK;
+    };
+
+#define CG_TRY(expr)                       \
+    do {                                   \
+        status = (expr);                   \
+        if (status != ICQB_OK) goto done;  \
+    } while (0)
+#define CG_CUDA(expr) CG_TRY(check_cuda(ctx, (expr), #expr))
+
+    {
+        CG_CUDA(cudaEventRecord(evTotal0, st));
+        k_zero<<<128, 256, 0, st>>>(ctx->d_work, small);
+        ctx->launches += 1;
+        if (storage == 1) {
+            k_recip<<<128, 256, 0, st>>>(ctx->d_area2, inv_area, n);
+            ctx->launches += 1;
+        }
+        LowerLayout L{0, 0, 0, 0, 0, 0, 0};
+        if (storage == 1) CG_TRY(lower_layout(ctx, &L));
+
+        // 128 x 128 blocks (used outside the caps), as in cg.cu
+        if (storage == 1)
+            k_cg_blocks_lower<<<vgrid, 256, 0, st>>>(A, L, scale, n, blocks);
+        else
+            k_cg_blocks_full<<<vgrid, 256, 0, st>>>(A, ld, mv.r0, mv.r1, scale, n, blocks);
+        ctx->launches += 1;
+        CG_CUDA(cudaGetLastError());
+        CG_TRY(comm_allreduce_sum(ctx, blocks, nT * kBlockElems, st));
+        CG_CUDA(cudaFuncSetAttribute(k_cg_invert_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     kInvSmem));
+        k_cg_invert_blocks<<<vgrid, kInvThreads, kInvSmem, st>>>(blocks);
+        ctx->launches += 1;
+        CG_CUDA(cudaGetLastError());
+
+        // dense caps: extract, all-reduce, invert (Gauss-Jordan, 2 kernels per pivot), symmetrise
+        for (int q = 0; q < 2; ++q) {
+            if (cap[q].tiles <= 0) continue;
+            const long long m = cap[q].m;
+            CG_CUDA(cudaMemsetAsync(cap[q].inv, 0, sizeof(double) * m * m, st));
+            const dim3 tgrid((unsigned)cap[q].tiles, (unsigned)cap[q].tiles);
+            if (storage == 1)
+                k_cap_extract_lower<<<tgrid, 256, 0, st>>>(A, L, scale, n, cap[q].t0, m, cap[q].inv);
+            else
+                k_cap_extract_full<<<tgrid, 256, 0, st>>>(A, ld, mv.r0, mv.r1, scale, n, cap[q].t0, m,
+                                                         cap[q].inv);
+            ctx->launches += 1;
+            CG_CUDA(cudaGetLastError());
+            CG_TRY(comm_allreduce_sum(ctx, cap[q].inv, m * m, st));
+            const dim3 ugrid((unsigned)(m / kT), (unsigned)m);
+            for (long long k = 0; k < m; ++k) {
+                k_gj_pivot<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(cap[q].inv, m, k, gjCol, gjRow);
+                k_gj_update<<<ugrid, kT, 0, st>>>(cap[q].inv, m, k, gjCol, gjRow);
+            }
+            k_cap_symmetrise<<<ugrid, kT, 0, st>>>(cap[q].inv, m);
+            ctx->launches += 2 * m + 1;
+            CG_CUDA(cudaGetLastError());
+        }
+
+        // z = s * (A x0); r, w, rho_0 and the norms of b
+        CG_TRY(mv.apply(x, B.z, scale, st));
+        k_cg_vec<<<vgrid, kT, 0, st>>>(kInit, 0, 0, b, scale, x, B);
+        ctx->launches += 1;
+        CG_TRY(precondition(kInit, 0, 0, nullptr));
+
+        CgState hs;
+        CG_TRY(read_state(ctx, B.state, &hs));
+        const bool use_max = (rel == 2);
+        const double thr = use_max ? tol * hs.bmax : (rel ? tol * sqrt(hs.bb) : tol);
+        const double thr_dev = use_max ? thr : thr * thr;
+        double err = use_max ? hs.resmax : sqrt(hs.res2);
+        long long k = 0;
+        int replacements = 0;
+        double true2 = sqrt(hs.res2), trueinf = hs.resmax, prev_true = -1.0;
+        bool breakdown = false;
+        k_cg_state<<<1, 1, 0, st>>>(B.state, 0, 0, thr_dev, use_max ? 1 : 0, 1);
+        ctx->launches += 1;
+        const long long batch = 8;
+
+        while (true) {
+            if (err <= thr || k >= maxit) {
+                CG_TRY(mv.apply(x, B.z, nullptr, st));
+                const bool last = (k >= maxit) || replacements >= 8;
+                const int kk = (int)(k & 0x3fffffff);
+                k_cg_vec<<<vgrid, kT, 0, st>>>(kTrue, kk, last ? 0 : 1, b, scale, x, B);
+                ctx->launches += 1;
+                CG_TRY(precondition(kTrue, kk, last ? 0 : 1, nullptr));
+                CG_TRY(read_state(ctx, B.state, &hs));
+                true2 = sqrt(hs.tru2);
+                trueinf = hs.trumax;
+                const double truem = use_max ? trueinf : true2;
+                if (truem <= thr || last) break;
+                if (prev_true >= 0.0 && truem > 0.5 * prev_true) break;
+                prev_true = truem;
+                ++replacements;
+                err = truem;
+                k_cg_state<<<1, 1, 0, st>>>(B.state, 0, 0, thr_dev, use_max ? 1 : 0, 0);
+                ctx->launches += 1;
+            }
+            long long enq = k;
+            int inflight = 0, head = 0;
+            bool stop = false;
+            while (true) {
+                while (!stop && inflight < 2 && enq < maxit) {
+                    const long long nb = std::min<long long>(batch, maxit - enq);
+                    CG_TRY(enqueue_batch(enq, nb, (head + inflight) & 1));
+                    enq += nb;
+                    ++inflight;
+                }
+                if (inflight == 0) break;
+                CG_CUDA(cudaEventSynchronize(evb[head]));
+                hs = hslot[head];
+                float gms = 0;
+                if (cudaEventElapsedTime(&gms, evg0[head], evg1[head]) == cudaSuccess) {
+                    gemv_ms += gms;
+                    ++gemv_count;
+                }
+                head ^= 1;
+                --inflight;
+                k = hs.iters;
+                err = use_max ? hs.resmax : sqrt(hs.res2);
+                if (!(hs.res2 == hs.res2)) breakdown = true;
+                if (hs.done || breakdown) stop = true;
+            }
+            if (breakdown) {
+                true2 = trueinf = nan("");
+                break;
+            }
+        }
+        CG_CUDA(cudaEventRecord(evTotal1, st));
+        CG_CUDA(cudaStreamSynchronize(st));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, evTotal0, evTotal1);
+        ctx->last_ms[kCg] = ms;
+        if (gemv_count) ctx->last_ms[kGemv] = gemv_ms / (double)gemv_count;
+        ctx->cg_replacements = replacements;
+        ctx->cg_products = mv.products;
+        if (iters) *iters = k;
+        if (resid2) *resid2 = true2;
+        if (residinf) *residinf = trueinf;
+    }
+done:
+    if (status != ICQB_OK) cudaStreamSynchronize(st);
+    for (int q = 0; q < 2; ++q) {
+        cudaEventDestroy(evg0[q]);
+        cudaEventDestroy(evg1[q]);
+        cudaEventDestroy(evb[q]);
+    }
+    return status;
+#undef CG_TRY
+#undef CG_CUDA
+}
+
+}  // namespace icqb

@@ -123,7 +123,9 @@ struct icqb_ctx {
     icqb::Comm* comm = nullptr;
     icqb::SymvPlan* symv = nullptr;
 
-    int precond_kind = 0;   // CG preconditioner when none is passed: 0 diag(A), 1 inverse 128x128 diagonal blocks
+    int precond_kind = 0;   // CG preconditioner when none is passed: 0 diag(A), 1 inverse 128x128 diagonal blocks,
+                            // 2 (experimental) blocks + dense caps over cap_head_tiles / cap_tail_tiles
+    int64_t cap_head_tiles = 0, cap_tail_tiles = 0;
     int64_t cg_replacements = 0, cg_products = 0;   // statistics of the last solve
 
     double last_ms[icqb::kNumPhases] = {0, 0, 0, 0, 0};
@@ -152,6 +154,12 @@ int launch_diag(icqb_ctx* ctx, int order, double* dOut, int64_t stride);
 int launch_gemv(icqb_ctx* ctx, const double* dA, int64_t nrows, int64_t ncols, int64_t ld,
                 const double* dx, double* dy, const double* drowscale, cudaStream_t stream,
                 const int* skip = nullptr);
+
+// experimental CG with dense cap blocks in the preconditioner (cg_caps.cu); arguments as
+// icqb_cg_solve_dev without the diagonal preconditioner
+int cg_solve_caps(icqb_ctx* ctx, uint64_t dA, int64_t n, int64_t ld, int storage, uint64_t drowscale,
+                  uint64_t db, uint64_t dx, double tol, int rel, int64_t maxit, int64_t* iters,
+                  double* resid2, double* residinf);
 
 // NCCL plumbing (comm.cu); all no-ops for a single rank
 int comm_nranks(const icqb_ctx* ctx);

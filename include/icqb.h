@@ -170,6 +170,13 @@ int icqb_cg_solve_dev(icqb_ctx* ctx, uint64_t dA, int64_t n, int64_t ld, int sto
  *           hold the strongest couplings: 2-3x fewer iterations on the refined spheres.
  * A new context uses kind 0.  The solver classes of the Python layer select kind 1. */
 int icqb_cg_set_preconditioner(icqb_ctx* ctx, int kind);
+/* EXPERIMENTAL (kind 2, written at the end of round 1 without GPU access, tests gated by
+ * ICQB_EXPERIMENTAL=1): as kind 1, but the first `head_tiles` and the last `tail_tiles`
+ * 128-row tiles each form ONE dense diagonal block.  Neighbouring sliver triangles make the
+ * reference's diag(area) G indefinite and the wrong-sign eigenvectors live on those
+ * triangles; a dense block over them restores the convergence of the
+ * CG in the numpy model.  With kind 2 and no cap tiles the solve is the one of kind 1. */
+int icqb_cg_set_cap_tiles(icqb_ctx* ctx, int64_t head_tiles, int64_t tail_tiles);
 /* Statistics of the last icqb_cg_solve_dev: how often the recurrence residual was replaced
  * by the true residual b - A x (0 = the first confirmation passed), and how many matrix
  * products were enqueued (iterations + confirmations + the ones skipped behind the stop

@@ -722,3 +722,55 @@ def test_config_c4_hollow_sphere_poisson(oracle_mod):
     assert tri.shape[0] == 49400      # the full-size C4 mesh of SURVEY.md section 8(d)
     solver = PoissonSolver(PolyData.from_arrays(xyz, tri), float('inf'), 5)
     _sampled_checks(solver, xyz, tri, oracle_mod, [0, 9800, 49399])
+
+
+# ---- EXPERIMENTAL: dense cap blocks in the preconditioner (cg_caps.cu) ----------------------
+# Written at the end of round 1 without GPU access; run with ICQB_EXPERIMENTAL=1.
+
+experimental = pytest.mark.skipif(__import__('os').environ.get('ICQB_EXPERIMENTAL') != '1',
+                                  reason='experimental code path: set ICQB_EXPERIMENTAL=1')
+
+
+@experimental
+@pytest.mark.parametrize('storage', ['lower', 'full'])
+def test_cap_blocks_on_sliver_sphere(oracle_mod, storage):
+    """UV sphere with the pole slivers of the C3 size (n_theta = 318): diag(A) G is
+    indefinite, the plain block preconditioner does not converge, blocks + caps does
+    (109 iterations in the numpy model) and the response satisfies the oracle's system."""
+    from icqsol_b200.mesh.generators import uvSphere
+    from icqsol_b200.mesh.polydata import PolyData
+    from icqsol_b200.bem.icqLaplaceSolver import LaplaceSolver
+    xyz, tri = uvSphere(1.0, 318, 20)
+    solver = LaplaceSolver(PolyData.from_arrays(xyz, tri), float('inf'), 5, storage=storage,
+                           preconditioner='block+caps')
+    assert solver.capTiles == (8, 9)
+    solver.setSourceFromExpression('1./sqrt(x**2 + (y-2.)**2 + (z-4.)**2)')
+    v = solver.getSourceArray(solver.getSourceArrayIndex())
+    rsp = solver.computeResponseField()
+    assert solver.lastSolveInfo['converged']
+    assert solver.lastSolveInfo['iterations'] < 300
+    g = oracle_mod.green_matrix(xyz, tri, 5, threads=True)
+    assert numpy.abs(v + g.dot(rsp)).max() / numpy.abs(v).max() < 1e-12
+
+
+@experimental
+def test_cap_blocks_same_answer_on_regular_sphere():
+    """On a mesh the plain blocks handle, explicit caps give the same response."""
+    from icqsol_b200.mesh.generators import uvSphere
+    from icqsol_b200.mesh.polydata import PolyData
+    from icqsol_b200.bem.icqLaplaceSolver import LaplaceSolver
+    xyz, tri = uvSphere(1.0, 48, 24)
+    out = []
+    for caps in (None, (2, 3)):
+        solver = LaplaceSolver(PolyData.from_arrays(xyz, tri), float('inf'), 5,
+                               preconditioner='block' if caps is None else 'block+caps')
+        if caps:
+            solver.ctx.check(solver.lib.icqb_cg_set_cap_tiles(solver.ctx.handle, *caps))
+        solver.setSourceFromExpression('1./sqrt(x**2 + (y-2.)**2 + (z-4.)**2)')
+        v = solver.getSourceArray(solver.getSourceArrayIndex())
+        rsp = solver.computeResponseField()
+        g = solver.getGreenMatrix()
+        assert numpy.abs(v + g.dot(rsp)).max() / numpy.abs(v).max() < 1e-12
+        out.append((rsp, solver.lastSolveInfo['iterations']))
+    assert relerr(out[1][0], out[0][0]) < 1e-6
+    assert out[1][1] <= out[0][1] + 3

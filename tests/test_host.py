@@ -248,3 +248,24 @@ def test_bench_reference_arm_runs():
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line['impl'] == 'reference' and line['value'] > 0 and line['unit'] == 'entries/s'
     assert line['cpu_baseline']['kind'] in ('reference', 'port')
+
+
+def test_sliver_cap_tiles():
+    """Tiles to merge into the dense cap blocks of the experimental preconditioner: the pole
+    fan plus the band(s) whose triangles exceed the aspect threshold -- fan + 1 band at
+    n_theta = 238 and 318, fan + 2 bands at 448 (what the numpy model needs to converge,
+    tools/experiments/pcg_cap_blocks.py), nothing at config C2."""
+    from icqsol_b200.bem import icqRowPartition as rp
+    from icqsol_b200.mesh import generators as gen
+    for nt, nph, bands in ((318, 20, 1), (318, 159, 1), (448, 12, 2), (238, 119, 1)):
+        xyz, tri = gen.uvSphere(1.0, nt, nph)
+        n = tri.shape[0]
+        cap = nt + 2 * nt * bands                    # triangles of the fan and the bands
+        head, tail = rp.sliverCapTiles(xyz, tri)
+        assert head == (cap + 127) // 128, (nt, nph)
+        assert tail == (n + 127) // 128 - (n - cap) // 128, (nt, nph)
+    xyz, tri = gen.uvSphere(1.0, 142, 71)
+    assert rp.sliverCapTiles(xyz, tri) == (0, 0)
+    xyz, tri = gen.uvSphere(1.0, 448, 12)
+    assert rp.sliverCapTiles(xyz, tri, maxTiles=4) == (4, 4)
+    assert rp.sliverCapTiles(numpy.zeros((0, 3)), numpy.zeros((0, 3), int)) == (0, 0)
