@@ -285,7 +285,12 @@ def run_b200(args):
     stream = torch.cuda.Stream(device=dev)
     ctx.check(lib.icqb_set_stream(ctx.handle, stream.cuda_stream))
     _lib.attachCommunicator(ctx, rank, world, rowPartition.broadcastBytes)
-    ctx.check(lib.icqb_cg_set_preconditioner(ctx.handle, 1 if args.preconditioner == 'block' else 0))
+    ctx.check(lib.icqb_cg_set_preconditioner(
+        ctx.handle, {'diagonal': 0, 'block': 1, 'block+caps': 2}[args.preconditioner]))
+    cap_tiles = (0, 0)
+    if args.preconditioner == 'block+caps':    # experimental, see icqsol_b200/csrc/cg_caps.cu
+        cap_tiles = rowPartition.sliverCapTiles(xyz, tri)
+        ctx.check(lib.icqb_cg_set_cap_tiles(ctx.handle, *cap_tiles))
     ctx.check(lib.icqb_set_mesh(ctx.handle, xyz.ctypes.data_as(_lib.c_double_p), xyz.shape[0],
                                 tri.ctypes.data_as(_lib.c_int64_p), n))
     lower = args.storage == 'lower'
@@ -434,7 +439,7 @@ def run_b200(args):
             'config': {'workload': label, 'triangles': n, 'diag_order': 5, 'offdiag_order': 8,
                        'step': 'fused G+K assembly + CG solve (max|v+G sigma| <= 5e-13 max|v|)',
                        'rows_per_gpu': rows, 'storage': args.storage,
-                       'preconditioner': args.preconditioner,
+                       'preconditioner': args.preconditioner, 'cap_tiles': list(cap_tiles),
                        'parallelism': ('folded row blocks, lower storage x{0}' if lower
                                        else 'row-block x{0}').format(world),
                        'l2': 'inputs larger than L2 ({0:.2f} GB of G streamed per product per GPU)'.format(
@@ -509,8 +514,9 @@ def main():
     ap.add_argument('--storage', default='lower', choices=['lower', 'full'],
                     help="'lower': each pair entry stored once (mirror rule), symmetric product; "
                          "'full': complete row blocks, row-major GEMV")
-    ap.add_argument('--preconditioner', default='block', choices=['block', 'diagonal'],
-                    help="CG preconditioner: inverse 128x128 diagonal blocks, or 1/diag")
+    ap.add_argument('--preconditioner', default='block', choices=['block', 'diagonal', 'block+caps'],
+                    help="CG preconditioner: inverse 128x128 diagonal blocks, 1/diag, or (experimental) "
+                         "blocks with dense caps over the sliver tiles")
     ap.add_argument('--max-iters', type=int, default=4000,
                     help='CG iteration cap (a solve that needs more is reported as not converged)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
