@@ -21,8 +21,9 @@ enum Phase { kPrepare = 0, kOffDiag = 1, kDiag = 2, kGemv = 3, kCg = 4, kNumPhas
 // Tile-contiguous layout of the block-lower-triangular storage: the locally owned
 // 128-row strips are stored one after the other; strip lt (global tile row I) holds its
 // tiles J = 0..I back to back, each tile a contiguous row-major 128 x 128 block (128 KB).
-// Every warp of the symmetric product therefore streams one contiguous 128 KB chunk, and
-// the storage is exactly the lower triangle: 4 N^2 + O(128 N) bytes over all ranks.
+// The stored tiles of a rank are therefore ONE contiguous array, which the symmetric product
+// cuts evenly into per-warp spans of 8 KB chunks, and the storage is exactly the lower
+// triangle: 4 N^2 + O(128 N) bytes over all ranks.
 constexpr int kLowerTile = 128;
 constexpr long long kLowerTileElems = (long long)kLowerTile * kLowerTile;
 
