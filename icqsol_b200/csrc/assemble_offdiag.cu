@@ -56,6 +56,28 @@ struct OffDiagParams {
     int lower;              // 1 = block-lower-triangular storage
 };
 
+#ifdef ICQB_EMU   // CPU emulation build of the test suite (tools/emu): no PTX
+// same refinement on a seed of single precision (the hardware seed has >= 22 bits)
+__device__ __forceinline__ double rsqrt_1ulp(double x) {
+    double y0 = (double)(float)(1.0 / sqrt(x));
+    double t = x * y0;
+    double e = fma(-t, y0, 1.0);
+    double p = fma(e, 0.375, 0.5);
+    double q = e * y0;
+    return fma(p, q, y0);
+}
+// mbarrier modelled as the count of completed phases; a bulk copy completes when issued
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int) { *bar = 0; }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t*, uint32_t) {}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while ((*reinterpret_cast<volatile uint64_t*>(bar) & 1) == parity) emu::yield();
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes,
+                                         uint64_t* bar) {
+    memcpy(dst, src, bytes);
+    *bar += 1;
+}
+#else
 __device__ __forceinline__ double rsqrt_1ulp(double x) {
     // MUFU.RSQ64H seed (rel. error <= 2^-22.4) + one third-order step:
     // 1/sqrt(x) = y0 (1 - e)^(-1/2), e = 1 - x y0^2  ->  y0 (1 + e/2 + 3 e^2/8),
@@ -107,6 +129,8 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
         "l"(src), "r"(bytes), "r"(smem_u32(bar))
         : "memory");
 }
+
+#endif
 
 // Decode the CTA's tile pair.  Task order: the locally owned square block first
 // (lower-triangular tile pairs incl. the diagonal tiles), then the column ranges
@@ -185,7 +209,9 @@ __global__ void __launch_bounds__(kTileObs) k_offdiag(const OffDiagParams P) {
     if (tid == 0) {
         mbar_init(&s_bar[0], 1);
         mbar_init(&s_bar[1], 1);
+#ifndef ICQB_EMU
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#endif
     }
     __syncthreads();
 

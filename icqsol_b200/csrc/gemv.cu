@@ -20,6 +20,11 @@ namespace {
 constexpr int kThreads = 256;
 constexpr int kRows = 4;
 
+#ifdef ICQB_EMU   // CPU emulation build of the test suite (tools/emu): no PTX
+__device__ __forceinline__ double2 ld_stream(const double* p) {
+    return *reinterpret_cast<const double2*>(p);
+}
+#else
 __device__ __forceinline__ double2 ld_stream(const double* p) {
     double2 v;
     asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];"
@@ -27,6 +32,7 @@ __device__ __forceinline__ double2 ld_stream(const double* p) {
                  : "l"(p));
     return v;
 }
+#endif
 
 template <bool ALIGNED>
 __global__ void __launch_bounds__(kThreads) k_gemv(const double* __restrict__ A, long long nrows,

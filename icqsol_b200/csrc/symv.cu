@@ -82,6 +82,20 @@ struct SymvParams {
     SymvFuse F;                 // CG fusion (all null: plain product)
 };
 
+#ifdef ICQB_EMU   // CPU emulation build of the test suite (tools/emu): no PTX
+// mbarrier modelled as the count of completed phases; a bulk copy completes when issued
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int) { *bar = 0; }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t*, uint32_t) {}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while ((*reinterpret_cast<volatile uint64_t*>(bar) & 1) == parity) emu::yield();
+}
+__device__ __forceinline__ uint64_t policy_evict_first() { return 0; }
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar,
+                                         uint64_t) {
+    memcpy(dst, src, bytes);
+    *bar += 1;
+}
+#else
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
@@ -128,6 +142,8 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
         : "memory");
 }
 
+#endif
+
 // entry c of the multiplied vector: x, or the CG direction w + beta * p_old
 __device__ __forceinline__ double vec_at(const SymvParams& P, double cgBeta, long long c) {
     const double xv = __ldg(P.x + c);
@@ -156,7 +172,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_symv(const SymvParams P) {
     if (lane == 0) {
 #pragma unroll
         for (int s = 0; s < kDepth; ++s) mbar_init(&bar[s], 1);
+#ifndef ICQB_EMU
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#endif
         policy = policy_evict_first();
     }
     __syncwarp();

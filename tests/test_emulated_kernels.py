@@ -1,0 +1,238 @@
+"""The CUDA translation units, compiled for the CPU and run thread by thread
+(tools/emu: one fiber per CUDA thread, blocks one after the other, bulk copies and
+mbarriers modelled, "device" memory = host memory), driven through the same C ABI.
+
+What this checks where there is no GPU: the kernels' indexing, tile/strip/chunk
+partitions, head slots, shuffles, reductions, the device-side CG state machine and the
+host orchestration -- against the oracle.  What it cannot check: races, memory ordering,
+PTX, performance.  The product never loads this build (different file, only this module
+asks for it); the `-m gpu` tests remain the parity tests proper.
+"""
+import ctypes
+import os
+import sys
+
+import numpy
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, 'tools', 'emu'))
+
+
+@pytest.fixture(scope='module')
+def emu():
+    import build as emu_build
+    from icqsol_b200 import _lib
+    lib = ctypes.CDLL(emu_build.build())
+    for name, restype, argtypes in _lib.SIGNATURES:
+        fn = getattr(lib, name)
+        fn.restype = restype
+        fn.argtypes = argtypes
+    return lib
+
+
+def dp(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+
+
+def lp(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_int64))
+
+
+class Ctx:
+    """One emulated context with a UV-sphere mesh; sms = SM count the library sees (the
+    persistent product kernel sizes its grid and its static partition from it)."""
+
+    def __init__(self, lib, n_theta, n_phi, sms=4):
+        from icqsol_b200.mesh.generators import uvSphere
+        self.lib = lib
+        os.environ['ICQB_EMU_SMS'] = str(sms)
+        self.h = ctypes.c_void_p()
+        assert lib.icqb_create(ctypes.byref(self.h), 0) == 0
+        xyz, tri = uvSphere(1.0, n_theta, n_phi)
+        self.xyz, self.tri = numpy.ascontiguousarray(xyz), numpy.ascontiguousarray(tri)
+        self.n = self.tri.shape[0]
+        self.check(lib.icqb_set_mesh(self.h, dp(self.xyz), self.xyz.shape[0], lp(self.tri), self.n))
+
+    def check(self, status):
+        if status != 0:
+            raise RuntimeError(self.lib.icqb_last_error(self.h))
+
+    def close(self):
+        self.lib.icqb_destroy(self.h)
+
+    def rhs(self):
+        t, x = self.tri, self.xyz
+        cen = (x[t[:, 0]] + x[t[:, 1]] + x[t[:, 2]]) / 3.
+        return -1. / numpy.sqrt(cen[:, 0] ** 2 + (cen[:, 1] - 2.) ** 2 + (cen[:, 2] - 4.) ** 2)
+
+    def assemble_lower(self, blocks=None, with_k=False):
+        n = self.n
+        blocks = blocks or (0, n, n, n)
+        self.check(self.lib.icqb_set_row_blocks(self.h, *blocks))
+        nt = self.lib.icqb_lower_num_tiles(self.h)
+        bufs = [numpy.full((max(nt, 1), 128, 128), numpy.nan) for _ in range(3 if with_k else 1)]
+        ptr = [b.ctypes.data for b in bufs] + [0, 0]
+        self.check(self.lib.icqb_assemble_lower_dev(self.h, 5, ptr[0], ptr[1], ptr[2]))
+        return bufs
+
+    def solve(self, g, storage, kind, caps=None, ld=0, maxit=500):
+        n = self.n
+        b = numpy.ascontiguousarray(self.rhs())
+        x = numpy.zeros(n)
+        self.check(self.lib.icqb_cg_set_preconditioner(self.h, kind))
+        self.check(self.lib.icqb_cg_set_cap_tiles(self.h, *(caps or (0, 0))))
+        it, r2, ri = ctypes.c_int64(0), ctypes.c_double(0.), ctypes.c_double(0.)
+        self.check(self.lib.icqb_cg_solve_dev(
+            self.h, g.ctypes.data, n, ld, storage, self.lib.icqb_area2_dev(self.h), 0, b.ctypes.data,
+            x.ctypes.data, 5e-13, 2, maxit, ctypes.byref(it), ctypes.byref(r2), ctypes.byref(ri)))
+        return x, it.value, ri.value, b
+
+
+def model_iterations(g, a2, b, cuts):
+    """numpy model of the block-preconditioned CG of csrc/cg.cu with diagonal blocks
+    [cuts[k], cuts[k+1]): iterations to max|r/s| <= 5e-13 max|b|."""
+    n = len(b)
+    ms = a2[:, None] * g
+    ms = 0.5 * (ms + ms.T)
+    cuts = [c for c in cuts if c < n] + [n]
+    invs = [numpy.linalg.inv(ms[p:q, p:q]) for p, q in zip(cuts[:-1], cuts[1:])]
+
+    def pre(r):
+        out = numpy.empty_like(r)
+        for k, (p, q) in enumerate(zip(cuts[:-1], cuts[1:])):
+            out[p:q] = invs[k].dot(r[p:q])
+        return out
+    x, r, p, rho_old = numpy.zeros(n), a2 * b, numpy.zeros(n), 1.
+    w = pre(r)
+    for k in range(2000):
+        rho = r.dot(w)
+        p = w + (rho / rho_old if k else 0.) * p
+        z = ms.dot(p)
+        alpha = rho / p.dot(z)
+        x += alpha * p
+        r -= alpha * z
+        w = pre(r)
+        rho_old = rho
+        if numpy.abs(r / a2).max() <= 5e-13 * numpy.abs(b).max():
+            return k + 1
+    return -1
+
+
+def test_emulated_assembly_full_storage(emu, oracle_mod):
+    """k_prepare, k_diag, k_offdiag<G+K> (full storage, host-buffer API) on 144 triangles."""
+    c = Ctx(emu, 12, 7)
+    n = c.n
+    g, k = numpy.full((n, n), numpy.nan), numpy.full((n, n), numpy.nan)
+    c.check(emu.icqb_assemble_host(c.h, 5, dp(g), dp(k)))
+    ref = oracle_mod.green_matrix(c.xyz, c.tri, 5)
+    assert numpy.abs(g / ref - 1.).max() < 1e-12
+    kref = oracle_mod.k_block(c.xyz, c.tri, 0, n, 0, n)
+    assert numpy.abs(k - kref).max() < 1e-9 * numpy.abs(kref).max()
+    c.close()
+
+
+@pytest.mark.parametrize('sms', [1, 3, 4])
+def test_emulated_lower_storage_and_product(emu, oracle_mod, sms):
+    """Tile-contiguous lower storage (every stored entry, K and its transpose) and the
+    persistent product kernel for several static partitions of the chunk sequence: with 1 SM
+    a warp owns several chunks of a tile, with 4 most spans start inside a tile (head slots)."""
+    from icqsol_b200.bem import icqRowPartition as rp
+    c = Ctx(emu, 16, 9, sms=sms)
+    n = c.n                                            # 256 triangles: 2 strips, 3 tiles
+    g, kl, ku = c.assemble_lower(with_k=True)
+    ref = oracle_mod.green_matrix(c.xyz, c.tri, 5)
+    kref = oracle_mod.k_block(c.xyz, c.tri, 0, n, 0, n)
+    rows = rp.lowerTilesToRows(g, (0, n, n, n), n)
+    krows = rp.lowerTilesToRows(kl, (0, n, n, n), n)
+    kurows = rp.lowerTilesToRows(ku, (0, n, n, n), n)
+    for i in range(n):
+        ce = min(n, (i // 128 + 1) * 128)
+        assert numpy.abs(rows[i, :ce] / ref[i, :ce] - 1.).max() < 1e-12
+        assert numpy.abs(krows[i, :ce] - kref[i, :ce]).max() < 1e-9 * numpy.abs(kref).max()
+        assert numpy.abs(kurows[i, :ce] - kref[:ce, i]).max() < 1e-9 * numpy.abs(kref).max()
+    rng = numpy.random.default_rng(sms)
+    a2 = oracle_mod.area2(c.xyz, c.tri)
+    for scaled in (0, 1):
+        x, y = rng.normal(size=n), numpy.full(n, numpy.nan)
+        c.check(emu.icqb_symv_dev(c.h, g.ctypes.data, x.ctypes.data, y.ctypes.data, scaled))
+        want = ref.dot(x) * (a2 if scaled else 1.)
+        bound = numpy.abs(ref).dot(numpy.abs(x)) * (a2 if scaled else 1.)
+        assert (numpy.abs(y - want) <= 1e-13 * bound).all()
+    c.close()
+
+
+def test_emulated_product_of_partial_row_blocks(emu, oracle_mod):
+    """A rank that stores two separated row blocks (the folded layout of a multi-GPU run):
+    its product is the operator restricted to the stored entries and their mirrors."""
+    c = Ctx(emu, 20, 11, sms=2)                        # 400 triangles, tile rows 0..3
+    n = c.n
+    blocks = (128, 256, 384, 400)
+    (g,) = c.assemble_lower(blocks)
+    ref = oracle_mod.green_matrix(c.xyz, c.tri, 5)
+    a2 = oracle_mod.area2(c.xyz, c.tri)
+    mask = numpy.zeros((n, n), bool)
+    for i in list(range(128, 256)) + list(range(384, 400)):
+        mask[i, :min(n, (i // 128 + 1) * 128)] = True
+    tile = numpy.arange(n) // 128
+    lower = mask & (tile[None, :] < tile[:, None])
+    full = numpy.where(mask, ref, 0.) + numpy.where(lower, ref, 0.).T * (a2[None, :] / a2[:, None])
+    x, y = numpy.random.default_rng(1).normal(size=n), numpy.full(n, numpy.nan)
+    c.check(emu.icqb_symv_dev(c.h, g.ctypes.data, x.ctypes.data, y.ctypes.data, 0))
+    assert (numpy.abs(y - full.dot(x)) <= 1e-13 * numpy.abs(full).dot(numpy.abs(x)) + 1e-300).all()
+    c.close()
+
+
+def test_emulated_cg_matches_model(emu, oracle_mod):
+    """The device-side CG state machine (three kernels per iteration, batches in flight,
+    confirmation with the true residual): same iteration count as the numpy model of the
+    same preconditioner, solution checked with the oracle's matrix."""
+    c = Ctx(emu, 12, 7)                                # 144 triangles: blocks of 128 and 16
+    n = c.n
+    (g,) = c.assemble_lower()
+    ref = oracle_mod.green_matrix(c.xyz, c.tri, 5)
+    a2 = oracle_mod.area2(c.xyz, c.tri)
+    for kind, cuts in ((1, [0, 128]), (0, list(range(n)))):
+        x, iters, rinf, b = c.solve(g, 1, kind)
+        assert numpy.abs(b - ref.dot(x)).max() <= 1e-12 * numpy.abs(b).max()
+        assert abs(iters - model_iterations(ref, a2, b, cuts)) <= 1
+        assert rinf <= 5e-13 * numpy.abs(b).max()
+    # row-block storage: k_gemv, k_cg_dir, k_cg_dot
+    ld = (n + 15) // 16 * 16
+    gf = numpy.zeros((n, ld))
+    c.check(emu.icqb_set_rows(c.h, 0, n))
+    c.check(emu.icqb_assemble_dev(c.h, 5, gf.ctypes.data, 0, ld))
+    x, iters, rinf, b = c.solve(gf, 0, 1, ld=ld)
+    assert numpy.abs(b - ref.dot(x)).max() <= 1e-12 * numpy.abs(b).max()
+    assert abs(iters - model_iterations(ref, a2, b, [0, 128])) <= 1
+    c.close()
+
+
+@pytest.mark.parametrize('caps,cuts', [((1, 1), [0, 128]), ((2, 0), [0])])
+def test_emulated_cap_blocks(emu, oracle_mod, caps, cuts):
+    """EXPERIMENTAL path (csrc/cg_caps.cu, never run on a GPU yet): dense cap blocks --
+    extraction with the symmetric fill and the identity padding of the ragged last tile,
+    Gauss-Jordan in global memory, split residual kernels, cap GEMV -- against the numpy
+    model: caps of one tile each are the plain blocks, one cap over everything is the
+    exact inverse (one iteration)."""
+    c = Ctx(emu, 12, 7)
+    (g,) = c.assemble_lower()
+    ref = oracle_mod.green_matrix(c.xyz, c.tri, 5)
+    a2 = oracle_mod.area2(c.xyz, c.tri)
+    x, iters, rinf, b = c.solve(g, 1, 2, caps)
+    assert numpy.abs(b - ref.dot(x)).max() <= 1e-12 * numpy.abs(b).max()
+    assert abs(iters - model_iterations(ref, a2, b, cuts)) <= 1
+    c.close()
+
+
+def test_emulated_gemv(emu):
+    """k_gemv, aligned and unaligned paths, ragged sizes."""
+    c = Ctx(emu, 6, 4)
+    rng = numpy.random.default_rng(0)
+    for nrows, ncols, ld in ((5, 130, 130), (37, 129, 131), (4, 16, 16), (9, 1, 3)):
+        a = rng.normal(size=(nrows, ld))
+        x, y = rng.normal(size=ncols), numpy.full(nrows, numpy.nan)
+        c.check(emu.icqb_gemv_host(c.h, a.ctypes.data, nrows, ncols, ld, dp(x), dp(y)))
+        want = a[:, :ncols].dot(x)
+        assert (numpy.abs(y - want) <= 1e-13 * numpy.abs(a[:, :ncols]).dot(numpy.abs(x))).all()
+    c.close()

@@ -1,0 +1,231 @@
+// Runtime of the CPU emulation build (see include/cuda_runtime.h): cooperative fibers for the
+// threads of one block, a fake synchronous CUDA runtime.  Test infrastructure only.
+#include <stdio.h>
+#include <ucontext.h>
+
+#include <chrono>
+#include <vector>
+
+#include "cuda_runtime.h"
+
+namespace emu {
+
+namespace {
+
+constexpr size_t kStackBytes = 256 * 1024;
+
+struct Fiber {
+    ucontext_t uc;
+    ThreadCtx ctx;
+    bool done = false;
+    int warp = 0;
+};
+
+struct Block {
+    std::vector<Fiber> fibers;
+    int alive = 0;
+    int arrived = 0;
+    unsigned gen = 0;
+    std::vector<int> warpAlive, warpArrived;
+    std::vector<unsigned> warpGen;
+    std::vector<uint64_t> slots;     // 32 per warp
+    std::vector<unsigned char> smem;
+    const std::function<void()>* body = nullptr;
+};
+
+Block g_block;
+ucontext_t g_sched;
+Fiber* g_cur = nullptr;
+std::vector<char*> g_stacks;
+ThreadCtx g_hostCtx;
+
+void release_if_complete() {
+    Block& b = g_block;
+    if (b.alive > 0 && b.arrived == b.alive) {
+        b.arrived = 0;
+        b.gen++;
+    }
+    for (size_t w = 0; w < b.warpAlive.size(); ++w)
+        if (b.warpAlive[w] > 0 && b.warpArrived[w] == b.warpAlive[w]) {
+            b.warpArrived[w] = 0;
+            b.warpGen[w]++;
+        }
+}
+
+void fiber_entry() {
+    Fiber* f = g_cur;
+    (*g_block.body)();
+    f->done = true;
+    g_block.alive--;
+    g_block.warpAlive[f->warp]--;
+    release_if_complete();   // threads that left do not hold the others at a barrier
+    swapcontext(&f->uc, &g_sched);
+}
+
+}  // namespace
+
+ThreadCtx& cur() { return g_cur ? g_cur->ctx : g_hostCtx; }
+
+void yield() {
+    Fiber* f = g_cur;
+    swapcontext(&f->uc, &g_sched);
+}
+
+void syncthreads() {
+    Block& b = g_block;
+    const unsigned gen = b.gen;
+    b.arrived++;
+    if (b.arrived == b.alive) {
+        b.arrived = 0;
+        b.gen++;
+        return;
+    }
+    while (b.gen == gen) yield();
+}
+
+void syncwarp() {
+    Block& b = g_block;
+    const int w = g_cur->warp;
+    const unsigned gen = b.warpGen[w];
+    b.warpArrived[w]++;
+    if (b.warpArrived[w] == b.warpAlive[w]) {
+        b.warpArrived[w] = 0;
+        b.warpGen[w]++;
+        return;
+    }
+    while (b.warpGen[w] == gen) yield();
+}
+
+void* dyn_smem() { return g_block.smem.data(); }
+
+uint64_t* warp_slots() { return g_block.slots.data() + 32 * g_cur->warp; }
+
+void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body) {
+    const int nthreads = (int)(block.x * block.y * block.z);
+    if (nthreads <= 0 || nthreads > 1024) {
+        fprintf(stderr, "emu::launch: bad block size %d\n", nthreads);
+        abort();
+    }
+    while ((int)g_stacks.size() < nthreads) g_stacks.push_back((char*)malloc(kStackBytes));
+    Block& b = g_block;
+    b.body = &body;
+    const int nwarps = (nthreads + 31) / 32;
+    for (unsigned bz = 0; bz < grid.z; ++bz)
+        for (unsigned by = 0; by < grid.y; ++by)
+            for (unsigned bx = 0; bx < grid.x; ++bx) {
+                b.fibers.assign(nthreads, Fiber());
+                b.alive = nthreads;
+                b.arrived = 0;
+                b.gen = 0;
+                b.warpAlive.assign(nwarps, 0);
+                b.warpArrived.assign(nwarps, 0);
+                b.warpGen.assign(nwarps, 0);
+                b.slots.assign(32 * (size_t)nwarps, 0);
+                b.smem.assign(smem + 256, 0);
+                for (int t = 0; t < nthreads; ++t) {
+                    Fiber& f = b.fibers[t];
+                    f.ctx.tid.x = t % block.x;
+                    f.ctx.tid.y = (t / block.x) % block.y;
+                    f.ctx.tid.z = t / (block.x * block.y);
+                    f.ctx.bid.x = bx;
+                    f.ctx.bid.y = by;
+                    f.ctx.bid.z = bz;
+                    f.ctx.bdim = block;
+                    f.ctx.gdim = grid;
+                    f.warp = t / 32;
+                    b.warpAlive[f.warp]++;
+                    getcontext(&f.uc);
+                    f.uc.uc_stack.ss_sp = g_stacks[t];
+                    f.uc.uc_stack.ss_size = kStackBytes;
+                    f.uc.uc_link = nullptr;
+                    makecontext(&f.uc, fiber_entry, 0);
+                }
+                // round robin until every thread of the block has returned
+                long idle = 0;
+                while (b.alive > 0) {
+                    bool progressed = false;
+                    for (int t = 0; t < nthreads; ++t) {
+                        Fiber& f = b.fibers[t];
+                        if (f.done) continue;
+                        g_cur = &f;
+                        swapcontext(&g_sched, &f.uc);
+                        g_cur = nullptr;
+                        progressed = true;
+                    }
+                    if (!progressed) break;
+                    if (++idle > 50000000L) {
+                        fprintf(stderr, "emu::launch: block (%u,%u,%u) does not terminate (deadlock at a barrier?)\n",
+                                bx, by, bz);
+                        abort();
+                    }
+                }
+            }
+    b.body = nullptr;
+}
+
+}  // namespace emu
+
+// ---- fake runtime ---------------------------------------------------------------------------
+struct emuStream {
+    int dummy;
+};
+struct emuEvent {
+    std::chrono::steady_clock::time_point t;
+};
+
+static int g_num_sms = 4;
+
+cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
+cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
+cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr, int) {
+    const char* e = getenv("ICQB_EMU_SMS");
+    *v = e ? atoi(e) : g_num_sms;
+    return cudaSuccess;
+}
+cudaError_t cudaGetLastError() { return cudaSuccess; }
+const char* cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : "emulated error"; }
+cudaError_t emuMalloc(void** p, size_t bytes) {
+    // poison fresh memory with NaN patterns: reads of never-written "device" memory show up
+    size_t n = (bytes + 63) / 64 * 64 + 64;
+    void* q = aligned_alloc(256, (n + 255) / 256 * 256);
+    if (!q) return cudaErrorInvalidValue;
+    memset(q, 0xff, n);
+    *p = q;
+    return cudaSuccess;
+}
+cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
+cudaError_t cudaFreeHost(void* p) { free(p); return cudaSuccess; }
+cudaError_t cudaMemcpy(void* dst, const void* src, size_t bytes, cudaMemcpyKind) {
+    memmove(dst, src, bytes);
+    return cudaSuccess;
+}
+cudaError_t cudaMemcpyAsync(void* dst, const void* src, size_t bytes, cudaMemcpyKind k, cudaStream_t) {
+    return cudaMemcpy(dst, src, bytes, k);
+}
+cudaError_t cudaMemcpy2DAsync(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width,
+                              size_t height, cudaMemcpyKind, cudaStream_t) {
+    for (size_t r = 0; r < height; ++r)
+        memmove((char*)dst + r * dpitch, (const char*)src + r * spitch, width);
+    return cudaSuccess;
+}
+cudaError_t cudaMemsetAsync(void* p, int value, size_t bytes, cudaStream_t) {
+    memset(p, value, bytes);
+    return cudaSuccess;
+}
+cudaError_t cudaStreamCreate(cudaStream_t* s) { *s = new emuStream(); return cudaSuccess; }
+cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { return cudaStreamCreate(s); }
+cudaError_t cudaStreamDestroy(cudaStream_t s) { delete s; return cudaSuccess; }
+cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = new emuEvent(); return cudaSuccess; }
+cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { return cudaEventCreate(e); }
+cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
+cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t) {
+    e->t = std::chrono::steady_clock::now();
+    return cudaSuccess;
+}
+cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b) {
+    *ms = std::chrono::duration<float, std::milli>(b->t - a->t).count();
+    return cudaSuccess;
+}
