@@ -35,6 +35,10 @@ SIGNATURES = [
     ('icqb_set_row_blocks', c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64]),
     ('icqb_area2_dev', c_uint64, [c_void_p]),
     ('icqb_area2_host', c_int, [c_void_p, c_double_p]),
+    ('icqb_subdivide_dev', c_int, [c_void_p, c_uint64, c_uint64, c_int64, c_int, c_int, c_uint64,
+                                   c_uint64]),
+    ('icqb_subdivide_host', c_int, [c_void_p, c_double_p, c_int64, c_int64_p, c_int64, c_int, c_int,
+                                    c_double_p, c_int64_p]),
     ('icqb_assemble_dev', c_int, [c_void_p, c_int, c_uint64, c_uint64, c_int64]),
     ('icqb_lower_num_tiles', c_int64, [c_void_p]),
     ('icqb_assemble_lower_dev', c_int, [c_void_p, c_int, c_uint64, c_uint64, c_uint64]),

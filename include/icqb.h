@@ -80,6 +80,21 @@ int icqb_set_row_blocks(icqb_ctx* ctx, int64_t r0, int64_t r1, int64_t q0, int64
 uint64_t icqb_area2_dev(const icqb_ctx* ctx);
 int icqb_area2_host(icqb_ctx* ctx, double* out); /* same values, host double[ntri] */
 
+/* ---- uniform refinement ------------------------------------------------------------
+ * Every triangle -> k*k children (k per edge), parent orientation kept; the part of the
+ * reference's RefineSurface (shapes/icqRefineSurface.py:46-177, cell data copied from the
+ * parent to its children at :155-174) that does not need pytriangle.  Output sizes:
+ * xyz_out double[ntri*(k+1)(k+2)/2][3] (points duplicated per parent), tri_out
+ * int64[ntri*k*k][3]; children of parent t are tri_out[t*k*k .. (t+1)*k*k), so a cell
+ * array is inherited by repeating each value k*k times.  float32_points != 0 rounds the new
+ * coordinates to float32 (VTK's default point type, shapes/icqShapeManager.py:794-798).
+ * Point/child order and roundings equal icqsol_b200.mesh.generators.subdivide (bit-exact).
+ * The _dev form takes device pointers and is asynchronous on the context stream. */
+int icqb_subdivide_dev(icqb_ctx* ctx, uint64_t dxyz, uint64_t dtri, int64_t ntri, int k,
+                       int float32_points, uint64_t dxyz_out, uint64_t dtri_out);
+int icqb_subdivide_host(icqb_ctx* ctx, const double* xyz, int64_t npts, const int64_t* tri,
+                        int64_t ntri, int k, int float32_points, double* xyz_out, int64_t* tri_out);
+
 /* ---- assembly ----------------------------------------------------------------
  * Fills rows [r0, r1) of G -- and of K when dK != 0 -- into caller-owned device
  * buffers: dG[(r - r0)*ld + c], c in [0, ntri), ld >= ntri.

@@ -236,3 +236,27 @@ def test_emulated_gemv(emu):
         want = a[:, :ncols].dot(x)
         assert (numpy.abs(y - want) <= 1e-13 * numpy.abs(a[:, :ncols]).dot(numpy.abs(x))).all()
     c.close()
+
+
+@pytest.mark.parametrize('k,f32', [(1, 1), (2, 1), (3, 0), (6, 1)])
+def test_emulated_subdivide(emu, golden, k, f32):
+    """k_subdivide: bit-identical points and the same children as the host version
+    (mesh.generators.subdivide) on the reference's bolt mesh."""
+    from icqsol_b200.mesh.generators import subdivide
+    xyz, tri = golden.mesh('boltFine')
+    xyz = numpy.ascontiguousarray(xyz[:], numpy.float64)
+    tri = numpy.ascontiguousarray(tri[:300], numpy.int64)
+    want_xyz, want_tri = subdivide(xyz, tri, k, float32_points=bool(f32))
+    c = Ctx(emu, 6, 4)
+    npl = (k + 1) * (k + 2) // 2
+    got_xyz = numpy.full((len(tri) * npl, 3), numpy.nan)
+    got_tri = numpy.full((len(tri) * k * k, 3), -1, numpy.int64)
+    c.check(emu.icqb_subdivide_host(c.h, dp(xyz), len(xyz), lp(tri), len(tri), k, f32,
+                                    dp(got_xyz), lp(got_tri)))
+    if k == 1:
+        # the host version returns the mesh itself for k = 1; the kernel re-indexes per parent
+        assert (got_xyz[got_tri] == want_xyz[want_tri]).all()
+    else:
+        assert (got_xyz == want_xyz).all()
+        assert (got_tri == want_tri).all()
+    c.close()

@@ -724,6 +724,26 @@ def test_config_c4_hollow_sphere_poisson(oracle_mod):
     _sampled_checks(solver, xyz, tri, oracle_mod, [0, 9800, 49399])
 
 
+def test_subdivide_on_device(golden):
+    """k_subdivide against the host version: bit-identical points, same children; config C3's
+    mesh (testBoltFine, k = 6 -> 84,600 triangles) is produced on the device."""
+    from icqsol_b200.mesh.generators import subdivide
+    from icqsol_b200.mesh.refine import subdivideOnDevice, inheritCellData
+    xyz, tri = golden.mesh('boltFine')
+    for k, f32 in ((2, True), (3, False), (6, True)):
+        want_xyz, want_tri = subdivide(xyz, tri, k, float32_points=f32)
+        got_xyz, got_tri = subdivideOnDevice(xyz, tri, k, float32_points=f32)
+        assert (got_xyz == want_xyz).all() and (got_tri == want_tri).all()
+    assert got_tri.shape[0] == 84600
+    vals = inheritCellData(numpy.arange(len(tri)) * 1.5, 6)
+    assert vals.shape[0] == 84600 and vals[35] == 0. and vals[36] == 1.5
+    # areas are conserved: the children tile their parent
+    def areas(p, t):
+        return numpy.linalg.norm(numpy.cross(p[t[:, 1]] - p[t[:, 0]], p[t[:, 2]] - p[t[:, 0]]), axis=1)
+    x2, t2 = subdivideOnDevice(xyz, tri, 4, float32_points=False)
+    assert numpy.abs(areas(x2, t2).reshape(-1, 16).sum(1) / areas(numpy.asarray(xyz, float), tri) - 1).max() < 1e-9
+
+
 # ---- EXPERIMENTAL: dense cap blocks in the preconditioner (cg_caps.cu) ----------------------
 # Written at the end of round 1 without GPU access; run with ICQB_EXPERIMENTAL=1.
 
