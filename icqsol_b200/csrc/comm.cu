@@ -30,6 +30,32 @@ struct Api {
     std::string error;
 };
 
+#ifdef ICQB_EMU   // CPU emulation build of the test suite (tools/emu): ranks are threads of one process
+extern "C" {
+int emu_ncclGetUniqueId(void* id128);
+int emu_ncclCommInitRank(void** comm, int nranks, const void* id128, int rank);
+int emu_ncclCommDestroy(void* comm);
+int emu_ncclAllReduceSumF64(const void* send, void* recv, size_t count, void* comm);
+int emu_ncclAllGatherF64(const void* send, void* recv, size_t count, void* comm);
+}
+Api& api() {
+    static Api a;
+    if (a.handle) return a;
+    a.handle = &a;
+    a.GetUniqueId = [](ncclUniqueId* id) -> ncclResult_t { return emu_ncclGetUniqueId(id); };
+    a.CommInitRank = [](ncclComm_t* c, int n, ncclUniqueId id, int r) -> ncclResult_t {
+        return emu_ncclCommInitRank(reinterpret_cast<void**>(c), n, &id, r);
+    };
+    a.CommDestroy = [](ncclComm_t c) -> ncclResult_t { return emu_ncclCommDestroy(c); };
+    a.AllGather = [](const void* s, void* r, size_t n, int, ncclComm_t c, cudaStream_t) -> ncclResult_t {
+        return emu_ncclAllGatherF64(s, r, n, c);
+    };
+    a.AllReduce = [](const void* s, void* r, size_t n, int, int, ncclComm_t c,
+                     cudaStream_t) -> ncclResult_t { return emu_ncclAllReduceSumF64(s, r, n, c); };
+    a.GetErrorString = [](ncclResult_t) -> const char* { return "emulated NCCL error"; };
+    return a;
+}
+#else
 Api& api() {
     static Api a;
     if (a.handle || !a.error.empty()) return a;
@@ -54,6 +80,7 @@ Api& api() {
 #undef ICQB_SYM
     return a;
 }
+#endif
 
 }  // namespace
 

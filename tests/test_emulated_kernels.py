@@ -260,3 +260,63 @@ def test_emulated_subdivide(emu, golden, k, f32):
         assert (got_xyz == want_xyz).all()
         assert (got_tri == want_tri).all()
     c.close()
+
+
+def _run_ranks(emu, nranks, n_theta, n_phi, storage, kind, caps=None):
+    """One rank per thread (ctypes releases the GIL), the in-process NCCL stand-in of
+    tools/emu underneath: folded row blocks, sharded assembly, distributed CG."""
+    import threading
+    from icqsol_b200.bem import icqRowPartition as rp
+    uid = ctypes.create_string_buffer(128)
+    assert emu.icqb_comm_unique_id(uid) == 0
+    out, errors = [None] * nranks, []
+
+    def work(rank):
+        try:
+            c = Ctx(emu, n_theta, n_phi, sms=2)
+            c.check(emu.icqb_comm_init(c.h, uid, rank, nranks))
+            n = c.n
+            if storage == 1:
+                (g,) = c.assemble_lower(rp.foldedBlocks(n, rank, nranks))
+                ld = 0
+            else:
+                r0, r1 = rp.rowRange(n, rank, nranks)
+                ld = (n + 15) // 16 * 16
+                g = numpy.zeros((max(r1 - r0, 1), ld))
+                c.check(emu.icqb_set_rows(c.h, r0, r1))
+                c.check(emu.icqb_assemble_dev(c.h, 5, g.ctypes.data, 0, ld))
+            out[rank] = c.solve(g, storage, kind, caps, ld=ld) + (c,)
+        except Exception as e:    # noqa: BLE001 -- reported by the caller
+            errors.append((rank, repr(e)))
+    threads = [threading.Thread(target=work, args=(r,)) for r in range(nranks)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=600)
+    assert not errors, errors
+    assert all(o is not None for o in out), 'a rank did not finish'
+    return out
+
+
+@pytest.mark.parametrize('nranks,storage,kind,caps', [(2, 1, 1, None), (3, 1, 0, None), (2, 0, 1, None),
+                                                      (2, 1, 2, (1, 2))])
+def test_emulated_multi_rank_cg(emu, oracle_mod, nranks, storage, kind, caps):
+    """Sharded assembly and the distributed CG (all-reduce of the partial products with p.z in
+    the slot behind them, all-reduce of the preconditioner blocks / cap blocks, all-gather for
+    row blocks): every rank returns the same solution, it solves the oracle's system, and
+    the iteration count is the single-rank one."""
+    out = _run_ranks(emu, nranks, 20, 11, storage, kind, caps)     # 400 triangles, 4 tile rows
+    c = out[0][-1]
+    ref = oracle_mod.green_matrix(c.xyz, c.tri, 5)
+    a2 = oracle_mod.area2(c.xyz, c.tri)
+    x0, iters0, _, b, _ = out[0]
+    for x, iters, rinf, _, _ in out:
+        assert (x == x0).all() and iters == iters0
+        assert rinf <= 5e-13 * numpy.abs(b).max()
+    assert numpy.abs(b - ref.dot(x0)).max() <= 1e-12 * numpy.abs(b).max()
+    cuts = {0: list(range(c.n)), 1: [0, 128, 256, 384], 2: [0, 128, 384]}[kind]
+    if caps == (1, 2):
+        cuts = [0, 128, 256]      # head cap = tile 0, tiles 1 plain, tail cap = tiles 2..3
+    assert abs(iters0 - model_iterations(ref, a2, b, cuts)) <= 1
+    for o in out:
+        o[-1].close()

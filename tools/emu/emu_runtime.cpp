@@ -1,5 +1,6 @@
 // Runtime of the CPU emulation build (see include/cuda_runtime.h): cooperative fibers for the
 // threads of one block, a fake synchronous CUDA runtime.  Test infrastructure only.
+#include <setjmp.h>
 #include <stdio.h>
 #include <ucontext.h>
 
@@ -14,10 +15,15 @@ namespace {
 
 constexpr size_t kStackBytes = 256 * 1024;
 
+// A fiber is born with makecontext/swapcontext (which set up its stack) and from then on
+// switched with _setjmp/_longjmp: those do not save the signal mask, i.e. no system call per
+// switch (swapcontext does one, and a kernel launch switches millions of times).
 struct Fiber {
     ucontext_t uc;
+    jmp_buf jb;
     ThreadCtx ctx;
     bool done = false;
+    bool started = false;
     int warp = 0;
 };
 
@@ -33,11 +39,13 @@ struct Block {
     const std::function<void()>* body = nullptr;
 };
 
-Block g_block;
-ucontext_t g_sched;
-Fiber* g_cur = nullptr;
-std::vector<char*> g_stacks;
-ThreadCtx g_hostCtx;
+// per OS thread: the multi-rank tests run one rank per thread
+thread_local Block g_block;
+thread_local ucontext_t g_sched;
+thread_local jmp_buf g_sched_jb;
+thread_local Fiber* g_cur = nullptr;
+thread_local std::vector<char*> g_stacks;
+thread_local ThreadCtx g_hostCtx;
 
 void release_if_complete() {
     Block& b = g_block;
@@ -59,7 +67,7 @@ void fiber_entry() {
     g_block.alive--;
     g_block.warpAlive[f->warp]--;
     release_if_complete();   // threads that left do not hold the others at a barrier
-    swapcontext(&f->uc, &g_sched);
+    _longjmp(g_sched_jb, 1);
 }
 
 }  // namespace
@@ -68,7 +76,7 @@ ThreadCtx& cur() { return g_cur ? g_cur->ctx : g_hostCtx; }
 
 void yield() {
     Fiber* f = g_cur;
-    swapcontext(&f->uc, &g_sched);
+    if (_setjmp(f->jb) == 0) _longjmp(g_sched_jb, 1);
 }
 
 void syncthreads() {
@@ -148,7 +156,14 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& bod
                         Fiber& f = b.fibers[t];
                         if (f.done) continue;
                         g_cur = &f;
-                        swapcontext(&g_sched, &f.uc);
+                        if (_setjmp(g_sched_jb) == 0) {
+                            if (!f.started) {
+                                f.started = true;
+                                setcontext(&f.uc);      // first entry: onto the fiber's stack
+                            } else {
+                                _longjmp(f.jb, 1);
+                            }
+                        }
                         g_cur = nullptr;
                         progressed = true;
                     }
@@ -229,3 +244,109 @@ cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b) {
     *ms = std::chrono::duration<float, std::milli>(b->t - a->t).count();
     return cudaSuccess;
 }
+
+// ---- in-process stand-in for NCCL: one rank per OS thread ----------------------------------------
+// (bound by csrc/comm.cu under ICQB_EMU instead of dlopen("libnccl.so.2"))
+#include <condition_variable>
+#include <map>
+#include <mutex>
+
+namespace {
+
+struct World {
+    int nranks = 0;
+    std::mutex m;
+    std::condition_variable cv;
+    int arrived = 0;
+    unsigned gen = 0;
+    std::vector<const void*> send;
+
+    void barrier() {
+        std::unique_lock<std::mutex> lock(m);
+        const unsigned g = gen;
+        if (++arrived == nranks) {
+            arrived = 0;
+            ++gen;
+            cv.notify_all();
+        } else {
+            cv.wait(lock, [&] { return gen != g; });
+        }
+    }
+};
+
+struct FakeComm {
+    World* world;
+    int rank;
+};
+
+std::mutex g_worlds_mutex;
+std::map<long long, World*> g_worlds;
+long long g_next_id = 1;
+
+}  // namespace
+
+extern "C" {
+
+int emu_ncclGetUniqueId(void* id128) {
+    std::lock_guard<std::mutex> lock(g_worlds_mutex);
+    memset(id128, 0, 128);
+    const long long id = g_next_id++;
+    memcpy(id128, &id, sizeof(id));
+    return 0;
+}
+
+int emu_ncclCommInitRank(void** comm, int nranks, const void* id128, int rank) {
+    long long id = 0;
+    memcpy(&id, id128, sizeof(id));
+    World* w;
+    {
+        std::lock_guard<std::mutex> lock(g_worlds_mutex);
+        World*& slot = g_worlds[id];
+        if (!slot) {
+            slot = new World();
+            slot->nranks = nranks;
+            slot->send.assign(nranks, nullptr);
+        }
+        w = slot;
+    }
+    *comm = new FakeComm{w, rank};
+    w->barrier();
+    return 0;
+}
+
+int emu_ncclCommDestroy(void* comm) {
+    delete static_cast<FakeComm*>(comm);
+    return 0;
+}
+
+// sum of doubles in rank order, identical on every rank
+int emu_ncclAllReduceSumF64(const void* send, void* recv, size_t count, void* comm) {
+    FakeComm* c = static_cast<FakeComm*>(comm);
+    World* w = c->world;
+    w->send[c->rank] = send;
+    w->barrier();
+    std::vector<double> tmp(count, 0.0);
+    for (int r = 0; r < w->nranks; ++r) {
+        const double* s = static_cast<const double*>(w->send[r]);
+        for (size_t k = 0; k < count; ++k) tmp[k] += s[k];
+    }
+    w->barrier();
+    memcpy(recv, tmp.data(), sizeof(double) * count);
+    w->barrier();
+    return 0;
+}
+
+int emu_ncclAllGatherF64(const void* send, void* recv, size_t count, void* comm) {
+    FakeComm* c = static_cast<FakeComm*>(comm);
+    World* w = c->world;
+    w->send[c->rank] = send;
+    w->barrier();
+    std::vector<double> tmp(count * w->nranks);
+    for (int r = 0; r < w->nranks; ++r) memcpy(tmp.data() + r * count, w->send[r], sizeof(double) * count);
+    w->barrier();
+    memcpy(recv, tmp.data(), sizeof(double) * count * w->nranks);
+    w->barrier();
+    return 0;
+}
+
+}  // extern "C"

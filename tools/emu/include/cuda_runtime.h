@@ -28,7 +28,8 @@
 #define __host__
 #define __forceinline__ inline
 #define __launch_bounds__(...)
-#define __shared__ static
+// one copy per OS thread: the multi-rank tests run one rank per thread
+#define __shared__ static thread_local
 #define __constant__ const
 #define __align__(n) __attribute__((aligned(n)))
 
