@@ -2,6 +2,7 @@
 ``cdll.LoadLibrary(getSharedLibraryName('icqLaplaceMatricesCpp'))`` at
 bem/icqBaseLaplaceSolver.py:26-27, with explicit argtypes/restype)."""
 import ctypes
+import os
 from ctypes import (POINTER, byref, c_char_p, c_double, c_int, c_int64, c_uint64,
                     c_void_p)
 
@@ -60,6 +61,8 @@ SIGNATURES = [
     ('icqb_comm_init', c_int, [c_void_p, c_void_p, c_int, c_int]),
     ('icqb_comm_share', c_int, [c_void_p, c_void_p]),
     ('icqb_comm_rank', c_int, [c_void_p, POINTER(c_int), POINTER(c_int)]),
+    ('icqb_peer_create', c_int, [c_void_p, c_int64, c_void_p]),
+    ('icqb_peer_attach', c_int, [c_void_p, c_void_p]),
     ('icqb_last_ms', c_double, [c_void_p, c_int]),
     ('icqb_launch_count', c_int64, [c_void_p]),
     ('icqb_measure_fp64_peak', c_int, [c_void_p, c_double_p]),
@@ -141,6 +144,7 @@ class Context:
 
 
 _comm_owner = {}
+PEER_EXCHANGE_MAX_N = 262144   # vector length the experimental peer-exchange buffers are sized for
 
 
 def attachCommunicator(ctx, rank, nranks, broadcastBytes):
@@ -158,5 +162,14 @@ def attachCommunicator(ctx, rank, nranks, broadcastBytes):
         raw = broadcastBytes(uid.raw, 128, 0)
         owner.check(owner.lib.icqb_comm_init(owner.handle, ctypes.create_string_buffer(raw, 128),
                                              int(rank), int(nranks)))
+        if os.environ.get('ICQB_PEER_EXCHANGE') == '1':
+            # EXPERIMENTAL (include/icqb.h, icqb_peer_create): exchange buffers for the fused
+            # product collective of the experimental solver; the 64-byte IPC handles are
+            # gathered with one broadcast per rank
+            handle = ctypes.create_string_buffer(64)
+            owner.check(owner.lib.icqb_peer_create(owner.handle, PEER_EXCHANGE_MAX_N, handle))
+            gathered = b''.join(broadcastBytes(handle.raw, 64, r) for r in range(int(nranks)))
+            owner.check(owner.lib.icqb_peer_attach(
+                owner.handle, ctypes.create_string_buffer(gathered, 64 * int(nranks))))
         _comm_owner[ctx.device] = owner
     ctx.check(ctx.lib.icqb_comm_share(ctx.handle, owner.handle))

@@ -21,11 +21,54 @@
 //         k_cg_vec    x += alpha p, r -= alpha z            (all rows)
 //         k_gemv      w_cap = C^-1 r_cap                    (one launch per cap)
 //         k_cg_close  w = M^-1 r on the other tiles, rho, norms, beta, stopping flag.
+//
+// The same experimental solver carries the PEER EXCHANGE (several ranks, lower storage, when
+// icqb_peer_create/attach have been called): k_symv_reduce<PEER> stores the partial product
+// and its p.z into every rank's exchange buffer and raises a flag there; k_peer_gather waits
+// for the P flags of the product's sequence number and adds the P slots in rank order -- no
+// NCCL call inside the iteration.  Slots are double-buffered by the parity of the sequence
+// number; a rank can be at most one product ahead of a peer because it needs that peer's flag
+// of the previous product, and restarts of the iteration pass through an NCCL all-reduce.
 #include "cg_kernels.cuh"
 
 namespace icqb {
 
 namespace {
+
+// z = sum over ranks of the partial products in this rank's exchange buffer (rank order:
+// identical on every rank), p.z likewise; waits for every rank's flag first.
+__global__ void __launch_bounds__(kT) k_peer_gather(const SymvPeer X, long long n, double* z,
+                                                    double* pz, const int* skip) {
+    __shared__ int s_ready;
+    if (skip && *skip) return;
+    const volatile unsigned long long* flags =
+        reinterpret_cast<const volatile unsigned long long*>(X.flags[X.rank]) + X.parity * X.nranks;
+    if (threadIdx.x == 0) {
+        for (int h = 0; h < X.nranks; ++h)
+            while (flags[h] < X.seq) {
+#ifdef ICQB_EMU
+                emu::yield();
+#endif
+            }
+        __threadfence_system();
+        s_ready = 1;
+    }
+    __syncthreads();
+    const double* slots = X.slots[X.rank] + (long long)X.parity * X.nranks * X.slotStride;
+    const long long i = (long long)blockIdx.x * kT + threadIdx.x;
+    if (i < n) {
+        double acc = 0.0;
+        for (int h = 0; h < X.nranks; ++h)
+            acc += reinterpret_cast<const volatile double*>(slots + h * X.slotStride)[i];
+        z[i] = acc;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        double acc = 0.0;
+        for (int h = 0; h < X.nranks; ++h)
+            acc += reinterpret_cast<const volatile double*>(slots + h * X.slotStride)[n];
+        *pz = acc;
+    }
+}
 
 struct Cap {
     long long t0 = 0, tiles = 0;   // tile rows [t0, t0 + tiles)
@@ -348,7 +391,10 @@ int cg_solve_caps(icqb_ctx* ctx, uint64_t dA_, int64_t n, int64_t ld, int storag
 
     SymvFuse fuse;
     const bool fuseDir = (storage == 1);
-    B.pz = (fuseDir && P > 1) ? B.z + n : &B.state->pz;
+    // peer exchange instead of the NCCL all-reduce of the iteration's product
+    SymvPeer probe;
+    const bool usePeer = fuseDir && P > 1 && comm_peer_next(ctx, n, &probe);
+    B.pz = (fuseDir && P > 1 && !usePeer) ? B.z + n : &B.state->pz;
     if (fuseDir) {
         fuse.w = B.w;
         fuse.beta = &B.state->beta;
@@ -398,8 +444,24 @@ int cg_solve_caps(icqb_ctx* ctx, uint64_t dA_, int64_t n, int64_t ld, int storag
                 ctx->launches += 1;
             }
             if (i == 0) ICQB_CUDA(ctx, cudaEventRecord(evg0[slot], st));
-            int r2 = mv.apply(B.p, B.z, scale, st, skip, fuseDir ? &fuse : nullptr, fuseDir ? 1 : 0);
-            if (r2 != ICQB_OK) return r2;
+            int r2;
+            if (usePeer) {
+                SymvPeer X;
+                if (!comm_peer_next(ctx, n, &X)) return set_error(ctx, ICQB_ESTATE, "peer exchange lost");
+                // the reduce kernel leaves this rank's p.z in a scratch slot; the sum over the
+                // ranks is formed by the gather kernel
+                SymvFuse f2 = fuse;
+                f2.pz = B.z + n;
+                r2 = launch_symv(ctx, A, B.p, mv.area, scale ? mv.area : nullptr,
+                                 scale ? nullptr : mv.inv_area, B.z, st, skip, &f2, &X);
+                if (r2 != ICQB_OK) return r2;
+                ++mv.products;
+                k_peer_gather<<<vgrid, kT, 0, st>>>(X, n, B.z, &B.state->pz, skip);
+                ctx->launches += 1;
+            } else {
+                r2 = mv.apply(B.p, B.z, scale, st, skip, fuseDir ? &fuse : nullptr, fuseDir ? 1 : 0);
+                if (r2 != ICQB_OK) return r2;
+            }
             if (i == 0) ICQB_CUDA(ctx, cudaEventRecord(evg1[slot], st));
             if (!fuseDir) {
                 k_cg_dot<<<vgrid, kT, 0, st>>>(B);

@@ -88,7 +88,44 @@ struct Comm {
     ncclComm_t comm = nullptr;
     int rank = 0, nranks = 1;
     int refs = 1;   // contexts sharing this communicator (icqb_comm_share)
+    // experimental peer exchange (SymvPeer, icqb_internal.cuh)
+    void* xbuf = nullptr;               // this rank's exchange buffer
+    void* xpeer[kMaxPeers] = {};        // every rank's buffer as mapped here (own: xbuf)
+    long long slotStride = 0;
+    bool xattached = false;
+    unsigned long long seq = 0;
 };
+
+constexpr size_t kPeerHeaderBytes = 256;
+
+static size_t peer_bytes(long long max_n, int nranks) {
+    return kPeerHeaderBytes + sizeof(double) * 2 * (size_t)nranks * (size_t)(max_n + 8);
+}
+
+static void peer_destroy(Comm* c) {
+    for (int h = 0; h < c->nranks && h < kMaxPeers; ++h)
+        if (c->xpeer[h] && c->xpeer[h] != c->xbuf) cudaIpcCloseMemHandle(c->xpeer[h]);
+    if (c->xbuf) cudaFree(c->xbuf);
+    c->xbuf = nullptr;
+    c->xattached = false;
+    for (int h = 0; h < kMaxPeers; ++h) c->xpeer[h] = nullptr;
+}
+
+bool comm_peer_next(icqb_ctx* ctx, long long n, SymvPeer* out) {
+    Comm* c = ctx->comm;
+    if (!c || !c->xattached || n + 1 > c->slotStride) return false;
+    out->nranks = c->nranks;
+    out->rank = c->rank;
+    out->seq = ++c->seq;
+    out->parity = (int)(out->seq & 1);
+    out->slotStride = c->slotStride;
+    for (int h = 0; h < c->nranks; ++h) {
+        char* base = static_cast<char*>(c->xpeer[h]);
+        out->flags[h] = reinterpret_cast<unsigned long long*>(base);
+        out->slots[h] = reinterpret_cast<double*>(base + kPeerHeaderBytes);
+    }
+    return true;
+}
 
 int comm_nranks(const icqb_ctx* ctx) { return ctx->comm ? ctx->comm->nranks : 1; }
 int comm_rank(const icqb_ctx* ctx) { return ctx->comm ? ctx->comm->rank : 0; }
@@ -125,6 +162,7 @@ int comm_allreduce_sum(icqb_ctx* ctx, double* buf, int64_t count, cudaStream_t s
 void comm_destroy(icqb_ctx* ctx) {
     if (!ctx->comm) return;
     if (--ctx->comm->refs == 0) {
+        peer_destroy(ctx->comm);
         if (ctx->comm->comm) api().CommDestroy(ctx->comm->comm);
         delete ctx->comm;
     }
@@ -179,6 +217,43 @@ int icqb_comm_share(icqb_ctx* ctx, icqb_ctx* owner) {
         ctx->comm = owner->comm;
         ctx->comm->refs += 1;
     }
+    return ICQB_OK;
+}
+
+int icqb_peer_create(icqb_ctx* ctx, int64_t max_n, void* handle64) {
+    if (!ctx || !handle64 || max_n <= 0) return set_error(ctx, ICQB_EARG, "icqb_peer_create: bad arguments");
+    Comm* c = ctx->comm;
+    if (!c) return set_error(ctx, ICQB_ESTATE, "icqb_peer_create: no communicator (single rank)");
+    if (c->nranks > kMaxPeers) return set_error(ctx, ICQB_EARG, "icqb_peer_create: at most 16 ranks");
+    ICQB_CUDA(ctx, cudaSetDevice(ctx->device));
+    peer_destroy(c);
+    const size_t bytes = peer_bytes(max_n, c->nranks);
+    ICQB_CUDA(ctx, cudaMalloc(&c->xbuf, bytes));
+    ICQB_CUDA(ctx, cudaMemset(c->xbuf, 0, bytes));
+    c->slotStride = max_n + 8;
+    c->seq = 0;
+    cudaIpcMemHandle_t h;
+    ICQB_CUDA(ctx, cudaIpcGetMemHandle(&h, c->xbuf));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+    memcpy(handle64, &h, 64);
+    return ICQB_OK;
+}
+
+int icqb_peer_attach(icqb_ctx* ctx, const void* handles) {
+    if (!ctx || !handles) return set_error(ctx, ICQB_EARG, "icqb_peer_attach: bad arguments");
+    Comm* c = ctx->comm;
+    if (!c || !c->xbuf) return set_error(ctx, ICQB_ESTATE, "icqb_peer_attach: call icqb_peer_create first");
+    ICQB_CUDA(ctx, cudaSetDevice(ctx->device));
+    for (int h = 0; h < c->nranks; ++h) {
+        if (h == c->rank) {
+            c->xpeer[h] = c->xbuf;
+            continue;
+        }
+        cudaIpcMemHandle_t ih;
+        memcpy(&ih, static_cast<const char*>(handles) + 64 * h, 64);
+        ICQB_CUDA(ctx, cudaIpcOpenMemHandle(&c->xpeer[h], ih, cudaIpcMemLazyEnablePeerAccess));
+    }
+    c->xattached = true;
     return ICQB_OK;
 }
 

@@ -94,6 +94,21 @@ struct SymvFuse {
     unsigned int* ticket = nullptr;
 };
 
+// EXPERIMENTAL peer exchange of the CG product (several ranks, lower storage): instead of an
+// NCCL all-reduce, k_symv_reduce stores its partial product and its p.z straight into a slot
+// of EVERY rank's exchange buffer (peer memory over NVLink, CUDA IPC) and raises a flag there;
+// k_peer_gather on each rank waits for the P flags and adds the P slots in rank order.
+// Buffer of a rank: flags [2 parities][P] (256 bytes reserved), then slots
+// [2 parities][P][slotStride] doubles; slot (parity, g) is written by rank g only.
+constexpr int kMaxPeers = 16;
+struct SymvPeer {
+    int nranks = 0, rank = 0, parity = 0;
+    unsigned long long seq = 0;             // flags are raised to the product's sequence number
+    long long slotStride = 0;               // doubles per slot (>= n + 1)
+    double* slots[kMaxPeers] = {};          // per rank h: its slot array
+    unsigned long long* flags[kMaxPeers] = {};   // per rank h: its flag array
+};
+
 }  // namespace icqb
 
 struct icqb_ctx {
@@ -150,7 +165,8 @@ int launch_diag_rows(icqb_ctx* ctx, int order, long long g0, long long g1, doubl
                      int64_t stride);
 int launch_symv(icqb_ctx* ctx, const double* dA, const double* dx,
                 const double* dgamma, const double* dalpha, const double* dbeta, double* dz,
-                cudaStream_t stream, const int* skip = nullptr, const SymvFuse* fuse = nullptr);
+                cudaStream_t stream, const int* skip = nullptr, const SymvFuse* fuse = nullptr,
+                const SymvPeer* peer = nullptr);
 int launch_diag(icqb_ctx* ctx, int order, double* dOut, int64_t stride);
 int launch_gemv(icqb_ctx* ctx, const double* dA, int64_t nrows, int64_t ncols, int64_t ld,
                 const double* dx, double* dy, const double* drowscale, cudaStream_t stream,
@@ -169,6 +185,9 @@ int comm_allgather(icqb_ctx* ctx, const double* send, double* recv, int64_t coun
                    cudaStream_t stream);
 int comm_allreduce_sum(icqb_ctx* ctx, double* buf, int64_t count, cudaStream_t stream);
 void comm_destroy(icqb_ctx* ctx);
+// experimental peer exchange (comm.cu): fills `out` for a product over n entries and draws its
+// sequence number; false when no exchange is attached or n does not fit
+bool comm_peer_next(icqb_ctx* ctx, long long n, SymvPeer* out);
 void symv_plan_free(icqb_ctx* ctx);
 
 }  // namespace icqb

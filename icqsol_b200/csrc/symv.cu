@@ -80,6 +80,7 @@ struct SymvParams {
     double* z;                  // [n]
     const int* skip;            // when non-null and *skip != 0 the kernels return at once
     SymvFuse F;                 // CG fusion (all null: plain product)
+    SymvPeer X;                 // peer exchange (k_symv_reduce<true> only)
 };
 
 #ifdef ICQB_EMU   // CPU emulation build of the test suite (tools/emu): no PTX
@@ -322,6 +323,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_symv(const SymvParams P) {
 // sums (many independent loads in flight: the kernel is latency bound) and are combined in a
 // fixed order.  With SymvFuse the CTA also stores the new direction
 // p_j = w_j + beta p_j and leaves its share of p.z; the last CTA adds the shares.
+// PEER (experimental): the partial product and its p.z also go to slot (parity, rank) of
+// every rank's exchange buffer, and the last CTA raises this rank's flag on every rank.
+template <bool PEER>
 __global__ void __launch_bounds__(kRedThreads) k_symv_reduce(const SymvParams P) {
     __shared__ double s_row[kRedGroups][kT], s_col[kRedGroups][kT];
     __shared__ double s_dot[4];
@@ -369,6 +373,10 @@ __global__ void __launch_bounds__(kRedThreads) k_symv_reduce(const SymvParams P)
         if (P.beta) col *= P.beta[j];
         const double zj = row + col;
         P.z[j] = zj;
+        if (PEER) {
+            const long long slot = ((long long)P.X.parity * P.X.nranks + P.X.rank) * P.X.slotStride;
+            for (int h = 0; h < P.X.nranks; ++h) P.X.slots[h][slot + j] = zj;
+        }
         if (P.F.w) {
             const double pj = fma(*P.F.beta, P.F.p[j], P.F.w[j]);   // same arithmetic as vec_at
             P.F.p[j] = pj;
@@ -380,6 +388,7 @@ __global__ void __launch_bounds__(kRedThreads) k_symv_reduce(const SymvParams P)
         __syncthreads();
         if (tid == 0) {
             P.F.pz_part[T] = join4<false>(s_dot);
+            if (PEER) __threadfence_system();   // this CTA's peer stores before its ticket
             s_last = take_ticket(P.F.ticket, gridDim.x) ? 1 : 0;
         }
         __syncthreads();
@@ -391,6 +400,15 @@ __global__ void __launch_bounds__(kRedThreads) k_symv_reduce(const SymvParams P)
                 *P.F.pz = pz;
                 *P.F.ticket = 0;
                 __threadfence();
+            }
+            if (PEER && tid < P.X.nranks) {
+                // every CTA has published: hand p.z over and raise the flag on rank `tid`
+                const long long slot =
+                    ((long long)P.X.parity * P.X.nranks + P.X.rank) * P.X.slotStride;
+                P.X.slots[tid][slot + P.n] = pz;
+                __threadfence_system();
+                *reinterpret_cast<volatile unsigned long long*>(
+                    P.X.flags[tid] + P.X.parity * P.X.nranks + P.X.rank) = P.X.seq;
             }
         }
     }
@@ -500,7 +518,7 @@ static int symv_plan(icqb_ctx* ctx) {
 
 int launch_symv(icqb_ctx* ctx, const double* dA, const double* dx, const double* dgamma,
                 const double* dalpha, const double* dbeta, double* dz, cudaStream_t stream,
-                const int* skip, const SymvFuse* fuse) {
+                const int* skip, const SymvFuse* fuse, const SymvPeer* peer) {
     if (ctx->ntri == 0) return ICQB_OK;
     if ((reinterpret_cast<uintptr_t>(dA) & 15) != 0)
         return set_error(ctx, ICQB_EARG, "symv: matrix must be 16-byte aligned");
@@ -527,11 +545,19 @@ int launch_symv(icqb_ctx* ctx, const double* dA, const double* dx, const double*
     P.z = dz;
     P.skip = skip;
     if (fuse) P.F = *fuse;
+    if (peer) {
+        if (!fuse || !fuse->pz_part)
+            return set_error(ctx, ICQB_EARG, "symv: the peer exchange needs the fused p.z");
+        P.X = *peer;
+    }
     if (p->nTasks > 0) {
         k_symv<<<p->grid, kThreads, kSmemBytes, stream>>>(P);
         ctx->launches += 1;
     }
-    k_symv_reduce<<<(unsigned)((p->n + kT - 1) / kT), dim3(kT, kRedGroups), 0, stream>>>(P);
+    if (peer)
+        k_symv_reduce<true><<<(unsigned)((p->n + kT - 1) / kT), dim3(kT, kRedGroups), 0, stream>>>(P);
+    else
+        k_symv_reduce<false><<<(unsigned)((p->n + kT - 1) / kT), dim3(kT, kRedGroups), 0, stream>>>(P);
     ctx->launches += 1;
     return check_cuda(ctx, cudaGetLastError(), "k_symv launch");
 }

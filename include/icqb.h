@@ -208,6 +208,15 @@ int icqb_comm_init(icqb_ctx* ctx, const void* unique_id_128, int rank, int nrank
  * (communicator creation costs ~1 s; solvers are created many times). */
 int icqb_comm_share(icqb_ctx* ctx, icqb_ctx* owner);
 int icqb_comm_rank(const icqb_ctx* ctx, int* rank, int* nranks);
+/* EXPERIMENTAL (written without GPU access; checked in the CPU emulation of the test suite
+ * with one rank per thread): peer exchange for the CG product of the lower storage.  Each rank
+ * allocates an exchange buffer for vectors of up to max_n entries (icqb_peer_create returns
+ * its 64-byte cudaIpcMemHandle_t), the caller all-gathers the handles and passes the
+ * nranks*64 bytes to icqb_peer_attach on every rank.  The experimental solver (preconditioner
+ * kind 2) then replaces the per-iteration NCCL all-reduce by stores into the peers' buffers
+ * from k_symv_reduce and a gather kernel (csrc/cg_caps.cu). */
+int icqb_peer_create(icqb_ctx* ctx, int64_t max_n, void* handle64);
+int icqb_peer_attach(icqb_ctx* ctx, const void* handles);
 
 /* ---- instrumentation ----------------------------------------------------------------
  * Milliseconds (CUDA events on the context stream) of the last call of each phase:

@@ -24,13 +24,22 @@ def main():
     from icqsol_b200.bem.icqLaplaceSolver import LaplaceSolver
     from icqsol_b200.bem.icqPoissonSolver import PoissonSolver
 
-    for nt, npz, storage in ((40, 20, 'full'), (40, 20, 'lower'), (64, 30, 'lower'), (64, 30, 'full'),
-                             (7, 4, 'full'), (7, 4, 'lower')):
+    # ICQB_EXPERIMENTAL=1 runs every case with the experimental solver as well (dense cap blocks;
+    # with ICQB_PEER_EXCHANGE=1 also the peer exchange instead of the NCCL all-reduce)
+    kinds = ['block'] + (['block+caps'] if os.environ.get('ICQB_EXPERIMENTAL') == '1' else [])
+    cases = [(nt, npz, storage, kind)
+             for (nt, npz, storage) in ((40, 20, 'full'), (40, 20, 'lower'), (64, 30, 'lower'),
+                                        (64, 30, 'full'), (7, 4, 'full'), (7, 4, 'lower'))
+             for kind in kinds]
+    for nt, npz, storage, kind in cases:
         xyz, tri = uvSphere(1.0, nt, npz)
         n = tri.shape[0]
         print('rank', rank, 'case', nt, npz, storage, flush=True)
         solver = LaplaceSolver(PolyData.from_arrays(xyz, tri), float('inf'), 5, computeK=True,
-                               storage=storage)
+                               storage=storage, preconditioner=kind)
+        if kind == 'block+caps' and n > 512:
+            # no slivers on these meshes: force caps so that the cap machinery runs
+            solver.ctx.check(solver.lib.icqb_cg_set_cap_tiles(solver.ctx.handle, 2, 1))
         assert solver.numRanks == world
         if storage == 'full':
             r0, r1 = solver.getRowRange()
@@ -63,8 +72,8 @@ def main():
         pref = gref.dot(cen[:, 0] + 1.0)
         assert numpy.abs(prsp - pref).max() / numpy.abs(pref).max() < 1e-12
         if rank == 0:
-            print('N={0} ranks={1} {4}: CG iters {2}, backward {3:.2e}'.format(
-                n, world, info['iterations'], backward, storage))
+            print('N={0} ranks={1} {4} {5}: CG iters {2}, backward {3:.2e}'.format(
+                n, world, info['iterations'], backward, storage, kind))
         del solver, psolver
     dist.barrier()
     dist.destroy_process_group()

@@ -262,20 +262,30 @@ def test_emulated_subdivide(emu, golden, k, f32):
     c.close()
 
 
-def _run_ranks(emu, nranks, n_theta, n_phi, storage, kind, caps=None):
+def _run_ranks(emu, nranks, n_theta, n_phi, storage, kind, caps=None, peer=False):
     """One rank per thread (ctypes releases the GIL), the in-process NCCL stand-in of
-    tools/emu underneath: folded row blocks, sharded assembly, distributed CG."""
+    tools/emu underneath: folded row blocks, sharded assembly, distributed CG.  peer=True
+    also sets up the experimental peer exchange (handles swapped through a shared list)."""
     import threading
     from icqsol_b200.bem import icqRowPartition as rp
     uid = ctypes.create_string_buffer(128)
     assert emu.icqb_comm_unique_id(uid) == 0
     out, errors = [None] * nranks, []
+    handles = [None] * nranks
+    meet = threading.Barrier(nranks, timeout=120)
 
     def work(rank):
         try:
             c = Ctx(emu, n_theta, n_phi, sms=2)
             c.check(emu.icqb_comm_init(c.h, uid, rank, nranks))
             n = c.n
+            if peer:
+                h = ctypes.create_string_buffer(64)
+                c.check(emu.icqb_peer_create(c.h, 1024, h))
+                handles[rank] = h.raw
+                meet.wait()
+                c.check(emu.icqb_peer_attach(c.h, ctypes.create_string_buffer(b''.join(handles), 64 * nranks)))
+                meet.wait()
             if storage == 1:
                 (g,) = c.assemble_lower(rp.foldedBlocks(n, rank, nranks))
                 ld = 0
@@ -298,14 +308,16 @@ def _run_ranks(emu, nranks, n_theta, n_phi, storage, kind, caps=None):
     return out
 
 
-@pytest.mark.parametrize('nranks,storage,kind,caps', [(2, 1, 1, None), (3, 1, 0, None), (2, 0, 1, None),
-                                                      (2, 1, 2, (1, 2))])
-def test_emulated_multi_rank_cg(emu, oracle_mod, nranks, storage, kind, caps):
+@pytest.mark.parametrize('nranks,storage,kind,caps,peer', [
+    (2, 1, 1, None, False), (3, 1, 0, None, False), (2, 0, 1, None, False), (2, 1, 2, (1, 2), False),
+    (3, 1, 2, None, True)])
+def test_emulated_multi_rank_cg(emu, oracle_mod, nranks, storage, kind, caps, peer):
     """Sharded assembly and the distributed CG (all-reduce of the partial products with p.z in
     the slot behind them, all-reduce of the preconditioner blocks / cap blocks, all-gather for
     row blocks): every rank returns the same solution, it solves the oracle's system, and
-    the iteration count is the single-rank one."""
-    out = _run_ranks(emu, nranks, 20, 11, storage, kind, caps)     # 400 triangles, 4 tile rows
+    the iteration count is the single-rank one.  The last case runs the EXPERIMENTAL peer
+    exchange (stores into the peers' buffers + flags instead of the all-reduce)."""
+    out = _run_ranks(emu, nranks, 20, 11, storage, kind, caps, peer)     # 400 triangles, 4 tile rows
     c = out[0][-1]
     ref = oracle_mod.green_matrix(c.xyz, c.tri, 5)
     a2 = oracle_mod.area2(c.xyz, c.tri)
@@ -314,7 +326,7 @@ def test_emulated_multi_rank_cg(emu, oracle_mod, nranks, storage, kind, caps):
         assert (x == x0).all() and iters == iters0
         assert rinf <= 5e-13 * numpy.abs(b).max()
     assert numpy.abs(b - ref.dot(x0)).max() <= 1e-12 * numpy.abs(b).max()
-    cuts = {0: list(range(c.n)), 1: [0, 128, 256, 384], 2: [0, 128, 384]}[kind]
+    cuts = {0: list(range(c.n)), 1: [0, 128, 256, 384], 2: [0, 128, 256, 384]}[kind]
     if caps == (1, 2):
         cuts = [0, 128, 256]      # head cap = tile 0, tiles 1 plain, tail cap = tiles 2..3
     assert abs(iters0 - model_iterations(ref, a2, b, cuts)) <= 1

@@ -228,6 +228,10 @@ cudaError_t cudaMemsetAsync(void* p, int value, size_t bytes, cudaStream_t) {
     memset(p, value, bytes);
     return cudaSuccess;
 }
+cudaError_t cudaMemset(void* p, int value, size_t bytes) {
+    memset(p, value, bytes);
+    return cudaSuccess;
+}
 cudaError_t cudaStreamCreate(cudaStream_t* s) { *s = new emuStream(); return cudaSuccess; }
 cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { return cudaStreamCreate(s); }
 cudaError_t cudaStreamDestroy(cudaStream_t s) { delete s; return cudaSuccess; }

@@ -180,6 +180,22 @@ cudaError_t cudaEventDestroy(cudaEvent_t e);
 cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t = nullptr);
 cudaError_t cudaEventSynchronize(cudaEvent_t e);
 cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b);
+// "IPC": the ranks of the emulation are threads of one process, a handle is the pointer itself
+struct cudaIpcMemHandle_t {
+    char reserved[64];
+};
+enum { cudaIpcMemLazyEnablePeerAccess = 1 };
+static inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p) {
+    memset(h, 0, sizeof(*h));
+    memcpy(h, &p, sizeof(p));
+    return cudaSuccess;
+}
+static inline cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned) {
+    memcpy(p, &h, sizeof(*p));
+    return cudaSuccess;
+}
+static inline cudaError_t cudaIpcCloseMemHandle(void*) { return cudaSuccess; }
+cudaError_t cudaMemset(void* p, int value, size_t bytes);
 template <class F>
 static inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) {
     return cudaSuccess;
