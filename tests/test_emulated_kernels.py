@@ -332,3 +332,30 @@ def test_emulated_multi_rank_cg(emu, oracle_mod, nranks, storage, kind, caps, pe
     assert abs(iters0 - model_iterations(ref, a2, b, cuts)) <= 1
     for o in out:
         o[-1].close()
+
+
+def test_emulated_quadrature_handle_api(emu, golden):
+    """The quadrature handle API (bem/icqQuadrature.h:19-40) of csrc/compat_quadrature.cu on a
+    sample of the reference's own known answers (tests/golden/known_answers.npz)."""
+    kat = golden['known_answers']
+    h = ctypes.c_void_p()
+    emu.icqQuadratureInit(ctypes.byref(h))
+    assert h.value
+    assert emu.icqQuadratureGetMaxOrder(ctypes.byref(h)) == 8
+    tris, obs = kat['corner_tris'], kat['single_obs']
+    for i in range(0, tris.shape[0], 8):
+        emu.icqQuadratureSetObserver(ctypes.byref(h), dp(numpy.ascontiguousarray(obs[i])))
+        t = numpy.ascontiguousarray(tris[i])
+        for order in range(10):
+            v = emu.icqQuadratureEvaluate(ctypes.byref(h), order, dp(t[0]), dp(t[1]), dp(t[2]))
+            ref = kat['single_vals'][i, order]
+            assert abs(v - ref) <= 1e-13 * abs(ref)
+    pairs = kat['double_pairs']
+    for i in range(0, pairs.shape[0], 8):
+        a, b = numpy.ascontiguousarray(pairs[i, 0]), numpy.ascontiguousarray(pairs[i, 1])
+        for order in (0, 1, 5, 8, 9):
+            v = emu.icqQuadratureEvaluateDouble(ctypes.byref(h), order, dp(a[0]), dp(a[1]), dp(a[2]),
+                                                dp(b[0]), dp(b[1]), dp(b[2]))
+            ref = kat['double_vals'][i, order]
+            assert abs(v - ref) <= 1e-13 * abs(ref)
+    emu.icqQuadratureDel(ctypes.byref(h))
