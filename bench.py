@@ -514,13 +514,17 @@ def main():
     ap.add_argument('--storage', default='lower', choices=['lower', 'full'],
                     help="'lower': each pair entry stored once (mirror rule), symmetric product; "
                          "'full': complete row blocks, row-major GEMV")
-    ap.add_argument('--preconditioner', default='block', choices=['block', 'diagonal', 'block+caps'],
+    ap.add_argument('--preconditioner', default='auto', choices=['auto', 'block', 'diagonal', 'block+caps'],
                     help="CG preconditioner: inverse 128x128 diagonal blocks, 1/diag, or (experimental) "
-                         "blocks with dense caps over the sliver tiles")
+                         "blocks with dense caps over the sliver tiles; auto = block, except for the "
+                         "c3/c5 workloads whose pole slivers make the matrix indefinite (DESIGN.md 4.6): "
+                         "block+caps there")
     ap.add_argument('--max-iters', type=int, default=4000,
                     help='CG iteration cap (a solve that needs more is reported as not converged)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
+    if args.preconditioner == 'auto':
+        args.preconditioner = 'block+caps' if args.workload in ('c3', 'c5') else 'block'
     if args.impl == 'reference':
         run_reference(args)
     else:
