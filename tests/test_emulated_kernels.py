@@ -359,3 +359,18 @@ def test_emulated_quadrature_handle_api(emu, golden):
             ref = kat['double_vals'][i, order]
             assert abs(v - ref) <= 1e-13 * abs(ref)
     emu.icqQuadratureDel(ctypes.byref(h))
+
+
+def test_emulated_ranks_without_rows(emu, oracle_mod):
+    """Four ranks, 144 triangles: the folded blocks leave ranks 2 and 3 without a single row
+    (no tiles, no product kernel, null task tables) -- they still take part in every
+    collective and return the same solution."""
+    out = _run_ranks(emu, 4, 12, 7, 1, 1)
+    c = out[0][-1]
+    ref = oracle_mod.green_matrix(c.xyz, c.tri, 5)
+    x0, iters0, _, b, _ = out[0]
+    for x, iters, rinf, _, _ in out:
+        assert (x == x0).all() and iters == iters0
+    assert numpy.abs(b - ref.dot(x0)).max() <= 1e-12 * numpy.abs(b).max()
+    for o in out:
+        o[-1].close()
