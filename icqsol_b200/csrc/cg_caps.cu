@@ -44,16 +44,31 @@ __global__ void __launch_bounds__(kT) k_peer_gather(const SymvPeer X, long long 
     const volatile unsigned long long* flags =
         reinterpret_cast<const volatile unsigned long long*>(X.flags[X.rank]) + X.parity * X.nranks;
     if (threadIdx.x == 0) {
-        for (int h = 0; h < X.nranks; ++h)
-            while (flags[h] < X.seq) {
+        int ready = 1;
 #ifdef ICQB_EMU
-                emu::yield();
+        for (int h = 0; h < X.nranks; ++h)
+            while (flags[h] < X.seq) emu::yield();
+#else
+        // bounded wait (~20 s): a peer that died must not hang this GPU -- the product then
+        // comes back as NaN and the solve stops with a breakdown
+        const long long t0 = clock64();
+        for (int h = 0; h < X.nranks && ready; ++h)
+            while (flags[h] < X.seq)
+                if (clock64() - t0 > 40000000000LL) {
+                    ready = 0;
+                    break;
+                }
 #endif
-            }
         __threadfence_system();
-        s_ready = 1;
+        s_ready = ready;
     }
     __syncthreads();
+    if (!s_ready) {
+        const long long i0 = (long long)blockIdx.x * kT + threadIdx.x;
+        if (i0 < n) z[i0] = nan("");
+        if (blockIdx.x == 0 && threadIdx.x == 0) *pz = nan("");
+        return;
+    }
     const double* slots = X.slots[X.rank] + (long long)X.parity * X.nranks * X.slotStride;
     const long long i = (long long)blockIdx.x * kT + threadIdx.x;
     if (i < n) {
