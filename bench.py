@@ -291,6 +291,11 @@ def run_b200(args):
     if args.preconditioner == 'block+caps':    # experimental, see icqsol_b200/csrc/cg_caps.cu
         cap_tiles = rowPartition.sliverCapTiles(xyz, tri)
         ctx.check(lib.icqb_cg_set_cap_tiles(ctx.handle, *cap_tiles))
+        if args.block_tiles > 1:
+            starts = numpy.ascontiguousarray(
+                rowPartition.blockPartition(n, args.block_tiles, *cap_tiles), numpy.int64)
+            ctx.check(lib.icqb_cg_set_block_partition(ctx.handle, starts.ctypes.data_as(_lib.c_int64_p),
+                                                      len(starts)))
     ctx.check(lib.icqb_set_mesh(ctx.handle, xyz.ctypes.data_as(_lib.c_double_p), xyz.shape[0],
                                 tri.ctypes.data_as(_lib.c_int64_p), n))
     lower = args.storage == 'lower'
@@ -405,7 +410,8 @@ def run_b200(args):
         barrier()
         t0 = time.perf_counter()
         solver = LaplaceSolver(pd, float('inf'), 5, computeK=True, device=local,
-                               storage=args.storage, preconditioner=args.preconditioner)
+                               storage=args.storage, preconditioner=args.preconditioner,
+                               blockTiles=args.block_tiles)
         solver.setSolverMaxNumberOfIterations(args.max_iters)
         rsp = solver.computeResponseField()
         torch.cuda.synchronize(dev)
@@ -439,7 +445,7 @@ def run_b200(args):
             'config': {'workload': label, 'triangles': n, 'diag_order': 5, 'offdiag_order': 8,
                        'step': 'fused G+K assembly + CG solve (max|v+G sigma| <= 5e-13 max|v|)',
                        'rows_per_gpu': rows, 'storage': args.storage,
-                       'preconditioner': args.preconditioner, 'cap_tiles': list(cap_tiles),
+                       'preconditioner': args.preconditioner, 'cap_tiles': list(cap_tiles), 'block_tiles': args.block_tiles,
                        'parallelism': ('folded row blocks, lower storage x{0}' if lower
                                        else 'row-block x{0}').format(world),
                        'l2': 'inputs larger than L2 ({0:.2f} GB of G streamed per product per GPU)'.format(
@@ -519,6 +525,8 @@ def main():
                          "blocks with dense caps over the sliver tiles; auto = block, except for the "
                          "c3/c5 workloads whose pole slivers make the matrix indefinite (DESIGN.md 4.6): "
                          "block+caps there")
+    ap.add_argument('--block-tiles', type=int, default=1,
+                    help='experimental, with block+caps: 128-triangle tiles per diagonal block')
     ap.add_argument('--max-iters', type=int, default=4000,
                     help='CG iteration cap (a solve that needs more is reported as not converged)')
     ap.add_argument('--no-cpu-baseline', action='store_true')

@@ -56,6 +56,7 @@ SIGNATURES = [
                                   c_double_p, c_double_p]),
     ('icqb_cg_set_preconditioner', c_int, [c_void_p, c_int]),
     ('icqb_cg_set_cap_tiles', c_int, [c_void_p, c_int64, c_int64]),
+    ('icqb_cg_set_block_partition', c_int, [c_void_p, c_int64_p, c_int64]),
     ('icqb_cg_last_stats', c_int, [c_void_p, c_int64_p, c_int64_p]),
     ('icqb_comm_unique_id', c_int, [c_void_p]),
     ('icqb_comm_init', c_int, [c_void_p, c_void_p, c_int, c_int]),

@@ -44,7 +44,7 @@ def leadingDimension(n):
 class BaseLaplaceSolver(BaseSolver):
 
     def __init__(self, pdata, max_edge_length, order=5, computeK=False, device=None,
-                 storage='lower', preconditioner='block'):
+                 storage='lower', preconditioner='block', blockTiles=1):
         """
         Constructor
         @param pdata polydata (vtkPolyData or stand-in)
@@ -61,6 +61,9 @@ class BaseLaplaceSolver(BaseSolver):
                        solvers/icqConjugateGradient.py:19), 'block+caps' = EXPERIMENTAL: blocks,
                        with one dense block over the leading and one over the trailing run of
                        tiles that hold sliver triangles (icqRowPartition.sliverCapTiles)
+        @param blockTiles EXPERIMENTAL, with 'block+caps' only: tiles (of 128 triangles) per
+                       diagonal block between the caps (numpy model at config C2: 167 iterations
+                       with 1, 121 with 2, 92 with 8)
         """
         BaseSolver.__init__(self, pdata, max_edge_length, order)
         if storage not in ('lower', 'full'):
@@ -91,6 +94,11 @@ class BaseLaplaceSolver(BaseSolver):
         if preconditioner == 'block+caps':
             self.capTiles = rowPartition.sliverCapTiles(self._xyz, self._tri)
             self.ctx.check(self.lib.icqb_cg_set_cap_tiles(self.ctx.handle, *self.capTiles))
+            if int(blockTiles) > 1:
+                starts = numpy.ascontiguousarray(rowPartition.blockPartition(
+                    self.numTriangles, int(blockTiles), *self.capTiles), numpy.int64)
+                self.ctx.check(self.lib.icqb_cg_set_block_partition(
+                    self.ctx.handle, starts.ctypes.data_as(_lib.c_int64_p), len(starts)))
 
         self.rank, self.numRanks = rowPartition.worldInfo()
         # one NCCL communicator per process, shared by every solver

@@ -114,6 +114,24 @@ def sliverCapTiles(xyz, tri, threshold=30., maxTiles=32):
     return head, tail
 
 
+def blockPartition(n, blockTiles, headTiles=0, tailTiles=0):
+    """First tile row of every diagonal block of the experimental preconditioner: a cap of
+    headTiles, blocks of blockTiles, a cap of tailTiles (icqb_cg_set_block_partition)."""
+    nT = (int(n) + TILE - 1) // TILE
+    head = min(max(int(headTiles), 0), nT)
+    tail = min(max(int(tailTiles), 0), nT - head)
+    k = max(int(blockTiles), 1)
+    starts = [0] if head > 0 or nT - tail > 0 else []
+    t = head
+    while t < nT - tail:
+        if t > 0:
+            starts.append(t)
+        t += k
+    if tail > 0 and nT - tail > 0:
+        starts.append(nT - tail)
+    return starts or [0]
+
+
 def foldedBlockSize(n, nranks):
     n, nranks = int(n), int(nranks)
     return max(TILE, (n + 2 * nranks * TILE - 1) // (2 * nranks * TILE) * TILE)

@@ -51,6 +51,17 @@ extern "C" int icqb_cg_set_cap_tiles(icqb_ctx* ctx, int64_t head_tiles, int64_t 
     return ICQB_OK;
 }
 
+extern "C" int icqb_cg_set_block_partition(icqb_ctx* ctx, const int64_t* starts, int64_t nblocks) {
+    if (!ctx) return ICQB_EARG;
+    if (nblocks < 0 || (nblocks > 0 && (!starts || starts[0] != 0)))
+        return set_error(ctx, ICQB_EARG, "icqb_cg_set_block_partition: starts[0] must be 0");
+    for (int64_t q = 1; q < nblocks; ++q)
+        if (starts[q] <= starts[q - 1])
+            return set_error(ctx, ICQB_EARG, "icqb_cg_set_block_partition: starts must increase");
+    ctx->block_starts.assign(starts, starts + nblocks);
+    return ICQB_OK;
+}
+
 extern "C" int icqb_cg_last_stats(const icqb_ctx* ctx, int64_t* replacements, int64_t* products) {
     if (!ctx) return ICQB_EARG;
     if (replacements) *replacements = ctx->cg_replacements;

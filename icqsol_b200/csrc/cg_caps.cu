@@ -85,24 +85,30 @@ __global__ void __launch_bounds__(kT) k_peer_gather(const SymvPeer X, long long 
     }
 }
 
-struct Cap {
-    long long t0 = 0, tiles = 0;   // tile rows [t0, t0 + tiles)
-    long long m = 0;               // 128 * tiles: order of the dense block
-    long long valid = 0;           // rows of the block below n
-    double* inv = nullptr;         // [m][m] row-major
+// One dense diagonal block of the preconditioner: tile rows [t0, t0 + tiles), tiles > 1.
+struct DenseDesc {
+    long long t0, tiles;
+    long long m;       // 128 * tiles: order of the block
+    long long valid;   // rows of the block below n
+    long long off;     // offset (doubles) of its m x m matrix in the dense buffer
+    long long row0;    // first compact row (valid rows of all dense blocks, concatenated)
 };
 
-// dense block of diag(scale) A over tile rows [t0, t0 + m/128) from the lower storage:
-// tiles J <= I are copied (rows this rank stores), tiles J < I also mirrored -- diag(s) A is
-// symmetric.  The buffer is zeroed before; identity beyond n.
-__global__ void __launch_bounds__(256) k_cap_extract_lower(const double* A, LowerLayout L,
-                                                           const double* scale, long long n,
-                                                           long long t0, long long m, double* out) {
-    const long long I = t0 + blockIdx.y, J = t0 + blockIdx.x;
+// dense block of diag(scale) A from the lower storage: tiles J <= I are copied (rows this rank
+// stores), tiles J < I also mirrored -- diag(s) A is symmetric.  The buffer is zeroed before;
+// identity beyond n.  Grid (kmax, kmax, blocks).
+__global__ void __launch_bounds__(256) k_dense_extract_lower(const double* A, LowerLayout L,
+                                                             const double* scale, long long n,
+                                                             const DenseDesc* desc, double* dense) {
+    const DenseDesc D = desc[blockIdx.z];
+    if (blockIdx.x >= D.tiles || blockIdx.y >= D.tiles) return;
+    const long long I = D.t0 + blockIdx.y, J = D.t0 + blockIdx.x;
     if (J > I) return;
     const int lt = L.stripOf(I * kT);
     if (lt < 0) return;
     const double* a = A + (L.tileBase(lt) + J) * kLowerTileElems;
+    double* out = dense + D.off;
+    const long long m = D.m;
     for (int e = threadIdx.x; e < kT * kT; e += blockDim.x) {
         const int r = e >> 7, c = e & (kT - 1);
         const long long i = I * kT + r, j = J * kT + c;
@@ -111,19 +117,22 @@ __global__ void __launch_bounds__(256) k_cap_extract_lower(const double* A, Lowe
             v = (scale ? scale[i] : 1.0) * a[e];
         else
             v = (I == J && r == c) ? 1.0 : 0.0;
-        const long long lr = (I - t0) * kT + r, lc = (J - t0) * kT + c;
+        const long long lr = (I - D.t0) * kT + r, lc = (J - D.t0) * kT + c;
         out[lr * m + lc] = v;
         if (J < I) out[lc * m + lr] = v;
     }
 }
 
 // the same block from row-block storage (every tile of the block, rows this rank holds)
-__global__ void __launch_bounds__(256) k_cap_extract_full(const double* A, long long ld,
-                                                          long long r0, long long r1,
-                                                          const double* scale, long long n,
-                                                          long long t0, long long m, double* out) {
-    const long long I = t0 + blockIdx.y, J = t0 + blockIdx.x;
+__global__ void __launch_bounds__(256) k_dense_extract_full(const double* A, long long ld,
+                                                            long long r0, long long r1,
+                                                            const double* scale, long long n,
+                                                            const DenseDesc* desc, double* dense) {
+    const DenseDesc D = desc[blockIdx.z];
+    if (blockIdx.x >= D.tiles || blockIdx.y >= D.tiles) return;
+    const long long I = D.t0 + blockIdx.y, J = D.t0 + blockIdx.x;
     const bool ownsLast = (n - 1 >= r0 && n - 1 < r1);
+    double* out = dense + D.off;
     for (int e = threadIdx.x; e < kT * kT; e += blockDim.x) {
         const int r = e >> 7, c = e & (kT - 1);
         const long long i = I * kT + r, j = J * kT + c;
@@ -133,43 +142,149 @@ __global__ void __launch_bounds__(256) k_cap_extract_full(const double* A, long 
         } else if (ownsLast) {
             v = (I == J && r == c) ? 1.0 : 0.0;
         }
-        out[((I - t0) * kT + r) * m + (J - t0) * kT + c] = v;
+        out[((I - D.t0) * kT + r) * D.m + (J - D.t0) * kT + c] = v;
     }
 }
 
-// Gauss-Jordan without pivoting, pivot k, in global memory: first the pivot row and column
-// are saved (no writes), then every entry is updated from them.
-__global__ void __launch_bounds__(256) k_gj_pivot(const double* a, long long m, long long k,
-                                                  double* colk, double* rowk) {
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= m) return;
-    const double pivinv = 1.0 / a[k * m + k];
-    colk[t] = a[t * m + k];
-    rowk[t] = (t == k) ? pivinv : a[k * m + t] * pivinv;
+// In-place BLOCK Gauss-Jordan of every dense block, 128 x 128 tiles, no pivoting.  Step K:
+//   (a) k_tile_invert   P = A_KK^-1                       (in shared memory, as k_cg_invert_blocks)
+//   (b) k_tile_gemm<0>  A_KJ <- P A_KJ            (J != K)
+//   (c) k_tile_gemm<1>  A_IJ <- A_IJ - A_IK A_KJ  (I, J != K; old column, new row)
+//   (d) k_tile_gemm<2>  A_IK <- -A_IK P           (I != K)
+// Matrix traffic m^2 per step instead of per pivot.
+__global__ void __launch_bounds__(kInvThreads) k_tile_invert(const DenseDesc* desc, double* dense,
+                                                             long long K) {
+    extern __shared__ double s_inv[];
+    const DenseDesc D = desc[blockIdx.z];
+    if (K >= D.tiles) return;
+    double* a = s_inv;                    // [128][129]
+    double* colk = a + kT * kInvLd;
+    double* rowk = colk + kT;
+    const long long m = D.m;
+    double* g = dense + D.off + (K * kT) * m + K * kT;
+    const int tid = threadIdx.x;
+    for (int e = tid; e < kT * kT; e += kInvThreads)
+        a[(e >> 7) * kInvLd + (e & (kT - 1))] = g[(long long)(e >> 7) * m + (e & (kT - 1))];
+    __syncthreads();
+    for (int k = 0; k < kT; ++k) {
+        const double pivinv = 1.0 / a[k * kInvLd + k];
+        if (tid < kT) {
+            colk[tid] = a[tid * kInvLd + k];
+            rowk[tid] = (tid == k) ? pivinv : a[k * kInvLd + tid] * pivinv;
+        }
+        __syncthreads();
+        for (int e = tid; e < kT * kT; e += kInvThreads) {
+            const int i = e >> 7, j = e & (kT - 1);
+            double v = a[i * kInvLd + j];
+            if (i == k)
+                v = rowk[j];
+            else if (j == k)
+                v = -colk[i] * pivinv;
+            else
+                v = fma(-colk[i], rowk[j], v);
+            a[i * kInvLd + j] = v;
+        }
+        __syncthreads();
+    }
+    for (int e = tid; e < kT * kT; e += kInvThreads)
+        g[(long long)(e >> 7) * m + (e & (kT - 1))] = a[(e >> 7) * kInvLd + (e & (kT - 1))];
 }
 
-__global__ void __launch_bounds__(kT) k_gj_update(double* a, long long m, long long k,
-                                                  const double* colk, const double* rowk) {
-    const long long i = blockIdx.y;
-    const long long j = (long long)blockIdx.x * kT + threadIdx.x;
-    const double pivinv = rowk[k];
-    double v = a[i * m + j];
-    if (i == k)
-        v = rowk[j];
-    else if (j == k)
-        v = -colk[i] * pivinv;
-    else
-        v = fma(-colk[i], rowk[j], v);
-    a[i * m + j] = v;
+// 128 x 128 x 128 tile product on tiles of a dense block (row pitch m), 256 threads, 8 x 8
+// outputs per thread, operands staged through shared memory in slabs of 16.
+// MODE 0: C_KJ = A_KK B_KJ (grid x = J);  1: C_IJ -= A_IK B_KJ (grid y = I, x = J);
+// MODE 2: C_IK = -A_IK B_KK (grid y = I).  C may alias an operand: it is written after the
+// last read.
+template <int MODE>
+__global__ void __launch_bounds__(256) k_tile_gemm(const DenseDesc* desc, double* dense, long long K) {
+    __shared__ double As[kT][17];
+    __shared__ double Bs[16][kT];
+    const DenseDesc D = desc[blockIdx.z];
+    if (K >= D.tiles) return;
+    long long I, J;
+    if (MODE == 0) { I = K; J = blockIdx.x; }
+    else if (MODE == 1) { I = blockIdx.y; J = blockIdx.x; }
+    else { I = blockIdx.y; J = K; }
+    if (I >= D.tiles || J >= D.tiles) return;
+    if (MODE == 0 && J == K) return;
+    if (MODE == 1 && (I == K || J == K)) return;
+    if (MODE == 2 && I == K) return;
+    const long long m = D.m;
+    double* base = dense + D.off;
+    const double* Ap = base + (I * kT) * m + K * kT;     // A_IK  (MODE 0: A_KK)
+    const double* Bp = base + (K * kT) * m + J * kT;     // B_KJ  (MODE 2: B_KK)
+    double* Cp = base + (I * kT) * m + J * kT;
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    double acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.0;
+    for (int k0 = 0; k0 < kT; k0 += 16) {
+        // A slab: 128 rows x 16 columns; B slab: 16 rows x 128 columns (2048 entries each)
+        for (int e = tid; e < kT * 16; e += 256) {
+            const int r = e >> 4, c = e & 15;
+            As[r][c] = Ap[(long long)r * m + k0 + c];
+            const int br = e >> 7, bc = e & (kT - 1);
+            Bs[br][bc] = Bp[(long long)(k0 + br) * m + bc];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) {
+            double av[8], bv[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) av[i] = As[ty * 8 + i][kk];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) bv[j] = Bs[kk][tx * 8 + j];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            double* c = Cp + (long long)(ty * 8 + i) * m + tx * 8 + j;
+            if (MODE == 0) *c = acc[i][j];
+            else if (MODE == 1) *c = *c - acc[i][j];
+            else *c = -acc[i][j];
+        }
 }
 
-__global__ void __launch_bounds__(kT) k_cap_symmetrise(double* a, long long m) {
+// grid (mmax/128, mmax, blocks)
+__global__ void __launch_bounds__(kT) k_dense_symmetrise(const DenseDesc* desc, double* dense) {
+    const DenseDesc D = desc[blockIdx.z];
     const long long i = blockIdx.y;
     const long long j = (long long)blockIdx.x * kT + threadIdx.x;
-    if (j <= i) return;
-    const double avg = 0.5 * (a[i * m + j] + a[j * m + i]);
-    a[i * m + j] = avg;
-    a[j * m + i] = avg;
+    if (i >= D.m || j >= D.m || j <= i) return;
+    double* a = dense + D.off;
+    const double avg = 0.5 * (a[i * D.m + j] + a[j * D.m + i]);
+    a[i * D.m + j] = avg;
+    a[j * D.m + i] = avg;
+}
+
+// w = C^-1 r on the rows of the dense blocks: one warp per (valid) row, lanes stride the
+// columns, butterfly sum (fixed order).  Grid ceil(rows / 8) CTAs of 256 threads.
+__global__ void __launch_bounds__(256) k_dense_apply(const DenseDesc* desc, int nblocks,
+                                                     long long totalRows, const double* dense,
+                                                     const double* x, double* y, const int* skip) {
+    if (skip && *skip) return;
+    const int lane = threadIdx.x & 31;
+    const long long cr = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (cr >= totalRows) return;   // whole warp
+    int b = 0;
+    while (b + 1 < nblocks && desc[b + 1].row0 <= cr) ++b;
+    const DenseDesc D = desc[b];
+    const long long lr = cr - D.row0, g0 = D.t0 * kT;
+    const double* row = dense + D.off + lr * D.m;
+    double acc = 0.0;
+    for (long long c = lane; c < D.valid; c += 32) acc = fma(row[c], x[g0 + c], acc);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (lane == 0) y[g0 + lr] = acc;
 }
 
 // first half of k_cg_resid: the vector update only
@@ -197,7 +312,7 @@ __global__ void __launch_bounds__(kT) k_cg_vec(int mode, int k, int replace, con
 // partials, and the closing step by the last CTA -- the same arithmetic as k_cg_resid
 __global__ void __launch_bounds__(kVThreads) k_cg_close(int mode, int k, int replace,
                                                         const double* b, CgBuf B,
-                                                        long long capHeadRows, long long capTailRow0) {
+                                                        const int* tileDense) {
     __shared__ double s_r[kT];
     __shared__ double s_acc[kGroups][kT];
     __shared__ double s_w4[5][4];
@@ -209,7 +324,7 @@ __global__ void __launch_bounds__(kVThreads) k_cg_close(int mode, int k, int rep
     const long long T = blockIdx.x;
     const long long i = T * kT + c;
     const bool own = (g == 0) && (i < B.n);
-    const bool capTile = (T * kT < capHeadRows) || (T * kT >= capTailRow0);   // uniform
+    const bool capTile = tileDense[T] >= 0;    // uniform: the tile lies in a dense block
     const bool needW = (mode != kTrue) || replace;                           // uniform
     double r = 0.0, ru = 0.0, a1 = 0.0, a2 = 0.0, w = 0.0;
     double m[kGroupRows];
@@ -341,28 +456,48 @@ int cg_solve_caps(icqb_ctx* ctx, uint64_t dA_, int64_t n, int64_t ld, int storag
                          "icqb_cg_solve_dev: the block preconditioner needs row blocks that end on "
                          "multiples of 128 (or at n)");
 
-    // the two caps (clipped so that they do not overlap)
-    Cap cap[2];
-    cap[0].t0 = 0;
-    cap[0].tiles = std::min<long long>(std::max<long long>(ctx->cap_head_tiles, 0), nT);
-    cap[1].tiles = std::min<long long>(std::max<long long>(ctx->cap_tail_tiles, 0), nT - cap[0].tiles);
-    cap[1].t0 = nT - cap[1].tiles;
-    long long capDoubles = 0, mMax = 0;
-    for (int q = 0; q < 2; ++q) {
-        cap[q].m = cap[q].tiles * kT;
-        cap[q].valid = std::max<long long>(0, std::min<long long>(n, (cap[q].t0 + cap[q].tiles) * kT) -
-                                                  cap[q].t0 * kT);
-        capDoubles += cap[q].m * cap[q].m;
-        mMax = std::max(mMax, cap[q].m);
+    // the partition of the tile rows into diagonal blocks: given explicitly
+    // (icqb_cg_set_block_partition), or two caps around single tiles (icqb_cg_set_cap_tiles)
+    std::vector<long long> starts;
+    if (!ctx->block_starts.empty()) {
+        for (long long t : ctx->block_starts)
+            if (t < nT) starts.push_back(t);
+    } else {
+        const long long head = std::min<long long>(std::max<long long>(ctx->cap_head_tiles, 0), nT);
+        const long long tail = std::min<long long>(std::max<long long>(ctx->cap_tail_tiles, 0), nT - head);
+        starts.push_back(0);
+        for (long long t = std::max<long long>(head, 1); t <= nT - tail && t < nT; ++t) starts.push_back(t);
     }
-    const long long capHeadRows = cap[0].m;
-    const long long capTailRow0 = cap[1].tiles > 0 ? cap[1].t0 * kT : nT * kT;
+    if (starts.empty() || starts[0] != 0) starts.insert(starts.begin(), 0);
+    std::vector<DenseDesc> hdesc;
+    std::vector<int> htile((size_t)nT, -1);
+    long long denseDoubles = 0, denseRows = 0, kMaxTiles = 0;
+    for (size_t q = 0; q < starts.size(); ++q) {
+        const long long t0 = starts[q], t1 = (q + 1 < starts.size()) ? starts[q + 1] : nT;
+        if (t1 - t0 <= 1) continue;      // single tiles use the 128 x 128 inverse blocks
+        DenseDesc D;
+        D.t0 = t0;
+        D.tiles = t1 - t0;
+        D.m = D.tiles * kT;
+        D.valid = std::min<long long>(n, t1 * kT) - t0 * kT;
+        D.off = denseDoubles;
+        D.row0 = denseRows;
+        denseDoubles += D.m * D.m;
+        denseRows += D.valid;
+        kMaxTiles = std::max(kMaxTiles, D.tiles);
+        for (long long t = t0; t < t1; ++t) htile[(size_t)t] = (int)hdesc.size();
+        hdesc.push_back(D);
+    }
+    const int nDense = (int)hdesc.size();
+    if (kMaxTiles > 64) return set_error(ctx, ICQB_EARG, "icqb_cg_solve_dev: dense blocks of at most 64 tiles");
+    const long long descDoubles = ((long long)sizeof(DenseDesc) * std::max(nDense, 1) + 7) / 8;
+    const long long tileDoubles = (4 * nT + 7) / 8;
 
     // work space
     const long long nfull = chunk * P;
     const long long stateDoubles = (sizeof(CgState) + 7) / 8;
     const long long small = 8 * n + 8 + nfull + 6 * nT + stateDoubles;
-    const long long need = small + nT * kBlockElems + capDoubles + 2 * mMax + 64;
+    const long long need = small + nT * kBlockElems + denseDoubles + descDoubles + tileDoubles + 64;
     int rc = ensure_work(ctx, need);
     if (rc != ICQB_OK) return rc;
     CgBuf B;
@@ -384,10 +519,9 @@ int cg_solve_caps(icqb_ctx* ctx, uint64_t dA_, int64_t n, int64_t ld, int storag
     B.part_pz = wp; wp += nT;
     B.state = reinterpret_cast<CgState*>(wp); wp += stateDoubles;
     double* blocks = wp; wp += nT * kBlockElems;
-    cap[0].inv = wp; wp += cap[0].m * cap[0].m;
-    cap[1].inv = wp; wp += cap[1].m * cap[1].m;
-    double* gjCol = wp; wp += mMax;
-    double* gjRow = wp; wp += mMax;
+    double* dense = wp; wp += denseDoubles;
+    DenseDesc* ddesc = reinterpret_cast<DenseDesc*>(wp); wp += descDoubles;
+    int* dtile = reinterpret_cast<int*>(wp); wp += tileDoubles;
     B.Minv = blocks;
     B.n = n;
 
@@ -437,16 +571,12 @@ int cg_solve_caps(icqb_ctx* ctx, uint64_t dA_, int64_t n, int64_t ld, int storag
     // w = M^-1 r and the closing step, after r has been updated by k_cg_vec
     auto precondition = [&](int mode, int kk, int replace, const int* skipFlag) -> int {
         const bool needW = (mode != kTrue) || replace;
-        if (needW) {
-            for (int q = 0; q < 2; ++q) {
-                if (cap[q].valid <= 0) continue;
-                const long long row0 = cap[q].t0 * kT;
-                int r2 = launch_gemv(ctx, cap[q].inv, cap[q].valid, cap[q].valid, cap[q].m,
-                                     B.r + row0, B.w + row0, nullptr, st, skipFlag);
-                if (r2 != ICQB_OK) return r2;
-            }
+        if (needW && denseRows > 0) {
+            k_dense_apply<<<(unsigned)((denseRows + 7) / 8), 256, 0, st>>>(ddesc, nDense, denseRows, dense,
+                                                                         B.r, B.w, skipFlag);
+            ctx->launches += 1;
         }
-        k_cg_close<<<vgrid, vblock, 0, st>>>(mode, kk, replace, b, B, capHeadRows, capTailRow0);
+        k_cg_close<<<vgrid, vblock, 0, st>>>(mode, kk, replace, b, B, dtile);
         ctx->launches += 1;
         return check_cuda(ctx, cudaGetLastError(), "k_cg_close launch");
     };
@@ -525,27 +655,33 @@ int cg_solve_caps(icqb_ctx* ctx, uint64_t dA_, int64_t n, int64_t ld, int storag
         ctx->launches += 1;
         CG_CUDA(cudaGetLastError());
 
-        // dense caps: extract, all-reduce, invert (Gauss-Jordan, 2 kernels per pivot), symmetrise
-        for (int q = 0; q < 2; ++q) {
-            if (cap[q].tiles <= 0) continue;
-            const long long m = cap[q].m;
-            CG_CUDA(cudaMemsetAsync(cap[q].inv, 0, sizeof(double) * m * m, st));
-            const dim3 tgrid((unsigned)cap[q].tiles, (unsigned)cap[q].tiles);
+        // tables of the dense blocks, then: extract, all-reduce, block Gauss-Jordan, symmetrise
+        CG_CUDA(cudaMemcpyAsync(dtile, htile.data(), sizeof(int) * (size_t)nT, cudaMemcpyHostToDevice, st));
+        if (nDense > 0) {
+            CG_CUDA(cudaMemcpyAsync(ddesc, hdesc.data(), sizeof(DenseDesc) * (size_t)nDense,
+                                    cudaMemcpyHostToDevice, st));
+            CG_CUDA(cudaMemsetAsync(dense, 0, sizeof(double) * (size_t)denseDoubles, st));
+            const dim3 tgrid((unsigned)kMaxTiles, (unsigned)kMaxTiles, (unsigned)nDense);
             if (storage == 1)
-                k_cap_extract_lower<<<tgrid, 256, 0, st>>>(A, L, scale, n, cap[q].t0, m, cap[q].inv);
+                k_dense_extract_lower<<<tgrid, 256, 0, st>>>(A, L, scale, n, ddesc, dense);
             else
-                k_cap_extract_full<<<tgrid, 256, 0, st>>>(A, ld, mv.r0, mv.r1, scale, n, cap[q].t0, m,
-                                                         cap[q].inv);
+                k_dense_extract_full<<<tgrid, 256, 0, st>>>(A, ld, mv.r0, mv.r1, scale, n, ddesc, dense);
             ctx->launches += 1;
             CG_CUDA(cudaGetLastError());
-            CG_TRY(comm_allreduce_sum(ctx, cap[q].inv, m * m, st));
-            const dim3 ugrid((unsigned)(m / kT), (unsigned)m);
-            for (long long k = 0; k < m; ++k) {
-                k_gj_pivot<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(cap[q].inv, m, k, gjCol, gjRow);
-                k_gj_update<<<ugrid, kT, 0, st>>>(cap[q].inv, m, k, gjCol, gjRow);
+            CG_TRY(comm_allreduce_sum(ctx, dense, denseDoubles, st));
+            CG_CUDA(cudaFuncSetAttribute(k_tile_invert, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         kInvSmem));
+            for (long long K = 0; K < kMaxTiles; ++K) {
+                k_tile_invert<<<dim3(1, 1, (unsigned)nDense), kInvThreads, kInvSmem, st>>>(ddesc, dense, K);
+                k_tile_gemm<0><<<dim3((unsigned)kMaxTiles, 1, (unsigned)nDense), 256, 0, st>>>(ddesc, dense, K);
+                k_tile_gemm<1><<<tgrid, 256, 0, st>>>(ddesc, dense, K);
+                k_tile_gemm<2><<<dim3(1, (unsigned)kMaxTiles, (unsigned)nDense), 256, 0, st>>>(ddesc, dense, K);
+                ctx->launches += 4;
             }
-            k_cap_symmetrise<<<ugrid, kT, 0, st>>>(cap[q].inv, m);
-            ctx->launches += 2 * m + 1;
+            const long long mMax = kMaxTiles * kT;
+            k_dense_symmetrise<<<dim3((unsigned)(mMax / kT), (unsigned)mMax, (unsigned)nDense), kT, 0, st>>>(
+                ddesc, dense);
+            ctx->launches += 1;
             CG_CUDA(cudaGetLastError());
         }
 

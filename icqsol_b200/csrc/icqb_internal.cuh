@@ -6,6 +6,7 @@
 #include <stdint.h>
 
 #include <string>
+#include <vector>
 
 #include "../../include/icqb.h"
 
@@ -142,6 +143,7 @@ struct icqb_ctx {
     int precond_kind = 0;   // CG preconditioner when none is passed: 0 diag(A), 1 inverse 128x128 diagonal blocks,
                             // 2 (experimental) blocks + dense caps over cap_head_tiles / cap_tail_tiles
     int64_t cap_head_tiles = 0, cap_tail_tiles = 0;
+    std::vector<int64_t> block_starts;   // experimental: first tile row of every diagonal block
     int64_t cg_replacements = 0, cg_products = 0;   // statistics of the last solve
 
     double last_ms[icqb::kNumPhases] = {0, 0, 0, 0, 0};

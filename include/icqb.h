@@ -192,6 +192,13 @@ int icqb_cg_set_preconditioner(icqb_ctx* ctx, int kind);
  * triangles; a dense block over them restores the convergence of the
  * CG in the numpy model.  With kind 2 and no cap tiles the solve is the one of kind 1. */
 int icqb_cg_set_cap_tiles(icqb_ctx* ctx, int64_t head_tiles, int64_t tail_tiles);
+/* EXPERIMENTAL (kind 2): the general form -- diagonal block q of the preconditioner covers the
+ * 128-row tiles [starts[q], starts[q+1]) (the last one up to the end), starts[0] = 0, at most
+ * 64 tiles per block; blocks of one tile use the 128 x 128 inverses of kind 1, larger ones are
+ * extracted as dense matrices, inverted by a block Gauss-Jordan on the device and applied by a
+ * batched product.  In the numpy model blocks of 8 tiles need 92 iterations instead of 167 at
+ * config C2.  nblocks = 0 clears the partition (icqb_cg_set_cap_tiles then applies). */
+int icqb_cg_set_block_partition(icqb_ctx* ctx, const int64_t* starts, int64_t nblocks);
 /* Statistics of the last icqb_cg_solve_dev: how often the recurrence residual was replaced
  * by the true residual b - A x (0 = the first confirmation passed), and how many matrix
  * products were enqueued (iterations + confirmations + the ones skipped behind the stop

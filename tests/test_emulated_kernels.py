@@ -76,12 +76,14 @@ class Ctx:
         self.check(self.lib.icqb_assemble_lower_dev(self.h, 5, ptr[0], ptr[1], ptr[2]))
         return bufs
 
-    def solve(self, g, storage, kind, caps=None, ld=0, maxit=500):
+    def solve(self, g, storage, kind, caps=None, ld=0, maxit=500, starts=None):
         n = self.n
         b = numpy.ascontiguousarray(self.rhs())
         x = numpy.zeros(n)
         self.check(self.lib.icqb_cg_set_preconditioner(self.h, kind))
         self.check(self.lib.icqb_cg_set_cap_tiles(self.h, *(caps or (0, 0))))
+        st = numpy.asarray(starts or [], numpy.int64)
+        self.check(self.lib.icqb_cg_set_block_partition(self.h, lp(st) if len(st) else None, len(st)))
         it, r2, ri = ctypes.c_int64(0), ctypes.c_double(0.), ctypes.c_double(0.)
         self.check(self.lib.icqb_cg_solve_dev(
             self.h, g.ctypes.data, n, ld, storage, self.lib.icqb_area2_dev(self.h), 0, b.ctypes.data,
@@ -374,3 +376,26 @@ def test_emulated_ranks_without_rows(emu, oracle_mod):
     assert numpy.abs(b - ref.dot(x0)).max() <= 1e-12 * numpy.abs(b).max()
     for o in out:
         o[-1].close()
+
+
+@pytest.mark.parametrize('starts,storage', [([0, 2], 1), ([0, 3], 1), ([0, 1, 3], 0)])
+def test_emulated_block_partition(emu, oracle_mod, starts, storage):
+    """EXPERIMENTAL: an explicit partition of the tile rows into diagonal blocks -- batched
+    extraction, block Gauss-Jordan with 128^3 tile products, batched apply -- against the
+    numpy model of the same blocks (400 triangles = 4 tile rows, the last one ragged)."""
+    c = Ctx(emu, 20, 11)
+    n = c.n
+    ref = oracle_mod.green_matrix(c.xyz, c.tri, 5)
+    a2 = oracle_mod.area2(c.xyz, c.tri)
+    if storage == 1:
+        (g,) = c.assemble_lower()
+        ld = 0
+    else:
+        ld = (n + 15) // 16 * 16
+        g = numpy.zeros((n, ld))
+        c.check(emu.icqb_set_rows(c.h, 0, n))
+        c.check(emu.icqb_assemble_dev(c.h, 5, g.ctypes.data, 0, ld))
+    x, iters, rinf, b = c.solve(g, storage, 2, ld=ld, starts=starts)
+    assert numpy.abs(b - ref.dot(x)).max() <= 1e-12 * numpy.abs(b).max()
+    assert abs(iters - model_iterations(ref, a2, b, [128 * t for t in starts])) <= 1
+    c.close()

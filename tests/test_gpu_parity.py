@@ -794,3 +794,26 @@ def test_cap_blocks_same_answer_on_regular_sphere():
         out.append((rsp, solver.lastSolveInfo['iterations']))
     assert relerr(out[1][0], out[0][0]) < 1e-6
     assert out[1][1] <= out[0][1] + 3
+
+
+@experimental
+@pytest.mark.parametrize('storage', ['lower', 'full'])
+def test_block_tiles_cut_iterations(storage):
+    """Diagonal blocks of several tiles (batched block Gauss-Jordan on the device): fewer
+    iterations than single tiles, same response."""
+    from icqsol_b200.mesh.generators import uvSphere
+    from icqsol_b200.mesh.polydata import PolyData
+    from icqsol_b200.bem.icqLaplaceSolver import LaplaceSolver
+    xyz, tri = uvSphere(1.0, 64, 32)        # 3,968 triangles, 31 tile rows
+    out = {}
+    for k in (1, 4, 8):
+        solver = LaplaceSolver(PolyData.from_arrays(xyz, tri), float('inf'), 5, storage=storage,
+                               preconditioner='block+caps', blockTiles=k)
+        solver.setSourceFromExpression('1./sqrt(x**2 + (y-2.)**2 + (z-4.)**2)')
+        v = solver.getSourceArray(solver.getSourceArrayIndex())
+        rsp = solver.computeResponseField()
+        g = solver.getGreenMatrix()
+        assert numpy.abs(v + g.dot(rsp)).max() / numpy.abs(v).max() < 1e-12
+        out[k] = (rsp, solver.lastSolveInfo['iterations'])
+    assert out[8][1] < out[4][1] < out[1][1]
+    assert relerr(out[8][0], out[1][0]) < 1e-6

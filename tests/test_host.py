@@ -298,3 +298,14 @@ def test_vtk_reader_on_reference_data_files():
     assert pd.GetCellData().GetArray('potential').GetNumberOfTuples() == 5232
     pd = readVtkPolyData('/root/reference/test_results/testBoltFineWithField3.vtk')
     assert pd.GetPointData().GetArray('wave') is not None
+
+
+def test_block_partition():
+    from icqsol_b200.bem import icqRowPartition as rp
+    assert rp.blockPartition(400, 2) == [0, 2]
+    assert rp.blockPartition(2560, 8, 3, 2) == [0, 3, 11, 18]
+    assert rp.blockPartition(2560, 4) == [0, 4, 8, 12, 16]
+    assert rp.blockPartition(100, 8) == [0]
+    assert rp.blockPartition(1280, 1, 10, 0) == [0]           # one cap over everything
+    assert rp.blockPartition(1280, 3, 0, 2) == [0, 3, 6, 8]
+    assert rp.blockPartition(1280, 1) == list(range(10))
