@@ -1,26 +1,30 @@
-// EXPERIMENTAL (written without GPU access at the end of round 1; not reachable unless the
-// caller selects preconditioner kind 2 AND sets cap tiles; its tests run only with
-// ICQB_EXPERIMENTAL=1): conjugate gradient with DENSE CAP BLOCKS in the block
-// preconditioner.
+// EXPERIMENTAL solver (written after round 1's GPU budget was spent: never run on a GPU,
+// checked in the CPU emulation of the test suite, tools/emu; reached only with preconditioner
+// kind 2; its GPU tests run only with ICQB_EXPERIMENTAL=1): conjugate gradient with DENSE
+// DIAGONAL BLOCKS of several 128-row tiles in the block preconditioner.
 //
-// Why: neighbouring sliver triangles (the two rings at each pole of a UV sphere) make the
+// Why: (1) neighbouring sliver triangles (the rings at the poles of a UV sphere) make the
 // reference's diag(A) G indefinite -- the wrong-sign eigenvectors live entirely on those
-// rings (tools/experiments/spectrum_sliver_sphere.py).  The CG of
-// cg.cu with 128 x 128 diagonal blocks then does not converge; with ONE dense diagonal block
-// over the leading sliver tiles and one over the trailing ones it converges in ~110
-// iterations in the numpy model (tools/experiments/pcg_cap_blocks.py).
+// rings -- and the CG of cg.cu with 128 x 128 blocks then does not
+// converge; with ONE dense block over the leading sliver tiles and one over the trailing
+// ones ("caps") it converges in ~110 iterations in the numpy model
+// (tools/experiments/pcg_cap_blocks.py).  (2) On regular meshes larger blocks simply pay:
+// 92 iterations instead of 167 at config C2 with blocks of 8 tiles
+// (tools/experiments/pcg_block_size.py).
 //
 // Same algorithm, state and product kernels as cg.cu (solvers/icqConjugateGradient.py:49-79);
 // what differs is the preconditioner step w = M^-1 r:
-//   * tile rows [0, head) and [nT - tail, nT) each form one dense block of diag(s) A,
-//     extracted from the stored tiles (lower storage: symmetric fill), all-reduced over the
-//     ranks, inverted in global memory by an unblocked Gauss-Jordan (2 small kernels per
-//     pivot: once per solve) and symmetrised;
-//   * per iteration the residual kernel is split in two so that the caps can be applied
-//     with the validated streaming GEMV in between:
-//         k_cg_vec    x += alpha p, r -= alpha z            (all rows)
-//         k_gemv      w_cap = C^-1 r_cap                    (one launch per cap)
-//         k_cg_close  w = M^-1 r on the other tiles, rho, norms, beta, stopping flag.
+//   * the tile rows are partitioned into diagonal blocks (icqb_cg_set_block_partition, or two
+//     caps around single tiles, icqb_cg_set_cap_tiles); blocks of one tile use the 128 x 128
+//     inverses of cg.cu; every larger block is extracted from the stored tiles as a dense
+//     matrix of diag(s) A (lower storage: symmetric fill), all-reduced over the ranks, inverted
+//     in place by a block Gauss-Jordan (128^3 tile products, all blocks batched in a launch)
+//     and symmetrised -- once per solve;
+//   * per iteration the residual kernel is split in two so that the dense blocks can be
+//     applied in between:
+//         k_cg_vec       x += alpha p, r -= alpha z            (all rows)
+//         k_dense_apply  w = C^-1 r on the rows of the dense blocks (one warp per row)
+//         k_cg_close     w = M^-1 r on the single tiles, rho, norms, beta, stopping flag.
 //
 // The same experimental solver carries the PEER EXCHANGE (several ranks, lower storage, when
 // icqb_peer_create/attach have been called): k_symv_reduce<PEER> stores the partial product
