@@ -68,7 +68,7 @@ def centroid_potential(xyz, tri):
 
 
 class ClockSampler(threading.Thread):
-    """SM clock and throttle reasons during the timed region: NVML polled every 5 ms
+    """SM clock and throttle reasons during the timed region: NVML polled every 20 ms
     (nvidia_ml_py), or -- when NVML cannot be opened -- nvidia-smi in a loop (the recipe's
     clocks line, ~10 samples per second)."""
     QUERY = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
@@ -131,7 +131,7 @@ class ClockSampler(threading.Thread):
             try:
                 if self.nvml is not None:
                     self._sample_nvml()
-                    time.sleep(0.005)
+                    time.sleep(0.02)
                 else:
                     self._sample_smi()
                     time.sleep(0.05)
@@ -296,6 +296,7 @@ def run_b200(args):
                 rowPartition.blockPartition(n, args.block_tiles, *cap_tiles), numpy.int64)
             ctx.check(lib.icqb_cg_set_block_partition(ctx.handle, starts.ctypes.data_as(_lib.c_int64_p),
                                                       len(starts)))
+    ctx.check(lib.icqb_set_assembly_variant(ctx.handle, args.assembly_variant))
     ctx.check(lib.icqb_set_mesh(ctx.handle, xyz.ctypes.data_as(_lib.c_double_p), xyz.shape[0],
                                 tri.ctypes.data_as(_lib.c_int64_p), n))
     lower = args.storage == 'lower'
@@ -411,7 +412,7 @@ def run_b200(args):
         t0 = time.perf_counter()
         solver = LaplaceSolver(pd, float('inf'), 5, computeK=True, device=local,
                                storage=args.storage, preconditioner=args.preconditioner,
-                               blockTiles=args.block_tiles)
+                               blockTiles=args.block_tiles, assemblyVariant=args.assembly_variant)
         solver.setSolverMaxNumberOfIterations(args.max_iters)
         rsp = solver.computeResponseField()
         torch.cuda.synchronize(dev)
@@ -433,6 +434,16 @@ def run_b200(args):
         # algorithmic flop of this rank's off-diagonal launch (pairs it evaluates x 256 x 18)
         flop = pairs_local * 256.0 * FLOP_PER_EVAL_GK
         achieved = flop / (off_ms * 1e-3) / 1e12
+        # FP64-pipe instructions per evaluation of the kernel's inner loop (SASS counts,
+        # tools/sass_loops.py; G+K): validated kernel 16; far-field arithmetic 13 (12 with the
+        # Newton step) for the (warp, source triangle) pairs that took it
+        far_frac = None
+        instr_per_eval = 16.0
+        if args.assembly_variant:
+            fast, allp = ctypes.c_int64(0), ctypes.c_int64(0)
+            ctx.check(lib.icqb_assembly_stats(ctx.handle, ctypes.byref(fast), ctypes.byref(allp)))
+            far_frac = fast.value / max(allp.value, 1)
+            instr_per_eval = 16.0 - far_frac * (3.0 if args.assembly_variant == 1 else 4.0)
         gemv_bytes = 8.0 * stored     # bytes of matrix this rank streams per product
         gemv_gbs = gemv_bytes / (gemv_ms * 1e-3) / 1e9 if gemv_ms > 0 else 0.0
         # products that ran: iterations + the initial one + one per confirmation (those
@@ -446,6 +457,7 @@ def run_b200(args):
                        'step': 'fused G+K assembly + CG solve (max|v+G sigma| <= 5e-13 max|v|)',
                        'rows_per_gpu': rows, 'storage': args.storage,
                        'preconditioner': args.preconditioner, 'cap_tiles': list(cap_tiles), 'block_tiles': args.block_tiles,
+                       'assembly_variant': args.assembly_variant,
                        'parallelism': ('folded row blocks, lower storage x{0}' if lower
                                        else 'row-block x{0}').format(world),
                        'l2': 'inputs larger than L2 ({0:.2f} GB of G streamed per product per GPU)'.format(
@@ -471,8 +483,9 @@ def run_b200(args):
                 'peak': peak.value, 'unit': 'TFLOP/s', 'frac': achieved / peak.value,
                 'traffic': traffic_of('k_offdiag', args.storage, n),
                 'peak_source': 'DFMA loop measured in this run (icqb_measure_fp64_peak)',
-                'flop_per_evaluation': FLOP_PER_EVAL_GK, 'fp64_instr_per_evaluation': 16,
-                'issue_frac': (pairs_local * 256.0 * 16 * 2 / (off_ms * 1e-3) / 1e12) / peak.value,
+                'flop_per_evaluation': FLOP_PER_EVAL_GK, 'fp64_instr_per_evaluation': instr_per_eval,
+                'far_field_fraction': far_frac,
+                'issue_frac': (pairs_local * 256.0 * instr_per_eval * 2 / (off_ms * 1e-3) / 1e12) / peak.value,
                 'launches_per_step': 1, 'ms_per_launch': off_ms,
                 'share_of_step': off_ms / ms_per_step},
             'roofline_gemv': {
@@ -527,6 +540,10 @@ def main():
                          "block+caps there")
     ap.add_argument('--block-tiles', type=int, default=1,
                     help='experimental, with block+caps: 128-triangle tiles per diagonal block')
+    ap.add_argument('--assembly-variant', type=int, default=0, choices=[0, 1, 2],
+                    help='experimental arithmetic of the off-diagonal kernel (include/icqb.h, '
+                         'icqb_set_assembly_variant): 0 validated kernel, 1 far-field split, '
+                         '2 far-field split + Newton reciprocal square root')
     ap.add_argument('--max-iters', type=int, default=4000,
                     help='CG iteration cap (a solve that needs more is reported as not converged)')
     ap.add_argument('--no-cpu-baseline', action='store_true')

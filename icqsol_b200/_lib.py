@@ -42,6 +42,8 @@ SIGNATURES = [
                                     c_double_p, c_int64_p]),
     ('icqb_assemble_dev', c_int, [c_void_p, c_int, c_uint64, c_uint64, c_int64]),
     ('icqb_lower_num_tiles', c_int64, [c_void_p]),
+    ('icqb_set_assembly_variant', c_int, [c_void_p, c_int]),
+    ('icqb_assembly_stats', c_int, [c_void_p, c_int64_p, c_int64_p]),
     ('icqb_assemble_lower_dev', c_int, [c_void_p, c_int, c_uint64, c_uint64, c_uint64]),
     ('icqb_symv_dev', c_int, [c_void_p, c_uint64, c_uint64, c_uint64, c_int]),
     ('icqb_assemble_host', c_int, [c_void_p, c_int, c_double_p, c_double_p]),

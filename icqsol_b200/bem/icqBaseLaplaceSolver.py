@@ -44,7 +44,7 @@ def leadingDimension(n):
 class BaseLaplaceSolver(BaseSolver):
 
     def __init__(self, pdata, max_edge_length, order=5, computeK=False, device=None,
-                 storage='lower', preconditioner='block', blockTiles=1):
+                 storage='lower', preconditioner='block', blockTiles=1, assemblyVariant=None):
         """
         Constructor
         @param pdata polydata (vtkPolyData or stand-in)
@@ -64,6 +64,10 @@ class BaseLaplaceSolver(BaseSolver):
         @param blockTiles EXPERIMENTAL, with 'block+caps' only: tiles (of 128 triangles) per
                        diagonal block between the caps (numpy model at config C2: 167 iterations
                        with 1, 121 with 2, 92 with 8)
+        @param assemblyVariant EXPERIMENTAL arithmetic of the off-diagonal kernel
+                       (include/icqb.h, icqb_set_assembly_variant): 0 = validated kernel,
+                       1 = far-field split, 2 = far-field split with a Newton reciprocal square
+                       root; None = environment variable ICQB_ASSEMBLY_VARIANT, else 0
         """
         BaseSolver.__init__(self, pdata, max_edge_length, order)
         if storage not in ('lower', 'full'):
@@ -87,6 +91,11 @@ class BaseLaplaceSolver(BaseSolver):
         # kernels (library) are then ordered without extra synchronisation
         self.ctx.check(self.lib.icqb_set_stream(self.ctx.handle,
                                                 torch.cuda.current_stream().cuda_stream or 1))
+
+        if assemblyVariant is None:
+            assemblyVariant = int(os.environ.get('ICQB_ASSEMBLY_VARIANT', '0'))
+        self.assemblyVariant = int(assemblyVariant)
+        self.ctx.check(self.lib.icqb_set_assembly_variant(self.ctx.handle, self.assemblyVariant))
 
         self.ctx.check(self.lib.icqb_cg_set_preconditioner(
             self.ctx.handle, {'diagonal': 0, 'block': 1, 'block+caps': 2}[preconditioner]))

@@ -1,0 +1,476 @@
+// EXPERIMENTAL far-field split of the fused G/K off-diagonal assembly (assembly variants 1
+// and 2, icqb_set_assembly_variant).  Written at the end of round 1 without GPU access:
+// checked in the CPU emulation (tests/test_emulated_kernels.py) and by its SASS instruction counts, never
+// run on a GPU; the default (variant 0) is the validated kernel of assemble_offdiag.cu.
+//
+// Same CTA shape, tile order, bulk-copy ring and stores as k_offdiag.  What changes is the
+// arithmetic of one kernel evaluation for pairs of triangles that are well separated.
+//
+//   * The observer points of a flat triangle are affine in the rule's nodes:
+//     o_k = a + xi_k (b - a) + eta_k (c - a).  With the origin moved to the observer's vertex
+//     a (s' = s - a, u_k = o_k - a),
+//         r^2 = |s' - u_k|^2 = (|s'|^2 + |u_k|^2) + xi_k (-2 s'.(b-a)) + eta_k (-2 s'.(c-a)),
+//     so per SOURCE POINT the thread forms A = |s'|^2, B = -2 s'.(b-a), C = -2 s'.(c-a)
+//     (12 FP64 instructions, amortised over 16 evaluations) and per evaluation
+//         r2 = fma(xi_k, B, fma(eta_k, C, A + q_k)),   q_k = |u_k|^2 kept in registers:
+//     1 DADD + 2 DFMA instead of 3 DADD + DMUL + 2 DFMA, and 16 registers of q instead of 48
+//     of observer points.
+//   * Moving the origin to the observer triangle keeps the cancellation harmless only when
+//     the two triangles are far apart compared with their size: the three terms are then all
+//     of the size of r^2 (relative rounding error of r^2 <= ~16 eps).
+//     Every lane tests |c_i - c_j| >= kappa (rho_i + rho_j) for its pair of triangles
+//     (centroids c, radii rho = largest centroid-vertex distance, kappa = 3) and the warp
+//     votes: only if all 32 pairs are far does the warp take the fast arithmetic for this
+//     source triangle; otherwise it evaluates the 256 points exactly as k_offdiag does, from
+//     the reference's rounded quadrature points (bem/icqQuadrature.cpp:233-239).  A second
+//     condition, |c_i - c_j| >= max|coordinate| / 512, bounds the difference between the
+//     affine points used here and the reference's rounded ones (<= 1.5 eps max|coordinate|
+//     each) to <= 2e-13 of r.
+//   * K: both triangles are flat, so n_j.(x - y) depends on the observer point only and is
+//     affine in the nodes as well; the mirrored n_i.(y - x) is n_i.s'.
+//   * Variant 2 also replaces the third-order step of the reciprocal square root by a Newton
+//     step (4 instead of 5 instructions; relative error <= 2.4e-14 instead of <= 1 ulp, inside
+//     the 1e-12 of the parity contract but not "last bit") -- on the fast path only.
+//
+// FP64-pipe instructions per evaluation on the fast path (SASS counts in DESIGN.md 4.1b):
+// G 9 (8 with the Newton step) instead of 12, G+K 13 (12) instead of 16, plus the
+// per-source-point work above.
+#include "offdiag_common.cuh"
+
+namespace icqb {
+
+namespace {
+
+// The order-8 rule as literals (bem/icqQuadrature.cpp:122-144, the 14-digit values of
+// quad_tables.cuh): identical literals share one constant, so the 48 numbers of the rule
+// need 15 uniform registers' worth of distinct values (10 coordinates, 5 weights) instead of
+// 48 loads from c_triNodes -- the unrolled loops below would otherwise spill uniform registers.
+#define ICQB_TRI8(X)                                              \
+    X(0, 0.33333333333333, 0.33333333333333, 0.14431560767779)    \
+    X(1, 0.45929258829272, 0.45929258829272, 0.09509163426728)    \
+    X(2, 0.45929258829272, 0.08141482341455, 0.09509163426728)    \
+    X(3, 0.08141482341455, 0.45929258829272, 0.09509163426728)    \
+    X(4, 0.17056930775176, 0.17056930775176, 0.10321737053472)    \
+    X(5, 0.17056930775176, 0.65886138449648, 0.10321737053472)    \
+    X(6, 0.65886138449648, 0.17056930775176, 0.10321737053472)    \
+    X(7, 0.05054722831703, 0.05054722831703, 0.03245849762320)    \
+    X(8, 0.05054722831703, 0.89890554336594, 0.03245849762320)    \
+    X(9, 0.89890554336594, 0.05054722831703, 0.03245849762320)    \
+    X(10, 0.26311282963464, 0.72849239295540, 0.02723031417443)   \
+    X(11, 0.72849239295540, 0.00839477740996, 0.02723031417443)   \
+    X(12, 0.00839477740996, 0.26311282963464, 0.02723031417443)   \
+    X(13, 0.72849239295540, 0.26311282963464, 0.02723031417443)   \
+    X(14, 0.26311282963464, 0.00839477740996, 0.02723031417443)   \
+    X(15, 0.00839477740996, 0.72849239295540, 0.02723031417443)
+#define ICQB_CHECK_NODE(K, XI, ETA, W)                                                       \
+    static_assert(kTriNodes[46 + K].xi == XI && kTriNodes[46 + K].eta == ETA &&              \
+                      kTriNodes[46 + K].w == W,                                               \
+                  "ICQB_TRI8 must repeat the order-8 rows of quad_tables.cuh");
+ICQB_TRI8(ICQB_CHECK_NODE)
+#undef ICQB_CHECK_NODE
+static_assert(kNq == 16, "ICQB_TRI8 lists 16 nodes");
+
+// reciprocal square root on the fast path: ORDER 3 = rsqrt_1ulp, ORDER 2 = one Newton step.
+// Newton from a seed y0 = y (1 + d), |d| <= 2^-22.4 (MUFU.RSQ64H): e = 1 - x y0^2 = -2d - d^2,
+// y0 (1 + e/2) = y (1 - 3/2 d^2): always low, by up to 4.9e-14.  Adding c = 3/4 dmax^2 to the
+// bracket centres the error, |.| <= 2.4e-14; it costs nothing: e is formed as (1 + 2c) - x y0^2.
+template <int ORDER>
+__device__ __forceinline__ double rsqrt_ff(double x) {
+    if (ORDER == 3) return rsqrt_1ulp(x);
+    double y0;
+#ifdef ICQB_EMU
+    // the hardware seed's worst case (relative error 2^-22.4), so that the emulation shows the
+    // largest error the Newton step can leave
+    y0 = (double)(float)(1.0 / sqrt(x)) * (1.0 + 1.8e-7);
+#else
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
+#endif
+    constexpr double kTwoC = 2.0 * 0.75 * 3.25e-14;   // 2c, dmax^2 = 2^-44.8 = 3.25e-14
+    const double t = x * y0;
+    const double e = fma(-t, y0, 1.0 + kTwoC);
+    const double h = 0.5 * y0;
+    return fma(e, h, y0);
+}
+
+// state of one observer triangle (one thread)
+struct Obs {
+    double ax, ay, az;       // vertex a
+    double b2x, b2y, b2z;    // -2 (b - a)
+    double c2x, c2y, c2z;    // -2 (c - a)
+    double q[kNq];           // |o_k - a|^2 of the affine points
+    double nx, ny, nz;       // unit normal (K)
+    double cx, cy, cz, rho;  // centroid, radius
+};
+
+struct PairSums {
+    double g;    // sum_i0 sum_i1 w_i0 w_i1 / r
+    double k;    // sum w w n_j.(x - y) / r^3   -> K[i,j]
+    double km;   // sum w w n_i.(y - x) / r^3   -> K[j,i]
+};
+
+// well separated pair: affine observer points, origin at the observer's vertex a
+template <bool WITH_K, int RSQ>
+__device__ __forceinline__ PairSums pair_fast(const Obs& O, const double* __restrict__ pj,
+                                              double njx, double njy, double njz, double pjax,
+                                              double pjay, double pjaz) {
+    PairSums S{0.0, 0.0, 0.0};
+    double r3row[WITH_K ? kNq : 1];
+    if (WITH_K) {
+#pragma unroll
+        for (int k = 0; k < kNq; ++k) r3row[k] = 0.0;
+    }
+#pragma unroll 1
+    for (int i1 = 0; i1 < kNq; ++i1) {
+        const double sx = pj[3 * i1 + 0] - O.ax;
+        const double sy = pj[3 * i1 + 1] - O.ay;
+        const double sz = pj[3 * i1 + 2] - O.az;
+        const double A = fma(sz, sz, fma(sy, sy, sx * sx));
+        const double B = fma(sz, O.b2z, fma(sy, O.b2y, sx * O.b2x));
+        const double C = fma(sz, O.c2z, fma(sy, O.c2y, sx * O.c2x));
+        const double w1 = c_triNodes[kTri8 + i1].w;
+        double in[4] = {0.0, 0.0, 0.0, 0.0};
+        double c3[2] = {0.0, 0.0};
+#define ICQB_FF_EVAL(K, XI, ETA, W)                                            \
+    {                                                                          \
+        const double r2 = fma(XI, B, fma(ETA, C, A + O.q[K]));                 \
+        const double ri = rsqrt_ff<RSQ>(r2);                                   \
+        in[K & 3] = fma(W, ri, in[K & 3]);                                     \
+        if (WITH_K) {                                                          \
+            const double r3 = ri * ri * ri;                                    \
+            r3row[K] = fma(w1, r3, r3row[K]);                                  \
+            c3[K & 1] = fma(W, r3, c3[K & 1]);                                 \
+        }                                                                      \
+    }
+        ICQB_TRI8(ICQB_FF_EVAL)
+#undef ICQB_FF_EVAL
+        const double in0 = in[0], in1 = in[1], in2 = in[2], in3 = in[3];
+        const double c30 = c3[0], c31 = c3[1];
+        S.g = fma(w1, (in0 + in1) + (in2 + in3), S.g);
+        if (WITH_K) {
+            // mirrored entry K[j,i]: n_i . (y - a_i) = n_i . s'
+            const double nd = fma(O.nz, sz, fma(O.ny, sy, O.nx * sx));
+            S.km = fma(w1 * nd, c30 + c31, S.km);
+        }
+    }
+    if (WITH_K) {
+        // K[i,j]: n_j . (o_k - a_j) = n_j.(a_i - a_j) - (xi_k n_j.b2 + eta_k n_j.c2) / 2
+        const double e0 = fma(njz, O.az - pjaz, fma(njy, O.ay - pjay, njx * (O.ax - pjax)));
+        const double nb = fma(njz, O.b2z, fma(njy, O.b2y, njx * O.b2x));
+        const double nc = fma(njz, O.c2z, fma(njy, O.c2y, njx * O.c2x));
+#define ICQB_FF_K(K, XI, ETA, W)                                   \
+    {                                                              \
+        const double t = fma(XI, nb, ETA * nc);                    \
+        const double nd = fma(-0.5, t, e0);                        \
+        S.k = fma(W * nd, r3row[K], S.k);                          \
+    }
+        ICQB_TRI8(ICQB_FF_K)
+#undef ICQB_FF_K
+    }
+    return S;
+}
+
+// near pair: the arithmetic of k_offdiag on the reference's rounded quadrature points
+// (observer points re-read from the component-major table: coalesced, L1-resident)
+template <bool WITH_K>
+__device__ __forceinline__ PairSums pair_exact(const OffDiagParams& P, long long iLoad,
+                                               const Obs& O, const double* __restrict__ pj,
+                                               double njx, double njy, double njz, double pjax,
+                                               double pjay, double pjaz) {
+    PairSums S{0.0, 0.0, 0.0};
+    double c3[WITH_K ? kNq : 1];
+    if (WITH_K) {
+#pragma unroll
+        for (int k = 0; k < kNq; ++k) c3[k] = 0.0;
+    }
+#pragma unroll 1
+    for (int i0 = 0; i0 < kNq; ++i0) {
+        const double ox = __ldg(P.qp_soa + (long long)(3 * i0 + 0) * P.npad + iLoad);
+        const double oy = __ldg(P.qp_soa + (long long)(3 * i0 + 1) * P.npad + iLoad);
+        const double oz = __ldg(P.qp_soa + (long long)(3 * i0 + 2) * P.npad + iLoad);
+        const double w0 = c_triNodes[kTri8 + i0].w;
+        double in0 = 0.0, in1 = 0.0, in2 = 0.0, in3 = 0.0;
+        double r30 = 0.0, r31 = 0.0;
+#pragma unroll
+        for (int i1 = 0; i1 < kNq; ++i1) {
+            const double dx = pj[3 * i1 + 0] - ox;
+            const double dy = pj[3 * i1 + 1] - oy;
+            const double dz = pj[3 * i1 + 2] - oz;
+            const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+            const double ri = rsqrt_1ulp(r2);
+            const double w1 = c_triNodes[kTri8 + i1].w;
+            if ((i1 & 3) == 0) in0 = fma(w1, ri, in0);
+            if ((i1 & 3) == 1) in1 = fma(w1, ri, in1);
+            if ((i1 & 3) == 2) in2 = fma(w1, ri, in2);
+            if ((i1 & 3) == 3) in3 = fma(w1, ri, in3);
+            if (WITH_K) {
+                const double r3 = ri * ri * ri;
+                c3[i1] = fma(w0, r3, c3[i1]);
+                if (i1 & 1) r31 = fma(w1, r3, r31);
+                else r30 = fma(w1, r3, r30);
+            }
+        }
+        S.g = fma(w0, (in0 + in1) + (in2 + in3), S.g);
+        if (WITH_K) {
+            // K[i,j]: n_j . (x - y) = n_j . (o - a_j)
+            const double nd = fma(njz, oz - pjaz, fma(njy, oy - pjay, njx * (ox - pjax)));
+            S.k = fma(w0 * nd, r30 + r31, S.k);
+        }
+    }
+    if (WITH_K) {
+        // K[j,i]: n_i . (y - x) = n_i . (s - a_i)
+#pragma unroll
+        for (int i1 = 0; i1 < kNq; ++i1) {
+            const double nd = fma(O.nz, pj[3 * i1 + 2] - O.az,
+                                  fma(O.ny, pj[3 * i1 + 1] - O.ay, O.nx * (pj[3 * i1 + 0] - O.ax)));
+            S.km = fma(c_triNodes[kTri8 + i1].w * nd, c3[i1], S.km);
+        }
+    }
+    return S;
+}
+
+template <bool WITH_K, int RSQ>
+__global__ void __launch_bounds__(kTileObs) k_offdiag_ff(const OffDiagParams P) {
+    __shared__ __align__(128) double s_src[kStages][kSub * kQpStride];
+    __shared__ __align__(8) uint64_t s_bar[kStages];
+
+    const int tid = threadIdx.x;
+    const Tile T = decode_tile(P, blockIdx.x);
+    if (T.kind < 0) return;  // lower storage: tile above the diagonal (whole CTA exits)
+
+    if (tid == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+#ifndef ICQB_EMU
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#endif
+    }
+    __syncthreads();
+
+    const long long srcLeft = T.srcEnd - T.src0;
+    const int nSubTiles =
+        (int)(srcLeft >= kTileSrc ? kTileSrc / kSub : (srcLeft + kSub - 1) / kSub);
+    if (tid == 0) {
+        for (int s = 0; s < kStages && s < nSubTiles; ++s) {
+            mbar_expect_tx(&s_bar[s], kSubBytes);
+            bulk_g2s(&s_src[s][0], P.qp_aos + (T.src0 + (long long)s * kSub) * kQpStride, kSubBytes,
+                     &s_bar[s]);
+        }
+    }
+
+    // observer triangle of this thread
+    const long long iObs = T.obs0 + tid;
+    const bool obsValid = iObs < T.obsEnd;
+    const long long iLoad = obsValid ? iObs : (T.obsEnd - 1);
+    Obs O;
+    {
+        const double* v = P.verts + 9 * iLoad;
+        O.ax = __ldg(v + 0);
+        O.ay = __ldg(v + 1);
+        O.az = __ldg(v + 2);
+        // b - a and c - a are exact or correctly rounded, as in k_prepare; the factor -2 is exact
+        O.b2x = -2.0 * (__ldg(v + 3) - O.ax);
+        O.b2y = -2.0 * (__ldg(v + 4) - O.ay);
+        O.b2z = -2.0 * (__ldg(v + 5) - O.az);
+        O.c2x = -2.0 * (__ldg(v + 6) - O.ax);
+        O.c2y = -2.0 * (__ldg(v + 7) - O.ay);
+        O.c2z = -2.0 * (__ldg(v + 8) - O.az);
+#define ICQB_FF_Q(K, XI, ETA, W)                                                   \
+    {                                                                              \
+        const double ux = fma(XI, O.b2x, ETA * O.c2x); /* -2 (o_K - a) */          \
+        const double uy = fma(XI, O.b2y, ETA * O.c2y);                             \
+        const double uz = fma(XI, O.b2z, ETA * O.c2z);                             \
+        O.q[K] = 0.25 * fma(uz, uz, fma(uy, uy, ux * ux));                         \
+    }
+        ICQB_TRI8(ICQB_FF_Q)
+#undef ICQB_FF_Q
+        O.nx = O.ny = O.nz = 0.0;
+        if (WITH_K) {
+            O.nx = __ldg(P.nrm + 4 * iLoad + 0);
+            O.ny = __ldg(P.nrm + 4 * iLoad + 1);
+            O.nz = __ldg(P.nrm + 4 * iLoad + 2);
+        }
+        O.cx = __ldg(P.bound + 4 * iLoad + 0);
+        O.cy = __ldg(P.bound + 4 * iLoad + 1);
+        O.cz = __ldg(P.bound + 4 * iLoad + 2);
+        O.rho = __ldg(P.bound + 4 * iLoad + 3);
+    }
+    const double a2Obs = __ldg(P.area2 + iLoad);
+    // -1/(4 pi) * 0.5  (icqLaplaceFunctor.cpp:9, icqQuadrature.cpp:245)
+    const double cG = 0.5 / (-4.0 * 3.14159265358979323846);
+
+    const long long rowOff = P.lower
+        ? T.tile * kLowerTileElems + (long long)(obsValid ? tid : 0) * kLowerTile - T.src0
+        : (T.lrow0 + (obsValid ? tid : 0)) * P.ld;
+    double* gRow = P.G + rowOff;
+    double* kRow = WITH_K ? (P.K + rowOff) : nullptr;
+    double* kuRow = (WITH_K && P.lower) ? (P.Ku + rowOff) : nullptr;
+
+    unsigned int nFast = 0, nAll = 0;   // statistics (lane 0 of every warp adds them up)
+
+    for (int sub = 0; sub < nSubTiles; ++sub) {
+        const int stage = sub & 1;
+        const uint32_t parity = (sub >> 1) & 1;
+        const long long j0 = T.src0 + (long long)sub * kSub;
+        mbar_wait(&s_bar[stage], parity);
+        const double* sp = &s_src[stage][0];
+
+        for (int jj = 0; jj < kSub; ++jj) {
+            const long long j = j0 + jj;
+            if (j >= T.srcEnd) break;  // uniform
+            const double* pj = sp + jj * kQpStride;
+            double njx = 0, njy = 0, njz = 0, pjax = 0, pjay = 0, pjaz = 0;
+            if (WITH_K) {
+                njx = __ldg(P.nrm + 4 * j + 0);
+                njy = __ldg(P.nrm + 4 * j + 1);
+                njz = __ldg(P.nrm + 4 * j + 2);
+                pjax = __ldg(P.verts + 9 * j + 0);
+                pjay = __ldg(P.verts + 9 * j + 1);
+                pjaz = __ldg(P.verts + 9 * j + 2);
+            }
+            // separation test of this lane's pair, then the warp's vote
+            const double ex = __ldg(P.bound + 4 * j + 0) - O.cx;
+            const double ey = __ldg(P.bound + 4 * j + 1) - O.cy;
+            const double ez = __ldg(P.bound + 4 * j + 2) - O.cz;
+            const double d2 = fma(ez, ez, fma(ey, ey, ex * ex));
+            const double lim = P.kappa * (O.rho + __ldg(P.bound + 4 * j + 3));
+            const bool farLane = (d2 >= lim * lim) && (d2 >= P.guard2);
+            const bool far = __all_sync(0xffffffffu, farLane) != 0;
+            nAll += 1;
+            PairSums S;
+            if (far) {
+                nFast += 1;
+                S = pair_fast<WITH_K, RSQ>(O, pj, njx, njy, njz, pjax, pjay, pjaz);
+            } else {
+                S = pair_exact<WITH_K>(P, iLoad, O, pj, njx, njy, njz, pjax, pjay, pjaz);
+            }
+
+            const bool offDiag = (T.kind != 0) || (j != iObs);
+            if (obsValid && offDiag) {
+                const double a2Src = __ldg(P.area2 + j);
+                gRow[j] = (cG * a2Src) * S.g;
+                if (T.kind == 1) {
+                    // mirror: G[j,i] = g * areaObs / areaSrc  (icqLaplaceMatrices.cpp:98)
+                    P.G[(j - P.r0) * P.ld + iObs] = (cG * a2Obs) * S.g;
+                }
+                if (WITH_K) {
+                    kRow[j] = (cG * a2Src) * S.k;
+                    if (T.kind == 1) P.K[(j - P.r0) * P.ld + iObs] = (cG * a2Obs) * S.km;
+                    if (P.lower) kuRow[j] = (cG * a2Obs) * S.km;   // K[j,i] kept next to K[i,j]
+                }
+            } else if (obsValid && WITH_K) {
+                kRow[j] = 0.0;  // K[i,i] = 0 (flat panel, principal value)
+                if (P.lower) kuRow[j] = 0.0;
+            }
+        }
+
+        // refill this stage with sub-tile sub+2 once every thread is done reading it
+        if (sub + kStages < nSubTiles) {
+            __syncthreads();
+            if (tid == 0) {
+                mbar_expect_tx(&s_bar[stage], kSubBytes);
+                bulk_g2s(&s_src[stage][0],
+                         P.qp_aos + (T.src0 + (long long)(sub + kStages) * kSub) * kQpStride,
+                         kSubBytes, &s_bar[stage]);
+            }
+        }
+    }
+    if (P.stats && (tid & 31) == 0) {
+        atomicAdd(P.stats + 0, (unsigned long long)nFast);
+        atomicAdd(P.stats + 1, (unsigned long long)nAll);
+    }
+}
+
+// centroid and radius (largest centroid-vertex distance, rounded up a little) per triangle;
+// the padding rows get a huge radius so that a padded triangle is never "far"
+__global__ void __launch_bounds__(128) k_bounds(const double* __restrict__ verts, long long n,
+                                                long long nalloc, double* __restrict__ bound) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nalloc) return;
+    if (t >= n) {
+        bound[4 * t + 0] = bound[4 * t + 1] = bound[4 * t + 2] = 0.0;
+        bound[4 * t + 3] = 1.0e300;
+        return;
+    }
+    const double* v = verts + 9 * t;
+    const double cx = (v[0] + v[3] + v[6]) * (1.0 / 3.0);
+    const double cy = (v[1] + v[4] + v[7]) * (1.0 / 3.0);
+    const double cz = (v[2] + v[5] + v[8]) * (1.0 / 3.0);
+    double r2 = 0.0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const double dx = v[3 * k + 0] - cx, dy = v[3 * k + 1] - cy, dz = v[3 * k + 2] - cz;
+        r2 = fmax(r2, fma(dz, dz, fma(dy, dy, dx * dx)));
+    }
+    bound[4 * t + 0] = cx;
+    bound[4 * t + 1] = cy;
+    bound[4 * t + 2] = cz;
+    bound[4 * t + 3] = sqrt(r2) * (1.0 + 1.0e-12);
+}
+
+}  // namespace
+
+constexpr double kFarKappa = 3.0;
+
+// Prepare the per-triangle bounds (once per mesh) and launch the variant's kernel.
+int launch_offdiag_ff(icqb_ctx* ctx, const OffDiagParams& params, dim3 grid, bool withK) {
+    OffDiagParams P = params;
+    const long long nalloc = ctx->ntri_pad + kPad;
+    if (!ctx->d_bound) {
+        ICQB_CUDA(ctx, cudaMalloc(&ctx->d_bound, sizeof(double) * 4 * nalloc));
+        k_bounds<<<(unsigned)((nalloc + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_verts, ctx->ntri,
+                                                                            nalloc, ctx->d_bound);
+        ctx->launches += 1;
+        ICQB_CUDA(ctx, cudaGetLastError());
+    }
+    if (!ctx->d_ffstats) ICQB_CUDA(ctx, cudaMalloc(&ctx->d_ffstats, 2 * sizeof(unsigned long long)));
+    ICQB_CUDA(ctx, cudaMemsetAsync(ctx->d_ffstats, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    P.bound = ctx->d_bound;
+    P.kappa = kFarKappa;
+    const double guard = ctx->coord_max / 512.0;
+    P.guard2 = guard * guard;
+    P.stats = ctx->d_ffstats;
+    cudaEventRecord(ctx->ev0, ctx->stream);
+    if (ctx->offdiag_variant == 2) {
+        if (withK)
+            k_offdiag_ff<true, 2><<<grid, kTileObs, 0, ctx->stream>>>(P);
+        else
+            k_offdiag_ff<false, 2><<<grid, kTileObs, 0, ctx->stream>>>(P);
+    } else {
+        if (withK)
+            k_offdiag_ff<true, 3><<<grid, kTileObs, 0, ctx->stream>>>(P);
+        else
+            k_offdiag_ff<false, 3><<<grid, kTileObs, 0, ctx->stream>>>(P);
+    }
+    cudaEventRecord(ctx->ev1, ctx->stream);
+    ctx->launches += 1;
+    return check_cuda(ctx, cudaGetLastError(), "k_offdiag_ff launch");
+}
+
+}  // namespace icqb
+
+using namespace icqb;
+
+extern "C" {
+
+int icqb_set_assembly_variant(icqb_ctx* ctx, int variant) {
+    if (!ctx) return ICQB_EARG;
+    if (variant < 0 || variant > 2)
+        return set_error(ctx, ICQB_EARG, "icqb_set_assembly_variant: variant must be 0, 1 or 2");
+    ctx->offdiag_variant = variant;
+    return ICQB_OK;
+}
+
+int icqb_assembly_stats(icqb_ctx* ctx, int64_t* fast_pairs, int64_t* all_pairs) {
+    if (!ctx) return ICQB_EARG;
+    unsigned long long h[2] = {0, 0};
+    if (ctx->d_ffstats) {
+        ICQB_CUDA(ctx, cudaSetDevice(ctx->device));
+        ICQB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ICQB_CUDA(ctx, cudaMemcpy(h, ctx->d_ffstats, sizeof(h), cudaMemcpyDeviceToHost));
+    }
+    if (fast_pairs) *fast_pairs = (int64_t)h[0];
+    if (all_pairs) *all_pairs = (int64_t)h[1];
+    return ICQB_OK;
+}
+
+}  // extern "C"

@@ -123,6 +123,8 @@ void free_mesh(icqb_ctx* ctx) {
     cudaFree(ctx->d_qp_aos);
     cudaFree(ctx->d_area2);
     cudaFree(ctx->d_nrm);
+    cudaFree(ctx->d_bound);
+    ctx->d_bound = nullptr;
     ctx->d_xyz = ctx->d_verts = ctx->d_qp_soa = ctx->d_qp_aos = ctx->d_area2 = ctx->d_nrm = nullptr;
     ctx->d_tri = nullptr;
 }
@@ -195,6 +197,7 @@ int icqb_destroy(icqb_ctx* ctx) {
     comm_destroy(ctx);
     symv_plan_free(ctx);
     free_mesh(ctx);
+    cudaFree(ctx->d_ffstats);
     cudaFree(ctx->d_work);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -246,6 +249,8 @@ int icqb_set_mesh(icqb_ctx* ctx, const double* xyz, int64_t npts, const int64_t*
     ctx->r0 = 0;
     ctx->r1 = ntri;
     ctx->q0 = ctx->q1 = 0;
+    ctx->coord_max = 0.0;
+    for (int64_t k = 0; k < 3 * npts; ++k) ctx->coord_max = fmax(ctx->coord_max, fabs(xyz[k]));
     if (ntri == 0) return ICQB_OK;
     const int64_t nalloc = ctx->ntri_pad + kPad;
     ICQB_CUDA(ctx, cudaMalloc(&ctx->d_xyz, sizeof(double) * 3 * (npts > 0 ? npts : 1)));

@@ -399,3 +399,97 @@ def test_emulated_block_partition(emu, oracle_mod, starts, storage):
     assert numpy.abs(b - ref.dot(x)).max() <= 1e-12 * numpy.abs(b).max()
     assert abs(iters - model_iterations(ref, a2, b, [128 * t for t in starts])) <= 1
     c.close()
+
+
+# ---- EXPERIMENTAL: far-field split of the off-diagonal assembly (assemble_offdiag_ff.cu) -------
+
+def _assembly_stats(emu, c):
+    fast, allp = ctypes.c_int64(0), ctypes.c_int64(0)
+    c.check(emu.icqb_assembly_stats(c.h, ctypes.byref(fast), ctypes.byref(allp)))
+    return fast.value, allp.value
+
+
+@pytest.mark.parametrize('variant', [1, 2])
+@pytest.mark.parametrize('with_k', [False, True])
+def test_emulated_far_field_split_full_storage(emu, oracle_mod, variant, with_k):
+    """k_offdiag_ff on 576 triangles, full storage (mirrored tiles inside the block): every G
+    entry within 1e-12 of the oracle (variant 1: within a few ulp of the validated kernel;
+    variant 2 runs the Newton step from the seed's worst case and stays below 5e-14), K against
+    the definition oracle; a third of the (warp, source) pairs take the far-field arithmetic."""
+    c = Ctx(emu, 24, 13)
+    n = c.n
+    ref = oracle_mod.green_matrix(c.xyz, c.tri, 5)
+    g0 = numpy.full((n, n), numpy.nan)
+    c.check(emu.icqb_assemble_host(c.h, 5, dp(g0), None))
+    assert _assembly_stats(emu, c) == (0, 0)
+    c.check(emu.icqb_set_assembly_variant(c.h, variant))
+    g, k = numpy.full((n, n), numpy.nan), numpy.full((n, n), numpy.nan)
+    c.check(emu.icqb_assemble_host(c.h, 5, dp(g), dp(k) if with_k else None))
+    fast, allp = _assembly_stats(emu, c)
+    assert allp == 7424 and 0.3 * allp < fast < 0.5 * allp
+    assert numpy.abs(g / ref - 1.).max() < 1e-12
+    assert numpy.abs(g / g0 - 1.).max() < (2e-15 if variant == 1 else 5e-14)
+    if with_k:
+        kref = oracle_mod.k_block(c.xyz, c.tri, 0, n, 0, n)
+        assert numpy.abs(k - kref).max() < 1e-12 * numpy.abs(kref).max()
+        assert (numpy.diag(k) == 0.).all()
+    assert emu.icqb_set_assembly_variant(c.h, 3) != 0
+    c.close()
+
+
+@pytest.mark.parametrize('variant', [1, 2])
+def test_emulated_far_field_split_lower_storage(emu, oracle_mod, variant):
+    """Lower storage with two separated row blocks, G, K and the transposed K entries."""
+    from icqsol_b200.bem import icqRowPartition as rp
+    c = Ctx(emu, 20, 11)                               # 400 triangles, tile rows 0..3
+    n = c.n
+    blocks = (128, 256, 384, 400)
+    c.check(emu.icqb_set_assembly_variant(c.h, variant))
+    g, kl, ku = c.assemble_lower(blocks, with_k=True)
+    fast, allp = _assembly_stats(emu, c)
+    assert allp > 0 and fast > 0
+    ref = oracle_mod.green_matrix(c.xyz, c.tri, 5)
+    kref = oracle_mod.k_block(c.xyz, c.tri, 0, n, 0, n)
+    rows, krows, kurows = (rp.lowerTilesToRows(m, blocks, n) for m in (g, kl, ku))
+    kmax = numpy.abs(kref).max()
+    for l, i in enumerate(list(range(128, 256)) + list(range(384, 400))):   # local, global row
+        ce = min(n, (i // 128 + 1) * 128)
+        sel = numpy.arange(ce) != i
+        assert numpy.abs(rows[l, :ce][sel] / ref[i, :ce][sel] - 1.).max() < 1e-12
+        assert numpy.abs(krows[l, :ce] - kref[i, :ce]).max() < 1e-12 * kmax
+        assert numpy.abs(kurows[l, :ce] - kref[:ce, i]).max() < 1e-12 * kmax
+    c.close()
+
+
+def test_emulated_far_field_guard_and_ragged(emu, oracle_mod):
+    """A mesh far from the origin: |c_i - c_j| < max|coordinate| / 512 for every pair, so no pair
+    may take the affine arithmetic (its points would differ from the reference's rounded ones
+    by ~eps max|coordinate|) -- and the result is the validated kernel's.  Then ragged sizes."""
+    from icqsol_b200.mesh.generators import uvSphere
+    xyz, tri = uvSphere(1.0, 12, 7, center=(3000., 0., 0.))
+    h = ctypes.c_void_p()
+    assert emu.icqb_create(ctypes.byref(h), 0) == 0
+    xyz, tri = numpy.ascontiguousarray(xyz), numpy.ascontiguousarray(tri)
+    n = tri.shape[0]
+    out = []
+    for variant in (0, 1):
+        assert emu.icqb_set_mesh(h, dp(xyz), xyz.shape[0], lp(tri), n) == 0
+        assert emu.icqb_set_assembly_variant(h, variant) == 0
+        g = numpy.full((n, n), numpy.nan)
+        assert emu.icqb_assemble_host(h, 5, dp(g), None) == 0
+        out.append(g)
+    fast, allp = ctypes.c_int64(0), ctypes.c_int64(0)
+    assert emu.icqb_assembly_stats(h, ctypes.byref(fast), ctypes.byref(allp)) == 0
+    assert fast.value == 0 and allp.value > 0
+    assert numpy.abs(out[1] / out[0] - 1.).max() < 1e-15
+    # ragged: 1, 2, 33, 129 triangles (clamped lanes vote with a valid triangle's bounds)
+    xyz, tri = uvSphere(1.0, 24, 13)
+    xyz, tri = numpy.ascontiguousarray(xyz), numpy.ascontiguousarray(tri)
+    for m in (1, 2, 33, 129):
+        sub = numpy.ascontiguousarray(tri[::len(tri) // m][:m])
+        assert emu.icqb_set_mesh(h, dp(xyz), xyz.shape[0], lp(sub), m) == 0
+        g = numpy.full((m, m), numpy.nan)
+        assert emu.icqb_assemble_host(h, 5, dp(g), None) == 0
+        ref = oracle_mod.green_matrix(xyz, sub, 5)
+        assert numpy.abs(g / ref - 1.).max() < 1e-12
+    emu.icqb_destroy(h)

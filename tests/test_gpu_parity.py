@@ -817,3 +817,73 @@ def test_block_tiles_cut_iterations(storage):
         out[k] = (rsp, solver.lastSolveInfo['iterations'])
     assert out[8][1] < out[4][1] < out[1][1]
     assert relerr(out[8][0], out[1][0]) < 1e-6
+
+
+# ---- EXPERIMENTAL: far-field split of the off-diagonal assembly (assemble_offdiag_ff.cu) -----
+# Written at the end of round 1 without GPU access (CPU emulation + SASS counts only).
+
+@experimental
+@pytest.mark.parametrize('variant', [1, 2])
+@pytest.mark.parametrize('nt,nph', [(16, 9), (64, 30)])
+def test_far_field_split_every_entry(ctx, oracle_mod, variant, nt, nph):
+    """Every G entry of a whole matrix within 1e-12 of the oracle (variant 1: within a few ulp
+    of the validated kernel, variant 2: within 5e-14), K against the definition, and most
+    (warp, source triangle) pairs of the larger sphere on the far-field arithmetic."""
+    from icqsol_b200.mesh.generators import uvSphere
+    xyz, tri = uvSphere(1.0, nt, nph)
+    n = tri.shape[0]
+    g0, k0 = assemble(ctx, xyz, tri, 5, with_k=True)
+    ctx.check(ctx.lib.icqb_set_assembly_variant(ctx.handle, variant))
+    g, k = assemble(ctx, xyz, tri, 5, with_k=True)
+    fast, allp = ctypes.c_int64(0), ctypes.c_int64(0)
+    ctx.check(ctx.lib.icqb_assembly_stats(ctx.handle, ctypes.byref(fast), ctypes.byref(allp)))
+    ref = oracle_mod.green_matrix(xyz, tri, 5, threads=True)
+    assert max_entry_relerr(g, ref) < TOL_ENTRY
+    assert max_entry_relerr(g, g0) < (5e-15 if variant == 1 else 5e-14)
+    assert numpy.abs(k - k0).max() < 1e-12 * numpy.abs(k0).max()
+    assert (numpy.diag(k) == 0).all()
+    assert allp.value > 0
+    if n > 3000:
+        assert fast.value > 0.7 * allp.value
+
+
+@experimental
+@pytest.mark.parametrize('variant', [1, 2])
+def test_far_field_split_row_blocks_and_ragged(ctx, golden, oracle_mod, variant):
+    """Row blocks (direct-only tiles left and right of the block) on the bolt, ragged sizes."""
+    xyz, tri = golden.mesh('boltFine')
+    n = tri.shape[0]
+    ctx.check(ctx.lib.icqb_set_assembly_variant(ctx.handle, variant))
+    for (r0, r1) in [(1000, 1300), (0, 129), (2349, 2350)]:
+        g, k = assemble(ctx, xyz, tri, 5, with_k=True, rows=(r0, r1))
+        gref = oracle_mod.block(xyz, tri, r0, r1, 0, n, 5)
+        assert max_entry_relerr(g, gref) < TOL_ENTRY
+        kref = oracle_mod.k_block(xyz, tri, r0, r1, 0, n)
+        assert numpy.abs(k - kref).max() / numpy.abs(kref).max() < K_TOL
+    xs, ts = golden.mesh('sphere')
+    for m in (1, 2, 127, 129, 257):
+        sub = numpy.ascontiguousarray(ts[:m])
+        g = assemble(ctx, xs, sub, 5)
+        assert max_entry_relerr(g, oracle_mod.green_matrix(xs, sub, 5)) < TOL_ENTRY
+
+
+@experimental
+@pytest.mark.parametrize('variant', [1, 2])
+def test_far_field_split_config_c2(oracle_mod, variant):
+    """Config C2 through the solver classes (lower storage): sampled columns of G against the
+    oracle, the response against oracle rows, ~96 % of the pairs on the far-field arithmetic."""
+    from icqsol_b200.mesh.generators import uvSphere
+    from icqsol_b200.mesh.polydata import PolyData
+    from icqsol_b200.bem.icqLaplaceSolver import LaplaceSolver
+    xyz, tri = uvSphere(1.0, 142, 71)
+    solver = LaplaceSolver(PolyData.from_arrays(xyz, tri), float('inf'), 5, computeK=True,
+                           assemblyVariant=variant)
+    fast, allp = ctypes.c_int64(0), ctypes.c_int64(0)
+    solver.ctx.check(solver.lib.icqb_assembly_stats(solver.ctx.handle, ctypes.byref(fast),
+                                                    ctypes.byref(allp)))
+    assert 0.94 * allp.value < fast.value < 0.97 * allp.value
+    solver.setSourceFromExpression('1./sqrt(x**2 + (y-2.)**2 + (z-4.)**2)')
+    v = solver.getSourceArray(solver.getSourceArrayIndex())
+    rsp = solver.computeResponseField()
+    assert solver.lastSolveInfo['converged']
+    _sampled_checks(solver, xyz, tri, oracle_mod, [0, 141, 9999, 19751, 19879], rsp, v)

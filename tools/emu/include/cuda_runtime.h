@@ -107,6 +107,24 @@ static inline T __shfl_sync(unsigned, T v, int src) {
     return emu_shfl(v, src);
 }
 
+// warp vote: every lane of the (full) warp deposits its predicate, all read all 32
+static inline int __all_sync(unsigned, int pred) {
+    uint64_t* slot = emu::warp_slots();
+    const int lane = (int)((emu::cur().tid.x + emu::cur().bdim.x * (emu::cur().tid.y +
+                            emu::cur().bdim.y * emu::cur().tid.z)) & 31);
+    slot[lane] = pred ? 1u : 0u;
+    emu::syncwarp();
+    int all = 1;
+    for (int l = 0; l < 32; ++l) all &= (int)slot[l];
+    emu::syncwarp();
+    return all;
+}
+
+static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) {
+    const unsigned long long old = *p;
+    *p = old + v;
+    return old;
+}
 static inline unsigned int atomicAdd(unsigned int* p, unsigned int v) {
     const unsigned int old = *p;
     *p = old + v;

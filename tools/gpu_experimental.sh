@@ -8,8 +8,29 @@ out=gpurun_out
 mkdir -p $out
 export ICQB_EXPERIMENTAL=1
 if [ "$n" = "1" ]; then
-  timeout 600 python -m pytest tests -m gpu -x -q -k "cap_blocks or subdivide" > $out/${tag}_exp_pytest.log 2>&1
+  timeout 600 python -m pytest tests -m gpu -x -q -k "cap_blocks or subdivide or block_tiles" > $out/${tag}_exp_pytest.log 2>&1
   echo "experimental pytest rc=$?"; tail -5 $out/${tag}_exp_pytest.log
+  # far-field split of the off-diagonal assembly (assemble_offdiag_ff.cu): parity, then the
+  # three variants side by side (same workload, same run), then one full capture of variant 1
+  timeout 900 python -m pytest tests -m gpu -x -q -k "far_field" > $out/${tag}_exp_ff_pytest.log 2>&1
+  echo "far-field pytest rc=$?"; tail -5 $out/${tag}_exp_ff_pytest.log
+  for v in 0 1 2; do
+    timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --e2e-steps 1 --assembly-variant $v \
+        > $out/${tag}_exp_bench_ff$v.json 2> $out/${tag}_exp_bench_ff$v.err
+    echo "bench variant $v rc=$?"; python - <<PY
+import json
+try:
+    d = json.load(open('$out/${tag}_exp_bench_ff$v.json'))
+    r = d['roofline_assembly']
+    print('variant $v: offdiag %.2f ms, %.2f TFLOP/s = %.1f %% of peak, far-field fraction %s, step %.1f ms, cg %d' % (
+        r['ms_per_launch'], r['achieved'], 100 * r['frac'], r.get('far_field_fraction'), d['ms_per_step'], d['phases']['cg_iters']))
+except Exception as e:
+    print('no bench line:', e)
+PY
+  done
+  timeout 300 ncu --set full --clock-control none --import-source on -k regex:'k_offdiag_ff' -s 1 -c 1 \
+      -o $out/${tag}_exp_offdiag_ff1 -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline --e2e-steps 0 \
+      --assembly-variant 1 > $out/${tag}_exp_ncu_offdiag_ff1.log 2>&1; echo "ncu offdiag_ff rc=$?"
   exit 0
 fi
 tr() { python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $1 "${@:2}"; }
