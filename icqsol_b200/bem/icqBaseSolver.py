@@ -195,8 +195,10 @@ class BaseSolver:
         mid += b
         mid += c
         mid /= 3.0
-        for i in range(n):
-            x, y, z = mid[i]
-            v = eval(expression)
+        # same evaluation as the reference (eval per centroid, bem/icqBaseSolver.py:147-156),
+        # with the expression compiled once instead of parsed n times
+        code = compile(expression, '<source expression>', 'eval')
+        for i, (x, y, z) in enumerate(mid.tolist()):
+            v = eval(code)
             sourceData.SetTuple(i, [v])
         self.pdata.GetCellData().AddArray(sourceData)
