@@ -44,7 +44,8 @@ def leadingDimension(n):
 class BaseLaplaceSolver(BaseSolver):
 
     def __init__(self, pdata, max_edge_length, order=5, computeK=False, device=None,
-                 storage='lower', preconditioner='block', blockTiles=1, assemblyVariant=None):
+                 storage='lower', preconditioner='block', blockTiles=1, assemblyVariant=None,
+                 directFallback=False):
         """
         Constructor
         @param pdata polydata (vtkPolyData or stand-in)
@@ -64,6 +65,9 @@ class BaseLaplaceSolver(BaseSolver):
         @param blockTiles EXPERIMENTAL, with 'block+caps' only: tiles (of 128 triangles) per
                        diagonal block between the caps (numpy model at config C2: 167 iterations
                        with 1, 121 with 2, 92 with 8)
+        @param directFallback EXPERIMENTAL: when the CG stops short of the requested backward
+                       error (one rank only), solve by LU instead (solveGreenSystemDirect) --
+                       what the reference does in the first place (bem/icqLaplaceSolver.py:36)
         @param assemblyVariant EXPERIMENTAL arithmetic of the off-diagonal kernel
                        (include/icqb.h, icqb_set_assembly_variant): 0 = validated kernel,
                        1 = far-field split, 2 = far-field split with a Newton reciprocal square
@@ -76,6 +80,7 @@ class BaseLaplaceSolver(BaseSolver):
             raise ValueError("preconditioner must be 'block', 'diagonal' or 'block+caps'")
         self.storage = storage
         self.preconditioner = preconditioner
+        self.directFallback = bool(directFallback)
 
         torch = _requireTorchCuda()
         if device is None:
@@ -307,7 +312,54 @@ class BaseLaplaceSolver(BaseSolver):
         self.lastSolveInfo['converged'] = bool(reached)
         if not reached:
             import warnings
-            warnings.warn('icqsol_b200: CG stopped after {0} iterations with max|rhs - G x| = {1:.3e} '
-                          '(requested {2:.3e})'.format(iters.value, rinf.value, float(tol) * bmax),
-                          RuntimeWarning)
+            msg = ('icqsol_b200: CG stopped after {0} iterations with max|rhs - G x| = {1:.3e} '
+                   '(requested {2:.3e})'.format(iters.value, rinf.value, float(tol) * bmax))
+            if self.directFallback and self.numRanks == 1:
+                warnings.warn(msg + '; solving by LU instead (directFallback)', RuntimeWarning)
+                return self.solveGreenSystemDirect(rhs)
+            warnings.warn(msg, RuntimeWarning)
+        return x.cpu().numpy()
+
+    def solveGreenSystemDirect(self, rhs):
+        """Solve G x = rhs by LU with partial pivoting -- the reference's own solve
+        (numpy.linalg.solve, bem/icqLaplaceSolver.py:36) -- on the GPU.  For the matrices the
+        reference's quadrature leaves too indefinite for a CG (sliver triangles, DESIGN.md
+        section 4.6).  EXPERIMENTAL (written without GPU access).  The factorisation is
+        cuSOLVER's through torch.linalg.solve (library code, not one of this package's
+        kernels); the matrix it factors is assembled row-major for the purpose by the same
+        kernels (k_diag, k_offdiag) unless the solver already holds complete rows.  One rank
+        only; needs 16 N^2 bytes of HBM during the solve (the matrix and cuSOLVER's copy).
+        @return x float64[N]; details in self.lastSolveInfo"""
+        torch = _requireTorchCuda()
+        if self.numRanks != 1:
+            raise RuntimeError('solveGreenSystemDirect: one rank only (the LU is not distributed)')
+        n = self.numTriangles
+        b = self._toDevice(rhs)
+        if n == 0:
+            return numpy.zeros(0, numpy.float64)
+        t0 = torch.cuda.Event(enable_timing=True)
+        t1 = torch.cuda.Event(enable_timing=True)
+        t0.record()
+        if self.storage == 'full':
+            full = self.gMatDevice
+        else:
+            # complete rows, assembled again (tens of milliseconds) rather than expanded
+            full = torch.empty((n, self.ld), dtype=torch.float64, device=b.device)
+            self.ctx.check(self.lib.icqb_set_rows(self.ctx.handle, 0, n))
+            try:
+                self.ctx.check(self.lib.icqb_assemble_dev(self.ctx.handle, int(self.order),
+                                                          full.data_ptr(), 0, self.ld))
+                self.ctx.check(self.lib.icqb_synchronize(self.ctx.handle))
+            finally:
+                self.ctx.check(self.lib.icqb_set_row_blocks(self.ctx.handle, *self.rowBlocks))
+        x = torch.linalg.solve(full[:n, :n], b)
+        resid = (b - full[:n, :n] @ x).abs().max()
+        t1.record()
+        t1.synchronize()
+        rinf = float(resid.item())
+        bmax = float(b.abs().max().item())
+        self.lastSolveInfo = {'iterations': 0, 'residual2': float('nan'), 'residualInf': rinf,
+                              'milliseconds': t0.elapsed_time(t1), 'gemvMilliseconds': 0.,
+                              'residualReplacements': 0, 'products': 0, 'method': 'lu',
+                              'converged': bool(rinf <= 1e-10 * bmax or bmax == 0.)}
         return x.cpu().numpy()

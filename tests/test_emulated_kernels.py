@@ -493,3 +493,32 @@ def test_emulated_far_field_guard_and_ragged(emu, oracle_mod):
         ref = oracle_mod.green_matrix(xyz, sub, 5)
         assert numpy.abs(g / ref - 1.).max() < 1e-12
     emu.icqb_destroy(h)
+
+
+def test_emulated_row_major_assembly_between_lower_products(emu, oracle_mod):
+    """The sequence behind BaseLaplaceSolver.solveGreenSystemDirect: a context that holds a lower
+    storage assembles complete row-major rows in between (icqb_set_rows, icqb_assemble_dev) and
+    gets its row blocks back; the lower matrix and its product plan are unaffected."""
+    c = Ctx(emu, 16, 9, sms=3)                         # 256 triangles
+    n = c.n
+    blocks = (0, n, n, n)
+    (g,) = c.assemble_lower(blocks)
+    x = numpy.random.default_rng(3).normal(size=n)
+    y0 = numpy.full(n, numpy.nan)
+    c.check(emu.icqb_symv_dev(c.h, g.ctypes.data, x.ctypes.data, y0.ctypes.data, 0))
+    ld = (n + 15) // 16 * 16
+    full = numpy.full((n, ld), numpy.nan)
+    c.check(emu.icqb_set_rows(c.h, 0, n))
+    c.check(emu.icqb_assemble_dev(c.h, 5, full.ctypes.data, 0, ld))
+    c.check(emu.icqb_set_row_blocks(c.h, *blocks))
+    ref = oracle_mod.green_matrix(c.xyz, c.tri, 5)
+    assert numpy.abs(full[:, :n] / ref - 1.).max() < 1e-12
+    y1 = numpy.full(n, numpy.nan)
+    c.check(emu.icqb_symv_dev(c.h, g.ctypes.data, x.ctypes.data, y1.ctypes.data, 0))
+    assert (y1 == y0).all()
+    assert numpy.abs(y1 - ref.dot(x)).max() <= 1e-13 * numpy.abs(ref).dot(numpy.abs(x)).max()
+    # the LU the direct solve hands to cuSOLVER, here numpy's: same response as the reference's
+    b = c.rhs()
+    assert numpy.abs(numpy.linalg.solve(full[:, :n], b) - numpy.linalg.solve(ref, b)).max() < \
+        1e-9 * numpy.abs(numpy.linalg.solve(ref, b)).max()
+    c.close()

@@ -887,3 +887,47 @@ def test_far_field_split_config_c2(oracle_mod, variant):
     rsp = solver.computeResponseField()
     assert solver.lastSolveInfo['converged']
     _sampled_checks(solver, xyz, tri, oracle_mod, [0, 141, 9999, 19751, 19879], rsp, v)
+
+
+@experimental
+@pytest.mark.parametrize('storage', ['lower', 'full'])
+def test_direct_solve_matches_reference_lu(golden, storage):
+    """solveGreenSystemDirect = LU with partial pivoting on the device matrix, against the
+    reference's own solve (numpy.linalg.solve on the reference G, golden LU response)."""
+    from icqsol_b200.mesh.polydata import PolyData
+    from icqsol_b200.bem.icqLaplaceSolver import LaplaceSolver
+    xyz, tri = golden.mesh('boltFine')
+    solver = LaplaceSolver(PolyData.from_arrays(xyz, tri), float('inf'), 5, storage=storage)
+    solver.setSourceFromExpression('1./sqrt(x**2 + (y-2.)**2 + (z-4.)**2)')
+    v = solver.getSourceArray(solver.getSourceArrayIndex())
+    x = solver.solveGreenSystemDirect(v)
+    assert solver.lastSolveInfo['method'] == 'lu' and solver.lastSolveInfo['converged']
+    g = solver.getGreenMatrix()
+    assert numpy.abs(v - g.dot(x)).max() < 1e-11 * numpy.abs(v).max()
+    ref = numpy.linalg.solve(g, v)
+    assert relerr(x, ref) < 1e-8          # cond(G) ~ 2e4: two LUs agree to ~cond * eps
+    # the lower storage is untouched by the temporary row-major assembly
+    rsp = solver.computeResponseField()
+    assert relerr(-rsp, ref) < 1e-8
+
+
+@experimental
+def test_direct_fallback_on_sliver_sphere(oracle_mod):
+    """The UV sphere with C3-size pole slivers: the block-preconditioned CG does not converge
+    (DESIGN.md 4.6); with directFallback the solver returns the LU solution."""
+    import warnings
+    from icqsol_b200.mesh.generators import uvSphere
+    from icqsol_b200.mesh.polydata import PolyData
+    from icqsol_b200.bem.icqLaplaceSolver import LaplaceSolver
+    xyz, tri = uvSphere(1.0, 318, 20)
+    solver = LaplaceSolver(PolyData.from_arrays(xyz, tri), float('inf'), 5, directFallback=True)
+    solver.setSolverMaxNumberOfIterations(600)
+    solver.setSourceFromExpression('1./sqrt(x**2 + (y-2.)**2 + (z-4.)**2)')
+    v = solver.getSourceArray(solver.getSourceArrayIndex())
+    with warnings.catch_warnings(record=True) as caught:
+        warnings.simplefilter('always')
+        rsp = solver.computeResponseField()
+    assert any('solving by LU' in str(w.message) for w in caught)
+    assert solver.lastSolveInfo['method'] == 'lu'
+    g = oracle_mod.green_matrix(xyz, tri, 5, threads=True)
+    assert numpy.abs(v + g.dot(rsp)).max() / numpy.abs(v).max() < 1e-10

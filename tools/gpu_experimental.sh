@@ -8,7 +8,7 @@ out=gpurun_out
 mkdir -p $out
 export ICQB_EXPERIMENTAL=1
 if [ "$n" = "1" ]; then
-  timeout 600 python -m pytest tests -m gpu -x -q -k "cap_blocks or subdivide or block_tiles" > $out/${tag}_exp_pytest.log 2>&1
+  timeout 600 python -m pytest tests -m gpu -x -q -k "cap_blocks or subdivide or block_tiles or direct_" > $out/${tag}_exp_pytest.log 2>&1
   echo "experimental pytest rc=$?"; tail -5 $out/${tag}_exp_pytest.log
   # far-field split of the off-diagonal assembly (assemble_offdiag_ff.cu): parity, then the
   # three variants side by side (same workload, same run), then one full capture of variant 1
