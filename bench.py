@@ -46,6 +46,21 @@ FLOP_PER_EVAL_G = 12.0
 FLOP_PER_EVAL_GK = 18.0    # + 1/r^3 (2 mul) and two weighted accumulations (2 fma), DESIGN.md
 
 
+def make_mesh(ngpus, name):
+    """(label, xyz, tri) of the workload: a UV sphere, or -- 'bolt' -- config C3's geometry:
+    the reference's test_results/testBoltFine.vtk (2,350 triangles, kept as a golden fixture in
+    tests/golden/meshes.npz) with every triangle cut into 36 (84,600 triangles)."""
+    if name == 'bolt':
+        from icqsol_b200.mesh.generators import subdivide
+        m = numpy.load(os.path.join(ROOT, 'tests', 'golden', 'meshes.npz'))
+        xyz, tri = subdivide(m['boltFine_xyz'], m['boltFine_tri'], 6)
+        return 'testBoltFine_k6_N{0} (config C3: refined bolt)'.format(tri.shape[0]), xyz, tri
+    from icqsol_b200.mesh.generators import uvSphere
+    label, nt, nph = workload(ngpus, name)
+    xyz, tri = uvSphere(1.0, nt, nph)
+    return label, xyz, tri
+
+
 def workload(ngpus, name):
     """(label, n_theta, n_phi) of the UV sphere for this GPU count."""
     if name == 'c2' or (name == 'auto' and ngpus == 1):
@@ -210,9 +225,7 @@ def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    label, nt, nph = workload(args.gpus, args.workload)
-    from icqsol_b200.mesh.generators import uvSphere
-    xyz, tri = uvSphere(1.0, nt, nph)
+    label, xyz, tri = make_mesh(args.gpus, args.workload)
     cores = os.cpu_count() or 1
     ns = args.cpu_sample
     times = []
@@ -274,8 +287,7 @@ def run_b200(args):
     if world != args.gpus and rank == 0:
         print('warning: --gpus {0} but WORLD_SIZE {1}'.format(args.gpus, world), file=sys.stderr)
 
-    label, nt, nph = workload(world, args.workload)
-    xyz, tri = uvSphere(1.0, nt, nph)
+    label, xyz, tri = make_mesh(world, args.workload)
     n = tri.shape[0]
     v = centroid_potential(xyz, tri)
 
@@ -526,7 +538,10 @@ def main():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--workload', default='auto', choices=['auto', 'c2', 'c3', 'c5', 'small'])
+    ap.add_argument('--workload', default='auto', choices=['auto', 'c2', 'c3', 'c5', 'small', 'bolt'],
+                    help="auto = config C2 on one GPU, C2 scaled with N^2/GPU fixed on several; c3/c5 = "
+                         "UV spheres of the C3/C5 sizes; bolt = config C3's own geometry (refined "
+                         "testBoltFine, 84,600 triangles)")
     ap.add_argument('--cpu-sample', type=int, default=3600,
                     help='triangles of the CPU baseline sub-mesh (3600 -> 10-20 s single core)')
     ap.add_argument('--e2e-steps', type=int, default=2)
