@@ -75,6 +75,35 @@ def main():
             print('N={0} ranks={1} {4} {5}: CG iters {2}, backward {3:.2e}'.format(
                 n, world, info['iterations'], backward, storage, kind))
         del solver, psolver
+    # the weak-scaling bench workload at full size (N^2 / GPU of config C2): the oracle cannot
+    # build this matrix, so columns are taken as device products G e_j and compared with oracle
+    # columns, and the response is checked against oracle rows (tests/test_gpu_parity.py,
+    # _sampled_checks); every rank checks different columns
+    nt = int(round(142 * world ** 0.25 / 2.0)) * 2
+    xyz, tri = uvSphere(1.0, nt, nt // 2)
+    n = tri.shape[0]
+    print('rank', rank, 'full-size case', nt, nt // 2, n, flush=True)
+    solver = LaplaceSolver(PolyData.from_arrays(xyz, tri), float('inf'), 5)
+    solver.setSourceFromExpression('1./sqrt(x**2 + (y-2.)**2 + (z-4.)**2)')
+    v = solver.getSourceArray(solver.getSourceArrayIndex())
+    rsp = solver.computeResponseField()
+    assert solver.lastSolveInfo['converged'], solver.lastSolveInfo
+    cols = [0, n // 3 + 17, n - 1]
+    for j in cols:                       # collective calls: same columns on every rank
+        e = numpy.zeros(n)
+        e[j] = 1.0
+        col = solver.applyGreenMatrix(e)
+        if cols.index(j) == rank % len(cols):
+            ref = oracle.block(xyz, tri, 0, n, j, j + 1, 5)[:, 0]
+            assert numpy.abs(col / ref - 1.).max() < 1e-12, ('column', j)
+    for i in (rank * (n // world), min(n - 1, rank * (n // world) + 4321 % max(n // world, 1))):
+        grow = oracle.block(xyz, tri, i, i + 1, 0, n, 5)[0]
+        assert abs(v[i] + grow.dot(rsp)) < 1e-12 * numpy.abs(v).max(), ('row', i)
+    if rank == 0:
+        print('N={0} ranks={1} full size: CG iters {2}, backward {3:.2e}'.format(
+            n, world, solver.lastSolveInfo['iterations'],
+            solver.lastSolveInfo['residualInf'] / numpy.abs(v).max()))
+    del solver
     dist.barrier()
     dist.destroy_process_group()
     print('rank {0} ok'.format(rank))
