@@ -431,6 +431,13 @@ def run_b200(args):
         dt = time.perf_counter() - t0
         if it > 0:
             e2e_times.append(dt)
+        # host-side phases of this end-to-end step: cumulative milliseconds -> per phase
+        e2e_phases = {}
+        for group in ('constructor', 'solve'):
+            last = 0.0
+            for name, t in solver.hostTimings[group]:
+                e2e_phases['{0}: {1}'.format(group, name)] = round(t - last, 3)
+                last = t
         del solver
     e2e_s = None
     if e2e_times:
@@ -511,6 +518,7 @@ def run_b200(args):
             'e2e': None if e2e_s is None else {
                 'value': 2.0 * n * n / e2e_s, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d),
                 'd2h_bytes_per_step': int(d2h), 'ms_per_step': 1e3 * e2e_s,
+                'host_phases_ms': e2e_phases,
                 'api': 'LaplaceSolver(pdata, inf, 5, computeK=True).computeResponseField()'},
             'gpu_launches': int(launches),
             'clocks': sampler.summary(),

@@ -17,6 +17,7 @@ the double-layer matrix K (not in the reference snapshot).
 """
 import ctypes
 import os
+import time
 
 import numpy
 
@@ -73,7 +74,16 @@ class BaseLaplaceSolver(BaseSolver):
                        1 = far-field split, 2 = far-field split with a Newton reciprocal square
                        root; None = environment variable ICQB_ASSEMBLY_VARIANT, else 0
         """
+        # wall-clock marks of the host-side phases (milliseconds since construction began), for
+        # the end-to-end breakdown of bench.py: hostTimings['constructor'] / ['solve']
+        t_begin = time.perf_counter()
+        self.hostTimings = {'constructor': [], 'solve': []}
+
+        def mark(name):
+            self.hostTimings['constructor'].append((name, 1e3 * (time.perf_counter() - t_begin)))
+
         BaseSolver.__init__(self, pdata, max_edge_length, order)
+        mark('mesh intake (host)')
         if storage not in ('lower', 'full'):
             raise ValueError("storage must be 'lower' or 'full'")
         if preconditioner not in ('block', 'diagonal', 'block+caps'):
@@ -91,6 +101,7 @@ class BaseLaplaceSolver(BaseSolver):
         # the compiled library (raises if it was not built: no fallback)
         self.ctx = _lib.Context(self.device)
         self.lib = self.ctx.lib
+        mark('context')
 
         # run the library on torch's current stream: buffer initialisation (torch) and the
         # kernels (library) are then ordered without extra synchronisation
@@ -117,6 +128,7 @@ class BaseLaplaceSolver(BaseSolver):
         self.rank, self.numRanks = rowPartition.worldInfo()
         # one NCCL communicator per process, shared by every solver
         _lib.attachCommunicator(self.ctx, self.rank, self.numRanks, rowPartition.broadcastBytes)
+        mark('options, communicator')
 
         n = self.numTriangles
         self.ctx.check(self.lib.icqb_set_mesh(
@@ -132,6 +144,7 @@ class BaseLaplaceSolver(BaseSolver):
         self.rowBegin, self.rowEnd = self.rowBlocks[0], self.rowBlocks[1]
         self.numLocalRows = (self.rowBlocks[1] - self.rowBlocks[0]) + \
             (self.rowBlocks[3] - self.rowBlocks[2])
+        mark('mesh upload, k_prepare')
 
         self.ld = leadingDimension(n)
         dev = torch.device('cuda', self.device)
@@ -153,8 +166,10 @@ class BaseLaplaceSolver(BaseSolver):
                 self.kMatDevice = torch.empty((rows, self.ld), dtype=torch.float64, device=dev)
         self.gMat = None   # host copy, made on demand
         self.kMat = None
+        mark('matrix buffers')
 
         self.__computeResponseMatrix()
+        mark('assembly')
 
     def __computeResponseMatrix(self):
         # diagonal (self) terms and off-diagonal terms, one library call
@@ -285,11 +300,14 @@ class BaseLaplaceSolver(BaseSolver):
         Stops when max|rhs - G x| <= tol*max|rhs| (backward error in the max norm).
         @return x float64[N]; details in self.lastSolveInfo"""
         torch = _requireTorchCuda()
+        t_begin = time.perf_counter()
+        marks = self.hostTimings['solve'] = []
         n = self.numTriangles
         b = self._toDevice(rhs)
         x = self._toDevice(x0) if x0 is not None else torch.zeros(n, dtype=torch.float64,
                                                                   device=b.device)
         torch.cuda.current_stream().synchronize()
+        marks.append(('vectors to device', 1e3 * (time.perf_counter() - t_begin)))
         iters = ctypes.c_int64(0)
         r2 = ctypes.c_double(0.)
         rinf = ctypes.c_double(0.)
@@ -299,6 +317,7 @@ class BaseLaplaceSolver(BaseSolver):
             1 if self.storage == 'lower' else 0, self.lib.icqb_area2_dev(self.ctx.handle), 0,
             b.data_ptr(), x.data_ptr(), float(tol), 2, maxit, ctypes.byref(iters),
             ctypes.byref(r2), ctypes.byref(rinf)))
+        marks.append(('icqb_cg_solve_dev', 1e3 * (time.perf_counter() - t_begin)))
         self.lastSolveInfo = {'iterations': iters.value, 'residual2': r2.value,
                               'residualInf': rinf.value, 'milliseconds': self.ctx.last_ms(4),
                               'gemvMilliseconds': self.ctx.last_ms(3)}
