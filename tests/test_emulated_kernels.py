@@ -23,12 +23,30 @@ sys.path.insert(0, os.path.join(ROOT, 'tools', 'emu'))
 def emu():
     import build as emu_build
     from icqsol_b200 import _lib
+    # every "device" allocation ends at an inaccessible page: a kernel that runs past the end
+    # of a buffer faults (the emulation's memcheck, tools/emu/emu_runtime.cpp)
+    os.environ.setdefault('ICQB_EMU_GUARD', '1')
     lib = ctypes.CDLL(emu_build.build())
     for name, restype, argtypes in _lib.SIGNATURES:
         fn = getattr(lib, name)
         fn.restype = restype
         fn.argtypes = argtypes
+    lib.emu_alloc.restype = ctypes.c_void_p
+    lib.emu_alloc.argtypes = [ctypes.c_size_t]
     return lib
+
+
+def dev_array(lib, shape, fill=numpy.nan):
+    """float64 array in a guarded "device" allocation (never freed: test-sized), for the
+    caller-owned matrices and vectors the kernels write."""
+    shape = tuple(int(v) for v in numpy.atleast_1d(shape))
+    count = int(numpy.prod(shape))
+    ptr = lib.emu_alloc(8 * max(count, 1))
+    assert ptr
+    arr = numpy.ctypeslib.as_array((ctypes.c_double * max(count, 1)).from_address(ptr))[:count]
+    arr = arr.reshape(shape)
+    arr[...] = fill
+    return arr
 
 
 def dp(a):
@@ -71,15 +89,16 @@ class Ctx:
         blocks = blocks or (0, n, n, n)
         self.check(self.lib.icqb_set_row_blocks(self.h, *blocks))
         nt = self.lib.icqb_lower_num_tiles(self.h)
-        bufs = [numpy.full((max(nt, 1), 128, 128), numpy.nan) for _ in range(3 if with_k else 1)]
+        bufs = [dev_array(self.lib, (max(nt, 1), 128, 128)) for _ in range(3 if with_k else 1)]
         ptr = [b.ctypes.data for b in bufs] + [0, 0]
         self.check(self.lib.icqb_assemble_lower_dev(self.h, 5, ptr[0], ptr[1], ptr[2]))
         return bufs
 
     def solve(self, g, storage, kind, caps=None, ld=0, maxit=500, starts=None):
         n = self.n
-        b = numpy.ascontiguousarray(self.rhs())
-        x = numpy.zeros(n)
+        b = dev_array(self.lib, n)
+        b[:] = self.rhs()
+        x = dev_array(self.lib, n, 0.)
         self.check(self.lib.icqb_cg_set_preconditioner(self.h, kind))
         self.check(self.lib.icqb_cg_set_cap_tiles(self.h, *(caps or (0, 0))))
         st = numpy.asarray(starts or [], numpy.int64)
@@ -156,7 +175,7 @@ def test_emulated_lower_storage_and_product(emu, oracle_mod, sms):
     rng = numpy.random.default_rng(sms)
     a2 = oracle_mod.area2(c.xyz, c.tri)
     for scaled in (0, 1):
-        x, y = rng.normal(size=n), numpy.full(n, numpy.nan)
+        x, y = rng.normal(size=n), dev_array(emu, n)
         c.check(emu.icqb_symv_dev(c.h, g.ctypes.data, x.ctypes.data, y.ctypes.data, scaled))
         want = ref.dot(x) * (a2 if scaled else 1.)
         bound = numpy.abs(ref).dot(numpy.abs(x)) * (a2 if scaled else 1.)
@@ -179,7 +198,7 @@ def test_emulated_product_of_partial_row_blocks(emu, oracle_mod):
     tile = numpy.arange(n) // 128
     lower = mask & (tile[None, :] < tile[:, None])
     full = numpy.where(mask, ref, 0.) + numpy.where(lower, ref, 0.).T * (a2[None, :] / a2[:, None])
-    x, y = numpy.random.default_rng(1).normal(size=n), numpy.full(n, numpy.nan)
+    x, y = numpy.random.default_rng(1).normal(size=n), dev_array(emu, n)
     c.check(emu.icqb_symv_dev(c.h, g.ctypes.data, x.ctypes.data, y.ctypes.data, 0))
     assert (numpy.abs(y - full.dot(x)) <= 1e-13 * numpy.abs(full).dot(numpy.abs(x)) + 1e-300).all()
     c.close()
@@ -201,7 +220,7 @@ def test_emulated_cg_matches_model(emu, oracle_mod):
         assert rinf <= 5e-13 * numpy.abs(b).max()
     # row-block storage: k_gemv, k_cg_dir, k_cg_dot
     ld = (n + 15) // 16 * 16
-    gf = numpy.zeros((n, ld))
+    gf = dev_array(emu, (n, ld), 0.)
     c.check(emu.icqb_set_rows(c.h, 0, n))
     c.check(emu.icqb_assemble_dev(c.h, 5, gf.ctypes.data, 0, ld))
     x, iters, rinf, b = c.solve(gf, 0, 1, ld=ld)
@@ -232,8 +251,9 @@ def test_emulated_gemv(emu):
     c = Ctx(emu, 6, 4)
     rng = numpy.random.default_rng(0)
     for nrows, ncols, ld in ((5, 130, 130), (37, 129, 131), (4, 16, 16), (9, 1, 3)):
-        a = rng.normal(size=(nrows, ld))
-        x, y = rng.normal(size=ncols), numpy.full(nrows, numpy.nan)
+        a = dev_array(emu, (nrows, ld))
+        a[...] = rng.normal(size=(nrows, ld))
+        x, y = rng.normal(size=ncols), dev_array(emu, nrows)
         c.check(emu.icqb_gemv_host(c.h, a.ctypes.data, nrows, ncols, ld, dp(x), dp(y)))
         want = a[:, :ncols].dot(x)
         assert (numpy.abs(y - want) <= 1e-13 * numpy.abs(a[:, :ncols]).dot(numpy.abs(x))).all()
@@ -294,7 +314,7 @@ def _run_ranks(emu, nranks, n_theta, n_phi, storage, kind, caps=None, peer=False
             else:
                 r0, r1 = rp.rowRange(n, rank, nranks)
                 ld = (n + 15) // 16 * 16
-                g = numpy.zeros((max(r1 - r0, 1), ld))
+                g = dev_array(emu, (max(r1 - r0, 1), ld), 0.)
                 c.check(emu.icqb_set_rows(c.h, r0, r1))
                 c.check(emu.icqb_assemble_dev(c.h, 5, g.ctypes.data, 0, ld))
             out[rank] = c.solve(g, storage, kind, caps, ld=ld) + (c,)
@@ -392,7 +412,7 @@ def test_emulated_block_partition(emu, oracle_mod, starts, storage):
         ld = 0
     else:
         ld = (n + 15) // 16 * 16
-        g = numpy.zeros((n, ld))
+        g = dev_array(emu, (n, ld), 0.)
         c.check(emu.icqb_set_rows(c.h, 0, n))
         c.check(emu.icqb_assemble_dev(c.h, 5, g.ctypes.data, 0, ld))
     x, iters, rinf, b = c.solve(g, storage, 2, ld=ld, starts=starts)
@@ -504,16 +524,16 @@ def test_emulated_row_major_assembly_between_lower_products(emu, oracle_mod):
     blocks = (0, n, n, n)
     (g,) = c.assemble_lower(blocks)
     x = numpy.random.default_rng(3).normal(size=n)
-    y0 = numpy.full(n, numpy.nan)
+    y0 = dev_array(emu, n)
     c.check(emu.icqb_symv_dev(c.h, g.ctypes.data, x.ctypes.data, y0.ctypes.data, 0))
     ld = (n + 15) // 16 * 16
-    full = numpy.full((n, ld), numpy.nan)
+    full = dev_array(emu, (n, ld))
     c.check(emu.icqb_set_rows(c.h, 0, n))
     c.check(emu.icqb_assemble_dev(c.h, 5, full.ctypes.data, 0, ld))
     c.check(emu.icqb_set_row_blocks(c.h, *blocks))
     ref = oracle_mod.green_matrix(c.xyz, c.tri, 5)
     assert numpy.abs(full[:, :n] / ref - 1.).max() < 1e-12
-    y1 = numpy.full(n, numpy.nan)
+    y1 = dev_array(emu, n)
     c.check(emu.icqb_symv_dev(c.h, g.ctypes.data, x.ctypes.data, y1.ctypes.data, 0))
     assert (y1 == y0).all()
     assert numpy.abs(y1 - ref.dot(x)).max() <= 1e-13 * numpy.abs(ref).dot(numpy.abs(x)).max()
@@ -522,3 +542,32 @@ def test_emulated_row_major_assembly_between_lower_products(emu, oracle_mod):
     assert numpy.abs(numpy.linalg.solve(full[:, :n], b) - numpy.linalg.solve(ref, b)).max() < \
         1e-9 * numpy.abs(numpy.linalg.solve(ref, b)).max()
     c.close()
+
+
+def test_emulated_guard_pages_catch_an_overrun():
+    """The memcheck of the emulation is real: a product whose matrix buffer is one row too short
+    dies with SIGSEGV at the guard page (in a child process), the correct call does not."""
+    import subprocess
+    script = r'''
+import ctypes, os, sys, numpy
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, 'tools', 'emu'))
+os.environ['ICQB_EMU_GUARD'] = '1'
+import build as emu_build
+from icqsol_b200 import _lib
+lib = ctypes.CDLL(emu_build.build())
+for name, restype, argtypes in _lib.SIGNATURES:
+    fn = getattr(lib, name); fn.restype = restype; fn.argtypes = argtypes
+lib.emu_alloc.restype = ctypes.c_void_p; lib.emu_alloc.argtypes = [ctypes.c_size_t]
+h = ctypes.c_void_p(); assert lib.icqb_create(ctypes.byref(h), 0) == 0
+rows, cols, short = 8, 512, int(sys.argv[1])
+a = lib.emu_alloc(8 * (rows - short) * cols)
+ctypes.memset(a, 0, 8 * (rows - short) * cols)
+x, y = numpy.ones(cols), numpy.zeros(rows)
+dp = lambda v: v.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+assert lib.icqb_gemv_host(h, a, rows, cols, cols, dp(x), dp(y)) == 0
+print('ok')
+'''.format(root=ROOT)
+    good = subprocess.run([sys.executable, '-c', script, '0'], capture_output=True, text=True, timeout=300)
+    assert good.returncode == 0 and 'ok' in good.stdout, good.stderr[-2000:]
+    bad = subprocess.run([sys.executable, '-c', script, '1'], capture_output=True, text=True, timeout=300)
+    assert bad.returncode == -11, (bad.returncode, bad.stdout, bad.stderr[-500:])

@@ -2,9 +2,12 @@
 // threads of one block, a fake synchronous CUDA runtime.  Test infrastructure only.
 #include <setjmp.h>
 #include <stdio.h>
+#include <sys/mman.h>
 #include <ucontext.h>
 
 #include <chrono>
+#include <mutex>
+#include <unordered_map>
 #include <vector>
 
 #include "cuda_runtime.h"
@@ -200,7 +203,32 @@ cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr, int) {
 }
 cudaError_t cudaGetLastError() { return cudaSuccess; }
 const char* cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : "emulated error"; }
+// ICQB_EMU_GUARD=1: every "device" allocation ends exactly (to 16 bytes) at an inaccessible
+// page, so a kernel or copy that runs past the end of a buffer faults at once instead of reading
+// the allocator's padding -- the emulation's stand-in for compute-sanitizer's memcheck.
+static bool guard_mode() {
+    static const int g = getenv("ICQB_EMU_GUARD") ? 1 : 0;
+    return g != 0;
+}
+static std::mutex g_guard_mu;
+static std::unordered_map<void*, std::pair<void*, size_t>> g_guarded;   // user pointer -> mapping
+
 cudaError_t emuMalloc(void** p, size_t bytes) {
+    if (guard_mode()) {
+        const size_t page = 4096;
+        const size_t b16 = (bytes + 15) / 16 * 16;
+        const size_t body = (b16 + page - 1) / page * page;
+        char* base = (char*)mmap(nullptr, body + page, PROT_READ | PROT_WRITE,
+                                 MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+        if (base == MAP_FAILED) return cudaErrorInvalidValue;
+        memset(base, 0xff, body);
+        mprotect(base + body, page, PROT_NONE);
+        void* q = base + body - b16;
+        std::lock_guard<std::mutex> lock(g_guard_mu);
+        g_guarded[q] = std::make_pair((void*)base, body + page);
+        *p = q;
+        return cudaSuccess;
+    }
     // poison fresh memory with NaN patterns: reads of never-written "device" memory show up
     size_t n = (bytes + 63) / 64 * 64 + 64;
     void* q = aligned_alloc(256, (n + 255) / 256 * 256);
@@ -209,8 +237,27 @@ cudaError_t emuMalloc(void** p, size_t bytes) {
     *p = q;
     return cudaSuccess;
 }
-cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
-cudaError_t cudaFreeHost(void* p) { free(p); return cudaSuccess; }
+static void emu_release(void* p) {
+    if (!p) return;
+    if (guard_mode()) {
+        std::lock_guard<std::mutex> lock(g_guard_mu);
+        auto it = g_guarded.find(p);
+        if (it != g_guarded.end()) {
+            munmap(it->second.first, it->second.second);
+            g_guarded.erase(it);
+            return;
+        }
+    }
+    free(p);
+}
+cudaError_t cudaFree(void* p) { emu_release(p); return cudaSuccess; }
+cudaError_t cudaFreeHost(void* p) { emu_release(p); return cudaSuccess; }
+// for the tests: a guarded (or plain) buffer to stand in for a caller-owned device array
+extern "C" void* emu_alloc(size_t bytes) {
+    void* p = nullptr;
+    return emuMalloc(&p, bytes) == cudaSuccess ? p : nullptr;
+}
+extern "C" void emu_free(void* p) { emu_release(p); }
 cudaError_t cudaMemcpy(void* dst, const void* src, size_t bytes, cudaMemcpyKind) {
     memmove(dst, src, bytes);
     return cudaSuccess;
