@@ -206,9 +206,10 @@ const char* cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no er
 // ICQB_EMU_GUARD=1: every "device" allocation ends exactly (to 16 bytes) at an inaccessible
 // page, so a kernel or copy that runs past the end of a buffer faults at once instead of reading
 // the allocator's padding -- the emulation's stand-in for compute-sanitizer's memcheck.
-static bool guard_mode() {
-    static const int g = getenv("ICQB_EMU_GUARD") ? 1 : 0;
-    return g != 0;
+// ICQB_EMU_GUARD=2 puts the inaccessible page BEFORE the buffer instead (underruns).
+static int guard_mode() {
+    static const int g = getenv("ICQB_EMU_GUARD") ? atoi(getenv("ICQB_EMU_GUARD")) : 0;
+    return g;
 }
 static std::mutex g_guard_mu;
 static std::unordered_map<void*, std::pair<void*, size_t>> g_guarded;   // user pointer -> mapping
@@ -221,9 +222,16 @@ cudaError_t emuMalloc(void** p, size_t bytes) {
         char* base = (char*)mmap(nullptr, body + page, PROT_READ | PROT_WRITE,
                                  MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
         if (base == MAP_FAILED) return cudaErrorInvalidValue;
-        memset(base, 0xff, body);
-        mprotect(base + body, page, PROT_NONE);
-        void* q = base + body - b16;
+        void* q;
+        if (guard_mode() == 2) {
+            mprotect(base, page, PROT_NONE);
+            memset(base + page, 0xff, body);
+            q = base + page;
+        } else {
+            memset(base, 0xff, body);
+            mprotect(base + body, page, PROT_NONE);
+            q = base + body - b16;
+        }
         std::lock_guard<std::mutex> lock(g_guard_mu);
         g_guarded[q] = std::make_pair((void*)base, body + page);
         *p = q;
