@@ -571,3 +571,20 @@ print('ok')
     assert good.returncode == 0 and 'ok' in good.stdout, good.stderr[-2000:]
     bad = subprocess.run([sys.executable, '-c', script, '1'], capture_output=True, text=True, timeout=300)
     assert bad.returncode == -11, (bad.returncode, bad.stdout, bad.stderr[-500:])
+
+
+@pytest.mark.parametrize('order', ['reverse', 'shuffle'])
+def test_emulated_kernels_under_other_thread_orders(order):
+    """The threads of a block run in ascending order between two synchronisation points by
+    default; a missing barrier can hide behind that order.  The assembly, product and CG tests
+    again in a child process with the order reversed / freshly permuted every round."""
+    import subprocess
+    if os.environ.get('ICQB_EMU_ORDER'):
+        pytest.skip('already running under ICQB_EMU_ORDER')
+    env = dict(os.environ, ICQB_EMU_ORDER=order)
+    out = subprocess.run(
+        [sys.executable, '-m', 'pytest', os.path.abspath(__file__), '-x', '-q', '-k',
+         'assembly_full_storage or lower_storage_and_product or cg_matches_model or cap_blocks or '
+         'far_field_split_lower or block_partition or subdivide or gemv'],
+        capture_output=True, text=True, env=env, timeout=1200, cwd=ROOT)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]

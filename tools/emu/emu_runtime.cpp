@@ -151,11 +151,25 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& bod
                     f.uc.uc_link = nullptr;
                     makecontext(&f.uc, fiber_entry, 0);
                 }
-                // round robin until every thread of the block has returned
+                // round robin until every thread of the block has returned.  ICQB_EMU_ORDER
+                // changes the order in which the threads run between two synchronisation points
+                // (reverse, or a fresh pseudo-random permutation every round): a missing barrier
+                // that the ascending order happens to hide shows up as a different result.
                 long idle = 0;
+                static const char* orderEnv = getenv("ICQB_EMU_ORDER");
+                const int orderMode = !orderEnv ? 0 : (orderEnv[0] == 'r' ? 1 : 2);
+                std::vector<int> order(nthreads);
+                for (int t = 0; t < nthreads; ++t) order[t] = orderMode == 1 ? nthreads - 1 - t : t;
+                uint64_t rng = 0x9e3779b97f4a7c15ULL ^ (bx * 73856093u) ^ (by * 19349663u) ^ (bz * 83492791u);
                 while (b.alive > 0) {
                     bool progressed = false;
-                    for (int t = 0; t < nthreads; ++t) {
+                    if (orderMode == 2)
+                        for (int t = nthreads - 1; t > 0; --t) {
+                            rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17;
+                            std::swap(order[t], order[(int)(rng % (uint64_t)(t + 1))]);
+                        }
+                    for (int ot = 0; ot < nthreads; ++ot) {
+                        const int t = order[ot];
                         Fiber& f = b.fibers[t];
                         if (f.done) continue;
                         g_cur = &f;
