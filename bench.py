@@ -303,9 +303,9 @@ def run_b200(args):
     if args.preconditioner == 'block+caps':    # experimental, see icqsol_b200/csrc/cg_caps.cu
         cap_tiles = rowPartition.sliverCapTiles(xyz, tri)
         ctx.check(lib.icqb_cg_set_cap_tiles(ctx.handle, *cap_tiles))
-        if args.block_tiles > 1:
-            starts = numpy.ascontiguousarray(
-                rowPartition.blockPartition(n, args.block_tiles, *cap_tiles), numpy.int64)
+        starts, dense_runs = rowPartition.sliverBlockPartition(xyz, tri, blockTiles=args.block_tiles)
+        if dense_runs or args.block_tiles > 1:
+            starts = numpy.ascontiguousarray(starts, numpy.int64)
             ctx.check(lib.icqb_cg_set_block_partition(ctx.handle, starts.ctypes.data_as(_lib.c_int64_p),
                                                       len(starts)))
     ctx.check(lib.icqb_set_assembly_variant(ctx.handle, args.assembly_variant))

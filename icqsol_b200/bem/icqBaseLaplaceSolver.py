@@ -61,8 +61,8 @@ class BaseLaplaceSolver(BaseSolver):
         @param preconditioner of the CG solve: 'block' = inverse 128 x 128 diagonal blocks of
                        diag(A) G, 'diagonal' = 1/diag (the reference CG class's default,
                        solvers/icqConjugateGradient.py:19), 'block+caps' = EXPERIMENTAL: blocks,
-                       with one dense block over the leading and one over the trailing run of
-                       tiles that hold sliver triangles (icqRowPartition.sliverCapTiles)
+                       with one dense block over every run of tiles that hold sliver triangles
+                       (icqRowPartition.sliverBlockPartition; on a UV sphere the two poles)
         @param blockTiles EXPERIMENTAL, with 'block+caps' only: tiles (of 128 triangles) per
                        diagonal block between the caps (numpy model at config C2: 167 iterations
                        with 1, 121 with 2, 92 with 8)
@@ -116,12 +116,16 @@ class BaseLaplaceSolver(BaseSolver):
         self.ctx.check(self.lib.icqb_cg_set_preconditioner(
             self.ctx.handle, {'diagonal': 0, 'block': 1, 'block+caps': 2}[preconditioner]))
         self.capTiles = (0, 0)
+        self.denseRuns = []
         if preconditioner == 'block+caps':
+            # one dense block per run of tiles that hold slivers, wherever it lies in the list
+            # (on a UV sphere: the head and tail caps of sliverCapTiles)
             self.capTiles = rowPartition.sliverCapTiles(self._xyz, self._tri)
+            starts, self.denseRuns = rowPartition.sliverBlockPartition(
+                self._xyz, self._tri, blockTiles=int(blockTiles))
             self.ctx.check(self.lib.icqb_cg_set_cap_tiles(self.ctx.handle, *self.capTiles))
-            if int(blockTiles) > 1:
-                starts = numpy.ascontiguousarray(rowPartition.blockPartition(
-                    self.numTriangles, int(blockTiles), *self.capTiles), numpy.int64)
+            if self.denseRuns or int(blockTiles) > 1:
+                starts = numpy.ascontiguousarray(starts, numpy.int64)
                 self.ctx.check(self.lib.icqb_cg_set_block_partition(
                     self.ctx.handle, starts.ctypes.data_as(_lib.c_int64_p), len(starts)))
 

@@ -114,6 +114,85 @@ def sliverCapTiles(xyz, tri, threshold=30., maxTiles=32):
     return head, tail
 
 
+def sliverTiles(xyz, tri, threshold=30.):
+    """bool[number of 128-triangle tiles]: the tile holds a sliver, a triangle whose aspect
+    Lmax^2 / |db x dc| exceeds ``threshold``."""
+    xyz = numpy.asarray(xyz, numpy.float64)
+    tri = numpy.asarray(tri, numpy.int64)
+    n = tri.shape[0]
+    flagged = numpy.zeros((n + TILE - 1) // TILE, bool)
+    if n == 0:
+        return flagged
+    a, b, c = xyz[tri[:, 0]], xyz[tri[:, 1]], xyz[tri[:, 2]]
+    e2 = numpy.maximum.reduce([((b - a) ** 2).sum(1), ((c - b) ** 2).sum(1), ((a - c) ** 2).sum(1)])
+    area2 = numpy.sqrt((numpy.cross(b - a, c - a) ** 2).sum(1))
+    numpy.logical_or.at(flagged, numpy.arange(n) // TILE, e2 > threshold * area2)
+    return flagged
+
+
+def sliverBlockPartition(xyz, tri, blockTiles=1, threshold=30., gapTiles=4, maxTiles=64,
+                         budgetFraction=0.125, budgetFloor=6.4e7):
+    """First tile row of every diagonal block of the experimental preconditioner
+    (icqb_cg_set_block_partition) for a mesh whose slivers may sit ANYWHERE in the triangle
+    list -- e.g. the poles of the inner sphere of a hollow sphere: every run of tiles that hold
+    slivers (runs separated by at most ``gapTiles`` clean tiles are merged: on a UV sphere
+    every other triangle of a band is a sliver and whole tiles in between are clean) becomes
+    ONE dense block, cut into pieces of at most ``maxTiles`` tiles; the clean stretches get
+    blocks of ``blockTiles`` tiles.  On a UV sphere this is sliverCapTiles' head and tail cap.
+    If the dense blocks would take more than ``budgetFraction`` of the lower storage
+    (N^2 / 2 entries; at least ``budgetFloor`` entries), the gaps are no longer merged; if that is still too much, only runs
+    that reach the two ends of the list are kept.
+    @return (starts, denseRuns): list of first tile rows; [(first tile, tiles)] of the runs"""
+    flagged = sliverTiles(xyz, tri, threshold)
+    nT = flagged.shape[0]
+    k = max(int(blockTiles), 1)
+    maxTiles = max(int(maxTiles), 1)
+    if nT == 0:
+        return [0], []
+    idx = numpy.nonzero(flagged)[0]
+
+    def runsFor(gap):
+        runs = []
+        for t in idx.tolist():
+            if runs and t - runs[-1][1] <= gap + 1:
+                runs[-1][1] = t
+            else:
+                runs.append([t, t])
+        return [(a, b - a + 1) for a, b in runs]
+
+    def cost(runs):
+        total = 0
+        for a, m in runs:
+            while m > 0:
+                piece = min(m, maxTiles)
+                if piece > 1:
+                    total += (piece * TILE) ** 2
+                m -= piece
+        return total
+
+    budget = max(budgetFraction * 0.5 * float(len(tri)) ** 2, float(budgetFloor))
+    runs = runsFor(int(gapTiles))
+    if cost(runs) > budget:
+        runs = runsFor(0)
+    if cost(runs) > budget:
+        runs = [r for r in runs if r[0] == 0 or r[0] + r[1] == nT]
+    if cost(runs) > budget:
+        runs = []
+    starts, t = [], 0
+    for a, m in runs:
+        while t < a:
+            starts.append(t)
+            t = min(t + k, a)
+        end = a + m
+        while t < end:
+            starts.append(t)
+            t = min(t + maxTiles, end)
+    while t < nT:
+        starts.append(t)
+        t = min(t + k, nT)
+    return (starts or [0]), [r for r in runs if r[1] > 1]
+
+
 def blockPartition(n, blockTiles, headTiles=0, tailTiles=0):
     """First tile row of every diagonal block of the experimental preconditioner: a cap of
     headTiles, blocks of blockTiles, a cap of tailTiles (icqb_cg_set_block_partition)."""

@@ -309,3 +309,38 @@ def test_block_partition():
     assert rp.blockPartition(1280, 1, 10, 0) == [0]           # one cap over everything
     assert rp.blockPartition(1280, 3, 0, 2) == [0, 3, 6, 8]
     assert rp.blockPartition(1280, 1) == list(range(10))
+
+
+def test_sliver_block_partition_general_position():
+    """One dense block per run of sliver tiles wherever it lies: the two caps on a UV sphere
+    (same partition as sliverCapTiles + blockPartition), the inner sphere's poles in the MIDDLE
+    of a hollow sphere's triangle list, nothing on the bolt's isolated slivers; the memory
+    budget drops merged gaps first, then everything but the two ends."""
+    from icqsol_b200.bem import icqRowPartition as rp
+    from icqsol_b200.mesh import generators as gen
+    for nt, nph in ((318, 20), (448, 12), (142, 71)):
+        xyz, tri = gen.uvSphere(1.0, nt, nph)
+        head, tail = rp.sliverCapTiles(xyz, tri)
+        for k in (1, 8):
+            starts, runs = rp.sliverBlockPartition(xyz, tri, blockTiles=k)
+            assert starts == rp.blockPartition(tri.shape[0], k, head, tail), (nt, nph, k)
+            assert [m for _, m in runs] == [t for t in (head, tail) if t > 1]
+    xyz, tri = gen.hollowSphere(2.0, 1.0, 100, 50)
+    nT = (tri.shape[0] + 127) // 128
+    starts, runs = rp.sliverBlockPartition(xyz, tri, blockTiles=4)
+    assert runs == [(76, 6), (381, 5)] and rp.sliverCapTiles(xyz, tri) == (0, 5)
+    assert starts[:3] == [0, 4, 8] and 76 in starts and 82 in starts and 77 not in starts
+    assert starts[-1] == 381 and starts == sorted(set(starts)) and starts[-1] < nT
+    sizes = numpy.diff(starts + [nT])
+    assert sizes.max() == 6 and (sizes >= 1).all()
+    # long runs are cut into pieces of maxTiles
+    starts, runs = rp.sliverBlockPartition(xyz, tri, maxTiles=4)
+    assert 76 in starts and 80 in starts and 82 in starts
+    # budget: a tiny one keeps nothing in the middle, then nothing at all
+    starts, runs = rp.sliverBlockPartition(xyz, tri, budgetFraction=6.5e-4, budgetFloor=0)
+    assert runs == [(76, 6), (381, 2), (384, 2)]          # gaps no longer merged
+    starts, runs = rp.sliverBlockPartition(xyz, tri, budgetFraction=4e-4, budgetFloor=0)
+    assert runs == [(384, 2)]                             # only what reaches an end of the list
+    starts, runs = rp.sliverBlockPartition(xyz, tri, budgetFraction=1e-6, budgetFloor=0)
+    assert runs == [] and starts == list(range(nT))
+    assert rp.sliverBlockPartition(numpy.zeros((0, 3)), numpy.zeros((0, 3), int)) == ([0], [])
