@@ -284,7 +284,7 @@ def test_emulated_subdivide(emu, golden, k, f32):
     c.close()
 
 
-def _run_ranks(emu, nranks, n_theta, n_phi, storage, kind, caps=None, peer=False):
+def _run_ranks(emu, nranks, n_theta, n_phi, storage, kind, caps=None, peer=False, starts=None):
     """One rank per thread (ctypes releases the GIL), the in-process NCCL stand-in of
     tools/emu underneath: folded row blocks, sharded assembly, distributed CG.  peer=True
     also sets up the experimental peer exchange (handles swapped through a shared list)."""
@@ -317,7 +317,7 @@ def _run_ranks(emu, nranks, n_theta, n_phi, storage, kind, caps=None, peer=False
                 g = dev_array(emu, (max(r1 - r0, 1), ld), 0.)
                 c.check(emu.icqb_set_rows(c.h, r0, r1))
                 c.check(emu.icqb_assemble_dev(c.h, 5, g.ctypes.data, 0, ld))
-            out[rank] = c.solve(g, storage, kind, caps, ld=ld) + (c,)
+            out[rank] = c.solve(g, storage, kind, caps, ld=ld, starts=starts) + (c,)
         except Exception as e:    # noqa: BLE001 -- reported by the caller
             errors.append((rank, repr(e)))
     threads = [threading.Thread(target=work, args=(r,)) for r in range(nranks)]
@@ -588,3 +588,29 @@ def test_emulated_kernels_under_other_thread_orders(order):
          'far_field_split_lower or block_partition or subdivide or gemv'],
         capture_output=True, text=True, env=env, timeout=1200, cwd=ROOT)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
+
+
+@pytest.mark.parametrize('nranks,storage,caps,starts,peer,cuts', [
+    (2, 1, (1, 2), None, True, [0, 128, 256]),        # caps + peer exchange
+    (4, 1, (1, 1), None, True, [0, 128, 256, 384]),   # four ranks, two of them with one strip
+    (2, 1, None, [0, 2], False, [0, 256]),            # explicit partition, all-reduced dense blocks
+    (3, 0, None, [0, 1, 3], False, [0, 128, 384]),    # row blocks, three ranks
+    (3, 1, None, [0, 3], True, [0, 384])])            # partition + peer exchange
+def test_emulated_multi_rank_experimental_combinations(emu, oracle_mod, nranks, storage, caps, starts,
+                                                       peer, cuts):
+    """EXPERIMENTAL solver, the combinations its first GPU visit will run (tests/dist_worker.py
+    with ICQB_EXPERIMENTAL / ICQB_PEER_EXCHANGE): dense blocks are extracted from the rows each
+    rank stores and all-reduced, every rank applies them; same solution and iteration count on
+    every rank, the count of the numpy model of the same blocks."""
+    out = _run_ranks(emu, nranks, 20, 11, storage, 2, caps, peer, starts)     # 400 triangles
+    c = out[0][-1]
+    ref = oracle_mod.green_matrix(c.xyz, c.tri, 5)
+    a2 = oracle_mod.area2(c.xyz, c.tri)
+    x0, iters0, _, b, _ = out[0]
+    for x, iters, rinf, _, _ in out:
+        assert (x == x0).all() and iters == iters0
+        assert rinf <= 5e-13 * numpy.abs(b).max()
+    assert numpy.abs(b - ref.dot(x0)).max() <= 1e-12 * numpy.abs(b).max()
+    assert abs(iters0 - model_iterations(ref, a2, b, cuts)) <= 1
+    for o in out:
+        o[-1].close()
