@@ -155,14 +155,16 @@ class BaseLaplaceSolver(BaseSolver):
         self.kMatDevice = None
         self.kMatUpperDevice = None
         if storage == 'lower':
-            # tile-contiguous lower triangle: [numTiles, 128, 128]; zero-filled because the
-            # ragged edge tiles are only partly written
+            # tile-contiguous lower triangle: [numTiles, 128, 128].  Not zero-filled (a 4N^2-byte
+            # memset per matrix): the ragged edge tiles are only partly written, and every
+            # reader masks rows and columns beyond N (k_symv, k_cg_blocks_lower,
+            # k_dense_extract_lower, lowerTilesToRows) -- the parity tests run on NaN-filled tiles
             self.numLocalTiles = int(self.lib.icqb_lower_num_tiles(self.ctx.handle))
             shape = (max(self.numLocalTiles, 1), rowPartition.TILE, rowPartition.TILE)
-            self.gMatDevice = torch.zeros(shape, dtype=torch.float64, device=dev)
+            self.gMatDevice = torch.empty(shape, dtype=torch.float64, device=dev)
             if computeK:
-                self.kMatDevice = torch.zeros(shape, dtype=torch.float64, device=dev)
-                self.kMatUpperDevice = torch.zeros(shape, dtype=torch.float64, device=dev)
+                self.kMatDevice = torch.empty(shape, dtype=torch.float64, device=dev)
+                self.kMatUpperDevice = torch.empty(shape, dtype=torch.float64, device=dev)
         else:
             rows = max(self.numLocalRows, 1)
             self.gMatDevice = torch.empty((rows, self.ld), dtype=torch.float64, device=dev)
@@ -248,7 +250,8 @@ class BaseLaplaceSolver(BaseSolver):
         """The part of G resident in this rank's HBM (a torch float64 view).
         storage='full': rows [rowBegin, rowEnd) complete, float64[rows, N].
         storage='lower': float64[numLocalTiles, 128, 128], the tile-contiguous lower
-        triangle of the rows in getRowBlocks() (icqRowPartition.lowerStrips gives the
+        triangle of the rows in getRowBlocks(); entries of the edge tiles beyond row/column N
+        are unspecified (icqRowPartition.lowerStrips gives the
         strip -> tile map; icqRowPartition.lowerTilesToRows rebuilds rows on the host)."""
         if self.storage == 'lower':
             return self.gMatDevice[:self.numLocalTiles]
