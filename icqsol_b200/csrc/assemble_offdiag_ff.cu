@@ -416,7 +416,7 @@ int launch_offdiag_ff(icqb_ctx* ctx, const OffDiagParams& params, dim3 grid, boo
     OffDiagParams P = params;
     const long long nalloc = ctx->ntri_pad + kPad;
     if (!ctx->d_bound) {
-        ICQB_CUDA(ctx, cudaMalloc(&ctx->d_bound, sizeof(double) * 4 * nalloc));
+        ICQB_CUDA(ctx, dev_alloc(ctx, &ctx->d_bound, sizeof(double) * 4 * nalloc));
         k_bounds<<<(unsigned)((nalloc + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_verts, ctx->ntri,
                                                                             nalloc, ctx->d_bound);
         ctx->launches += 1;

@@ -44,12 +44,41 @@ int lower_layout(icqb_ctx* ctx, LowerLayout* L) {
     return ICQB_OK;
 }
 
+static bool pool_alloc() {
+    static const bool on = [] {
+        const char* e = getenv("ICQB_POOL_ALLOC");
+        return e && e[0] == '1';
+    }();
+    return on;
+}
+
+cudaError_t dev_alloc_raw(icqb_ctx* ctx, void** p, size_t bytes) {
+    if (!pool_alloc()) return cudaMalloc(p, bytes);
+    static std::once_flag once;
+    std::call_once(once, [ctx] {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) {
+            unsigned long long keep = ~0ULL;   // never hand freed blocks back to the driver
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    });
+    return cudaMallocAsync(p, bytes, ctx->stream);
+}
+
+void dev_free(icqb_ctx* ctx, void* p) {
+    if (!p) return;
+    if (pool_alloc())
+        cudaFreeAsync(p, ctx->stream);
+    else
+        cudaFree(p);
+}
+
 int ensure_work(icqb_ctx* ctx, int64_t doubles) {
     if (doubles <= ctx->work_doubles) return ICQB_OK;
-    if (ctx->d_work) cudaFree(ctx->d_work);
+    dev_free(ctx, ctx->d_work);
     ctx->d_work = nullptr;
     ctx->work_doubles = 0;
-    ICQB_CUDA(ctx, cudaMalloc(&ctx->d_work, sizeof(double) * doubles));
+    ICQB_CUDA(ctx, dev_alloc(ctx, &ctx->d_work, sizeof(double) * doubles));
     ctx->work_doubles = doubles;
     return ICQB_OK;
 }
@@ -116,14 +145,14 @@ __global__ void k_prepare(const double* __restrict__ xyz, const int64_t* __restr
 }
 
 void free_mesh(icqb_ctx* ctx) {
-    cudaFree(ctx->d_xyz);
-    cudaFree(ctx->d_tri);
-    cudaFree(ctx->d_verts);
-    cudaFree(ctx->d_qp_soa);
-    cudaFree(ctx->d_qp_aos);
-    cudaFree(ctx->d_area2);
-    cudaFree(ctx->d_nrm);
-    cudaFree(ctx->d_bound);
+    dev_free(ctx, ctx->d_xyz);
+    dev_free(ctx, ctx->d_tri);
+    dev_free(ctx, ctx->d_verts);
+    dev_free(ctx, ctx->d_qp_soa);
+    dev_free(ctx, ctx->d_qp_aos);
+    dev_free(ctx, ctx->d_area2);
+    dev_free(ctx, ctx->d_nrm);
+    dev_free(ctx, ctx->d_bound);
     ctx->d_bound = nullptr;
     ctx->d_xyz = ctx->d_verts = ctx->d_qp_soa = ctx->d_qp_aos = ctx->d_area2 = ctx->d_nrm = nullptr;
     ctx->d_tri = nullptr;
@@ -198,7 +227,8 @@ int icqb_destroy(icqb_ctx* ctx) {
     symv_plan_free(ctx);
     free_mesh(ctx);
     cudaFree(ctx->d_ffstats);
-    cudaFree(ctx->d_work);
+    dev_free(ctx, ctx->d_work);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);   // stream-ordered frees (ICQB_POOL_ALLOC)
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -253,13 +283,13 @@ int icqb_set_mesh(icqb_ctx* ctx, const double* xyz, int64_t npts, const int64_t*
     for (int64_t k = 0; k < 3 * npts; ++k) ctx->coord_max = fmax(ctx->coord_max, fabs(xyz[k]));
     if (ntri == 0) return ICQB_OK;
     const int64_t nalloc = ctx->ntri_pad + kPad;
-    ICQB_CUDA(ctx, cudaMalloc(&ctx->d_xyz, sizeof(double) * 3 * (npts > 0 ? npts : 1)));
-    ICQB_CUDA(ctx, cudaMalloc(&ctx->d_tri, sizeof(int64_t) * 3 * ntri));
-    ICQB_CUDA(ctx, cudaMalloc(&ctx->d_verts, sizeof(double) * 9 * ntri));
-    ICQB_CUDA(ctx, cudaMalloc(&ctx->d_qp_soa, sizeof(double) * kQpStride * ctx->ntri_pad));
-    ICQB_CUDA(ctx, cudaMalloc(&ctx->d_qp_aos, sizeof(double) * kQpStride * nalloc));
-    ICQB_CUDA(ctx, cudaMalloc(&ctx->d_area2, sizeof(double) * nalloc));
-    ICQB_CUDA(ctx, cudaMalloc(&ctx->d_nrm, sizeof(double) * 4 * nalloc));
+    ICQB_CUDA(ctx, dev_alloc(ctx, &ctx->d_xyz, sizeof(double) * 3 * (npts > 0 ? npts : 1)));
+    ICQB_CUDA(ctx, dev_alloc(ctx, &ctx->d_tri, sizeof(int64_t) * 3 * ntri));
+    ICQB_CUDA(ctx, dev_alloc(ctx, &ctx->d_verts, sizeof(double) * 9 * ntri));
+    ICQB_CUDA(ctx, dev_alloc(ctx, &ctx->d_qp_soa, sizeof(double) * kQpStride * ctx->ntri_pad));
+    ICQB_CUDA(ctx, dev_alloc(ctx, &ctx->d_qp_aos, sizeof(double) * kQpStride * nalloc));
+    ICQB_CUDA(ctx, dev_alloc(ctx, &ctx->d_area2, sizeof(double) * nalloc));
+    ICQB_CUDA(ctx, dev_alloc(ctx, &ctx->d_nrm, sizeof(double) * 4 * nalloc));
     ICQB_CUDA(ctx, cudaMemcpyAsync(ctx->d_xyz, xyz, sizeof(double) * 3 * npts,
                                    cudaMemcpyHostToDevice, ctx->stream));
     ICQB_CUDA(ctx, cudaMemcpyAsync(ctx->d_tri, tri, sizeof(int64_t) * 3 * ntri,

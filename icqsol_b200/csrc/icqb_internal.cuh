@@ -163,6 +163,17 @@ int set_error(icqb_ctx* ctx, int code, const std::string& msg);
 int lower_layout(icqb_ctx* ctx, LowerLayout* L);
 int check_cuda(icqb_ctx* ctx, cudaError_t e, const char* what);
 int ensure_work(icqb_ctx* ctx, int64_t doubles);
+// Device buffers of the context (mesh tables, work space, product plan).  Default: cudaMalloc /
+// cudaFree.  EXPERIMENTAL, with ICQB_POOL_ALLOC=1 in the environment: cudaMallocAsync /
+// cudaFreeAsync on the context's stream from the device's default memory pool with an unlimited
+// release threshold, so that a process that builds one solver after the other (bench.py's
+// end-to-end loop) gets its ~20 buffers back from the pool instead of from the driver.
+cudaError_t dev_alloc_raw(icqb_ctx* ctx, void** p, size_t bytes);
+void dev_free(icqb_ctx* ctx, void* p);
+template <class T>
+inline cudaError_t dev_alloc(icqb_ctx* ctx, T** p, size_t bytes) {
+    return dev_alloc_raw(ctx, reinterpret_cast<void**>(p), bytes);
+}
 
 // kernels' host launchers (each returns ICQB_OK or sets the context error)
 int launch_prepare(icqb_ctx* ctx);

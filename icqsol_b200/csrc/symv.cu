@@ -435,13 +435,13 @@ struct SymvPlan {
 void symv_plan_free(icqb_ctx* ctx) {
     SymvPlan* p = ctx->symv;
     if (!p) return;
-    cudaFree(p->d_tasks);
-    cudaFree(p->d_Wc);
-    cudaFree(p->d_Wr);
-    cudaFree(p->d_Wh);
-    cudaFree(p->d_headSlot);
-    cudaFree(p->d_headColBegin);
-    cudaFree(p->d_headColSlots);
+    dev_free(ctx, p->d_tasks);
+    dev_free(ctx, p->d_Wc);
+    dev_free(ctx, p->d_Wr);
+    dev_free(ctx, p->d_Wh);
+    dev_free(ctx, p->d_headSlot);
+    dev_free(ctx, p->d_headColBegin);
+    dev_free(ctx, p->d_headColSlots);
     delete p;
     ctx->symv = nullptr;
 }
@@ -494,13 +494,13 @@ static int symv_plan(icqb_ctx* ctx) {
         std::vector<int> fill(headColBegin.begin(), headColBegin.end() - 1);
         for (int sidx = 0; sidx < slots; ++sidx) headColSlots[(size_t)fill[(size_t)slotCol[sidx]]++] = sidx;
     }
-    ICQB_CUDA(ctx, cudaMalloc(&p->d_tasks, sizeof(SymvTask) * tasks.size()));
-    ICQB_CUDA(ctx, cudaMalloc(&p->d_Wc, sizeof(double) * (size_t)L.nLocal() * p->wcols));
-    ICQB_CUDA(ctx, cudaMalloc(&p->d_Wr, sizeof(double) * (size_t)p->nTasks * kT));
-    ICQB_CUDA(ctx, cudaMalloc(&p->d_Wh, sizeof(double) * (size_t)std::max(slots, 1) * kT));
-    ICQB_CUDA(ctx, cudaMalloc(&p->d_headSlot, sizeof(int) * headSlot.size()));
-    ICQB_CUDA(ctx, cudaMalloc(&p->d_headColBegin, sizeof(int) * headColBegin.size()));
-    ICQB_CUDA(ctx, cudaMalloc(&p->d_headColSlots, sizeof(int) * headColSlots.size()));
+    ICQB_CUDA(ctx, dev_alloc(ctx, &p->d_tasks, sizeof(SymvTask) * tasks.size()));
+    ICQB_CUDA(ctx, dev_alloc(ctx, &p->d_Wc, sizeof(double) * (size_t)L.nLocal() * p->wcols));
+    ICQB_CUDA(ctx, dev_alloc(ctx, &p->d_Wr, sizeof(double) * (size_t)p->nTasks * kT));
+    ICQB_CUDA(ctx, dev_alloc(ctx, &p->d_Wh, sizeof(double) * (size_t)std::max(slots, 1) * kT));
+    ICQB_CUDA(ctx, dev_alloc(ctx, &p->d_headSlot, sizeof(int) * headSlot.size()));
+    ICQB_CUDA(ctx, dev_alloc(ctx, &p->d_headColBegin, sizeof(int) * headColBegin.size()));
+    ICQB_CUDA(ctx, dev_alloc(ctx, &p->d_headColSlots, sizeof(int) * headColSlots.size()));
     ICQB_CUDA(ctx, cudaMemcpy(p->d_tasks, tasks.data(), sizeof(SymvTask) * tasks.size(),
                               cudaMemcpyHostToDevice));
     ICQB_CUDA(ctx, cudaMemcpy(p->d_headSlot, headSlot.data(), sizeof(int) * headSlot.size(),

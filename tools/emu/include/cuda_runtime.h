@@ -182,6 +182,21 @@ static inline cudaError_t cudaMallocHost(T** p, size_t bytes) {
     return emuMalloc(reinterpret_cast<void**>(p), bytes);
 }
 cudaError_t cudaFree(void* p);
+// stream-ordered allocation (ICQB_POOL_ALLOC): the same allocator, synchronously
+typedef struct emuMemPool* cudaMemPool_t;
+enum cudaMemPoolAttr { cudaMemPoolAttrReleaseThreshold = 4 };
+static inline cudaError_t cudaDeviceGetDefaultMemPool(cudaMemPool_t* pool, int) {
+    *pool = nullptr;
+    return cudaSuccess;
+}
+static inline cudaError_t cudaMemPoolSetAttribute(cudaMemPool_t, cudaMemPoolAttr, void*) {
+    return cudaSuccess;
+}
+template <class T>
+static inline cudaError_t cudaMallocAsync(T** p, size_t bytes, cudaStream_t) {
+    return emuMalloc(reinterpret_cast<void**>(p), bytes);
+}
+static inline cudaError_t cudaFreeAsync(void* p, cudaStream_t) { return cudaFree(p); }
 cudaError_t cudaFreeHost(void* p);
 cudaError_t cudaMemcpy(void* dst, const void* src, size_t bytes, cudaMemcpyKind);
 cudaError_t cudaMemcpyAsync(void* dst, const void* src, size_t bytes, cudaMemcpyKind, cudaStream_t = nullptr);

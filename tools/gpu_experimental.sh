@@ -28,6 +28,19 @@ except Exception as e:
     print('no bench line:', e)
 PY
   done
+  # stream-ordered pool allocation of the context's buffers: end-to-end time with and without
+  for pool in 0 1; do
+    ICQB_POOL_ALLOC=$pool timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --e2e-steps 4 \
+        > $out/${tag}_exp_bench_pool$pool.json 2> $out/${tag}_exp_bench_pool$pool.err
+    echo "bench ICQB_POOL_ALLOC=$pool rc=$?"; python - <<PY
+import json
+try:
+    d = json.load(open('$out/${tag}_exp_bench_pool$pool.json'))
+    print('pool $pool: e2e %.2f ms, step %.2f ms, host phases %s' % (d['e2e']['ms_per_step'], d['ms_per_step'], d['e2e'].get('host_phases_ms')))
+except Exception as e:
+    print('no bench line:', e)
+PY
+  done
   timeout 300 ncu --set full --clock-control none --import-source on -k regex:'k_offdiag_ff' -s 1 -c 1 \
       -o $out/${tag}_exp_offdiag_ff1 -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline --e2e-steps 0 \
       --assembly-variant 1 > $out/${tag}_exp_ncu_offdiag_ff1.log 2>&1; echo "ncu offdiag_ff rc=$?"
