@@ -309,6 +309,7 @@ def run_b200(args):
             ctx.check(lib.icqb_cg_set_block_partition(ctx.handle, starts.ctypes.data_as(_lib.c_int64_p),
                                                       len(starts)))
     ctx.check(lib.icqb_set_assembly_variant(ctx.handle, args.assembly_variant))
+    ctx.check(lib.icqb_cg_set_mixed_precision(ctx.handle, args.mixed_switch))
     ctx.check(lib.icqb_set_mesh(ctx.handle, xyz.ctypes.data_as(_lib.c_double_p), xyz.shape[0],
                                 tri.ctypes.data_as(_lib.c_int64_p), n))
     lower = args.storage == 'lower'
@@ -351,7 +352,7 @@ def run_b200(args):
     torch.cuda.synchronize(dev)
 
     phase = {'assembly_ms': [], 'offdiag_ms': [], 'diag_ms': [], 'solve_ms': [], 'gemv_ms': [],
-             'iters': [], 'resid': [], 'residinf': [], 'replacements': [], 'products': []}
+             'iters': [], 'resid': [], 'residinf': [], 'replacements': [], 'products': [], 'products32': []}
 
     def step(record):
         with torch.cuda.stream(stream):
@@ -381,6 +382,9 @@ def run_b200(args):
             rep, prod = ctx.cg_stats()
             phase['replacements'].append(rep)
             phase['products'].append(prod)
+            n32 = ctypes.c_int64(0)
+            ctx.check(lib.icqb_cg_last_mixed(ctx.handle, ctypes.byref(n32)))
+            phase['products32'].append(n32.value)
 
     def barrier():
         if world > 1:
@@ -424,7 +428,8 @@ def run_b200(args):
         t0 = time.perf_counter()
         solver = LaplaceSolver(pd, float('inf'), 5, computeK=True, device=local,
                                storage=args.storage, preconditioner=args.preconditioner,
-                               blockTiles=args.block_tiles, assemblyVariant=args.assembly_variant)
+                               blockTiles=args.block_tiles, assemblyVariant=args.assembly_variant,
+                               mixedPrecision=args.mixed_switch)
         solver.setSolverMaxNumberOfIterations(args.max_iters)
         rsp = solver.computeResponseField()
         torch.cuda.synchronize(dev)
@@ -476,7 +481,7 @@ def run_b200(args):
                        'step': 'fused G+K assembly + CG solve (max|v+G sigma| <= 5e-13 max|v|)',
                        'rows_per_gpu': rows, 'storage': args.storage,
                        'preconditioner': args.preconditioner, 'cap_tiles': list(cap_tiles), 'block_tiles': args.block_tiles,
-                       'assembly_variant': args.assembly_variant,
+                       'assembly_variant': args.assembly_variant, 'mixed_switch': args.mixed_switch,
                        'parallelism': ('folded row blocks, lower storage x{0}' if lower
                                        else 'row-block x{0}').format(world),
                        'l2': 'inputs larger than L2 ({0:.2f} GB of G streamed per product per GPU)'.format(
@@ -489,6 +494,7 @@ def run_b200(args):
                        'cg_iters': int(numpy.mean(phase['iters'])),
                        'cg_residual_replacements': int(numpy.max(phase['replacements'])),
                        'cg_products_enqueued': int(numpy.mean(phase['products'])),
+                       'cg_float32_products': int(numpy.mean(phase['products32'])),
                        'cg_converged': bool(numpy.max(phase['residinf']) <= 1e-12 * numpy.abs(v).max()),
                        'cg_residual2': float(numpy.max(phase['resid'])),
                        'cg_backward_error_max_norm': float(numpy.max(phase['residinf']) / numpy.abs(v).max()),
@@ -567,6 +573,9 @@ def main():
                     help='experimental arithmetic of the off-diagonal kernel (include/icqb.h, '
                          'icqb_set_assembly_variant): 0 validated kernel, 1 far-field split, '
                          '2 far-field split + Newton reciprocal square root')
+    ap.add_argument('--mixed-switch', type=float, default=0.,
+                    help='experimental, with block+caps and lower storage: relative residual below '
+                         'which the CG products stream a float32 copy of the matrix (1e-6); 0 = off')
     ap.add_argument('--max-iters', type=int, default=4000,
                     help='CG iteration cap (a solve that needs more is reported as not converged)')
     ap.add_argument('--no-cpu-baseline', action='store_true')

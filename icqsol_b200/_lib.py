@@ -46,6 +46,7 @@ SIGNATURES = [
     ('icqb_assembly_stats', c_int, [c_void_p, c_int64_p, c_int64_p]),
     ('icqb_assemble_lower_dev', c_int, [c_void_p, c_int, c_uint64, c_uint64, c_uint64]),
     ('icqb_symv_dev', c_int, [c_void_p, c_uint64, c_uint64, c_uint64, c_int]),
+    ('icqb_symv_f32_dev', c_int, [c_void_p, c_uint64, c_uint64, c_uint64, c_int]),
     ('icqb_assemble_host', c_int, [c_void_p, c_int, c_double_p, c_double_p]),
     ('icqb_diagonal_host', c_int, [c_void_p, c_int, c_double_p]),
     ('computeOffDiagonalTermsArrays', c_int, [c_double_p, c_int64, c_int64_p, c_int64, c_double_p]),
@@ -60,6 +61,8 @@ SIGNATURES = [
     ('icqb_cg_set_cap_tiles', c_int, [c_void_p, c_int64, c_int64]),
     ('icqb_cg_set_block_partition', c_int, [c_void_p, c_int64_p, c_int64]),
     ('icqb_cg_last_stats', c_int, [c_void_p, c_int64_p, c_int64_p]),
+    ('icqb_cg_set_mixed_precision', c_int, [c_void_p, c_double]),
+    ('icqb_cg_last_mixed', c_int, [c_void_p, c_int64_p]),
     ('icqb_comm_unique_id', c_int, [c_void_p]),
     ('icqb_comm_init', c_int, [c_void_p, c_void_p, c_int, c_int]),
     ('icqb_comm_share', c_int, [c_void_p, c_void_p]),

@@ -46,7 +46,7 @@ class BaseLaplaceSolver(BaseSolver):
 
     def __init__(self, pdata, max_edge_length, order=5, computeK=False, device=None,
                  storage='lower', preconditioner='block', blockTiles=1, assemblyVariant=None,
-                 directFallback=False):
+                 directFallback=False, mixedPrecision=0.):
         """
         Constructor
         @param pdata polydata (vtkPolyData or stand-in)
@@ -66,6 +66,10 @@ class BaseLaplaceSolver(BaseSolver):
         @param blockTiles EXPERIMENTAL, with 'block+caps' only: tiles (of 128 triangles) per
                        diagonal block between the caps (numpy model at config C2: 167 iterations
                        with 1, 121 with 2, 92 with 8)
+        @param mixedPrecision EXPERIMENTAL, with 'block+caps' and storage='lower' only: relative
+                       residual below which the products of the CG stream a float32 copy of
+                       the matrix (include/icqb.h, icqb_cg_set_mixed_precision; 1e-6 saves a
+                       quarter of the matrix traffic in the numpy model); 0 = off
         @param directFallback EXPERIMENTAL: when the CG stops short of the requested backward
                        error (one rank only), solve by LU instead (solveGreenSystemDirect) --
                        what the reference does in the first place (bem/icqLaplaceSolver.py:36)
@@ -115,6 +119,7 @@ class BaseLaplaceSolver(BaseSolver):
 
         self.ctx.check(self.lib.icqb_cg_set_preconditioner(
             self.ctx.handle, {'diagonal': 0, 'block': 1, 'block+caps': 2}[preconditioner]))
+        self.ctx.check(self.lib.icqb_cg_set_mixed_precision(self.ctx.handle, float(mixedPrecision)))
         self.capTiles = (0, 0)
         self.denseRuns = []
         if preconditioner == 'block+caps':
@@ -330,6 +335,9 @@ class BaseLaplaceSolver(BaseSolver):
                               'gemvMilliseconds': self.ctx.last_ms(3)}
         self.lastSolveInfo['residualReplacements'], self.lastSolveInfo['products'] = \
             self.ctx.cg_stats()
+        n32 = ctypes.c_int64(0)
+        self.ctx.check(self.lib.icqb_cg_last_mixed(self.ctx.handle, ctypes.byref(n32)))
+        self.lastSolveInfo['float32Products'] = n32.value
         # the reference's LU (bem/icqLaplaceSolver.py:36) cannot "not converge"; say so loudly
         # when the iteration stopped short of the requested backward error (iteration cap,
         # attainable accuracy, or a matrix the quadrature left too indefinite for CG)

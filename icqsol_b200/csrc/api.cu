@@ -143,6 +143,44 @@ int icqb_symv_dev(icqb_ctx* ctx, uint64_t dA, uint64_t dx, uint64_t dy, int scal
     return finish_phase(ctx, kGemv);
 }
 
+int icqb_symv_f32_dev(icqb_ctx* ctx, uint64_t dA, uint64_t dx, uint64_t dy, int scaled) {
+    if (!ctx) return ICQB_EARG;
+    if (!dA || !dx || !dy) return set_error(ctx, ICQB_EARG, "icqb_symv_f32_dev: null pointer");
+    if (!ctx->d_area2) return set_error(ctx, ICQB_ESTATE, "icqb_symv_f32_dev: no mesh set");
+    ICQB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int64_t n = ctx->ntri;
+    LowerLayout L;
+    int st = lower_layout(ctx, &L);
+    if (st != ICQB_OK) return st;
+    const long long count = L.numTiles() * kLowerTileElems;
+    if (count > ctx->a32_floats) {
+        dev_free(ctx, ctx->d_A32);
+        ctx->d_A32 = nullptr;
+        ctx->a32_floats = 0;
+        ICQB_CUDA(ctx, dev_alloc(ctx, &ctx->d_A32, sizeof(float) * (size_t)(count > 4 ? count : 4)));
+        ctx->a32_floats = count;
+    }
+    st = launch_f64_to_f32(ctx, reinterpret_cast<const double*>(dA), ctx->d_A32, count, ctx->stream);
+    if (st != ICQB_OK) return st;
+    double* inv = nullptr;
+    if (!scaled) {
+        st = ensure_work(ctx, n + 64);
+        if (st != ICQB_OK) return st;
+        inv = ctx->d_work;
+        st = launch_reciprocal(ctx, ctx->d_area2, inv, n);
+        if (st != ICQB_OK) return st;
+    }
+    cudaEventRecord(ctx->ev0, ctx->stream);
+    st = launch_symv_f32_only(ctx, ctx->d_A32, reinterpret_cast<const double*>(dx), ctx->d_area2,
+                              scaled ? ctx->d_area2 : nullptr, scaled ? nullptr : inv,
+                              reinterpret_cast<double*>(dy), ctx->stream);
+    cudaEventRecord(ctx->ev1, ctx->stream);
+    if (st != ICQB_OK) return st;
+    st = comm_allreduce_sum(ctx, reinterpret_cast<double*>(dy), n, ctx->stream);
+    if (st != ICQB_OK) return st;
+    return finish_phase(ctx, kGemv);
+}
+
 int icqb_assemble_host(icqb_ctx* ctx, int diag_order, double* gMat, double* kMat) {
     if (!ctx || !gMat) return set_error(ctx, ICQB_EARG, "icqb_assemble_host: null output");
     const int64_t rows = ctx->r1 - ctx->r0, n = ctx->ntri;

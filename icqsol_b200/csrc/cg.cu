@@ -51,6 +51,20 @@ extern "C" int icqb_cg_set_cap_tiles(icqb_ctx* ctx, int64_t head_tiles, int64_t 
     return ICQB_OK;
 }
 
+extern "C" int icqb_cg_set_mixed_precision(icqb_ctx* ctx, double switch_rel) {
+    if (!ctx) return ICQB_EARG;
+    if (!(switch_rel >= 0.0) || switch_rel >= 1.0)
+        return set_error(ctx, ICQB_EARG, "icqb_cg_set_mixed_precision: need 0 <= switch_rel < 1");
+    ctx->mixed_switch = switch_rel;
+    return ICQB_OK;
+}
+
+extern "C" int icqb_cg_last_mixed(const icqb_ctx* ctx, int64_t* products32) {
+    if (!ctx) return ICQB_EARG;
+    if (products32) *products32 = ctx->cg_products32;
+    return ICQB_OK;
+}
+
 extern "C" int icqb_cg_set_block_partition(icqb_ctx* ctx, const int64_t* starts, int64_t nblocks) {
     if (!ctx) return ICQB_EARG;
     if (nblocks < 0 || (nblocks > 0 && (!starts || starts[0] != 0)))

@@ -291,6 +291,15 @@ __global__ void __launch_bounds__(256) k_dense_apply(const DenseDesc* desc, int 
     if (lane == 0) y[g0 + lr] = acc;
 }
 
+// mixed-precision fields of the state (switch_thr 0: float32 products off)
+__global__ void k_cg_mixed(CgState* s, double switch_thr) {
+    s->lowp = 0;
+    s->n32 = 0;
+    s->switch_thr = switch_thr;
+    s->skip64 = s->done;
+    s->skip32 = 1;
+}
+
 // first half of k_cg_resid: the vector update only
 __global__ void __launch_bounds__(kT) k_cg_vec(int mode, int k, int replace, const double* b,
                                                const double* scale, double* x, CgBuf B) {
@@ -418,6 +427,12 @@ __global__ void __launch_bounds__(kVThreads) k_cg_close(int mode, int k, int rep
             S->resmax = resmax;
             S->iters += 1;
             if ((S->use_max ? resmax : res2) <= S->thr) S->done = 1;
+            // mixed precision: this iteration's product was a float32 one if lowp was set;
+            // from the first residual below switch_thr on, the products read the float32 copy
+            if (S->lowp) S->n32 += 1;
+            if (S->switch_thr > 0.0 && resmax <= S->switch_thr) S->lowp = 1;
+            S->skip64 = S->done | S->lowp;
+            S->skip32 = S->done | (S->lowp ^ 1);
         } else if (mode == kInit) {
             S->rho[0] = rho;
             S->beta = 0.0;
@@ -572,6 +587,9 @@ int cg_solve_caps(icqb_ctx* ctx, uint64_t dA_, int64_t n, int64_t ld, int storag
     const int* skip = reinterpret_cast<const int*>(B.state);   // &state->done
     CgState* hslot = reinterpret_cast<CgState*>(ctx->h_pinned);
 
+    const bool mixedOn = (ctx->mixed_switch > 0.0) && storage == 1;   // float32 late products
+    long long products32 = 0;
+
     // w = M^-1 r and the closing step, after r has been updated by k_cg_vec
     auto precondition = [&](int mode, int kk, int replace, const int* skipFlag) -> int {
         const bool needW = (mode != kTrue) || replace;
@@ -601,12 +619,25 @@ int cg_solve_caps(icqb_ctx* ctx, uint64_t dA_, int64_t n, int64_t ld, int storag
                 // ranks is formed by the gather kernel
                 SymvFuse f2 = fuse;
                 f2.pz = B.z + n;
-                r2 = launch_symv(ctx, A, B.p, mv.area, scale ? mv.area : nullptr,
-                                 scale ? nullptr : mv.inv_area, B.z, st, skip, &f2, &X);
+                if (mixedOn)
+                    r2 = launch_symv_mixed(ctx, A, ctx->d_A32, B.p, mv.area, scale ? mv.area : nullptr,
+                                           scale ? nullptr : mv.inv_area, B.z, st, skip,
+                                           &B.state->skip64, &B.state->skip32, &f2, &X);
+                else
+                    r2 = launch_symv(ctx, A, B.p, mv.area, scale ? mv.area : nullptr,
+                                     scale ? nullptr : mv.inv_area, B.z, st, skip, &f2, &X);
                 if (r2 != ICQB_OK) return r2;
                 ++mv.products;
                 k_peer_gather<<<vgrid, kT, 0, st>>>(X, n, B.z, &B.state->pz, skip);
                 ctx->launches += 1;
+            } else if (mixedOn) {
+                r2 = launch_symv_mixed(ctx, A, ctx->d_A32, B.p, mv.area, scale ? mv.area : nullptr,
+                                       scale ? nullptr : mv.inv_area, B.z, st, skip, &B.state->skip64,
+                                       &B.state->skip32, &fuse, nullptr);
+                if (r2 != ICQB_OK) return r2;
+                ++mv.products;
+                r2 = comm_allreduce_sum(ctx, B.z, n + 1, st);
+                if (r2 != ICQB_OK) return r2;
             } else {
                 r2 = mv.apply(B.p, B.z, scale, st, skip, fuseDir ? &fuse : nullptr, fuseDir ? 1 : 0);
                 if (r2 != ICQB_OK) return r2;
@@ -689,6 +720,20 @@ int cg_solve_caps(icqb_ctx* ctx, uint64_t dA_, int64_t n, int64_t ld, int storag
             CG_CUDA(cudaGetLastError());
         }
 
+        // float32 copy of the stored tiles for the late products (mixed precision)
+        const bool mixed = (ctx->mixed_switch > 0.0) && storage == 1;
+        if (mixed) {
+            const long long count = L.numTiles() * kLowerTileElems;
+            if (count > ctx->a32_floats) {
+                dev_free(ctx, ctx->d_A32);
+                ctx->d_A32 = nullptr;
+                ctx->a32_floats = 0;
+                CG_CUDA(dev_alloc(ctx, &ctx->d_A32, sizeof(float) * (size_t)std::max<long long>(count, 4)));
+                ctx->a32_floats = count;
+            }
+            CG_TRY(launch_f64_to_f32(ctx, A, ctx->d_A32, count, st));
+        }
+
         // z = s * (A x0); r, w, rho_0 and the norms of b
         CG_TRY(mv.apply(x, B.z, scale, st));
         k_cg_vec<<<vgrid, kT, 0, st>>>(kInit, 0, 0, b, scale, x, B);
@@ -706,7 +751,8 @@ int cg_solve_caps(icqb_ctx* ctx, uint64_t dA_, int64_t n, int64_t ld, int storag
         double true2 = sqrt(hs.res2), trueinf = hs.resmax, prev_true = -1.0;
         bool breakdown = false;
         k_cg_state<<<1, 1, 0, st>>>(B.state, 0, 0, thr_dev, use_max ? 1 : 0, 1);
-        ctx->launches += 1;
+        k_cg_mixed<<<1, 1, 0, st>>>(B.state, mixed ? ctx->mixed_switch * hs.bmax : 0.0);
+        ctx->launches += 2;
         const long long batch = 8;
 
         while (true) {
@@ -727,7 +773,9 @@ int cg_solve_caps(icqb_ctx* ctx, uint64_t dA_, int64_t n, int64_t ld, int storag
                 ++replacements;
                 err = truem;
                 k_cg_state<<<1, 1, 0, st>>>(B.state, 0, 0, thr_dev, use_max ? 1 : 0, 0);
-                ctx->launches += 1;
+                k_cg_mixed<<<1, 1, 0, st>>>(B.state, 0.0);   // continue in double precision only
+                ctx->launches += 2;
+                products32 += hs.n32;
             }
             long long enq = k;
             int inflight = 0, head = 0;
@@ -767,6 +815,7 @@ int cg_solve_caps(icqb_ctx* ctx, uint64_t dA_, int64_t n, int64_t ld, int storag
         if (gemv_count) ctx->last_ms[kGemv] = gemv_ms / (double)gemv_count;
         ctx->cg_replacements = replacements;
         ctx->cg_products = mv.products;
+        ctx->cg_products32 = products32 + hs.n32;
         if (iters) *iters = k;
         if (resid2) *resid2 = true2;
         if (residinf) *residinf = trueinf;

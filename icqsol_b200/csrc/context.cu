@@ -227,6 +227,7 @@ int icqb_destroy(icqb_ctx* ctx) {
     symv_plan_free(ctx);
     free_mesh(ctx);
     cudaFree(ctx->d_ffstats);
+    dev_free(ctx, ctx->d_A32);
     dev_free(ctx, ctx->d_work);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);   // stream-ordered frees (ICQB_POOL_ALLOC)
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);

@@ -81,6 +81,13 @@ struct CgState {
     double beta;               // rho_{k+1}/rho_k for the next direction
     double bb, bmax;           // |b|_2^2, max|b|
     double tru2, trumax;       // true residual |b - A x|_2^2, max norm
+    // EXPERIMENTAL mixed-precision products (cg_caps.cu only; appended: the validated kernels'
+    // offsets are unchanged): once the recurrence residual max|r/s| falls below switch_thr the
+    // products read the float32 copy of the matrix
+    int lowp;                  // 1: float32 products
+    int skip64, skip32;        // done | lowp,  done | !lowp  (the two matrix kernels' skip flags)
+    int n32;                   // float32 products so far
+    double switch_thr;         // 0: mixed precision off
 };
 
 // Conjugate-gradient work fused into the symmetric product (single rank, lower storage):
@@ -150,6 +157,10 @@ struct icqb_ctx {
     int64_t cap_head_tiles = 0, cap_tail_tiles = 0;
     std::vector<int64_t> block_starts;   // experimental: first tile row of every diagonal block
     int64_t cg_replacements = 0, cg_products = 0;   // statistics of the last solve
+    double mixed_switch = 0.0;     // experimental: relative residual below which products use float32 (0 = off)
+    float* d_A32 = nullptr;        // experimental: float32 copy of the stored tiles
+    int64_t a32_floats = 0;
+    int64_t cg_products32 = 0;     // float32 products of the last solve (from the device state)
 
     double last_ms[icqb::kNumPhases] = {0, 0, 0, 0, 0};
     int64_t launches = 0;
@@ -185,6 +196,15 @@ int launch_symv(icqb_ctx* ctx, const double* dA, const double* dx,
                 const double* dgamma, const double* dalpha, const double* dbeta, double* dz,
                 cudaStream_t stream, const int* skip = nullptr, const SymvFuse* fuse = nullptr,
                 const SymvPeer* peer = nullptr);
+// EXPERIMENTAL float32 products of the mixed-precision CG (symv.cu)
+int launch_symv_mixed(icqb_ctx* ctx, const double* dA, const float* dA32, const double* dx,
+                      const double* dgamma, const double* dalpha, const double* dbeta, double* dz,
+                      cudaStream_t stream, const int* done, const int* skip64, const int* skip32,
+                      const SymvFuse* fuse, const SymvPeer* peer);
+int launch_f64_to_f32(icqb_ctx* ctx, const double* dA, float* dA32, long long count,
+                      cudaStream_t stream);
+int launch_symv_f32_only(icqb_ctx* ctx, const float* dA32, const double* dx, const double* dgamma,
+                         const double* dalpha, const double* dbeta, double* dz, cudaStream_t stream);
 int launch_diag(icqb_ctx* ctx, int order, double* dOut, int64_t stride);
 int launch_gemv(icqb_ctx* ctx, const double* dA, int64_t nrows, int64_t ncols, int64_t ld,
                 const double* dx, double* dy, const double* drowscale, cudaStream_t stream,

@@ -55,6 +55,13 @@ static_assert(kRedGroups == 8, "k_symv_reduce joins exactly eight groups");
 constexpr int kSmemBytes =
     kWarps * kDepth * kChunkBytes + kWarps * kT * 8 + kWarps * kDepth * 8;   // 204,992 B
 
+// EXPERIMENTAL float32 product (k_symv_f32): the same chunks of 8 rows x 128 columns are 4 KB,
+// the ring holds twice as many of them
+constexpr int kDepth32 = 6;
+constexpr int kChunkBytes32 = kChunkElems * 4;
+constexpr int kSmemBytes32 =
+    kWarps * kDepth32 * kChunkBytes32 + kWarps * kT * 8 + kWarps * kDepth32 * 8;   // 205,184 B
+
 struct SymvTask {
     int lt;        // local strip (tile row) index
     int J;         // global source tile, J <= I
@@ -81,6 +88,7 @@ struct SymvParams {
     const int* skip;            // when non-null and *skip != 0 the kernels return at once
     SymvFuse F;                 // CG fusion (all null: plain product)
     SymvPeer X;                 // peer exchange (k_symv_reduce<true> only)
+    const float* A32 = nullptr; // EXPERIMENTAL k_symv_f32: float32 copy of A, same tile layout
 };
 
 #ifdef ICQB_EMU   // CPU emulation build of the test suite (tools/emu): no PTX
@@ -318,6 +326,181 @@ __global__ void __launch_bounds__(kThreads, 1) k_symv(const SymvParams P) {
     flush();
 }
 
+// EXPERIMENTAL (never run on a GPU; checked in the CPU emulation): the same product on a
+// FLOAT32 copy of the stored tiles -- half the bytes -- for the late iterations of the CG, where
+// the direction is so small that a product accurate to 6e-8 of |A||p| still keeps the residual
+// recurrence honest to well below the stopping threshold (inexact Krylov;
+// tools/experiments/pcg_mixed_precision.py: -25..28 % traffic at an unchanged 5e-13 backward
+// error).  Same static partition, chunks (8 rows x 128 columns = 4 KB), row butterfly, partial
+// arrays and reduce kernel as k_symv; a lane owns four consecutive columns (one 16-byte
+// read), entries are widened to double before they meet the double vectors, all sums in double.
+__global__ void __launch_bounds__(kThreads, 1) k_symv_f32(const SymvParams P) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    if (P.skip && *P.skip) return;
+    float* s_ring = reinterpret_cast<float*>(smem_raw);              // [kWarps][kDepth32][kChunkElems]
+    double* s_mul = reinterpret_cast<double*>(s_ring + kWarps * kDepth32 * kChunkElems);   // [kWarps][kT]
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_mul + kWarps * kT);   // [kWarps][kDepth32]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long gw = (long long)blockIdx.x * kWarps + warp;
+    const long long nW = (long long)gridDim.x * kWarps;
+    const long long total = (long long)P.nTasks * kChunksPerTile;
+    const long long c0 = total * gw / nW, c1 = total * (gw + 1) / nW;   // this warp's chunks
+    const long long nCh = c1 - c0;
+    if (nCh <= 0) return;
+
+    float* ring = s_ring + warp * kDepth32 * kChunkElems;
+    double* mul = s_mul + warp * kT;
+    uint64_t* bar = s_bar + warp * kDepth32;
+    uint64_t policy = 0;
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < kDepth32; ++s) mbar_init(&bar[s], 1);
+#ifndef ICQB_EMU
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#endif
+        policy = policy_evict_first();
+    }
+    __syncwarp();
+    if (lane == 0) {
+        const int pre = (int)min((long long)kDepth32, nCh);
+        for (int s = 0; s < pre; ++s) {
+            mbar_expect_tx(&bar[s], kChunkBytes32);
+            bulk_g2s(ring + s * kChunkElems, P.A32 + (c0 + s) * kChunkElems, kChunkBytes32, &bar[s],
+                     policy);
+        }
+    }
+
+    const double cgBeta = P.F.w ? *P.F.beta : 0.0;
+
+    // state of the tile being processed
+    long long curTile = -1;
+    bool diagTile = false, ragged = false, ownsStart = false;
+    bool v0 = true, v1 = true, v2 = true, v3 = true;
+    int nrows = 0, curLt = 0;
+    long long colA = 0;
+    double x0 = 0, x1 = 0, x2 = 0, x3 = 0;
+    double ca0 = 0, ca1 = 0, ca2 = 0, ca3 = 0;
+
+    // column partials of the finished segment: to the tile's slot when this warp began
+    // the tile, else to the warp's head slot
+    auto flush = [&]() {
+        if (curTile < 0 || diagTile) return;
+        double* wc = ownsStart ? P.Wc + (long long)curLt * P.wcols + colA
+                               : P.Wh + (long long)__ldg(P.headSlot + gw) * kT + 4 * lane;
+        reinterpret_cast<double2*>(wc)[0] = make_double2(ca0, ca1);
+        reinterpret_cast<double2*>(wc + 2)[0] = make_double2(ca2, ca3);
+    };
+
+    for (long long i = 0; i < nCh; ++i) {
+        const long long ch = c0 + i;
+        const long long tile = ch / kChunksPerTile;
+        const int rbase = (int)(ch % kChunksPerTile) * kChunkRows;
+
+        if (tile != curTile) {
+            flush();
+            curTile = tile;
+            ownsStart = (tile * kChunksPerTile >= c0);
+            const SymvTask task = P.tasks[tile];
+            curLt = task.lt;
+            const long long obs0 = P.L.obs0(task.lt), obsEnd = P.L.obsEnd(task.lt);
+            const long long I = obs0 / kT, J = task.J;
+            nrows = (int)min((long long)kT, obsEnd - obs0);
+            diagTile = (J == I);
+            // valid columns: tiles below the diagonal tile are complete; the diagonal tile ends at n
+            const long long cEnd = diagTile ? min(P.n, (J + 1) * kT) : (J + 1) * kT;
+            ragged = cEnd < (J + 1) * kT;
+            colA = J * kT + 4 * lane;     // this lane's four consecutive columns
+            v0 = colA < cEnd;
+            v1 = colA + 1 < cEnd;
+            v2 = colA + 2 < cEnd;
+            v3 = colA + 3 < cEnd;
+            x0 = v0 ? vec_at(P, cgBeta, colA) : 0.0;
+            x1 = v1 ? vec_at(P, cgBeta, colA + 1) : 0.0;
+            x2 = v2 ? vec_at(P, cgBeta, colA + 2) : 0.0;
+            x3 = v3 ? vec_at(P, cgBeta, colA + 3) : 0.0;
+            ca0 = ca1 = ca2 = ca3 = 0.0;
+            if (!diagTile) {
+                // multipliers of the mirrored entries: gamma_i x_i for the tile's 128 rows
+                __syncwarp();
+#pragma unroll
+                for (int q = 0; q < kT / 32; ++q) {
+                    const int r = q * 32 + lane;
+                    double m = 0.0;
+                    if (r < nrows) {
+                        m = vec_at(P, cgBeta, obs0 + r);
+                        if (P.gamma) m *= __ldg(P.gamma + obs0 + r);
+                    }
+                    mul[r] = m;
+                }
+                __syncwarp();
+            }
+        }
+
+        const int s = (int)(i % kDepth32);
+        mbar_wait(&bar[s], (uint32_t)((i / kDepth32) & 1));
+        const float* sp = ring + s * kChunkElems + 4 * lane;
+
+        double part[kChunkRows];
+#pragma unroll
+        for (int u = 0; u < kChunkRows; ++u) {
+            const int r = rbase + u;
+            part[u] = 0.0;
+            if (r < nrows) {   // uniform across the warp
+                const float4 af = *reinterpret_cast<const float4*>(sp + u * kT);   // 16 bytes
+                double2 a01 = make_double2((double)af.x, (double)af.y);
+                double2 a23 = make_double2((double)af.z, (double)af.w);
+                if (ragged) {   // columns beyond n were never written: mask them
+                    if (!v0) a01.x = 0.0;
+                    if (!v1) a01.y = 0.0;
+                    if (!v2) a23.x = 0.0;
+                    if (!v3) a23.y = 0.0;
+                }
+                part[u] = fma(a23.y, x3, fma(a23.x, x2, fma(a01.y, x1, a01.x * x0)));
+                if (!diagTile) {
+                    const double m = mul[r];   // same address on every lane: broadcast
+                    ca0 = fma(a01.x, m, ca0);
+                    ca1 = fma(a01.y, m, ca1);
+                    ca2 = fma(a23.x, m, ca2);
+                    ca3 = fma(a23.y, m, ca3);
+                }
+            }
+        }
+        // every lane has read its part of the stage: lane 0 may refill it
+        __syncwarp();
+        if (lane == 0 && i + kDepth32 < nCh) {
+            mbar_expect_tx(&bar[s], kChunkBytes32);
+            bulk_g2s(ring + s * kChunkElems, P.A32 + (ch + kDepth32) * kChunkElems, kChunkBytes32, &bar[s],
+                     policy);
+        }
+
+        // transposed butterfly: 8 row sums over 32 lanes in 4+2+1+1+1 shuffles; row
+        // (lane >> 2) of the chunk ends up on the four lanes of its group
+        const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const double send = b4 ? part[q] : part[q + 4];
+            const double keep = b4 ? part[q + 4] : part[q];
+            part[q] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const double send = b3 ? part[q] : part[q + 2];
+            const double keep = b3 ? part[q + 2] : part[q];
+            part[q] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+        {
+            const double send = b2 ? part[0] : part[1];
+            const double keep = b2 ? part[1] : part[0];
+            part[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+        part[0] += __shfl_xor_sync(0xffffffffu, part[0], 2);
+        part[0] += __shfl_xor_sync(0xffffffffu, part[0], 1);
+        if ((lane & 3) == 0) P.Wr[tile * kT + rbase + (lane >> 2)] = part[0];
+    }
+    flush();
+}
+
 // z[j] = alpha_j * (row partials of j's strip over its tiles) + beta_j * (column partials of
 // the strips below).  One CTA per 128 global indices, kRedGroups thread groups split the two
 // sums (many independent loads in flight: the kernel is latency bound) and are combined in a
@@ -412,6 +595,13 @@ __global__ void __launch_bounds__(kRedThreads) k_symv_reduce(const SymvParams P)
             }
         }
     }
+}
+
+__global__ void __launch_bounds__(256) k_f64_to_f32(const double* __restrict__ a,
+                                                    float* __restrict__ out, long long count) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count;
+         i += (long long)gridDim.x * blockDim.x)
+        out[i] = (float)a[i];
 }
 
 }  // namespace
@@ -513,6 +703,8 @@ static int symv_plan(icqb_ctx* ctx) {
     // tile's Wc slot, so Wc needs no initialisation)
     ICQB_CUDA(ctx, cudaFuncSetAttribute(k_symv, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         kSmemBytes));
+    ICQB_CUDA(ctx, cudaFuncSetAttribute(k_symv_f32, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        kSmemBytes32));
     return ICQB_OK;
 }
 
@@ -560,6 +752,105 @@ int launch_symv(icqb_ctx* ctx, const double* dA, const double* dx, const double*
         k_symv_reduce<false><<<(unsigned)((p->n + kT - 1) / kT), dim3(kT, kRedGroups), 0, stream>>>(P);
     ctx->launches += 1;
     return check_cuda(ctx, cudaGetLastError(), "k_symv launch");
+}
+
+// EXPERIMENTAL: one product of the mixed-precision CG.  Both matrix kernels are enqueued; the
+// device flags decide which one does the work (skip64 / skip32 are maintained by k_cg_close:
+// exactly one of them is 0 while the iteration runs), the reduce kernel follows either.
+int launch_symv_mixed(icqb_ctx* ctx, const double* dA, const float* dA32, const double* dx,
+                      const double* dgamma, const double* dalpha, const double* dbeta, double* dz,
+                      cudaStream_t stream, const int* done, const int* skip64, const int* skip32,
+                      const SymvFuse* fuse, const SymvPeer* peer) {
+    if (ctx->ntri == 0) return ICQB_OK;
+    if ((reinterpret_cast<uintptr_t>(dA) & 15) != 0 || (reinterpret_cast<uintptr_t>(dA32) & 15) != 0)
+        return set_error(ctx, ICQB_EARG, "symv: matrices must be 16-byte aligned");
+    int st = symv_plan(ctx);
+    if (st != ICQB_OK) return st;
+    SymvPlan* p = ctx->symv;
+    SymvParams P;
+    P.A = dA;
+    P.A32 = dA32;
+    P.n = p->n;
+    P.L = p->L;
+    P.nTasks = p->nTasks;
+    P.tasks = p->d_tasks;
+    P.x = dx;
+    P.gamma = dgamma;
+    P.alpha = dalpha;
+    P.beta = dbeta;
+    P.Wc = p->d_Wc;
+    P.Wr = p->d_Wr;
+    P.Wh = p->d_Wh;
+    P.headSlot = p->d_headSlot;
+    P.headColBegin = p->d_headColBegin;
+    P.headColSlots = p->d_headColSlots;
+    P.wcols = p->wcols;
+    P.z = dz;
+    if (fuse) P.F = *fuse;
+    if (peer) {
+        if (!fuse || !fuse->pz_part)
+            return set_error(ctx, ICQB_EARG, "symv: the peer exchange needs the fused p.z");
+        P.X = *peer;
+    }
+    if (p->nTasks > 0) {
+        P.skip = skip64;
+        k_symv<<<p->grid, kThreads, kSmemBytes, stream>>>(P);
+        P.skip = skip32;
+        k_symv_f32<<<p->grid, kThreads, kSmemBytes32, stream>>>(P);
+        ctx->launches += 2;
+    }
+    P.skip = done;
+    if (peer)
+        k_symv_reduce<true><<<(unsigned)((p->n + kT - 1) / kT), dim3(kT, kRedGroups), 0, stream>>>(P);
+    else
+        k_symv_reduce<false><<<(unsigned)((p->n + kT - 1) / kT), dim3(kT, kRedGroups), 0, stream>>>(P);
+    ctx->launches += 1;
+    return check_cuda(ctx, cudaGetLastError(), "k_symv (mixed) launch");
+}
+
+// float32 copy of the locally stored tiles (count = stored tiles * 128 * 128)
+int launch_f64_to_f32(icqb_ctx* ctx, const double* dA, float* dA32, long long count,
+                      cudaStream_t stream) {
+    if (count <= 0) return ICQB_OK;
+    k_f64_to_f32<<<148 * 8, 256, 0, stream>>>(dA, dA32, count);
+    ctx->launches += 1;
+    return check_cuda(ctx, cudaGetLastError(), "k_f64_to_f32 launch");
+}
+
+// plain float32 product (tests): z = G x with the float32 copy
+int launch_symv_f32_only(icqb_ctx* ctx, const float* dA32, const double* dx, const double* dgamma,
+                         const double* dalpha, const double* dbeta, double* dz, cudaStream_t stream) {
+    if (ctx->ntri == 0) return ICQB_OK;
+    int st = symv_plan(ctx);
+    if (st != ICQB_OK) return st;
+    SymvPlan* p = ctx->symv;
+    SymvParams P;
+    P.A = nullptr;
+    P.A32 = dA32;
+    P.n = p->n;
+    P.L = p->L;
+    P.nTasks = p->nTasks;
+    P.tasks = p->d_tasks;
+    P.x = dx;
+    P.gamma = dgamma;
+    P.alpha = dalpha;
+    P.beta = dbeta;
+    P.Wc = p->d_Wc;
+    P.Wr = p->d_Wr;
+    P.Wh = p->d_Wh;
+    P.headSlot = p->d_headSlot;
+    P.headColBegin = p->d_headColBegin;
+    P.headColSlots = p->d_headColSlots;
+    P.wcols = p->wcols;
+    P.z = dz;
+    P.skip = nullptr;
+    if (p->nTasks > 0) {
+        k_symv_f32<<<p->grid, kThreads, kSmemBytes32, stream>>>(P);
+        ctx->launches += 1;
+    }
+    k_symv_reduce<false><<<(unsigned)((p->n + kT - 1) / kT), dim3(kT, kRedGroups), 0, stream>>>(P);
+    ctx->launches += 1;
+    return check_cuda(ctx, cudaGetLastError(), "k_symv_f32 launch");
 }
 
 }  // namespace icqb

@@ -122,6 +122,10 @@ int icqb_assemble_lower_dev(icqb_ctx* ctx, int diag_order, uint64_t dG, uint64_t
  * each stored entry once (4 N^2 bytes instead of 8 N^2) and all-reduces the partial
  * vectors over the ranks.  x, y: device double[ntri], replicated.  Blocking. */
 int icqb_symv_dev(icqb_ctx* ctx, uint64_t dA, uint64_t dx, uint64_t dy, int scaled);
+/* EXPERIMENTAL (emulated only): the same product on a float32 copy of the stored tiles (made
+ * by the call; the timed part is the product alone) -- the kernel behind the mixed-precision
+ * CG (icqb_cg_set_mixed_precision); the result is G32 x with all sums in double. */
+int icqb_symv_f32_dev(icqb_ctx* ctx, uint64_t dA, uint64_t dx, uint64_t dy, int scaled);
 
 /* Host-buffer forms (blocking; host<->device copies inside the call).
  * gMat/kMat: row-major double[(r1-r0)*ntri]; kMat may be NULL. */
@@ -221,6 +225,17 @@ int icqb_cg_set_block_partition(icqb_ctx* ctx, const int64_t* starts, int64_t nb
  * products were enqueued (iterations + confirmations + the ones skipped behind the stop
  * flag). */
 int icqb_cg_last_stats(const icqb_ctx* ctx, int64_t* replacements, int64_t* products);
+/* EXPERIMENTAL (kind 2, lower storage; emulated only): mixed-precision products.  Once the
+ * recurrence residual max|b - A x| falls below switch_rel * max|b| the products of the
+ * iteration stream a float32 copy of the stored tiles (half the bytes; converted once per
+ * solve, 2 N^2 more bytes of HBM over all ranks) -- a direction that small tolerates a product
+ * accurate to 6e-8 (inexact Krylov); the solve still ends with the double-precision residual
+ * b - A x, and if that misses the tolerance it continues in double precision only.  In the
+ * numpy model switch_rel = 1e-6 saves 25-28 % of the matrix traffic at an unchanged 5e-13
+ * backward error.  0 (default) = off. */
+int icqb_cg_set_mixed_precision(icqb_ctx* ctx, double switch_rel);
+/* float32 products of the last solve */
+int icqb_cg_last_mixed(const icqb_ctx* ctx, int64_t* products32);
 
 /* ---- multi-GPU plumbing -----------------------------------------------------------
  * One rank per process.  `unique_id` is the 128-byte ncclUniqueId produced by

@@ -284,7 +284,8 @@ def test_emulated_subdivide(emu, golden, k, f32):
     c.close()
 
 
-def _run_ranks(emu, nranks, n_theta, n_phi, storage, kind, caps=None, peer=False, starts=None):
+def _run_ranks(emu, nranks, n_theta, n_phi, storage, kind, caps=None, peer=False, starts=None,
+               mixed=0.):
     """One rank per thread (ctypes releases the GIL), the in-process NCCL stand-in of
     tools/emu underneath: folded row blocks, sharded assembly, distributed CG.  peer=True
     also sets up the experimental peer exchange (handles swapped through a shared list)."""
@@ -300,6 +301,7 @@ def _run_ranks(emu, nranks, n_theta, n_phi, storage, kind, caps=None, peer=False
         try:
             c = Ctx(emu, n_theta, n_phi, sms=2)
             c.check(emu.icqb_comm_init(c.h, uid, rank, nranks))
+            c.check(emu.icqb_cg_set_mixed_precision(c.h, mixed))
             n = c.n
             if peer:
                 h = ctypes.create_string_buffer(64)
@@ -612,5 +614,129 @@ def test_emulated_multi_rank_experimental_combinations(emu, oracle_mod, nranks, 
         assert rinf <= 5e-13 * numpy.abs(b).max()
     assert numpy.abs(b - ref.dot(x0)).max() <= 1e-12 * numpy.abs(b).max()
     assert abs(iters0 - model_iterations(ref, a2, b, cuts)) <= 1
+    for o in out:
+        o[-1].close()
+
+
+# ---- EXPERIMENTAL: float32 late products of the CG (k_symv_f32, cg_caps.cu) ---------------------
+
+@pytest.mark.parametrize('sms', [1, 3, 4])
+def test_emulated_float32_product(emu, oracle_mod, sms):
+    """k_symv_f32 on the float32 copy of the stored tiles: equals the product with the
+    float32-rounded entries (sums in double) for several static partitions of the chunk
+    sequence, two separated row blocks and a ragged last tile."""
+    c = Ctx(emu, 20, 11, sms=sms)                      # 400 triangles, tile rows 0..3
+    n = c.n
+    ref = oracle_mod.green_matrix(c.xyz, c.tri, 5)
+    a2 = oracle_mod.area2(c.xyz, c.tri)
+    rng = numpy.random.default_rng(sms)
+    for blocks in ((0, n, n, n), (128, 256, 384, 400)):
+        (g,) = c.assemble_lower(blocks)
+        rows = list(range(blocks[0], blocks[1])) + list(range(blocks[2], blocks[3]))
+        mask = numpy.zeros((n, n), bool)
+        for i in rows:
+            mask[i, :min(n, (i // 128 + 1) * 128)] = True
+        tile = numpy.arange(n) // 128
+        lower = mask & (tile[None, :] < tile[:, None])
+        r32 = ref.astype(numpy.float32).astype(numpy.float64)
+        full = numpy.where(mask, r32, 0.) + numpy.where(lower, r32, 0.).T * (a2[None, :] / a2[:, None])
+        for scaled in (0, 1):
+            x, y = rng.normal(size=n), dev_array(emu, n)
+            c.check(emu.icqb_symv_f32_dev(c.h, g.ctypes.data, x.ctypes.data, y.ctypes.data, scaled))
+            want = full.dot(x) * (a2 if scaled else 1.)
+            bound = numpy.abs(full).dot(numpy.abs(x)) * (a2 if scaled else 1.)
+            assert (numpy.abs(y - want) <= 1e-13 * bound + 1e-300).all()
+            # and it IS a float32 product: away from the double one by ~1e-8
+            exact = (numpy.where(mask, ref, 0.) + numpy.where(lower, ref, 0.).T *
+                     (a2[None, :] / a2[:, None])).dot(x) * (a2 if scaled else 1.)
+            assert 1e-10 * bound.max() < numpy.abs(y - exact).max() < 1e-6 * bound.max()
+    c.close()
+
+
+def model_iterations_mixed(g, a2, b, cuts, switch):
+    """numpy model of the mixed-precision CG: as model_iterations, the product reads the
+    float32-rounded matrix from the first residual below switch * max|b| on.
+    @return (iterations, float32 products)"""
+    n = len(b)
+    ms = a2[:, None] * g
+    g32 = g.astype(numpy.float32).astype(numpy.float64)
+    cuts = [c for c in cuts if c < n] + [n]
+    msym = 0.5 * (ms + ms.T)
+    invs = [numpy.linalg.inv(msym[p:q, p:q]) for p, q in zip(cuts[:-1], cuts[1:])]
+
+    def pre(r):
+        out = numpy.empty_like(r)
+        for k, (p, q) in enumerate(zip(cuts[:-1], cuts[1:])):
+            out[p:q] = invs[k].dot(r[p:q])
+        return out
+    x, r, p, rho_old = numpy.zeros(n), a2 * b, numpy.zeros(n), 1.
+    w = pre(r)
+    lowp, n32 = False, 0
+    for k in range(2000):
+        rho = r.dot(w)
+        p = w + (rho / rho_old if k else 0.) * p
+        z = a2 * ((g32 if lowp else g).dot(p))
+        n32 += int(lowp)
+        alpha = rho / p.dot(z)
+        x += alpha * p
+        r -= alpha * z
+        w = pre(r)
+        rho_old = rho
+        res = numpy.abs(r / a2).max()
+        if res <= switch * numpy.abs(b).max():
+            lowp = True
+        if res <= 5e-13 * numpy.abs(b).max():
+            return k + 1, n32
+    return -1, n32
+
+
+@pytest.mark.parametrize('starts,cuts', [([0, 1, 2, 3], [0, 128, 256, 384]), ([0, 2], [0, 256])])
+def test_emulated_mixed_precision_cg(emu, oracle_mod, starts, cuts):
+    """The CG of cg_caps.cu with float32 late products (switch at 1e-6): same iteration and
+    float32-product counts as the numpy model, the solution satisfies the oracle's system to
+    1e-12, and switching the option off restores the double-precision solve."""
+    c = Ctx(emu, 20, 11)
+    n = c.n
+    (g,) = c.assemble_lower()
+    ref = oracle_mod.green_matrix(c.xyz, c.tri, 5)
+    a2 = oracle_mod.area2(c.xyz, c.tri)
+    assert emu.icqb_cg_set_mixed_precision(c.h, 1.5) != 0
+    c.check(emu.icqb_cg_set_mixed_precision(c.h, 1e-6))
+    x, iters, rinf, b = c.solve(g, 1, 2, starts=starts)
+    n32 = ctypes.c_int64(-1)
+    c.check(emu.icqb_cg_last_mixed(c.h, ctypes.byref(n32)))
+    want_iters, want32 = model_iterations_mixed(ref, a2, numpy.array(b), cuts, 1e-6)
+    assert numpy.abs(b - ref.dot(x)).max() <= 1e-12 * numpy.abs(b).max()
+    assert rinf <= 1e-12 * numpy.abs(b).max()
+    assert abs(iters - want_iters) <= 2 and abs(n32.value - want32) <= 2 and n32.value > 5
+    c.check(emu.icqb_cg_set_mixed_precision(c.h, 0.))
+    x2, iters2, rinf2, _ = c.solve(g, 1, 2, starts=starts)
+    c.check(emu.icqb_cg_last_mixed(c.h, ctypes.byref(n32)))
+    assert n32.value == 0 and abs(iters2 - model_iterations(ref, a2, numpy.array(b), cuts)) <= 1
+    assert numpy.abs(x2 - x).max() <= 1e-9 * numpy.abs(x).max()
+    c.close()
+
+
+@pytest.mark.parametrize('nranks,peer', [(2, False), (3, True)])
+def test_emulated_mixed_precision_multi_rank(emu, oracle_mod, nranks, peer):
+    """Float32 late products with the partial products all-reduced (NCCL stand-in) or exchanged
+    through the peer buffers: every rank takes the same switch decision (replicated state), the
+    same solution and counts on every rank, the counts of the numpy model."""
+    out = _run_ranks(emu, nranks, 20, 11, 1, 2, None, peer, [0, 2], mixed=1e-6)
+    c = out[0][-1]
+    ref = oracle_mod.green_matrix(c.xyz, c.tri, 5)
+    a2 = oracle_mod.area2(c.xyz, c.tri)
+    x0, iters0, _, b, _ = out[0]
+    counts = []
+    for x, iters, rinf, _, cc in out:
+        assert (x == x0).all() and iters == iters0
+        assert rinf <= 1e-12 * numpy.abs(b).max()
+        n32 = ctypes.c_int64(-1)
+        cc.check(emu.icqb_cg_last_mixed(cc.h, ctypes.byref(n32)))
+        counts.append(n32.value)
+    assert len(set(counts)) == 1 and counts[0] > 5
+    assert numpy.abs(b - ref.dot(x0)).max() <= 1e-12 * numpy.abs(b).max()
+    want_iters, want32 = model_iterations_mixed(ref, a2, numpy.array(b), [0, 256], 1e-6)
+    assert abs(iters0 - want_iters) <= 2 and abs(counts[0] - want32) <= 2
     for o in out:
         o[-1].close()

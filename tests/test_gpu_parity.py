@@ -931,3 +931,55 @@ def test_direct_fallback_on_sliver_sphere(oracle_mod):
     assert solver.lastSolveInfo['method'] == 'lu'
     g = oracle_mod.green_matrix(xyz, tri, 5, threads=True)
     assert numpy.abs(v + g.dot(rsp)).max() / numpy.abs(v).max() < 1e-10
+
+
+@experimental
+@pytest.mark.parametrize('nt,nph', [(16, 9), (64, 30)])
+def test_float32_product_kernel(oracle_mod, nt, nph):
+    """k_symv_f32 (icqb_symv_f32_dev): the product with the float32-rounded stored entries,
+    sums in double."""
+    import torch
+    from icqsol_b200.mesh.generators import uvSphere
+    from icqsol_b200.mesh.polydata import PolyData
+    from icqsol_b200.bem.icqPoissonSolver import PoissonSolver
+    xyz, tri = uvSphere(1.0, nt, nph)
+    n = tri.shape[0]
+    solver = PoissonSolver(PolyData.from_arrays(xyz, tri), float('inf'), 5, storage='lower')
+    g = solver.getGreenMatrix()
+    a2 = solver.getTriangleAreas2()
+    t = numpy.arange(n) // 128
+    stored = t[None, :] <= t[:, None]
+    g32 = numpy.where(stored, g, 0.).astype(numpy.float32).astype(numpy.float64)
+    full = g32 + numpy.where(t[None, :] < t[:, None], g32, 0.).T * (a2[None, :] / a2[:, None])
+    rng = numpy.random.default_rng(n)
+    x = rng.normal(size=n)
+    dx = torch.from_numpy(x).to(solver.gMatDevice.device)
+    dy = torch.zeros(n, dtype=torch.float64, device=dx.device)
+    solver.ctx.check(solver.lib.icqb_symv_f32_dev(solver.ctx.handle, solver.gMatDevice.data_ptr(),
+                                                  dx.data_ptr(), dy.data_ptr(), 0))
+    y = dy.cpu().numpy()
+    assert (numpy.abs(y - full.dot(x)) <= 1e-13 * numpy.abs(full).dot(numpy.abs(x))).all()
+
+
+@experimental
+def test_mixed_precision_cg():
+    """Float32 late products (switch at 1e-6) in the experimental solver: same backward error,
+    a good share of the products in float32, a few more iterations at most."""
+    from icqsol_b200.mesh.generators import uvSphere
+    from icqsol_b200.mesh.polydata import PolyData
+    from icqsol_b200.bem.icqLaplaceSolver import LaplaceSolver
+    xyz, tri = uvSphere(1.0, 64, 32)
+    out = {}
+    for mixed in (0., 1e-6):
+        solver = LaplaceSolver(PolyData.from_arrays(xyz, tri), float('inf'), 5,
+                               preconditioner='block+caps', blockTiles=4, mixedPrecision=mixed)
+        solver.setSourceFromExpression('1./sqrt(x**2 + (y-2.)**2 + (z-4.)**2)')
+        v = solver.getSourceArray(solver.getSourceArrayIndex())
+        rsp = solver.computeResponseField()
+        g = solver.getGreenMatrix()
+        assert numpy.abs(v + g.dot(rsp)).max() / numpy.abs(v).max() < 1e-12
+        out[mixed] = (rsp, solver.lastSolveInfo)
+    assert out[0.][1]['float32Products'] == 0
+    assert out[1e-6][1]['float32Products'] > 0.3 * out[1e-6][1]['iterations']
+    assert out[1e-6][1]['iterations'] <= out[0.][1]['iterations'] + 8
+    assert relerr(out[1e-6][0], out[0.][0]) < 1e-8

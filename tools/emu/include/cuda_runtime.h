@@ -38,6 +38,9 @@ struct alignas(16) double2 {
     double x, y;
 };
 static inline double2 make_double2(double x, double y) { return double2{x, y}; }
+struct alignas(16) float4 {
+    float x, y, z, w;
+};
 
 struct dim3 {
     unsigned x, y, z;

@@ -8,7 +8,7 @@ out=gpurun_out
 mkdir -p $out
 export ICQB_EXPERIMENTAL=1
 if [ "$n" = "1" ]; then
-  timeout 600 python -m pytest tests -m gpu -x -q -k "cap_blocks or subdivide or block_tiles or direct_" > $out/${tag}_exp_pytest.log 2>&1
+  timeout 600 python -m pytest tests -m gpu -x -q -k "cap_blocks or subdivide or block_tiles or direct_ or float32 or mixed_precision" > $out/${tag}_exp_pytest.log 2>&1
   echo "experimental pytest rc=$?"; tail -5 $out/${tag}_exp_pytest.log
   # far-field split of the off-diagonal assembly (assemble_offdiag_ff.cu): parity, then the
   # three variants side by side (same workload, same run), then one full capture of variant 1
@@ -24,6 +24,23 @@ try:
     r = d['roofline_assembly']
     print('variant $v: offdiag %.2f ms, %.2f TFLOP/s = %.1f %% of peak, far-field fraction %s, step %.1f ms, cg %d' % (
         r['ms_per_launch'], r['achieved'], 100 * r['frac'], r.get('far_field_fraction'), d['ms_per_step'], d['phases']['cg_iters']))
+except Exception as e:
+    print('no bench line:', e)
+PY
+  done
+  # the solver's options one after the other on config C2 (block+caps = the experimental solver)
+  for opt in "--preconditioner block+caps" "--preconditioner block+caps --block-tiles 8" \
+             "--preconditioner block+caps --block-tiles 8 --mixed-switch 1e-6"; do
+    name=$(echo $opt | tr -d ' +-' | tr -c 'a-zA-Z0-9\n' '_')
+    timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --e2e-steps 1 $opt \
+        > $out/${tag}_exp_bench_$name.json 2> $out/${tag}_exp_bench_$name.err
+    echo "bench $opt rc=$?"; python - <<PY
+import json
+try:
+    d = json.load(open('$out/${tag}_exp_bench_$name.json'))
+    p = d['phases']
+    print('$opt: step %.1f ms, solve %.1f ms, %d iterations (%d float32 products), product %.3f ms, converged %s' % (
+        d['ms_per_step'], p['solve_ms'], p['cg_iters'], p.get('cg_float32_products', 0), p['gemv_ms'], p['cg_converged']))
 except Exception as e:
     print('no bench line:', e)
 PY
