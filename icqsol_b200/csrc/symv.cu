@@ -442,27 +442,44 @@ __global__ void __launch_bounds__(kThreads, 1) k_symv_f32(const SymvParams P) {
         const float* sp = ring + s * kChunkElems + 4 * lane;
 
         double part[kChunkRows];
+        if (!ragged && !diagTile && rbase + kChunkRows <= nrows) {
+            // the common case -- a complete chunk of a tile below the diagonal: no masks, no
+            // per-row tests (half the instructions of the general loop; this kernel moves half
+            // the bytes per chunk, so the instruction count per byte matters twice as much)
 #pragma unroll
-        for (int u = 0; u < kChunkRows; ++u) {
-            const int r = rbase + u;
-            part[u] = 0.0;
-            if (r < nrows) {   // uniform across the warp
+            for (int u = 0; u < kChunkRows; ++u) {
                 const float4 af = *reinterpret_cast<const float4*>(sp + u * kT);   // 16 bytes
-                double2 a01 = make_double2((double)af.x, (double)af.y);
-                double2 a23 = make_double2((double)af.z, (double)af.w);
-                if (ragged) {   // columns beyond n were never written: mask them
-                    if (!v0) a01.x = 0.0;
-                    if (!v1) a01.y = 0.0;
-                    if (!v2) a23.x = 0.0;
-                    if (!v3) a23.y = 0.0;
-                }
-                part[u] = fma(a23.y, x3, fma(a23.x, x2, fma(a01.y, x1, a01.x * x0)));
-                if (!diagTile) {
-                    const double m = mul[r];   // same address on every lane: broadcast
-                    ca0 = fma(a01.x, m, ca0);
-                    ca1 = fma(a01.y, m, ca1);
-                    ca2 = fma(a23.x, m, ca2);
-                    ca3 = fma(a23.y, m, ca3);
+                const double a0 = (double)af.x, a1 = (double)af.y, a2 = (double)af.z, a3 = (double)af.w;
+                part[u] = fma(a3, x3, fma(a2, x2, fma(a1, x1, a0 * x0)));
+                const double m = mul[rbase + u];   // same address on every lane: broadcast
+                ca0 = fma(a0, m, ca0);
+                ca1 = fma(a1, m, ca1);
+                ca2 = fma(a2, m, ca2);
+                ca3 = fma(a3, m, ca3);
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < kChunkRows; ++u) {
+                const int r = rbase + u;
+                part[u] = 0.0;
+                if (r < nrows) {   // uniform across the warp
+                    const float4 af = *reinterpret_cast<const float4*>(sp + u * kT);   // 16 bytes
+                    double2 a01 = make_double2((double)af.x, (double)af.y);
+                    double2 a23 = make_double2((double)af.z, (double)af.w);
+                    if (ragged) {   // columns beyond n were never written: mask them
+                        if (!v0) a01.x = 0.0;
+                        if (!v1) a01.y = 0.0;
+                        if (!v2) a23.x = 0.0;
+                        if (!v3) a23.y = 0.0;
+                    }
+                    part[u] = fma(a23.y, x3, fma(a23.x, x2, fma(a01.y, x1, a01.x * x0)));
+                    if (!diagTile) {
+                        const double m = mul[r];   // same address on every lane: broadcast
+                        ca0 = fma(a01.x, m, ca0);
+                        ca1 = fma(a01.y, m, ca1);
+                        ca2 = fma(a23.x, m, ca2);
+                        ca3 = fma(a23.y, m, ca3);
+                    }
                 }
             }
         }
