@@ -8,11 +8,14 @@ out=gpurun_out
 mkdir -p $out
 export ICQB_EXPERIMENTAL=1
 if [ "$n" = "1" ]; then
-  timeout 600 python -m pytest tests -m gpu -x -q -k "cap_blocks or subdivide or block_tiles or direct_ or float32 or mixed_precision" > $out/${tag}_exp_pytest.log 2>&1
-  echo "experimental pytest rc=$?"; tail -5 $out/${tag}_exp_pytest.log
+  # one pytest run per experimental feature: a failure in one must not hide the others
+  for grp in subdivide cap_blocks block_tiles direct_ float32 mixed_precision; do
+    timeout 400 python -m pytest tests -m gpu -q -k "$grp" > $out/${tag}_exp_pytest_$grp.log 2>&1
+    echo "experimental pytest [$grp] rc=$?"; tail -3 $out/${tag}_exp_pytest_$grp.log
+  done
   # far-field split of the off-diagonal assembly (assemble_offdiag_ff.cu): parity, then the
   # three variants side by side (same workload, same run), then one full capture of variant 1
-  timeout 900 python -m pytest tests -m gpu -x -q -k "far_field" > $out/${tag}_exp_ff_pytest.log 2>&1
+  timeout 900 python -m pytest tests -m gpu -q -k "far_field" > $out/${tag}_exp_ff_pytest.log 2>&1
   echo "far-field pytest rc=$?"; tail -5 $out/${tag}_exp_ff_pytest.log
   for v in 0 1 2; do
     timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --e2e-steps 1 --assembly-variant $v \
