@@ -31,6 +31,8 @@ except Exception as e:
     print('no bench line:', e)
 PY
   done
+  timeout 300 python tools/bench_kernels.py > $out/${tag}_exp_kernels.json 2> $out/${tag}_exp_kernels.err
+  echo "kernel timings rc=$?"; cat $out/${tag}_exp_kernels.json
   # the solver's options one after the other on config C2 (block+caps = the experimental solver)
   for opt in "--preconditioner block+caps" "--preconditioner block+caps --block-tiles 8" \
              "--preconditioner block+caps --block-tiles 8 --mixed-switch 1e-6"; do
