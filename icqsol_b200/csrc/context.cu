@@ -28,6 +28,13 @@ int set_error(icqb_ctx* ctx, int code, const std::string& msg) {
 }
 
 int check_cuda(icqb_ctx* ctx, cudaError_t e, const char* what) {
+    // ICQB_DEBUG_SYNC=1 (debugging aid): wait for the device after every checked call, so that
+    // an asynchronous fault is reported by the launch that caused it, not by a later call
+    static const bool debugSync = [] {
+        const char* v = getenv("ICQB_DEBUG_SYNC");
+        return v && v[0] == '1';
+    }();
+    if (e == cudaSuccess && debugSync && ctx) e = cudaStreamSynchronize(ctx->stream);
     if (e == cudaSuccess) return ICQB_OK;
     return set_error(ctx, ICQB_ECUDA, std::string(what) + ": " + cudaGetErrorString(e));
 }
