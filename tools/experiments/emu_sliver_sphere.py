@@ -4,7 +4,7 @@ sliver sphere: the oracle's G packed into the tile-contiguous lower storage, the
 icqb_cg_solve_dev with preconditioner kind 2 and the partition of sliverBlockPartition --
 k_dense_extract_lower, the unpivoted block Gauss-Jordan on the indefinite caps, k_dense_apply,
 k_cg_vec / k_cg_close and the persistent product, exactly the code a GPU will run.
-usage: emu_sliver_sphere.py <n_theta> <n_phi> [caps|plain] [block_tiles] [max_iters]
+usage: emu_sliver_sphere.py <n_theta> <n_phi> [caps|plain] [block_tiles] [max_iters] [mixed_switch]
 318 20 caps: 12,084 triangles, caps of 8 and 9 tiles, converged in 110 iterations (numpy model 109),
 oracle backward error 3.2e-13; 16 minutes on one core."""
 import ctypes, os, sys, time, numpy
@@ -51,9 +51,14 @@ else:
     assert lib.icqb_cg_set_preconditioner(h, 2) == 0
     st = numpy.asarray(starts, numpy.int64)
     assert lib.icqb_cg_set_block_partition(h, lp(st), len(st)) == 0
+mixed = float(sys.argv[6]) if len(sys.argv) > 6 else 0.
+assert lib.icqb_cg_set_mixed_precision(h, mixed) == 0
 it, r2, ri = ctypes.c_int64(0), ctypes.c_double(0.), ctypes.c_double(0.)
 t0 = time.time()
 st = lib.icqb_cg_solve_dev(h, tiles.ctypes.data, n, 0, 1, lib.icqb_area2_dev(h), 0, b.ctypes.data, x.ctypes.data,
                            5e-13, 2, int(sys.argv[5]) if len(sys.argv) > 5 else 400, ctypes.byref(it), ctypes.byref(r2), ctypes.byref(ri))
 print('status', st, lib.icqb_last_error(h), 'iters', it.value, 'resid inf rel %.2e' % (ri.value/numpy.abs(b).max()), 'solve %.0f s' % (time.time()-t0), flush=True)
+n32 = ctypes.c_int64(0)
+lib.icqb_cg_last_mixed(h, ctypes.byref(n32))
+print('float32 products', n32.value)
 print('oracle backward error %.2e' % (numpy.abs(b - g.dot(x)).max()/numpy.abs(b).max()))

@@ -31,6 +31,15 @@ except Exception as e:
     print('no bench line:', e)
 PY
   done
+  # memcheck and racecheck on one small case per new kernel (the emulation cannot see real races)
+  for tool in memcheck racecheck; do
+    timeout 600 compute-sanitizer --tool $tool python -m pytest -q -m gpu \
+        "tests/test_gpu_parity.py::test_far_field_split_every_entry[16-9-1]" \
+        "tests/test_gpu_parity.py::test_float32_product_kernel[16-9]" \
+        "tests/test_gpu_parity.py::test_cap_blocks_same_answer_on_regular_sphere" \
+        > $out/${tag}_exp_sanitizer_$tool.log 2>&1
+    echo "compute-sanitizer $tool rc=$?"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|passed|failed" $out/${tag}_exp_sanitizer_$tool.log | tail -4
+  done
   timeout 300 python tools/bench_kernels.py > $out/${tag}_exp_kernels.json 2> $out/${tag}_exp_kernels.err
   echo "kernel timings rc=$?"; cat $out/${tag}_exp_kernels.json
   # the solver's options one after the other on config C2 (block+caps = the experimental solver)
