@@ -121,6 +121,12 @@ class Context:
             msg = self.lib.icqb_last_error(None)
             raise RuntimeError('icqb_create failed ({0}): {1}'.format(st, msg.decode() if msg else ''))
         self.device = int(device)
+        # EXPERIMENTAL: ICQB_ASSEMBLY_VARIANT=1|2 makes every context start with the far-field
+        # split of the assembly kernel (include/icqb.h, icqb_set_assembly_variant), so that the
+        # whole parity suite can be run against it: ICQB_ASSEMBLY_VARIANT=1 pytest -m gpu
+        variant = os.environ.get('ICQB_ASSEMBLY_VARIANT')
+        if variant:
+            self.check(self.lib.icqb_set_assembly_variant(self.handle, int(variant)))
 
     def check(self, status):
         check(self.handle, status)

@@ -44,9 +44,16 @@ def leadingDimension(n):
 
 class BaseLaplaceSolver(BaseSolver):
 
+    # defaults of the solver options; ICQB_DEFAULTS=next (EXPERIMENTAL) switches the ones a caller
+    # leaves unset to the candidates for the next defaults, so that the whole parity suite can be
+    # run against them:  ICQB_DEFAULTS=next ICQB_EXPERIMENTAL=1 pytest -m gpu
+    DEFAULTS = {'preconditioner': 'block', 'blockTiles': 1, 'assemblyVariant': 0, 'mixedPrecision': 0.}
+    NEXT_DEFAULTS = {'preconditioner': 'block+caps', 'blockTiles': 8, 'assemblyVariant': 1,
+                     'mixedPrecision': 1.e-6}
+
     def __init__(self, pdata, max_edge_length, order=5, computeK=False, device=None,
-                 storage='lower', preconditioner='block', blockTiles=1, assemblyVariant=None,
-                 directFallback=False, mixedPrecision=0.):
+                 storage='lower', preconditioner=None, blockTiles=None, assemblyVariant=None,
+                 directFallback=False, mixedPrecision=None):
         """
         Constructor
         @param pdata polydata (vtkPolyData or stand-in)
@@ -77,6 +84,8 @@ class BaseLaplaceSolver(BaseSolver):
                        (include/icqb.h, icqb_set_assembly_variant): 0 = validated kernel,
                        1 = far-field split, 2 = far-field split with a Newton reciprocal square
                        root; None = environment variable ICQB_ASSEMBLY_VARIANT, else 0
+                       (options left at None take BaseLaplaceSolver.DEFAULTS, or NEXT_DEFAULTS
+                       with ICQB_DEFAULTS=next in the environment)
         """
         # wall-clock marks of the host-side phases (milliseconds since construction began), for
         # the end-to-end breakdown of bench.py: hostTimings['constructor'] / ['solve']
@@ -85,6 +94,22 @@ class BaseLaplaceSolver(BaseSolver):
 
         def mark(name):
             self.hostTimings['constructor'].append((name, 1e3 * (time.perf_counter() - t_begin)))
+
+        defaults = dict(self.DEFAULTS)
+        if os.environ.get('ICQB_ASSEMBLY_VARIANT'):
+            defaults['assemblyVariant'] = int(os.environ['ICQB_ASSEMBLY_VARIANT'])
+        if os.environ.get('ICQB_DEFAULTS') == 'next':
+            defaults.update(self.NEXT_DEFAULTS)
+        if preconditioner is None:
+            preconditioner = defaults['preconditioner']
+        if blockTiles is None:
+            blockTiles = defaults['blockTiles']
+        if assemblyVariant is None:
+            assemblyVariant = defaults['assemblyVariant']
+        if mixedPrecision is None:
+            mixedPrecision = defaults['mixedPrecision']
+        if preconditioner != 'block+caps' or storage != 'lower':
+            mixedPrecision = 0.      # the float32 products exist in the experimental solver only
 
         BaseSolver.__init__(self, pdata, max_edge_length, order)
         mark('mesh intake (host)')
@@ -112,8 +137,6 @@ class BaseLaplaceSolver(BaseSolver):
         self.ctx.check(self.lib.icqb_set_stream(self.ctx.handle,
                                                 torch.cuda.current_stream().cuda_stream or 1))
 
-        if assemblyVariant is None:
-            assemblyVariant = int(os.environ.get('ICQB_ASSEMBLY_VARIANT', '0'))
         self.assemblyVariant = int(assemblyVariant)
         self.ctx.check(self.lib.icqb_set_assembly_variant(self.ctx.handle, self.assemblyVariant))
 

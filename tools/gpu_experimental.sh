@@ -31,6 +31,13 @@ except Exception as e:
     print('no bench line:', e)
 PY
   done
+  # the WHOLE validated parity suite against the experimental kernels: first the far-field
+  # assembly alone (every context starts with variant 1), then all candidates for the next
+  # defaults at once (far-field assembly, cap/8-tile blocks, float32 late products)
+  ICQB_ASSEMBLY_VARIANT=1 timeout 900 python -m pytest tests -m gpu -q > $out/${tag}_exp_suite_variant1.log 2>&1
+  echo "parity suite with ICQB_ASSEMBLY_VARIANT=1 rc=$?"; tail -4 $out/${tag}_exp_suite_variant1.log
+  ICQB_DEFAULTS=next timeout 900 python -m pytest tests -m gpu -q > $out/${tag}_exp_suite_next.log 2>&1
+  echo "parity suite with ICQB_DEFAULTS=next rc=$?"; tail -4 $out/${tag}_exp_suite_next.log
   # memcheck and racecheck on one small case per new kernel (the emulation cannot see real races)
   for tool in memcheck racecheck; do
     timeout 600 compute-sanitizer --tool $tool python -m pytest -q -m gpu \
