@@ -47,6 +47,10 @@ PY
         > $out/${tag}_exp_sanitizer_$tool.log 2>&1
     echo "compute-sanitizer $tool rc=$?"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|passed|failed" $out/${tag}_exp_sanitizer_$tool.log | tail -4
   done
+  for v in 0 1; do
+    timeout 300 python tools/bench_c4.py 3 $v > $out/${tag}_exp_c4_variant$v.json 2> $out/${tag}_exp_c4_variant$v.err
+    echo "config C4 (Poisson, hollow sphere) variant $v rc=$?"; cat $out/${tag}_exp_c4_variant$v.json
+  done
   timeout 300 python tools/bench_kernels.py > $out/${tag}_exp_kernels.json 2> $out/${tag}_exp_kernels.err
   echo "kernel timings rc=$?"; cat $out/${tag}_exp_kernels.json
   # the solver's options one after the other on config C2 (block+caps = the experimental solver)
