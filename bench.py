@@ -71,6 +71,8 @@ def workload(ngpus, name):
         return 'uv_sphere_318x159_N100488 (size of config C3)', 318, 159
     if name == 'small':
         return 'uv_sphere_48x24_N2208 (smoke size)', 48, 24
+    if name == 'tiny':
+        return 'uv_sphere_16x11_N320 (emulation size: tools/emu/run_emulated.py)', 16, 11
     # weak scaling from C2: N^2/P fixed  ->  n_theta ~ 142 * P^(1/4)
     nt = int(round(142 * ngpus ** 0.25 / 2.0)) * 2
     return 'uv_sphere_{0}x{1}_N{2} (C2 scaled to {3} GPUs, N^2/GPU fixed)'.format(
@@ -552,7 +554,7 @@ def main():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--workload', default='auto', choices=['auto', 'c2', 'c3', 'c5', 'small', 'bolt'],
+    ap.add_argument('--workload', default='auto', choices=['auto', 'c2', 'c3', 'c5', 'small', 'tiny', 'bolt'],
                     help="auto = config C2 on one GPU, C2 scaled with N^2/GPU fixed on several; c3/c5 = "
                          "UV spheres of the C3/C5 sizes; bolt = config C3's own geometry (refined "
                          "testBoltFine, 84,600 triangles)")

@@ -344,3 +344,54 @@ def test_sliver_block_partition_general_position():
     starts, runs = rp.sliverBlockPartition(xyz, tri, budgetFraction=1e-6, budgetFloor=0)
     assert runs == [] and starts == list(range(nT))
     assert rp.sliverBlockPartition(numpy.zeros((0, 3)), numpy.zeros((0, 3), int)) == ([0], [])
+
+
+def _run_emulated(args, timeout=900):
+    """tools/emu/run_emulated.py: a Python entry point of the repository against the emulated
+    library (the build container has no GPU)."""
+    env = dict(os.environ, ICQB_EMU_SMS='1')     # sizes the emulated grids (and the DFMA peak loop)
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'tools', 'emu', 'run_emulated.py')] + args,
+                         capture_output=True, text=True, timeout=timeout, cwd=ROOT, env=env)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-3000:]
+    return out.stdout
+
+
+@pytest.mark.parametrize('options', [
+    [],
+    ['--preconditioner', 'block+caps', '--block-tiles', '2', '--mixed-switch', '1e-6',
+     '--assembly-variant', '1']])
+def test_bench_json_line_in_emulation(options):
+    """bench.py end to end (timed loop, fp64 peak, end-to-end leg through LaplaceSolver, CPU
+    baseline, JSON line) on a 320-triangle sphere with the emulated library: every key of the
+    bench contract is there and the solve converged -- for the defaults and for the
+    experimental options."""
+    import json
+    text = _run_emulated(['bench.py', '--workload', 'tiny', '--steps', '1', '--warmup', '1',
+                          '--e2e-steps', '1', '--cpu-sample', '120'] + options)
+    line = json.loads([ln for ln in text.splitlines() if ln.startswith('{')][-1])
+    for key in ('metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step',
+                'higher_is_better', 'scaling', 'vs_baseline', 'dtype', 'data', 'config', 'roofline',
+                'cpu_baseline', 'e2e', 'gpu_launches', 'clocks'):
+        assert key in line, key
+    assert line['config']['workload'].startswith('uv_sphere_16x11_N320')
+    assert line['n_gpus'] == 1 and line['dtype'] == 'f64' and line['value'] > 0
+    assert line['phases']['cg_converged'] and line['phases']['cg_backward_error_max_norm'] < 1e-12
+    for key in ('bound', 'achieved', 'peak', 'unit', 'frac', 'traffic'):
+        assert key in line['roofline'], key
+    for key in ('value', 'unit', 'h2d_bytes_per_step', 'd2h_bytes_per_step', 'host_phases_ms'):
+        assert key in line['e2e'], key
+    assert line['e2e']['h2d_bytes_per_step'] > 0 and line['e2e']['d2h_bytes_per_step'] > 0
+    for key in ('value', 'unit', 'cores', 'kind', 'sample'):
+        assert key in line['cpu_baseline'], key
+    assert line['gpu_launches'] > 0
+    if '--assembly-variant' in options:
+        assert line['roofline_assembly']['far_field_fraction'] is not None
+    if '--mixed-switch' in options:
+        assert line['phases']['cg_float32_products'] > 0
+
+
+def test_smoke_in_emulation():
+    """__graft_entry__.smoke() (LaplaceSolver on a 320-triangle sphere, checked against the
+    oracle) with the emulated library."""
+    text = _run_emulated(['__graft_entry__:smoke'])
+    assert 'smoke: N=320' in text
