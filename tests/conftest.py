@@ -12,6 +12,13 @@ GOLDEN = os.path.join(ROOT, 'tests', 'golden')
 
 def pytest_configure(config):
     config.addinivalue_line('markers', 'gpu: needs a CUDA device (B200); run with -m gpu')
+    # ICQB_EMULATE=1 (build container, no GPU): run `-m gpu` tests against the CPU emulation of
+    # the library (tools/emu/run_emulated.py) -- a dry run of the tests' own code and of the host
+    # layer before GPU time is spent on them; slow, so pick small cases with -k
+    if os.environ.get('ICQB_EMULATE') == '1':
+        sys.path.insert(0, os.path.join(ROOT, 'tools', 'emu'))
+        import run_emulated
+        run_emulated.install()
 
 
 @pytest.fixture(scope='session')
