@@ -87,6 +87,7 @@ def install():
         out = real_to(self, *args, **kwargs)
         return out.clone() if out.data_ptr() == self.data_ptr() else out    # a copy, as H2D is
     torch.Tensor.to = to
+    torch.Tensor.cuda = lambda self, *a, **k: self.clone()    # H2D copy
     real_cpu = torch.Tensor.cpu
     torch.Tensor.cpu = lambda self, *a, **k: real_cpu(self, *a, **k).clone()   # a copy, as D2H is
     return lib
