@@ -469,7 +469,7 @@ def run_b200(args):
             fast, allp = ctypes.c_int64(0), ctypes.c_int64(0)
             ctx.check(lib.icqb_assembly_stats(ctx.handle, ctypes.byref(fast), ctypes.byref(allp)))
             far_frac = fast.value / max(allp.value, 1)
-            instr_per_eval = 16.0 - far_frac * (3.0 if args.assembly_variant == 1 else 4.0)
+            instr_per_eval = 16.0 - far_frac * (3.0 if args.assembly_variant in (1, 3) else 4.0)
         gemv_bytes = 8.0 * stored     # bytes of matrix this rank streams per product
         gemv_gbs = gemv_bytes / (gemv_ms * 1e-3) / 1e9 if gemv_ms > 0 else 0.0
         # products that ran: iterations + the initial one + one per confirmation (those
@@ -571,10 +571,10 @@ def main():
                          "block+caps there")
     ap.add_argument('--block-tiles', type=int, default=1,
                     help='experimental, with block+caps: 128-triangle tiles per diagonal block')
-    ap.add_argument('--assembly-variant', type=int, default=0, choices=[0, 1, 2],
+    ap.add_argument('--assembly-variant', type=int, default=0, choices=[0, 1, 2, 3, 4],
                     help='experimental arithmetic of the off-diagonal kernel (include/icqb.h, '
                          'icqb_set_assembly_variant): 0 validated kernel, 1 far-field split, '
-                         '2 far-field split + Newton reciprocal square root')
+                         '2 far-field split + Newton reciprocal square root, 3/4 = 1/2 at three CTAs per SM')
     ap.add_argument('--mixed-switch', type=float, default=0.,
                     help='experimental, with block+caps and lower storage: relative residual below '
                          'which the CG products stream a float32 copy of the matrix (1e-6); 0 = off')

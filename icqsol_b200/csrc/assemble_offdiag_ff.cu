@@ -229,7 +229,7 @@ __device__ __forceinline__ PairSums pair_exact(const OffDiagParams& P, long long
 }
 
 template <bool WITH_K, int RSQ>
-__global__ void __launch_bounds__(kTileObs) k_offdiag_ff(const OffDiagParams P) {
+__device__ __forceinline__ void offdiag_ff_body(const OffDiagParams& P) {
     __shared__ __align__(128) double s_src[kStages][kSub * kQpStride];
     __shared__ __align__(8) uint64_t s_bar[kStages];
 
@@ -380,6 +380,20 @@ __global__ void __launch_bounds__(kTileObs) k_offdiag_ff(const OffDiagParams P) 
     }
 }
 
+// The kernel proper, with as many registers as it wants (254 for G+K: two CTAs per SM, as
+// k_offdiag) ...
+template <bool WITH_K, int RSQ>
+__global__ void __launch_bounds__(kTileObs) k_offdiag_ff(const OffDiagParams P) {
+    offdiag_ff_body<WITH_K, RSQ>(P);
+}
+
+// ... and compiled for three CTAs per SM (at most 168 registers; G+K then spills ~350 bytes,
+// outside the fast loop for the most part): variants 3 and 4, to be measured against 1 and 2.
+template <bool WITH_K, int RSQ>
+__global__ void __launch_bounds__(kTileObs, 3) k_offdiag_ff3(const OffDiagParams P) {
+    offdiag_ff_body<WITH_K, RSQ>(P);
+}
+
 // centroid and radius (largest centroid-vertex distance, rounded up a little) per triangle;
 // the padding rows get a huge radius so that a padded triangle is never "far"
 __global__ void __launch_bounds__(128) k_bounds(const double* __restrict__ verts, long long n,
@@ -430,16 +444,15 @@ int launch_offdiag_ff(icqb_ctx* ctx, const OffDiagParams& params, dim3 grid, boo
     P.guard2 = guard * guard;
     P.stats = ctx->d_ffstats;
     cudaEventRecord(ctx->ev0, ctx->stream);
-    if (ctx->offdiag_variant == 2) {
-        if (withK)
-            k_offdiag_ff<true, 2><<<grid, kTileObs, 0, ctx->stream>>>(P);
-        else
-            k_offdiag_ff<false, 2><<<grid, kTileObs, 0, ctx->stream>>>(P);
-    } else {
-        if (withK)
-            k_offdiag_ff<true, 3><<<grid, kTileObs, 0, ctx->stream>>>(P);
-        else
-            k_offdiag_ff<false, 3><<<grid, kTileObs, 0, ctx->stream>>>(P);
+    switch (ctx->offdiag_variant * 2 + (withK ? 1 : 0)) {
+        case 2: k_offdiag_ff<false, 3><<<grid, kTileObs, 0, ctx->stream>>>(P); break;
+        case 3: k_offdiag_ff<true, 3><<<grid, kTileObs, 0, ctx->stream>>>(P); break;
+        case 4: k_offdiag_ff<false, 2><<<grid, kTileObs, 0, ctx->stream>>>(P); break;
+        case 5: k_offdiag_ff<true, 2><<<grid, kTileObs, 0, ctx->stream>>>(P); break;
+        case 6: k_offdiag_ff3<false, 3><<<grid, kTileObs, 0, ctx->stream>>>(P); break;
+        case 7: k_offdiag_ff3<true, 3><<<grid, kTileObs, 0, ctx->stream>>>(P); break;
+        case 8: k_offdiag_ff3<false, 2><<<grid, kTileObs, 0, ctx->stream>>>(P); break;
+        default: k_offdiag_ff3<true, 2><<<grid, kTileObs, 0, ctx->stream>>>(P); break;
     }
     cudaEventRecord(ctx->ev1, ctx->stream);
     ctx->launches += 1;
@@ -454,8 +467,8 @@ extern "C" {
 
 int icqb_set_assembly_variant(icqb_ctx* ctx, int variant) {
     if (!ctx) return ICQB_EARG;
-    if (variant < 0 || variant > 2)
-        return set_error(ctx, ICQB_EARG, "icqb_set_assembly_variant: variant must be 0, 1 or 2");
+    if (variant < 0 || variant > 4)
+        return set_error(ctx, ICQB_EARG, "icqb_set_assembly_variant: variant must be 0 ... 4");
     ctx->offdiag_variant = variant;
     return ICQB_OK;
 }

@@ -139,7 +139,8 @@ struct icqb_ctx {
     double* d_area2 = nullptr;   // [ntri_pad]  |db x dc|
     double* d_nrm = nullptr;     // [ntri_pad][4]  unit normal, n . pa
     // experimental far-field split of the off-diagonal assembly (assemble_offdiag_ff.cu)
-    int offdiag_variant = 0;     // 0 validated kernel, 1 far-field split, 2 + Newton reciprocal square root
+    int offdiag_variant = 0;     // 0 validated kernel, 1 far-field split, 2 + Newton reciprocal square root,
+                                 // 3 / 4 = 1 / 2 compiled for three CTAs per SM
     double coord_max = 0.0;      // max |coordinate| of the mesh points
     double* d_bound = nullptr;   // [ntri_pad + 128][4]  centroid, radius; built on first use
     unsigned long long* d_ffstats = nullptr;   // [2] (warp, source) pairs on the fast path / all

@@ -160,7 +160,9 @@ int icqb_gemv_host(icqb_ctx* ctx, uint64_t dA, int64_t nrows, int64_t ncols, int
  *              observer's own vertex, 9 / 13 instructions per evaluation, entries within a
  *              few ulp of variant 0; all other pairs are evaluated as in variant 0;
  *   variant 2  variant 1 with a Newton step instead of the third-order step in the far-field
- *              reciprocal square root (8 / 12 instructions; relative error <= 2.4e-14).
+ *              reciprocal square root (8 / 12 instructions; relative error <= 2.4e-14);
+ *   variants 3, 4  = 1, 2 compiled for three CTAs per SM (at most 168 registers; the G+K kernel
+ *              then spills a little) instead of two -- which one is faster is a measurement.
  * The stored layouts and every other entry point are unchanged. */
 int icqb_set_assembly_variant(icqb_ctx* ctx, int variant);
 /* After an assembly with variant 1 or 2: how many (warp of 32 observers, source triangle)

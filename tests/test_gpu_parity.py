@@ -848,7 +848,7 @@ def test_far_field_split_every_entry(ctx, oracle_mod, variant, nt, nph):
 
 
 @experimental
-@pytest.mark.parametrize('variant', [1, 2])
+@pytest.mark.parametrize('variant', [1, 2, 3, 4])
 def test_far_field_split_row_blocks_and_ragged(ctx, golden, oracle_mod, variant):
     """Row blocks (direct-only tiles left and right of the block) on the bolt, ragged sizes."""
     xyz, tri = golden.mesh('boltFine')
