@@ -17,7 +17,7 @@ if [ "$n" = "1" ]; then
   # three variants side by side (same workload, same run), then one full capture of variant 1
   timeout 900 python -m pytest tests -m gpu -q -k "far_field" > $out/${tag}_exp_ff_pytest.log 2>&1
   echo "far-field pytest rc=$?"; tail -5 $out/${tag}_exp_ff_pytest.log
-  for v in 0 1 2; do
+  for v in 0 1 2 3 4; do
     timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --e2e-steps 1 --assembly-variant $v \
         > $out/${tag}_exp_bench_ff$v.json 2> $out/${tag}_exp_bench_ff$v.err
     echo "bench variant $v rc=$?"; python - <<PY
