@@ -35,6 +35,8 @@
 // FP64-pipe instructions per evaluation on the fast path (SASS counts in DESIGN.md 4.1b):
 // G 9 (8 with the Newton step) instead of 12, G+K 13 (12) instead of 16, plus the
 // per-source-point work above.
+#include <stdlib.h>
+
 #include "offdiag_common.cuh"
 
 namespace icqb {
@@ -439,7 +441,13 @@ int launch_offdiag_ff(icqb_ctx* ctx, const OffDiagParams& params, dim3 grid, boo
     if (!ctx->d_ffstats) ICQB_CUDA(ctx, cudaMalloc(&ctx->d_ffstats, 2 * sizeof(unsigned long long)));
     ICQB_CUDA(ctx, cudaMemsetAsync(ctx->d_ffstats, 0, 2 * sizeof(unsigned long long), ctx->stream));
     P.bound = ctx->d_bound;
-    P.kappa = kFarKappa;
+    // ICQB_FF_KAPPA (experiments): separation factor of the far-field test, 2 <= kappa <= 16
+    static const double kappa = [] {
+        const char* e = getenv("ICQB_FF_KAPPA");
+        const double v = e ? atof(e) : kFarKappa;
+        return (v >= 2.0 && v <= 16.0) ? v : kFarKappa;
+    }();
+    P.kappa = kappa;
     const double guard = ctx->coord_max / 512.0;
     P.guard2 = guard * guard;
     P.stats = ctx->d_ffstats;
