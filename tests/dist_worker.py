@@ -79,7 +79,7 @@ def main():
     # build this matrix, so columns are taken as device products G e_j and compared with oracle
     # columns, and the response is checked against oracle rows (tests/test_gpu_parity.py,
     # _sampled_checks); every rank checks different columns
-    nt = int(round(142 * world ** 0.25 / 2.0)) * 2
+    nt = int(os.environ.get('ICQB_WORKER_NT', int(round(142 * world ** 0.25 / 2.0)) * 2))   # (override: dry runs)
     xyz, tri = uvSphere(1.0, nt, nt // 2)
     n = tri.shape[0]
     print('rank', rank, 'full-size case', nt, nt // 2, n, flush=True)

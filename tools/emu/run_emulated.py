@@ -88,6 +88,14 @@ def install():
         return out.clone() if out.data_ptr() == self.data_ptr() else out    # a copy, as H2D is
     torch.Tensor.to = to
     torch.Tensor.cuda = lambda self, *a, **k: self.clone()    # H2D copy
+    # a single-rank process group for scripts that ask for NCCL (tests/dist_worker.py)
+    import torch.distributed as dist
+    real_init = dist.init_process_group
+
+    def init_process_group(backend=None, **kwargs):
+        kwargs.pop('device_id', None)
+        return real_init('gloo', **kwargs)
+    dist.init_process_group = init_process_group
     real_cpu = torch.Tensor.cpu
     torch.Tensor.cpu = lambda self, *a, **k: real_cpu(self, *a, **k).clone()   # a copy, as D2H is
     return lib
