@@ -5,7 +5,7 @@ Solve Laplace equation given Dirichlet boundary conditions
 Same command line as the reference's examples/solveLaplace.py (--input, --dirichlet,
 --refine, --input_name, --output_name, --ascii, --output, --verbose); the matrix assembly
 and the solve run on the GPU (icqsol_b200), the mesh is read and written with the
-VTK-free legacy POLYDATA reader/writer.  PLY input needs VTK and is not supported.
+VTK-free readers (legacy POLYDATA, PLY) and the legacy POLYDATA writer.
 
     python examples/solveLaplace.py --input sphere.vtk --dirichlet 'sin(pi*x)*cos(pi*y)*z' \
         --output out.vtk --verbose
@@ -21,6 +21,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 from icqsol_b200.bem.icqLaplaceSolver import LaplaceSolver  # noqa: E402
 from icqsol_b200.mesh.vtk_legacy_io import readVtkPolyData, writeVtkPolyData  # noqa: E402
+from icqsol_b200.mesh.ply_io import readPly  # noqa: E402
 
 
 def main(argv=None):
@@ -30,7 +31,7 @@ def main(argv=None):
     description = 'Solve Laplace equation given Dirichlet boundary conditions'
     parser = argparse.ArgumentParser(description=description)
     parser.add_argument('--input', dest='input', default='',
-                        help='Input file (legacy VTK POLYDATA).')
+                        help='Input file (PLY or legacy VTK POLYDATA).')
     parser.add_argument('--dirichlet', dest='dirichlet', default='sin(pi*x)*cos(pi*y)*z',
                         help='Dirichlet boundary conditions, expression of x, y, and z.')
     parser.add_argument('--refine', dest='refine', default=0.0, type=float,
@@ -50,15 +51,17 @@ def main(argv=None):
     if not args.input:
         print('ERROR: must specify input file: --input <file>')
         return 3
-    if args.input.lower().endswith('.ply'):
-        print('ERROR: PLY input needs VTK; convert the file to legacy VTK POLYDATA')
-        return 4
 
     # make sure the field names contain no spaces
     args.input_name = re.sub(r'\s', '_', args.input_name)
     args.output_name = re.sub(r'\s', '_', args.output_name)
 
-    pdata = readVtkPolyData(args.input)
+    # the format of the input -- either vtk or ply, by suffix as util.getFileFormat does
+    # (reference examples/solveLaplace.py:58-69)
+    if args.input.lower().endswith('.ply'):
+        pdata = readPly(args.input)
+    else:
+        pdata = readVtkPolyData(args.input)
 
     maxEdgeLength = float('inf')
     if args.refine > 0:

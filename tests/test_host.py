@@ -395,3 +395,59 @@ def test_smoke_in_emulation():
     oracle) with the emulated library."""
     text = _run_emulated(['__graft_entry__:smoke'])
     assert 'smoke: N=320' in text
+
+
+def test_ply_reader_and_writer(tmp_path):
+    """PLY input of the BEM command line (reference examples/solveLaplace.py:58-69, vtkPLYReader):
+    ASCII / little- / big-endian files, triangles and mixed polygons, extra vertex properties
+    kept as point arrays, unknown elements skipped; the reference's own PLY files when present."""
+    import glob
+    from icqsol_b200.mesh.ply_io import readPly, writePly
+    from icqsol_b200.mesh.polydata import PolyData, extract_mesh
+    from icqsol_b200.mesh.generators import uvSphere
+    xyz, tri = uvSphere(1.0, 8, 5)
+    for binary in (True, False):
+        name = str(tmp_path / ('s%d.ply' % binary))
+        writePly(PolyData.from_arrays(xyz, tri), name, binary)
+        x2, t2 = extract_mesh(readPly(name))
+        assert (x2 == xyz).all() and (numpy.asarray(t2) == tri).all()
+    # mixed polygons, colours, an edge element to skip; all three encodings of the same content
+    pts = numpy.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0], [.5, .5, 1]], numpy.float64)
+    faces = [[0, 1, 2, 3], [0, 1, 4], [1, 2, 4]]
+    red = numpy.array([10, 20, 30, 40, 50], numpy.uint8)
+    head = ('ply\nformat {0} 1.0\ncomment test\nelement vertex 5\nproperty double x\nproperty double y\n'
+            'property double z\nproperty uchar red\nelement edge 1\nproperty int vertex1\n'
+            'property int vertex2\nelement face 3\nproperty list uchar uint vertex_index\n'
+            'property uchar flag\nend_header\n')
+    for fmt, order in (('ascii', None), ('binary_little_endian', '<'), ('binary_big_endian', '>')):
+        name = str(tmp_path / (fmt + '.ply'))
+        with open(name, 'wb') as f:
+            f.write(head.format(fmt).encode('ascii'))
+            if order is None:
+                for p, r in zip(pts, red):
+                    f.write('{0} {1} {2} {3}\n'.format(p[0], p[1], p[2], int(r)).encode())
+                f.write(b'0 1\n')
+                for c in faces:
+                    f.write((' '.join(str(v) for v in [len(c)] + c) + ' 7\n').encode())
+            else:
+                for p, r in zip(pts, red):
+                    f.write(p.astype(order + 'f8').tobytes() + r.tobytes())
+                f.write(numpy.array([0, 1], order + 'i4').tobytes())
+                for c in faces:
+                    f.write(numpy.uint8(len(c)).tobytes() + numpy.array(c, order + 'u4').tobytes() +
+                            numpy.uint8(7).tobytes())
+        pd = readPly(name)
+        x2, c2 = extract_mesh(pd)
+        assert (x2 == pts).all() and [list(c) for c in c2] == faces
+        assert pd.GetPointData().GetArray(0).GetName() == 'red'
+        assert [pd.GetPointData().GetArray(0).GetComponent(i, 0) for i in range(5)] == [10, 20, 30, 40, 50]
+    bad = str(tmp_path / 'bad.ply')
+    open(bad, 'wb').write(b'# vtk DataFile Version 3.0\n')
+    with pytest.raises(ValueError):
+        readPly(bad)
+    for f in sorted(glob.glob('/root/reference/test_results/cyl*.ply')):   # build container only
+        hdr = open(f, 'rb').read(400).decode('latin-1')
+        nv = int(hdr.split('element vertex')[1].split()[0])
+        nf = int(hdr.split('element face')[1].split()[0])
+        x2, c2 = extract_mesh(readPly(f))
+        assert x2.shape == (nv, 3) and len(c2) == nf and numpy.isfinite(x2).all()
