@@ -470,7 +470,11 @@ def run_b200(args):
             ctx.check(lib.icqb_assembly_stats(ctx.handle, ctypes.byref(fast), ctypes.byref(allp)))
             far_frac = fast.value / max(allp.value, 1)
             instr_per_eval = 16.0 - far_frac * (3.0 if args.assembly_variant in (1, 3) else 4.0)
-        gemv_bytes = 8.0 * stored     # bytes of matrix this rank streams per product
+        # bytes of matrix this rank streams per product; with float32 late products
+        # (--mixed-switch) the timed products are a mixture: 8 bytes per stored entry for the
+        # double ones, 4 for the float32 ones, weighted by their share of the iterations
+        frac32 = float(numpy.mean(phase['products32'])) / max(float(numpy.mean(phase['iters'])), 1.0)
+        gemv_bytes = stored * (8.0 - 4.0 * min(max(frac32, 0.0), 1.0))
         gemv_gbs = gemv_bytes / (gemv_ms * 1e-3) / 1e9 if gemv_ms > 0 else 0.0
         # products that ran: iterations + the initial one + one per confirmation (those
         # enqueued behind the stop flag return at once and are not counted)
