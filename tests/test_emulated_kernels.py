@@ -740,3 +740,42 @@ def test_emulated_mixed_precision_multi_rank(emu, oracle_mod, nranks, peer):
     assert abs(iters0 - want_iters) <= 2 and abs(counts[0] - want32) <= 2
     for o in out:
         o[-1].close()
+
+
+def test_emulated_far_field_split_fuzz(emu):
+    """Random triangle soups -- sizes over three decades, a fifth of the triangles slivers,
+    random scale, the whole mesh displaced by up to a few hundred times its size -- through
+    the far-field variants against the validated kernel: G within the bound of the guard
+    (2e-13; it is a few 1e-14 when the displacement is large, 1e-15 otherwise), K to 1e-11."""
+    rng = numpy.random.default_rng(7)
+    h = ctypes.c_void_p()
+    assert emu.icqb_create(ctypes.byref(h), 0) == 0
+    for trial in range(4):
+        n = int(rng.integers(40, 160))
+        scale = 10.0 ** rng.uniform(-3, 3)
+        offset = rng.normal(size=3) * scale * 10.0 ** rng.uniform(-1, 2.5)
+        cen = rng.uniform(-1, 1, size=(n, 3))
+        size = 10.0 ** rng.uniform(-3, -0.3, size=n)
+        e1, e2 = rng.normal(size=(n, 3)), rng.normal(size=(n, 3))
+        sliver = rng.uniform(size=n) < 0.2
+        e2 = numpy.where(sliver[:, None], e1 * rng.uniform(0.5, 1.5, size=(n, 1)) + 0.02 * e2, e2)
+        xyz = numpy.vstack([cen, cen + size[:, None] * e1, cen + size[:, None] * e2]) * scale + offset
+        if trial % 2:
+            xyz = xyz.astype(numpy.float32).astype(numpy.float64)
+        xyz = numpy.ascontiguousarray(xyz)
+        tri = numpy.ascontiguousarray(
+            numpy.stack([numpy.arange(n), n + numpy.arange(n), 2 * n + numpy.arange(n)], 1).astype(numpy.int64))
+        out = {}
+        for variant in (0, 1, 2):
+            assert emu.icqb_set_mesh(h, dp(xyz), xyz.shape[0], lp(tri), n) == 0
+            assert emu.icqb_set_assembly_variant(h, variant) == 0
+            g, k = numpy.full((n, n), numpy.nan), numpy.full((n, n), numpy.nan)
+            assert emu.icqb_assemble_host(h, 5, dp(g), dp(k)) == 0
+            out[variant] = (g, k)
+        off = ~numpy.eye(n, dtype=bool)
+        g0, k0 = out[0]
+        for variant in (1, 2):
+            g, k = out[variant]
+            assert numpy.abs(g[off] / g0[off] - 1.).max() < (2e-13 if variant == 1 else 3e-13)
+            assert numpy.abs(k - k0)[off].max() < 1e-11 * numpy.abs(k0[off]).max()
+    emu.icqb_destroy(h)
