@@ -131,7 +131,7 @@ def sliverTiles(xyz, tri, threshold=30.):
 
 
 def sliverBlockPartition(xyz, tri, blockTiles=1, threshold=30., gapTiles=4, maxTiles=64,
-                         budgetFraction=0.125, budgetFloor=6.4e7):
+                         budgetFraction=0.125, budgetFloor=6.4e7, flagged=None):
     """First tile row of every diagonal block of the experimental preconditioner
     (icqb_cg_set_block_partition) for a mesh whose slivers may sit ANYWHERE in the triangle
     list -- e.g. the poles of the inner sphere of a hollow sphere: every run of tiles that hold
@@ -143,7 +143,9 @@ def sliverBlockPartition(xyz, tri, blockTiles=1, threshold=30., gapTiles=4, maxT
     (N^2 / 2 entries; at least ``budgetFloor`` entries), the gaps are no longer merged; if that is still too much, only runs
     that reach the two ends of the list are kept.
     @return (starts, denseRuns): list of first tile rows; [(first tile, tiles)] of the runs"""
-    flagged = sliverTiles(xyz, tri, threshold)
+    if flagged is None:
+        flagged = sliverTiles(xyz, tri, threshold)
+    flagged = numpy.asarray(flagged, bool)     # (tests pass the tile flags directly)
     nT = flagged.shape[0]
     k = max(int(blockTiles), 1)
     maxTiles = max(int(maxTiles), 1)

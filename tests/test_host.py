@@ -451,3 +451,39 @@ def test_ply_reader_and_writer(tmp_path):
         nf = int(hdr.split('element face')[1].split()[0])
         x2, c2 = extract_mesh(readPly(f))
         assert x2.shape == (nv, 3) and len(c2) == nf and numpy.isfinite(x2).all()
+
+
+def test_sliver_block_partition_properties():
+    """Random tile flags: the partition starts at 0, increases strictly, stays below the tile
+    count, no block exceeds maxTiles, clean stretches are cut into blocks of blockTiles, and --
+    budget permitting -- every run of flagged tiles (gaps merged) lies inside dense blocks
+    that hold nothing else."""
+    from icqsol_b200.bem import icqRowPartition as rp
+    rng = numpy.random.default_rng(11)
+    for trial in range(200):
+        nT = int(rng.integers(1, 120))
+        flagged = rng.uniform(size=nT) < rng.choice([0.0, 0.05, 0.3, 0.9])
+        k = int(rng.choice([1, 2, 8]))
+        maxTiles = int(rng.choice([4, 16, 64]))
+        gap = int(rng.choice([0, 1, 4]))
+        tri = numpy.zeros((nT * 128 - int(rng.integers(0, 128)), 3), int)   # only its length is used
+        starts, runs = rp.sliverBlockPartition(None, tri, blockTiles=k, gapTiles=gap, maxTiles=maxTiles,
+                                               budgetFloor=1e18, flagged=flagged)
+        assert starts[0] == 0 and starts == sorted(set(starts)) and starts[-1] < nT
+        sizes = numpy.diff(starts + [nT])
+        assert sizes.max() <= max(maxTiles, k)
+        block = numpy.searchsorted(starts, numpy.arange(nT), side='right') - 1
+        inRun = numpy.zeros(nT, bool)
+        for a, m in runs:
+            assert m > 1 and flagged[a] and flagged[a + m - 1]
+            inRun[a:a + m] = True
+        # a block never mixes tiles of a dense run with tiles outside it
+        for b in range(len(starts)):
+            members = inRun[block == b]
+            assert members.all() or not members.any()
+        # every flagged tile that is not alone is inside a run
+        idx = numpy.nonzero(flagged)[0]
+        for t in idx:
+            near = [u for u in idx if u != t and abs(u - t) <= gap + 1]
+            if near:
+                assert inRun[t], (trial, t)
