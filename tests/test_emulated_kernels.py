@@ -575,7 +575,7 @@ print('ok')
     assert bad.returncode == -11, (bad.returncode, bad.stdout, bad.stderr[-500:])
 
 
-@pytest.mark.parametrize('order', ['reverse', 'shuffle'])
+@pytest.mark.parametrize('order', ['shuffle'])     # 'reverse' as well: ICQB_EMU_ORDER=reverse pytest ...
 def test_emulated_kernels_under_other_thread_orders(order):
     """The threads of a block run in ascending order between two synchronisation points by
     default; a missing barrier can hide behind that order.  The assembly, product and CG tests
