@@ -3,7 +3,7 @@
 PoissonSolver on the 49,400-triangle hollow sphere (SURVEY.md section 8d) -- G assembly (no K;
 the reference has none and the Poisson response does not need it) + one product v = G charge
 (bem/icqPoissonSolver.py:36), through the public classes, host mesh in / host response out.
-Prints one JSON line.   usage: tools/bench_c4.py [steps] [assembly_variant]"""
+Prints one JSON line.   usage: tools/bench_c4.py [steps] [assembly_variant] [n_theta n_phi (outer sphere; default 100 50)]"""
 import json
 import os
 import sys
@@ -22,7 +22,8 @@ def main():
     from icqsol_b200.bem.icqPoissonSolver import PoissonSolver
     steps = int(sys.argv[1]) if len(sys.argv) > 1 else 3
     variant = int(sys.argv[2]) if len(sys.argv) > 2 else 0
-    xyz, tri = hollowSphere(2.0, 1.0, 100, 50)
+    nt, nph = (int(sys.argv[3]), int(sys.argv[4])) if len(sys.argv) > 4 else (100, 50)
+    xyz, tri = hollowSphere(2.0, 1.0, nt, nph)
     n = tri.shape[0]
     charge = numpy.ones(n)
     e2e, asm, prod = [], [], []
@@ -41,7 +42,7 @@ def main():
             prod.append(solver.ctx.last_ms(3))
         del solver
     ntiles = sum(i + 1 for i in range((n + 127) // 128))
-    out = {'config': 'C4: hollow sphere, N={0}, PoissonSolver, diagonal order 5'.format(n),
+    out = {'config': 'C4: hollow sphere {1}x{2}, N={0}, PoissonSolver, diagonal order 5'.format(n, nt, nph),
            'assembly_variant': variant, 'e2e_ms': round(1e3 * float(numpy.mean(e2e)), 2),
            'assembly_ms': round(float(numpy.mean(asm)), 2),
            'G_entries_per_s_assembly': float(n) * n / (numpy.mean(asm) * 1e-3),
