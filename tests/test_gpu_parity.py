@@ -638,37 +638,6 @@ def test_example_solve_laplace_cli(tmp_path, oracle_mod, capsys):
     assert numpy.abs(v + g.dot(sigma)).max() / numpy.abs(v).max() < 1e-12
 
 
-def test_example_solve_laplace_cli_ply_input(tmp_path, oracle_mod):
-    """The command line's other input format (reference examples/solveLaplace.py:58-69): the same
-    mesh as PLY gives the same response file content as the legacy-VTK input."""
-    import importlib.util
-    import os
-    from icqsol_b200.mesh.generators import uvSphere
-    from icqsol_b200.mesh.polydata import PolyData
-    from icqsol_b200.mesh.ply_io import writePly
-    from icqsol_b200.mesh.vtk_legacy_io import readVtkPolyData, writeVtkPolyData
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    spec = importlib.util.spec_from_file_location('solveLaplacePly',
-                                                  os.path.join(root, 'examples', 'solveLaplace.py'))
-    mod = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(mod)
-    xyz, tri = uvSphere(1.0, 12, 7)                      # float32-representable points
-    out = {}
-    for kind in ('vtk', 'ply'):
-        src, dst = str(tmp_path / ('in.' + kind)), str(tmp_path / ('out_' + kind + '.vtk'))
-        if kind == 'ply':
-            writePly(PolyData.from_arrays(xyz, tri), src, binary=True)
-        else:
-            writeVtkPolyData(PolyData.from_arrays(xyz, tri), src)
-        assert mod.main(['--input', src, '--output', dst, '--dirichlet', 'x*y + z']) == 0
-        out[kind] = readVtkPolyData(dst).GetCellData().GetArray('normal_electric_field').as_numpy()[:, 0]
-    assert (out['ply'] == out['vtk']).all()
-    g = oracle_mod.green_matrix(xyz, tri, 5)
-    cen = (xyz[tri[:, 0]] + xyz[tri[:, 1]] + xyz[tri[:, 2]]) / 3.
-    v = cen[:, 0] * cen[:, 1] + cen[:, 2]
-    assert numpy.abs(v + g.dot(out['ply'])).max() / numpy.abs(v).max() < 1e-12
-
-
 # ---- BASELINE.json configurations at (or near) full size: sampled oracle rows/columns and
 # ---- size-independent properties (the oracle cannot build a whole matrix of this size) ----
 
@@ -773,6 +742,37 @@ def test_subdivide_on_device(golden):
         return numpy.linalg.norm(numpy.cross(p[t[:, 1]] - p[t[:, 0]], p[t[:, 2]] - p[t[:, 0]]), axis=1)
     x2, t2 = subdivideOnDevice(xyz, tri, 4, float32_points=False)
     assert numpy.abs(areas(x2, t2).reshape(-1, 16).sum(1) / areas(numpy.asarray(xyz, float), tri) - 1).max() < 1e-9
+
+
+def test_example_solve_laplace_cli_ply_input(tmp_path, oracle_mod):
+    """The command line's other input format (reference examples/solveLaplace.py:58-69): the same
+    mesh as PLY gives the same response file content as the legacy-VTK input."""
+    import importlib.util
+    import os
+    from icqsol_b200.mesh.generators import uvSphere
+    from icqsol_b200.mesh.polydata import PolyData
+    from icqsol_b200.mesh.ply_io import writePly
+    from icqsol_b200.mesh.vtk_legacy_io import readVtkPolyData, writeVtkPolyData
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location('solveLaplacePly',
+                                                  os.path.join(root, 'examples', 'solveLaplace.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    xyz, tri = uvSphere(1.0, 12, 7)                      # float32-representable points
+    out = {}
+    for kind in ('vtk', 'ply'):
+        src, dst = str(tmp_path / ('in.' + kind)), str(tmp_path / ('out_' + kind + '.vtk'))
+        if kind == 'ply':
+            writePly(PolyData.from_arrays(xyz, tri), src, binary=True)
+        else:
+            writeVtkPolyData(PolyData.from_arrays(xyz, tri), src)
+        assert mod.main(['--input', src, '--output', dst, '--dirichlet', 'x*y + z']) == 0
+        out[kind] = readVtkPolyData(dst).GetCellData().GetArray('normal_electric_field').as_numpy()[:, 0]
+    assert (out['ply'] == out['vtk']).all()
+    g = oracle_mod.green_matrix(xyz, tri, 5)
+    cen = (xyz[tri[:, 0]] + xyz[tri[:, 1]] + xyz[tri[:, 2]]) / 3.
+    v = cen[:, 0] * cen[:, 1] + cen[:, 2]
+    assert numpy.abs(v + g.dot(out['ply'])).max() / numpy.abs(v).max() < 1e-12
 
 
 # ---- EXPERIMENTAL: dense cap blocks in the preconditioner (cg_caps.cu) ----------------------
