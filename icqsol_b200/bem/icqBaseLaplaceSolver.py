@@ -69,7 +69,8 @@ class BaseLaplaceSolver(BaseSolver):
                        diag(A) G, 'diagonal' = 1/diag (the reference CG class's default,
                        solvers/icqConjugateGradient.py:19), 'block+caps' = EXPERIMENTAL: blocks,
                        with one dense block over every run of tiles that hold sliver triangles
-                       (icqRowPartition.sliverBlockPartition; on a UV sphere the two poles)
+                       (icqRowPartition.sliverBlockPartition; on a UV sphere the two poles),
+                       'auto' = EXPERIMENTAL: 'block+caps' if the mesh has such runs, else 'block'
         @param blockTiles EXPERIMENTAL, with 'block+caps' only: tiles (of 128 triangles) per
                        diagonal block between the caps (numpy model at config C2: 167 iterations
                        with 1, 121 with 2, 92 with 8)
@@ -115,8 +116,12 @@ class BaseLaplaceSolver(BaseSolver):
         mark('mesh intake (host)')
         if storage not in ('lower', 'full'):
             raise ValueError("storage must be 'lower' or 'full'")
-        if preconditioner not in ('block', 'diagonal', 'block+caps'):
-            raise ValueError("preconditioner must be 'block', 'diagonal' or 'block+caps'")
+        if preconditioner not in ('block', 'diagonal', 'block+caps', 'auto'):
+            raise ValueError("preconditioner must be 'block', 'diagonal', 'block+caps' or 'auto'")
+        if preconditioner == 'auto':
+            # EXPERIMENTAL: the dense sliver blocks only where the mesh has runs of sliver tiles
+            hasRuns = bool(rowPartition.sliverBlockPartition(self._xyz, self._tri)[1])
+            preconditioner = 'block+caps' if hasRuns else 'block'
         self.storage = storage
         self.preconditioner = preconditioner
         self.directFallback = bool(directFallback)
