@@ -10,6 +10,9 @@ python bench.py --steps 5 --warmup 3 > $out/${tag}_bench.json 2> $out/${tag}_ben
 cat $out/${tag}_bench.json
 python bench.py --impl reference --steps 2 --warmup 1 > $out/${tag}_bench_reference.json 2>> $out/${tag}_bench.err; echo "bench reference rc=$?"
 cat $out/${tag}_bench_reference.json
+# config C3's own geometry (refined bolt, 84,600 triangles) on this one GPU, validated path
+timeout 300 python bench.py --workload bolt --steps 2 --warmup 1 --e2e-steps 1 --no-cpu-baseline --max-iters 1500 > $out/${tag}_bench_bolt.json 2> $out/${tag}_bench_bolt.err; echo "bench bolt rc=$?"
+cat $out/${tag}_bench_bolt.json
 if [ "$2" != "noncu" ]; then
 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file $out/${tag}_launches.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --e2e-steps 0 > $out/${tag}_ncu_launches.log 2>&1; echo "ncu list rc=$?"
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:'k_symv|k_cg_resid' -s 40 -c 6 -o $out/${tag}_solve -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline --e2e-steps 0 > $out/${tag}_ncu_solve.log 2>&1; echo "ncu solve rc=$?"
