@@ -272,7 +272,6 @@ def run_b200(args):
     from icqsol_b200 import _lib
     from icqsol_b200.bem import icqRowPartition as rowPartition
     from icqsol_b200.bem.icqBaseLaplaceSolver import leadingDimension
-    from icqsol_b200.mesh.generators import uvSphere
     from icqsol_b200.mesh.polydata import PolyData, DataArray
     from icqsol_b200.bem.icqLaplaceSolver import LaplaceSolver
 
