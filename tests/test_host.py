@@ -487,3 +487,11 @@ def test_sliver_block_partition_properties():
             near = [u for u in idx if u != t and abs(u - t) <= gap + 1]
             if near:
                 assert inRun[t], (trial, t)
+
+
+def test_direct_fallback_flow_in_emulation():
+    """directFallback=True: an unconverged CG hands over to the LU of a row-major re-assembly
+    (tests/emulated_scripts/direct_fallback.py, both storages) -- with the emulated library,
+    torch.linalg.solve on the host standing in for cuSOLVER."""
+    text = _run_emulated([os.path.join('tests', 'emulated_scripts', 'direct_fallback.py')])
+    assert text.count('direct fallback ok') == 2
