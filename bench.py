@@ -509,9 +509,9 @@ def run_b200(args):
                        if gemv_ms > 0 else 0.0},
             'roofline': None,
             'roofline_assembly': {
-                'bound': 'fp64', 'kernel': 'k_offdiag<G+K>', 'achieved': achieved,
+                'bound': 'fp64', 'kernel': 'k_offdiag<G+K>' if not args.assembly_variant else 'k_offdiag_ff<G+K> (variant {0})'.format(args.assembly_variant), 'achieved': achieved,
                 'peak': peak.value, 'unit': 'TFLOP/s', 'frac': achieved / peak.value,
-                'traffic': traffic_of('k_offdiag', args.storage, n),
+                'traffic': traffic_of('k_offdiag', args.storage, n) if not args.assembly_variant else None,
                 'peak_source': 'DFMA loop measured in this run (icqb_measure_fp64_peak)',
                 'flop_per_evaluation': FLOP_PER_EVAL_GK, 'fp64_instr_per_evaluation': instr_per_eval,
                 'far_field_fraction': far_frac,
