@@ -1,28 +1,42 @@
 #!/usr/bin/env python
 """Benchmark of the boundary-element hot path (BASELINE.json: "G+K entries/sec
-(fp64) and CG GEMV GB/s ... vs host-CPU reference").
+(fp64) and CG GEMV GB/s at 1/2/4/8 B200 vs host-CPU reference").
 
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
     python bench.py --impl reference --gpus N --steps K ...  # reference CPU path
 
-One step = one pass of the hot path on a synthetic refined UV sphere
-(SURVEY.md section 8d): fused G+K assembly (diagonal + off-diagonal kernels) into
-resident HBM buffers, then the dense CG solve of G sigma = -v to a backward error
-max|v + G sigma| <= 5e-13 max|v| (inside the 1e-12 parity criterion).  N=1 runs config C2 (19,880 triangles); for N>1 the mesh is
-refined so that the N^2 matrix work per GPU stays fixed ("weak" scaling), rows
-block-sharded over the ranks, NCCL only inside the CG.
+One step = one pass of the hot path over one mesh: fused G+K assembly (diagonal +
+off-diagonal kernels) into resident HBM buffers, then the dense solve of G sigma = -v to a
+backward error max|v + G sigma| <= 5e-13 max|v| (inside the 1e-12 parity criterion).
+
+Workloads:
+  N = 1 (default)  config C2: UV sphere, 19,880 triangles.
+  N > 1 (default)  config C3's own geometry: the reference's test_results/testBoltFine.vtk with
+                   every triangle cut into 36 (84,600 triangles), the SAME problem on 2, 4 and
+                   8 GPUs -> "strong" scaling.  It also fits ONE B200 (--gpus 1 --workload bolt
+                   is the base of that curve; profiles/ holds the 1/2/4/8 runs).
+  --workload c3|c5 UV spheres of 100,488 / 199,808 triangles (C3 size, config C5);
+  --workload c4    config C4: 49,400-triangle hollow sphere, G+K assembly + the Poisson product
+                   v = G q (bem/icqPoissonSolver.py:36) instead of the solve;
+  --workload weak  C2 refined so that N^2 / GPU stays fixed (round 1's curve).
 
 value   = G+K entries per second over the whole step = 2*N^2 / ms_per_step
           (N^2 entries per matrix are DEFINED by a step in either storage: in 'lower'
           storage the upper half is the mirror rule applied on read)
-e2e     = same metric through the public Python API (LaplaceSolver on a host
+e2e     = same metric through the public Python API (LaplaceSolver / PoissonSolver on a host
           polydata -> host response), host<->device copies inside the timed region
-roofline= dominant kernel (fused G+K off-diagonal assembly) against the FP64 FMA
-          rate measured on this GPU in the same run; roofline_gemv = CG GEMV against
-          MEASURED_PEAKS.json's HBM copy bandwidth
-cpu_baseline = the reference's own C++ (oracle/_ref/libicqref.so, unmodified
-          sources) or, when that was not built, the C restatement, on a bounded
-          sub-mesh sample, 1 thread (the reference ships single-threaded).
+roofline= dominant kernel (fused G+K off-diagonal assembly) against the FP64 FMA rate measured
+          on this GPU in the same run; roofline_gemv = the CG product (+ its exchange between
+          the ranks) against MEASURED_PEAKS.json's HBM copy bandwidth, heaviest rank
+phases  = per-phase times: mean over the steps on rank 0, and max / min over the ranks
+g_only  = G entries per second of a G-only pass (what the reference computes: it has no K)
+cpu_baseline = the reference's own C++ for G (oracle/_ref/libicqref.so, unmodified sources)
+          and the C restatement of K (the reference has no K), on a bounded sub-mesh sample,
+          1 thread (the reference ships single-threaded).
+--impl reference = the same step on the host cores: G by the reference's C++, K by the C
+          restatement, self terms, and the reference's LU (numpy.linalg.solve), on a bounded
+          sample; `value` is extrapolated to the config's N by the stated rule (assembly by
+          pair count, LU by N^3).
 """
 import argparse
 import json
@@ -44,26 +58,39 @@ UNIT = 'entries/s'
 EXPR_V = '1./sqrt(x**2 + (y-2.)**2 + (z-4.)**2)'   # CMakeLists.txt:487 of the reference
 FLOP_PER_EVAL_G = 12.0
 FLOP_PER_EVAL_GK = 18.0    # + 1/r^3 (2 mul) and two weighted accumulations (2 fma), DESIGN.md
+DEFAULT_BLOCK_TILES = 8    # diagonal blocks of the CG preconditioner, in 128-triangle tiles
+REFERENCE_WORKERS = 16     # host processes of the reference arm (fewer if the box has fewer cores)
+
+
+def resolve_workload(ngpus, name):
+    if name != 'auto':
+        return name
+    return 'c2' if ngpus == 1 else 'bolt'
 
 
 def make_mesh(ngpus, name):
-    """(label, xyz, tri) of the workload: a UV sphere, or -- 'bolt' -- config C3's geometry:
-    the reference's test_results/testBoltFine.vtk (2,350 triangles, kept as a golden fixture in
-    tests/golden/meshes.npz) with every triangle cut into 36 (84,600 triangles)."""
+    """(label, xyz, tri) of the workload."""
+    name = resolve_workload(ngpus, name)
     if name == 'bolt':
+        # config C3's geometry: the reference's test_results/testBoltFine.vtk (2,350 triangles,
+        # kept as a golden fixture in tests/golden/meshes.npz) with every triangle cut into 36
         from icqsol_b200.mesh.generators import subdivide
         m = numpy.load(os.path.join(ROOT, 'tests', 'golden', 'meshes.npz'))
         xyz, tri = subdivide(m['boltFine_xyz'], m['boltFine_tri'], 6)
         return 'testBoltFine_k6_N{0} (config C3: refined bolt)'.format(tri.shape[0]), xyz, tri
+    if name == 'c4':
+        from icqsol_b200.mesh.generators import hollowSphere
+        xyz, tri = hollowSphere(2.0, 1.0, 100, 50)
+        return 'hollow_sphere_100x50+200x100_N{0} (config C4, Poisson product)'.format(tri.shape[0]), xyz, tri
     from icqsol_b200.mesh.generators import uvSphere
-    label, nt, nph = workload(ngpus, name)
+    label, nt, nph = sphere_workload(ngpus, name)
     xyz, tri = uvSphere(1.0, nt, nph)
     return label, xyz, tri
 
 
-def workload(ngpus, name):
-    """(label, n_theta, n_phi) of the UV sphere for this GPU count."""
-    if name == 'c2' or (name == 'auto' and ngpus == 1):
+def sphere_workload(ngpus, name):
+    """(label, n_theta, n_phi) of the UV sphere workloads."""
+    if name == 'c2':
         return 'uv_sphere_142x71_N19880 (config C2)', 142, 71
     if name == 'c5':
         return 'uv_sphere_448x224_N199808 (config C5)', 448, 224
@@ -77,6 +104,29 @@ def workload(ngpus, name):
     nt = int(round(142 * ngpus ** 0.25 / 2.0)) * 2
     return 'uv_sphere_{0}x{1}_N{2} (C2 scaled to {3} GPUs, N^2/GPU fixed)'.format(
         nt, nt // 2, 2 * nt * (nt // 2 - 1), ngpus), nt, nt // 2
+
+
+def scaling_label(ngpus, name):
+    """'strong': the problem is fixed whatever the GPU count (every workload but 'weak')."""
+    return 'weak' if resolve_workload(ngpus, name) == 'weak' else 'strong'
+
+
+def bench_config(args, label, n, world):
+    """`config` of the JSON line -- the SAME dictionary for the CUDA arm and the reference arm
+    (nothing in it depends on a GPU being present)."""
+    poisson = resolve_workload(world, args.workload) == 'c4'
+    lower = args.storage == 'lower'
+    return {
+        'workload': label, 'triangles': int(n), 'diag_order': 5, 'offdiag_order': 8,
+        'step': ('fused G+K assembly + Poisson product v = G q' if poisson else
+                 'fused G+K assembly + dense solve of G sigma = -v (max|v+G sigma| <= 5e-13 max|v|)'),
+        'storage': args.storage, 'preconditioner': args.preconditioner,
+        'block_tiles': args.block_tiles, 'assembly_variant': args.assembly_variant,
+        'mixed_switch': args.mixed_switch,
+        'parallelism': ('folded row blocks balanced by stored tiles, lower storage x{0}' if lower
+                        else 'row-block x{0}').format(world),
+        'l2': 'inputs larger than L2 ({0:.2f} GB of G streamed per product per GPU)'.format(
+            (4.0 if lower else 8.0) * n * n / world / 1e9)}
 
 
 def centroid_potential(xyz, tri):
@@ -189,73 +239,124 @@ def traffic_of(kernel, storage, n):
 # ---------------------------------------------------------------------------------------
 
 def _ref_worker(args):
-    xyz, tri, order, use_ref = args
+    """G (reference C++ when built, else the C restatement), the self terms and K (C restatement:
+    the reference has none) of one sub-mesh; returns the seconds spent on (G, K)."""
+    xyz, tri, order, use_ref, with_k = args
     from oracle import oracle
+    n = tri.shape[0]
     t0 = time.perf_counter()
     if use_ref:
         g = oracle.ref_offdiag(xyz, tri)
     else:
         g = oracle.offdiag(xyz, tri)
     g[numpy.diag_indices_from(g)] = oracle.diag(xyz, tri, order)
-    return time.perf_counter() - t0, float(g[0, 1])
+    t1 = time.perf_counter()
+    if with_k:
+        oracle.k_block(xyz, tri, 0, n, 0, n, threads=False)
+    t2 = time.perf_counter()
+    return t1 - t0, t2 - t1
 
 
-def cpu_assembly_sample(xyz, tri, ns, workers, order=5):
-    """Each worker assembles G for its own ns-triangle sub-mesh of the workload with
-    the reference's C++ (off-diagonal) and the restated self term.  Returns
-    (seconds wall, entries, kind)."""
+def cpu_assembly_sample(xyz, tri, ns, workers, order=5, with_k=True):
+    """Each worker assembles G (and K) for its own ns-triangle sub-mesh of the workload.
+    Returns (seconds wall, seconds wall of the G part alone (estimate), workers*ns*ns, kind)."""
     from oracle import oracle
     oracle.build()
     use_ref = oracle.have_reference()
     n = tri.shape[0]
+    ns = min(int(ns), n)
     jobs = []
     for w in range(workers):
         start = (w * ns) % max(1, n - ns)
-        jobs.append((xyz, tri[start:start + ns], order, use_ref))
+        jobs.append((xyz, numpy.ascontiguousarray(tri[start:start + ns]), order, use_ref, with_k))
     t0 = time.perf_counter()
     if workers == 1:
-        _ref_worker(jobs[0])
+        parts = [_ref_worker(jobs[0])]
     else:
         import multiprocessing
         with multiprocessing.get_context('fork').Pool(workers) as pool:
-            pool.map(_ref_worker, jobs)
+            parts = pool.map(_ref_worker, jobs)
     wall = time.perf_counter() - t0
-    return wall, workers * ns * ns, 'reference' if use_ref else 'port'
+    tg = max(p[0] for p in parts)
+    tk = max(p[1] for p in parts)
+    wall_g = wall * tg / max(tg + tk, 1e-30)
+    return wall, wall_g, workers * ns * ns, 'reference' if use_ref else 'port'
 
 
 def run_reference(args):
+    """The step of the CUDA arm on the host cores, the way the reference does it: G by its own
+    C++ (bem/icqLaplaceMatrices.cpp:37-105, one process per core on disjoint sub-meshes: the
+    shipped code is single-threaded), self terms, K by the C restatement of its definition
+    (the reference has none), and the reference's solve, numpy.linalg.solve
+    (bem/icqLaplaceSolver.py:36).  Every step works on a bounded sample; `value` extrapolates
+    the sample to the config's N: assembly time by entry count (cost per pair is
+    size-independent), LU time by N^3."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    label, xyz, tri = make_mesh(args.gpus, args.workload)
-    cores = os.cpu_count() or 1
-    ns = args.cpu_sample
-    times = []
-    kind = 'port'
+    world = int(os.environ.get('WORLD_SIZE', str(args.gpus)))
+    label, xyz, tri = make_mesh(world, args.workload)
+    n = tri.shape[0]
+    poisson = resolve_workload(world, args.workload) == 'c4'
+    workers = max(1, min(REFERENCE_WORKERS, os.cpu_count() or 1))
+    ns = min(args.ref_sample, n)
+    nlu = min(args.ref_lu_size, n)
+    from oracle import oracle
+    oracle.build()
+    rng = numpy.random.default_rng(0)
+    lu_mat = None
+    rec = []
     for it in range(args.warmup + args.steps):
         t0 = time.perf_counter()
-        wall, entries, kind = cpu_assembly_sample(xyz, tri, ns, cores)
-        # the reference's solve: LU on the sample system (bem/icqLaplaceSolver.py:36)
-        from oracle import oracle
-        g = oracle.green_matrix(xyz, tri[:ns], 5, threads=True) if it == 0 else g
-        v = centroid_potential(xyz, tri[:ns])
-        oracle.laplace_response(g, v)
+        wall, wall_g, entries, kind = cpu_assembly_sample(xyz, tri, ns, workers)
+        t1 = time.perf_counter()
+        if poisson:
+            # the reference's apply: numpy.dot(gMat, src) (bem/icqPoissonSolver.py:36)
+            if lu_mat is None:
+                lu_mat = rng.standard_normal((nlu, nlu))
+            tl0 = time.perf_counter()
+            lu_mat.dot(numpy.ones(nlu))
+            t_solve = time.perf_counter() - tl0
+        else:
+            # the reference's solve on a matrix of the sample size with G's structure
+            # (LAPACK dgesv: the time does not depend on the entries)
+            if lu_mat is None:
+                lu_mat = oracle.green_matrix(xyz, numpy.ascontiguousarray(tri[:nlu]), 5, threads=True)
+            v = centroid_potential(xyz, tri[:nlu])
+            tl0 = time.perf_counter()
+            oracle.laplace_response(lu_mat, v)
+            t_solve = time.perf_counter() - tl0
         dt = time.perf_counter() - t0
         if it >= args.warmup:
-            times.append((dt, entries))
-    total_t = sum(t for t, _ in times)
-    total_e = sum(e for _, e in times)
-    value = total_e / total_t
-    sample = ('{0} processes x G of a {1}-triangle sub-mesh of the workload (reference C++ '
-              'off-diagonal + restated self term) + one numpy LU solve of that size; the reference '
-              'has no K, entries counted are G entries'.format(cores, ns))
+            rec.append((dt, wall, wall_g, t_solve, entries))
+    t_step = float(numpy.mean([r[0] for r in rec]))
+    t_asm = float(numpy.mean([r[1] for r in rec]))
+    t_asm_g = float(numpy.mean([r[2] for r in rec]))
+    t_solve = float(numpy.mean([r[3] for r in rec]))
+    entries = rec[0][4]                      # G entries of the sample (workers * ns^2)
+    # extrapolation to the config's N
+    asm_rate_gk = 2.0 * entries / t_asm      # G+K entries/s of the host, size-independent
+    asm_rate_g = entries / t_asm_g
+    t_asm_full = 2.0 * n * n / asm_rate_gk
+    t_solve_full = t_solve * ((n / float(nlu)) ** (2 if poisson else 3))
+    value = 2.0 * n * n / (t_asm_full + t_solve_full)
+    sample = ('per step: {0} processes x (G by the reference C++ + self terms + K by the C '
+              'restatement) of a {1}-triangle sub-mesh of the workload, then one {2} of size {3}; '
+              'extrapolated to N = {4}: assembly by entry count ({5:.1f} s), {2} by N^{6} ({7:.1f} s)'
+              .format(workers, ns, 'numpy.dot' if poisson else 'numpy.linalg.solve', nlu, n,
+                      t_asm_full, 2 if poisson else 3, t_solve_full))
     line = {
-        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
-        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * total_t / len(times),
-        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
-        'data': 'synthetic', 'config': {'workload': label, 'sample': sample},
-        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': kind, 'sample': sample},
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * t_step,
+        'higher_is_better': True, 'scaling': scaling_label(world, args.workload),
+        'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': bench_config(args, label, n, world),
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': workers, 'kind': kind, 'sample': sample},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'g_only': {'value': asm_rate_g, 'unit': 'G entries/s (assembly only)', 'cores': workers},
+        'extrapolation': {'assembly_GK_entries_per_s': asm_rate_gk, 'assembly_s_at_N': t_asm_full,
+                          'solve_s_at_sample': t_solve, 'solve_sample_size': nlu,
+                          'solve_s_at_N': t_solve_full, 'sample_step_s': t_step},
         'gpu_launches': 0,
     }
     print(json.dumps(line))
@@ -264,6 +365,20 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------
 # CUDA arm
 # ---------------------------------------------------------------------------------------
+
+def local_work(blocks, n, lower, rows):
+    """(pairs of triangles this rank evaluates, matrix entries it streams per product)."""
+    if lower:
+        pairs, stored = 0.0, 0.0
+        for (b, e) in ((blocks[0], blocks[1]), (blocks[2], blocks[3])):
+            for t0 in range(b, e, 128):
+                h = min(128, e - t0)
+                w_diag = min(128, n - t0)
+                pairs += h * t0 + h * (w_diag - 1)      # below the diagonal tile + inside it
+                stored += 128.0 * t0 + 128.0 * 128.0    # whole tiles are streamed
+        return pairs, stored
+    return rows * (rows - 1) / 2.0 + rows * (n - rows), float(rows) * n
+
 
 def run_b200(args):
     import ctypes
@@ -274,6 +389,7 @@ def run_b200(args):
     from icqsol_b200.bem.icqBaseLaplaceSolver import leadingDimension
     from icqsol_b200.mesh.polydata import PolyData, DataArray
     from icqsol_b200.bem.icqLaplaceSolver import LaplaceSolver
+    from icqsol_b200.bem.icqPoissonSolver import PoissonSolver
 
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -288,9 +404,11 @@ def run_b200(args):
     if world != args.gpus and rank == 0:
         print('warning: --gpus {0} but WORLD_SIZE {1}'.format(args.gpus, world), file=sys.stderr)
 
+    wname = resolve_workload(world, args.workload)
+    poisson = wname == 'c4'
     label, xyz, tri = make_mesh(world, args.workload)
     n = tri.shape[0]
-    v = centroid_potential(xyz, tri)
+    v = numpy.ones(n) if poisson else centroid_potential(xyz, tri)
 
     # ---- resident set-up (not timed): context, mesh in HBM, matrix buffers ----------------
     ctx = _lib.Context(local)
@@ -298,17 +416,15 @@ def run_b200(args):
     stream = torch.cuda.Stream(device=dev)
     ctx.check(lib.icqb_set_stream(ctx.handle, stream.cuda_stream))
     _lib.attachCommunicator(ctx, rank, world, rowPartition.broadcastBytes)
-    ctx.check(lib.icqb_cg_set_preconditioner(
-        ctx.handle, {'diagonal': 0, 'block': 1, 'block+caps': 2}[args.preconditioner]))
-    cap_tiles = (0, 0)
-    if args.preconditioner == 'block+caps':    # experimental, see icqsol_b200/csrc/cg_caps.cu
-        cap_tiles = rowPartition.sliverCapTiles(xyz, tri)
-        ctx.check(lib.icqb_cg_set_cap_tiles(ctx.handle, *cap_tiles))
+    kind = {'diagonal': 0, 'block': 1, 'block+caps': 2}[args.preconditioner]
+    ctx.check(lib.icqb_cg_set_preconditioner(ctx.handle, kind))
+    dense_runs = []
+    if kind == 2:
+        # one dense block per run of sliver tiles, blocks of --block-tiles tiles elsewhere
         starts, dense_runs = rowPartition.sliverBlockPartition(xyz, tri, blockTiles=args.block_tiles)
-        if dense_runs or args.block_tiles > 1:
-            starts = numpy.ascontiguousarray(starts, numpy.int64)
-            ctx.check(lib.icqb_cg_set_block_partition(ctx.handle, starts.ctypes.data_as(_lib.c_int64_p),
-                                                      len(starts)))
+        starts = numpy.ascontiguousarray(starts, numpy.int64)
+        ctx.check(lib.icqb_cg_set_block_partition(ctx.handle, starts.ctypes.data_as(_lib.c_int64_p),
+                                                  len(starts)))
     ctx.check(lib.icqb_set_assembly_variant(ctx.handle, args.assembly_variant))
     ctx.check(lib.icqb_cg_set_mixed_precision(ctx.handle, args.mixed_switch))
     ctx.check(lib.icqb_set_mesh(ctx.handle, xyz.ctypes.data_as(_lib.c_double_p), xyz.shape[0],
@@ -326,71 +442,74 @@ def run_b200(args):
     if lower:
         ntiles = int(lib.icqb_lower_num_tiles(ctx.handle))
         shape = (max(ntiles, 1), 128, 128)
-        gbuf = torch.zeros(shape, dtype=torch.float64, device=dev)
-        kbuf = torch.zeros(shape, dtype=torch.float64, device=dev)
-        kubuf = torch.zeros(shape, dtype=torch.float64, device=dev)
     else:
-        gbuf = torch.empty((max(rows, 1), ld), dtype=torch.float64, device=dev)
-        kbuf = torch.empty((max(rows, 1), ld), dtype=torch.float64, device=dev)
-        kubuf = None
+        shape = (max(rows, 1), ld)
+    gbuf = torch.empty(shape, dtype=torch.float64, device=dev)
+    kbuf = torch.empty(shape, dtype=torch.float64, device=dev)
+    kubuf = torch.empty(shape, dtype=torch.float64, device=dev) if lower else None
     bdev = torch.from_numpy(v).to(dev)
     xdev = torch.zeros(n, dtype=torch.float64, device=dev)
     area2 = lib.icqb_area2_dev(ctx.handle)
-    # pairs of triangles this rank evaluates, stored entries it streams per product
-    if lower:
-        tiles = 0
-        pairs_local = 0.0
-        stored = 0.0
-        for (b, e) in ((blocks[0], blocks[1]), (blocks[2], blocks[3])):
-            for t0 in range(b, e, 128):
-                h = min(128, e - t0)
-                w_diag = min(128, n - t0)
-                pairs_local += h * t0 + h * (w_diag - 1)      # below the diagonal tile + inside it
-                stored += 128.0 * t0 + 128.0 * 128.0    # whole tiles are streamed
-    else:
-        pairs_local = rows * (rows - 1) / 2.0 + rows * (n - rows)
-        stored = float(rows) * n
+    pairs_local, stored = local_work(blocks, n, lower, rows)
     torch.cuda.synchronize(dev)
 
-    phase = {'assembly_ms': [], 'offdiag_ms': [], 'diag_ms': [], 'solve_ms': [], 'gemv_ms': [],
-             'iters': [], 'resid': [], 'residinf': [], 'replacements': [], 'products': [], 'products32': []}
+    names = ('assembly_ms', 'offdiag_ms', 'diag_ms', 'solve_ms', 'gemv_ms')
+    phase = {k: [] for k in names + ('iters', 'resid', 'residinf', 'replacements', 'products', 'products32')}
+
+    def assemble(with_k=True):
+        kp = kbuf.data_ptr() if with_k else 0
+        if lower:
+            ctx.check(lib.icqb_assemble_lower_dev(ctx.handle, 5, gbuf.data_ptr(), kp,
+                                                  kubuf.data_ptr() if with_k else 0))
+        else:
+            ctx.check(lib.icqb_assemble_dev(ctx.handle, 5, gbuf.data_ptr(), kp, ld))
 
     def step(record):
         with torch.cuda.stream(stream):
             xdev.zero_()
         t0 = time.perf_counter()
-        if lower:
-            ctx.check(lib.icqb_assemble_lower_dev(ctx.handle, 5, gbuf.data_ptr(), kbuf.data_ptr(),
-                                                  kubuf.data_ptr()))
-        else:
-            ctx.check(lib.icqb_assemble_dev(ctx.handle, 5, gbuf.data_ptr(), kbuf.data_ptr(), ld))
+        assemble()
         t1 = time.perf_counter()
         iters = ctypes.c_int64(0)
         r2 = ctypes.c_double(0.)
         rinf = ctypes.c_double(0.)
-        ctx.check(lib.icqb_cg_solve_dev(ctx.handle, gbuf.data_ptr(), n, ld, 1 if lower else 0, area2, 0,
-                                        bdev.data_ptr(), xdev.data_ptr(), 5e-13, 2, args.max_iters,
-                                        ctypes.byref(iters), ctypes.byref(r2), ctypes.byref(rinf)))
+        if poisson:
+            if lower:
+                ctx.check(lib.icqb_symv_dev(ctx.handle, gbuf.data_ptr(), bdev.data_ptr(), xdev.data_ptr(), 0))
+            else:
+                ctx.check(lib.icqb_gemv_dev(ctx.handle, gbuf.data_ptr(), rows, n, ld, bdev.data_ptr(),
+                                            xdev.data_ptr(), 0, stream.cuda_stream))
+        else:
+            ctx.check(lib.icqb_cg_solve_dev(ctx.handle, gbuf.data_ptr(), n, ld, 1 if lower else 0, area2, 0,
+                                            bdev.data_ptr(), xdev.data_ptr(), 5e-13, 2, args.max_iters,
+                                            ctypes.byref(iters), ctypes.byref(r2), ctypes.byref(rinf)))
         if record:
             phase['assembly_ms'].append(1e3 * (t1 - t0))
             phase['offdiag_ms'].append(ctx.last_ms(1))
             phase['diag_ms'].append(ctx.last_ms(2))
-            phase['solve_ms'].append(ctx.last_ms(4))
+            phase['solve_ms'].append(0.0 if poisson else ctx.last_ms(4))
             phase['gemv_ms'].append(ctx.last_ms(3))
             phase['iters'].append(iters.value)
             phase['resid'].append(r2.value)
             phase['residinf'].append(rinf.value)
-            rep, prod = ctx.cg_stats()
+            rep, prod = (0, 1) if poisson else ctx.cg_stats()
             phase['replacements'].append(rep)
             phase['products'].append(prod)
             n32 = ctypes.c_int64(0)
             ctx.check(lib.icqb_cg_last_mixed(ctx.handle, ctypes.byref(n32)))
-            phase['products32'].append(n32.value)
+            phase['products32'].append(0 if poisson else n32.value)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
+
+    def max_over_ranks(x):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     for _ in range(args.warmup):
         step(False)
@@ -405,33 +524,62 @@ def run_b200(args):
     e1.record(stream)
     barrier()
     sampler.stop_flag = True
-    ms_total = e0.elapsed_time(e1)
+    ms_per_step = max_over_ranks(e0.elapsed_time(e1)) / args.steps
     launches = ctx.launch_count() - launches0
-    if world > 1:
-        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
-    ms_per_step = ms_total / args.steps
     value = 2.0 * n * n / (ms_per_step * 1e-3)
+
+    # ---- G-only pass (what the reference computes), same buffers, timed the same way ------
+    barrier()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    assemble(False)
+    g0.record(stream)
+    for _ in range(2):
+        assemble(False)
+    g1.record(stream)
+    barrier()
+    g_only_ms = max_over_ranks(g0.elapsed_time(g1)) / 2.0
+    g_only_kernel_ms = ctx.last_ms(1)
 
     # ---- fp64 peak of this GPU, measured in-run -------------------------------------------
     peak = ctypes.c_double(0.)
     ctx.check(lib.icqb_measure_fp64_peak(ctx.handle, ctypes.byref(peak)))
+    far_frac = None
+    if args.assembly_variant:
+        fast, allp = ctypes.c_int64(0), ctypes.c_int64(0)
+        ctx.check(lib.icqb_assembly_stats(ctx.handle, ctypes.byref(fast), ctypes.byref(allp)))
+        far_frac = fast.value / max(allp.value, 1)
+
+    # ---- per-rank phase means -> max / min over the ranks ---------------------------------
+    mine = {k: float(numpy.mean(phase[k])) for k in names}
+    mine['stored_bytes'] = 8.0 * stored
+    mine['pairs'] = pairs_local
+    if world > 1:
+        everyone = [None] * world
+        dist.all_gather_object(everyone, mine)
+    else:
+        everyone = [mine]
 
     # ---- e2e through the public Python API (host polydata in, host response out) ----------
+    # the resident buffers go first: on one GPU the 84,600-triangle matrices take 86 GB, and the
+    # solver class holds its own
+    del gbuf, kbuf, kubuf
+    torch.cuda.empty_cache()
     e2e_times = []
+    e2e_phases = {}
     h2d = xyz.nbytes + tri.nbytes + v.nbytes
     d2h = 8 * n
     for it in range(1 + args.e2e_steps if args.e2e_steps > 0 else 0):
         pd = PolyData.from_arrays(xyz, tri, dtype=numpy.float64)
-        pd.GetCellData().AddArray(DataArray('v', v))
+        pd.GetCellData().AddArray(DataArray('charge' if poisson else 'v', v))
         barrier()
         t0 = time.perf_counter()
-        solver = LaplaceSolver(pd, float('inf'), 5, computeK=True, device=local,
-                               storage=args.storage, preconditioner=args.preconditioner,
-                               blockTiles=args.block_tiles, assemblyVariant=args.assembly_variant,
-                               mixedPrecision=args.mixed_switch)
-        solver.setSolverMaxNumberOfIterations(args.max_iters)
+        cls = PoissonSolver if poisson else LaplaceSolver
+        solver = cls(pd, float('inf'), 5, computeK=True, device=local,
+                     storage=args.storage, preconditioner=args.preconditioner,
+                     blockTiles=args.block_tiles, assemblyVariant=args.assembly_variant,
+                     mixedPrecision=args.mixed_switch)
+        if not poisson:
+            solver.setSolverMaxNumberOfIterations(args.max_iters)
         rsp = solver.computeResponseField()
         torch.cuda.synchronize(dev)
         dt = time.perf_counter() - t0
@@ -444,69 +592,62 @@ def run_b200(args):
             for name, t in solver.hostTimings[group]:
                 e2e_phases['{0}: {1}'.format(group, name)] = round(t - last, 3)
                 last = t
-        del solver
+        del solver, rsp
+        torch.cuda.empty_cache()
     e2e_s = None
     if e2e_times:
-        e2e_s = float(numpy.mean(e2e_times))
-        if world > 1:
-            t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e2e_s = float(t.item())
+        e2e_s = max_over_ranks(float(numpy.mean(e2e_times)))
     if rank == 0:
         peaks, peak_src = measured_peaks()
-        off_ms = float(numpy.mean(phase['offdiag_ms']))
-        gemv_ms = float(numpy.mean(phase['gemv_ms']))
-        # algorithmic flop of this rank's off-diagonal launch (pairs it evaluates x 256 x 18)
-        flop = pairs_local * 256.0 * FLOP_PER_EVAL_GK
-        achieved = flop / (off_ms * 1e-3) / 1e12
+        off_ms = mine['offdiag_ms']
+        gemv_ms = mine['gemv_ms']
+        iters_mean = float(numpy.mean(phase['iters']))
+        bmax = float(numpy.abs(v).max())
+        # the off-diagonal launch of the rank that evaluates the most pairs
+        heavy = max(everyone, key=lambda d: d['pairs'])
+        flop = heavy['pairs'] * 256.0 * FLOP_PER_EVAL_GK
+        achieved = flop / (heavy['offdiag_ms'] * 1e-3) / 1e12
         # FP64-pipe instructions per evaluation of the kernel's inner loop (SASS counts,
-        # tools/sass_loops.py; G+K): validated kernel 16; far-field arithmetic 13 (12 with the
-        # Newton step) for the (warp, source triangle) pairs that took it
-        far_frac = None
-        instr_per_eval = 16.0
-        if args.assembly_variant:
-            fast, allp = ctypes.c_int64(0), ctypes.c_int64(0)
-            ctx.check(lib.icqb_assembly_stats(ctx.handle, ctypes.byref(fast), ctypes.byref(allp)))
-            far_frac = fast.value / max(allp.value, 1)
-            instr_per_eval = 16.0 - far_frac * (3.0 if args.assembly_variant in (1, 3) else 4.0)
-        # bytes of matrix this rank streams per product; with float32 late products
-        # (--mixed-switch) the timed products are a mixture: 8 bytes per stored entry for the
-        # double ones, 4 for the float32 ones, weighted by their share of the iterations
-        frac32 = float(numpy.mean(phase['products32'])) / max(float(numpy.mean(phase['iters'])), 1.0)
-        gemv_bytes = stored * (8.0 - 4.0 * min(max(frac32, 0.0), 1.0))
-        gemv_gbs = gemv_bytes / (gemv_ms * 1e-3) / 1e9 if gemv_ms > 0 else 0.0
-        # products that ran: iterations + the initial one + one per confirmation (those
-        # enqueued behind the stop flag return at once and are not counted)
-        products_mean = float(numpy.mean(phase['iters'])) + 2 + float(numpy.max(phase['replacements']))
+        # tools/sass_loops.py; G+K): validated kernel 16; far-field arithmetic 13
+        instr_per_eval = 16.0 if far_frac is None else 16.0 - far_frac * 3.0
+        # bytes of matrix a rank streams per product (float32 late products: 4 bytes per entry
+        # for their share of the products); heaviest rank, and its time (the exchange between
+        # the ranks is inside the timed product)
+        frac32 = float(numpy.mean(phase['products32'])) / max(iters_mean, 1.0)
+        width = 8.0 - 4.0 * min(max(frac32, 0.0), 1.0)
+        heavy_g = max(everyone, key=lambda d: d['stored_bytes'])
+        gemv_bytes = heavy_g['stored_bytes'] / 8.0 * width
+        gemv_ms_max = max(d['gemv_ms'] for d in everyone)
+        gemv_gbs = gemv_bytes / (gemv_ms_max * 1e-3) / 1e9 if gemv_ms_max > 0 else 0.0
+        products_mean = 1.0 if poisson else iters_mean + 2 + float(numpy.max(phase['replacements']))
+        spread = {k: {'max': max(d[k] for d in everyone), 'min': min(d[k] for d in everyone)}
+                  for k in names + ('stored_bytes', 'pairs')}
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True,
-            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': {'workload': label, 'triangles': n, 'diag_order': 5, 'offdiag_order': 8,
-                       'step': 'fused G+K assembly + CG solve (max|v+G sigma| <= 5e-13 max|v|)',
-                       'rows_per_gpu': rows, 'storage': args.storage,
-                       'preconditioner': args.preconditioner, 'cap_tiles': list(cap_tiles), 'block_tiles': args.block_tiles,
-                       'assembly_variant': args.assembly_variant, 'mixed_switch': args.mixed_switch,
-                       'parallelism': ('folded row blocks, lower storage x{0}' if lower
-                                       else 'row-block x{0}').format(world),
-                       'l2': 'inputs larger than L2 ({0:.2f} GB of G streamed per product per GPU)'.format(
-                           gemv_bytes / 1e9)},
-            'phases': {'assembly_ms': float(numpy.mean(phase['assembly_ms'])),
+            'scaling': scaling_label(world, args.workload), 'vs_baseline': None, 'dtype': 'f64',
+            'data': 'synthetic',
+            'config': bench_config(args, label, n, world),
+            'phases': {'assembly_ms': mine['assembly_ms'],
                        'offdiag_kernel_ms': off_ms,
-                       'diag_kernel_ms': float(numpy.mean(phase['diag_ms'])),
-                       'assembly_entries_per_s': 2.0 * n * n / (numpy.mean(phase['assembly_ms']) * 1e-3),
-                       'solve_ms': float(numpy.mean(phase['solve_ms'])),
-                       'cg_iters': int(numpy.mean(phase['iters'])),
+                       'diag_kernel_ms': mine['diag_ms'],
+                       'assembly_entries_per_s': 2.0 * n * n / (spread['offdiag_ms']['max'] * 1e-3),
+                       'solve_ms': mine['solve_ms'],
+                       'cg_iters': int(iters_mean),
                        'cg_residual_replacements': int(numpy.max(phase['replacements'])),
                        'cg_products_enqueued': int(numpy.mean(phase['products'])),
                        'cg_float32_products': int(numpy.mean(phase['products32'])),
-                       'cg_converged': bool(numpy.max(phase['residinf']) <= 1e-12 * numpy.abs(v).max()),
+                       'cg_converged': bool(poisson or numpy.max(phase['residinf']) <= 1e-12 * bmax),
                        'cg_residual2': float(numpy.max(phase['resid'])),
-                       'cg_backward_error_max_norm': float(numpy.max(phase['residinf']) / numpy.abs(v).max()),
+                       'cg_backward_error_max_norm': float(numpy.max(phase['residinf']) / bmax),
+                       'dense_preconditioner_runs': [list(map(int, r)) for r in dense_runs],
                        'gemv_ms': gemv_ms, 'gemv_gbs_per_gpu': gemv_gbs,
-                       'gemv_gbs_aggregate': gemv_gbs * world,
-                       'gemv_equivalent_dense_gbs_aggregate': 8.0 * n * n / (gemv_ms * 1e-3) / 1e9
-                       if gemv_ms > 0 else 0.0},
+                       'gemv_gbs_aggregate': sum(d['stored_bytes'] for d in everyone) / 8.0 * width /
+                       (gemv_ms_max * 1e-3) / 1e9 if gemv_ms_max > 0 else 0.0,
+                       'gemv_equivalent_dense_gbs_aggregate': 8.0 * n * n / (gemv_ms_max * 1e-3) / 1e9
+                       if gemv_ms_max > 0 else 0.0,
+                       'over_ranks': spread,
+                       'stored_bytes_per_rank': [d['stored_bytes'] for d in everyone]},
             'roofline': None,
             'roofline_assembly': {
                 'bound': 'fp64', 'kernel': 'k_offdiag<G+K>' if not args.assembly_variant else 'k_offdiag_ff<G+K> (variant {0})'.format(args.assembly_variant), 'achieved': achieved,
@@ -515,22 +656,26 @@ def run_b200(args):
                 'peak_source': 'DFMA loop measured in this run (icqb_measure_fp64_peak)',
                 'flop_per_evaluation': FLOP_PER_EVAL_GK, 'fp64_instr_per_evaluation': instr_per_eval,
                 'far_field_fraction': far_frac,
-                'issue_frac': (pairs_local * 256.0 * instr_per_eval * 2 / (off_ms * 1e-3) / 1e12) / peak.value,
-                'launches_per_step': 1, 'ms_per_launch': off_ms,
-                'share_of_step': off_ms / ms_per_step},
+                'issue_frac': (heavy['pairs'] * 256.0 * instr_per_eval * 2 / (heavy['offdiag_ms'] * 1e-3) / 1e12) / peak.value,
+                'launches_per_step': 1, 'ms_per_launch': heavy['offdiag_ms'],
+                'share_of_step': heavy['offdiag_ms'] / ms_per_step},
             'roofline_gemv': {
                 'bound': 'hbm', 'kernel': 'k_symv+k_symv_reduce' if lower else 'k_gemv',
                 'achieved': gemv_gbs, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
                 'frac': gemv_gbs / peaks['hbm_gbs'],
                 'traffic': traffic_of('k_symv' if lower else 'k_gemv', args.storage, n),
                 'peak_source': peak_src, 'algorithmic_bytes_per_launch': gemv_bytes,
-                'launches_per_step': products_mean, 'ms_per_launch': gemv_ms,
-                'share_of_step': min(1.0, products_mean * gemv_ms / ms_per_step)},
+                'launches_per_step': products_mean, 'ms_per_launch': gemv_ms_max,
+                'share_of_step': min(1.0, products_mean * gemv_ms_max / ms_per_step),
+                'rank': 'heaviest rank (bytes), slowest rank (time), exchange between the ranks inside'},
+            'g_only': {'value': float(n) * n / (g_only_ms * 1e-3), 'unit': 'G entries/s (assembly only)',
+                       'ms': g_only_ms, 'offdiag_kernel_ms': g_only_kernel_ms},
             'e2e': None if e2e_s is None else {
                 'value': 2.0 * n * n / e2e_s, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d),
                 'd2h_bytes_per_step': int(d2h), 'ms_per_step': 1e3 * e2e_s,
                 'host_phases_ms': e2e_phases,
-                'api': 'LaplaceSolver(pdata, inf, 5, computeK=True).computeResponseField()'},
+                'api': '{0}(pdata, inf, 5, computeK=True).computeResponseField()'.format(
+                    'PoissonSolver' if poisson else 'LaplaceSolver')},
             'gpu_launches': int(launches),
             'clocks': sampler.summary(),
         }
@@ -538,13 +683,14 @@ def run_b200(args):
         dom = 'roofline_gemv' if line['roofline_gemv']['share_of_step'] > \
             line['roofline_assembly']['share_of_step'] else 'roofline_assembly'
         line['roofline'] = dict(line[dom])
-        if world == 1 and not args.no_cpu_baseline:
-            wall, entries, kind = cpu_assembly_sample(xyz, tri, args.cpu_sample, 1)
+        if not args.no_cpu_baseline:
+            wall, wall_g, entries, kindc = cpu_assembly_sample(xyz, tri, args.cpu_sample, 1)
             line['cpu_baseline'] = {
-                'value': entries / wall, 'unit': UNIT, 'cores': 1, 'kind': kind,
-                'sample': 'G (no K in the reference) of the first {0} triangles of the workload: '
-                          'reference C++ off-diagonal + restated self term, {1:.1f} s'.format(
-                              args.cpu_sample, wall)}
+                'value': 2.0 * entries / wall, 'unit': UNIT, 'cores': 1, 'kind': kindc,
+                'g_only_value': entries / wall_g,
+                'sample': 'G and K of the first {0} triangles of the workload, assembly only: reference '
+                          'C++ off-diagonal + restated self term for G, C restatement for K (the '
+                          'reference has none), {1:.1f} s, 1 thread'.format(min(args.cpu_sample, n), wall)}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
@@ -557,36 +703,38 @@ def main():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--workload', default='auto', choices=['auto', 'c2', 'c3', 'c5', 'small', 'tiny', 'bolt'],
-                    help="auto = config C2 on one GPU, C2 scaled with N^2/GPU fixed on several; c3/c5 = "
-                         "UV spheres of the C3/C5 sizes; bolt = config C3's own geometry (refined "
-                         "testBoltFine, 84,600 triangles)")
-    ap.add_argument('--cpu-sample', type=int, default=3600,
-                    help='triangles of the CPU baseline sub-mesh (3600 -> 10-20 s single core)')
+    ap.add_argument('--workload', default='auto',
+                    choices=['auto', 'c2', 'c3', 'c4', 'c5', 'bolt', 'weak', 'small', 'tiny'],
+                    help="auto = config C2 on one GPU, the refined bolt of config C3 (84,600 "
+                         "triangles, strong scaling) on several; c3/c5 = UV spheres of the C3/C5 "
+                         "sizes; c4 = hollow sphere, Poisson product; weak = C2 refined with "
+                         "N^2/GPU fixed")
+    ap.add_argument('--cpu-sample', type=int, default=2000,
+                    help='triangles of the CPU baseline sub-mesh (2000 -> ~15 s single core, G and K)')
+    ap.add_argument('--ref-sample', type=int, default=1000,
+                    help='--impl reference: triangles of the sub-mesh each host process assembles per step')
+    ap.add_argument('--ref-lu-size', type=int, default=5000,
+                    help='--impl reference: size of the LU solve timed per step (extrapolated by N^3)')
     ap.add_argument('--e2e-steps', type=int, default=2)
     ap.add_argument('--storage', default='lower', choices=['lower', 'full'],
                     help="'lower': each pair entry stored once (mirror rule), symmetric product; "
                          "'full': complete row blocks, row-major GEMV")
-    ap.add_argument('--preconditioner', default='auto', choices=['auto', 'block', 'diagonal', 'block+caps'],
-                    help="CG preconditioner: inverse 128x128 diagonal blocks, 1/diag, or (experimental) "
-                         "blocks with dense caps over the sliver tiles; auto = block, except for the "
-                         "c3/c5 workloads whose pole slivers make the matrix indefinite (DESIGN.md 4.6): "
-                         "block+caps there")
-    ap.add_argument('--block-tiles', type=int, default=1,
-                    help='experimental, with block+caps: 128-triangle tiles per diagonal block')
-    ap.add_argument('--assembly-variant', type=int, default=0, choices=[0, 1, 2, 3, 4],
-                    help='experimental arithmetic of the off-diagonal kernel (include/icqb.h, '
-                         'icqb_set_assembly_variant): 0 validated kernel, 1 far-field split, '
-                         '2 far-field split + Newton reciprocal square root, 3/4 = 1/2 at three CTAs per SM')
+    ap.add_argument('--preconditioner', default='block+caps', choices=['block', 'diagonal', 'block+caps'],
+                    help="CG preconditioner: 'block+caps' (default) = inverse diagonal blocks of "
+                         "--block-tiles tiles, with one dense block over every run of sliver tiles "
+                         "(DESIGN.md 4.6); 'block' = inverse 128x128 blocks; 'diagonal' = 1/diag")
+    ap.add_argument('--block-tiles', type=int, default=DEFAULT_BLOCK_TILES,
+                    help='with block+caps: 128-triangle tiles per diagonal block')
+    ap.add_argument('--assembly-variant', type=int, default=0, choices=[0, 1],
+                    help='arithmetic of the off-diagonal kernel (include/icqb.h, '
+                         'icqb_set_assembly_variant): 0 direct, 1 far-field split')
     ap.add_argument('--mixed-switch', type=float, default=0.,
-                    help='experimental, with block+caps and lower storage: relative residual below '
+                    help='with block+caps and lower storage: relative residual below '
                          'which the CG products stream a float32 copy of the matrix (1e-6); 0 = off')
-    ap.add_argument('--max-iters', type=int, default=4000,
+    ap.add_argument('--max-iters', type=int, default=1500,
                     help='CG iteration cap (a solve that needs more is reported as not converged)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
-    if args.preconditioner == 'auto':
-        args.preconditioner = 'block+caps' if args.workload in ('c3', 'c5') else 'block'
     if args.impl == 'reference':
         run_reference(args)
     else:

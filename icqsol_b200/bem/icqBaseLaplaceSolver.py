@@ -44,16 +44,13 @@ def leadingDimension(n):
 
 class BaseLaplaceSolver(BaseSolver):
 
-    # defaults of the solver options; ICQB_DEFAULTS=next (EXPERIMENTAL) switches the ones a caller
-    # leaves unset to the candidates for the next defaults, so that the whole parity suite can be
-    # run against them:  ICQB_DEFAULTS=next ICQB_EXPERIMENTAL=1 pytest -m gpu
-    DEFAULTS = {'preconditioner': 'block', 'blockTiles': 1, 'assemblyVariant': 0, 'mixedPrecision': 0.}
-    NEXT_DEFAULTS = {'preconditioner': 'block+caps', 'blockTiles': 8, 'assemblyVariant': 1,
-                     'mixedPrecision': 1.e-6}
+    # defaults of the solver options a caller leaves at None
+    DEFAULTS = {'preconditioner': 'block+caps', 'blockTiles': 8, 'assemblyVariant': 0,
+                'mixedPrecision': 0.}
 
     def __init__(self, pdata, max_edge_length, order=5, computeK=False, device=None,
                  storage='lower', preconditioner=None, blockTiles=None, assemblyVariant=None,
-                 directFallback=False, mixedPrecision=None):
+                 directFallback=True, mixedPrecision=None):
         """
         Constructor
         @param pdata polydata (vtkPolyData or stand-in)
@@ -65,28 +62,25 @@ class BaseLaplaceSolver(BaseSolver):
         @param storage 'lower': block-lower-triangular, each pair entry stored once, the
                        upper part given by the mirror rule G[j,i] = G[i,j] A_i/A_j
                        (bem/icqLaplaceMatrices.cpp:97-98); 'full': complete row blocks
-        @param preconditioner of the CG solve: 'block' = inverse 128 x 128 diagonal blocks of
-                       diag(A) G, 'diagonal' = 1/diag (the reference CG class's default,
-                       solvers/icqConjugateGradient.py:19), 'block+caps' = EXPERIMENTAL: blocks,
-                       with one dense block over every run of tiles that hold sliver triangles
-                       (icqRowPartition.sliverBlockPartition; on a UV sphere the two poles),
-                       'auto' = EXPERIMENTAL: 'block+caps' if the mesh has such runs, else 'block'
-        @param blockTiles EXPERIMENTAL, with 'block+caps' only: tiles (of 128 triangles) per
-                       diagonal block between the caps (numpy model at config C2: 167 iterations
-                       with 1, 121 with 2, 92 with 8)
-        @param mixedPrecision EXPERIMENTAL, with 'block+caps' and storage='lower' only: relative
+        @param preconditioner of the CG solve: 'block+caps' (default) = inverse diagonal blocks
+                       of ``blockTiles`` tiles of diag(A) G, with one dense block over every run
+                       of tiles that hold sliver triangles (icqRowPartition.sliverBlockPartition;
+                       on a UV sphere the two poles -- without them diag(A) G is indefinite
+                       there and the iteration stalls); 'block' = inverse
+                       128 x 128 blocks only; 'diagonal' = 1/diag (the reference CG class's
+                       default, solvers/icqConjugateGradient.py:19); 'auto' = 'block+caps'
+        @param blockTiles with 'block+caps': tiles (of 128 triangles) per diagonal block
+                       between the sliver runs (config C2 on a B200: 165 iterations with 1,
+                       91 with 8)
+        @param mixedPrecision with 'block+caps' and storage='lower' only: relative
                        residual below which the products of the CG stream a float32 copy of
-                       the matrix (include/icqb.h, icqb_cg_set_mixed_precision; 1e-6 saves a
-                       quarter of the matrix traffic in the numpy model); 0 = off
-        @param directFallback EXPERIMENTAL: when the CG stops short of the requested backward
-                       error (one rank only), solve by LU instead (solveGreenSystemDirect) --
-                       what the reference does in the first place (bem/icqLaplaceSolver.py:36)
-        @param assemblyVariant EXPERIMENTAL arithmetic of the off-diagonal kernel
-                       (include/icqb.h, icqb_set_assembly_variant): 0 = validated kernel,
-                       1 = far-field split, 2 = far-field split with a Newton reciprocal square
-                       root; None = environment variable ICQB_ASSEMBLY_VARIANT, else 0
-                       (options left at None take BaseLaplaceSolver.DEFAULTS, or NEXT_DEFAULTS
-                       with ICQB_DEFAULTS=next in the environment)
+                       the matrix (include/icqb.h, icqb_cg_set_mixed_precision); 0 = off
+        @param directFallback when the CG stops short of the requested backward error, solve
+                       by LU with partial pivoting instead (solveGreenSystemDirect) -- what the
+                       reference does in the first place (bem/icqLaplaceSolver.py:36); without
+                       it an unconverged solve raises RuntimeError
+        @param assemblyVariant arithmetic of the off-diagonal kernel (include/icqb.h,
+                       icqb_set_assembly_variant): 0 = direct, 1 = far-field split
         """
         # wall-clock marks of the host-side phases (milliseconds since construction began), for
         # the end-to-end breakdown of bench.py: hostTimings['constructor'] / ['solve']
@@ -97,10 +91,6 @@ class BaseLaplaceSolver(BaseSolver):
             self.hostTimings['constructor'].append((name, 1e3 * (time.perf_counter() - t_begin)))
 
         defaults = dict(self.DEFAULTS)
-        if os.environ.get('ICQB_ASSEMBLY_VARIANT'):
-            defaults['assemblyVariant'] = int(os.environ['ICQB_ASSEMBLY_VARIANT'])
-        if os.environ.get('ICQB_DEFAULTS') == 'next':
-            defaults.update(self.NEXT_DEFAULTS)
         if preconditioner is None:
             preconditioner = defaults['preconditioner']
         if blockTiles is None:
@@ -109,19 +99,17 @@ class BaseLaplaceSolver(BaseSolver):
             assemblyVariant = defaults['assemblyVariant']
         if mixedPrecision is None:
             mixedPrecision = defaults['mixedPrecision']
+        if preconditioner == 'auto':
+            preconditioner = 'block+caps'
         if preconditioner != 'block+caps' or storage != 'lower':
-            mixedPrecision = 0.      # the float32 products exist in the experimental solver only
+            mixedPrecision = 0.      # the float32 products exist in the block+caps solver only
 
         BaseSolver.__init__(self, pdata, max_edge_length, order)
         mark('mesh intake (host)')
         if storage not in ('lower', 'full'):
             raise ValueError("storage must be 'lower' or 'full'")
-        if preconditioner not in ('block', 'diagonal', 'block+caps', 'auto'):
+        if preconditioner not in ('block', 'diagonal', 'block+caps'):
             raise ValueError("preconditioner must be 'block', 'diagonal', 'block+caps' or 'auto'")
-        if preconditioner == 'auto':
-            # EXPERIMENTAL: the dense sliver blocks only where the mesh has runs of sliver tiles
-            hasRuns = bool(rowPartition.sliverBlockPartition(self._xyz, self._tri)[1])
-            preconditioner = 'block+caps' if hasRuns else 'block'
         self.storage = storage
         self.preconditioner = preconditioner
         self.directFallback = bool(directFallback)
@@ -156,11 +144,9 @@ class BaseLaplaceSolver(BaseSolver):
             self.capTiles = rowPartition.sliverCapTiles(self._xyz, self._tri)
             starts, self.denseRuns = rowPartition.sliverBlockPartition(
                 self._xyz, self._tri, blockTiles=int(blockTiles))
-            self.ctx.check(self.lib.icqb_cg_set_cap_tiles(self.ctx.handle, *self.capTiles))
-            if self.denseRuns or int(blockTiles) > 1:
-                starts = numpy.ascontiguousarray(starts, numpy.int64)
-                self.ctx.check(self.lib.icqb_cg_set_block_partition(
-                    self.ctx.handle, starts.ctypes.data_as(_lib.c_int64_p), len(starts)))
+            starts = numpy.ascontiguousarray(starts, numpy.int64)
+            self.ctx.check(self.lib.icqb_cg_set_block_partition(
+                self.ctx.handle, starts.ctypes.data_as(_lib.c_int64_p), len(starts)))
 
         self.rank, self.numRanks = rowPartition.worldInfo()
         # one NCCL communicator per process, shared by every solver
@@ -366,20 +352,25 @@ class BaseLaplaceSolver(BaseSolver):
         n32 = ctypes.c_int64(0)
         self.ctx.check(self.lib.icqb_cg_last_mixed(self.ctx.handle, ctypes.byref(n32)))
         self.lastSolveInfo['float32Products'] = n32.value
-        # the reference's LU (bem/icqLaplaceSolver.py:36) cannot "not converge"; say so loudly
-        # when the iteration stopped short of the requested backward error (iteration cap,
-        # attainable accuracy, or a matrix the quadrature left too indefinite for CG)
+        # the reference's LU (bem/icqLaplaceSolver.py:36) cannot "not converge": when the
+        # iteration stopped short of the requested backward error (iteration cap, attainable
+        # accuracy, or a matrix the quadrature left too indefinite for CG) the system is solved
+        # by LU instead, or the call raises -- an unconverged iterate is never returned
         bmax = float(numpy.abs(numpy.asarray(rhs, numpy.float64)).max()) if n else 0.
-        reached = rinf.value <= 2. * float(tol) * bmax or bmax == 0.
+        reached = rinf.value <= float(tol) * bmax or bmax == 0.
         self.lastSolveInfo['converged'] = bool(reached)
+        self.lastSolveInfo['method'] = 'cg'
         if not reached:
             import warnings
             msg = ('icqsol_b200: CG stopped after {0} iterations with max|rhs - G x| = {1:.3e} '
                    '(requested {2:.3e})'.format(iters.value, rinf.value, float(tol) * bmax))
-            if self.directFallback and self.numRanks == 1:
-                warnings.warn(msg + '; solving by LU instead (directFallback)', RuntimeWarning)
-                return self.solveGreenSystemDirect(rhs)
-            warnings.warn(msg, RuntimeWarning)
+            if not self.directFallback:
+                raise RuntimeError(msg + '; directFallback=False, no solution returned')
+            warnings.warn(msg + '; solving by LU instead (directFallback)', RuntimeWarning)
+            cgInfo = dict(self.lastSolveInfo)
+            xd = self.solveGreenSystemDirect(rhs)
+            self.lastSolveInfo['cg'] = cgInfo
+            return xd
         return x.cpu().numpy()
 
     def solveGreenSystemDirect(self, rhs):

@@ -1,5 +1,6 @@
 """Run by tests/test_host.py through tools/emu/run_emulated.py: a CG that is cut short after two
-iterations must hand over to the LU fallback (directFallback=True) and still return the solution."""
+iterations must hand over to the LU fallback (directFallback, the default) and still return the
+solution; with directFallback=False it raises instead of returning the unconverged iterate."""
 import warnings
 
 import numpy
@@ -11,7 +12,7 @@ from icqsol_b200.bem.icqLaplaceSolver import LaplaceSolver
 for storage in ('lower', 'full'):
     xyz, tri = uvSphere(1.0, 16, 9)
     solver = LaplaceSolver(PolyData.from_arrays(xyz, tri), float('inf'), 5, storage=storage,
-                           directFallback=True)
+                           preconditioner='diagonal')
     solver.setSolverMaxNumberOfIterations(2)
     solver.setSourceFromExpression('1./sqrt(x**2 + (y-2.)**2 + (z-4.)**2)')
     v = solver.getSourceArray(solver.getSourceArrayIndex())
@@ -22,12 +23,16 @@ for storage in ('lower', 'full'):
     assert solver.lastSolveInfo['method'] == 'lu' and solver.lastSolveInfo['converged']
     g = solver.getGreenMatrix()
     assert numpy.abs(v + g.dot(rsp)).max() < 1e-11 * numpy.abs(v).max()
-    # without the fallback the same cut-short solve only warns
-    plain = LaplaceSolver(PolyData.from_arrays(xyz, tri), float('inf'), 5, storage=storage)
+    assert solver.lastSolveInfo['cg']['iterations'] == 2 and not solver.lastSolveInfo['cg']['converged']
+    # without the fallback the same cut-short solve raises: no unconverged iterate comes back
+    plain = LaplaceSolver(PolyData.from_arrays(xyz, tri), float('inf'), 5, storage=storage,
+                          preconditioner='diagonal', directFallback=False)
     plain.setSolverMaxNumberOfIterations(2)
     plain.setSourceFromExpression('1./sqrt(x**2 + (y-2.)**2 + (z-4.)**2)')
-    with warnings.catch_warnings(record=True) as caught:
-        warnings.simplefilter('always')
+    try:
         plain.computeResponseField()
-    assert any('CG stopped' in str(w.message) for w in caught) and not plain.lastSolveInfo['converged']
+        raise AssertionError('an unconverged solve must raise')
+    except RuntimeError as e:
+        assert 'CG stopped' in str(e)
+    assert not plain.lastSolveInfo['converged']
     print('direct fallback ok:', storage)

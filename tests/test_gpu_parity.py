@@ -775,14 +775,10 @@ def test_example_solve_laplace_cli_ply_input(tmp_path, oracle_mod):
     assert numpy.abs(v + g.dot(out['ply'])).max() / numpy.abs(v).max() < 1e-12
 
 
-# ---- EXPERIMENTAL: dense cap blocks in the preconditioner (cg_caps.cu) ----------------------
-# Written at the end of round 1 without GPU access; run with ICQB_EXPERIMENTAL=1.
-
-experimental = pytest.mark.skipif(__import__('os').environ.get('ICQB_EXPERIMENTAL') != '1',
-                                  reason='experimental code path: set ICQB_EXPERIMENTAL=1')
+# ---- dense blocks over the sliver runs in the preconditioner (cg_caps.cu) --------------------
+# (first run on a B200 in round 2: gpurun_out/r2a_*)
 
 
-@experimental
 @pytest.mark.parametrize('storage', ['lower', 'full'])
 def test_cap_blocks_on_sliver_sphere(oracle_mod, storage):
     """UV sphere with the pole slivers of the C3 size (n_theta = 318): diag(A) G is
@@ -804,7 +800,6 @@ def test_cap_blocks_on_sliver_sphere(oracle_mod, storage):
     assert numpy.abs(v + g.dot(rsp)).max() / numpy.abs(v).max() < 1e-12
 
 
-@experimental
 def test_cap_blocks_same_answer_on_regular_sphere():
     """On a mesh the plain blocks handle, explicit caps give the same response."""
     from icqsol_b200.mesh.generators import uvSphere
@@ -827,7 +822,6 @@ def test_cap_blocks_same_answer_on_regular_sphere():
     assert out[1][1] <= out[0][1] + 3
 
 
-@experimental
 @pytest.mark.parametrize('storage', ['lower', 'full'])
 def test_block_tiles_cut_iterations(storage):
     """Diagonal blocks of several tiles (batched block Gauss-Jordan on the device): fewer
@@ -850,16 +844,14 @@ def test_block_tiles_cut_iterations(storage):
     assert relerr(out[8][0], out[1][0]) < 1e-6
 
 
-# ---- EXPERIMENTAL: far-field split of the off-diagonal assembly (assemble_offdiag_ff.cu) -----
-# Written at the end of round 1 without GPU access (CPU emulation + SASS counts only).
+# ---- far-field split of the off-diagonal assembly (assemble_offdiag_ff.cu) -------------------
 
-@experimental
-@pytest.mark.parametrize('variant', [1, 2])
+@pytest.mark.parametrize('variant', [1])
 @pytest.mark.parametrize('nt,nph', [(16, 9), (64, 30)])
 def test_far_field_split_every_entry(ctx, oracle_mod, variant, nt, nph):
-    """Every G entry of a whole matrix within 1e-12 of the oracle (variant 1: within a few ulp
-    of the validated kernel, variant 2: within 5e-14), K against the definition, and most
-    (warp, source triangle) pairs of the larger sphere on the far-field arithmetic."""
+    """Every G entry of a whole matrix within 1e-12 of the oracle and within a few ulp of the
+    direct kernel, K against the definition, and most (warp, source triangle) pairs of the
+    larger sphere on the far-field arithmetic."""
     from icqsol_b200.mesh.generators import uvSphere
     xyz, tri = uvSphere(1.0, nt, nph)
     n = tri.shape[0]
@@ -870,7 +862,7 @@ def test_far_field_split_every_entry(ctx, oracle_mod, variant, nt, nph):
     ctx.check(ctx.lib.icqb_assembly_stats(ctx.handle, ctypes.byref(fast), ctypes.byref(allp)))
     ref = oracle_mod.green_matrix(xyz, tri, 5, threads=True)
     assert max_entry_relerr(g, ref) < TOL_ENTRY
-    assert max_entry_relerr(g, g0) < (5e-15 if variant == 1 else 5e-14)
+    assert max_entry_relerr(g, g0) < 5e-15
     assert numpy.abs(k - k0).max() < 1e-12 * numpy.abs(k0).max()
     assert (numpy.diag(k) == 0).all()
     assert allp.value > 0
@@ -878,8 +870,7 @@ def test_far_field_split_every_entry(ctx, oracle_mod, variant, nt, nph):
         assert fast.value > 0.7 * allp.value
 
 
-@experimental
-@pytest.mark.parametrize('variant', [1, 2, 3, 4])
+@pytest.mark.parametrize('variant', [1])
 def test_far_field_split_row_blocks_and_ragged(ctx, golden, oracle_mod, variant):
     """Row blocks (direct-only tiles left and right of the block) on the bolt, ragged sizes."""
     xyz, tri = golden.mesh('boltFine')
@@ -898,8 +889,7 @@ def test_far_field_split_row_blocks_and_ragged(ctx, golden, oracle_mod, variant)
         assert max_entry_relerr(g, oracle_mod.green_matrix(xs, sub, 5)) < TOL_ENTRY
 
 
-@experimental
-@pytest.mark.parametrize('variant', [1, 2])
+@pytest.mark.parametrize('variant', [1])
 def test_far_field_split_config_c2(oracle_mod, variant):
     """Config C2 through the solver classes (lower storage): sampled columns of G against the
     oracle, the response against oracle rows, ~96 % of the pairs on the far-field arithmetic."""
@@ -920,7 +910,6 @@ def test_far_field_split_config_c2(oracle_mod, variant):
     _sampled_checks(solver, xyz, tri, oracle_mod, [0, 141, 9999, 19751, 19879], rsp, v)
 
 
-@experimental
 @pytest.mark.parametrize('storage', ['lower', 'full'])
 def test_direct_solve_matches_reference_lu(golden, storage):
     """solveGreenSystemDirect = LU with partial pivoting on the device matrix, against the
@@ -942,7 +931,6 @@ def test_direct_solve_matches_reference_lu(golden, storage):
     assert relerr(-rsp, ref) < 1e-8
 
 
-@experimental
 def test_direct_fallback_on_sliver_sphere(oracle_mod):
     """The UV sphere with C3-size pole slivers: the block-preconditioned CG does not converge
     (DESIGN.md 4.6); with directFallback the solver returns the LU solution."""
@@ -951,8 +939,8 @@ def test_direct_fallback_on_sliver_sphere(oracle_mod):
     from icqsol_b200.mesh.polydata import PolyData
     from icqsol_b200.bem.icqLaplaceSolver import LaplaceSolver
     xyz, tri = uvSphere(1.0, 318, 20)
-    solver = LaplaceSolver(PolyData.from_arrays(xyz, tri), float('inf'), 5, directFallback=True)
-    solver.setSolverMaxNumberOfIterations(600)
+    solver = LaplaceSolver(PolyData.from_arrays(xyz, tri), float('inf'), 5, preconditioner='block')
+    solver.setSolverMaxNumberOfIterations(300)
     solver.setSourceFromExpression('1./sqrt(x**2 + (y-2.)**2 + (z-4.)**2)')
     v = solver.getSourceArray(solver.getSourceArrayIndex())
     with warnings.catch_warnings(record=True) as caught:
@@ -964,7 +952,6 @@ def test_direct_fallback_on_sliver_sphere(oracle_mod):
     assert numpy.abs(v + g.dot(rsp)).max() / numpy.abs(v).max() < 1e-10
 
 
-@experimental
 @pytest.mark.parametrize('nt,nph', [(16, 9), (64, 30)])
 def test_float32_product_kernel(oracle_mod, nt, nph):
     """k_symv_f32 (icqb_symv_f32_dev): the product with the float32-rounded stored entries,
@@ -992,7 +979,6 @@ def test_float32_product_kernel(oracle_mod, nt, nph):
     assert (numpy.abs(y - full.dot(x)) <= 1e-13 * numpy.abs(full).dot(numpy.abs(x))).all()
 
 
-@experimental
 def test_mixed_precision_cg():
     """Float32 late products (switch at 1e-6) in the experimental solver: same backward error,
     a good share of the products in float32, a few more iterations at most."""
