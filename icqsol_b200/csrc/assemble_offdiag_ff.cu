@@ -1,12 +1,12 @@
-// EXPERIMENTAL far-field split of the fused G/K off-diagonal assembly (assembly variants 1
-// and 2, icqb_set_assembly_variant).  Written at the end of round 1 without GPU access:
-// checked in the CPU emulation (tests/test_emulated_kernels.py) and by its SASS instruction counts, never
-// run on a GPU; the default (variant 0) is the validated kernel of assemble_offdiag.cu.
+// Far-field split of the fused G/K off-diagonal assembly (assembly variant 1,
+// icqb_set_assembly_variant).  First run on a B200 in round 2 (gpurun_out/r2a_*, r2b_*): every
+// G entry within 5e-15 of the direct kernel's; the direct kernel (variant 0, assemble_offdiag.cu)
+// stays the default until this one is faster by more than a few per cent.
 //
-// Same CTA shape, tile order, bulk-copy ring and stores as k_offdiag.  What changes is the
-// arithmetic of one kernel evaluation for pairs of triangles that are well separated.
+// Same CTA shape, tile order and stores as k_offdiag.  What changes:
 //
-//   * The observer points of a flat triangle are affine in the rule's nodes:
+//   * The arithmetic of one kernel evaluation for pairs of triangles that are well separated.
+//     The observer points of a flat triangle are affine in the rule's nodes:
 //     o_k = a + xi_k (b - a) + eta_k (c - a).  With the origin moved to the observer's vertex
 //     a (s' = s - a, u_k = o_k - a),
 //         r^2 = |s' - u_k|^2 = (|s'|^2 + |u_k|^2) + xi_k (-2 s'.(b-a)) + eta_k (-2 s'.(c-a)),
@@ -22,19 +22,22 @@
 //     (centroids c, radii rho = largest centroid-vertex distance, kappa = 3) and the warp
 //     votes: only if all 32 pairs are far does the warp take the fast arithmetic for this
 //     source triangle; otherwise it evaluates the 256 points exactly as k_offdiag does, from
-//     the reference's rounded quadrature points (bem/icqQuadrature.cpp:233-239).  A second
+//     the reference's rounded quadrature points (bem/icqQuadrature.cpp:233-239), which the
+//     thread re-forms from its own vertices with the rounding order of k_prepare.  A second
 //     condition, |c_i - c_j| >= max|coordinate| / 512, bounds the difference between the
 //     affine points used here and the reference's rounded ones (<= 1.5 eps max|coordinate|
 //     each) to <= 2e-13 of r.
 //   * K: both triangles are flat, so n_j.(x - y) depends on the observer point only and is
 //     affine in the nodes as well; the mirrored n_i.(y - x) is n_i.s'.
-//   * Variant 2 also replaces the third-order step of the reciprocal square root by a Newton
-//     step (4 instead of 5 instructions; relative error <= 2.4e-14 instead of <= 1 ulp, inside
-//     the 1e-12 of the parity contract but not "last bit") -- on the fast path only.
+//   * The warps of a CTA no longer run in lockstep (one takes the near path while the others
+//     do not), so the 2-stage ring with a __syncthreads per refill of k_offdiag would stall
+//     them (ncu, round 2: 4.8 % of the warp samples at that barrier).  Here the whole source
+//     tile -- 128 triangles: quadrature points, bounds + first vertex, normals, 60 KB -- is
+//     requested up front as four sub-tiles, each on its own mbarrier, and no warp ever waits
+//     for another.
 //
 // FP64-pipe instructions per evaluation on the fast path (SASS counts in DESIGN.md 4.1b):
-// G 9 (8 with the Newton step) instead of 12, G+K 13 (12) instead of 16, plus the
-// per-source-point work above.
+// G 9 instead of 12, G+K 13 instead of 16, plus the per-source-point work above.
 #include <stdlib.h>
 
 #include "offdiag_common.cuh"
@@ -72,28 +75,6 @@ ICQB_TRI8(ICQB_CHECK_NODE)
 #undef ICQB_CHECK_NODE
 static_assert(kNq == 16, "ICQB_TRI8 lists 16 nodes");
 
-// reciprocal square root on the fast path: ORDER 3 = rsqrt_1ulp, ORDER 2 = one Newton step.
-// Newton from a seed y0 = y (1 + d), |d| <= 2^-22.4 (MUFU.RSQ64H): e = 1 - x y0^2 = -2d - d^2,
-// y0 (1 + e/2) = y (1 - 3/2 d^2): always low, by up to 4.9e-14.  Adding c = 3/4 dmax^2 to the
-// bracket centres the error, |.| <= 2.4e-14; it costs nothing: e is formed as (1 + 2c) - x y0^2.
-template <int ORDER>
-__device__ __forceinline__ double rsqrt_ff(double x) {
-    if (ORDER == 3) return rsqrt_1ulp(x);
-    double y0;
-#ifdef ICQB_EMU
-    // the hardware seed's worst case (relative error 2^-22.4), so that the emulation shows the
-    // largest error the Newton step can leave
-    y0 = (double)(float)(1.0 / sqrt(x)) * (1.0 + 1.8e-7);
-#else
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
-#endif
-    constexpr double kTwoC = 2.0 * 0.75 * 3.25e-14;   // 2c, dmax^2 = 2^-44.8 = 3.25e-14
-    const double t = x * y0;
-    const double e = fma(-t, y0, 1.0 + kTwoC);
-    const double h = 0.5 * y0;
-    return fma(e, h, y0);
-}
-
 // state of one observer triangle (one thread)
 struct Obs {
     double ax, ay, az;       // vertex a
@@ -110,11 +91,22 @@ struct PairSums {
     double km;   // sum w w n_i.(y - x) / r^3   -> K[j,i]
 };
 
+// per-triangle record next to the quadrature points of a source sub-tile (k_bounds):
+// centroid, radius, first vertex
+constexpr int kBndStride = 8;
+// the whole source tile in shared memory: kFfSub sub-tiles of 32 triangles, one mbarrier each
+constexpr int kFfSub = kTileSrc / kSub;
+constexpr int kFfSrcDoubles = kSub * kQpStride;      // 1536
+constexpr int kFfBndDoubles = kSub * kBndStride;     // 256
+constexpr int kFfNrmDoubles = kSub * 4;              // 128
+constexpr int kFfStageDoubles = kFfSrcDoubles + kFfBndDoubles + kFfNrmDoubles;
+constexpr int kFfSmemBytes = kFfSub * kFfStageDoubles * 8 + 64;   // 61,504 B
+
 // well separated pair: affine observer points, origin at the observer's vertex a
-template <bool WITH_K, int RSQ>
+template <bool WITH_K>
 __device__ __forceinline__ PairSums pair_fast(const Obs& O, const double* __restrict__ pj,
-                                              double njx, double njy, double njz, double pjax,
-                                              double pjay, double pjaz) {
+                                              const double* __restrict__ nj,
+                                              const double* __restrict__ bj) {
     PairSums S{0.0, 0.0, 0.0};
     double r3row[WITH_K ? kNq : 1];
     if (WITH_K) {
@@ -135,7 +127,7 @@ __device__ __forceinline__ PairSums pair_fast(const Obs& O, const double* __rest
 #define ICQB_FF_EVAL(K, XI, ETA, W)                                            \
     {                                                                          \
         const double r2 = fma(XI, B, fma(ETA, C, A + O.q[K]));                 \
-        const double ri = rsqrt_ff<RSQ>(r2);                                   \
+        const double ri = rsqrt_1ulp(r2);                                      \
         in[K & 3] = fma(W, ri, in[K & 3]);                                     \
         if (WITH_K) {                                                          \
             const double r3 = ri * ri * ri;                                    \
@@ -156,7 +148,8 @@ __device__ __forceinline__ PairSums pair_fast(const Obs& O, const double* __rest
     }
     if (WITH_K) {
         // K[i,j]: n_j . (o_k - a_j) = n_j.(a_i - a_j) - (xi_k n_j.b2 + eta_k n_j.c2) / 2
-        const double e0 = fma(njz, O.az - pjaz, fma(njy, O.ay - pjay, njx * (O.ax - pjax)));
+        const double njx = nj[0], njy = nj[1], njz = nj[2];
+        const double e0 = fma(njz, O.az - bj[6], fma(njy, O.ay - bj[5], njx * (O.ax - bj[4])));
         const double nb = fma(njz, O.b2z, fma(njy, O.b2y, njx * O.b2x));
         const double nc = fma(njz, O.c2z, fma(njy, O.c2y, njx * O.c2x));
 #define ICQB_FF_K(K, XI, ETA, W)                                   \
@@ -172,23 +165,32 @@ __device__ __forceinline__ PairSums pair_fast(const Obs& O, const double* __rest
 }
 
 // near pair: the arithmetic of k_offdiag on the reference's rounded quadrature points
-// (observer points re-read from the component-major table: coalesced, L1-resident)
+// p = pa + xi db + eta dc (bem/icqQuadrature.cpp:233-234), re-formed from the thread's own
+// vertices with the explicitly rounded operations of k_prepare: bit-identical to the tables
 template <bool WITH_K>
-__device__ __forceinline__ PairSums pair_exact(const OffDiagParams& P, long long iLoad,
-                                               const Obs& O, const double* __restrict__ pj,
-                                               double njx, double njy, double njz, double pjax,
-                                               double pjay, double pjaz) {
+__device__ __forceinline__ PairSums pair_exact(const Obs& O, const double* __restrict__ pj,
+                                               const double* __restrict__ nj,
+                                               const double* __restrict__ bj) {
     PairSums S{0.0, 0.0, 0.0};
     double c3[WITH_K ? kNq : 1];
     if (WITH_K) {
 #pragma unroll
         for (int k = 0; k < kNq; ++k) c3[k] = 0.0;
     }
+    double njx = 0, njy = 0, njz = 0, pjax = 0, pjay = 0, pjaz = 0;
+    if (WITH_K) {
+        njx = nj[0], njy = nj[1], njz = nj[2];
+        pjax = bj[4], pjay = bj[5], pjaz = bj[6];
+    }
+    // b - a and c - a: O.b2 = -2 (b - a) exactly, so -0.5 * O.b2 is the rounded difference
+    const double dbx = -0.5 * O.b2x, dby = -0.5 * O.b2y, dbz = -0.5 * O.b2z;
+    const double dcx = -0.5 * O.c2x, dcy = -0.5 * O.c2y, dcz = -0.5 * O.c2z;
 #pragma unroll 1
     for (int i0 = 0; i0 < kNq; ++i0) {
-        const double ox = __ldg(P.qp_soa + (long long)(3 * i0 + 0) * P.npad + iLoad);
-        const double oy = __ldg(P.qp_soa + (long long)(3 * i0 + 1) * P.npad + iLoad);
-        const double oz = __ldg(P.qp_soa + (long long)(3 * i0 + 2) * P.npad + iLoad);
+        const double xi = c_triNodes[kTri8 + i0].xi, eta = c_triNodes[kTri8 + i0].eta;
+        const double ox = __dadd_rn(__dadd_rn(O.ax, __dmul_rn(xi, dbx)), __dmul_rn(eta, dcx));
+        const double oy = __dadd_rn(__dadd_rn(O.ay, __dmul_rn(xi, dby)), __dmul_rn(eta, dcy));
+        const double oz = __dadd_rn(__dadd_rn(O.az, __dmul_rn(xi, dbz)), __dmul_rn(eta, dcz));
         const double w0 = c_triNodes[kTri8 + i0].w;
         double in0 = 0.0, in1 = 0.0, in2 = 0.0, in3 = 0.0;
         double r30 = 0.0, r31 = 0.0;
@@ -230,34 +232,37 @@ __device__ __forceinline__ PairSums pair_exact(const OffDiagParams& P, long long
     return S;
 }
 
-template <bool WITH_K, int RSQ>
-__device__ __forceinline__ void offdiag_ff_body(const OffDiagParams& P) {
-    __shared__ __align__(128) double s_src[kStages][kSub * kQpStride];
-    __shared__ __align__(8) uint64_t s_bar[kStages];
+template <bool WITH_K>
+__global__ void __launch_bounds__(kTileObs) k_offdiag_ff(const OffDiagParams P) {
+    // [kFfSub] x { quadrature points 32 x 48 | bounds 32 x 8 | normals 32 x 4 }, then the barriers
+    extern __shared__ __align__(128) double s_tile[];
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_tile + kFfSub * kFfStageDoubles);
 
     const int tid = threadIdx.x;
     const Tile T = decode_tile(P, blockIdx.x);
     if (T.kind < 0) return;  // lower storage: tile above the diagonal (whole CTA exits)
 
-    if (tid == 0) {
-        mbar_init(&s_bar[0], 1);
-        mbar_init(&s_bar[1], 1);
-#ifndef ICQB_EMU
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-#endif
-    }
-    __syncthreads();
-
     const long long srcLeft = T.srcEnd - T.src0;
     const int nSubTiles =
         (int)(srcLeft >= kTileSrc ? kTileSrc / kSub : (srcLeft + kSub - 1) / kSub);
     if (tid == 0) {
-        for (int s = 0; s < kStages && s < nSubTiles; ++s) {
-            mbar_expect_tx(&s_bar[s], kSubBytes);
-            bulk_g2s(&s_src[s][0], P.qp_aos + (T.src0 + (long long)s * kSub) * kQpStride, kSubBytes,
-                     &s_bar[s]);
+        for (int s = 0; s < kFfSub; ++s) mbar_init(&s_bar[s], 1);
+#ifndef ICQB_EMU
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#endif
+        // the whole source tile at once: the tables are padded by 128 rows beyond n, so that
+        // complete sub-tiles can always be copied
+        for (int s = 0; s < nSubTiles; ++s) {
+            double* dst = s_tile + s * kFfStageDoubles;
+            const long long j0 = T.src0 + (long long)s * kSub;
+            mbar_expect_tx(&s_bar[s], (kFfSrcDoubles + kFfBndDoubles + (WITH_K ? kFfNrmDoubles : 0)) * 8);
+            bulk_g2s(dst, P.qp_aos + j0 * kQpStride, kFfSrcDoubles * 8, &s_bar[s]);
+            bulk_g2s(dst + kFfSrcDoubles, P.bound + j0 * kBndStride, kFfBndDoubles * 8, &s_bar[s]);
+            if (WITH_K)
+                bulk_g2s(dst + kFfSrcDoubles + kFfBndDoubles, P.nrm + j0 * 4, kFfNrmDoubles * 8, &s_bar[s]);
         }
     }
+    __syncthreads();   // the barriers are initialised before anybody waits on them
 
     // observer triangle of this thread
     const long long iObs = T.obs0 + tid;
@@ -291,10 +296,10 @@ __device__ __forceinline__ void offdiag_ff_body(const OffDiagParams& P) {
             O.ny = __ldg(P.nrm + 4 * iLoad + 1);
             O.nz = __ldg(P.nrm + 4 * iLoad + 2);
         }
-        O.cx = __ldg(P.bound + 4 * iLoad + 0);
-        O.cy = __ldg(P.bound + 4 * iLoad + 1);
-        O.cz = __ldg(P.bound + 4 * iLoad + 2);
-        O.rho = __ldg(P.bound + 4 * iLoad + 3);
+        O.cx = __ldg(P.bound + kBndStride * iLoad + 0);
+        O.cy = __ldg(P.bound + kBndStride * iLoad + 1);
+        O.cz = __ldg(P.bound + kBndStride * iLoad + 2);
+        O.rho = __ldg(P.bound + kBndStride * iLoad + 3);
     }
     const double a2Obs = __ldg(P.area2 + iLoad);
     // -1/(4 pi) * 0.5  (icqLaplaceFunctor.cpp:9, icqQuadrature.cpp:245)
@@ -310,40 +315,33 @@ __device__ __forceinline__ void offdiag_ff_body(const OffDiagParams& P) {
     unsigned int nFast = 0, nAll = 0;   // statistics (lane 0 of every warp adds them up)
 
     for (int sub = 0; sub < nSubTiles; ++sub) {
-        const int stage = sub & 1;
-        const uint32_t parity = (sub >> 1) & 1;
         const long long j0 = T.src0 + (long long)sub * kSub;
-        mbar_wait(&s_bar[stage], parity);
-        const double* sp = &s_src[stage][0];
+        mbar_wait(&s_bar[sub], 0);
+        const double* sp = s_tile + sub * kFfStageDoubles;
+        const double* sb = sp + kFfSrcDoubles;
+        const double* sn = sb + kFfBndDoubles;
 
         for (int jj = 0; jj < kSub; ++jj) {
             const long long j = j0 + jj;
             if (j >= T.srcEnd) break;  // uniform
             const double* pj = sp + jj * kQpStride;
-            double njx = 0, njy = 0, njz = 0, pjax = 0, pjay = 0, pjaz = 0;
-            if (WITH_K) {
-                njx = __ldg(P.nrm + 4 * j + 0);
-                njy = __ldg(P.nrm + 4 * j + 1);
-                njz = __ldg(P.nrm + 4 * j + 2);
-                pjax = __ldg(P.verts + 9 * j + 0);
-                pjay = __ldg(P.verts + 9 * j + 1);
-                pjaz = __ldg(P.verts + 9 * j + 2);
-            }
+            const double* bj = sb + jj * kBndStride;
+            const double* nj = sn + jj * 4;
             // separation test of this lane's pair, then the warp's vote
-            const double ex = __ldg(P.bound + 4 * j + 0) - O.cx;
-            const double ey = __ldg(P.bound + 4 * j + 1) - O.cy;
-            const double ez = __ldg(P.bound + 4 * j + 2) - O.cz;
+            const double ex = bj[0] - O.cx;
+            const double ey = bj[1] - O.cy;
+            const double ez = bj[2] - O.cz;
             const double d2 = fma(ez, ez, fma(ey, ey, ex * ex));
-            const double lim = P.kappa * (O.rho + __ldg(P.bound + 4 * j + 3));
+            const double lim = P.kappa * (O.rho + bj[3]);
             const bool farLane = (d2 >= lim * lim) && (d2 >= P.guard2);
             const bool far = __all_sync(0xffffffffu, farLane) != 0;
             nAll += 1;
             PairSums S;
             if (far) {
                 nFast += 1;
-                S = pair_fast<WITH_K, RSQ>(O, pj, njx, njy, njz, pjax, pjay, pjaz);
+                S = pair_fast<WITH_K>(O, pj, nj, bj);
             } else {
-                S = pair_exact<WITH_K>(P, iLoad, O, pj, njx, njy, njz, pjax, pjay, pjaz);
+                S = pair_exact<WITH_K>(O, pj, nj, bj);
             }
 
             const bool offDiag = (T.kind != 0) || (j != iObs);
@@ -364,17 +362,6 @@ __device__ __forceinline__ void offdiag_ff_body(const OffDiagParams& P) {
                 if (P.lower) kuRow[j] = 0.0;
             }
         }
-
-        // refill this stage with sub-tile sub+2 once every thread is done reading it
-        if (sub + kStages < nSubTiles) {
-            __syncthreads();
-            if (tid == 0) {
-                mbar_expect_tx(&s_bar[stage], kSubBytes);
-                bulk_g2s(&s_src[stage][0],
-                         P.qp_aos + (T.src0 + (long long)(sub + kStages) * kSub) * kQpStride,
-                         kSubBytes, &s_bar[stage]);
-            }
-        }
     }
     if (P.stats && (tid & 31) == 0) {
         atomicAdd(P.stats + 0, (unsigned long long)nFast);
@@ -382,29 +369,17 @@ __device__ __forceinline__ void offdiag_ff_body(const OffDiagParams& P) {
     }
 }
 
-// The kernel proper, with as many registers as it wants (254 for G+K: two CTAs per SM, as
-// k_offdiag) ...
-template <bool WITH_K, int RSQ>
-__global__ void __launch_bounds__(kTileObs) k_offdiag_ff(const OffDiagParams P) {
-    offdiag_ff_body<WITH_K, RSQ>(P);
-}
-
-// ... and compiled for three CTAs per SM (at most 168 registers; G+K then spills ~350 bytes,
-// outside the fast loop for the most part): variants 3 and 4, to be measured against 1 and 2.
-template <bool WITH_K, int RSQ>
-__global__ void __launch_bounds__(kTileObs, 3) k_offdiag_ff3(const OffDiagParams P) {
-    offdiag_ff_body<WITH_K, RSQ>(P);
-}
-
-// centroid and radius (largest centroid-vertex distance, rounded up a little) per triangle;
-// the padding rows get a huge radius so that a padded triangle is never "far"
+// centroid, radius (largest centroid-vertex distance, rounded up a little) and first vertex
+// per triangle; the padding rows get a huge radius so that a padded triangle is never "far"
 __global__ void __launch_bounds__(128) k_bounds(const double* __restrict__ verts, long long n,
                                                 long long nalloc, double* __restrict__ bound) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nalloc) return;
+    double* o = bound + kBndStride * t;
     if (t >= n) {
-        bound[4 * t + 0] = bound[4 * t + 1] = bound[4 * t + 2] = 0.0;
-        bound[4 * t + 3] = 1.0e300;
+#pragma unroll
+        for (int k = 0; k < kBndStride; ++k) o[k] = 0.0;
+        o[3] = 1.0e300;
         return;
     }
     const double* v = verts + 9 * t;
@@ -417,22 +392,26 @@ __global__ void __launch_bounds__(128) k_bounds(const double* __restrict__ verts
         const double dx = v[3 * k + 0] - cx, dy = v[3 * k + 1] - cy, dz = v[3 * k + 2] - cz;
         r2 = fmax(r2, fma(dz, dz, fma(dy, dy, dx * dx)));
     }
-    bound[4 * t + 0] = cx;
-    bound[4 * t + 1] = cy;
-    bound[4 * t + 2] = cz;
-    bound[4 * t + 3] = sqrt(r2) * (1.0 + 1.0e-12);
+    o[0] = cx;
+    o[1] = cy;
+    o[2] = cz;
+    o[3] = sqrt(r2) * (1.0 + 1.0e-12);
+    o[4] = v[0];
+    o[5] = v[1];
+    o[6] = v[2];
+    o[7] = 0.0;
 }
 
 }  // namespace
 
 constexpr double kFarKappa = 3.0;
 
-// Prepare the per-triangle bounds (once per mesh) and launch the variant's kernel.
+// Prepare the per-triangle bounds (once per mesh) and launch the kernel.
 int launch_offdiag_ff(icqb_ctx* ctx, const OffDiagParams& params, dim3 grid, bool withK) {
     OffDiagParams P = params;
     const long long nalloc = ctx->ntri_pad + kPad;
     if (!ctx->d_bound) {
-        ICQB_CUDA(ctx, dev_alloc(ctx, &ctx->d_bound, sizeof(double) * 4 * nalloc));
+        ICQB_CUDA(ctx, dev_alloc(ctx, &ctx->d_bound, sizeof(double) * kBndStride * nalloc));
         k_bounds<<<(unsigned)((nalloc + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_verts, ctx->ntri,
                                                                             nalloc, ctx->d_bound);
         ctx->launches += 1;
@@ -451,17 +430,19 @@ int launch_offdiag_ff(icqb_ctx* ctx, const OffDiagParams& params, dim3 grid, boo
     const double guard = ctx->coord_max / 512.0;
     P.guard2 = guard * guard;
     P.stats = ctx->d_ffstats;
-    cudaEventRecord(ctx->ev0, ctx->stream);
-    switch (ctx->offdiag_variant * 2 + (withK ? 1 : 0)) {
-        case 2: k_offdiag_ff<false, 3><<<grid, kTileObs, 0, ctx->stream>>>(P); break;
-        case 3: k_offdiag_ff<true, 3><<<grid, kTileObs, 0, ctx->stream>>>(P); break;
-        case 4: k_offdiag_ff<false, 2><<<grid, kTileObs, 0, ctx->stream>>>(P); break;
-        case 5: k_offdiag_ff<true, 2><<<grid, kTileObs, 0, ctx->stream>>>(P); break;
-        case 6: k_offdiag_ff3<false, 3><<<grid, kTileObs, 0, ctx->stream>>>(P); break;
-        case 7: k_offdiag_ff3<true, 3><<<grid, kTileObs, 0, ctx->stream>>>(P); break;
-        case 8: k_offdiag_ff3<false, 2><<<grid, kTileObs, 0, ctx->stream>>>(P); break;
-        default: k_offdiag_ff3<true, 2><<<grid, kTileObs, 0, ctx->stream>>>(P); break;
+    static bool attr = false;
+    if (!attr) {
+        ICQB_CUDA(ctx, cudaFuncSetAttribute(k_offdiag_ff<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            kFfSmemBytes));
+        ICQB_CUDA(ctx, cudaFuncSetAttribute(k_offdiag_ff<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            kFfSmemBytes));
+        attr = true;
     }
+    cudaEventRecord(ctx->ev0, ctx->stream);
+    if (withK)
+        k_offdiag_ff<true><<<grid, kTileObs, kFfSmemBytes, ctx->stream>>>(P);
+    else
+        k_offdiag_ff<false><<<grid, kTileObs, kFfSmemBytes, ctx->stream>>>(P);
     cudaEventRecord(ctx->ev1, ctx->stream);
     ctx->launches += 1;
     return check_cuda(ctx, cudaGetLastError(), "k_offdiag_ff launch");
@@ -475,8 +456,8 @@ extern "C" {
 
 int icqb_set_assembly_variant(icqb_ctx* ctx, int variant) {
     if (!ctx) return ICQB_EARG;
-    if (variant < 0 || variant > 4)
-        return set_error(ctx, ICQB_EARG, "icqb_set_assembly_variant: variant must be 0 ... 4");
+    if (variant < 0 || variant > 1)
+        return set_error(ctx, ICQB_EARG, "icqb_set_assembly_variant: variant must be 0 or 1");
     ctx->offdiag_variant = variant;
     return ICQB_OK;
 }

@@ -270,8 +270,13 @@ __global__ void __launch_bounds__(kT) k_dense_symmetrise(const DenseDesc* desc, 
     a[j * D.m + i] = avg;
 }
 
-// w = C^-1 r on the rows of the dense blocks: one warp per (valid) row, lanes stride the
-// columns, butterfly sum (fixed order).  Grid ceil(rows / 8) CTAs of 256 threads.
+// w = C^-1 r on the rows of the dense blocks: HBM-bound (the inverse blocks are streamed once
+// per iteration: 1024 * blockTiles * N bytes).  One warp per (valid) row; a lane reads 16-byte
+// pairs of the row, 64 columns apart, eight of them in flight before the first is used (a
+// single dependent 8-byte load per iteration reached 0.8 TB/s in round 2's first run), four
+// partial sums per lane joined in a fixed order, then a butterfly.  The multiplied vector
+// comes through L1 (every row of a block re-reads the same <= 64 KB).
+// Grid ceil(rows / 8) CTAs of 256 threads.
 __global__ void __launch_bounds__(256) k_dense_apply(const DenseDesc* desc, int nblocks,
                                                      long long totalRows, const double* dense,
                                                      const double* x, double* y, const int* skip) {
@@ -283,12 +288,32 @@ __global__ void __launch_bounds__(256) k_dense_apply(const DenseDesc* desc, int 
     while (b + 1 < nblocks && desc[b + 1].row0 <= cr) ++b;
     const DenseDesc D = desc[b];
     const long long lr = cr - D.row0, g0 = D.t0 * kT;
-    const double* row = dense + D.off + lr * D.m;
-    double acc = 0.0;
-    for (long long c = lane; c < D.valid; c += 32) acc = fma(row[c], x[g0 + c], acc);
+    const double* row = dense + D.off + lr * D.m;   // 16-byte aligned: D.off and D.m are even
+    const double* xv = x + g0;
+    const long long valid = D.valid;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    long long c = 2 * lane;
+    // full groups of eight pairs (512 columns per warp pass)
+    for (; c + 7 * 64 + 1 < valid; c += 8 * 64) {
+        double2 a[8];
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-    if (lane == 0) y[g0 + lr] = acc;
+        for (int u = 0; u < 8; ++u)
+            a[u] = __ldcs(reinterpret_cast<const double2*>(row + c + 64 * u));
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            acc[u & 3] = fma(a[u].x, __ldg(xv + c + 64 * u), acc[u & 3]);
+            acc[u & 3] = fma(a[u].y, __ldg(xv + c + 64 * u + 1), acc[u & 3]);
+        }
+    }
+    for (; c < valid; c += 64) {
+        const double2 a = __ldcs(reinterpret_cast<const double2*>(row + c));
+        acc[0] = fma(a.x, __ldg(xv + c), acc[0]);
+        if (c + 1 < valid) acc[1] = fma(a.y, __ldg(xv + c + 1), acc[1]);
+    }
+    double sum = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+    if (lane == 0) y[g0 + lr] = sum;
 }
 
 // mixed-precision fields of the state (switch_thr 0: float32 products off)
@@ -516,7 +541,7 @@ int cg_solve_caps(icqb_ctx* ctx, uint64_t dA_, int64_t n, int64_t ld, int storag
     const long long nfull = chunk * P;
     const long long stateDoubles = (sizeof(CgState) + 7) / 8;
     const long long small = 8 * n + 8 + nfull + 6 * nT + stateDoubles;
-    const long long need = small + nT * kBlockElems + denseDoubles + descDoubles + tileDoubles + 64;
+    const long long need = small + nT * kBlockElems + denseDoubles + descDoubles + tileDoubles + 66;
     int rc = ensure_work(ctx, need);
     if (rc != ICQB_OK) return rc;
     CgBuf B;
@@ -538,6 +563,7 @@ int cg_solve_caps(icqb_ctx* ctx, uint64_t dA_, int64_t n, int64_t ld, int storag
     B.part_pz = wp; wp += nT;
     B.state = reinterpret_cast<CgState*>(wp); wp += stateDoubles;
     double* blocks = wp; wp += nT * kBlockElems;
+    if ((reinterpret_cast<uintptr_t>(wp) & 15) != 0) wp += 1;   // k_dense_apply reads 16-byte pairs
     double* dense = wp; wp += denseDoubles;
     DenseDesc* ddesc = reinterpret_cast<DenseDesc*>(wp); wp += descDoubles;
     int* dtile = reinterpret_cast<int*>(wp); wp += tileDoubles;

@@ -55,16 +55,20 @@ __device__ __forceinline__ double rsqrt_1ulp(double x) {
     double q = e * y0;
     return fma(p, q, y0);
 }
-// mbarrier modelled as the count of completed phases; a bulk copy completes when issued
+// mbarrier modelled as (pending transaction bytes << 32) | completed phases; a bulk copy
+// completes when issued, and the phase completes with the last expected byte
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int) { *bar = 0; }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t*, uint32_t) {}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    *bar += (uint64_t)bytes << 32;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     while ((*reinterpret_cast<volatile uint64_t*>(bar) & 1) == parity) emu::yield();
 }
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes,
                                          uint64_t* bar) {
     memcpy(dst, src, bytes);
-    *bar += 1;
+    *bar -= (uint64_t)bytes << 32;
+    if ((*bar >> 32) == 0) *bar += 1;
 }
 #else
 __device__ __forceinline__ double rsqrt_1ulp(double x) {

@@ -150,22 +150,21 @@ int icqb_gemv_dev(icqb_ctx* ctx, uint64_t dA, int64_t nrows, int64_t ncols, int6
 int icqb_gemv_host(icqb_ctx* ctx, uint64_t dA, int64_t nrows, int64_t ncols, int64_t ld,
                    const double* x, double* y);
 
-/* EXPERIMENTAL (written at the end of round 1 without GPU access; checked in the CPU emulation
- * and by SASS instruction counts only, tests gated by ICQB_EXPERIMENTAL=1): arithmetic of the
- * off-diagonal assembly (bem/icqLaplaceMatrices.cpp:75-101, bem/icqQuadrature.cpp:232-243).
- *   variant 0  (default) the validated kernel: every evaluation from the reference's rounded
- *              quadrature points, 12 (G) / 16 (G+K) FP64 instructions per evaluation;
+/* Arithmetic of the off-diagonal assembly (bem/icqLaplaceMatrices.cpp:75-101,
+ * bem/icqQuadrature.cpp:232-243).
+ *   variant 0  (default) direct: every evaluation from the reference's rounded quadrature
+ *              points, 12 (G) / 16 (G+K) FP64 instructions per evaluation;
  *   variant 1  far-field split: pairs of triangles with |c_i - c_j| >= 3 (rho_i + rho_j)
  *              (centroids, radii) use the affine form of the observer points about the
  *              observer's own vertex, 9 / 13 instructions per evaluation, entries within a
- *              few ulp of variant 0; all other pairs are evaluated as in variant 0;
- *   variant 2  variant 1 with a Newton step instead of the third-order step in the far-field
- *              reciprocal square root (8 / 12 instructions; relative error <= 2.4e-14);
- *   variants 3, 4  = 1, 2 compiled for three CTAs per SM (at most 168 registers; the G+K kernel
- *              then spills a little) instead of two -- which one is faster is a measurement.
+ *              few ulp of variant 0 (5e-15 on a B200, tests/test_gpu_parity.py); all other
+ *              pairs are evaluated as in variant 0.
+ * (Round 1's variants 2-4 -- a Newton step in the reciprocal square root, three CTAs per SM --
+ * were measured on a B200 in round 2 and removed: the Newton step left 3.3e-13, too close to the
+ * 1e-12 contract, and three CTAs per SM were slower.)
  * The stored layouts and every other entry point are unchanged. */
 int icqb_set_assembly_variant(icqb_ctx* ctx, int variant);
-/* After an assembly with variant 1 or 2: how many (warp of 32 observers, source triangle)
+/* After an assembly with variant 1: how many (warp of 32 observers, source triangle)
  * pairs took the far-field arithmetic, out of how many; zeros with variant 0. */
 int icqb_assembly_stats(icqb_ctx* ctx, int64_t* fast_pairs, int64_t* all_pairs);
 

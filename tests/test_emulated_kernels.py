@@ -431,12 +431,11 @@ def _assembly_stats(emu, c):
     return fast.value, allp.value
 
 
-@pytest.mark.parametrize('variant', [1, 2])
+@pytest.mark.parametrize('variant', [1])
 @pytest.mark.parametrize('with_k', [False, True])
 def test_emulated_far_field_split_full_storage(emu, oracle_mod, variant, with_k):
     """k_offdiag_ff on 576 triangles, full storage (mirrored tiles inside the block): every G
-    entry within 1e-12 of the oracle (variant 1: within a few ulp of the validated kernel;
-    variant 2 runs the Newton step from the seed's worst case and stays below 5e-14), K against
+    entry within 1e-12 of the oracle and within a few ulp of the direct kernel, K against
     the definition oracle; a third of the (warp, source) pairs take the far-field arithmetic."""
     c = Ctx(emu, 24, 13)
     n = c.n
@@ -450,16 +449,16 @@ def test_emulated_far_field_split_full_storage(emu, oracle_mod, variant, with_k)
     fast, allp = _assembly_stats(emu, c)
     assert allp == 7424 and 0.3 * allp < fast < 0.5 * allp
     assert numpy.abs(g / ref - 1.).max() < 1e-12
-    assert numpy.abs(g / g0 - 1.).max() < (2e-15 if variant == 1 else 5e-14)
+    assert numpy.abs(g / g0 - 1.).max() < 2e-15
     if with_k:
         kref = oracle_mod.k_block(c.xyz, c.tri, 0, n, 0, n)
         assert numpy.abs(k - kref).max() < 1e-12 * numpy.abs(kref).max()
         assert (numpy.diag(k) == 0.).all()
-    assert emu.icqb_set_assembly_variant(c.h, 5) != 0
+    assert emu.icqb_set_assembly_variant(c.h, 2) != 0
     c.close()
 
 
-@pytest.mark.parametrize('variant', [1, 2, 3, 4])
+@pytest.mark.parametrize('variant', [1])
 def test_emulated_far_field_split_lower_storage(emu, oracle_mod, variant):
     """Lower storage with two separated row blocks, G, K and the transposed K entries."""
     from icqsol_b200.bem import icqRowPartition as rp
@@ -766,7 +765,7 @@ def test_emulated_far_field_split_fuzz(emu):
         tri = numpy.ascontiguousarray(
             numpy.stack([numpy.arange(n), n + numpy.arange(n), 2 * n + numpy.arange(n)], 1).astype(numpy.int64))
         out = {}
-        for variant in (0, 1, 2):
+        for variant in (0, 1):
             assert emu.icqb_set_mesh(h, dp(xyz), xyz.shape[0], lp(tri), n) == 0
             assert emu.icqb_set_assembly_variant(h, variant) == 0
             g, k = numpy.full((n, n), numpy.nan), numpy.full((n, n), numpy.nan)
@@ -774,8 +773,8 @@ def test_emulated_far_field_split_fuzz(emu):
             out[variant] = (g, k)
         off = ~numpy.eye(n, dtype=bool)
         g0, k0 = out[0]
-        for variant in (1, 2):
+        for variant in (1,):
             g, k = out[variant]
-            assert numpy.abs(g[off] / g0[off] - 1.).max() < (2e-13 if variant == 1 else 3e-13)
+            assert numpy.abs(g[off] / g0[off] - 1.).max() < 2e-13
             assert numpy.abs(k - k0)[off].max() < 1e-11 * numpy.abs(k0[off]).max()
     emu.icqb_destroy(h)

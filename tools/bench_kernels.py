@@ -2,7 +2,7 @@
 """Kernel-level timings on one GPU (not the bench contract: tools for the round's notes).
   tools/bench_kernels.py [n_theta n_phi]   -- default 142 71 (config C2)
 Times, with CUDA events on the library's stream, after warm-up:
-  * the off-diagonal assembly (G only and G+K) for assembly variants 0 ... 4;
+  * the off-diagonal assembly (G only and G+K) for assembly variants 0 and 1;
   * the symmetric product on the double matrix (k_symv + k_symv_reduce) and on its float32 copy
     (k_symv_f32 + k_symv_reduce), as GB/s of the bytes each one streams.
 Prints one JSON line."""
@@ -37,7 +37,7 @@ def main():
     ku = torch.empty_like(g)
     out = {'triangles': n, 'stored_tiles': ntiles, 'assembly_ms': {}, 'far_field_fraction': {}}
     pairs = 0.5 * n * n
-    for variant in (0, 1, 2, 3, 4):
+    for variant in (0, 1):
         ctx.check(lib.icqb_set_assembly_variant(ctx.handle, variant))
         for with_k in (False, True):
             times = []

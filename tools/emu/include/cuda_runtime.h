@@ -84,6 +84,11 @@ static inline T __ldg(const T* p) {
 }
 
 template <class T>
+static inline T __ldcs(const T* p) {
+    return *p;
+}
+
+template <class T>
 static inline T emu_shfl(T v, int src) {
     static_assert(sizeof(T) <= 8, "shuffle of at most 8 bytes");
     uint64_t* slot = emu::warp_slots();

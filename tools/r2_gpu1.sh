@@ -13,7 +13,7 @@ done
 summ() { python - "$1" <<'PY'
 import json, sys
 try:
-    d = json.load(open(sys.argv[1]))
+    d = json.loads([l for l in open(sys.argv[1]) if l.startswith("{")][-1])
     r = d['roofline_assembly']; p = d['phases']
     print('  N=%d offdiag %.2f ms %.2f TF/s frac %.3f ff %s | step %.1f ms solve %.1f ms iters %d conv %s bwd %.2e gemv %.3f ms %.0f GB/s' % (
         d['config']['triangles'], r['ms_per_launch'], r['achieved'], r['frac'], r.get('far_field_fraction'),

@@ -8,7 +8,7 @@ timeout 600 python -m pytest tests -m gpu -q > $out/${tag}_pytest.log 2>&1; echo
 summ() { python - "$1" <<'PY'
 import json, sys
 try:
-    d = json.load(open(sys.argv[1]))
+    d = json.loads([l for l in open(sys.argv[1]) if l.startswith("{")][-1])
     r = d['roofline_assembly']; p = d['phases']; e = d.get('e2e') or {}
     print('  N=%d offdiag %.2f ms %.2f TF/s frac %.3f | step %.1f ms solve %.1f ms iters %d conv %s bwd %.2e gemv %.3f ms %.0f GB/s | e2e %s ms | G-only %.1f ms' % (
         d['config']['triangles'], r['ms_per_launch'], r['achieved'], r['frac'],
