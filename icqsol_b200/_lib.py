@@ -63,6 +63,9 @@ SIGNATURES = [
     ('icqb_cg_last_stats', c_int, [c_void_p, c_int64_p, c_int64_p]),
     ('icqb_cg_set_mixed_precision', c_int, [c_void_p, c_double]),
     ('icqb_cg_last_mixed', c_int, [c_void_p, c_int64_p]),
+    ('icqb_lu_local_columns', c_int64, [c_void_p, c_int64]),
+    ('icqb_lu_factor_dev', c_int, [c_void_p, c_uint64, c_int64, c_int64, c_uint64, POINTER(c_int)]),
+    ('icqb_lu_solve_dev', c_int, [c_void_p, c_uint64, c_int64, c_int64, c_uint64, c_uint64, c_uint64]),
     ('icqb_comm_unique_id', c_int, [c_void_p]),
     ('icqb_comm_init', c_int, [c_void_p, c_void_p, c_int, c_int]),
     ('icqb_comm_share', c_int, [c_void_p, c_void_p]),

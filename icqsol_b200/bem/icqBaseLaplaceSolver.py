@@ -373,46 +373,103 @@ class BaseLaplaceSolver(BaseSolver):
             return xd
         return x.cpu().numpy()
 
-    def solveGreenSystemDirect(self, rhs):
+    def solveGreenSystemDirect(self, rhs, tol=5.e-13, maxRefinements=3):
         """Solve G x = rhs by LU with partial pivoting -- the reference's own solve
-        (numpy.linalg.solve, bem/icqLaplaceSolver.py:36) -- on the GPU.  For the matrices the
-        reference's quadrature leaves too indefinite for a CG (sliver triangles, DESIGN.md
-        section 4.6).  EXPERIMENTAL (written without GPU access).  The factorisation is
-        cuSOLVER's through torch.linalg.solve (library code, not one of this package's
-        kernels); the matrix it factors is assembled row-major for the purpose by the same
-        kernels (k_diag, k_offdiag) unless the solver already holds complete rows.  One rank
-        only; needs 16 N^2 bytes of HBM during the solve (the matrix and cuSOLVER's copy).
+        (numpy.linalg.solve, bem/icqLaplaceSolver.py:36) -- on the GPU(s), for the matrices the
+        reference's quadrature leaves too indefinite for a CG and as
+        the fallback of solveGreenSystem.  The factorisation is this package's own
+        (csrc/lu.cu: column blocks of 128 dealt to the ranks, panel factorisation, FP64 tile
+        kernel for the updates).  What it factors is S = diag(A) G (symmetric): complete rows
+        of G are assembled for the purpose by the same kernels (k_diag, k_offdiag) into a
+        separate buffer -- 8 N^2 / P bytes per rank -- and are the columns of S once scaled.
+        The solution is checked against the RESIDENT matrix with the product kernel and
+        refined until max|rhs - G x| <= tol max|rhs| (at most ``maxRefinements`` times).
         @return x float64[N]; details in self.lastSolveInfo"""
         torch = _requireTorchCuda()
-        if self.numRanks != 1:
-            raise RuntimeError('solveGreenSystemDirect: one rank only (the LU is not distributed)')
         n = self.numTriangles
-        b = self._toDevice(rhs)
         if n == 0:
             return numpy.zeros(0, numpy.float64)
-        t0 = torch.cuda.Event(enable_timing=True)
-        t1 = torch.cuda.Event(enable_timing=True)
-        t0.record()
-        if self.storage == 'full':
-            full = self.gMatDevice
-        else:
-            # complete rows, assembled again (tens of milliseconds) rather than expanded
-            full = torch.empty((n, self.ld), dtype=torch.float64, device=b.device)
-            self.ctx.check(self.lib.icqb_set_rows(self.ctx.handle, 0, n))
-            try:
-                self.ctx.check(self.lib.icqb_assemble_dev(self.ctx.handle, int(self.order),
-                                                          full.data_ptr(), 0, self.ld))
-                self.ctx.check(self.lib.icqb_synchronize(self.ctx.handle))
-            finally:
-                self.ctx.check(self.lib.icqb_set_row_blocks(self.ctx.handle, *self.rowBlocks))
-        x = torch.linalg.solve(full[:n, :n], b)
-        resid = (b - full[:n, :n] @ x).abs().max()
-        t1.record()
-        t1.synchronize()
-        rinf = float(resid.item())
+        lib, ctx = self.lib, self.ctx
+        b = self._toDevice(rhs)
+        dev = b.device
+        P, rank = self.numRanks, self.rank
+        ncols = int(lib.icqb_lu_local_columns(ctx.handle, n))
+        ld = self.ld
+        t_wall = time.perf_counter()
+        w = torch.empty((max(ncols, 1), ld), dtype=torch.float64, device=dev)
+        # rows of G into the local column blocks: local block lb <-> global block lb * P + rank
+        nblk = (n + rowPartition.TILE - 1) // rowPartition.TILE
+        try:
+            if P == 1:
+                ctx.check(lib.icqb_set_rows(ctx.handle, 0, n))
+                ctx.check(lib.icqb_assemble_dev(ctx.handle, int(self.order), w.data_ptr(), 0, ld))
+            else:
+                for lb, kb in enumerate(range(rank, nblk, P)):
+                    r0 = kb * rowPartition.TILE
+                    r1 = min(n, r0 + rowPartition.TILE)
+                    ctx.check(lib.icqb_set_rows(ctx.handle, r0, r1))
+                    ctx.check(lib.icqb_assemble_dev(ctx.handle, int(self.order),
+                                                    w[lb * rowPartition.TILE].data_ptr(), 0, ld))
+        finally:
+            if self.storage == 'lower':
+                ctx.check(lib.icqb_set_row_blocks(ctx.handle, *self.rowBlocks))
+            else:
+                ctx.check(lib.icqb_set_rows(ctx.handle, self.rowBlocks[0], self.rowBlocks[1]))
+        assembly_ms = 1e3 * (time.perf_counter() - t_wall)
+        area2 = lib.icqb_area2_dev(ctx.handle)
+        info = ctypes.c_int(0)
+        ctx.check(lib.icqb_lu_factor_dev(ctx.handle, w.data_ptr(), n, ld, area2, ctypes.byref(info)))
+        factor_ms = ctx.last_ms(5)
+        if info.value != 0:
+            raise RuntimeError('solveGreenSystemDirect: the matrix is singular (zero pivot at row '
+                               '{0})'.format(info.value))
+        x = torch.empty(n, dtype=torch.float64, device=dev)
+        ctx.check(lib.icqb_lu_solve_dev(ctx.handle, w.data_ptr(), n, ld, area2, b.data_ptr(), x.data_ptr()))
+        solve_ms = ctx.last_ms(6)
+        # residual with the resident matrix (the validated product), refinement on the factors
         bmax = float(b.abs().max().item())
-        self.lastSolveInfo = {'iterations': 0, 'residual2': float('nan'), 'residualInf': rinf,
-                              'milliseconds': t0.elapsed_time(t1), 'gemvMilliseconds': 0.,
-                              'residualReplacements': 0, 'products': 0, 'method': 'lu',
-                              'converged': bool(rinf <= 1e-10 * bmax or bmax == 0.)}
+        r = torch.empty(n, dtype=torch.float64, device=dev)
+        dx = torch.empty(n, dtype=torch.float64, device=dev)
+        history = []
+        for sweep in range(int(maxRefinements) + 1):
+            self._applyDevice(x, r)                       # r = G x
+            torch.sub(b, r, out=r)
+            rinf = float(r.abs().max().item())
+            history.append(rinf)
+            if rinf <= float(tol) * bmax or sweep == int(maxRefinements):
+                break
+            ctx.check(lib.icqb_lu_solve_dev(ctx.handle, w.data_ptr(), n, ld, area2, r.data_ptr(),
+                                            dx.data_ptr()))
+            solve_ms += ctx.last_ms(6)
+            x += dx
+        del w
+        self.lastSolveInfo = {'iterations': 0, 'residual2': float('nan'), 'residualInf': history[-1],
+                              'milliseconds': assembly_ms + factor_ms + solve_ms,
+                              'luAssemblyMilliseconds': assembly_ms,
+                              'luFactorMilliseconds': factor_ms, 'luSolveMilliseconds': solve_ms,
+                              'gemvMilliseconds': 0., 'residualReplacements': 0, 'products': len(history),
+                              'refinements': len(history) - 1, 'residualHistory': history,
+                              'method': 'lu',
+                              'converged': bool(history[-1] <= float(tol) * bmax or bmax == 0.)}
         return x.cpu().numpy()
+
+    def _applyDevice(self, x, y):
+        """y = G x on device vectors (replicated on every rank), resident matrix."""
+        torch = _requireTorchCuda()
+        n = self.numTriangles
+        torch.cuda.current_stream().synchronize()
+        if self.storage == 'lower':
+            self.ctx.check(self.lib.icqb_symv_dev(self.ctx.handle, self.gMatDevice.data_ptr(),
+                                                  x.data_ptr(), y.data_ptr(), 0))
+            self.ctx.check(self.lib.icqb_synchronize(self.ctx.handle))
+            return
+        rows = self.rowEnd - self.rowBegin
+        yl = torch.empty(max(rows, 1), dtype=torch.float64, device=x.device)
+        stream = self.lib.icqb_stream(self.ctx.handle)
+        self.ctx.check(self.lib.icqb_gemv_dev(self.ctx.handle, self.gMatDevice.data_ptr(), rows, n,
+                                              self.ld, x.data_ptr(), yl.data_ptr(), 0, stream))
+        self.ctx.check(self.lib.icqb_synchronize(self.ctx.handle))
+        if self.numRanks == 1:
+            y.copy_(yl[:n])
+        else:
+            y.copy_(torch.from_numpy(rowPartition.allGatherRows(yl[:rows].cpu().numpy(), n)))

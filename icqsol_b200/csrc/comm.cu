@@ -18,6 +18,7 @@ typedef struct { char internal[128]; } ncclUniqueId;
 typedef int ncclResult_t;
 constexpr int ncclFloat64 = 8;
 constexpr int ncclSum = 0;
+constexpr int ncclMax = 2;
 
 struct Api {
     void* handle = nullptr;
@@ -26,6 +27,7 @@ struct Api {
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
     std::string error;
 };
@@ -37,6 +39,8 @@ int emu_ncclCommInitRank(void** comm, int nranks, const void* id128, int rank);
 int emu_ncclCommDestroy(void* comm);
 int emu_ncclAllReduceSumF64(const void* send, void* recv, size_t count, void* comm);
 int emu_ncclAllGatherF64(const void* send, void* recv, size_t count, void* comm);
+int emu_ncclAllReduceMaxF64(const void* send, void* recv, size_t count, void* comm);
+int emu_ncclBroadcastF64(const void* send, void* recv, size_t count, int root, void* comm);
 }
 Api& api() {
     static Api a;
@@ -50,8 +54,12 @@ Api& api() {
     a.AllGather = [](const void* s, void* r, size_t n, int, ncclComm_t c, cudaStream_t) -> ncclResult_t {
         return emu_ncclAllGatherF64(s, r, n, c);
     };
-    a.AllReduce = [](const void* s, void* r, size_t n, int, int, ncclComm_t c,
-                     cudaStream_t) -> ncclResult_t { return emu_ncclAllReduceSumF64(s, r, n, c); };
+    a.AllReduce = [](const void* s, void* r, size_t n, int, int op, ncclComm_t c,
+                     cudaStream_t) -> ncclResult_t {
+        return op == ncclMax ? emu_ncclAllReduceMaxF64(s, r, n, c) : emu_ncclAllReduceSumF64(s, r, n, c);
+    };
+    a.Broadcast = [](const void* s, void* r, size_t n, int, int root, ncclComm_t c,
+                     cudaStream_t) -> ncclResult_t { return emu_ncclBroadcastF64(s, r, n, root, c); };
     a.GetErrorString = [](ncclResult_t) -> const char* { return "emulated NCCL error"; };
     return a;
 }
@@ -76,6 +84,7 @@ Api& api() {
     ICQB_SYM(CommDestroy, "ncclCommDestroy")
     ICQB_SYM(AllGather, "ncclAllGather")
     ICQB_SYM(AllReduce, "ncclAllReduce")
+    ICQB_SYM(Broadcast, "ncclBroadcast")
     ICQB_SYM(GetErrorString, "ncclGetErrorString")
 #undef ICQB_SYM
     return a;
@@ -157,6 +166,22 @@ int comm_allreduce_sum(icqb_ctx* ctx, double* buf, int64_t count, cudaStream_t s
                       api().AllReduce(buf, buf, (size_t)count, ncclFloat64, ncclSum,
                                       ctx->comm->comm, stream),
                       "ncclAllReduce");
+}
+
+int comm_allreduce_max(icqb_ctx* ctx, double* buf, int64_t count, cudaStream_t stream) {
+    if (comm_nranks(ctx) == 1) return ICQB_OK;
+    return nccl_check(ctx,
+                      api().AllReduce(buf, buf, (size_t)count, ncclFloat64, ncclMax,
+                                      ctx->comm->comm, stream),
+                      "ncclAllReduce(max)");
+}
+
+int comm_broadcast(icqb_ctx* ctx, double* buf, int64_t count, int root, cudaStream_t stream) {
+    if (comm_nranks(ctx) == 1 || count <= 0) return ICQB_OK;
+    return nccl_check(ctx,
+                      api().Broadcast(buf, buf, (size_t)count, ncclFloat64, root, ctx->comm->comm,
+                                      stream),
+                      "ncclBroadcast");
 }
 
 void comm_destroy(icqb_ctx* ctx) {

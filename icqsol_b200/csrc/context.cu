@@ -232,6 +232,7 @@ int icqb_destroy(icqb_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     comm_destroy(ctx);
     symv_plan_free(ctx);
+    lu_free(ctx);
     free_mesh(ctx);
     cudaFree(ctx->d_ffstats);
     dev_free(ctx, ctx->d_A32);

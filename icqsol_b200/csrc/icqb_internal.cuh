@@ -17,7 +17,7 @@ constexpr int kQpStride = 48;    // doubles per triangle in the quadrature-point
 constexpr int kPad = 128;        // triangle count is padded to a multiple of this
 
 // phases for icqb_last_ms
-enum Phase { kPrepare = 0, kOffDiag = 1, kDiag = 2, kGemv = 3, kCg = 4, kNumPhases = 5 };
+enum Phase { kPrepare = 0, kOffDiag = 1, kDiag = 2, kGemv = 3, kCg = 4, kLu = 5, kLuSolve = 6, kNumPhases = 7 };
 
 // Tile-contiguous layout of the block-lower-triangular storage: the locally owned
 // 128-row strips are stored one after the other; strip lt (global tile row I) holds its
@@ -163,7 +163,13 @@ struct icqb_ctx {
     int64_t a32_floats = 0;
     int64_t cg_products32 = 0;     // float32 products of the last solve (from the device state)
 
-    double last_ms[icqb::kNumPhases] = {0, 0, 0, 0, 0};
+    // LU with partial pivoting (lu.cu): pivot rows of the last factorisation, panel buffer, small state
+    long long* d_lu_piv = nullptr;
+    double* d_lu_buf = nullptr;
+    double* d_lu_small = nullptr;
+    int64_t lu_n = 0;
+
+    double last_ms[icqb::kNumPhases] = {0, 0, 0, 0, 0, 0, 0};
     int64_t launches = 0;
     std::string err;
 };
@@ -223,6 +229,10 @@ int comm_rank(const icqb_ctx* ctx);
 int comm_allgather(icqb_ctx* ctx, const double* send, double* recv, int64_t count_per_rank,
                    cudaStream_t stream);
 int comm_allreduce_sum(icqb_ctx* ctx, double* buf, int64_t count, cudaStream_t stream);
+int comm_allreduce_max(icqb_ctx* ctx, double* buf, int64_t count, cudaStream_t stream);
+// in place: `buf` of rank `root` to every rank
+int comm_broadcast(icqb_ctx* ctx, double* buf, int64_t count, int root, cudaStream_t stream);
+void lu_free(icqb_ctx* ctx);
 void comm_destroy(icqb_ctx* ctx);
 // experimental peer exchange (comm.cu): fills `out` for a product over n entries and draws its
 // sequence number; false when no exchange is attached or n does not fit

@@ -238,6 +238,27 @@ int icqb_cg_set_mixed_precision(icqb_ctx* ctx, double switch_rel);
 /* float32 products of the last solve */
 int icqb_cg_last_mixed(const icqb_ctx* ctx, int64_t* products32);
 
+/* ---- direct solve: LU with partial pivoting -----------------------------------------
+ * Replaces rsp = numpy.linalg.solve(gMat, src) (bem/icqLaplaceSolver.py:36, LAPACK dgesv) as
+ * the solve behind the conjugate gradient that cannot "not converge" (sliver meshes).
+ * The matrix is distributed over the ranks of the communicator by COLUMN blocks of 128,
+ * block-cyclic: global column block kb lives on rank kb % P as local block kb / P; the local
+ * columns are stored one after the other, each contiguous with pitch ld (even, >= n), 16-byte
+ * aligned.  icqb_lu_local_columns = how many columns that is for this rank.
+ * icqb_lu_factor_dev overwrites dW with the factors; `dscale` (device, length n, may be 0)
+ * multiplies local column c by scale[global column of c] first -- the host layer stores ROWS of
+ * G there (what the assembly kernels produce) and passes s = |db x dc|, so that the columns are
+ * those of the symmetric matrix S = diag(s) G.  *info = 0, or the (1-based) index of the first
+ * exactly zero pivot (dgetrf's info > 0).
+ * icqb_lu_solve_dev: dx = inv(M) (dscale .* db) for the factored matrix M, i.e. with the same
+ * dscale the solution of G x = b; db and dx are full-length device vectors on every rank (dx is
+ * the same on every rank afterwards).  Milliseconds: icqb_last_ms(ctx, 5) factorisation,
+ * icqb_last_ms(ctx, 6) solve. */
+int64_t icqb_lu_local_columns(const icqb_ctx* ctx, int64_t n);
+int icqb_lu_factor_dev(icqb_ctx* ctx, uint64_t dW, int64_t n, int64_t ld, uint64_t dscale, int* info);
+int icqb_lu_solve_dev(icqb_ctx* ctx, uint64_t dW, int64_t n, int64_t ld, uint64_t dscale,
+                      uint64_t db, uint64_t dx);
+
 /* ---- multi-GPU plumbing -----------------------------------------------------------
  * One rank per process.  `unique_id` is the 128-byte ncclUniqueId produced by
  * icqb_comm_unique_id on rank 0 and broadcast by the caller (torch.distributed
@@ -260,7 +281,8 @@ int icqb_peer_attach(icqb_ctx* ctx, const void* handles);
 
 /* ---- instrumentation ----------------------------------------------------------------
  * Milliseconds (CUDA events on the context stream) of the last call of each phase:
- * which = 0 prepare, 1 off-diagonal, 2 diagonal, 3 last gemv, 4 last cg solve;
+ * which = 0 prepare, 1 off-diagonal, 2 diagonal, 3 last gemv, 4 last cg solve, 5 LU
+ * factorisation, 6 LU solve sweeps;
  * icqb_launch_count: kernels launched by this context since creation. */
 double icqb_last_ms(const icqb_ctx* ctx, int which);
 int64_t icqb_launch_count(const icqb_ctx* ctx);

@@ -409,6 +409,35 @@ int emu_ncclAllReduceSumF64(const void* send, void* recv, size_t count, void* co
     return 0;
 }
 
+int emu_ncclAllReduceMaxF64(const void* send, void* recv, size_t count, void* comm) {
+    FakeComm* c = static_cast<FakeComm*>(comm);
+    World* w = c->world;
+    w->send[c->rank] = send;
+    w->barrier();
+    std::vector<double> tmp(static_cast<const double*>(w->send[0]), static_cast<const double*>(w->send[0]) + count);
+    for (int r = 1; r < w->nranks; ++r) {
+        const double* s = static_cast<const double*>(w->send[r]);
+        for (size_t k = 0; k < count; ++k) tmp[k] = s[k] > tmp[k] ? s[k] : tmp[k];
+    }
+    w->barrier();
+    memcpy(recv, tmp.data(), sizeof(double) * count);
+    w->barrier();
+    return 0;
+}
+
+int emu_ncclBroadcastF64(const void* send, void* recv, size_t count, int root, void* comm) {
+    FakeComm* c = static_cast<FakeComm*>(comm);
+    World* w = c->world;
+    w->send[c->rank] = send;
+    w->barrier();
+    std::vector<double> tmp(static_cast<const double*>(w->send[root]),
+                            static_cast<const double*>(w->send[root]) + count);
+    w->barrier();
+    memcpy(recv, tmp.data(), sizeof(double) * count);
+    w->barrier();
+    return 0;
+}
+
 int emu_ncclAllGatherF64(const void* send, void* recv, size_t count, void* comm) {
     FakeComm* c = static_cast<FakeComm*>(comm);
     World* w = c->world;
