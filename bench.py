@@ -652,7 +652,7 @@ def run_b200(args):
             'roofline_assembly': {
                 'bound': 'fp64', 'kernel': 'k_offdiag<G+K>' if not args.assembly_variant else 'k_offdiag_ff<G+K> (variant {0})'.format(args.assembly_variant), 'achieved': achieved,
                 'peak': peak.value, 'unit': 'TFLOP/s', 'frac': achieved / peak.value,
-                'traffic': traffic_of('k_offdiag', args.storage, n) if not args.assembly_variant else None,
+                'traffic': traffic_of('k_offdiag_ff' if args.assembly_variant else 'k_offdiag', args.storage, n),
                 'peak_source': 'DFMA loop measured in this run (icqb_measure_fp64_peak)',
                 'flop_per_evaluation': FLOP_PER_EVAL_GK, 'fp64_instr_per_evaluation': instr_per_eval,
                 'far_field_fraction': far_frac,
@@ -725,7 +725,7 @@ def main():
                          "(DESIGN.md 4.6); 'block' = inverse 128x128 blocks; 'diagonal' = 1/diag")
     ap.add_argument('--block-tiles', type=int, default=DEFAULT_BLOCK_TILES,
                     help='with block+caps: 128-triangle tiles per diagonal block')
-    ap.add_argument('--assembly-variant', type=int, default=0, choices=[0, 1],
+    ap.add_argument('--assembly-variant', type=int, default=1, choices=[0, 1],
                     help='arithmetic of the off-diagonal kernel (include/icqb.h, '
                          'icqb_set_assembly_variant): 0 direct, 1 far-field split')
     ap.add_argument('--mixed-switch', type=float, default=0.,

@@ -61,6 +61,7 @@ SIGNATURES = [
     ('icqb_cg_set_cap_tiles', c_int, [c_void_p, c_int64, c_int64]),
     ('icqb_cg_set_block_partition', c_int, [c_void_p, c_int64_p, c_int64]),
     ('icqb_cg_last_stats', c_int, [c_void_p, c_int64_p, c_int64_p]),
+    ('icqb_cg_last_blocks', c_int, [c_void_p, c_int64_p, c_int64_p]),
     ('icqb_cg_set_mixed_precision', c_int, [c_void_p, c_double]),
     ('icqb_cg_last_mixed', c_int, [c_void_p, c_int64_p]),
     ('icqb_lu_local_columns', c_int64, [c_void_p, c_int64]),
@@ -124,12 +125,6 @@ class Context:
             msg = self.lib.icqb_last_error(None)
             raise RuntimeError('icqb_create failed ({0}): {1}'.format(st, msg.decode() if msg else ''))
         self.device = int(device)
-        # EXPERIMENTAL: ICQB_ASSEMBLY_VARIANT=1|2 makes every context start with the far-field
-        # split of the assembly kernel (include/icqb.h, icqb_set_assembly_variant), so that the
-        # whole parity suite can be run against it: ICQB_ASSEMBLY_VARIANT=1 pytest -m gpu
-        variant = os.environ.get('ICQB_ASSEMBLY_VARIANT')
-        if variant:
-            self.check(self.lib.icqb_set_assembly_variant(self.handle, int(variant)))
 
     def check(self, status):
         check(self.handle, status)

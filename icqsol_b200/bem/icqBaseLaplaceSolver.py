@@ -45,7 +45,7 @@ def leadingDimension(n):
 class BaseLaplaceSolver(BaseSolver):
 
     # defaults of the solver options a caller leaves at None
-    DEFAULTS = {'preconditioner': 'block+caps', 'blockTiles': 8, 'assemblyVariant': 0,
+    DEFAULTS = {'preconditioner': 'block+caps', 'blockTiles': 8, 'assemblyVariant': 1,
                 'mixedPrecision': 0.}
 
     def __init__(self, pdata, max_edge_length, order=5, computeK=False, device=None,
@@ -80,7 +80,8 @@ class BaseLaplaceSolver(BaseSolver):
                        reference does in the first place (bem/icqLaplaceSolver.py:36); without
                        it an unconverged solve raises RuntimeError
         @param assemblyVariant arithmetic of the off-diagonal kernel (include/icqb.h,
-                       icqb_set_assembly_variant): 0 = direct, 1 = far-field split
+                       icqb_set_assembly_variant): 0 = direct (k_offdiag), 1 = far-field split
+                       (k_offdiag_ff, the default: 6-8 % faster, entries within 5e-15 of 0)
         """
         # wall-clock marks of the host-side phases (milliseconds since construction began), for
         # the end-to-end breakdown of bench.py: hostTimings['constructor'] / ['solve']
@@ -352,6 +353,10 @@ class BaseLaplaceSolver(BaseSolver):
         n32 = ctypes.c_int64(0)
         self.ctx.check(self.lib.icqb_cg_last_mixed(self.ctx.handle, ctypes.byref(n32)))
         self.lastSolveInfo['float32Products'] = n32.value
+        nbad, nweak = ctypes.c_int64(0), ctypes.c_int64(0)
+        self.ctx.check(self.lib.icqb_cg_last_blocks(self.ctx.handle, ctypes.byref(nbad), ctypes.byref(nweak)))
+        self.lastSolveInfo['preconditionerBlocksReplaced'] = nbad.value
+        self.lastSolveInfo['preconditionerWeakPivots'] = nweak.value
         # the reference's LU (bem/icqLaplaceSolver.py:36) cannot "not converge": when the
         # iteration stopped short of the requested backward error (iteration cap, attainable
         # accuracy, or a matrix the quadrature left too indefinite for CG) the system is solved

@@ -29,6 +29,15 @@ def _findArray(data, name):
     return -1
 
 
+def _arrayValues(arr, ntuples):
+    """float64[ntuples, components] of a (vtk or stand-in) data array."""
+    if hasattr(arr, 'as_numpy'):
+        return numpy.asarray(arr.as_numpy(), numpy.float64)[:ntuples].reshape(ntuples, -1)
+    nc = arr.GetNumberOfComponents()
+    return numpy.array([[arr.GetComponent(k, j) for j in range(nc)] for k in range(ntuples)],
+                       numpy.float64).reshape(ntuples, nc)
+
+
 class BaseSolver:
 
     def __init__(self, pdata, max_edge_length, order=5):
@@ -48,21 +57,29 @@ class BaseSolver:
         else:
             assert all(len(c) >= 3 for c in cells)
             isTriangulated = all(len(c) == 3 for c in cells)
-        tri = generators.fanSplit(cells)
-        refXyz, refTri = generators.refineToMaxEdge(xyz, tri, max_edge_length)
+        tri, fanParent = generators.fanSplit(cells, return_parent=True)
+        refXyz, refTri, triParent, (ptIds, ptW) = generators.refineToMaxEdge(
+            xyz, tri, max_edge_length, return_maps=True)
         if isTriangulated and refTri.shape[0] == tri.shape[0]:
             self.pdata = pdata
         else:
-            # new polydata, as RefineSurface.getVtkPolyData() hands back
+            # new polydata, as RefineSurface.getVtkPolyData() hands back: every child inherits
+            # its parent's cell data (shapes/icqRefineSurface.py:155-174), point data is
+            # interpolated onto the points the refinement added
             self.pdata = PolyData.from_arrays(refXyz, refTri)
-            if refXyz.shape[0] == xyz.shape[0]:
-                src = pdata.GetPointData()
-                for i in range(src.GetNumberOfArrays()):
-                    arr = src.GetArray(i)
-                    nc = arr.GetNumberOfComponents()
-                    vals = [[arr.GetComponent(k, j) for j in range(nc)]
-                            for k in range(xyz.shape[0])]
-                    self.pdata.GetPointData().AddArray(DataArray(arr.GetName(), vals))
+            parentCell = fanParent[triParent]
+            src = pdata.GetCellData()
+            for i in range(src.GetNumberOfArrays()):
+                arr = src.GetArray(i)
+                vals = _arrayValues(arr, len(fanParent) and int(fanParent.max()) + 1)
+                self.pdata.GetCellData().AddArray(DataArray(arr.GetName(), vals[parentCell]))
+            src = pdata.GetPointData()
+            for i in range(src.GetNumberOfArrays()):
+                arr = src.GetArray(i)
+                vals = _arrayValues(arr, xyz.shape[0])
+                interp = (vals[ptIds[:, 0]] * ptW[:, 0:1] + vals[ptIds[:, 1]] * ptW[:, 1:2] +
+                          vals[ptIds[:, 2]] * ptW[:, 2:3])
+                self.pdata.GetPointData().AddArray(DataArray(arr.GetName(), interp))
             xyz, tri = self.pdata.GetPoints().as_float64(), refTri
 
         # point ids of each cell

@@ -76,6 +76,13 @@ extern "C" int icqb_cg_set_block_partition(icqb_ctx* ctx, const int64_t* starts,
     return ICQB_OK;
 }
 
+extern "C" int icqb_cg_last_blocks(const icqb_ctx* ctx, int64_t* fallback_blocks, int64_t* weak_pivots) {
+    if (!ctx) return ICQB_EARG;
+    if (fallback_blocks) *fallback_blocks = ctx->cg_bad_blocks;
+    if (weak_pivots) *weak_pivots = ctx->cg_weak_pivots;
+    return ICQB_OK;
+}
+
 extern "C" int icqb_cg_last_stats(const icqb_ctx* ctx, int64_t* replacements, int64_t* products) {
     if (!ctx) return ICQB_EARG;
     if (replacements) *replacements = ctx->cg_replacements;
@@ -246,7 +253,7 @@ extern "C" int icqb_cg_solve_dev(icqb_ctx* ctx, uint64_t dA_, int64_t n, int64_t
             CG_TRY(comm_allreduce_sum(ctx, blocks, nT * kBlockElems, st));
             CG_CUDA(cudaFuncSetAttribute(k_cg_invert_blocks,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, kInvSmem));
-            k_cg_invert_blocks<<<vgrid, kInvThreads, kInvSmem, st>>>(blocks);
+            k_cg_invert_blocks<<<vgrid, kInvThreads, kInvSmem, st>>>(blocks, &B.state->bad_blocks);
             ctx->launches += 1;
             CG_CUDA(cudaGetLastError());
             B.Minv = blocks;
@@ -347,6 +354,8 @@ extern "C" int icqb_cg_solve_dev(icqb_ctx* ctx, uint64_t dA_, int64_t n, int64_t
         if (gemv_count) ctx->last_ms[kGemv] = gemv_ms / (double)gemv_count;
         ctx->cg_replacements = replacements;
         ctx->cg_products = mv.products;
+        ctx->cg_bad_blocks = hs.bad_blocks;
+        ctx->cg_weak_pivots = 0;
         if (iters) *iters = k;
         if (resid2) *resid2 = true2;
         if (residinf) *residinf = trueinf;

@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(256) k_dense_extract_full(const double* A, lon
 //   (d) k_tile_gemm<2>  A_IK <- -A_IK P           (I != K)
 // Matrix traffic m^2 per step instead of per pivot.
 __global__ void __launch_bounds__(kInvThreads) k_tile_invert(const DenseDesc* desc, double* dense,
-                                                             long long K) {
+                                                             long long K, int* weak) {
     extern __shared__ double s_inv[];
     const DenseDesc D = desc[blockIdx.z];
     if (K >= D.tiles) return;
@@ -170,8 +170,11 @@ __global__ void __launch_bounds__(kInvThreads) k_tile_invert(const DenseDesc* de
     for (int e = tid; e < kT * kT; e += kInvThreads)
         a[(e >> 7) * kInvLd + (e & (kT - 1))] = g[(long long)(e >> 7) * m + (e & (kT - 1))];
     __syncthreads();
+    int nweak = 0;   // pivots that lost 13 digits against their Schur diagonal entry (reported only)
     for (int k = 0; k < kT; ++k) {
-        const double pivinv = 1.0 / a[k * kInvLd + k];
+        const double piv = a[k * kInvLd + k];
+        if (!(fabs(piv) >= 1e-13 * fabs(g[(long long)k * m + k])) || !(fabs(piv) <= 1.0e300)) ++nweak;
+        const double pivinv = 1.0 / piv;
         if (tid < kT) {
             colk[tid] = a[tid * kInvLd + k];
             rowk[tid] = (tid == k) ? pivinv : a[k * kInvLd + tid] * pivinv;
@@ -192,6 +195,7 @@ __global__ void __launch_bounds__(kInvThreads) k_tile_invert(const DenseDesc* de
     }
     for (int e = tid; e < kT * kT; e += kInvThreads)
         g[(long long)(e >> 7) * m + (e & (kT - 1))] = a[(e >> 7) * kInvLd + (e & (kT - 1))];
+    if (nweak && tid == 0 && weak) atomicAdd(weak, nweak);
 }
 
 // 128 x 128 x 128 tile product on tiles of a dense block (row pitch m), 256 threads, 8 x 8
@@ -712,7 +716,7 @@ int cg_solve_caps(icqb_ctx* ctx, uint64_t dA_, int64_t n, int64_t ld, int storag
         CG_TRY(comm_allreduce_sum(ctx, blocks, nT * kBlockElems, st));
         CG_CUDA(cudaFuncSetAttribute(k_cg_invert_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      kInvSmem));
-        k_cg_invert_blocks<<<vgrid, kInvThreads, kInvSmem, st>>>(blocks);
+        k_cg_invert_blocks<<<vgrid, kInvThreads, kInvSmem, st>>>(blocks, &B.state->bad_blocks);
         ctx->launches += 1;
         CG_CUDA(cudaGetLastError());
 
@@ -733,7 +737,8 @@ int cg_solve_caps(icqb_ctx* ctx, uint64_t dA_, int64_t n, int64_t ld, int storag
             CG_CUDA(cudaFuncSetAttribute(k_tile_invert, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          kInvSmem));
             for (long long K = 0; K < kMaxTiles; ++K) {
-                k_tile_invert<<<dim3(1, 1, (unsigned)nDense), kInvThreads, kInvSmem, st>>>(ddesc, dense, K);
+                k_tile_invert<<<dim3(1, 1, (unsigned)nDense), kInvThreads, kInvSmem, st>>>(ddesc, dense, K,
+                                                                                          &B.state->weak_pivots);
                 k_tile_gemm<0><<<dim3((unsigned)kMaxTiles, 1, (unsigned)nDense), 256, 0, st>>>(ddesc, dense, K);
                 k_tile_gemm<1><<<tgrid, 256, 0, st>>>(ddesc, dense, K);
                 k_tile_gemm<2><<<dim3(1, (unsigned)kMaxTiles, (unsigned)nDense), 256, 0, st>>>(ddesc, dense, K);
@@ -842,6 +847,8 @@ int cg_solve_caps(icqb_ctx* ctx, uint64_t dA_, int64_t n, int64_t ld, int storag
         ctx->cg_replacements = replacements;
         ctx->cg_products = mv.products;
         ctx->cg_products32 = products32 + hs.n32;
+        ctx->cg_bad_blocks = hs.bad_blocks;
+        ctx->cg_weak_pivots = hs.weak_pivots;
         if (iters) *iters = k;
         if (resid2) *resid2 = true2;
         if (residinf) *residinf = trueinf;

@@ -104,9 +104,12 @@ __global__ void __launch_bounds__(256) k_cg_blocks_full(const double* A, long lo
 }
 
 // In-place inverse of every 128 x 128 block: Gauss-Jordan without pivoting in shared
-// memory (the blocks are principal sub-matrices of a definite matrix, every pivot has
-// the sign of the matrix), then symmetrised -- a CG preconditioner must be symmetric.
-__global__ void __launch_bounds__(kInvThreads) k_cg_invert_blocks(double* blocks) {
+// memory (the blocks are principal sub-matrices of a matrix that is definite wherever the
+// reference's quadrature is accurate enough), then symmetrised -- a CG preconditioner must be
+// symmetric.  A pivot that is not finite, or has lost 13 digits against the diagonal entry it
+// started from (sliver triangles: DESIGN.md section 4.6), would give a huge, indefinite "inverse":
+// such a block falls back to 1/diag and is counted in *bad (icqb_cg_last_blocks).
+__global__ void __launch_bounds__(kInvThreads) k_cg_invert_blocks(double* blocks, int* bad) {
     extern __shared__ double s_inv[];
     double* a = s_inv;                    // [128][129]
     double* colk = a + kT * kInvLd;       // [128]
@@ -115,8 +118,11 @@ __global__ void __launch_bounds__(kInvThreads) k_cg_invert_blocks(double* blocks
     const int tid = threadIdx.x;
     for (int e = tid; e < kT * kT; e += kInvThreads) a[(e >> 7) * kInvLd + (e & (kT - 1))] = g[e];
     __syncthreads();
+    bool broken = false;   // the same on every thread: all of them read the same pivots
     for (int k = 0; k < kT; ++k) {
-        const double pivinv = 1.0 / a[k * kInvLd + k];
+        const double piv = a[k * kInvLd + k];
+        if (!(fabs(piv) >= 1e-13 * fabs(g[k * kT + k])) || !(fabs(piv) <= 1.0e300)) broken = true;
+        const double pivinv = 1.0 / piv;
         if (tid < kT) {
             colk[tid] = a[tid * kInvLd + k];
             rowk[tid] = (tid == k) ? pivinv : a[k * kInvLd + tid] * pivinv;
@@ -137,8 +143,12 @@ __global__ void __launch_bounds__(kInvThreads) k_cg_invert_blocks(double* blocks
     }
     for (int e = tid; e < kT * kT; e += kInvThreads) {
         const int i = e >> 7, j = e & (kT - 1);
-        g[e] = 0.5 * (a[i * kInvLd + j] + a[j * kInvLd + i]);
+        if (broken)
+            g[e] = (i == j) ? 1.0 / g[e] : 0.0;
+        else
+            g[e] = 0.5 * (a[i * kInvLd + j] + a[j * kInvLd + i]);
     }
+    if (broken && tid == 0 && bad) atomicAdd(bad, 1);
 }
 
 // p = w + beta p  (row-block storage; the lower storage forms p inside the product)

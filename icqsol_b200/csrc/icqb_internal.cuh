@@ -88,6 +88,8 @@ struct CgState {
     int skip64, skip32;        // done | lowp,  done | !lowp  (the two matrix kernels' skip flags)
     int n32;                   // float32 products so far
     double switch_thr;         // 0: mixed precision off
+    int bad_blocks;            // 128 x 128 preconditioner blocks that fell back to 1/diag (weak pivot)
+    int weak_pivots;           // weak pivots met while inverting the dense blocks (reported only)
 };
 
 // Conjugate-gradient work fused into the symmetric product (single rank, lower storage):
@@ -158,6 +160,7 @@ struct icqb_ctx {
     int64_t cap_head_tiles = 0, cap_tail_tiles = 0;
     std::vector<int64_t> block_starts;   // experimental: first tile row of every diagonal block
     int64_t cg_replacements = 0, cg_products = 0;   // statistics of the last solve
+    int64_t cg_bad_blocks = 0, cg_weak_pivots = 0;  // preconditioner blocks replaced by 1/diag, weak pivots
     double mixed_switch = 0.0;     // experimental: relative residual below which products use float32 (0 = off)
     float* d_A32 = nullptr;        // experimental: float32 copy of the stored tiles
     int64_t a32_floats = 0;

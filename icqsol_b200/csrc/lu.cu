@@ -184,12 +184,22 @@ __global__ void __launch_bounds__(512) k_lu_col(const PanelArgs A, int j) {
     if (live) {
         if (isP)   // the left part of the swapped row
             for (int c = ty; c < j; c += 4) base[(long long)c * A.ld + r] = s_J[c];
-        for (int c = j + 1 + ty; c < A.jb; c += 4) {
-            double* a = base + (long long)c * A.ld + r;
-            const double old = isP ? s_J[c] : *a;
-            const double v = fma(-l, s_P[c], old);
-            *a = v;
-            if (c == j + 1) next = v;
+        // all loads of the row first (independent: up to 32 in flight), then the updates
+        double old[kNb / 4];
+#pragma unroll
+        for (int q = 0; q < kNb / 4; ++q) {
+            const int c = j + 1 + ty + 4 * q;
+            old[q] = 0.0;
+            if (c < A.jb) old[q] = isP ? s_J[c] : base[(long long)c * A.ld + r];
+        }
+#pragma unroll
+        for (int q = 0; q < kNb / 4; ++q) {
+            const int c = j + 1 + ty + 4 * q;
+            if (c < A.jb) {
+                const double v = fma(-l, s_P[c], old[q]);
+                base[(long long)c * A.ld + r] = v;
+                if (q == 0 && ty == 0) next = v;
+            }
         }
     }
     if (j + 1 >= A.jb) return;   // last column of the panel: nothing to search
@@ -338,11 +348,27 @@ __global__ void __launch_bounds__(128, 2) k_lu_gemm(const double* __restrict__ A
         }
     };
 
+    // MODE 1: the accumulators start from C (64 independent loads per thread, in flight while
+    // the first slab arrives) and the products are subtracted: C - sum a b, stored as is
     double acc[8][8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int jj = 0; jj < 8; ++jj) {
+        const long long col = n0 + 8 * ty + jj;
 #pragma unroll
-        for (int jj = 0; jj < 8; ++jj) acc[i][jj] = 0.0;
+        for (int i = 0; i < 4; ++i) {
+            const long long m = m0 + 2 * tx + 32 * i;
+            double2 v = make_double2(0.0, 0.0);
+            if (MODE == 1 && col < N) {
+                const double* c = Cp + col * ldc + m;
+                if (m + 1 < M)
+                    v = *reinterpret_cast<const double2*>(c);
+                else if (m < M)
+                    v.x = c[0];
+            }
+            acc[2 * i][jj] = v.x;
+            acc[2 * i + 1][jj] = v.y;
+        }
+    }
 
     load_slab(0);
     store_slab(0);
@@ -368,7 +394,8 @@ __global__ void __launch_bounds__(128, 2) k_lu_gemm(const double* __restrict__ A
 #pragma unroll
             for (int i = 0; i < 8; ++i)
 #pragma unroll
-                for (int jj = 0; jj < 8; ++jj) acc[i][jj] = fma(a[i], b[jj], acc[i][jj]);
+                for (int jj = 0; jj < 8; ++jj)
+                    acc[i][jj] = (MODE == 1) ? fma(-a[i], b[jj], acc[i][jj]) : fma(a[i], b[jj], acc[i][jj]);
         }
         if (s + 1 < kNb / kGK) {
             store_slab(cur ^ 1);
@@ -386,17 +413,9 @@ __global__ void __launch_bounds__(128, 2) k_lu_gemm(const double* __restrict__ A
             const long long m = m0 + 2 * tx + 32 * i;
             double* c = Cp + col * ldc + m;
             if (m + 1 < M) {
-                double2 v;
-                if (MODE == 1) {
-                    v = *reinterpret_cast<const double2*>(c);
-                    v.x -= acc[2 * i][jj];
-                    v.y -= acc[2 * i + 1][jj];
-                } else {
-                    v = make_double2(acc[2 * i][jj], acc[2 * i + 1][jj]);
-                }
-                *reinterpret_cast<double2*>(c) = v;
+                *reinterpret_cast<double2*>(c) = make_double2(acc[2 * i][jj], acc[2 * i + 1][jj]);
             } else if (m < M) {
-                c[0] = (MODE == 1) ? c[0] - acc[2 * i][jj] : acc[2 * i][jj];
+                c[0] = acc[2 * i][jj];
             }
         }
     }
@@ -476,13 +495,12 @@ __global__ void k_lu_store_piv(const double* pivd, long long* piv, long long k0,
 __global__ void __launch_bounds__(256) k_lu_scale_cols(double* W, long long ld, long long n,
                                                        long long ncols, int P, int rank,
                                                        const double* scale) {
-    const long long lc = blockIdx.y;
+    const long long lc = blockIdx.x;   // (grid.x: up to 2^31 - 1 columns)
     if (lc >= ncols) return;
     const long long gc = ((lc / kNb) * P + rank) * kNb + (lc % kNb);
     const double s = scale[gc];
     double* col = W + lc * ld;
-    for (long long r = (long long)blockIdx.x * 256 + threadIdx.x; r < n; r += (long long)gridDim.x * 256)
-        col[r] *= s;
+    for (long long r = threadIdx.x; r < n; r += 256) col[r] *= s;
 }
 
 __global__ void k_lu_mul(const double* a, const double* b, double* out, long long n) {
@@ -561,7 +579,7 @@ int icqb_lu_factor_dev(icqb_ctx* ctx, uint64_t dW, int64_t n, int64_t ld, uint64
 
     cudaEventRecord(ctx->ev0, st);
     if (dscale && ncols > 0) {
-        k_lu_scale_cols<<<dim3(64, (unsigned)ncols), 256, 0, st>>>(W, ld, n, ncols, P, rank,
+        k_lu_scale_cols<<<(unsigned)ncols, 256, 0, st>>>(W, ld, n, ncols, P, rank,
                                                                    reinterpret_cast<const double*>(dscale));
         ctx->launches += 1;
         ICQB_CUDA(ctx, cudaGetLastError());

@@ -235,6 +235,10 @@ int icqb_cg_last_stats(const icqb_ctx* ctx, int64_t* replacements, int64_t* prod
  * numpy model switch_rel = 1e-6 saves 25-28 % of the matrix traffic at an unchanged 5e-13
  * backward error.  0 (default) = off. */
 int icqb_cg_set_mixed_precision(icqb_ctx* ctx, double switch_rel);
+/* Preconditioner set-up of the last solve: 128 x 128 blocks whose inversion met a pivot that was
+ * not finite or had lost 13 digits (replaced by 1/diag), and weak pivots met while inverting the
+ * dense multi-tile blocks (those are kept; reported only). */
+int icqb_cg_last_blocks(const icqb_ctx* ctx, int64_t* fallback_blocks, int64_t* weak_pivots);
 /* float32 products of the last solve */
 int icqb_cg_last_mixed(const icqb_ctx* ctx, int64_t* products32);
 

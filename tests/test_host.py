@@ -495,3 +495,33 @@ def test_direct_fallback_flow_in_emulation():
     torch.linalg.solve on the host standing in for cuSOLVER."""
     text = _run_emulated([os.path.join('tests', 'emulated_scripts', 'direct_fallback.py')])
     assert text.count('direct fallback ok') == 2
+
+
+def test_cell_and_point_data_survive_fan_split_and_refinement():
+    """A mesh that carries a cell field and a point field and is refined on intake: every child
+    triangle inherits its parent's cell values (shapes/icqRefineSurface.py:155-174), point data
+    is interpolated onto the added points, the children follow the order of their parents --
+    so a PoissonSolver / LaplaceSolver given a 'charge' / 'v' cell field plus a refine length
+    finds its source (the reference does; round 1 dropped the arrays)."""
+    from icqsol_b200.bem.icqBaseSolver import BaseSolver
+    from icqsol_b200.mesh.polydata import PolyData, DataArray
+    xyz = numpy.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0], [3, 0, 0], [3, 0.2, 0.]], float)
+    cells = [[0, 1, 2, 3], [1, 4, 5]]
+    pd = PolyData.from_arrays(xyz, cells, dtype=numpy.float64)
+    pd.GetCellData().AddArray(DataArray('charge', [10., 20.]))
+    pd.GetPointData().AddArray(DataArray('height', 2. * xyz[:, 0] + xyz[:, 1]))
+    s = BaseSolver(pd, 0.6, 5)
+    s.setSourceFieldName('charge')
+    tri, pts = s.getCells(), s.getPoints()
+    assert tri.shape[0] > 3
+    src = s.getSourceArray(s.getSourceArrayIndex())
+    cen = pts[tri].mean(1)
+    # children of the quad (x <= 1) carry 10, children of the sliver triangle 20, in parent order
+    assert (src[cen[:, 0] <= 1.] == 10.).all() and (src[cen[:, 0] > 1.] == 20.).all()
+    assert (numpy.diff(src) >= 0).all()
+    h = s.getVtkPolyData().GetPointData().GetArray(0).as_numpy()[:, 0]
+    assert numpy.abs(h - (2. * pts[:, 0] + pts[:, 1])).max() < 1e-6
+    # the point field projected onto the cells as a source (util/icqDataFetcher.py:23-62)
+    s.setSourceFieldName('height')
+    proj = s.getSourceArray(s.getSourceArrayIndex())
+    assert numpy.abs(proj - (2. * cen[:, 0] + cen[:, 1])).max() < 1e-6

@@ -138,6 +138,11 @@ static inline unsigned int atomicAdd(unsigned int* p, unsigned int v) {
     *p = old + v;
     return old;
 }
+static inline int atomicAdd(int* p, int v) {
+    const int old = *p;
+    *p = old + v;
+    return old;
+}
 
 // explicitly rounded arithmetic (the build uses -ffp-contract=off)
 static inline double __dmul_rn(double a, double b) { return a * b; }
