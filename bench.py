@@ -421,7 +421,8 @@ def run_b200(args):
     dense_runs = []
     if kind == 2:
         # one dense block per run of sliver tiles, blocks of --block-tiles tiles elsewhere
-        starts, dense_runs = rowPartition.sliverBlockPartition(xyz, tri, blockTiles=args.block_tiles)
+        cuts = rowPartition.rankCuts(n, world) if (args.storage == 'lower' and world > 1) else None
+        starts, dense_runs = rowPartition.sliverBlockPartition(xyz, tri, blockTiles=args.block_tiles, cuts=cuts)
         starts = numpy.ascontiguousarray(starts, numpy.int64)
         ctx.check(lib.icqb_cg_set_block_partition(ctx.handle, starts.ctypes.data_as(_lib.c_int64_p),
                                                   len(starts)))

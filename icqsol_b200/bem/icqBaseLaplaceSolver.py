@@ -137,19 +137,22 @@ class BaseLaplaceSolver(BaseSolver):
         self.ctx.check(self.lib.icqb_cg_set_preconditioner(
             self.ctx.handle, {'diagonal': 0, 'block': 1, 'block+caps': 2}[preconditioner]))
         self.ctx.check(self.lib.icqb_cg_set_mixed_precision(self.ctx.handle, float(mixedPrecision)))
+        self.rank, self.numRanks = rowPartition.worldInfo()
         self.capTiles = (0, 0)
         self.denseRuns = []
         if preconditioner == 'block+caps':
             # one dense block per run of tiles that hold slivers, wherever it lies in the list
-            # (on a UV sphere: the head and tail caps of sliverCapTiles)
+            # (on a UV sphere: the head and tail caps of sliverCapTiles); the other blocks end
+            # where the ranks' row blocks do, so that each of them lives on one rank
             self.capTiles = rowPartition.sliverCapTiles(self._xyz, self._tri)
+            cuts = rowPartition.rankCuts(self.numTriangles, self.numRanks) \
+                if (storage == 'lower' and self.numRanks > 1) else None
             starts, self.denseRuns = rowPartition.sliverBlockPartition(
-                self._xyz, self._tri, blockTiles=int(blockTiles))
+                self._xyz, self._tri, blockTiles=int(blockTiles), cuts=cuts)
             starts = numpy.ascontiguousarray(starts, numpy.int64)
             self.ctx.check(self.lib.icqb_cg_set_block_partition(
                 self.ctx.handle, starts.ctypes.data_as(_lib.c_int64_p), len(starts)))
 
-        self.rank, self.numRanks = rowPartition.worldInfo()
         # one NCCL communicator per process, shared by every solver
         _lib.attachCommunicator(self.ctx, self.rank, self.numRanks, rowPartition.broadcastBytes)
         mark('options, communicator')

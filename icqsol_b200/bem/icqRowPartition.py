@@ -195,8 +195,18 @@ def sliverTiles(xyz, tri, threshold=30.):
     return flagged
 
 
+def rankCuts(n, nranks):
+    """Tile rows at which the folded row blocks of the ranks begin or end (foldedTileRows): a
+    diagonal block of the preconditioner that does not cross one of them lives on ONE rank,
+    which then extracts, inverts and applies it alone (csrc/cg_caps.cu)."""
+    cuts = set()
+    for (a0, a1, b0, b1) in foldedTileRows(n, nranks):
+        cuts.update((a0, a1, b0, b1))
+    return sorted(cuts)
+
+
 def sliverBlockPartition(xyz, tri, blockTiles=1, threshold=30., gapTiles=4, maxTiles=64,
-                         budgetFraction=0.125, budgetFloor=6.4e7, flagged=None):
+                         budgetFraction=0.125, budgetFloor=6.4e7, flagged=None, cuts=None):
     """First tile row of every diagonal block of the experimental preconditioner
     (icqb_cg_set_block_partition) for a mesh whose slivers may sit ANYWHERE in the triangle
     list -- e.g. the poles of the inner sphere of a hollow sphere: every run of tiles that hold
@@ -207,6 +217,8 @@ def sliverBlockPartition(xyz, tri, blockTiles=1, threshold=30., gapTiles=4, maxT
     If the dense blocks would take more than ``budgetFraction`` of the lower storage
     (N^2 / 2 entries; at least ``budgetFloor`` entries), the gaps are no longer merged; if that is still too much, only runs
     that reach the two ends of the list are kept.
+    ``cuts`` (tile rows, e.g. rankCuts): the blocks of the clean stretches also end there (the
+    sliver runs are never cut).
     @return (starts, denseRuns): list of first tile rows; [(first tile, tiles)] of the runs"""
     if flagged is None:
         flagged = sliverTiles(xyz, tri, threshold)
@@ -245,18 +257,29 @@ def sliverBlockPartition(xyz, tri, blockTiles=1, threshold=30., gapTiles=4, maxT
         runs = [r for r in runs if r[0] == 0 or r[0] + r[1] == nT]
     if cost(runs) > budget:
         runs = []
+    cutList = sorted(int(c) for c in (cuts or []) if 0 < int(c) < nT)
+
+    def step(t, limit):
+        """end of the clean block that starts at t: k tiles, the next cut or `limit`"""
+        end = min(t + k, limit)
+        for c in cutList:
+            if t < c < end:
+                end = c
+                break
+        return end
+
     starts, t = [], 0
     for a, m in runs:
         while t < a:
             starts.append(t)
-            t = min(t + k, a)
+            t = step(t, a)
         end = a + m
         while t < end:
             starts.append(t)
             t = min(t + maxTiles, end)
     while t < nT:
         starts.append(t)
-        t = min(t + k, nT)
+        t = step(t, nT)
     return (starts or [0]), [r for r in runs if r[1] > 1]
 
 

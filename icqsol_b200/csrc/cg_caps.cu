@@ -320,6 +320,36 @@ __global__ void __launch_bounds__(256) k_dense_apply(const DenseDesc* desc, int 
     if (lane == 0) y[g0 + lr] = sum;
 }
 
+// Sharded dense blocks (several ranks): a block whose tile rows all live on ONE rank is
+// extracted, inverted and applied by that rank only; the pieces of w travel in one all-gather
+// per iteration.  GatherDesc: rows [row, row + count) of w come from (or go to) position src of
+// rank `owner`'s send buffer.
+struct GatherDesc {
+    long long row, count, src;
+    int owner, pad;
+};
+
+// own pieces of w -> the send buffer
+__global__ void __launch_bounds__(256) k_w_pack(const GatherDesc* g, int rank, const double* w,
+                                                double* send, const int* skip) {
+    if (skip && *skip) return;
+    const GatherDesc D = g[blockIdx.y];
+    if (D.owner != rank) return;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < D.count; i += (long long)gridDim.x * 256)
+        send[D.src + i] = w[D.row + i];
+}
+
+// the other ranks' pieces, out of the gathered buffers [nranks][slot], into w
+__global__ void __launch_bounds__(256) k_w_unpack(const GatherDesc* g, int rank, long long slot,
+                                                  const double* recv, double* w, const int* skip) {
+    if (skip && *skip) return;
+    const GatherDesc D = g[blockIdx.y];
+    if (D.owner == rank) return;
+    const double* src = recv + (long long)D.owner * slot + D.src;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < D.count; i += (long long)gridDim.x * 256)
+        w[D.row + i] = src[i];
+}
+
 // mixed-precision fields of the state (switch_thr 0: float32 products off)
 __global__ void k_cg_mixed(CgState* s, double switch_thr) {
     s->lowp = 0;
@@ -517,25 +547,99 @@ int cg_solve_caps(icqb_ctx* ctx, uint64_t dA_, int64_t n, int64_t ld, int storag
         for (long long t = std::max<long long>(head, 1); t <= nT - tail && t < nT; ++t) starts.push_back(t);
     }
     if (starts.empty() || starts[0] != 0) starts.insert(starts.begin(), 0);
-    std::vector<DenseDesc> hdesc;
+    // every dense block (more than one tile), in index order
+    struct BlockRange { long long t0, t1; };
+    std::vector<BlockRange> ranges;
     std::vector<int> htile((size_t)nT, -1);
-    long long denseDoubles = 0, denseRows = 0, kMaxTiles = 0;
     for (size_t q = 0; q < starts.size(); ++q) {
         const long long t0 = starts[q], t1 = (q + 1 < starts.size()) ? starts[q + 1] : nT;
         if (t1 - t0 <= 1) continue;      // single tiles use the 128 x 128 inverse blocks
-        DenseDesc D;
-        D.t0 = t0;
-        D.tiles = t1 - t0;
-        D.m = D.tiles * kT;
-        D.valid = std::min<long long>(n, t1 * kT) - t0 * kT;
-        D.off = denseDoubles;
-        D.row0 = denseRows;
-        denseDoubles += D.m * D.m;
-        denseRows += D.valid;
-        kMaxTiles = std::max(kMaxTiles, D.tiles);
-        for (long long t = t0; t < t1; ++t) htile[(size_t)t] = (int)hdesc.size();
-        hdesc.push_back(D);
+        for (long long t = t0; t < t1; ++t) htile[(size_t)t] = (int)ranges.size();
+        ranges.push_back({t0, t1});
     }
+    const int nAll = (int)ranges.size();
+    // Who holds a block?  A block whose tile rows all lie in this rank's rows is OWNED: it is
+    // extracted, inverted and applied here only, and its piece of w is all-gathered.  Blocks
+    // that straddle a boundary between ranks (none when the host layer aligns the partition with
+    // the row blocks, icqRowPartition.sliverBlockPartition(cuts=...)) stay REPLICATED: extracted
+    // by all-reduce, inverted and applied by every rank.  One small all-reduce tells every rank
+    // the owner of every block.
+    LowerLayout L{0, 0, 0, 0, 0, 0, 0};
+    if (storage == 1) {
+        int rcL = lower_layout(ctx, &L);
+        if (rcL != ICQB_OK) return rcL;
+    }
+    const long long fr0 = std::min<long long>(n, (long long)rank * chunk);
+    const long long fr1 = std::min<long long>(n, fr0 + chunk);
+    auto holdsTileRow = [&](long long t) -> bool {
+        if (storage == 1) return L.stripOf(t * kT) >= 0;
+        return t * kT >= fr0 && std::min<long long>(n, (t + 1) * kT) <= fr1;
+    };
+    std::vector<int> owner((size_t)nAll, P == 1 ? 0 : -1);
+    if (P > 1 && nAll > 0) {
+        std::vector<double> vote(2 * (size_t)nAll, 0.0);
+        for (int bq = 0; bq < nAll; ++bq) {
+            bool all = true;
+            for (long long t = ranges[bq].t0; t < ranges[bq].t1 && all; ++t) all = holdsTileRow(t);
+            if (all) {
+                vote[2 * bq] = 1.0;
+                vote[2 * bq + 1] = rank + 1.0;
+            }
+        }
+        int rcV = ensure_work(ctx, 2 * (long long)nAll + 64);
+        if (rcV != ICQB_OK) return rcV;
+        ICQB_CUDA(ctx, cudaMemcpyAsync(ctx->d_work, vote.data(), sizeof(double) * vote.size(),
+                                       cudaMemcpyHostToDevice, st));
+        rcV = comm_allreduce_sum(ctx, ctx->d_work, 2 * (long long)nAll, st);
+        if (rcV != ICQB_OK) return rcV;
+        ICQB_CUDA(ctx, cudaMemcpyAsync(vote.data(), ctx->d_work, sizeof(double) * vote.size(),
+                                       cudaMemcpyDeviceToHost, st));
+        ICQB_CUDA(ctx, cudaStreamSynchronize(st));
+        for (int bq = 0; bq < nAll; ++bq)
+            if (vote[2 * bq] == 1.0) owner[bq] = (int)llround(vote[2 * bq + 1]) - 1;
+    }
+    // local list: the blocks this rank inverts and applies (owned first, then replicated)
+    std::vector<DenseDesc> hdesc;
+    std::vector<GatherDesc> hgather;
+    std::vector<long long> sendLen((size_t)P, 0);
+    long long denseDoubles = 0, denseRows = 0, kMaxTiles = 0, repDoubles = 0, repOff = 0;
+    int nOwn = 0;
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int bq = 0; bq < nAll; ++bq) {
+            const bool mine = (owner[bq] == rank), rep = (owner[bq] < 0);
+            if (pass == 0 && bq < nAll && owner[bq] >= 0) {
+                // gather table: every owned block, whoever owns it
+                GatherDesc G;
+                G.row = ranges[bq].t0 * kT;
+                G.count = std::min<long long>(n, ranges[bq].t1 * kT) - G.row;
+                G.owner = owner[bq];
+                G.pad = 0;
+                G.src = sendLen[(size_t)owner[bq]];
+                sendLen[(size_t)owner[bq]] += G.count;
+                hgather.push_back(G);
+            }
+            if ((pass == 0 && !mine) || (pass == 1 && !rep)) continue;
+            DenseDesc D;
+            D.t0 = ranges[bq].t0;
+            D.tiles = ranges[bq].t1 - ranges[bq].t0;
+            D.m = D.tiles * kT;
+            D.valid = std::min<long long>(n, ranges[bq].t1 * kT) - D.t0 * kT;
+            D.off = denseDoubles;
+            D.row0 = denseRows;
+            denseDoubles += D.m * D.m;
+            denseRows += D.valid;
+            kMaxTiles = std::max(kMaxTiles, D.tiles);
+            hdesc.push_back(D);
+            if (pass == 0) ++nOwn;
+            else repDoubles += D.m * D.m;
+        }
+        if (pass == 0) repOff = denseDoubles;
+    }
+    const bool sharded = (P > 1) && !hgather.empty();
+    long long slot = 0;
+    for (long long v : sendLen) slot = std::max(slot, v);
+    const long long gatherDoubles = sharded ? (long long)(P + 1) * slot : 0;
+    const long long gdescDoubles = ((long long)sizeof(GatherDesc) * std::max<size_t>(hgather.size(), 1) + 7) / 8;
     const int nDense = (int)hdesc.size();
     if (kMaxTiles > 64) return set_error(ctx, ICQB_EARG, "icqb_cg_solve_dev: dense blocks of at most 64 tiles");
     const long long descDoubles = ((long long)sizeof(DenseDesc) * std::max(nDense, 1) + 7) / 8;
@@ -545,7 +649,8 @@ int cg_solve_caps(icqb_ctx* ctx, uint64_t dA_, int64_t n, int64_t ld, int storag
     const long long nfull = chunk * P;
     const long long stateDoubles = (sizeof(CgState) + 7) / 8;
     const long long small = 8 * n + 8 + nfull + 6 * nT + stateDoubles;
-    const long long need = small + nT * kBlockElems + denseDoubles + descDoubles + tileDoubles + 66;
+    const long long need = small + nT * kBlockElems + denseDoubles + descDoubles + tileDoubles + gatherDoubles +
+                           gdescDoubles + 66;
     int rc = ensure_work(ctx, need);
     if (rc != ICQB_OK) return rc;
     CgBuf B;
@@ -571,6 +676,9 @@ int cg_solve_caps(icqb_ctx* ctx, uint64_t dA_, int64_t n, int64_t ld, int storag
     double* dense = wp; wp += denseDoubles;
     DenseDesc* ddesc = reinterpret_cast<DenseDesc*>(wp); wp += descDoubles;
     int* dtile = reinterpret_cast<int*>(wp); wp += tileDoubles;
+    double* wsend = wp; wp += sharded ? slot : 0;
+    double* wrecv = wp; wp += sharded ? (long long)P * slot : 0;
+    GatherDesc* dgather = reinterpret_cast<GatherDesc*>(wp); wp += gdescDoubles;
     B.Minv = blocks;
     B.n = n;
 
@@ -627,6 +735,15 @@ int cg_solve_caps(icqb_ctx* ctx, uint64_t dA_, int64_t n, int64_t ld, int storag
             k_dense_apply<<<(unsigned)((denseRows + 7) / 8), 256, 0, st>>>(ddesc, nDense, denseRows, dense,
                                                                          B.r, B.w, skipFlag);
             ctx->launches += 1;
+        }
+        if (needW && sharded) {
+            // the owners' pieces of w to every rank: pack, all-gather, unpack
+            const dim3 ggrid(4, (unsigned)hgather.size());
+            k_w_pack<<<ggrid, 256, 0, st>>>(dgather, rank, B.w, wsend, skipFlag);
+            int rcg = comm_allgather(ctx, wsend, wrecv, slot, st);
+            if (rcg != ICQB_OK) return rcg;
+            k_w_unpack<<<ggrid, 256, 0, st>>>(dgather, rank, slot, wrecv, B.w, skipFlag);
+            ctx->launches += 2;
         }
         k_cg_close<<<vgrid, vblock, 0, st>>>(mode, kk, replace, b, B, dtile);
         ctx->launches += 1;
@@ -703,9 +820,6 @@ int cg_solve_caps(icqb_ctx* ctx, uint64_t dA_, int64_t n, int64_t ld, int storag
             k_recip<<<128, 256, 0, st>>>(ctx->d_area2, inv_area, n);
             ctx->launches += 1;
         }
-        LowerLayout L{0, 0, 0, 0, 0, 0, 0};
-        if (storage == 1) CG_TRY(lower_layout(ctx, &L));
-
         // 128 x 128 blocks (used outside the caps), as in cg.cu
         if (storage == 1)
             k_cg_blocks_lower<<<vgrid, 256, 0, st>>>(A, L, scale, n, blocks);
@@ -722,18 +836,31 @@ int cg_solve_caps(icqb_ctx* ctx, uint64_t dA_, int64_t n, int64_t ld, int storag
 
         // tables of the dense blocks, then: extract, all-reduce, block Gauss-Jordan, symmetrise
         CG_CUDA(cudaMemcpyAsync(dtile, htile.data(), sizeof(int) * (size_t)nT, cudaMemcpyHostToDevice, st));
-        if (nDense > 0) {
-            CG_CUDA(cudaMemcpyAsync(ddesc, hdesc.data(), sizeof(DenseDesc) * (size_t)nDense,
+        if (sharded)
+            CG_CUDA(cudaMemcpyAsync(dgather, hgather.data(), sizeof(GatherDesc) * hgather.size(),
                                     cudaMemcpyHostToDevice, st));
-            CG_CUDA(cudaMemsetAsync(dense, 0, sizeof(double) * (size_t)denseDoubles, st));
+        if (nDense > 0 || repDoubles > 0) {
+            if (nDense > 0)
+                CG_CUDA(cudaMemcpyAsync(ddesc, hdesc.data(), sizeof(DenseDesc) * (size_t)nDense,
+                                        cudaMemcpyHostToDevice, st));
+            if (denseDoubles > 0)
+                CG_CUDA(cudaMemsetAsync(dense, 0, sizeof(double) * (size_t)denseDoubles, st));
+            const dim3 tgrid((unsigned)std::max<long long>(kMaxTiles, 1), (unsigned)std::max<long long>(kMaxTiles, 1),
+                             (unsigned)std::max(nDense, 1));
+            if (nDense > 0) {
+                if (storage == 1)
+                    k_dense_extract_lower<<<tgrid, 256, 0, st>>>(A, L, scale, n, ddesc, dense);
+                else
+                    k_dense_extract_full<<<tgrid, 256, 0, st>>>(A, ld, mv.r0, mv.r1, scale, n, ddesc, dense);
+                ctx->launches += 1;
+                CG_CUDA(cudaGetLastError());
+            }
+            // the replicated blocks (behind the owned ones in the buffer) are summed over the
+            // ranks: every rank fills what it stores; same count on every rank
+            if (repDoubles > 0) CG_TRY(comm_allreduce_sum(ctx, dense + repOff, repDoubles, st));
+        }
+        if (nDense > 0) {
             const dim3 tgrid((unsigned)kMaxTiles, (unsigned)kMaxTiles, (unsigned)nDense);
-            if (storage == 1)
-                k_dense_extract_lower<<<tgrid, 256, 0, st>>>(A, L, scale, n, ddesc, dense);
-            else
-                k_dense_extract_full<<<tgrid, 256, 0, st>>>(A, ld, mv.r0, mv.r1, scale, n, ddesc, dense);
-            ctx->launches += 1;
-            CG_CUDA(cudaGetLastError());
-            CG_TRY(comm_allreduce_sum(ctx, dense, denseDoubles, st));
             CG_CUDA(cudaFuncSetAttribute(k_tile_invert, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          kInvSmem));
             for (long long K = 0; K < kMaxTiles; ++K) {

@@ -902,3 +902,36 @@ def test_emulated_lu_multi_rank(emu, oracle_mod, nranks):
         assert numpy.abs(x - lu).max() <= 1e-9 * numpy.abs(lu).max()
     for o in out:
         o[2].close()
+
+
+@pytest.mark.parametrize('nranks,peer', [(2, False), (3, False), (2, True)])
+def test_emulated_sharded_preconditioner_blocks(emu, oracle_mod, nranks, peer):
+    """Diagonal blocks cut at the ranks' row-block boundaries (icqRowPartition.rankCuts): every
+    block lives on one rank, which extracts, inverts and applies it alone; the pieces of w are
+    all-gathered.  Same solution on every rank, the oracle's system solved, the iteration count
+    of the numpy model of the same blocks."""
+    from icqsol_b200.bem import icqRowPartition as rp
+    nt, nph = 28, 15                                     # 784 triangles, 7 tile rows
+    n = 2 * nt * (nph - 1)
+    nT = (n + 127) // 128
+    cuts = rp.rankCuts(n, nranks)
+    starts, _ = rp.sliverBlockPartition(None, numpy.zeros((n, 3), int), blockTiles=2,
+                                        flagged=numpy.zeros(nT, bool), cuts=cuts)
+    # (every multi-tile block inside one rank's rows)
+    rows = rp.foldedTileRows(n, nranks)
+    for a, b in zip(starts, starts[1:] + [nT]):
+        assert len({g for g, (a0, a1, b0, b1) in enumerate(rows) for t in range(a, b)
+                    if a0 <= t < a1 or b0 <= t < b1}) == 1
+    assert any(b - a > 1 for a, b in zip(starts, starts[1:] + [nT]))
+    out = _run_ranks(emu, nranks, nt, nph, 1, 2, None, peer, starts)
+    c = out[0][-1]
+    ref = oracle_mod.green_matrix(c.xyz, c.tri, 5, threads=True)
+    a2 = oracle_mod.area2(c.xyz, c.tri)
+    x0, iters0, _, b, _ = out[0]
+    for x, iters, rinf, _, _ in out:
+        assert (x == x0).all() and iters == iters0
+        assert rinf <= 5e-13 * numpy.abs(b).max()
+    assert numpy.abs(b - ref.dot(x0)).max() <= 1e-12 * numpy.abs(b).max()
+    assert abs(iters0 - model_iterations(ref, a2, b, [128 * s for s in starts])) <= 1
+    for o in out:
+        o[-1].close()

@@ -33,4 +33,9 @@ for w in auto "$@"; do
   done
 done
 unset ICQB_PEER_EXCHANGE
+# the direct solve (csrc/lu.cu) over the ranks
+for w in c2 bolt; do
+  timeout 300 bash -c "$(declare -f run); n=$n; run 29734 tools/bench_lu.py $w" > $out/${tag}_lu_n${n}_$w.json 2> $out/${tag}_lu_n${n}_$w.err
+  echo "LU $w rc=$?"; grep '^{' $out/${tag}_lu_n${n}_$w.json; tail -n 2 $out/${tag}_lu_n${n}_$w.err
+done
 exit 0
