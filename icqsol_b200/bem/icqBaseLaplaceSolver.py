@@ -144,11 +144,12 @@ class BaseLaplaceSolver(BaseSolver):
             # one dense block per run of tiles that hold slivers, wherever it lies in the list
             # (on a UV sphere: the head and tail caps of sliverCapTiles); the other blocks end
             # where the ranks' row blocks do, so that each of them lives on one rank
-            self.capTiles = rowPartition.sliverCapTiles(self._xyz, self._tri)
+            flagged = rowPartition.sliverTiles(self._xyz, self._tri)
+            self.capTiles = rowPartition.sliverCapTiles(self._xyz, self._tri, flagged=flagged)
             cuts = rowPartition.rankCuts(self.numTriangles, self.numRanks) \
                 if (storage == 'lower' and self.numRanks > 1) else None
             starts, self.denseRuns = rowPartition.sliverBlockPartition(
-                self._xyz, self._tri, blockTiles=int(blockTiles), cuts=cuts)
+                self._xyz, self._tri, blockTiles=int(blockTiles), cuts=cuts, flagged=flagged)
             starts = numpy.ascontiguousarray(starts, numpy.int64)
             self.ctx.check(self.lib.icqb_cg_set_block_partition(
                 self.ctx.handle, starts.ctypes.data_as(_lib.c_int64_p), len(starts)))

@@ -148,28 +148,22 @@ def lowerTilesToRows(tiles, blocks, n):
     return out
 
 
-def sliverCapTiles(xyz, tri, threshold=30., maxTiles=32):
-    """(head_tiles, tail_tiles) for the experimental 'block+caps' preconditioner: how many
-    leading (trailing) 128-triangle tiles to merge into one dense block so that every sliver
-    -- a triangle whose aspect Lmax^2 / |db x dc| exceeds ``threshold`` -- among the first
-    (last) ``maxTiles`` tiles is inside it.  Neighbouring slivers make diag(area) G
-    indefinite; on the UV spheres they are the fan at each pole and
-    every other triangle of the next band(s), i.e. they sit at the two ends of the triangle
-    list (aspect 51 at n_theta = 318, 26 for the rest of the first band, below 30 from the
-    second band on), and the block has to span the whole band to restore convergence.
-    Slivers in the middle of the list are not covered."""
-    xyz = numpy.asarray(xyz, numpy.float64)
-    tri = numpy.asarray(tri, numpy.int64)
-    n = tri.shape[0]
-    if n == 0:
+def sliverCapTiles(xyz, tri, threshold=30., maxTiles=32, flagged=None):
+    """(head_tiles, tail_tiles): how many leading (trailing) 128-triangle tiles hold slivers --
+    triangles whose aspect Lmax^2 / |db x dc| exceeds ``threshold`` -- among the first (last)
+    ``maxTiles`` tiles.  Neighbouring slivers make diag(area) G indefinite (DESIGN.md section
+    4.6); on the UV spheres they are the fan at each pole and every other triangle of the next
+    band(s), i.e. they sit at the two ends of the triangle list (aspect 51 at n_theta = 318, 26
+    for the rest of the first band, below 30 from the second band on), and a dense block has to
+    span the whole band to restore convergence.  Informational: the preconditioner's blocks
+    come from sliverBlockPartition, which also covers slivers in the middle of the list.
+    ``flagged``: the result of sliverTiles, if already at hand."""
+    if flagged is None:
+        flagged = sliverTiles(xyz, tri, threshold)
+    flagged = numpy.asarray(flagged, bool)
+    nT = flagged.shape[0]
+    if nT == 0:
         return 0, 0
-    a, b, c = xyz[tri[:, 0]], xyz[tri[:, 1]], xyz[tri[:, 2]]
-    e2 = numpy.maximum.reduce([((b - a) ** 2).sum(1), ((c - b) ** 2).sum(1), ((a - c) ** 2).sum(1)])
-    area2 = numpy.sqrt((numpy.cross(b - a, c - a) ** 2).sum(1))
-    sliver = e2 > threshold * area2
-    nT = (n + TILE - 1) // TILE
-    flagged = numpy.zeros(nT, bool)
-    numpy.logical_or.at(flagged, numpy.arange(n) // TILE, sliver)
     w = min(int(maxTiles), nT)
     lead = numpy.nonzero(flagged[:w])[0]
     head = int(lead[-1]) + 1 if lead.size else 0
@@ -185,14 +179,22 @@ def sliverTiles(xyz, tri, threshold=30.):
     xyz = numpy.asarray(xyz, numpy.float64)
     tri = numpy.asarray(tri, numpy.int64)
     n = tri.shape[0]
-    flagged = numpy.zeros((n + TILE - 1) // TILE, bool)
+    nT = (n + TILE - 1) // TILE
     if n == 0:
-        return flagged
-    a, b, c = xyz[tri[:, 0]], xyz[tri[:, 1]], xyz[tri[:, 2]]
-    e2 = numpy.maximum.reduce([((b - a) ** 2).sum(1), ((c - b) ** 2).sum(1), ((a - c) ** 2).sum(1)])
-    area2 = numpy.sqrt((numpy.cross(b - a, c - a) ** 2).sum(1))
-    numpy.logical_or.at(flagged, numpy.arange(n) // TILE, e2 > threshold * area2)
-    return flagged
+        return numpy.zeros(nT, bool)
+    # component arrays (contiguous), no numpy.cross: this runs inside every solver constructor
+    x, y, z = (numpy.ascontiguousarray(xyz[:, k]) for k in range(3))
+    i0, i1, i2 = (numpy.ascontiguousarray(tri[:, k]) for k in range(3))
+    bx, by, bz = x[i1] - x[i0], y[i1] - y[i0], z[i1] - z[i0]
+    cx, cy, cz = x[i2] - x[i0], y[i2] - y[i0], z[i2] - z[i0]
+    e2 = numpy.maximum(bx * bx + by * by + bz * bz, cx * cx + cy * cy + cz * cz)
+    dx, dy, dz = cx - bx, cy - by, cz - bz
+    e2 = numpy.maximum(e2, dx * dx + dy * dy + dz * dz)
+    nx, ny, nz = by * cz - bz * cy, bz * cx - bx * cz, bx * cy - by * cx
+    sliver = e2 * e2 > (threshold * threshold) * (nx * nx + ny * ny + nz * nz)
+    pad = numpy.zeros(nT * TILE, bool)
+    pad[:n] = sliver
+    return pad.reshape(nT, TILE).any(axis=1)
 
 
 def rankCuts(n, nranks):
