@@ -77,6 +77,16 @@ def lib(threads=False):
     return _libs[name]
 
 
+def tri_rule(order):
+    """[(xi, eta, w)] of the triangle rule of ``order`` (bem/icqQuadrature.cpp:20-144)."""
+    L = lib()
+    L.icqo_tri_rule.restype = ctypes.c_int
+    L.icqo_tri_rule.argtypes = [ctypes.c_int] + [ctypes.POINTER(c_dp)] * 3
+    xi, eta, w = c_dp(), c_dp(), c_dp()
+    n = L.icqo_tri_rule(int(order), ctypes.byref(xi), ctypes.byref(eta), ctypes.byref(w))
+    return [(xi[k], eta[k], w[k]) for k in range(n)]
+
+
 def have_reference():
     return os.path.exists(os.path.join(_REFDIR, 'libicqref.so'))
 

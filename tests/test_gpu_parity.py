@@ -213,6 +213,38 @@ def test_k_row_sums_closed_surface(ctx):
     assert numpy.abs(rs - 0.5).max() < 0.02
 
 
+def test_k_against_analytic_solid_angles(ctx, oracle_mod):
+    """The device K against an anchor that is not this repository's code: the double-layer
+    potential of a flat triangle is its solid angle, K[i,j] = sum_k w_k Omega_j(o_k) / (4 pi) up to
+    the source-side quadrature error (tests/test_oracle.py pins the oracle the same way):
+    well separated pairs to 5e-12 of the largest such entry, in both kernels (direct and
+    far-field split), K and the transposed part of the lower storage."""
+    from test_oracle import _solid_angle
+    from icqsol_b200.mesh.generators import uvSphere
+    xyz, tri = uvSphere(1.0, 32, 16)
+    n = tri.shape[0]
+    nodes = numpy.array(oracle_mod.tri_rule(8))
+    a, b, c = xyz[tri[:, 0]], xyz[tri[:, 1]], xyz[tri[:, 2]]
+    obs = a[:, None, :] + nodes[None, :, 0:1] * (b - a)[:, None, :] + nodes[None, :, 1:2] * (c - a)[:, None, :]
+    exact = numpy.zeros((n, n))
+    for j in range(n):
+        om = _solid_angle(obs.reshape(-1, 3), a[j], b[j], c[j]).reshape(n, 16)
+        exact[:, j] = (om * nodes[None, :, 2]).sum(1) / (4. * numpy.pi)
+    cen = (a + b + c) / 3.
+    dist = numpy.sqrt(((cen[:, None, :] - cen[None, :, :]) ** 2).sum(-1))
+    size = numpy.sqrt(numpy.maximum.reduce([((b - a) ** 2).sum(1), ((c - b) ** 2).sum(1), ((a - c) ** 2).sum(1)]))
+    far = dist > 3. * (size[:, None] + size[None, :])
+    assert far.sum() > 0.4 * n * n
+    for variant in (0, 1):
+        ctx.check(ctx.lib.icqb_set_assembly_variant(ctx.handle, variant))
+        g, k = assemble(ctx, xyz, tri, 5, with_k=True)
+        assert numpy.abs(k[far] - exact[far]).max() < 5e-12 * numpy.abs(exact[far]).max()
+        # closed outward surface: every row of the exact entries adds up to 1/2; the computed ones
+        # miss it by the quadrature error of the touching pairs only
+        assert numpy.abs(k.sum(1) - 0.5).max() < 0.05
+    ctx.check(ctx.lib.icqb_set_assembly_variant(ctx.handle, 0))
+
+
 def test_k_row_block_and_sampled_oracle(ctx, golden, oracle_mod):
     xyz, tri = golden.mesh('boltFine')
     g, k = assemble(ctx, xyz, tri, 5, with_k=True, rows=(1000, 1300))

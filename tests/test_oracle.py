@@ -160,3 +160,47 @@ def test_k_definition_properties(oracle_mod):
     assert numpy.abs(k.sum(axis=1) - 0.5).max() < 0.05
     kin = oracle_mod.k_block(xyz, tri[:, ::-1].copy(), 0, 16, 0, n)
     assert numpy.abs(kin + k).max() < 1e-13   # reversed vertex order: different quadrature-node order
+
+
+def _solid_angle(x, a, b, c):
+    """Signed solid angle of triangle (a, b, c) seen from x (van Oosterom & Strackee 1983),
+    positive when x lies on the side the normal (b - a) x (c - a) points away from."""
+    ra, rb, rc = a - x, b - x, c - x
+    la, lb, lc = (numpy.sqrt((v * v).sum(-1)) for v in (ra, rb, rc))
+    num = (ra * numpy.cross(rb, rc)).sum(-1)
+    den = la * lb * lc + (ra * rb).sum(-1) * lc + (ra * rc).sum(-1) * lb + (rb * rc).sum(-1) * la
+    return 2. * numpy.arctan2(num, den)
+
+
+def test_k_against_the_analytic_double_layer_of_a_flat_triangle(oracle_mod):
+    """An anchor for K that does not come from the code under test (the reference snapshot has no
+    K): the double-layer potential of a flat triangle is its solid angle,
+    integral over T_j of n_j.(x - y)/|x - y|^3 dS_y = -Omega_j(x) (signed as in _solid_angle), so
+        K[i,j] = sum_k w_k Omega_j(o_k) / (4 pi)     up to the source-side quadrature error,
+    o_k the observer triangle's quadrature points.  Measured on this mesh: pairs with
+    |c_i - c_j| > 3 (L_i + L_j) (45 % of them) agree to 7e-13 of the largest such entry, > 2 (L_i +
+    L_j) to 5e-11, > (L_i + L_j) (93 %) to 7e-8; touching triangles do not (a 16-point rule on a
+    nearly singular kernel -- the same is true of the reference's G).  Checks the sign, the
+    normal's orientation, the 1/(4 pi), the area factor and the observer averaging."""
+    from icqsol_b200.mesh.generators import uvSphere
+    xyz, tri = uvSphere(1.0, 32, 16)
+    n = tri.shape[0]
+    k = oracle_mod.k_block(xyz, tri, 0, n, 0, n)
+    nodes = numpy.array(oracle_mod.tri_rule(8))            # [16, 3]: xi, eta, w
+    a, b, c = xyz[tri[:, 0]], xyz[tri[:, 1]], xyz[tri[:, 2]]
+    obs = a[:, None, :] + nodes[None, :, 0:1] * (b - a)[:, None, :] + nodes[None, :, 1:2] * (c - a)[:, None, :]
+    exact = numpy.zeros((n, n))
+    for j in range(n):
+        om = _solid_angle(obs.reshape(-1, 3), a[j], b[j], c[j]).reshape(n, 16)
+        exact[:, j] = (om * nodes[None, :, 2]).sum(1) / (4. * numpy.pi)
+    numpy.fill_diagonal(exact, 0.)
+    cen = (a + b + c) / 3.
+    dist = numpy.sqrt(((cen[:, None, :] - cen[None, :, :]) ** 2).sum(-1))
+    size = numpy.sqrt(numpy.maximum.reduce([((b - a) ** 2).sum(1), ((c - b) ** 2).sum(1), ((a - c) ** 2).sum(1)]))
+    for kappa, share, tol in ((3., 0.4, 5e-12), (2., 0.7, 5e-10), (1., 0.9, 1e-6)):
+        far = dist > kappa * (size[:, None] + size[None, :])
+        assert far.sum() > share * n * n
+        assert numpy.abs(k[far] - exact[far]).max() < tol * numpy.abs(exact[far]).max()
+    # closed outward surface: the exact entries of a row add up to the interior-limit value 1/2
+    # of the double-layer potential minus the (flat, vanishing) self term
+    assert numpy.abs(exact.sum(1) - 0.5).max() < 1e-12
