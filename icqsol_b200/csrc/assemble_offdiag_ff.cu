@@ -152,14 +152,16 @@ __device__ __forceinline__ PairSums pair_fast(const Obs& O, const double* __rest
         const double e0 = fma(njz, O.az - bj[6], fma(njy, O.ay - bj[5], njx * (O.ax - bj[4])));
         const double nb = fma(njz, O.b2z, fma(njy, O.b2y, njx * O.b2x));
         const double nc = fma(njz, O.c2z, fma(njy, O.c2y, njx * O.c2x));
+        double sk[4] = {0.0, 0.0, 0.0, 0.0};   // four chains instead of sixteen dependent DFMAs
 #define ICQB_FF_K(K, XI, ETA, W)                                   \
     {                                                              \
         const double t = fma(XI, nb, ETA * nc);                    \
         const double nd = fma(-0.5, t, e0);                        \
-        S.k = fma(W * nd, r3row[K], S.k);                          \
+        sk[K & 3] = fma(W * nd, r3row[K], sk[K & 3]);              \
     }
         ICQB_TRI8(ICQB_FF_K)
 #undef ICQB_FF_K
+        S.k = (sk[0] + sk[1]) + (sk[2] + sk[3]);
     }
     return S;
 }

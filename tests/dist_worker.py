@@ -33,6 +33,8 @@ def main():
                                         (64, 30, 'full'), (7, 4, 'full'), (7, 4, 'lower'))
              for kind in kinds]
     refs = {}     # oracle matrices per mesh: built once, used by every storage / solver kind
+    if os.environ.get('ICQB_WORKER_ONLY_FULL') == '1':
+        cases = []
     for nt, npz, storage, kind in cases:
         xyz, tri = uvSphere(1.0, nt, npz)
         n = tri.shape[0]
@@ -93,6 +95,14 @@ def main():
     if kbolt > 0:
         m = numpy.load(os.path.join(ROOT, 'tests', 'golden', 'meshes.npz'))
         full.append(('bolt k={0}'.format(kbolt), subdivide(m['boltFine_xyz'], m['boltFine_tri'], kbolt)))
+    # ICQB_WORKER_SPHERES="318x159,448x224": also the UV spheres of the C3 size (100,488
+    # triangles) and of config C5 (199,808; eight GPUs) -- the meshes whose pole slivers make
+    # diag(A) G indefinite
+    for spec in filter(None, os.environ.get('ICQB_WORKER_SPHERES', '').split(',')):
+        nth, nph = (int(v) for v in spec.split('x'))
+        full.append(('sphere {0}x{1}'.format(nth, nph), uvSphere(1.0, nth, nph)))
+    if os.environ.get('ICQB_WORKER_ONLY_FULL') == '1':
+        full = full[2:]
     for name, (xyz, tri) in full:
         n = tri.shape[0]
         print('rank', rank, 'full-size case', name, n, flush=True)

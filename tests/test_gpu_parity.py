@@ -734,6 +734,38 @@ def test_config_c3_refined_bolt(golden, oracle_mod):
     _sampled_checks(solver, xyz, tri, oracle_mod, [0, 4701, n - 1], rsp, v)
 
 
+@pytest.mark.parametrize('mesh', ['bolt_k6', 'sphere_318x159'])
+def test_config_c3_full_size_on_one_gpu(golden, oracle_mod, mesh):
+    """Config C3 at FULL size on one B200 (lower storage: 28.6 / 40.4 GB): the reference's
+    testBoltFine.vtk with every triangle cut into 36 (84,600 triangles, bench.py's multi-GPU
+    workload) and the UV sphere of the same size class (100,488 triangles) whose pole slivers
+    make diag(A) G indefinite -- the CG with the dense sliver blocks converges,
+    the response satisfies the oracle's rows of G sigma = -v to 1e-12 max|v|, sampled columns of
+    the device matrix equal the oracle's to 1e-12."""
+    import torch
+    from icqsol_b200.mesh.generators import subdivide, uvSphere
+    from icqsol_b200.mesh.polydata import PolyData
+    from icqsol_b200.bem.icqLaplaceSolver import LaplaceSolver
+    if torch.cuda.get_device_properties(0).total_memory < 60e9:
+        pytest.skip('needs 60 GB of HBM')
+    if mesh == 'bolt_k6':
+        xyz, tri = subdivide(*golden.mesh('boltFine'), 6)
+        assert tri.shape[0] == 84600
+    else:
+        xyz, tri = uvSphere(1.0, 318, 159)
+        assert tri.shape[0] == 100488
+    n = tri.shape[0]
+    solver = LaplaceSolver(PolyData.from_arrays(xyz, tri), float('inf'), 5, directFallback=False)
+    solver.setSourceFromExpression('1./sqrt(x**2 + (y-2.)**2 + (z-4.)**2)')
+    v = solver.getSourceArray(solver.getSourceArrayIndex())
+    rsp = solver.computeResponseField()
+    assert solver.lastSolveInfo['method'] == 'cg' and solver.lastSolveInfo['converged']
+    assert solver.lastSolveInfo['iterations'] < 400
+    _sampled_checks(solver, xyz, tri, oracle_mod, [0, n // 2 + 77, n - 1], rsp, v)
+    del solver
+    torch.cuda.empty_cache()
+
+
 def test_config_c4_hollow_sphere_poisson(oracle_mod):
     """Config C4's geometry (tests/testHollowSphere.py: outer shell plus an inward-oriented
     inner shell of doubled resolution), PoissonSolver v = G.charge against the oracle."""
