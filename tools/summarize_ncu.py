@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Turn the ncu outputs of tools/gpu_round.sh into the text summaries kept under profiles/.
+"""Turn the ncu outputs of the GPU visits (tools/gpu_visits/) into the text summaries kept under profiles/.
 
     python tools/summarize_ncu.py launches gpurun_out/<tag>_launches.csv
     python tools/summarize_ncu.py kernels  gpurun_out/<tag>_solve.ncu-rep
