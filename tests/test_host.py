@@ -349,7 +349,8 @@ def test_sliver_block_partition_general_position():
 def _run_emulated(args, timeout=900):
     """tools/emu/run_emulated.py: a Python entry point of the repository against the emulated
     library (the build container has no GPU)."""
-    env = dict(os.environ, ICQB_EMU_SMS='1')     # sizes the emulated grids (and the DFMA peak loop)
+    # ICQB_EMU_SMS sizes the emulated grids (and the DFMA peak loop); smoke() at emulation size
+    env = dict(os.environ, ICQB_EMU_SMS='1', ICQB_SMOKE_SPHERE='16x11')
     out = subprocess.run([sys.executable, os.path.join(ROOT, 'tools', 'emu', 'run_emulated.py')] + args,
                          capture_output=True, text=True, timeout=timeout, cwd=ROOT, env=env)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-3000:]
