@@ -564,7 +564,7 @@ def run_b200(args):
     # the resident buffers go first: on one GPU the 84,600-triangle matrices take 86 GB, and the
     # solver class holds its own
     matrix_bytes = 3.0 * 8.0 * stored if lower else 2.0 * 8.0 * stored
-    tight = 2.0 * matrix_bytes > 0.8 * torch.cuda.get_device_properties(dev).total_memory
+    tight = 2.0 * matrix_bytes > 0.8 * torch.cuda.mem_get_info(dev)[1]
     del gbuf, kbuf, kubuf
     if tight:
         torch.cuda.empty_cache()
@@ -730,9 +730,9 @@ def main():
                          "(DESIGN.md 4.6); 'block' = inverse 128x128 blocks; 'diagonal' = 1/diag")
     ap.add_argument('--block-tiles', type=int, default=DEFAULT_BLOCK_TILES,
                     help='with block+caps: 128-triangle tiles per diagonal block')
-    ap.add_argument('--assembly-variant', type=int, default=1, choices=[0, 1],
+    ap.add_argument('--assembly-variant', type=int, default=1, choices=[0, 1, 2],
                     help='arithmetic of the off-diagonal kernel (include/icqb.h, '
-                         'icqb_set_assembly_variant): 0 direct, 1 far-field split')
+                         'icqb_set_assembly_variant): 0 direct, 1 far-field split, 2 = 1 software-pipelined')
     ap.add_argument('--mixed-switch', type=float, default=0.,
                     help='with block+caps and lower storage: relative residual below '
                          'which the CG products stream a float32 copy of the matrix (1e-6); 0 = off')

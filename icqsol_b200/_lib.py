@@ -29,6 +29,7 @@ SIGNATURES = [
     ('icqb_stream', c_uint64, [c_void_p]),
     ('icqb_set_stream', c_int, [c_void_p, c_uint64]),
     ('icqb_synchronize', c_int, [c_void_p]),
+    ('icqb_release_cached_memory', c_int, [c_int]),
     ('icqb_set_mesh', c_int, [c_void_p, c_double_p, c_int64, c_int64_p, c_int64]),
     ('icqb_num_triangles', c_int64, [c_void_p]),
     ('icqb_set_rows', c_int, [c_void_p, c_int64, c_int64]),

@@ -81,7 +81,8 @@ class BaseLaplaceSolver(BaseSolver):
                        it an unconverged solve raises RuntimeError
         @param assemblyVariant arithmetic of the off-diagonal kernel (include/icqb.h,
                        icqb_set_assembly_variant): 0 = direct (k_offdiag), 1 = far-field split
-                       (k_offdiag_ff, the default: 6-8 % faster, entries within 5e-15 of 0)
+                       (k_offdiag_ff, the default: 6-8 % faster, entries within 5e-15 of 0),
+                       2 = 1 with the source-point set-up software-pipelined (same arithmetic)
         """
         # wall-clock marks of the host-side phases (milliseconds since construction began), for
         # the end-to-end breakdown of bench.py: hostTimings['constructor'] / ['solve']
@@ -162,6 +163,7 @@ class BaseLaplaceSolver(BaseSolver):
         self.ctx.check(self.lib.icqb_set_mesh(
             self.ctx.handle, self._xyz.ctypes.data_as(_lib.c_double_p), self._xyz.shape[0],
             self._tri.ctypes.data_as(_lib.c_int64_p), n))
+        mark('mesh upload, k_prepare')
         if storage == 'lower':
             self.rowBlocks = rowPartition.foldedBlocks(n, self.rank, self.numRanks)
             self.ctx.check(self.lib.icqb_set_row_blocks(self.ctx.handle, *self.rowBlocks))
@@ -172,7 +174,7 @@ class BaseLaplaceSolver(BaseSolver):
         self.rowBegin, self.rowEnd = self.rowBlocks[0], self.rowBlocks[1]
         self.numLocalRows = (self.rowBlocks[1] - self.rowBlocks[0]) + \
             (self.rowBlocks[3] - self.rowBlocks[2])
-        mark('mesh upload, k_prepare')
+        mark('row blocks')
 
         self.ld = leadingDimension(n)
         dev = torch.device('cuda', self.device)

@@ -221,10 +221,11 @@ int launch_offdiag_lower(icqb_ctx* ctx, double* dG, double* dK, double* dKu) {
     if (st != ICQB_OK) return st;
     const long long nLocal = P.L.nLocal();
     if (nLocal == 0) return ICQB_OK;
-    const long long lastRow = (P.L.q1 > P.L.q0) ? P.L.q1 : P.L.r1;
-    const long long nSrcTiles = (lastRow + kTileSrc - 1) / kTileSrc;   // J <= I for every local I
-    if (nLocal > 65535) return set_error(ctx, ICQB_EARG, "too many observer tiles for one launch");
-    dim3 grid((unsigned)nSrcTiles, (unsigned)nLocal);
+    // one CTA per stored tile (the 2-D grid of round 1 launched as many CTAs again above the
+    // diagonal, only to exit)
+    const long long nStored = P.L.numTiles();
+    if (nStored > 0x7fffffffLL) return set_error(ctx, ICQB_EARG, "too many tiles for one launch");
+    dim3 grid((unsigned)nStored);
     if (ctx->offdiag_variant != 0) return launch_offdiag_ff(ctx, P, grid, dK != nullptr);
     cudaEventRecord(ctx->ev0, ctx->stream);
     if (dK)

@@ -100,10 +100,25 @@ constexpr int kFfSrcDoubles = kSub * kQpStride;      // 1536
 constexpr int kFfBndDoubles = kSub * kBndStride;     // 256
 constexpr int kFfNrmDoubles = kSub * 4;              // 128
 constexpr int kFfStageDoubles = kFfSrcDoubles + kFfBndDoubles + kFfNrmDoubles;
-constexpr int kFfSmemBytes = kFfSub * kFfStageDoubles * 8 + 64;   // 61,504 B
+// Row-coalesced stores: a lane owns a ROW of the tile, so storing each entry as it is produced
+// writes 8 bytes at a 1 KB stride -- partial sectors that the L2 has to read-fill and write
+// twice (ncu, round 1: 6.41 GB of DRAM traffic for 4.82 GB of matrices).  Instead every warp
+// parks the entries of kStCols consecutive source triangles in its own shared-memory patch
+// ([matrix][32 rows][kStCols + 1]) and then writes, per matrix, 32 row segments of
+// kStCols * 8 = 64 contiguous bytes (two complete sectors each).
+constexpr int kStCols = 8;
+constexpr int kStPitch = kStCols + 1;
+constexpr int kStWarpDoubles = 3 * 32 * kStPitch;                  // G, K, Ku
+constexpr int kFfBarBytes = 64;
+constexpr int kFfSmemBytes = kFfSub * kFfStageDoubles * 8 + kFfBarBytes + (kTileObs / 32) * kStWarpDoubles * 8;   // 89,216 B
 
-// well separated pair: affine observer points, origin at the observer's vertex a
-template <bool WITH_K>
+// well separated pair: affine observer points, origin at the observer's vertex a.
+// PIPELINED: the per-source-point work of point i1 + 1 (three shared-memory loads, then the short
+// dependent chains that form A, B, C and n_i . s') is issued inside the evaluation block of point
+// i1, where the scheduler can slot it between the sixteen independent evaluations -- with two
+// warps per scheduler (254 registers) nothing else hides that latency at the head of every
+// iteration.
+template <bool WITH_K, bool PIPELINED>
 __device__ __forceinline__ PairSums pair_fast(const Obs& O, const double* __restrict__ pj,
                                               const double* __restrict__ nj,
                                               const double* __restrict__ bj) {
@@ -113,14 +128,28 @@ __device__ __forceinline__ PairSums pair_fast(const Obs& O, const double* __rest
 #pragma unroll
         for (int k = 0; k < kNq; ++k) r3row[k] = 0.0;
     }
-#pragma unroll 1
-    for (int i1 = 0; i1 < kNq; ++i1) {
+    double nA = 0.0, nB = 0.0, nC = 0.0, nNd = 0.0;
+    auto point = [&](int i1, double& A, double& B, double& C, double& nd) {
         const double sx = pj[3 * i1 + 0] - O.ax;
         const double sy = pj[3 * i1 + 1] - O.ay;
         const double sz = pj[3 * i1 + 2] - O.az;
-        const double A = fma(sz, sz, fma(sy, sy, sx * sx));
-        const double B = fma(sz, O.b2z, fma(sy, O.b2y, sx * O.b2x));
-        const double C = fma(sz, O.c2z, fma(sy, O.c2y, sx * O.c2x));
+        A = fma(sz, sz, fma(sy, sy, sx * sx));
+        B = fma(sz, O.b2z, fma(sy, O.b2y, sx * O.b2x));
+        C = fma(sz, O.c2z, fma(sy, O.c2y, sx * O.c2x));
+        // mirrored entry K[j,i]: n_i . (y - a_i) = n_i . s'
+        if (WITH_K) nd = fma(O.nz, sz, fma(O.ny, sy, O.nx * sx));
+    };
+    if (PIPELINED) point(0, nA, nB, nC, nNd);
+#pragma unroll 1
+    for (int i1 = 0; i1 < kNq; ++i1) {
+        double A, B, C, nd = 0.0;
+        if (PIPELINED) {
+            A = nA, B = nB, C = nC, nd = nNd;
+            // (the last iteration re-forms point 15: one wasted set-up in sixteen, no branch)
+            point(i1 + 1 < kNq ? i1 + 1 : kNq - 1, nA, nB, nC, nNd);
+        } else {
+            point(i1, A, B, C, nd);
+        }
         const double w1 = c_triNodes[kTri8 + i1].w;
         double in[4] = {0.0, 0.0, 0.0, 0.0};
         double c3[2] = {0.0, 0.0};
@@ -140,11 +169,7 @@ __device__ __forceinline__ PairSums pair_fast(const Obs& O, const double* __rest
         const double in0 = in[0], in1 = in[1], in2 = in[2], in3 = in[3];
         const double c30 = c3[0], c31 = c3[1];
         S.g = fma(w1, (in0 + in1) + (in2 + in3), S.g);
-        if (WITH_K) {
-            // mirrored entry K[j,i]: n_i . (y - a_i) = n_i . s'
-            const double nd = fma(O.nz, sz, fma(O.ny, sy, O.nx * sx));
-            S.km = fma(w1 * nd, c30 + c31, S.km);
-        }
+        if (WITH_K) S.km = fma(w1 * nd, c30 + c31, S.km);
     }
     if (WITH_K) {
         // K[i,j]: n_j . (o_k - a_j) = n_j.(a_i - a_j) - (xi_k n_j.b2 + eta_k n_j.c2) / 2
@@ -234,11 +259,12 @@ __device__ __forceinline__ PairSums pair_exact(const Obs& O, const double* __res
     return S;
 }
 
-template <bool WITH_K>
+template <bool WITH_K, bool PIPELINED>
 __global__ void __launch_bounds__(kTileObs) k_offdiag_ff(const OffDiagParams P) {
     // [kFfSub] x { quadrature points 32 x 48 | bounds 32 x 8 | normals 32 x 4 }, then the barriers
     extern __shared__ __align__(128) double s_tile[];
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_tile + kFfSub * kFfStageDoubles);
+    double* s_park = s_tile + kFfSub * kFfStageDoubles + kFfBarBytes / 8 + (threadIdx.x >> 5) * kStWarpDoubles;
 
     const int tid = threadIdx.x;
     const Tile T = decode_tile(P, blockIdx.x);
@@ -307,12 +333,33 @@ __global__ void __launch_bounds__(kTileObs) k_offdiag_ff(const OffDiagParams P) 
     // -1/(4 pi) * 0.5  (icqLaplaceFunctor.cpp:9, icqQuadrature.cpp:245)
     const double cG = 0.5 / (-4.0 * 3.14159265358979323846);
 
-    const long long rowOff = P.lower
-        ? T.tile * kLowerTileElems + (long long)(obsValid ? tid : 0) * kLowerTile - T.src0
-        : (T.lrow0 + (obsValid ? tid : 0)) * P.ld;
-    double* gRow = P.G + rowOff;
-    double* kRow = WITH_K ? (P.K + rowOff) : nullptr;
-    double* kuRow = (WITH_K && P.lower) ? (P.Ku + rowOff) : nullptr;
+    // storage row of local row 0 of this CTA (the warp adds its rows when it flushes its patch)
+    const long long rowPitch = P.lower ? (long long)kLowerTile : P.ld;
+    const long long rowBase = P.lower ? T.tile * kLowerTileElems - T.src0 : T.lrow0 * P.ld;
+    const int lane = tid & 31, wrow0 = tid & ~31;
+
+    // the patch of this warp -> global memory: `count` columns starting at source triangle jf0;
+    // 4 rows x 8 columns per instruction, 64 contiguous bytes per row
+    auto flush = [&](long long jf0, int count) {
+        __syncwarp();
+        const int col = lane & (kStCols - 1);
+#pragma unroll
+        for (int rr = 0; rr < 32; rr += 4) {
+            const int row = rr + (lane >> 3);
+            const long long iRow = T.obs0 + wrow0 + row;
+            if (col < count && iRow < T.obsEnd) {
+                const long long at = rowBase + (long long)(wrow0 + row) * rowPitch + jf0 + col;
+                const bool offDiag = (T.kind != 0) || (jf0 + col != iRow);
+                // (the diagonal of G belongs to k_diag: never written here)
+                if (offDiag) P.G[at] = s_park[row * kStPitch + col];
+                if (WITH_K) {
+                    P.K[at] = s_park[(32 + row) * kStPitch + col];
+                    if (P.lower) P.Ku[at] = s_park[(64 + row) * kStPitch + col];
+                }
+            }
+        }
+        __syncwarp();
+    };
 
     unsigned int nFast = 0, nAll = 0;   // statistics (lane 0 of every warp adds them up)
 
@@ -341,28 +388,27 @@ __global__ void __launch_bounds__(kTileObs) k_offdiag_ff(const OffDiagParams P) 
             PairSums S;
             if (far) {
                 nFast += 1;
-                S = pair_fast<WITH_K>(O, pj, nj, bj);
+                S = pair_fast<WITH_K, PIPELINED>(O, pj, nj, bj);
             } else {
                 S = pair_exact<WITH_K>(O, pj, nj, bj);
             }
 
             const bool offDiag = (T.kind != 0) || (j != iObs);
-            if (obsValid && offDiag) {
-                const double a2Src = __ldg(P.area2 + j);
-                gRow[j] = (cG * a2Src) * S.g;
-                if (T.kind == 1) {
-                    // mirror: G[j,i] = g * areaObs / areaSrc  (icqLaplaceMatrices.cpp:98)
-                    P.G[(j - P.r0) * P.ld + iObs] = (cG * a2Obs) * S.g;
-                }
-                if (WITH_K) {
-                    kRow[j] = (cG * a2Src) * S.k;
-                    if (T.kind == 1) P.K[(j - P.r0) * P.ld + iObs] = (cG * a2Obs) * S.km;
-                    if (P.lower) kuRow[j] = (cG * a2Obs) * S.km;   // K[j,i] kept next to K[i,j]
-                }
-            } else if (obsValid && WITH_K) {
-                kRow[j] = 0.0;  // K[i,i] = 0 (flat panel, principal value)
-                if (P.lower) kuRow[j] = 0.0;
+            const double a2Src = __ldg(P.area2 + j);
+            const int pc = jj & (kStCols - 1);
+            s_park[lane * kStPitch + pc] = (cG * a2Src) * S.g;
+            if (WITH_K) {
+                // K[i,i] = 0 (flat panel, principal value); K[j,i] is kept next to K[i,j]
+                s_park[(32 + lane) * kStPitch + pc] = offDiag ? (cG * a2Src) * S.k : 0.0;
+                s_park[(64 + lane) * kStPitch + pc] = offDiag ? (cG * a2Obs) * S.km : 0.0;
             }
+            if (T.kind == 1 && obsValid) {
+                // mirror: G[j,i] = g * areaObs / areaSrc  (icqLaplaceMatrices.cpp:98); consecutive
+                // lanes write consecutive entries of row j
+                P.G[(j - P.r0) * P.ld + iObs] = (cG * a2Obs) * S.g;
+                if (WITH_K) P.K[(j - P.r0) * P.ld + iObs] = (cG * a2Obs) * S.km;
+            }
+            if (pc == kStCols - 1 || j + 1 >= T.srcEnd) flush(j - pc, pc + 1);
         }
     }
     if (P.stats && (tid & 31) == 0) {
@@ -419,7 +465,7 @@ int launch_offdiag_ff(icqb_ctx* ctx, const OffDiagParams& params, dim3 grid, boo
         ctx->launches += 1;
         ICQB_CUDA(ctx, cudaGetLastError());
     }
-    if (!ctx->d_ffstats) ICQB_CUDA(ctx, cudaMalloc(&ctx->d_ffstats, 2 * sizeof(unsigned long long)));
+    if (!ctx->d_ffstats) ICQB_CUDA(ctx, dev_alloc(ctx, &ctx->d_ffstats, 2 * sizeof(unsigned long long)));
     ICQB_CUDA(ctx, cudaMemsetAsync(ctx->d_ffstats, 0, 2 * sizeof(unsigned long long), ctx->stream));
     P.bound = ctx->d_bound;
     // ICQB_FF_KAPPA (experiments): separation factor of the far-field test, 2 <= kappa <= 16
@@ -434,17 +480,22 @@ int launch_offdiag_ff(icqb_ctx* ctx, const OffDiagParams& params, dim3 grid, boo
     P.stats = ctx->d_ffstats;
     static bool attr = false;
     if (!attr) {
-        ICQB_CUDA(ctx, cudaFuncSetAttribute(k_offdiag_ff<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            kFfSmemBytes));
-        ICQB_CUDA(ctx, cudaFuncSetAttribute(k_offdiag_ff<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            kFfSmemBytes));
+        ICQB_CUDA(ctx, cudaFuncSetAttribute(k_offdiag_ff<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFfSmemBytes));
+        ICQB_CUDA(ctx, cudaFuncSetAttribute(k_offdiag_ff<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFfSmemBytes));
+        ICQB_CUDA(ctx, cudaFuncSetAttribute(k_offdiag_ff<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFfSmemBytes));
+        ICQB_CUDA(ctx, cudaFuncSetAttribute(k_offdiag_ff<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFfSmemBytes));
         attr = true;
     }
+    const bool pipelined = ctx->offdiag_variant == 2;
     cudaEventRecord(ctx->ev0, ctx->stream);
-    if (withK)
-        k_offdiag_ff<true><<<grid, kTileObs, kFfSmemBytes, ctx->stream>>>(P);
+    if (withK && pipelined)
+        k_offdiag_ff<true, true><<<grid, kTileObs, kFfSmemBytes, ctx->stream>>>(P);
+    else if (withK)
+        k_offdiag_ff<true, false><<<grid, kTileObs, kFfSmemBytes, ctx->stream>>>(P);
+    else if (pipelined)
+        k_offdiag_ff<false, true><<<grid, kTileObs, kFfSmemBytes, ctx->stream>>>(P);
     else
-        k_offdiag_ff<false><<<grid, kTileObs, kFfSmemBytes, ctx->stream>>>(P);
+        k_offdiag_ff<false, false><<<grid, kTileObs, kFfSmemBytes, ctx->stream>>>(P);
     cudaEventRecord(ctx->ev1, ctx->stream);
     ctx->launches += 1;
     return check_cuda(ctx, cudaGetLastError(), "k_offdiag_ff launch");
@@ -458,8 +509,8 @@ extern "C" {
 
 int icqb_set_assembly_variant(icqb_ctx* ctx, int variant) {
     if (!ctx) return ICQB_EARG;
-    if (variant < 0 || variant > 1)
-        return set_error(ctx, ICQB_EARG, "icqb_set_assembly_variant: variant must be 0 or 1");
+    if (variant < 0 || variant > 2)
+        return set_error(ctx, ICQB_EARG, "icqb_set_assembly_variant: variant must be 0, 1 or 2");
     ctx->offdiag_variant = variant;
     return ICQB_OK;
 }

@@ -153,6 +153,7 @@ extern "C" int icqb_cg_solve_dev(icqb_ctx* ctx, uint64_t dA_, int64_t n, int64_t
     B.part_b = wp; wp += nT;
     B.part_pz = wp; wp += nT;
     B.state = reinterpret_cast<CgState*>(wp); wp += stateDoubles;
+    if ((reinterpret_cast<uintptr_t>(wp) & 15) != 0) wp += 1;   // tile_to_regs moves 16-byte pairs
     double* blocks = wp;
     B.Minv = nullptr;
     B.n = n;

@@ -96,6 +96,7 @@ struct DenseDesc {
     long long valid;   // rows of the block below n
     long long off;     // offset (doubles) of its m x m matrix in the dense buffer
     long long row0;    // first compact row (valid rows of all dense blocks, concatenated)
+    long long row0pad; // sum of m over the blocks before this one (position in the panel buffers)
 };
 
 // dense block of diag(scale) A from the lower storage: tiles J <= I are copied (rows this rank
@@ -150,128 +151,275 @@ __global__ void __launch_bounds__(256) k_dense_extract_full(const double* A, lon
     }
 }
 
-// In-place BLOCK Gauss-Jordan of every dense block, 128 x 128 tiles, no pivoting.  Step K:
-//   (a) k_tile_invert   P = A_KK^-1                       (in shared memory, as k_cg_invert_blocks)
-//   (b) k_tile_gemm<0>  A_KJ <- P A_KJ            (J != K)
-//   (c) k_tile_gemm<1>  A_IJ <- A_IJ - A_IK A_KJ  (I, J != K; old column, new row)
-//   (d) k_tile_gemm<2>  A_IK <- -A_IK P           (I != K)
-// Matrix traffic m^2 per step instead of per pivot.
-__global__ void __launch_bounds__(kInvThreads) k_tile_invert(const DenseDesc* desc, double* dense,
+// In-place inverse of every dense block (symmetric, m = 128 tiles): BLOCK SWEEP on the lower
+// block triangle, no pivoting.  Gauss-Jordan on a symmetric matrix keeps, after the pivot tiles
+// S = {0..K-1} have been swept, [S,S] = A_SS^-1 and [U,U] = the Schur complement symmetric and
+// [S,U] = -[U,S]^T, so the upper block triangle never has to be formed.  Step K, with
+// V_J (128 x 128, k-major) = A_KJ for J < K and A_JK^T for J > K ("row K of the completed
+// matrix"):
+//   (a) k_sweep_pivot    P = A_KK^-1 in registers (tile_gauss_jordan), symmetrised, in place
+//   (b) k_sweep_panel    W_J = P V_J for every J != K; V and W go to two 128 x m panel buffers
+//   (c) k_sweep_update   A_IJ += s_I V_I^T W_J for I >= J, both != K; s_I = +1 (I < K), -1 (I > K)
+//   (d) k_sweep_finish   row K: A_KJ = W_J (J < K); column K: A_IK = -W_I^T (I > K)
+// i.e. (T - 1) + T (T - 1) / 2 tile products per step instead of the (T - 1) (T + 1) of the
+// unsymmetric block Gauss-Jordan this replaces (T = 8: 35 instead of 63), and after the last step
+// k_dense_mirror copies the lower triangle into the upper one (k_dense_apply streams full rows).
+// Round 2 on a B200, config C2 (20 blocks of 8 tiles): the first version took 7.5 ms of a 40 ms
+// solve -- 354 us per pivot tile inverted in shared memory, tile products at 9 TFLOP/s.
+//
+// (b) and (c) share one FP64 tile kernel: CTA tile 128 x 64, 128 threads, 8 x 8 outputs per
+// thread (rows {2 tx, 2 tx + 1} + 32 i, columns 8 ty .. 8 ty + 7), K = 128 in slabs of 16 through
+// double-buffered shared memory, the next slab's global loads in flight while the current one is
+// multiplied (the arrangement of k_lu_gemm, lu.cu); both operands are k-major.
+constexpr int kSwM = 128, kSwN = 64, kSwK = 16;
+constexpr int kSwLdB = kSwN;       // (no padding: 2 x 16 x (128 + 64) doubles are the 48 KB of static shared memory)
+
+__global__ void __launch_bounds__(kInvThreads) k_sweep_pivot(const DenseDesc* desc, double* dense,
                                                              long long K, int* weak) {
     extern __shared__ double s_inv[];
     const DenseDesc D = desc[blockIdx.z];
     if (K >= D.tiles) return;
-    double* a = s_inv;                    // [128][129]
-    double* colk = a + kT * kInvLd;
-    double* rowk = colk + kT;
-    const long long m = D.m;
-    double* g = dense + D.off + (K * kT) * m + K * kT;
-    const int tid = threadIdx.x;
-    for (int e = tid; e < kT * kT; e += kInvThreads)
-        a[(e >> 7) * kInvLd + (e & (kT - 1))] = g[(long long)(e >> 7) * m + (e & (kT - 1))];
-    __syncthreads();
-    int nweak = 0;   // pivots that lost 13 digits against their Schur diagonal entry (reported only)
-    for (int k = 0; k < kT; ++k) {
-        const double piv = a[k * kInvLd + k];
-        if (!(fabs(piv) >= 1e-13 * fabs(g[(long long)k * m + k])) || !(fabs(piv) <= 1.0e300)) ++nweak;
-        const double pivinv = 1.0 / piv;
-        if (tid < kT) {
-            colk[tid] = a[tid * kInvLd + k];
-            rowk[tid] = (tid == k) ? pivinv : a[k * kInvLd + tid] * pivinv;
-        }
-        __syncthreads();
-        for (int e = tid; e < kT * kT; e += kInvThreads) {
-            const int i = e >> 7, j = e & (kT - 1);
-            double v = a[i * kInvLd + j];
-            if (i == k)
-                v = rowk[j];
-            else if (j == k)
-                v = -colk[i] * pivinv;
-            else
-                v = fma(-colk[i], rowk[j], v);
-            a[i * kInvLd + j] = v;
-        }
-        __syncthreads();
-    }
-    for (int e = tid; e < kT * kT; e += kInvThreads)
-        g[(long long)(e >> 7) * m + (e & (kT - 1))] = a[(e >> 7) * kInvLd + (e & (kT - 1))];
-    if (nweak && tid == 0 && weak) atomicAdd(weak, nweak);
+    double* s_t = s_inv;
+    double* s_vec = s_inv + kT * kInvLd;
+    double* g = dense + D.off + (K * kT) * D.m + K * kT;
+    double a[4][4];
+    tile_to_regs(g, D.m, a);
+    const int nweak = tile_gauss_jordan(a, s_vec);   // weak pivots are reported only
+    if (nweak && weak) atomicAdd(weak, nweak);
+    regs_to_tile_symmetric(a, s_t, g, D.m);
 }
 
-// 128 x 128 x 128 tile product on tiles of a dense block (row pitch m), 256 threads, 8 x 8
-// outputs per thread, operands staged through shared memory in slabs of 16.
-// MODE 0: C_KJ = A_KK B_KJ (grid x = J);  1: C_IJ -= A_IK B_KJ (grid y = I, x = J);
-// MODE 2: C_IK = -A_IK B_KK (grid y = I).  C may alias an operand: it is written after the
-// last read.
-template <int MODE>
-__global__ void __launch_bounds__(256) k_tile_gemm(const DenseDesc* desc, double* dense, long long K) {
-    __shared__ double As[kT][17];
-    __shared__ double Bs[16][kT];
+// slab kc .. kc + 15 of a k-major operand X[k][c], c < WIDTH: into registers (WIDTH / 16 double2
+// per thread), then into shared memory
+template <int WIDTH>
+struct SwSlab {
+    static constexpr int kPairs = WIDTH * kSwK / 2 / 128;   // double2 per thread: 8 (128 wide), 4 (64)
+    double2 v[kPairs];
+    // X[k][c] = src[k * ld + c]
+    __device__ __forceinline__ void load_rows(const double* src, long long ld, int kc, int tid) {
+#pragma unroll
+        for (int q = 0; q < kPairs; ++q) {
+            const int idx = tid + 128 * q, kk = idx / (WIDTH / 2), c = (idx % (WIDTH / 2)) * 2;
+            v[q] = *reinterpret_cast<const double2*>(src + (long long)(kc + kk) * ld + c);
+        }
+    }
+    // X[k][c] = src[c * ld + k]  (the transposed tile)
+    __device__ __forceinline__ void load_cols(const double* src, long long ld, int kc, int tid) {
+#pragma unroll
+        for (int q = 0; q < kPairs; ++q) {
+            const int idx = tid + 128 * q, c = idx >> 3, kk = (idx & 7) * 2;
+            v[q] = *reinterpret_cast<const double2*>(src + (long long)c * ld + kc + kk);
+        }
+    }
+    template <int LD>
+    __device__ __forceinline__ void store_rows(double (*dst)[LD], int tid, double sign) const {
+#pragma unroll
+        for (int q = 0; q < kPairs; ++q) {
+            const int idx = tid + 128 * q, kk = idx / (WIDTH / 2), c = (idx % (WIDTH / 2)) * 2;
+            *reinterpret_cast<double2*>(&dst[kk][c]) = make_double2(sign * v[q].x, sign * v[q].y);
+        }
+    }
+    template <int LD>
+    __device__ __forceinline__ void store_cols(double (*dst)[LD], int tid) const {
+#pragma unroll
+        for (int q = 0; q < kPairs; ++q) {
+            const int idx = tid + 128 * q, c = idx >> 3, kk = (idx & 7) * 2;
+            dst[kk][c] = v[q].x;
+            dst[kk + 1][c] = v[q].y;
+        }
+    }
+};
+
+// one slab of 16: acc[i][j] += As[kk][rows of the thread] * Bs[kk][columns of the thread]
+__device__ __forceinline__ void sw_multiply(const double (*As)[kSwM], const double (*Bs)[kSwLdB], int tx,
+                                            int ty, double (&acc)[8][8]) {
+#pragma unroll
+    for (int kk = 0; kk < kSwK; ++kk) {
+        double a[8], b[8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const double2 v = *reinterpret_cast<const double2*>(&As[kk][2 * tx + 32 * i]);
+            a[2 * i] = v.x;
+            a[2 * i + 1] = v.y;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const double2 v = *reinterpret_cast<const double2*>(&Bs[kk][8 * ty + 2 * i]);
+            b[2 * i] = v.x;
+            b[2 * i + 1] = v.y;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+    }
+}
+
+// (b) W[:, c0 .. c0 + 63] = P V[:, c0 .. c0 + 63]; grid (m / 64, 1, blocks).  P is symmetric, so
+// its k-major form is P itself.  The V chunk passes through shared memory anyway and is written
+// to the V panel from there (k-major, whichever triangle it came from).
+__global__ void __launch_bounds__(128, 2) k_sweep_panel(const DenseDesc* desc, double* dense, double* panels,
+                                                        long long K) {
+    __shared__ __align__(16) double As[2][kSwK][kSwM];
+    __shared__ __align__(16) double Bs[2][kSwK][kSwLdB];
     const DenseDesc D = desc[blockIdx.z];
     if (K >= D.tiles) return;
-    long long I, J;
-    if (MODE == 0) { I = K; J = blockIdx.x; }
-    else if (MODE == 1) { I = blockIdx.y; J = blockIdx.x; }
-    else { I = blockIdx.y; J = K; }
-    if (I >= D.tiles || J >= D.tiles) return;
-    if (MODE == 0 && J == K) return;
-    if (MODE == 1 && (I == K || J == K)) return;
-    if (MODE == 2 && I == K) return;
-    const long long m = D.m;
+    const long long m = D.m, c0 = (long long)blockIdx.x * kSwN, J = c0 / kT;
+    if (J >= D.tiles || J == K) return;
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     double* base = dense + D.off;
-    const double* Ap = base + (I * kT) * m + K * kT;     // A_IK  (MODE 0: A_KK)
-    const double* Bp = base + (K * kT) * m + J * kT;     // B_KJ  (MODE 2: B_KK)
-    double* Cp = base + (I * kT) * m + J * kT;
-    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    const double* P = base + (K * kT) * m + K * kT;
+    // V[k][c0 + c]: row K of the block (J < K), or column K transposed (J > K)
+    const bool fromRow = J < K;
+    const double* Vsrc = fromRow ? base + (K * kT) * m + c0 : base + c0 * m + K * kT;
+    double* Vp = panels + 2 * D.row0pad * kT;           // this block's V panel [128][m]
+    double* Wp = Vp + kT * m;                           // and W panel
+
+    SwSlab<kSwM> sa;
+    SwSlab<kSwN> sb;
     double acc[8][8];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[i][j] = 0.0;
-    for (int k0 = 0; k0 < kT; k0 += 16) {
-        // A slab: 128 rows x 16 columns; B slab: 16 rows x 128 columns (2048 entries each)
-        for (int e = tid; e < kT * 16; e += 256) {
-            const int r = e >> 4, c = e & 15;
-            As[r][c] = Ap[(long long)r * m + k0 + c];
-            const int br = e >> 7, bc = e & (kT - 1);
-            Bs[br][bc] = Bp[(long long)(k0 + br) * m + bc];
+    sa.load_rows(P, m, 0, tid);
+    if (fromRow) sb.load_rows(Vsrc, m, 0, tid); else sb.load_cols(Vsrc, m, 0, tid);
+    sa.store_rows(As[0], tid, 1.0);
+    if (fromRow) sb.store_rows(Bs[0], tid, 1.0); else sb.store_cols(Bs[0], tid);
+    __syncthreads();
+    for (int s = 0; s < kT / kSwK; ++s) {
+        const int cur = s & 1;
+        if (s + 1 < kT / kSwK) {
+            sa.load_rows(P, m, (s + 1) * kSwK, tid);
+            if (fromRow) sb.load_rows(Vsrc, m, (s + 1) * kSwK, tid); else sb.load_cols(Vsrc, m, (s + 1) * kSwK, tid);
         }
-        __syncthreads();
+        // the V slab to its panel, k-major: 16 x 64 doubles, four double2 per thread
 #pragma unroll
-        for (int kk = 0; kk < 16; ++kk) {
-            double av[8], bv[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) av[i] = As[ty * 8 + i][kk];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) bv[j] = Bs[kk][tx * 8 + j];
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-#pragma unroll
-                for (int j = 0; j < 8; ++j) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
+        for (int q = 0; q < 4; ++q) {
+            const int idx = tid + 128 * q, kk = idx >> 5, c = (idx & 31) * 2;
+            *reinterpret_cast<double2*>(Vp + (long long)(s * kSwK + kk) * m + c0 + c) =
+                *reinterpret_cast<const double2*>(&Bs[cur][kk][c]);
         }
-        __syncthreads();
+        sw_multiply(As[cur], Bs[cur], tx, ty, acc);
+        if (s + 1 < kT / kSwK) {
+            sa.store_rows(As[cur ^ 1], tid, 1.0);
+            if (fromRow) sb.store_rows(Bs[cur ^ 1], tid, 1.0); else sb.store_cols(Bs[cur ^ 1], tid);
+            __syncthreads();
+        }
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < 8; ++i) {
+        const int row = 2 * tx + 32 * (i >> 1) + (i & 1);
+        double2* dst = reinterpret_cast<double2*>(Wp + (long long)row * m + c0 + 8 * ty);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            double* c = Cp + (long long)(ty * 8 + i) * m + tx * 8 + j;
-            if (MODE == 0) *c = acc[i][j];
-            else if (MODE == 1) *c = *c - acc[i][j];
-            else *c = -acc[i][j];
-        }
+        for (int j = 0; j < 4; ++j) dst[j] = make_double2(acc[i][2 * j], acc[i][2 * j + 1]);
+    }
 }
 
-// grid (mmax/128, mmax, blocks)
-__global__ void __launch_bounds__(kT) k_dense_symmetrise(const DenseDesc* desc, double* dense) {
+// (c) A_IJ[:, n0 .. n0 + 63] += s_I V_I^T W_J; grid (T (T - 1) / 2 pairs x 2 halves, 1, blocks)
+__global__ void __launch_bounds__(128, 2) k_sweep_update(const DenseDesc* desc, double* dense,
+                                                         const double* panels, long long K) {
+    __shared__ __align__(16) double As[2][kSwK][kSwM];
+    __shared__ __align__(16) double Bs[2][kSwK][kSwLdB];
+    const DenseDesc D = desc[blockIdx.z];
+    if (K >= D.tiles) return;
+    // pair (a >= b) over the tile indices without K
+    const long long t = blockIdx.x >> 1;
+    long long a = (long long)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+    while (a * (a + 1) / 2 > t) --a;
+    while ((a + 1) * (a + 2) / 2 <= t) ++a;
+    const long long b = t - a * (a + 1) / 2;
+    if (a >= D.tiles - 1) return;
+    const long long I = a + (a >= K ? 1 : 0), J = b + (b >= K ? 1 : 0);
+    const long long m = D.m, n0 = (long long)(blockIdx.x & 1) * kSwN;
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const double* Vp = panels + 2 * D.row0pad * kT;
+    const double* Wp = Vp + kT * m;
+    const double* Asrc = Vp + I * kT;
+    const double* Bsrc = Wp + J * kT + n0;
+    const double sign = (I < K) ? 1.0 : -1.0;
+    double* C = dense + D.off + (I * kT) * m + J * kT + n0;
+
+    SwSlab<kSwM> sa;
+    SwSlab<kSwN> sb;
+    sa.load_rows(Asrc, m, 0, tid);
+    sb.load_rows(Bsrc, m, 0, tid);
+    // the accumulators start from C: 32 independent loads per thread, in flight with the first slab
+    double acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int row = 2 * tx + 32 * (i >> 1) + (i & 1);
+        const double2* src = reinterpret_cast<const double2*>(C + (long long)row * m + 8 * ty);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const double2 v = src[j];
+            acc[i][2 * j] = v.x;
+            acc[i][2 * j + 1] = v.y;
+        }
+    }
+    sa.store_rows(As[0], tid, sign);
+    sb.store_rows(Bs[0], tid, 1.0);
+    __syncthreads();
+    for (int s = 0; s < kT / kSwK; ++s) {
+        const int cur = s & 1;
+        if (s + 1 < kT / kSwK) {
+            sa.load_rows(Asrc, m, (s + 1) * kSwK, tid);
+            sb.load_rows(Bsrc, m, (s + 1) * kSwK, tid);
+        }
+        sw_multiply(As[cur], Bs[cur], tx, ty, acc);
+        if (s + 1 < kT / kSwK) {
+            sa.store_rows(As[cur ^ 1], tid, sign);
+            sb.store_rows(Bs[cur ^ 1], tid, 1.0);
+            __syncthreads();
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int row = 2 * tx + 32 * (i >> 1) + (i & 1);
+        double2* dst = reinterpret_cast<double2*>(C + (long long)row * m + 8 * ty);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dst[j] = make_double2(acc[i][2 * j], acc[i][2 * j + 1]);
+    }
+}
+
+// (d) row K: A_KJ = W_J (J < K); column K: A_IK = -W_I^T (I > K).  Grid (m / 128, 1, blocks),
+// 256 threads, 32 x 32 sub-tiles through shared memory for the transposed copies.
+__global__ void __launch_bounds__(256) k_sweep_finish(const DenseDesc* desc, double* dense,
+                                                      const double* panels, long long K) {
+    __shared__ double s_t[32][33];
+    const DenseDesc D = desc[blockIdx.z];
+    const long long J = blockIdx.x;
+    if (K >= D.tiles || J >= D.tiles || J == K) return;
+    const long long m = D.m;
+    const double* W = panels + 2 * D.row0pad * kT + kT * m + J * kT;   // W_J[k][j], pitch m
+    double* base = dense + D.off;
+    const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;   // 32 x 8
+    if (J < K) {
+        double* dst = base + (K * kT) * m + J * kT;
+        for (int e = threadIdx.x; e < kT * kT; e += 256) {
+            const int k = e >> 7, j = e & (kT - 1);
+            dst[(long long)k * m + j] = W[(long long)k * m + j];
+        }
+        return;
+    }
+    double* dst = base + (J * kT) * m + K * kT;   // A_JK[j][k] = -W_J[k][j]
+    for (int sub = 0; sub < 16; ++sub) {
+        const int k0 = (sub >> 2) * 32, j0 = (sub & 3) * 32;
+        for (int r = ly; r < 32; r += 8) s_t[r][lx] = W[(long long)(k0 + r) * m + j0 + lx];
+        __syncthreads();
+        for (int r = ly; r < 32; r += 8) dst[(long long)(j0 + r) * m + k0 + lx] = -s_t[lx][r];
+        __syncthreads();
+    }
+}
+
+// the upper triangle from the lower one; grid (mmax / 128, mmax, blocks)
+__global__ void __launch_bounds__(kT) k_dense_mirror(const DenseDesc* desc, double* dense) {
     const DenseDesc D = desc[blockIdx.z];
     const long long i = blockIdx.y;
     const long long j = (long long)blockIdx.x * kT + threadIdx.x;
     if (i >= D.m || j >= D.m || j <= i) return;
     double* a = dense + D.off;
-    const double avg = 0.5 * (a[i * D.m + j] + a[j * D.m + i]);
-    a[i * D.m + j] = avg;
-    a[j * D.m + i] = avg;
+    a[i * D.m + j] = a[j * D.m + i];
 }
 
 // w = C^-1 r on the rows of the dense blocks: HBM-bound (the inverse blocks are streamed once
@@ -602,7 +750,7 @@ int cg_solve_caps(icqb_ctx* ctx, uint64_t dA_, int64_t n, int64_t ld, int storag
     std::vector<DenseDesc> hdesc;
     std::vector<GatherDesc> hgather;
     std::vector<long long> sendLen((size_t)P, 0);
-    long long denseDoubles = 0, denseRows = 0, kMaxTiles = 0, repDoubles = 0, repOff = 0;
+    long long denseDoubles = 0, denseRows = 0, denseRowsPad = 0, kMaxTiles = 0, repDoubles = 0, repOff = 0;
     int nOwn = 0;
     for (int pass = 0; pass < 2; ++pass) {
         for (int bq = 0; bq < nAll; ++bq) {
@@ -626,8 +774,10 @@ int cg_solve_caps(icqb_ctx* ctx, uint64_t dA_, int64_t n, int64_t ld, int storag
             D.valid = std::min<long long>(n, ranges[bq].t1 * kT) - D.t0 * kT;
             D.off = denseDoubles;
             D.row0 = denseRows;
+            D.row0pad = denseRowsPad;
             denseDoubles += D.m * D.m;
             denseRows += D.valid;
+            denseRowsPad += D.m;
             kMaxTiles = std::max(kMaxTiles, D.tiles);
             hdesc.push_back(D);
             if (pass == 0) ++nOwn;
@@ -649,8 +799,9 @@ int cg_solve_caps(icqb_ctx* ctx, uint64_t dA_, int64_t n, int64_t ld, int storag
     const long long nfull = chunk * P;
     const long long stateDoubles = (sizeof(CgState) + 7) / 8;
     const long long small = 8 * n + 8 + nfull + 6 * nT + stateDoubles;
-    const long long need = small + nT * kBlockElems + denseDoubles + descDoubles + tileDoubles + gatherDoubles +
-                           gdescDoubles + 66;
+    const long long panelDoubles = 2 * kT * denseRowsPad;   // V and W panels of the block sweep
+    const long long need = small + nT * kBlockElems + denseDoubles + panelDoubles + descDoubles + tileDoubles +
+                           gatherDoubles + gdescDoubles + 68;
     int rc = ensure_work(ctx, need);
     if (rc != ICQB_OK) return rc;
     CgBuf B;
@@ -671,9 +822,11 @@ int cg_solve_caps(icqb_ctx* ctx, uint64_t dA_, int64_t n, int64_t ld, int storag
     B.part_b = wp; wp += nT;
     B.part_pz = wp; wp += nT;
     B.state = reinterpret_cast<CgState*>(wp); wp += stateDoubles;
+    if ((reinterpret_cast<uintptr_t>(wp) & 15) != 0) wp += 1;   // tile_to_regs moves 16-byte pairs
     double* blocks = wp; wp += nT * kBlockElems;
     if ((reinterpret_cast<uintptr_t>(wp) & 15) != 0) wp += 1;   // k_dense_apply reads 16-byte pairs
     double* dense = wp; wp += denseDoubles;
+    double* panels = wp; wp += panelDoubles;
     DenseDesc* ddesc = reinterpret_cast<DenseDesc*>(wp); wp += descDoubles;
     int* dtile = reinterpret_cast<int*>(wp); wp += tileDoubles;
     double* wsend = wp; wp += sharded ? slot : 0;
@@ -820,22 +973,28 @@ int cg_solve_caps(icqb_ctx* ctx, uint64_t dA_, int64_t n, int64_t ld, int storag
             k_recip<<<128, 256, 0, st>>>(ctx->d_area2, inv_area, n);
             ctx->launches += 1;
         }
-        // 128 x 128 blocks (used outside the caps), as in cg.cu
-        if (storage == 1)
-            k_cg_blocks_lower<<<vgrid, 256, 0, st>>>(A, L, scale, n, blocks);
-        else
-            k_cg_blocks_full<<<vgrid, 256, 0, st>>>(A, ld, mv.r0, mv.r1, scale, n, blocks);
-        ctx->launches += 1;
-        CG_CUDA(cudaGetLastError());
-        CG_TRY(comm_allreduce_sum(ctx, blocks, nT * kBlockElems, st));
-        CG_CUDA(cudaFuncSetAttribute(k_cg_invert_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     kInvSmem));
-        k_cg_invert_blocks<<<vgrid, kInvThreads, kInvSmem, st>>>(blocks, &B.state->bad_blocks);
-        ctx->launches += 1;
-        CG_CUDA(cudaGetLastError());
+        // tables of the partition first: tile -> dense block (or -1: single tile)
+        CG_CUDA(cudaMemcpyAsync(dtile, htile.data(), sizeof(int) * (size_t)nT, cudaMemcpyHostToDevice, st));
+        // 128 x 128 blocks (used by the single tiles of the partition), as in cg.cu; skipped
+        // altogether when every tile belongs to a dense block (the default partition at C2)
+        bool singles = false;
+        for (long long t = 0; t < nT; ++t) singles = singles || htile[(size_t)t] < 0;
+        if (singles) {
+            if (storage == 1)
+                k_cg_blocks_lower<<<vgrid, 256, 0, st>>>(A, L, scale, n, blocks);
+            else
+                k_cg_blocks_full<<<vgrid, 256, 0, st>>>(A, ld, mv.r0, mv.r1, scale, n, blocks);
+            ctx->launches += 1;
+            CG_CUDA(cudaGetLastError());
+            CG_TRY(comm_allreduce_sum(ctx, blocks, nT * kBlockElems, st));
+            CG_CUDA(cudaFuncSetAttribute(k_cg_invert_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         kInvSmem));
+            k_cg_invert_blocks<<<vgrid, kInvThreads, kInvSmem, st>>>(blocks, &B.state->bad_blocks, dtile);
+            ctx->launches += 1;
+            CG_CUDA(cudaGetLastError());
+        }
 
         // tables of the dense blocks, then: extract, all-reduce, block Gauss-Jordan, symmetrise
-        CG_CUDA(cudaMemcpyAsync(dtile, htile.data(), sizeof(int) * (size_t)nT, cudaMemcpyHostToDevice, st));
         if (sharded)
             CG_CUDA(cudaMemcpyAsync(dgather, hgather.data(), sizeof(GatherDesc) * hgather.size(),
                                     cudaMemcpyHostToDevice, st));
@@ -860,20 +1019,20 @@ int cg_solve_caps(icqb_ctx* ctx, uint64_t dA_, int64_t n, int64_t ld, int storag
             if (repDoubles > 0) CG_TRY(comm_allreduce_sum(ctx, dense + repOff, repDoubles, st));
         }
         if (nDense > 0) {
-            const dim3 tgrid((unsigned)kMaxTiles, (unsigned)kMaxTiles, (unsigned)nDense);
-            CG_CUDA(cudaFuncSetAttribute(k_tile_invert, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         kInvSmem));
+            CG_CUDA(cudaFuncSetAttribute(k_sweep_pivot, cudaFuncAttributeMaxDynamicSharedMemorySize, kInvSmem));
+            const long long mMax = kMaxTiles * kT;
+            const unsigned pairs2 = (unsigned)(kMaxTiles * (kMaxTiles - 1));   // pairs x two column halves
             for (long long K = 0; K < kMaxTiles; ++K) {
-                k_tile_invert<<<dim3(1, 1, (unsigned)nDense), kInvThreads, kInvSmem, st>>>(ddesc, dense, K,
+                k_sweep_pivot<<<dim3(1, 1, (unsigned)nDense), kInvThreads, kInvSmem, st>>>(ddesc, dense, K,
                                                                                           &B.state->weak_pivots);
-                k_tile_gemm<0><<<dim3((unsigned)kMaxTiles, 1, (unsigned)nDense), 256, 0, st>>>(ddesc, dense, K);
-                k_tile_gemm<1><<<tgrid, 256, 0, st>>>(ddesc, dense, K);
-                k_tile_gemm<2><<<dim3(1, (unsigned)kMaxTiles, (unsigned)nDense), 256, 0, st>>>(ddesc, dense, K);
+                k_sweep_panel<<<dim3((unsigned)(mMax / kSwN), 1, (unsigned)nDense), 128, 0, st>>>(ddesc, dense, panels,
+                                                                                                K);
+                if (pairs2 > 0)
+                    k_sweep_update<<<dim3(pairs2, 1, (unsigned)nDense), 128, 0, st>>>(ddesc, dense, panels, K);
+                k_sweep_finish<<<dim3((unsigned)kMaxTiles, 1, (unsigned)nDense), 256, 0, st>>>(ddesc, dense, panels, K);
                 ctx->launches += 4;
             }
-            const long long mMax = kMaxTiles * kT;
-            k_dense_symmetrise<<<dim3((unsigned)(mMax / kT), (unsigned)mMax, (unsigned)nDense), kT, 0, st>>>(
-                ddesc, dense);
+            k_dense_mirror<<<dim3((unsigned)(mMax / kT), (unsigned)mMax, (unsigned)nDense), kT, 0, st>>>(ddesc, dense);
             ctx->launches += 1;
             CG_CUDA(cudaGetLastError());
         }

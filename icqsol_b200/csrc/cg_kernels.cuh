@@ -24,7 +24,7 @@ static_assert(kGroups == 8, "k_cg_resid joins exactly eight groups");
 constexpr long long kBlockElems = (long long)kT * kT;
 constexpr int kInvThreads = 1024;
 constexpr int kInvLd = kT + 1;               // padded row of the in-shared-memory inversion
-constexpr int kInvSmem = (kT * kInvLd + 2 * kT) * 8;   // 134,144 B
+constexpr int kInvSmem = (kT * kInvLd + 5 * kT) * 8;   // 137,216 B: staging tile + published vectors
 
 enum ResidMode { kUpdate = 0, kInit = 1, kTrue = 2 };
 
@@ -103,52 +103,151 @@ __global__ void __launch_bounds__(256) k_cg_blocks_full(const double* A, long lo
     }
 }
 
-// In-place inverse of every 128 x 128 block: Gauss-Jordan without pivoting in shared
-// memory (the blocks are principal sub-matrices of a matrix that is definite wherever the
-// reference's quadrature is accurate enough), then symmetrised -- a CG preconditioner must be
-// symmetric.  A pivot that is not finite, or has lost 13 digits against the diagonal entry it
-// started from (sliver triangles: DESIGN.md section 4.6), would give a huge, indefinite "inverse":
-// such a block falls back to 1/diag and is counted in *bad (icqb_cg_last_blocks).
-__global__ void __launch_bounds__(kInvThreads) k_cg_invert_blocks(double* blocks, int* bad) {
-    extern __shared__ double s_inv[];
-    double* a = s_inv;                    // [128][129]
-    double* colk = a + kT * kInvLd;       // [128]
-    double* rowk = colk + kT;             // [128]
-    double* g = blocks + (long long)blockIdx.x * kBlockElems;
-    const int tid = threadIdx.x;
-    for (int e = tid; e < kT * kT; e += kInvThreads) a[(e >> 7) * kInvLd + (e & (kT - 1))] = g[e];
+// Gauss-Jordan inverse (no pivoting) of a 128 x 128 tile held in REGISTERS: 1,024 threads, thread
+// (ty = warp, tx = lane) owns the 4 x 4 sub-block rows 4 ty.., columns 4 tx...  Per pivot k the
+// warp that owns row k publishes the scaled pivot row (pivinv at position k), one lane per warp
+// publishes its four entries of column k, and after ONE barrier every thread does its 16 DFMAs
+// from registers (the two published vectors are double-buffered by the parity of k, so the
+// next pivot's writers cannot overtake this pivot's readers).  The first version kept the tile
+// in shared memory and moved 4 shared-memory words per DFMA: 2.8 us per pivot, 354 us per tile
+// (ncu, round 2); this one is bound by the barrier and the row warp's division.
+// s_vec: [2][2][128] doubles (row / column, two parities) + [128] original diagonal.
+// Returns the number of weak pivots seen by this thread's warp (lane 0 of the row warps only).
+constexpr int kGjVecDoubles = 5 * kT;
+__device__ __forceinline__ int tile_gauss_jordan(double (&a)[4][4], double* s_vec) {
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    double* s_diag = s_vec + 4 * kT;
+    if (tx == ty) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) s_diag[4 * ty + r] = a[r][r];
+    }
     __syncthreads();
-    bool broken = false;   // the same on every thread: all of them read the same pivots
+    int nweak = 0;
     for (int k = 0; k < kT; ++k) {
-        const double piv = a[k * kInvLd + k];
-        if (!(fabs(piv) >= 1e-13 * fabs(g[k * kT + k])) || !(fabs(piv) <= 1.0e300)) broken = true;
-        const double pivinv = 1.0 / piv;
-        if (tid < kT) {
-            colk[tid] = a[tid * kInvLd + k];
-            rowk[tid] = (tid == k) ? pivinv : a[k * kInvLd + tid] * pivinv;
+        const int kw = k >> 2, kr = k & 3;
+        double* s_row = s_vec + (k & 1) * 2 * kT;
+        double* s_col = s_row + kT;
+        if (ty == kw) {
+            double rk[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+                if (r == kr) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) rk[c] = a[r][c];
+                }
+            double pv = rk[0];
+#pragma unroll
+            for (int c = 1; c < 4; ++c)
+                if (c == kr) pv = rk[c];
+            const double piv = __shfl_sync(0xffffffffu, pv, kw);
+            // a pivot that is not finite, or has lost 13 digits against the diagonal entry it
+            // started from, is reported (the caller decides what to do with the tile)
+            if (tx == 0 && (!(fabs(piv) >= 1e-13 * fabs(s_diag[k])) || !(fabs(piv) <= 1.0e300))) ++nweak;
+            const double pivinv = 1.0 / piv;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) s_row[4 * tx + c] = (4 * tx + c == k) ? pivinv : rk[c] * pivinv;
+        }
+        if (tx == kw) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                double v = a[r][0];
+#pragma unroll
+                for (int c = 1; c < 4; ++c)
+                    if (c == kr) v = a[r][c];
+                s_col[4 * ty + r] = v;
+            }
         }
         __syncthreads();
-        for (int e = tid; e < kT * kT; e += kInvThreads) {
+        double rs[4], cs[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) rs[c] = s_row[4 * tx + c];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) cs[r] = s_col[4 * ty + r];
+        const double pivinv = s_row[k];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) a[r][c] = fma(-cs[r], rs[c], a[r][c]);
+        if (tx == kw) {   // column k: -a_ik / pivot
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    if (c == kr) a[r][c] = -cs[r] * pivinv;
+        }
+        if (ty == kw) {   // row k: the scaled pivot row, 1 / pivot on the diagonal
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+                if (r == kr) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) a[r][c] = rs[c];
+                }
+        }
+    }
+    return nweak;
+}
+
+// tile (row pitch ld) <-> the threads' 4 x 4 sub-blocks: a warp moves one row of 1 KB at a time
+__device__ __forceinline__ void tile_to_regs(const double* g, long long ld, double (&a)[4][4]) {
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const double2* src = reinterpret_cast<const double2*>(g + (long long)(4 * ty + r) * ld + 4 * tx);
+        const double2 lo = src[0], hi = src[1];
+        a[r][0] = lo.x; a[r][1] = lo.y; a[r][2] = hi.x; a[r][3] = hi.y;
+    }
+}
+
+// symmetrised store: out = (a + a^T) / 2 through a [128][129] staging tile in shared memory
+__device__ __forceinline__ void regs_to_tile_symmetric(const double (&a)[4][4], double* s_t, double* g,
+                                                       long long ld) {
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) s_t[(4 * ty + r) * kInvLd + 4 * tx + c] = a[r][c];
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        double o[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) o[c] = 0.5 * (a[r][c] + s_t[(4 * tx + c) * kInvLd + 4 * ty + r]);
+        double2* dst = reinterpret_cast<double2*>(g + (long long)(4 * ty + r) * ld + 4 * tx);
+        dst[0] = make_double2(o[0], o[1]);
+        dst[1] = make_double2(o[2], o[3]);
+    }
+}
+
+// In-place inverse of every 128 x 128 block (the blocks are principal sub-matrices of a matrix
+// that is definite wherever the reference's quadrature is accurate enough), then symmetrised -- a
+// CG preconditioner must be symmetric.  A weak pivot (sliver triangles: DESIGN.md section 4.6)
+// would give a huge, indefinite "inverse": such a block falls back to 1/diag and is counted in
+// *bad (icqb_cg_last_blocks).  `tiles` (optional): only blocks with tiles[block] < 0 are single
+// tiles of the partition; the others belong to dense blocks and are skipped.
+__global__ void __launch_bounds__(kInvThreads) k_cg_invert_blocks(double* blocks, int* bad,
+                                                                  const int* tiles = nullptr) {
+    extern __shared__ double s_inv[];
+    if (tiles && tiles[blockIdx.x] >= 0) return;
+    double* s_t = s_inv;                     // [128][129] staging of the symmetrised store
+    double* s_vec = s_inv + kT * kInvLd;     // published rows / columns, original diagonal
+    __shared__ int s_broken;
+    double* g = blocks + (long long)blockIdx.x * kBlockElems;
+    if (threadIdx.x == 0) s_broken = 0;
+    double a[4][4];
+    tile_to_regs(g, kT, a);
+    const int nweak = tile_gauss_jordan(a, s_vec);
+    if (nweak) s_broken = 1;
+    __syncthreads();
+    if (s_broken) {
+        const double* s_diag = s_vec + 4 * kT;
+        for (int e = threadIdx.x; e < kT * kT; e += kInvThreads) {
             const int i = e >> 7, j = e & (kT - 1);
-            double v = a[i * kInvLd + j];
-            if (i == k)
-                v = rowk[j];
-            else if (j == k)
-                v = -colk[i] * pivinv;
-            else
-                v = fma(-colk[i], rowk[j], v);
-            a[i * kInvLd + j] = v;
+            g[e] = (i == j) ? 1.0 / s_diag[i] : 0.0;
         }
-        __syncthreads();
+        if (threadIdx.x == 0 && bad) atomicAdd(bad, 1);
+        return;
     }
-    for (int e = tid; e < kT * kT; e += kInvThreads) {
-        const int i = e >> 7, j = e & (kT - 1);
-        if (broken)
-            g[e] = (i == j) ? 1.0 / g[e] : 0.0;
-        else
-            g[e] = 0.5 * (a[i * kInvLd + j] + a[j * kInvLd + i]);
-    }
-    if (broken && tid == 0 && bad) atomicAdd(bad, 1);
+    regs_to_tile_symmetric(a, s_t, g, kT);
 }
 
 // p = w + beta p  (row-block storage; the lower storage forms p inside the product)

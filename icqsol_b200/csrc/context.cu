@@ -7,6 +7,9 @@
 // (bem/icqLaplaceMatrices.cpp:9-30, once per pair) -- into one O(N) kernel.
 #include <stdio.h>
 
+#include <stdlib.h>
+
+#include <map>
 #include <mutex>
 
 #include "icqb_internal.cuh"
@@ -51,33 +54,113 @@ int lower_layout(icqb_ctx* ctx, LowerLayout* L) {
     return ICQB_OK;
 }
 
-static bool pool_alloc() {
-    static const bool on = [] {
-        const char* e = getenv("ICQB_POOL_ALLOC");
-        return e && e[0] == '1';
-    }();
-    return on;
+// Process-wide cache of freed device blocks, keyed by (device, size).  A process that builds one
+// solver after the other on the same mesh size (bench.py's end-to-end loop, a parameter sweep)
+// asks for the same ~20 buffers again and again; cudaMalloc / cudaFree cost 0.1-1 ms each (they
+// map and unmap memory and synchronise the device), which was ~10 % of an end-to-end step at
+// config C2.  dev_free waits for the context's stream -- every kernel that touches a context
+// buffer runs there -- and keeps the block; dev_alloc hands out a cached block of exactly the
+// requested size when there is one.  Blocks above 1 GiB, or beyond a total of
+// ICQB_ALLOC_CACHE_MB (default 2048, 0 = cache off), go back to the driver; a failed cudaMalloc
+// empties the cache and retries once.
+namespace {
+
+struct BlockCache {
+    std::mutex m;
+    std::multimap<std::pair<int, size_t>, void*> blocks;   // free blocks
+    std::map<void*, std::pair<int, size_t>> live;          // blocks handed out by dev_alloc_raw
+    size_t cached = 0;
+};
+
+BlockCache& block_cache() {
+    static BlockCache* c = new BlockCache();   // never destroyed: contexts may outlive static teardown
+    return *c;
 }
 
-cudaError_t dev_alloc_raw(icqb_ctx* ctx, void** p, size_t bytes) {
-    if (!pool_alloc()) return cudaMalloc(p, bytes);
-    static std::once_flag once;
-    std::call_once(once, [ctx] {
-        cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) {
-            unsigned long long keep = ~0ULL;   // never hand freed blocks back to the driver
-            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+size_t cache_limit_bytes() {
+    static const size_t limit = [] {
+        const char* e = getenv("ICQB_ALLOC_CACHE_MB");
+        const long long mb = e ? atoll(e) : 2048;
+        return (size_t)(mb > 0 ? mb : 0) << 20;
+    }();
+    return limit;
+}
+
+constexpr size_t kCacheMaxBlock = (size_t)1 << 30;
+
+// give every cached block of `device` (or of all devices: -1) back to the driver
+void cache_release(int device) {
+    BlockCache& C = block_cache();
+    std::lock_guard<std::mutex> lock(C.m);
+    int current = 0;
+    cudaGetDevice(&current);
+    for (auto it = C.blocks.begin(); it != C.blocks.end();) {
+        if (device >= 0 && it->first.first != device) {
+            ++it;
+            continue;
         }
-    });
-    return cudaMallocAsync(p, bytes, ctx->stream);
+        cudaSetDevice(it->first.first);
+        cudaFree(it->second);
+        C.cached -= it->first.second;
+        it = C.blocks.erase(it);
+    }
+    cudaSetDevice(current);
+}
+
+}  // namespace
+
+cudaError_t dev_alloc_raw(icqb_ctx* ctx, void** p, size_t bytes) {
+    BlockCache& C = block_cache();
+    if (bytes == 0) bytes = 8;
+    {
+        std::lock_guard<std::mutex> lock(C.m);
+        auto it = C.blocks.find({ctx->device, bytes});
+        if (it != C.blocks.end()) {
+            *p = it->second;
+            C.cached -= bytes;
+            C.blocks.erase(it);
+            C.live[*p] = {ctx->device, bytes};
+            return cudaSuccess;
+        }
+    }
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e == cudaErrorMemoryAllocation) {
+        cudaGetLastError();   // clear the sticky-free error state
+        cache_release(-1);
+        e = cudaMalloc(p, bytes);
+    }
+    if (e == cudaSuccess) {
+        std::lock_guard<std::mutex> lock(C.m);
+        C.live[*p] = {ctx->device, bytes};
+    }
+    return e;
 }
 
 void dev_free(icqb_ctx* ctx, void* p) {
     if (!p) return;
-    if (pool_alloc())
-        cudaFreeAsync(p, ctx->stream);
-    else
+    BlockCache& C = block_cache();
+    size_t bytes = 0;
+    {
+        std::lock_guard<std::mutex> lock(C.m);
+        auto it = C.live.find(p);
+        if (it != C.live.end()) {
+            bytes = it->second.second;
+            C.live.erase(it);
+        }
+    }
+    if (bytes == 0 || bytes > kCacheMaxBlock || cache_limit_bytes() == 0) {
+        cudaFree(p);   // (synchronises the device)
+        return;
+    }
+    // the block may still be in use by kernels of this context: they all run on its stream
+    if (ctx && ctx->stream) cudaStreamSynchronize(ctx->stream);
+    std::lock_guard<std::mutex> lock(C.m);
+    if (C.cached + bytes > cache_limit_bytes()) {
         cudaFree(p);
+        return;
+    }
+    C.blocks.insert({{ctx ? ctx->device : 0, bytes}, p});
+    C.cached += bytes;
 }
 
 int ensure_work(icqb_ctx* ctx, int64_t doubles) {
@@ -234,10 +317,9 @@ int icqb_destroy(icqb_ctx* ctx) {
     symv_plan_free(ctx);
     lu_free(ctx);
     free_mesh(ctx);
-    cudaFree(ctx->d_ffstats);
+    dev_free(ctx, ctx->d_ffstats);
     dev_free(ctx, ctx->d_A32);
     dev_free(ctx, ctx->d_work);
-    if (ctx->stream) cudaStreamSynchronize(ctx->stream);   // stream-ordered frees (ICQB_POOL_ALLOC)
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -249,6 +331,11 @@ int icqb_destroy(icqb_ctx* ctx) {
 const char* icqb_last_error(const icqb_ctx* ctx) {
     if (ctx) return ctx->err.c_str();
     return g_create_error.c_str();
+}
+
+int icqb_release_cached_memory(int device) {
+    cache_release(device);
+    return ICQB_OK;
 }
 
 int icqb_device(const icqb_ctx* ctx) { return ctx ? ctx->device : -1; }

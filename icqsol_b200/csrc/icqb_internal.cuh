@@ -184,11 +184,10 @@ int set_error(icqb_ctx* ctx, int code, const std::string& msg);
 int lower_layout(icqb_ctx* ctx, LowerLayout* L);
 int check_cuda(icqb_ctx* ctx, cudaError_t e, const char* what);
 int ensure_work(icqb_ctx* ctx, int64_t doubles);
-// Device buffers of the context (mesh tables, work space, product plan).  Default: cudaMalloc /
-// cudaFree.  EXPERIMENTAL, with ICQB_POOL_ALLOC=1 in the environment: cudaMallocAsync /
-// cudaFreeAsync on the context's stream from the device's default memory pool with an unlimited
-// release threshold, so that a process that builds one solver after the other (bench.py's
-// end-to-end loop) gets its ~20 buffers back from the pool instead of from the driver.
+// Device buffers of the context (mesh tables, work space, product plan): cudaMalloc behind a
+// process-wide cache of freed blocks keyed by (device, size) -- context.cu; a process that builds
+// one solver after the other gets its ~20 buffers back from the cache instead of from the driver.
+// dev_free waits for the context's stream before it keeps a block.
 cudaError_t dev_alloc_raw(icqb_ctx* ctx, void** p, size_t bytes);
 void dev_free(icqb_ctx* ctx, void* p);
 template <class T>

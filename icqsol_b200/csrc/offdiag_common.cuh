@@ -137,24 +137,36 @@ struct Tile {
     long long srcEnd; // one past the last valid source triangle of this tile's range
     int kind;         // 0 = diagonal tile, 1 = mirrored (I > J inside the block), 2 = direct only,
                       // 3 = lower storage, strictly below the diagonal tile
-                      // -1 = nothing to do
+                      // (-1 = nothing to do: no longer produced, the grids hold stored tiles only)
 };
 
 __device__ __forceinline__ Tile decode_tile(const OffDiagParams& P, long long task) {
-    Tile t;
     if (P.lower) {
-        // 2-D grid: x = global source tile J, y = local observer tile; only J <= I is stored
-        const int lt = blockIdx.y;
-        t.obs0 = P.L.obs0(lt);
-        t.obsEnd = P.L.obsEnd(lt);
-        t.lrow0 = 0;
-        const long long I = t.obs0 / kTileObs, J = blockIdx.x;
-        t.tile = P.L.tileBase(lt) + J;
-        t.src0 = J * kTileSrc;
-        t.srcEnd = (J == I) ? min(P.n, t.src0 + kTileSrc) : t.src0 + kTileSrc;
-        t.kind = (J > I) ? -1 : (J == I ? 0 : 3);
-        return t;
+        // 1-D grid over the STORED tiles only (J <= I): task = position of the tile in the local
+        // tile sequence.  Strip lt of a row block whose first tile row is I0 starts at
+        // k (I0 + 1) + k (k - 1) / 2, k = the strip's index inside its block.
+        const bool second = task >= P.L.tiles0;
+        const long long t = second ? task - P.L.tiles0 : task;
+        const long long I0 = (second ? P.L.q0 : P.L.r0) / kTileObs;
+        const double bq = 2.0 * (double)I0 + 1.0;
+        long long k = (long long)((sqrt(bq * bq + 8.0 * (double)t) - bq) * 0.5);
+        if (k < 0) k = 0;
+        while (k * (I0 + 1) + k * (k - 1) / 2 > t) --k;
+        while ((k + 1) * (I0 + 1) + (k + 1) * k / 2 <= t) ++k;
+        const int lt = (int)k + (second ? P.L.nTiles0 : 0);
+        const long long J = t - (k * (I0 + 1) + k * (k - 1) / 2);
+        Tile r;
+        r.obs0 = P.L.obs0(lt);
+        r.obsEnd = P.L.obsEnd(lt);
+        r.lrow0 = 0;
+        const long long I = r.obs0 / kTileObs;
+        r.tile = task;
+        r.src0 = J * kTileSrc;
+        r.srcEnd = (J == I) ? min(P.n, r.src0 + kTileSrc) : r.src0 + kTileSrc;
+        r.kind = (J == I) ? 0 : 3;
+        return r;
     }
+    Tile t;
     const long long nT = P.nObsTiles;
     const long long nTri = nT * (nT + 1) / 2;
     if (task < nTri) {

@@ -57,6 +57,12 @@ uint64_t icqb_stream(const icqb_ctx* ctx);
  * default stream); 0 restores the context's own. */
 int icqb_set_stream(icqb_ctx* ctx, uint64_t stream);
 int icqb_synchronize(icqb_ctx* ctx);
+/* The contexts' device buffers (mesh tables, work space, product plans) come from cudaMalloc
+ * behind a process-wide cache of freed blocks, so that building one solver after the other does
+ * not pay the driver's map/unmap each time (at most ICQB_ALLOC_CACHE_MB megabytes are kept,
+ * default 2048; 0 turns the cache off).  This call hands the cached blocks of `device` (-1: of
+ * every device) back to the driver.  No reference counterpart (host malloc/free there). */
+int icqb_release_cached_memory(int device);
 
 /* ---- mesh ------------------------------------------------------------------
  * Host arrays, copied.  Replaces the vtkPoints/vtkCellArray traversal at

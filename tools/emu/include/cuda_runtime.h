@@ -170,7 +170,7 @@ static inline double max(double a, double b) { return a > b ? a : b; }
 
 // ---- runtime API (synchronous, one "device") -------------------------------------------------
 typedef int cudaError_t;
-enum { cudaSuccess = 0, cudaErrorInvalidValue = 1 };
+enum { cudaSuccess = 0, cudaErrorInvalidValue = 1, cudaErrorMemoryAllocation = 2 };
 typedef struct emuStream* cudaStream_t;
 typedef struct emuEvent* cudaEvent_t;
 enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice,

@@ -64,6 +64,8 @@ def install():
     torch.cuda.Stream = lambda device=None: FakeStream()
     torch.cuda.stream = lambda s: contextlib.nullcontext()
     torch.cuda.Event = FakeEvent
+    torch.cuda.mem_get_info = lambda d=None: (180 << 30, 180 << 30)
+    torch.cuda.empty_cache = lambda: None
 
     def host(device):
         if device is None:
