@@ -730,9 +730,9 @@ def main():
                          "(DESIGN.md 4.6); 'block' = inverse 128x128 blocks; 'diagonal' = 1/diag")
     ap.add_argument('--block-tiles', type=int, default=DEFAULT_BLOCK_TILES,
                     help='with block+caps: 128-triangle tiles per diagonal block')
-    ap.add_argument('--assembly-variant', type=int, default=1, choices=[0, 1, 2],
+    ap.add_argument('--assembly-variant', type=int, default=1, choices=[0, 1],
                     help='arithmetic of the off-diagonal kernel (include/icqb.h, '
-                         'icqb_set_assembly_variant): 0 direct, 1 far-field split, 2 = 1 software-pipelined')
+                         'icqb_set_assembly_variant): 0 direct, 1 far-field split')
     ap.add_argument('--mixed-switch', type=float, default=0.,
                     help='with block+caps and lower storage: relative residual below '
                          'which the CG products stream a float32 copy of the matrix (1e-6); 0 = off')

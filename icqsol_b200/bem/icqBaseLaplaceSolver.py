@@ -81,8 +81,7 @@ class BaseLaplaceSolver(BaseSolver):
                        it an unconverged solve raises RuntimeError
         @param assemblyVariant arithmetic of the off-diagonal kernel (include/icqb.h,
                        icqb_set_assembly_variant): 0 = direct (k_offdiag), 1 = far-field split
-                       (k_offdiag_ff, the default: 6-8 % faster, entries within 5e-15 of 0),
-                       2 = 1 with the source-point set-up software-pipelined (same arithmetic)
+                       (k_offdiag_ff, the default: 9 % faster, entries within 5e-15 of 0)
         """
         # wall-clock marks of the host-side phases (milliseconds since construction began), for
         # the end-to-end breakdown of bench.py: hostTimings['constructor'] / ['solve']

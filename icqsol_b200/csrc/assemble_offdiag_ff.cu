@@ -113,12 +113,14 @@ constexpr int kFfBarBytes = 64;
 constexpr int kFfSmemBytes = kFfSub * kFfStageDoubles * 8 + kFfBarBytes + (kTileObs / 32) * kStWarpDoubles * 8;   // 89,216 B
 
 // well separated pair: affine observer points, origin at the observer's vertex a.
-// PIPELINED: the per-source-point work of point i1 + 1 (three shared-memory loads, then the short
-// dependent chains that form A, B, C and n_i . s') is issued inside the evaluation block of point
-// i1, where the scheduler can slot it between the sixteen independent evaluations -- with two
-// warps per scheduler (254 registers) nothing else hides that latency at the head of every
-// iteration.
-template <bool WITH_K, bool PIPELINED>
+// Software-pipelined: the per-source-point work of point i1 + 1 (three shared-memory loads, then
+// the short dependent chains that form A, B, C and n_i . s') is issued inside the evaluation
+// block of point i1, where the scheduler can slot it between the sixteen independent
+// evaluations -- with two warps per scheduler (255 registers) nothing else hides that latency
+// at the head of every iteration (B200, config C2, G+K: 50.6 -> 47.9 ms, identical entries).  The
+// loop over the source points is unrolled twice: no gain for G+K, 1.8 % for G alone (fewer
+// re-materialised constants).
+template <bool WITH_K>
 __device__ __forceinline__ PairSums pair_fast(const Obs& O, const double* __restrict__ pj,
                                               const double* __restrict__ nj,
                                               const double* __restrict__ bj) {
@@ -139,17 +141,12 @@ __device__ __forceinline__ PairSums pair_fast(const Obs& O, const double* __rest
         // mirrored entry K[j,i]: n_i . (y - a_i) = n_i . s'
         if (WITH_K) nd = fma(O.nz, sz, fma(O.ny, sy, O.nx * sx));
     };
-    if (PIPELINED) point(0, nA, nB, nC, nNd);
-#pragma unroll 1
+    point(0, nA, nB, nC, nNd);
+#pragma unroll 2
     for (int i1 = 0; i1 < kNq; ++i1) {
-        double A, B, C, nd = 0.0;
-        if (PIPELINED) {
-            A = nA, B = nB, C = nC, nd = nNd;
-            // (the last iteration re-forms point 15: one wasted set-up in sixteen, no branch)
-            point(i1 + 1 < kNq ? i1 + 1 : kNq - 1, nA, nB, nC, nNd);
-        } else {
-            point(i1, A, B, C, nd);
-        }
+        const double A = nA, B = nB, C = nC, nd = nNd;
+        // (the last iteration re-forms point 15: one wasted set-up in sixteen, no branch)
+        point(i1 + 1 < kNq ? i1 + 1 : kNq - 1, nA, nB, nC, nNd);
         const double w1 = c_triNodes[kTri8 + i1].w;
         double in[4] = {0.0, 0.0, 0.0, 0.0};
         double c3[2] = {0.0, 0.0};
@@ -259,7 +256,7 @@ __device__ __forceinline__ PairSums pair_exact(const Obs& O, const double* __res
     return S;
 }
 
-template <bool WITH_K, bool PIPELINED>
+template <bool WITH_K>
 __global__ void __launch_bounds__(kTileObs) k_offdiag_ff(const OffDiagParams P) {
     // [kFfSub] x { quadrature points 32 x 48 | bounds 32 x 8 | normals 32 x 4 }, then the barriers
     extern __shared__ __align__(128) double s_tile[];
@@ -388,7 +385,7 @@ __global__ void __launch_bounds__(kTileObs) k_offdiag_ff(const OffDiagParams P) 
             PairSums S;
             if (far) {
                 nFast += 1;
-                S = pair_fast<WITH_K, PIPELINED>(O, pj, nj, bj);
+                S = pair_fast<WITH_K>(O, pj, nj, bj);
             } else {
                 S = pair_exact<WITH_K>(O, pj, nj, bj);
             }
@@ -480,22 +477,17 @@ int launch_offdiag_ff(icqb_ctx* ctx, const OffDiagParams& params, dim3 grid, boo
     P.stats = ctx->d_ffstats;
     static bool attr = false;
     if (!attr) {
-        ICQB_CUDA(ctx, cudaFuncSetAttribute(k_offdiag_ff<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFfSmemBytes));
-        ICQB_CUDA(ctx, cudaFuncSetAttribute(k_offdiag_ff<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFfSmemBytes));
-        ICQB_CUDA(ctx, cudaFuncSetAttribute(k_offdiag_ff<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFfSmemBytes));
-        ICQB_CUDA(ctx, cudaFuncSetAttribute(k_offdiag_ff<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFfSmemBytes));
+        ICQB_CUDA(ctx, cudaFuncSetAttribute(k_offdiag_ff<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            kFfSmemBytes));
+        ICQB_CUDA(ctx, cudaFuncSetAttribute(k_offdiag_ff<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            kFfSmemBytes));
         attr = true;
     }
-    const bool pipelined = ctx->offdiag_variant == 2;
     cudaEventRecord(ctx->ev0, ctx->stream);
-    if (withK && pipelined)
-        k_offdiag_ff<true, true><<<grid, kTileObs, kFfSmemBytes, ctx->stream>>>(P);
-    else if (withK)
-        k_offdiag_ff<true, false><<<grid, kTileObs, kFfSmemBytes, ctx->stream>>>(P);
-    else if (pipelined)
-        k_offdiag_ff<false, true><<<grid, kTileObs, kFfSmemBytes, ctx->stream>>>(P);
+    if (withK)
+        k_offdiag_ff<true><<<grid, kTileObs, kFfSmemBytes, ctx->stream>>>(P);
     else
-        k_offdiag_ff<false, false><<<grid, kTileObs, kFfSmemBytes, ctx->stream>>>(P);
+        k_offdiag_ff<false><<<grid, kTileObs, kFfSmemBytes, ctx->stream>>>(P);
     cudaEventRecord(ctx->ev1, ctx->stream);
     ctx->launches += 1;
     return check_cuda(ctx, cudaGetLastError(), "k_offdiag_ff launch");
@@ -509,8 +501,8 @@ extern "C" {
 
 int icqb_set_assembly_variant(icqb_ctx* ctx, int variant) {
     if (!ctx) return ICQB_EARG;
-    if (variant < 0 || variant > 2)
-        return set_error(ctx, ICQB_EARG, "icqb_set_assembly_variant: variant must be 0, 1 or 2");
+    if (variant < 0 || variant > 1)
+        return set_error(ctx, ICQB_EARG, "icqb_set_assembly_variant: variant must be 0 or 1");
     ctx->offdiag_variant = variant;
     return ICQB_OK;
 }

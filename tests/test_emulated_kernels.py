@@ -431,7 +431,7 @@ def _assembly_stats(emu, c):
     return fast.value, allp.value
 
 
-@pytest.mark.parametrize('variant', [1, 2])
+@pytest.mark.parametrize('variant', [1])
 @pytest.mark.parametrize('with_k', [False, True])
 def test_emulated_far_field_split_full_storage(emu, oracle_mod, variant, with_k):
     """k_offdiag_ff on 576 triangles, full storage (mirrored tiles inside the block): every G
@@ -454,11 +454,11 @@ def test_emulated_far_field_split_full_storage(emu, oracle_mod, variant, with_k)
         kref = oracle_mod.k_block(c.xyz, c.tri, 0, n, 0, n)
         assert numpy.abs(k - kref).max() < 1e-12 * numpy.abs(kref).max()
         assert (numpy.diag(k) == 0.).all()
-    assert emu.icqb_set_assembly_variant(c.h, 3) != 0
+    assert emu.icqb_set_assembly_variant(c.h, 2) != 0
     c.close()
 
 
-@pytest.mark.parametrize('variant', [1, 2])
+@pytest.mark.parametrize('variant', [1])
 def test_emulated_far_field_split_lower_storage(emu, oracle_mod, variant):
     """Lower storage with two separated row blocks, G, K and the transposed K entries."""
     from icqsol_b200.bem import icqRowPartition as rp

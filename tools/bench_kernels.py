@@ -38,7 +38,7 @@ def main():
     out = {'triangles': n, 'stored_tiles': ntiles, 'assembly_ms': {}, 'far_field_fraction': {}}
     pairs = 0.5 * n * n
     keep = {}
-    for variant in (0, 1, 2):
+    for variant in (0, 1):
         ctx.check(lib.icqb_set_assembly_variant(ctx.handle, variant))
         for with_k in (False, True):
             times = []
@@ -55,10 +55,6 @@ def main():
         fast, allp = ctypes.c_int64(0), ctypes.c_int64(0)
         ctx.check(lib.icqb_assembly_stats(ctx.handle, ctypes.byref(fast), ctypes.byref(allp)))
         out['far_field_fraction'][str(variant)] = fast.value / max(allp.value, 1)
-    # variants 1 and 2 are the same arithmetic: identical matrices (NaN-free comparison of the
-    # stored tiles; the ragged edge tiles hold unspecified entries beyond n, hence nan_to_num)
-    out['variant2_equals_variant1'] = all(
-        bool(torch.equal(torch.nan_to_num(a), torch.nan_to_num(b))) for a, b in zip(keep[1], keep[2]))
     out['max_rel_diff_variant1_vs_0_G'] = float(
         (torch.nan_to_num(keep[1][0] / keep[0][0], nan=1.0, posinf=1.0, neginf=1.0) - 1.0).abs().max())
     del keep
