@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(kInvThreads) k_sweep_pivot(const DenseDesc* de
     double* s_t = s_inv;
     double* s_vec = s_inv + kT * kInvLd;
     double* g = dense + D.off + (K * kT) * D.m + K * kT;
-    double a[4][4];
+    double a[kGjRows][4];
     tile_to_regs(g, D.m, a);
     const int nweak = tile_gauss_jordan(a, s_vec);   // weak pivots are reported only
     if (nweak && weak) atomicAdd(weak, nweak);

@@ -22,7 +22,7 @@ constexpr int kGroupRows = kT / kGroups;     // 16 rows of the inverse block per
 constexpr int kVThreads = kT * kGroups;      // 1024
 static_assert(kGroups == 8, "k_cg_resid joins exactly eight groups");
 constexpr long long kBlockElems = (long long)kT * kT;
-constexpr int kInvThreads = 1024;
+constexpr int kInvThreads = 512;
 constexpr int kInvLd = kT + 1;               // padded row of the in-shared-memory inversion
 constexpr int kInvSmem = (kT * kInvLd + 5 * kT) * 8;   // 137,216 B: staging tile + published vectors
 
@@ -103,116 +103,131 @@ __global__ void __launch_bounds__(256) k_cg_blocks_full(const double* A, long lo
     }
 }
 
-// Gauss-Jordan inverse (no pivoting) of a 128 x 128 tile held in REGISTERS: 1,024 threads, thread
-// (ty = warp, tx = lane) owns the 4 x 4 sub-block rows 4 ty.., columns 4 tx...  Per pivot k the
+// Gauss-Jordan inverse (no pivoting) of a 128 x 128 tile held in REGISTERS: 512 threads, thread
+// (ty = warp, tx = lane) owns the 8 x 4 sub-block rows 8 ty.., columns 4 tx...  Per pivot k the
 // warp that owns row k publishes the scaled pivot row (pivinv at position k), one lane per warp
-// publishes its four entries of column k, and after ONE barrier every thread does its 16 DFMAs
+// publishes its eight entries of column k, and after ONE barrier every thread does its 32 DFMAs
 // from registers (the two published vectors are double-buffered by the parity of k, so the
-// next pivot's writers cannot overtake this pivot's readers).  The first version kept the tile
-// in shared memory and moved 4 shared-memory words per DFMA: 2.8 us per pivot, 354 us per tile
-// (ncu, round 2); this one is bound by the barrier and the row warp's division.
+// next pivot's writers cannot overtake this pivot's readers).  The position of row / column k
+// inside the owners' sub-blocks is a compile-time constant (eight instantiations of the pivot
+// step), so no register is ever selected at run time.  The first version kept the tile in shared
+// memory and moved 4 shared-memory words per DFMA: 2.8 us per pivot, 354 us per tile (ncu,
+// round 2); this one is bound by the barrier and the row warp's division.
 // s_vec: [2][2][128] doubles (row / column, two parities) + [128] original diagonal.
-// Returns the number of weak pivots seen by this thread's warp (lane 0 of the row warps only).
-constexpr int kGjVecDoubles = 5 * kT;
-__device__ __forceinline__ int tile_gauss_jordan(double (&a)[4][4], double* s_vec) {
+// Returns the number of weak pivots seen by this thread (lane 0 of the row warps only).
+constexpr int kGjRows = 8;
+constexpr int kGjThreads = (kT / kGjRows) * 32;   // 512
+static_assert(kInvThreads == kGjThreads, "the tile inversion kernels are launched with kInvThreads");
+
+template <int J>   // k = 8 kw + J
+__device__ __forceinline__ void tile_gj_pivot(double (&a)[kGjRows][4], double* s_vec, int kw, int tx, int ty,
+                                              int& nweak) {
+    constexpr int KC = J & 3;                 // column k inside its owner's four columns
+    const int k = kGjRows * kw + J;
+    const int lk = 2 * kw + (J >> 2);         // the lane that owns column k
+    const double* s_diag = s_vec + 4 * kT;
+    double* s_row = s_vec + (J & 1) * 2 * kT;   // parity of k
+    double* s_col = s_row + kT;
+    if (ty == kw) {   // the warp that owns row k
+        const double piv = __shfl_sync(0xffffffffu, a[J][KC], lk);
+        // a pivot that is not finite, or has lost 13 digits against the diagonal entry it
+        // started from, is reported (the caller decides what to do with the tile)
+        if (tx == 0 && (!(fabs(piv) >= 1e-13 * fabs(s_diag[k])) || !(fabs(piv) <= 1.0e300))) ++nweak;
+        const double pivinv = 1.0 / piv;
+        double o[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) o[c] = a[J][c] * pivinv;
+        if (tx == lk) o[KC] = pivinv;
+        double2* dst = reinterpret_cast<double2*>(s_row + 4 * tx);
+        dst[0] = make_double2(o[0], o[1]);
+        dst[1] = make_double2(o[2], o[3]);
+    }
+    if (tx == lk) {   // one lane per warp owns eight entries of column k
+        double2* dst = reinterpret_cast<double2*>(s_col + kGjRows * ty);
+#pragma unroll
+        for (int r = 0; r < kGjRows; r += 2) dst[r >> 1] = make_double2(a[r][KC], a[r + 1][KC]);
+    }
+    __syncthreads();
+    double rs[4], cs[kGjRows];
+    {
+        const double2 r01 = *reinterpret_cast<const double2*>(s_row + 4 * tx);
+        const double2 r23 = *reinterpret_cast<const double2*>(s_row + 4 * tx + 2);
+        rs[0] = r01.x; rs[1] = r01.y; rs[2] = r23.x; rs[3] = r23.y;
+    }
+#pragma unroll
+    for (int r = 0; r < kGjRows; r += 2) {
+        const double2 c2 = *reinterpret_cast<const double2*>(s_col + kGjRows * ty + r);
+        cs[r] = c2.x;
+        cs[r + 1] = c2.y;
+    }
+#pragma unroll
+    for (int r = 0; r < kGjRows; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) a[r][c] = fma(-cs[r], rs[c], a[r][c]);
+    if (tx == lk) {   // column k: -a_ik / pivot  (rs[KC] of this lane is 1 / pivot)
+#pragma unroll
+        for (int r = 0; r < kGjRows; ++r) a[r][KC] = -cs[r] * rs[KC];
+    }
+    if (ty == kw) {   // row k: the scaled pivot row, 1 / pivot on the diagonal
+#pragma unroll
+        for (int c = 0; c < 4; ++c) a[J][c] = rs[c];
+    }
+}
+
+__device__ __forceinline__ int tile_gauss_jordan(double (&a)[kGjRows][4], double* s_vec) {
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     double* s_diag = s_vec + 4 * kT;
-    if (tx == ty) {
+    // the diagonal entries of rows 8 ty .. 8 ty + 7 sit in lanes 2 ty (rows 0-3) and 2 ty + 1
+    if (tx == 2 * ty) {
 #pragma unroll
-        for (int r = 0; r < 4; ++r) s_diag[4 * ty + r] = a[r][r];
+        for (int r = 0; r < 4; ++r) s_diag[kGjRows * ty + r] = a[r][r];
+    }
+    if (tx == 2 * ty + 1) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) s_diag[kGjRows * ty + 4 + r] = a[4 + r][r];
     }
     __syncthreads();
     int nweak = 0;
-    for (int k = 0; k < kT; ++k) {
-        const int kw = k >> 2, kr = k & 3;
-        double* s_row = s_vec + (k & 1) * 2 * kT;
-        double* s_col = s_row + kT;
-        if (ty == kw) {
-            double rk[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-            for (int r = 0; r < 4; ++r)
-                if (r == kr) {
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) rk[c] = a[r][c];
-                }
-            double pv = rk[0];
-#pragma unroll
-            for (int c = 1; c < 4; ++c)
-                if (c == kr) pv = rk[c];
-            const double piv = __shfl_sync(0xffffffffu, pv, kw);
-            // a pivot that is not finite, or has lost 13 digits against the diagonal entry it
-            // started from, is reported (the caller decides what to do with the tile)
-            if (tx == 0 && (!(fabs(piv) >= 1e-13 * fabs(s_diag[k])) || !(fabs(piv) <= 1.0e300))) ++nweak;
-            const double pivinv = 1.0 / piv;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) s_row[4 * tx + c] = (4 * tx + c == k) ? pivinv : rk[c] * pivinv;
-        }
-        if (tx == kw) {
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                double v = a[r][0];
-#pragma unroll
-                for (int c = 1; c < 4; ++c)
-                    if (c == kr) v = a[r][c];
-                s_col[4 * ty + r] = v;
-            }
-        }
-        __syncthreads();
-        double rs[4], cs[4];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) rs[c] = s_row[4 * tx + c];
-#pragma unroll
-        for (int r = 0; r < 4; ++r) cs[r] = s_col[4 * ty + r];
-        const double pivinv = s_row[k];
-#pragma unroll
-        for (int r = 0; r < 4; ++r)
-#pragma unroll
-            for (int c = 0; c < 4; ++c) a[r][c] = fma(-cs[r], rs[c], a[r][c]);
-        if (tx == kw) {   // column k: -a_ik / pivot
-#pragma unroll
-            for (int r = 0; r < 4; ++r)
-#pragma unroll
-                for (int c = 0; c < 4; ++c)
-                    if (c == kr) a[r][c] = -cs[r] * pivinv;
-        }
-        if (ty == kw) {   // row k: the scaled pivot row, 1 / pivot on the diagonal
-#pragma unroll
-            for (int r = 0; r < 4; ++r)
-                if (r == kr) {
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) a[r][c] = rs[c];
-                }
-        }
+#pragma unroll 1
+    for (int kw = 0; kw < kT / kGjRows; ++kw) {
+        tile_gj_pivot<0>(a, s_vec, kw, tx, ty, nweak);
+        tile_gj_pivot<1>(a, s_vec, kw, tx, ty, nweak);
+        tile_gj_pivot<2>(a, s_vec, kw, tx, ty, nweak);
+        tile_gj_pivot<3>(a, s_vec, kw, tx, ty, nweak);
+        tile_gj_pivot<4>(a, s_vec, kw, tx, ty, nweak);
+        tile_gj_pivot<5>(a, s_vec, kw, tx, ty, nweak);
+        tile_gj_pivot<6>(a, s_vec, kw, tx, ty, nweak);
+        tile_gj_pivot<7>(a, s_vec, kw, tx, ty, nweak);
     }
     return nweak;
 }
 
-// tile (row pitch ld) <-> the threads' 4 x 4 sub-blocks: a warp moves one row of 1 KB at a time
-__device__ __forceinline__ void tile_to_regs(const double* g, long long ld, double (&a)[4][4]) {
+// tile (row pitch ld) <-> the threads' 8 x 4 sub-blocks: a warp moves one row of 1 KB at a time
+__device__ __forceinline__ void tile_to_regs(const double* g, long long ld, double (&a)[kGjRows][4]) {
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        const double2* src = reinterpret_cast<const double2*>(g + (long long)(4 * ty + r) * ld + 4 * tx);
+    for (int r = 0; r < kGjRows; ++r) {
+        const double2* src = reinterpret_cast<const double2*>(g + (long long)(kGjRows * ty + r) * ld + 4 * tx);
         const double2 lo = src[0], hi = src[1];
         a[r][0] = lo.x; a[r][1] = lo.y; a[r][2] = hi.x; a[r][3] = hi.y;
     }
 }
 
 // symmetrised store: out = (a + a^T) / 2 through a [128][129] staging tile in shared memory
-__device__ __forceinline__ void regs_to_tile_symmetric(const double (&a)[4][4], double* s_t, double* g,
+__device__ __forceinline__ void regs_to_tile_symmetric(const double (&a)[kGjRows][4], double* s_t, double* g,
                                                        long long ld) {
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
+    for (int r = 0; r < kGjRows; ++r)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) s_t[(4 * ty + r) * kInvLd + 4 * tx + c] = a[r][c];
+        for (int c = 0; c < 4; ++c) s_t[(kGjRows * ty + r) * kInvLd + 4 * tx + c] = a[r][c];
     __syncthreads();
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
+    for (int r = 0; r < kGjRows; ++r) {
         double o[4];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) o[c] = 0.5 * (a[r][c] + s_t[(4 * tx + c) * kInvLd + 4 * ty + r]);
-        double2* dst = reinterpret_cast<double2*>(g + (long long)(4 * ty + r) * ld + 4 * tx);
+        for (int c = 0; c < 4; ++c) o[c] = 0.5 * (a[r][c] + s_t[(4 * tx + c) * kInvLd + kGjRows * ty + r]);
+        double2* dst = reinterpret_cast<double2*>(g + (long long)(kGjRows * ty + r) * ld + 4 * tx);
         dst[0] = make_double2(o[0], o[1]);
         dst[1] = make_double2(o[2], o[3]);
     }
@@ -233,7 +248,7 @@ __global__ void __launch_bounds__(kInvThreads) k_cg_invert_blocks(double* blocks
     __shared__ int s_broken;
     double* g = blocks + (long long)blockIdx.x * kBlockElems;
     if (threadIdx.x == 0) s_broken = 0;
-    double a[4][4];
+    double a[kGjRows][4];
     tile_to_regs(g, kT, a);
     const int nweak = tile_gauss_jordan(a, s_vec);
     if (nweak) s_broken = 1;
