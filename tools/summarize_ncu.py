@@ -60,6 +60,19 @@ def kernels(path):
             if m in hdr:
                 i = hdr.index(m)
                 print('{0:<70s} {1:<16s} {2}'.format(m, units[i], r[i]))
+        # warp-state sampling: where the warps wait (share of the samples)
+        stalls = []
+        for i, name in enumerate(hdr):
+            if 'pcsamp_warps_issue_stalled_' in name and not name.endswith('_not_issued'):
+                try:
+                    stalls.append((float(r[i]), name.split('pcsamp_warps_issue_stalled_')[1]))
+                except ValueError:
+                    pass
+        tot = sum(v for v, _ in stalls)
+        if tot > 0:
+            top = sorted(stalls, reverse=True)[:6]
+            print('{0:<70s} {1:<16s} {2}'.format('warp samples by state', '%', ', '.join(
+                '{0} {1:.1f}'.format(nm, 100. * v / tot) for v, nm in top)))
         print()
 
 
