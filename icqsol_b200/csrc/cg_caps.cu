@@ -1,15 +1,14 @@
-// EXPERIMENTAL solver (written after round 1's GPU budget was spent: never run on a GPU,
-// checked in the CPU emulation of the test suite, tools/emu; reached only with preconditioner
-// kind 2; its GPU tests run only with ICQB_EXPERIMENTAL=1): conjugate gradient with DENSE
-// DIAGONAL BLOCKS of several 128-row tiles in the block preconditioner.
+// The solver behind icqb_cg_solve_dev for preconditioner kind 2 (the default of the solver
+// classes; validated on B200 in round 2 up to 199,808 triangles on 8 GPUs): conjugate gradient
+// with DENSE DIAGONAL BLOCKS of several 128-row tiles in the block preconditioner.
 //
 // Why: (1) neighbouring sliver triangles (the rings at the poles of a UV sphere) make the
 // reference's diag(A) G indefinite -- the wrong-sign eigenvectors live entirely on those
 // rings -- and the CG of cg.cu with 128 x 128 blocks then does not
-// converge; with ONE dense block over the leading sliver tiles and one over the trailing
-// ones ("caps") it converges in ~110 iterations in the numpy model
-// (tools/experiments/pcg_cap_blocks.py).  (2) On regular meshes larger blocks simply pay:
-// 92 iterations instead of 167 at config C2 with blocks of 8 tiles
+// converge; with ONE dense block over every run of sliver tiles (on a UV sphere the leading
+// and the trailing tiles, "caps") it converges: 171 iterations at 100,488 triangles, 273 at
+// 199,808 (tools/experiments/pcg_cap_blocks.py for the model).  (2) On regular meshes larger
+// blocks simply pay: 91 iterations instead of 165 at config C2 with blocks of 8 tiles
 // (tools/experiments/pcg_block_size.py).
 //
 // Same algorithm, state and product kernels as cg.cu (solvers/icqConjugateGradient.py:49-79);
@@ -17,16 +16,16 @@
 //   * the tile rows are partitioned into diagonal blocks (icqb_cg_set_block_partition, or two
 //     caps around single tiles, icqb_cg_set_cap_tiles); blocks of one tile use the 128 x 128
 //     inverses of cg.cu; every larger block is extracted from the stored tiles as a dense
-//     matrix of diag(s) A (lower storage: symmetric fill), all-reduced over the ranks, inverted
-//     in place by a block Gauss-Jordan (128^3 tile products, all blocks batched in a launch)
-//     and symmetrised -- once per solve;
+//     matrix of diag(s) A (lower storage: symmetric fill) by the rank that holds its rows (or
+//     all-reduced when it straddles ranks), inverted in place by a symmetric block sweep (below;
+//     all blocks batched in a launch) -- once per solve;
 //   * per iteration the residual kernel is split in two so that the dense blocks can be
 //     applied in between:
 //         k_cg_vec       x += alpha p, r -= alpha z            (all rows)
 //         k_dense_apply  w = C^-1 r on the rows of the dense blocks (one warp per row)
 //         k_cg_close     w = M^-1 r on the single tiles, rho, norms, beta, stopping flag.
 //
-// The same experimental solver carries the PEER EXCHANGE (several ranks, lower storage, when
+// The same solver carries the optional PEER EXCHANGE (several ranks, lower storage, when
 // icqb_peer_create/attach have been called): k_symv_reduce<PEER> stores the partial product
 // and its p.z into every rank's exchange buffer and raises a flag there; k_peer_gather waits
 // for the P flags of the product's sequence number and adds the P slots in rank order -- no

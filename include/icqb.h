@@ -128,9 +128,10 @@ int icqb_assemble_lower_dev(icqb_ctx* ctx, int diag_order, uint64_t dG, uint64_t
  * each stored entry once (4 N^2 bytes instead of 8 N^2) and all-reduces the partial
  * vectors over the ranks.  x, y: device double[ntri], replicated.  Blocking. */
 int icqb_symv_dev(icqb_ctx* ctx, uint64_t dA, uint64_t dx, uint64_t dy, int scaled);
-/* EXPERIMENTAL (emulated only): the same product on a float32 copy of the stored tiles (made
- * by the call; the timed part is the product alone) -- the kernel behind the mixed-precision
- * CG (icqb_cg_set_mixed_precision); the result is G32 x with all sums in double. */
+/* The same product on a float32 copy of the stored tiles (made by the call; the timed part is
+ * the product alone) -- the kernel behind the optional mixed-precision CG
+ * (icqb_cg_set_mixed_precision); the result is G32 x with all sums in double.  B200: 4.6 TB/s
+ * of float32 entries (tests/test_gpu_parity.py::test_float32_product_kernel). */
 int icqb_symv_f32_dev(icqb_ctx* ctx, uint64_t dA, uint64_t dx, uint64_t dy, int scaled);
 
 /* Host-buffer forms (blocking; host<->device copies inside the call).
@@ -158,13 +159,14 @@ int icqb_gemv_host(icqb_ctx* ctx, uint64_t dA, int64_t nrows, int64_t ncols, int
 
 /* Arithmetic of the off-diagonal assembly (bem/icqLaplaceMatrices.cpp:75-101,
  * bem/icqQuadrature.cpp:232-243).
- *   variant 0  (default) direct: every evaluation from the reference's rounded quadrature
- *              points, 12 (G) / 16 (G+K) FP64 instructions per evaluation;
- *   variant 1  far-field split: pairs of triangles with |c_i - c_j| >= 3 (rho_i + rho_j)
+ *   variant 0  direct (what a new context uses): every evaluation from the reference's rounded
+ *              quadrature points, 12 (G) / 16 (G+K) FP64 instructions per evaluation;
+ *   variant 1  (what the solver classes and bench.py select) far-field split: pairs of
+ *              triangles with |c_i - c_j| >= 3 (rho_i + rho_j)
  *              (centroids, radii) use the affine form of the observer points about the
  *              observer's own vertex, 9 / 13 instructions per evaluation, entries within a
- *              few ulp of variant 0 (5e-15 on a B200, tests/test_gpu_parity.py); all other
- *              pairs are evaluated as in variant 0.
+ *              few ulp of variant 0 (1.2e-15 on a B200, tests/test_gpu_parity.py); all other
+ *              pairs are evaluated as in variant 0.  9 % faster at config C2 (G+K).
  * (Round 1's variants 2-4 -- a Newton step in the reciprocal square root, three CTAs per SM --
  * were measured on a B200 in round 2 and removed: the Newton step left 3.3e-13, too close to the
  * 1e-12 contract, and three CTAs per SM were slower.)
@@ -211,35 +213,43 @@ int icqb_cg_solve_dev(icqb_ctx* ctx, uint64_t dA, int64_t n, int64_t ld, int sto
  *           (extracted from the matrix, all-reduced over the ranks, inverted and applied on
  *           the device).  Consecutive triangles are neighbours on the surface, so the blocks
  *           hold the strongest couplings: 2-3x fewer iterations on the refined spheres.
- * A new context uses kind 0.  The solver classes of the Python layer select kind 1. */
+ *   kind 2  as kind 1, with the tile rows partitioned into larger diagonal blocks
+ *           (icqb_cg_set_block_partition / icqb_cg_set_cap_tiles below): what the solver classes
+ *           of the Python layer select (dense blocks over the runs of sliver tiles, blocks of 8
+ *           tiles elsewhere).
+ * A new context uses kind 0. */
 int icqb_cg_set_preconditioner(icqb_ctx* ctx, int kind);
-/* EXPERIMENTAL (kind 2, written at the end of round 1 without GPU access, tests gated by
- * ICQB_EXPERIMENTAL=1): as kind 1, but the first `head_tiles` and the last `tail_tiles`
- * 128-row tiles each form ONE dense diagonal block.  Neighbouring sliver triangles make the
- * reference's diag(area) G indefinite and the wrong-sign eigenvectors live on those
- * triangles; a dense block over them restores the convergence of the
- * CG in the numpy model.  With kind 2 and no cap tiles the solve is the one of kind 1. */
+/* Kind 2: as kind 1, but the first `head_tiles` and the last `tail_tiles` 128-row tiles each
+ * form ONE dense diagonal block.  Neighbouring sliver triangles make the reference's
+ * diag(area) G indefinite and the wrong-sign eigenvectors live on those triangles (DESIGN.md
+ * section 4.6); a dense block over them restores the convergence of the CG (B200: the
+ * 100,488- and 199,808-triangle UV spheres converge in 171 / 273 iterations; with 128 x 128
+ * blocks they do not converge at all).  With kind 2 and no cap tiles the solve is the one of
+ * kind 1. */
 int icqb_cg_set_cap_tiles(icqb_ctx* ctx, int64_t head_tiles, int64_t tail_tiles);
-/* EXPERIMENTAL (kind 2): the general form -- diagonal block q of the preconditioner covers the
- * 128-row tiles [starts[q], starts[q+1]) (the last one up to the end), starts[0] = 0, at most
- * 64 tiles per block; blocks of one tile use the 128 x 128 inverses of kind 1, larger ones are
- * extracted as dense matrices, inverted by a block Gauss-Jordan on the device and applied by a
- * batched product.  In the numpy model blocks of 8 tiles need 92 iterations instead of 167 at
- * config C2.  nblocks = 0 clears the partition (icqb_cg_set_cap_tiles then applies). */
+/* Kind 2, the general form -- diagonal block q of the preconditioner covers the 128-row tiles
+ * [starts[q], starts[q+1]) (the last one up to the end), starts[0] = 0, at most 64 tiles per
+ * block; blocks of one tile use the 128 x 128 inverses of kind 1, larger ones are extracted as
+ * dense matrices, inverted by a symmetric block sweep on the device (csrc/cg_caps.cu) and
+ * applied by a batched product.  Blocks of 8 tiles need 91 iterations instead of 165 at config
+ * C2 (B200).  With several ranks, blocks that end at the ranks' row-block boundaries are
+ * extracted, inverted and applied by the rank that holds their rows.  nblocks = 0 clears the
+ * partition (icqb_cg_set_cap_tiles then applies). */
 int icqb_cg_set_block_partition(icqb_ctx* ctx, const int64_t* starts, int64_t nblocks);
 /* Statistics of the last icqb_cg_solve_dev: how often the recurrence residual was replaced
  * by the true residual b - A x (0 = the first confirmation passed), and how many matrix
  * products were enqueued (iterations + confirmations + the ones skipped behind the stop
  * flag). */
 int icqb_cg_last_stats(const icqb_ctx* ctx, int64_t* replacements, int64_t* products);
-/* EXPERIMENTAL (kind 2, lower storage; emulated only): mixed-precision products.  Once the
+/* Optional, off by default (kind 2, lower storage): mixed-precision products.  Once the
  * recurrence residual max|b - A x| falls below switch_rel * max|b| the products of the
  * iteration stream a float32 copy of the stored tiles (half the bytes; converted once per
  * solve, 2 N^2 more bytes of HBM over all ranks) -- a direction that small tolerates a product
  * accurate to 6e-8 (inexact Krylov); the solve still ends with the double-precision residual
  * b - A x, and if that misses the tolerance it continues in double precision only.  In the
  * numpy model switch_rel = 1e-6 saves 25-28 % of the matrix traffic at an unchanged 5e-13
- * backward error.  0 (default) = off. */
+ * backward error (GPU test: tests/test_gpu_parity.py::test_mixed_precision_cg).  0 (default)
+ * = off: the bench and the solver classes compute in double precision throughout. */
 int icqb_cg_set_mixed_precision(icqb_ctx* ctx, double switch_rel);
 /* Preconditioner set-up of the last solve: 128 x 128 blocks whose inversion met a pivot that was
  * not finite or had lost 13 digits (replaced by 1/diag), and weak pivots met while inverting the
@@ -279,13 +289,14 @@ int icqb_comm_init(icqb_ctx* ctx, const void* unique_id_128, int rank, int nrank
  * (communicator creation costs ~1 s; solvers are created many times). */
 int icqb_comm_share(icqb_ctx* ctx, icqb_ctx* owner);
 int icqb_comm_rank(const icqb_ctx* ctx, int* rank, int* nranks);
-/* EXPERIMENTAL (written without GPU access; checked in the CPU emulation of the test suite
- * with one rank per thread): peer exchange for the CG product of the lower storage.  Each rank
+/* Optional peer exchange for the CG product of the lower storage (validated on 4 and 8 B200
+ * in round 2: same iterations and solutions as the NCCL path, 0.4 % faster -- so the NCCL
+ * all-reduce stays the default; the Python layer attaches it with ICQB_PEER_EXCHANGE=1).  Each rank
  * allocates an exchange buffer for vectors of up to max_n entries (icqb_peer_create returns
  * its 64-byte cudaIpcMemHandle_t), the caller all-gathers the handles and passes the
- * nranks*64 bytes to icqb_peer_attach on every rank.  The experimental solver (preconditioner
- * kind 2) then replaces the per-iteration NCCL all-reduce by stores into the peers' buffers
- * from k_symv_reduce and a gather kernel (csrc/cg_caps.cu). */
+ * nranks*64 bytes to icqb_peer_attach on every rank.  The solver of preconditioner kind 2
+ * then replaces the per-iteration NCCL all-reduce by stores into the peers' buffers from
+ * k_symv_reduce and a gather kernel (csrc/cg_caps.cu). */
 int icqb_peer_create(icqb_ctx* ctx, int64_t max_n, void* handle64);
 int icqb_peer_attach(icqb_ctx* ctx, const void* handles);
 
