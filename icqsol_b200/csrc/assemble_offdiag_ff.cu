@@ -174,16 +174,18 @@ __device__ __forceinline__ PairSums pair_fast(const Obs& O, const double* __rest
         const double e0 = fma(njz, O.az - bj[6], fma(njy, O.ay - bj[5], njx * (O.ax - bj[4])));
         const double nb = fma(njz, O.b2z, fma(njy, O.b2y, njx * O.b2x));
         const double nc = fma(njz, O.c2z, fma(njy, O.c2y, njx * O.c2x));
-        double sk[4] = {0.0, 0.0, 0.0, 0.0};   // four chains instead of sixteen dependent DFMAs
+        // sum_k w_k (e0 - (xi_k nb + eta_k nc) / 2) R_k as three moment sums of the row sums R_k
+        // with literal weights (w_k, w_k xi_k, w_k eta_k): 3 DFMA per node instead of 5 instructions
+        double m0[2] = {0.0, 0.0}, m1[2] = {0.0, 0.0}, m2[2] = {0.0, 0.0};
 #define ICQB_FF_K(K, XI, ETA, W)                                   \
     {                                                              \
-        const double t = fma(XI, nb, ETA * nc);                    \
-        const double nd = fma(-0.5, t, e0);                        \
-        sk[K & 3] = fma(W * nd, r3row[K], sk[K & 3]);              \
+        m0[K & 1] = fma(W, r3row[K], m0[K & 1]);                   \
+        m1[K & 1] = fma(W * XI, r3row[K], m1[K & 1]);              \
+        m2[K & 1] = fma(W * ETA, r3row[K], m2[K & 1]);             \
     }
         ICQB_TRI8(ICQB_FF_K)
 #undef ICQB_FF_K
-        S.k = (sk[0] + sk[1]) + (sk[2] + sk[3]);
+        S.k = fma(e0, m0[0] + m0[1], -0.5 * fma(nb, m1[0] + m1[1], nc * (m2[0] + m2[1])));
     }
     return S;
 }

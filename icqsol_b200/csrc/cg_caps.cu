@@ -659,6 +659,152 @@ __global__ void __launch_bounds__(kVThreads) k_cg_close(int mode, int k, int rep
     }
 }
 
+// One kernel instead of k_cg_vec + k_dense_apply + k_cg_close for an iteration of the common
+// case (one rank, every tile in a dense block): CTA = kUpRows consecutive rows of one block.
+//   * every CTA forms r_new = r_old - alpha z for the COLUMNS of its block in shared memory (the
+//     multiplied vector of the block product; r is double-buffered by the parity of the
+//     iteration, so no CTA reads entries another one has already replaced) and writes back x
+//     and r_new for its own rows;
+//   * each warp streams its rows of the inverse block against that vector, two rows at a time
+//     (16 loads of 16 bytes in flight per lane), w = C^-1 r_new;
+//   * partials of rho = r.w, |r/s|^2, max|r/s| per CTA; the CTA that finishes last adds them in
+//     a fixed order and closes the iteration exactly as k_cg_close does.
+// Columns of a block beyond n multiply zeros (the vector is zero-filled up to m; the inverse of
+// the identity-padded block is finite there), so the inner loop has no bounds checks.
+constexpr int kUpRows = 32;
+constexpr int kUpThreads = 256;
+
+__device__ __forceinline__ void up_row_pair(const double* __restrict__ rowA, const double* __restrict__ rowB,
+                                            const double* s_r, long long m, int lane, double& outA,
+                                            double& outB) {
+    double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+    long long c = 2 * lane;
+    for (; c + 7 * 64 < m; c += 8 * 64) {
+        double2 va[8], vb[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            va[u] = __ldcs(reinterpret_cast<const double2*>(rowA + c + 64 * u));
+            vb[u] = __ldcs(reinterpret_cast<const double2*>(rowB + c + 64 * u));
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const double2 x = *reinterpret_cast<const double2*>(s_r + c + 64 * u);
+            a0 = fma(va[u].x, x.x, a0);
+            a1 = fma(va[u].y, x.y, a1);
+            b0 = fma(vb[u].x, x.x, b0);
+            b1 = fma(vb[u].y, x.y, b1);
+        }
+    }
+    for (; c < m; c += 64) {
+        const double2 va = __ldcs(reinterpret_cast<const double2*>(rowA + c));
+        const double2 vb = __ldcs(reinterpret_cast<const double2*>(rowB + c));
+        const double2 x = *reinterpret_cast<const double2*>(s_r + c);
+        a0 = fma(va.x, x.x, a0);
+        a1 = fma(va.y, x.y, a1);
+        b0 = fma(vb.x, x.x, b0);
+        b1 = fma(vb.y, x.y, b1);
+    }
+    double sa = a0 + a1, sb = b0 + b1;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        sa += __shfl_xor_sync(0xffffffffu, sa, off);
+        sb += __shfl_xor_sync(0xffffffffu, sb, off);
+    }
+    outA = sa;
+    outB = sb;
+}
+
+__global__ void __launch_bounds__(kUpThreads) k_cg_update_dense(const DenseDesc* desc, int nblocks,
+                                                                const double* dense, int k, double* x, CgBuf B,
+                                                                const double* r_old, double* r_new,
+                                                                double* part) {
+    extern __shared__ __align__(16) double s_r[];   // [m of the largest block]
+    __shared__ double s_w[kUpRows];
+    __shared__ double s_fin[3 * kUpThreads];
+    __shared__ int s_last;
+    CgState* S = B.state;
+    if (S->done) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long cr0 = (long long)blockIdx.x * kUpRows;
+    int b = 0;
+    while (b + 1 < nblocks && desc[b + 1].row0 <= cr0) ++b;
+    const DenseDesc D = desc[b];
+    const long long lr0 = cr0 - D.row0, g0 = D.t0 * kT, m = D.m, valid = D.valid;
+    const double alpha = S->rho[k & 1] / *B.pz;
+    for (long long c = tid; c < m; c += kUpThreads)
+        s_r[c] = (c < valid) ? fma(-alpha, B.z[g0 + c], r_old[g0 + c]) : 0.0;
+    __syncthreads();
+    if (tid < kUpRows && lr0 + tid < valid) {
+        const long long i = g0 + lr0 + tid;
+        x[i] = fma(alpha, B.p[i], x[i]);
+        r_new[i] = s_r[lr0 + tid];
+    }
+    const double* inv = dense + D.off;
+#pragma unroll
+    for (int q = 0; q < kUpRows / 8; q += 2) {
+        const int lw = warp * (kUpRows / 8) + q;            // local rows lw, lw + 1 of this CTA
+        const long long lrA = lr0 + lw, lrB = lrA + 1;
+        if (lrA < valid) {                                   // warp-uniform
+            const long long rb = lrB < valid ? lrB : lrA;    // (a ragged last row: multiply row A twice)
+            double wa, wb;
+            up_row_pair(inv + lrA * m, inv + rb * m, s_r, m, lane, wa, wb);
+            if (lane == 0) {
+                B.w[g0 + lrA] = wa;
+                s_w[lw] = wa;
+                if (lrB < valid) {
+                    B.w[g0 + lrB] = wb;
+                    s_w[lw + 1] = wb;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (warp == 0) {
+        double rw = 0.0, r2 = 0.0, rm = 0.0;
+        const long long lr = lr0 + lane;
+        if (lr < valid) {
+            const double r = s_r[lr];
+            const double ru = r / B.s[g0 + lr];
+            rw = r * s_w[lane];
+            r2 = ru * ru;
+            rm = fabs(ru);
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            rw += __shfl_xor_sync(0xffffffffu, rw, off);
+            r2 += __shfl_xor_sync(0xffffffffu, r2, off);
+            rm = fmax(rm, __shfl_xor_sync(0xffffffffu, rm, off));
+        }
+        if (lane == 0) {
+            const long long nP = gridDim.x;
+            part[blockIdx.x] = rw;
+            part[nP + blockIdx.x] = r2;
+            part[2 * nP + blockIdx.x] = rm;
+            s_last = take_ticket(&S->ticket_res, gridDim.x) ? 1 : 0;
+        }
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const int nP = (int)gridDim.x;
+    double rho = 0.0, res2 = 0.0, resmax = 0.0;
+    final_reduce3(part, part + nP, part + 2 * nP, nP, s_fin, tid, kUpThreads, &rho, &res2, &resmax);
+    if (tid == 0) {
+        S->rho[(k + 1) & 1] = rho;
+        S->beta = rho / S->rho[k & 1];
+        S->res2 = res2;
+        S->resmax = resmax;
+        S->iters += 1;
+        if ((S->use_max ? resmax : res2) <= S->thr) S->done = 1;
+        if (S->lowp) S->n32 += 1;
+        if (S->switch_thr > 0.0 && resmax <= S->switch_thr) S->lowp = 1;
+        S->skip64 = S->done | S->lowp;
+        S->skip32 = S->done | (S->lowp ^ 1);
+        S->ticket_res = 0;
+        __threadfence();
+    }
+}
+
 }  // namespace
 
 int cg_solve_caps(icqb_ctx* ctx, uint64_t dA_, int64_t n, int64_t ld, int storage,
@@ -799,8 +945,22 @@ int cg_solve_caps(icqb_ctx* ctx, uint64_t dA_, int64_t n, int64_t ld, int storag
     const long long stateDoubles = (sizeof(CgState) + 7) / 8;
     const long long small = 8 * n + 8 + nfull + 6 * nT + stateDoubles;
     const long long panelDoubles = 2 * kT * denseRowsPad;   // V and W panels of the block sweep
+    // The fused update kernel (k_cg_update_dense) serves the common case: one rank, every tile in
+    // a dense block, and only the last block ragged (its CTAs never straddle two blocks).
+    bool fusedUpdate = (P == 1) && nDense > 0;
+    for (long long t = 0; t < nT && fusedUpdate; ++t) fusedUpdate = htile[(size_t)t] >= 0;
+    for (int q = 0; q + 1 < nDense && fusedUpdate; ++q) fusedUpdate = hdesc[(size_t)q].valid == hdesc[(size_t)q].m;
+    {
+        static const bool off = [] {
+            const char* e = getenv("ICQB_CG_UNFUSED");   // debugging aid: the three-kernel update
+            return e && e[0] == '1';
+        }();
+        if (off) fusedUpdate = false;
+    }
+    const long long nUpd = (denseRows + kUpRows - 1) / kUpRows;
+    const long long updDoubles = fusedUpdate ? 3 * nUpd : 0;
     const long long need = small + nT * kBlockElems + denseDoubles + panelDoubles + descDoubles + tileDoubles +
-                           gatherDoubles + gdescDoubles + 68;
+                           gatherDoubles + gdescDoubles + updDoubles + 68;
     int rc = ensure_work(ctx, need);
     if (rc != ICQB_OK) return rc;
     CgBuf B;
@@ -811,7 +971,7 @@ int cg_solve_caps(icqb_ctx* ctx, uint64_t dA_, int64_t n, int64_t ld, int storag
     B.z = wp; wp += n + 8;
     B.minv = wp; wp += n;
     B.s = wp; wp += n;
-    wp += n;   // (diag(A) slot of cg.cu, unused here)
+    double* r_alt = wp; wp += n;   // second residual buffer of the fused update (cg.cu keeps diag(A) here)
     double* inv_area = wp; wp += n;
     double* gathered = wp; wp += nfull;
     B.part_rw = wp; wp += nT;
@@ -831,6 +991,20 @@ int cg_solve_caps(icqb_ctx* ctx, uint64_t dA_, int64_t n, int64_t ld, int storag
     double* wsend = wp; wp += sharded ? slot : 0;
     double* wrecv = wp; wp += sharded ? (long long)P * slot : 0;
     GatherDesc* dgather = reinterpret_cast<GatherDesc*>(wp); wp += gdescDoubles;
+    double* updPart = wp; wp += updDoubles;
+    double* rbuf[2] = {B.r, fusedUpdate ? r_alt : B.r};
+    // the residual of iteration k lives in rbuf[k & 1] (fused update: double-buffered)
+    auto atIter = [&](long long kq) {
+        CgBuf c = B;
+        c.r = rbuf[kq & 1];
+        return c;
+    };
+    size_t updSmem = 0;
+    if (fusedUpdate) {
+        updSmem = sizeof(double) * (size_t)(kMaxTiles * kT);
+        ICQB_CUDA(ctx, cudaFuncSetAttribute(k_cg_update_dense, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)updSmem));
+    }
     B.Minv = blocks;
     B.n = n;
 
@@ -882,6 +1056,7 @@ int cg_solve_caps(icqb_ctx* ctx, uint64_t dA_, int64_t n, int64_t ld, int storag
 
     // w = M^-1 r and the closing step, after r has been updated by k_cg_vec
     auto precondition = [&](int mode, int kk, int replace, const int* skipFlag) -> int {
+        const CgBuf B = atIter(kk);   // (shadows the solver's: the residual buffer of iteration kk)
         const bool needW = (mode != kTrue) || replace;
         if (needW && denseRows > 0) {
             k_dense_apply<<<(unsigned)((denseRows + 7) / 8), 256, 0, st>>>(ddesc, nDense, denseRows, dense,
@@ -946,9 +1121,16 @@ int cg_solve_caps(icqb_ctx* ctx, uint64_t dA_, int64_t n, int64_t ld, int storag
                 k_cg_dot<<<vgrid, kT, 0, st>>>(B);
                 ctx->launches += 1;
             }
-            k_cg_vec<<<vgrid, kT, 0, st>>>(kUpdate, kk, 0, b, scale, x, B);
-            ctx->launches += 1;
-            r2 = precondition(kUpdate, kk, 0, skip);
+            if (fusedUpdate) {
+                k_cg_update_dense<<<(unsigned)nUpd, kUpThreads, updSmem, st>>>(
+                    ddesc, nDense, dense, kk, x, B, rbuf[kk & 1], rbuf[(kk + 1) & 1], updPart);
+                ctx->launches += 1;
+                r2 = check_cuda(ctx, cudaGetLastError(), "k_cg_update_dense launch");
+            } else {
+                k_cg_vec<<<vgrid, kT, 0, st>>>(kUpdate, kk, 0, b, scale, x, B);
+                ctx->launches += 1;
+                r2 = precondition(kUpdate, kk, 0, skip);
+            }
             if (r2 != ICQB_OK) return r2;
         }
         ICQB_CUDA(ctx, cudaGetLastError());
@@ -1052,7 +1234,7 @@ int cg_solve_caps(icqb_ctx* ctx, uint64_t dA_, int64_t n, int64_t ld, int storag
 
         // z = s * (A x0); r, w, rho_0 and the norms of b
         CG_TRY(mv.apply(x, B.z, scale, st));
-        k_cg_vec<<<vgrid, kT, 0, st>>>(kInit, 0, 0, b, scale, x, B);
+        k_cg_vec<<<vgrid, kT, 0, st>>>(kInit, 0, 0, b, scale, x, atIter(0));
         ctx->launches += 1;
         CG_TRY(precondition(kInit, 0, 0, nullptr));
 
@@ -1076,7 +1258,7 @@ int cg_solve_caps(icqb_ctx* ctx, uint64_t dA_, int64_t n, int64_t ld, int storag
                 CG_TRY(mv.apply(x, B.z, nullptr, st));
                 const bool last = (k >= maxit) || replacements >= 8;
                 const int kk = (int)(k & 0x3fffffff);
-                k_cg_vec<<<vgrid, kT, 0, st>>>(kTrue, kk, last ? 0 : 1, b, scale, x, B);
+                k_cg_vec<<<vgrid, kT, 0, st>>>(kTrue, kk, last ? 0 : 1, b, scale, x, atIter(kk));
                 ctx->launches += 1;
                 CG_TRY(precondition(kTrue, kk, last ? 0 : 1, nullptr));
                 CG_TRY(read_state(ctx, B.state, &hs));
