@@ -148,13 +148,14 @@ __device__ __forceinline__ PairSums pair_fast(const Obs& O, const double* __rest
         // (the last iteration re-forms point 15: one wasted set-up in sixteen, no branch)
         point(i1 + 1 < kNq ? i1 + 1 : kNq - 1, nA, nB, nC, nNd);
         const double w1 = c_triNodes[kTri8 + i1].w;
-        double in[4] = {0.0, 0.0, 0.0, 0.0};
+        double in[2] = {0.0, 0.0};   // two chains of eight: enough with sixteen evaluations in flight
         double c3[2] = {0.0, 0.0};
 #define ICQB_FF_EVAL(K, XI, ETA, W)                                            \
     {                                                                          \
-        const double r2 = fma(XI, B, fma(ETA, C, A + O.q[K]));                 \
+        /* fma(XI, B, A) is shared by the nodes with the same xi (10 distinct values) */ \
+        const double r2 = fma(ETA, C, fma(XI, B, A) + O.q[K]);                 \
         const double ri = rsqrt_1ulp(r2);                                      \
-        in[K & 3] = fma(W, ri, in[K & 3]);                                     \
+        in[K & 1] = fma(W, ri, in[K & 1]);                                     \
         if (WITH_K) {                                                          \
             const double r3 = ri * ri * ri;                                    \
             r3row[K] = fma(w1, r3, r3row[K]);                                  \
@@ -163,9 +164,9 @@ __device__ __forceinline__ PairSums pair_fast(const Obs& O, const double* __rest
     }
         ICQB_TRI8(ICQB_FF_EVAL)
 #undef ICQB_FF_EVAL
-        const double in0 = in[0], in1 = in[1], in2 = in[2], in3 = in[3];
+        const double in0 = in[0], in1 = in[1];
         const double c30 = c3[0], c31 = c3[1];
-        S.g = fma(w1, (in0 + in1) + (in2 + in3), S.g);
+        S.g = fma(w1, in0 + in1, S.g);
         if (WITH_K) S.km = fma(w1 * nd, c30 + c31, S.km);
     }
     if (WITH_K) {

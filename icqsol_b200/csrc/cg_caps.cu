@@ -1038,10 +1038,22 @@ int cg_solve_caps(icqb_ctx* ctx, uint64_t dA_, int64_t n, int64_t ld, int storag
 
     cudaEvent_t evTotal0 = ctx->ev0, evTotal1 = ctx->ev1;
     cudaEvent_t evg0[2] = {nullptr, nullptr}, evg1[2] = {nullptr, nullptr}, evb[2] = {nullptr, nullptr};
-    for (int q = 0; q < 2; ++q) {
-        ICQB_CUDA(ctx, cudaEventCreate(&evg0[q]));
-        ICQB_CUDA(ctx, cudaEventCreate(&evg1[q]));
-        ICQB_CUDA(ctx, cudaEventCreateWithFlags(&evb[q], cudaEventDisableTiming));
+    {
+        // (created together: a failure leaves nothing behind)
+        cudaError_t ee = cudaSuccess;
+        for (int q = 0; q < 2 && ee == cudaSuccess; ++q) {
+            ee = cudaEventCreate(&evg0[q]);
+            if (ee == cudaSuccess) ee = cudaEventCreate(&evg1[q]);
+            if (ee == cudaSuccess) ee = cudaEventCreateWithFlags(&evb[q], cudaEventDisableTiming);
+        }
+        if (ee != cudaSuccess) {
+            for (int q = 0; q < 2; ++q) {
+                if (evg0[q]) cudaEventDestroy(evg0[q]);
+                if (evg1[q]) cudaEventDestroy(evg1[q]);
+                if (evb[q]) cudaEventDestroy(evb[q]);
+            }
+            return check_cuda(ctx, ee, "cudaEventCreate");
+        }
     }
     double gemv_ms = 0.0;
     long long gemv_count = 0;
@@ -1251,7 +1263,10 @@ int cg_solve_caps(icqb_ctx* ctx, uint64_t dA_, int64_t n, int64_t ld, int storag
         k_cg_state<<<1, 1, 0, st>>>(B.state, 0, 0, thr_dev, use_max ? 1 : 0, 1);
         k_cg_mixed<<<1, 1, 0, st>>>(B.state, mixed ? ctx->mixed_switch * hs.bmax : 0.0);
         ctx->launches += 2;
-        const long long batch = 8;
+        // iterations enqueued per host check, two batches in flight.  Behind the stop flag the
+        // kernels of the remaining ones return at once but the collectives of several ranks
+        // still run: smaller batches there (at most 7 wasted iterations instead of 15).
+        const long long batch = (P > 1) ? 4 : 8;
 
         while (true) {
             if (err <= thr || k >= maxit) {
