@@ -14,8 +14,8 @@
 // Same algorithm, state and product kernels as cg.cu (solvers/icqConjugateGradient.py:49-79);
 // what differs is the preconditioner step w = M^-1 r:
 //   * the tile rows are partitioned into diagonal blocks (icqb_cg_set_block_partition, or two
-//     caps around single tiles, icqb_cg_set_cap_tiles); blocks of one tile use the 128 x 128
-//     inverses of cg.cu; every larger block is extracted from the stored tiles as a dense
+//     caps around single tiles, icqb_cg_set_cap_tiles); every block -- a single tile included --
+//     is extracted from the stored tiles as a dense
 //     matrix of diag(s) A (lower storage: symmetric fill) by the rank that holds its rows (or
 //     all-reduced when it straddles ranks), inverted in place by a symmetric block sweep (below;
 //     all blocks batched in a launch) -- once per solve;
@@ -174,17 +174,35 @@ constexpr int kSwM = 128, kSwN = 64, kSwK = 16;
 constexpr int kSwLdB = kSwN;       // (no padding: 2 x 16 x (128 + 64) doubles are the 48 KB of static shared memory)
 
 __global__ void __launch_bounds__(kInvThreads) k_sweep_pivot(const DenseDesc* desc, double* dense,
-                                                             long long K, int* weak) {
+                                                             long long K, int* weak, int* bad) {
     extern __shared__ double s_inv[];
     const DenseDesc D = desc[blockIdx.z];
     if (K >= D.tiles) return;
     double* s_t = s_inv;
     double* s_vec = s_inv + kT * kInvLd;
     double* g = dense + D.off + (K * kT) * D.m + K * kT;
+    __shared__ int s_bad;
+    if (threadIdx.x == 0) s_bad = 0;   // (tile_gauss_jordan begins with a barrier)
     double a[kGjRows][4];
     tile_to_regs(g, D.m, a);
-    const int nweak = tile_gauss_jordan(a, s_vec);   // weak pivots are reported only
-    if (nweak && weak) atomicAdd(weak, nweak);
+    const int nweak = tile_gauss_jordan(a, s_vec);
+    if (D.tiles == 1) {
+        // a block of one tile: as k_cg_invert_blocks -- a weak pivot would give a huge, indefinite
+        // "inverse", so the block falls back to 1/diag and is counted (icqb_cg_last_blocks)
+        if (nweak) s_bad = 1;
+        __syncthreads();
+        if (s_bad) {
+            const double* s_diag = s_vec + 4 * kT;
+            for (int e = threadIdx.x; e < kT * kT; e += kInvThreads) {
+                const int i = e >> 7, j = e & (kT - 1);
+                g[(long long)i * D.m + j] = (i == j) ? 1.0 / s_diag[i] : 0.0;
+            }
+            if (threadIdx.x == 0 && bad) atomicAdd(bad, 1);
+            return;
+        }
+    } else if (nweak && weak) {
+        atomicAdd(weak, nweak);   // inside a larger block weak pivots are reported only
+    }
     regs_to_tile_symmetric(a, s_t, g, D.m);
 }
 
@@ -421,6 +439,17 @@ __global__ void __launch_bounds__(kT) k_dense_mirror(const DenseDesc* desc, doub
     a[i * D.m + j] = a[j * D.m + i];
 }
 
+// the block that holds compact row cr (row0 ascending): binary search -- a partition into single
+// tiles has as many blocks as tile rows
+__device__ __forceinline__ int find_block(const DenseDesc* desc, int nblocks, long long cr) {
+    int lo = 0, hi = nblocks - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (desc[mid].row0 <= cr) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
 // w = C^-1 r on the rows of the dense blocks: HBM-bound (the inverse blocks are streamed once
 // per iteration: 1024 * blockTiles * N bytes).  One warp per (valid) row; a lane reads 16-byte
 // pairs of the row, 64 columns apart, eight of them in flight before the first is used (a
@@ -435,9 +464,7 @@ __global__ void __launch_bounds__(256) k_dense_apply(const DenseDesc* desc, int 
     const int lane = threadIdx.x & 31;
     const long long cr = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (cr >= totalRows) return;   // whole warp
-    int b = 0;
-    while (b + 1 < nblocks && desc[b + 1].row0 <= cr) ++b;
-    const DenseDesc D = desc[b];
+    const DenseDesc D = desc[find_block(desc, nblocks, cr)];
     const long long lr = cr - D.row0, g0 = D.t0 * kT;
     const double* row = dense + D.off + lr * D.m;   // 16-byte aligned: D.off and D.m are even
     const double* xv = x + g0;
@@ -726,9 +753,7 @@ __global__ void __launch_bounds__(kUpThreads) k_cg_update_dense(const DenseDesc*
     if (S->done) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long cr0 = (long long)blockIdx.x * kUpRows;
-    int b = 0;
-    while (b + 1 < nblocks && desc[b + 1].row0 <= cr0) ++b;
-    const DenseDesc D = desc[b];
+    const DenseDesc D = desc[find_block(desc, nblocks, cr0)];
     const long long lr0 = cr0 - D.row0, g0 = D.t0 * kT, m = D.m, valid = D.valid;
     const double alpha = S->rho[k & 1] / *B.pz;
     for (long long c = tid; c < m; c += kUpThreads)
@@ -846,7 +871,7 @@ int cg_solve_caps(icqb_ctx* ctx, uint64_t dA_, int64_t n, int64_t ld, int storag
     std::vector<int> htile((size_t)nT, -1);
     for (size_t q = 0; q < starts.size(); ++q) {
         const long long t0 = starts[q], t1 = (q + 1 < starts.size()) ? starts[q + 1] : nT;
-        if (t1 - t0 <= 1) continue;      // single tiles use the 128 x 128 inverse blocks
+        // (single tiles are dense blocks of one tile: same extraction, inversion and product)
         for (long long t = t0; t < t1; ++t) htile[(size_t)t] = (int)ranges.size();
         ranges.push_back({t0, t1});
     }
@@ -959,7 +984,7 @@ int cg_solve_caps(icqb_ctx* ctx, uint64_t dA_, int64_t n, int64_t ld, int storag
     }
     const long long nUpd = (denseRows + kUpRows - 1) / kUpRows;
     const long long updDoubles = fusedUpdate ? 3 * nUpd : 0;
-    const long long need = small + nT * kBlockElems + denseDoubles + panelDoubles + descDoubles + tileDoubles +
+    const long long need = small + denseDoubles + panelDoubles + descDoubles + tileDoubles +
                            gatherDoubles + gdescDoubles + updDoubles + 68;
     int rc = ensure_work(ctx, need);
     if (rc != ICQB_OK) return rc;
@@ -981,8 +1006,7 @@ int cg_solve_caps(icqb_ctx* ctx, uint64_t dA_, int64_t n, int64_t ld, int storag
     B.part_b = wp; wp += nT;
     B.part_pz = wp; wp += nT;
     B.state = reinterpret_cast<CgState*>(wp); wp += stateDoubles;
-    if ((reinterpret_cast<uintptr_t>(wp) & 15) != 0) wp += 1;   // tile_to_regs moves 16-byte pairs
-    double* blocks = wp; wp += nT * kBlockElems;
+    double* blocks = nullptr;   // (the 128 x 128 inverses of cg.cu: not used by this solver)
     if ((reinterpret_cast<uintptr_t>(wp) & 15) != 0) wp += 1;   // k_dense_apply reads 16-byte pairs
     double* dense = wp; wp += denseDoubles;
     double* panels = wp; wp += panelDoubles;
@@ -1166,28 +1190,11 @@ int cg_solve_caps(icqb_ctx* ctx, uint64_t dA_, int64_t n, int64_t ld, int storag
             k_recip<<<128, 256, 0, st>>>(ctx->d_area2, inv_area, n);
             ctx->launches += 1;
         }
-        // tables of the partition first: tile -> dense block (or -1: single tile)
+        // table of the partition: tile -> dense block (every tile belongs to one; blocks of a
+        // single tile are dense blocks like the others, so the 128 x 128 set of cg.cu is not built)
         CG_CUDA(cudaMemcpyAsync(dtile, htile.data(), sizeof(int) * (size_t)nT, cudaMemcpyHostToDevice, st));
-        // 128 x 128 blocks (used by the single tiles of the partition), as in cg.cu; skipped
-        // altogether when every tile belongs to a dense block (the default partition at C2)
-        bool singles = false;
-        for (long long t = 0; t < nT; ++t) singles = singles || htile[(size_t)t] < 0;
-        if (singles) {
-            if (storage == 1)
-                k_cg_blocks_lower<<<vgrid, 256, 0, st>>>(A, L, scale, n, blocks);
-            else
-                k_cg_blocks_full<<<vgrid, 256, 0, st>>>(A, ld, mv.r0, mv.r1, scale, n, blocks);
-            ctx->launches += 1;
-            CG_CUDA(cudaGetLastError());
-            CG_TRY(comm_allreduce_sum(ctx, blocks, nT * kBlockElems, st));
-            CG_CUDA(cudaFuncSetAttribute(k_cg_invert_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         kInvSmem));
-            k_cg_invert_blocks<<<vgrid, kInvThreads, kInvSmem, st>>>(blocks, &B.state->bad_blocks, dtile);
-            ctx->launches += 1;
-            CG_CUDA(cudaGetLastError());
-        }
 
-        // tables of the dense blocks, then: extract, all-reduce, block Gauss-Jordan, symmetrise
+        // tables of the dense blocks, then: extract, all-reduce (replicated ones), block sweep, mirror
         if (sharded)
             CG_CUDA(cudaMemcpyAsync(dgather, hgather.data(), sizeof(GatherDesc) * hgather.size(),
                                     cudaMemcpyHostToDevice, st));
@@ -1216,8 +1223,8 @@ int cg_solve_caps(icqb_ctx* ctx, uint64_t dA_, int64_t n, int64_t ld, int storag
             const long long mMax = kMaxTiles * kT;
             const unsigned pairs2 = (unsigned)(kMaxTiles * (kMaxTiles - 1));   // pairs x two column halves
             for (long long K = 0; K < kMaxTiles; ++K) {
-                k_sweep_pivot<<<dim3(1, 1, (unsigned)nDense), kInvThreads, kInvSmem, st>>>(ddesc, dense, K,
-                                                                                          &B.state->weak_pivots);
+                k_sweep_pivot<<<dim3(1, 1, (unsigned)nDense), kInvThreads, kInvSmem, st>>>(
+                    ddesc, dense, K, &B.state->weak_pivots, &B.state->bad_blocks);
                 k_sweep_panel<<<dim3((unsigned)(mMax / kSwN), 1, (unsigned)nDense), 128, 0, st>>>(ddesc, dense, panels,
                                                                                                 K);
                 if (pairs2 > 0)
