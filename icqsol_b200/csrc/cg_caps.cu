@@ -698,14 +698,15 @@ __global__ void __launch_bounds__(kVThreads) k_cg_close(int mode, int k, int rep
 //     a fixed order and closes the iteration exactly as k_cg_close does.
 // Columns of a block beyond n multiply zeros (the vector is zero-filled up to m; the inverse of
 // the identity-padded block is finite there), so the inner loop has no bounds checks.
-constexpr int kUpRows = 32;
+constexpr int kUpRows = 16;      // two rows per warp: 1,244 CTAs at config C2 (2.8 waves of 3 CTAs per SM;
+                                 // with 32 rows the 622 CTAs made 1.4 waves and the second one ran half empty)
 constexpr int kUpThreads = 256;
+static_assert(kUpRows == 2 * (kUpThreads / 32), "every warp multiplies one pair of rows; warp 0 closes the CTA's rows");
 
+// two rows of an inverse block against the staged vector, columns [c, m) of this lane's pairs:
+// eight 16-byte loads per row in flight
 __device__ __forceinline__ void up_row_pair(const double* __restrict__ rowA, const double* __restrict__ rowB,
-                                            const double* s_r, long long m, int lane, double& outA,
-                                            double& outB) {
-    double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
-    long long c = 2 * lane;
+                                            const double* s_r, long long m, long long c, double (&acc)[4]) {
     for (; c + 7 * 64 < m; c += 8 * 64) {
         double2 va[8], vb[8];
 #pragma unroll
@@ -716,29 +717,21 @@ __device__ __forceinline__ void up_row_pair(const double* __restrict__ rowA, con
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const double2 x = *reinterpret_cast<const double2*>(s_r + c + 64 * u);
-            a0 = fma(va[u].x, x.x, a0);
-            a1 = fma(va[u].y, x.y, a1);
-            b0 = fma(vb[u].x, x.x, b0);
-            b1 = fma(vb[u].y, x.y, b1);
+            acc[0] = fma(va[u].x, x.x, acc[0]);
+            acc[1] = fma(va[u].y, x.y, acc[1]);
+            acc[2] = fma(vb[u].x, x.x, acc[2]);
+            acc[3] = fma(vb[u].y, x.y, acc[3]);
         }
     }
     for (; c < m; c += 64) {
         const double2 va = __ldcs(reinterpret_cast<const double2*>(rowA + c));
         const double2 vb = __ldcs(reinterpret_cast<const double2*>(rowB + c));
         const double2 x = *reinterpret_cast<const double2*>(s_r + c);
-        a0 = fma(va.x, x.x, a0);
-        a1 = fma(va.y, x.y, a1);
-        b0 = fma(vb.x, x.x, b0);
-        b1 = fma(vb.y, x.y, b1);
+        acc[0] = fma(va.x, x.x, acc[0]);
+        acc[1] = fma(va.y, x.y, acc[1]);
+        acc[2] = fma(vb.x, x.x, acc[2]);
+        acc[3] = fma(vb.y, x.y, acc[3]);
     }
-    double sa = a0 + a1, sb = b0 + b1;
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        sa += __shfl_xor_sync(0xffffffffu, sa, off);
-        sb += __shfl_xor_sync(0xffffffffu, sb, off);
-    }
-    outA = sa;
-    outB = sb;
 }
 
 __global__ void __launch_bounds__(kUpThreads) k_cg_update_dense(const DenseDesc* desc, int nblocks,
@@ -755,6 +748,25 @@ __global__ void __launch_bounds__(kUpThreads) k_cg_update_dense(const DenseDesc*
     const long long cr0 = (long long)blockIdx.x * kUpRows;
     const DenseDesc D = desc[find_block(desc, nblocks, cr0)];
     const long long lr0 = cr0 - D.row0, g0 = D.t0 * kT, m = D.m, valid = D.valid;
+    // this warp's two rows; their first 512 columns are requested BEFORE the vector is staged, so
+    // that the matrix loads are already in flight while the CTA forms r_new
+    const double* inv = dense + D.off;
+    const int lw = 2 * warp;
+    const long long lrA = lr0 + lw, lrB = lrA + 1;
+    const bool active = lrA < valid;                              // warp-uniform
+    const long long rb = lrB < valid ? lrB : lrA;                 // (a ragged last row: row A twice)
+    const double* rowA = inv + (active ? lrA : 0) * m;
+    const double* rowB = inv + (active ? rb : 0) * m;
+    const long long c0 = 2 * lane;
+    const bool head = active && (c0 + 7 * 64 < m);               // uniform: m is a multiple of 128
+    double2 va[8], vb[8];
+    if (head) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            va[u] = __ldcs(reinterpret_cast<const double2*>(rowA + c0 + 64 * u));
+            vb[u] = __ldcs(reinterpret_cast<const double2*>(rowB + c0 + 64 * u));
+        }
+    }
     const double alpha = S->rho[k & 1] / *B.pz;
     for (long long c = tid; c < m; c += kUpThreads)
         s_r[c] = (c < valid) ? fma(-alpha, B.z[g0 + c], r_old[g0 + c]) : 0.0;
@@ -764,22 +776,33 @@ __global__ void __launch_bounds__(kUpThreads) k_cg_update_dense(const DenseDesc*
         x[i] = fma(alpha, B.p[i], x[i]);
         r_new[i] = s_r[lr0 + tid];
     }
-    const double* inv = dense + D.off;
+    if (active) {
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        long long c = c0;
+        if (head) {
 #pragma unroll
-    for (int q = 0; q < kUpRows / 8; q += 2) {
-        const int lw = warp * (kUpRows / 8) + q;            // local rows lw, lw + 1 of this CTA
-        const long long lrA = lr0 + lw, lrB = lrA + 1;
-        if (lrA < valid) {                                   // warp-uniform
-            const long long rb = lrB < valid ? lrB : lrA;    // (a ragged last row: multiply row A twice)
-            double wa, wb;
-            up_row_pair(inv + lrA * m, inv + rb * m, s_r, m, lane, wa, wb);
-            if (lane == 0) {
-                B.w[g0 + lrA] = wa;
-                s_w[lw] = wa;
-                if (lrB < valid) {
-                    B.w[g0 + lrB] = wb;
-                    s_w[lw + 1] = wb;
-                }
+            for (int u = 0; u < 8; ++u) {
+                const double2 xv = *reinterpret_cast<const double2*>(s_r + c0 + 64 * u);
+                acc[0] = fma(va[u].x, xv.x, acc[0]);
+                acc[1] = fma(va[u].y, xv.y, acc[1]);
+                acc[2] = fma(vb[u].x, xv.x, acc[2]);
+                acc[3] = fma(vb[u].y, xv.y, acc[3]);
+            }
+            c += 8 * 64;
+        }
+        up_row_pair(rowA, rowB, s_r, m, c, acc);
+        double wa = acc[0] + acc[1], wb = acc[2] + acc[3];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            wa += __shfl_xor_sync(0xffffffffu, wa, off);
+            wb += __shfl_xor_sync(0xffffffffu, wb, off);
+        }
+        if (lane == 0) {
+            B.w[g0 + lrA] = wa;
+            s_w[lw] = wa;
+            if (lrB < valid) {
+                B.w[g0 + lrB] = wb;
+                s_w[lw + 1] = wb;
             }
         }
     }
@@ -787,7 +810,7 @@ __global__ void __launch_bounds__(kUpThreads) k_cg_update_dense(const DenseDesc*
     if (warp == 0) {
         double rw = 0.0, r2 = 0.0, rm = 0.0;
         const long long lr = lr0 + lane;
-        if (lr < valid) {
+        if (lane < kUpRows && lr < valid) {
             const double r = s_r[lr];
             const double ru = r / B.s[g0 + lr];
             rw = r * s_w[lane];
