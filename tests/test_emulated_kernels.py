@@ -400,6 +400,28 @@ def test_emulated_ranks_without_rows(emu, oracle_mod):
         o[-1].close()
 
 
+def test_emulated_block_cache_between_contexts(emu, oracle_mod):
+    """The contexts' device buffers come from a process-wide cache of freed blocks
+    (csrc/context.cu): a second solver of the same size gets the first one's blocks back, stale
+    contents included.  Two different meshes of the same size, one after the other, each checked
+    against the oracle; then the same again after icqb_release_cached_memory."""
+    from icqsol_b200.mesh.generators import uvSphere
+    emu.icqb_release_cached_memory.argtypes = [ctypes.c_int]
+    emu.icqb_release_cached_memory.restype = ctypes.c_int
+    for sweep in range(2):
+        for radius in (1.0, 1.7):
+            c = Ctx(emu, 12, 7)
+            xyz, tri = uvSphere(radius, 12, 7)
+            c.xyz, c.tri = numpy.ascontiguousarray(xyz), numpy.ascontiguousarray(tri)
+            c.check(emu.icqb_set_mesh(c.h, dp(c.xyz), c.xyz.shape[0], lp(c.tri), c.n))
+            ref = oracle_mod.green_matrix(c.xyz, c.tri, 5)
+            (g,) = c.assemble_lower()
+            x, iters, rinf, b = c.solve(g, 1, 2, starts=[0])
+            assert numpy.abs(b - ref.dot(x)).max() <= 1e-12 * numpy.abs(b).max()
+            c.close()
+        assert emu.icqb_release_cached_memory(-1) == 0
+
+
 @pytest.mark.parametrize('starts,storage', [([0, 2], 1), ([0, 3], 1), ([0, 1, 3], 0), ([0], 1), ([0], 0)])
 def test_emulated_block_partition(emu, oracle_mod, starts, storage):
     """EXPERIMENTAL: an explicit partition of the tile rows into diagonal blocks -- batched
