@@ -692,46 +692,52 @@ __global__ void __launch_bounds__(kVThreads) k_cg_close(int mode, int k, int rep
 //     multiplied vector of the block product; r is double-buffered by the parity of the
 //     iteration, so no CTA reads entries another one has already replaced) and writes back x
 //     and r_new for its own rows;
-//   * each warp multiplies one row of the inverse block with that vector, w = C^-1 r_new; the
-//     row's first 1,024 columns (16 loads of 16 bytes per lane) are requested before the vector is
-//     staged, so a CTA has one memory phase, not three;
+//   * each warp streams its rows of the inverse block against that vector, two rows at a time
+//     (16 loads of 16 bytes in flight per lane), w = C^-1 r_new;
 //   * partials of rho = r.w, |r/s|^2, max|r/s| per CTA; the CTA that finishes last adds them in
 //     a fixed order and closes the iteration exactly as k_cg_close does.
 // Columns of a block beyond n multiply zeros (the vector is zero-filled up to m; the inverse of
 // the identity-padded block is finite there), so the inner loop has no bounds checks.
-constexpr int kUpRows = 8;       // one row per warp: 2,485 CTAs at config C2 (with 32 rows per CTA the 622
-                                 // CTAs made 1.4 waves and the second one ran half empty)
+constexpr int kUpRows = 16;      // two rows per warp: 1,244 CTAs at config C2 (2.8 waves of 3 CTAs per SM;
+                                 // with 32 rows the 622 CTAs made 1.4 waves and the second one ran half empty)
 constexpr int kUpThreads = 256;
-constexpr int kUpAhead = 16;     // 16-byte loads a lane has in flight: a whole row of a 1,024-column block
-static_assert(kUpRows == kUpThreads / 32, "every warp multiplies one row; warp 0 closes the CTA's rows");
+static_assert(kUpRows == 2 * (kUpThreads / 32), "every warp multiplies one pair of rows; warp 0 closes the CTA's rows");
 
-// one row of an inverse block against the staged vector, columns [c, m) of this lane's pairs:
-// eight 16-byte loads in flight
-__device__ __forceinline__ void up_row(const double* __restrict__ row, const double* s_r, long long m,
-                                       long long c, double (&acc)[4]) {
+// two rows of an inverse block against the staged vector, columns [c, m) of this lane's pairs:
+// eight 16-byte loads per row in flight
+__device__ __forceinline__ void up_row_pair(const double* __restrict__ rowA, const double* __restrict__ rowB,
+                                            const double* s_r, long long m, long long c, double (&acc)[4]) {
     for (; c + 7 * 64 < m; c += 8 * 64) {
-        double2 v[8];
+        double2 va[8], vb[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = __ldcs(reinterpret_cast<const double2*>(row + c + 64 * u));
+        for (int u = 0; u < 8; ++u) {
+            va[u] = __ldcs(reinterpret_cast<const double2*>(rowA + c + 64 * u));
+            vb[u] = __ldcs(reinterpret_cast<const double2*>(rowB + c + 64 * u));
+        }
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const double2 x = *reinterpret_cast<const double2*>(s_r + c + 64 * u);
-            acc[(2 * u) & 3] = fma(v[u].x, x.x, acc[(2 * u) & 3]);
-            acc[(2 * u + 1) & 3] = fma(v[u].y, x.y, acc[(2 * u + 1) & 3]);
+            acc[0] = fma(va[u].x, x.x, acc[0]);
+            acc[1] = fma(va[u].y, x.y, acc[1]);
+            acc[2] = fma(vb[u].x, x.x, acc[2]);
+            acc[3] = fma(vb[u].y, x.y, acc[3]);
         }
     }
     for (; c < m; c += 64) {
-        const double2 v = __ldcs(reinterpret_cast<const double2*>(row + c));
+        const double2 va = __ldcs(reinterpret_cast<const double2*>(rowA + c));
+        const double2 vb = __ldcs(reinterpret_cast<const double2*>(rowB + c));
         const double2 x = *reinterpret_cast<const double2*>(s_r + c);
-        acc[0] = fma(v.x, x.x, acc[0]);
-        acc[1] = fma(v.y, x.y, acc[1]);
+        acc[0] = fma(va.x, x.x, acc[0]);
+        acc[1] = fma(va.y, x.y, acc[1]);
+        acc[2] = fma(vb.x, x.x, acc[2]);
+        acc[3] = fma(vb.y, x.y, acc[3]);
     }
 }
 
-__global__ void __launch_bounds__(kUpThreads, 3) k_cg_update_dense(const DenseDesc* desc, int nblocks,
+__global__ void __launch_bounds__(kUpThreads) k_cg_update_dense(const DenseDesc* desc, int nblocks,
                                                                 const double* dense, int k, double* x, CgBuf B,
                                                                 const double* r_old, double* r_new,
-                                                                double* part, const int* ctaBlock) {
+                                                                double* part) {
     extern __shared__ __align__(16) double s_r[];   // [m of the largest block]
     __shared__ double s_w[kUpRows];
     __shared__ double s_fin[3 * kUpThreads];
@@ -740,20 +746,26 @@ __global__ void __launch_bounds__(kUpThreads, 3) k_cg_update_dense(const DenseDe
     if (S->done) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long cr0 = (long long)blockIdx.x * kUpRows;
-    const DenseDesc D = desc[ctaBlock[blockIdx.x]];   // (host table: no search at the head of the CTA)
+    const DenseDesc D = desc[find_block(desc, nblocks, cr0)];
     const long long lr0 = cr0 - D.row0, g0 = D.t0 * kT, m = D.m, valid = D.valid;
-    // this warp's row; its first 1,024 columns are requested BEFORE the vector is staged, so
+    // this warp's two rows; their first 512 columns are requested BEFORE the vector is staged, so
     // that the matrix loads are already in flight while the CTA forms r_new
     const double* inv = dense + D.off;
-    const long long lrA = lr0 + warp;
+    const int lw = 2 * warp;
+    const long long lrA = lr0 + lw, lrB = lrA + 1;
     const bool active = lrA < valid;                              // warp-uniform
-    const double* row = inv + (active ? lrA : 0) * m;
+    const long long rb = lrB < valid ? lrB : lrA;                 // (a ragged last row: row A twice)
+    const double* rowA = inv + (active ? lrA : 0) * m;
+    const double* rowB = inv + (active ? rb : 0) * m;
     const long long c0 = 2 * lane;
-    const bool head = active && (c0 + (kUpAhead - 1) * 64 < m);   // uniform: m is a multiple of 128
-    double2 v[kUpAhead];
+    const bool head = active && (c0 + 7 * 64 < m);               // uniform: m is a multiple of 128
+    double2 va[8], vb[8];
     if (head) {
 #pragma unroll
-        for (int u = 0; u < kUpAhead; ++u) v[u] = __ldcs(reinterpret_cast<const double2*>(row + c0 + 64 * u));
+        for (int u = 0; u < 8; ++u) {
+            va[u] = __ldcs(reinterpret_cast<const double2*>(rowA + c0 + 64 * u));
+            vb[u] = __ldcs(reinterpret_cast<const double2*>(rowB + c0 + 64 * u));
+        }
     }
     const double alpha = S->rho[k & 1] / *B.pz;
     for (long long c = tid; c < m; c += kUpThreads)
@@ -769,20 +781,29 @@ __global__ void __launch_bounds__(kUpThreads, 3) k_cg_update_dense(const DenseDe
         long long c = c0;
         if (head) {
 #pragma unroll
-            for (int u = 0; u < kUpAhead; ++u) {
+            for (int u = 0; u < 8; ++u) {
                 const double2 xv = *reinterpret_cast<const double2*>(s_r + c0 + 64 * u);
-                acc[(2 * u) & 3] = fma(v[u].x, xv.x, acc[(2 * u) & 3]);
-                acc[(2 * u + 1) & 3] = fma(v[u].y, xv.y, acc[(2 * u + 1) & 3]);
+                acc[0] = fma(va[u].x, xv.x, acc[0]);
+                acc[1] = fma(va[u].y, xv.y, acc[1]);
+                acc[2] = fma(vb[u].x, xv.x, acc[2]);
+                acc[3] = fma(vb[u].y, xv.y, acc[3]);
             }
-            c += kUpAhead * 64;
+            c += 8 * 64;
         }
-        up_row(row, s_r, m, c, acc);
-        double wa = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+        up_row_pair(rowA, rowB, s_r, m, c, acc);
+        double wa = acc[0] + acc[1], wb = acc[2] + acc[3];
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) wa += __shfl_xor_sync(0xffffffffu, wa, off);
+        for (int off = 16; off > 0; off >>= 1) {
+            wa += __shfl_xor_sync(0xffffffffu, wa, off);
+            wb += __shfl_xor_sync(0xffffffffu, wb, off);
+        }
         if (lane == 0) {
             B.w[g0 + lrA] = wa;
-            s_w[warp] = wa;
+            s_w[lw] = wa;
+            if (lrB < valid) {
+                B.w[g0 + lrB] = wb;
+                s_w[lw + 1] = wb;
+            }
         }
     }
     __syncthreads();
@@ -985,7 +1006,7 @@ int cg_solve_caps(icqb_ctx* ctx, uint64_t dA_, int64_t n, int64_t ld, int storag
         if (off) fusedUpdate = false;
     }
     const long long nUpd = (denseRows + kUpRows - 1) / kUpRows;
-    const long long updDoubles = fusedUpdate ? 3 * nUpd + (nUpd + 1) / 2 : 0;   // partials + CTA -> block table
+    const long long updDoubles = fusedUpdate ? 3 * nUpd : 0;
     const long long need = small + denseDoubles + panelDoubles + descDoubles + tileDoubles +
                            gatherDoubles + gdescDoubles + updDoubles + 68;
     int rc = ensure_work(ctx, need);
@@ -1018,16 +1039,6 @@ int cg_solve_caps(icqb_ctx* ctx, uint64_t dA_, int64_t n, int64_t ld, int storag
     double* wrecv = wp; wp += sharded ? (long long)P * slot : 0;
     GatherDesc* dgather = reinterpret_cast<GatherDesc*>(wp); wp += gdescDoubles;
     double* updPart = wp; wp += updDoubles;
-    int* updBlock = reinterpret_cast<int*>(updPart + 3 * nUpd);
-    std::vector<int> hUpdBlock;
-    if (fusedUpdate) {
-        hUpdBlock.resize((size_t)nUpd);
-        int bq = 0;
-        for (long long q = 0; q < nUpd; ++q) {
-            while (bq + 1 < nDense && hdesc[(size_t)bq + 1].row0 <= q * kUpRows) ++bq;
-            hUpdBlock[(size_t)q] = bq;
-        }
-    }
     double* rbuf[2] = {B.r, fusedUpdate ? r_alt : B.r};
     // the residual of iteration k lives in rbuf[k & 1] (fused update: double-buffered)
     auto atIter = [&](long long kq) {
@@ -1171,7 +1182,7 @@ int cg_solve_caps(icqb_ctx* ctx, uint64_t dA_, int64_t n, int64_t ld, int storag
             }
             if (fusedUpdate) {
                 k_cg_update_dense<<<(unsigned)nUpd, kUpThreads, updSmem, st>>>(
-                    ddesc, nDense, dense, kk, x, B, rbuf[kk & 1], rbuf[(kk + 1) & 1], updPart, updBlock);
+                    ddesc, nDense, dense, kk, x, B, rbuf[kk & 1], rbuf[(kk + 1) & 1], updPart);
                 ctx->launches += 1;
                 r2 = check_cuda(ctx, cudaGetLastError(), "k_cg_update_dense launch");
             } else {
@@ -1205,9 +1216,6 @@ int cg_solve_caps(icqb_ctx* ctx, uint64_t dA_, int64_t n, int64_t ld, int storag
         // table of the partition: tile -> dense block (every tile belongs to one; blocks of a
         // single tile are dense blocks like the others, so the 128 x 128 set of cg.cu is not built)
         CG_CUDA(cudaMemcpyAsync(dtile, htile.data(), sizeof(int) * (size_t)nT, cudaMemcpyHostToDevice, st));
-        if (fusedUpdate)
-            CG_CUDA(cudaMemcpyAsync(updBlock, hUpdBlock.data(), sizeof(int) * (size_t)nUpd, cudaMemcpyHostToDevice,
-                                    st));
 
         // tables of the dense blocks, then: extract, all-reduce (replicated ones), block sweep, mirror
         if (sharded)
