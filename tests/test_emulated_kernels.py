@@ -400,6 +400,38 @@ def test_emulated_ranks_without_rows(emu, oracle_mod):
         o[-1].close()
 
 
+@pytest.mark.parametrize('kind,starts,expect', [(1, None, 'fallback'), (2, [0, 1, 2, 3], 'fallback'),
+                                                (2, [0, 2], 'weak')])
+def test_emulated_weak_pivot_in_a_preconditioner_block(emu, oracle_mod, kind, starts, expect):
+    """A 128 x 128 diagonal block whose unpivoted inversion meets a pivot that has lost 14 digits
+    ([[1, 1], [1, 1 + 1e-14]] inside tile 1 of a synthetic symmetric matrix): the block
+    falls back to 1/diag and is counted (both solvers; a block of ONE tile of the partitioned
+    solver behaves the same), inside a larger dense block the pivot is reported only
+    (icqb_cg_last_blocks; ADVICE of round 1)."""
+    c = Ctx(emu, 20, 11)
+    n = c.n
+    a2 = oracle_mod.area2(c.xyz, c.tri)
+    rng = numpy.random.default_rng(5)
+    noise = rng.standard_normal((n, n)) * 1e-3
+    sym = 4. * numpy.eye(n) + 0.5 * (noise + noise.T)
+    sym[128:130, :] = 0.
+    sym[:, 128:130] = 0.
+    sym[128:130, 128:130] = [[1., 1.], [1., 1. + 1e-14]]
+    ld = (n + 15) // 16 * 16
+    g = dev_array(emu, (n, ld), 0.)
+    g[:, :n] = sym / a2[:, None]          # diag(a2) g is the symmetric matrix above
+    c.check(emu.icqb_set_rows(c.h, 0, n))
+    c.solve(g, 0, kind, ld=ld, maxit=3, starts=starts)
+    bad, weak = ctypes.c_int64(-1), ctypes.c_int64(-1)
+    emu.icqb_cg_last_blocks.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)]
+    c.check(emu.icqb_cg_last_blocks(c.h, ctypes.byref(bad), ctypes.byref(weak)))
+    if expect == 'fallback':
+        assert bad.value == 1
+    else:
+        assert bad.value == 0 and weak.value >= 1
+    c.close()
+
+
 def test_emulated_block_cache_between_contexts(emu, oracle_mod):
     """The contexts' device buffers come from a process-wide cache of freed blocks
     (csrc/context.cu): a second solver of the same size gets the first one's blocks back, stale

@@ -589,6 +589,51 @@ def test_symmetric_product_synthetic_matrix(ctx, n, blocks):
         assert (numpy.abs(y - ref) <= 1e-13 * bound + 1e-300).all()
 
 
+@pytest.mark.parametrize('kind,starts,expect', [(1, None, 'fallback'), (2, [0, 1, 2, 3], 'fallback'),
+                                                (2, [0, 2], 'weak')])
+def test_weak_pivot_in_a_preconditioner_block(ctx, kind, starts, expect):
+    """A 128 x 128 diagonal block whose unpivoted inversion meets a pivot that has lost 14 digits
+    ([[1, 1], [1, 1 + 1e-14]] inside tile 1 of a synthetic symmetric matrix, row-block storage):
+    the block falls back to 1/diag and is counted (both solvers; a block of ONE tile of the
+    partitioned solver behaves the same), inside a larger dense block the pivot is reported only
+    (icqb_cg_last_blocks)."""
+    import torch
+    from icqsol_b200.mesh.generators import uvSphere
+    xyz, tri = uvSphere(1.0, 20, 11)
+    n = tri.shape[0]
+    ctx.check(ctx.lib.icqb_set_mesh(ctx.handle, dp(xyz), xyz.shape[0], lp(numpy.ascontiguousarray(tri)), n))
+    ctx.check(ctx.lib.icqb_set_rows(ctx.handle, 0, n))
+    a2 = numpy.zeros(n)
+    ctx.check(ctx.lib.icqb_area2_host(ctx.handle, dp(a2)))
+    rng = numpy.random.default_rng(5)
+    noise = rng.standard_normal((n, n)) * 1e-3
+    sym = 4. * numpy.eye(n) + 0.5 * (noise + noise.T)
+    sym[128:130, :] = 0.
+    sym[:, 128:130] = 0.
+    sym[128:130, 128:130] = [[1., 1.], [1., 1. + 1e-14]]
+    ld = (n + 15) // 16 * 16
+    g = numpy.zeros((n, ld))
+    g[:, :n] = sym / a2[:, None]          # diag(a2) g is the symmetric matrix above
+    dev = torch.device('cuda', 0)
+    dA = torch.from_numpy(g).to(dev)
+    db = torch.ones(n, dtype=torch.float64, device=dev)
+    dx = torch.zeros(n, dtype=torch.float64, device=dev)
+    ctx.check(ctx.lib.icqb_cg_set_preconditioner(ctx.handle, kind))
+    st = numpy.asarray(starts or [], numpy.int64)
+    ctx.check(ctx.lib.icqb_cg_set_block_partition(ctx.handle, lp(st) if len(st) else None, len(st)))
+    it, r2, ri = ctypes.c_int64(0), ctypes.c_double(0.), ctypes.c_double(0.)
+    ctx.check(ctx.lib.icqb_cg_solve_dev(ctx.handle, dA.data_ptr(), n, ld, 0, ctx.lib.icqb_area2_dev(ctx.handle), 0,
+                                        db.data_ptr(), dx.data_ptr(), 5e-13, 2, 3, ctypes.byref(it),
+                                        ctypes.byref(r2), ctypes.byref(ri)))
+    bad, weak = ctypes.c_int64(-1), ctypes.c_int64(-1)
+    ctx.check(ctx.lib.icqb_cg_last_blocks(ctx.handle, ctypes.byref(bad), ctypes.byref(weak)))
+    if expect == 'fallback':
+        assert bad.value == 1
+    else:
+        assert bad.value == 0 and weak.value >= 1
+    assert numpy.isfinite(dx.cpu().numpy()).all()
+
+
 def test_block_preconditioner_cuts_iterations():
     """LaplaceSolver with the inverse-diagonal-block preconditioner needs fewer CG
     iterations than 1/diag (the reference class's default) and gives the same response."""
