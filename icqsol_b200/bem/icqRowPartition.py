@@ -209,7 +209,7 @@ def rankCuts(n, nranks):
 
 def sliverBlockPartition(xyz, tri, blockTiles=1, threshold=30., gapTiles=4, maxTiles=64,
                          budgetFraction=0.125, budgetFloor=6.4e7, flagged=None, cuts=None):
-    """First tile row of every diagonal block of the experimental preconditioner
+    """First tile row of every diagonal block of the block preconditioner (kind 2, the default)
     (icqb_cg_set_block_partition) for a mesh whose slivers may sit ANYWHERE in the triangle
     list -- e.g. the poles of the inner sphere of a hollow sphere: every run of tiles that hold
     slivers (runs separated by at most ``gapTiles`` clean tiles are merged: on a UV sphere
@@ -286,7 +286,7 @@ def sliverBlockPartition(xyz, tri, blockTiles=1, threshold=30., gapTiles=4, maxT
 
 
 def blockPartition(n, blockTiles, headTiles=0, tailTiles=0):
-    """First tile row of every diagonal block of the experimental preconditioner: a cap of
+    """First tile row of every diagonal block of the block preconditioner (kind 2): a cap of
     headTiles, blocks of blockTiles, a cap of tailTiles (icqb_cg_set_block_partition)."""
     nT = (int(n) + TILE - 1) // TILE
     head = min(max(int(headTiles), 0), nT)

@@ -116,7 +116,7 @@ extern "C" int icqb_cg_solve_dev(icqb_ctx* ctx, uint64_t dA_, int64_t n, int64_t
         return set_error(ctx, ICQB_EARG,
                          "icqb_cg_solve_dev: with lower storage the row scaling must be icqb_area2_dev()");
 
-    // experimental solver: blocks + dense caps over the sliver tiles, peer exchange (cg_caps.cu)
+    // preconditioner kind 2: larger dense blocks, dense blocks over the sliver tiles (cg_caps.cu)
     if (!precond && ctx->precond_kind == 2)
         return cg_solve_caps(ctx, dA_, n, ld, storage, drowscale_, db_, dx_, tol, rel, maxit, iters,
                              resid2, residinf);

@@ -1,5 +1,5 @@
 // Kernels and host helpers of the conjugate gradient, shared by cg.cu (the solver behind
-// icqb_cg_solve_dev) and cg_caps.cu (its experimental variant with dense cap blocks in the
+// icqb_cg_solve_dev) and cg_caps.cu (the solver of preconditioner kind 2, with larger dense blocks in the
 // preconditioner).  Everything here has internal linkage: each translation unit that
 // includes this header gets its own copy.  See cg.cu for the algorithm.
 #pragma once

@@ -97,7 +97,7 @@ struct Comm {
     ncclComm_t comm = nullptr;
     int rank = 0, nranks = 1;
     int refs = 1;   // contexts sharing this communicator (icqb_comm_share)
-    // experimental peer exchange (SymvPeer, icqb_internal.cuh)
+    // optional peer exchange (SymvPeer, icqb_internal.cuh)
     void* xbuf = nullptr;               // this rank's exchange buffer
     void* xpeer[kMaxPeers] = {};        // every rank's buffer as mapped here (own: xbuf)
     long long slotStride = 0;

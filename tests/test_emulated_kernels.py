@@ -231,7 +231,7 @@ def test_emulated_cg_matches_model(emu, oracle_mod):
 
 @pytest.mark.parametrize('caps,cuts', [((1, 1), [0, 128]), ((2, 0), [0])])
 def test_emulated_cap_blocks(emu, oracle_mod, caps, cuts):
-    """EXPERIMENTAL path (csrc/cg_caps.cu, never run on a GPU yet): dense cap blocks --
+    """csrc/cg_caps.cu (preconditioner kind 2): dense cap blocks --
     extraction with the symmetric fill and the identity padding of the ragged last tile,
     Gauss-Jordan in global memory, split residual kernels, cap GEMV -- against the numpy
     model: caps of one tile each are the plain blocks, one cap over everything is the
@@ -288,7 +288,7 @@ def _run_ranks(emu, nranks, n_theta, n_phi, storage, kind, caps=None, peer=False
                mixed=0.):
     """One rank per thread (ctypes releases the GIL), the in-process NCCL stand-in of
     tools/emu underneath: folded row blocks, sharded assembly, distributed CG.  peer=True
-    also sets up the experimental peer exchange (handles swapped through a shared list)."""
+    also sets up the optional peer exchange (handles swapped through a shared list)."""
     import threading
     from icqsol_b200.bem import icqRowPartition as rp
     uid = ctypes.create_string_buffer(128)
@@ -339,7 +339,7 @@ def test_emulated_multi_rank_cg(emu, oracle_mod, nranks, storage, kind, caps, pe
     """Sharded assembly and the distributed CG (all-reduce of the partial products with p.z in
     the slot behind them, all-reduce of the preconditioner blocks / cap blocks, all-gather for
     row blocks): every rank returns the same solution, it solves the oracle's system, and
-    the iteration count is the single-rank one.  The last case runs the EXPERIMENTAL peer
+    the iteration count is the single-rank one.  The last case runs the optional peer
     exchange (stores into the peers' buffers + flags instead of the all-reduce)."""
     out = _run_ranks(emu, nranks, 20, 11, storage, kind, caps, peer)     # 400 triangles, 4 tile rows
     c = out[0][-1]
@@ -456,7 +456,7 @@ def test_emulated_block_cache_between_contexts(emu, oracle_mod):
 
 @pytest.mark.parametrize('starts,storage', [([0, 2], 1), ([0, 3], 1), ([0, 1, 3], 0), ([0], 1), ([0], 0)])
 def test_emulated_block_partition(emu, oracle_mod, starts, storage):
-    """EXPERIMENTAL: an explicit partition of the tile rows into diagonal blocks -- batched
+    """An explicit partition of the tile rows into diagonal blocks -- batched
     extraction, block Gauss-Jordan with 128^3 tile products, batched apply -- against the
     numpy model of the same blocks (400 triangles = 4 tile rows, the last one ragged)."""
     c = Ctx(emu, 20, 11)
@@ -477,7 +477,7 @@ def test_emulated_block_partition(emu, oracle_mod, starts, storage):
     c.close()
 
 
-# ---- EXPERIMENTAL: far-field split of the off-diagonal assembly (assemble_offdiag_ff.cu) -------
+# ---- far-field split of the off-diagonal assembly (assemble_offdiag_ff.cu) ---------------------
 
 def _assembly_stats(emu, c):
     fast, allp = ctypes.c_int64(0), ctypes.c_int64(0)
@@ -653,8 +653,8 @@ def test_emulated_kernels_under_other_thread_orders(order):
     (3, 1, None, [0, 3], True, [0, 384])])            # partition + peer exchange
 def test_emulated_multi_rank_experimental_combinations(emu, oracle_mod, nranks, storage, caps, starts,
                                                        peer, cuts):
-    """EXPERIMENTAL solver, the combinations its first GPU visit will run (tests/dist_worker.py
-    with ICQB_EXPERIMENTAL / ICQB_PEER_EXCHANGE): dense blocks are extracted from the rows each
+    """Solver of kind 2, the combinations tests/dist_worker.py runs on the GPUs (also with
+    ICQB_PEER_EXCHANGE): dense blocks are extracted from the rows each
     rank stores and all-reduced, every rank applies them; same solution and iteration count on
     every rank, the count of the numpy model of the same blocks."""
     out = _run_ranks(emu, nranks, 20, 11, storage, 2, caps, peer, starts)     # 400 triangles
@@ -671,7 +671,7 @@ def test_emulated_multi_rank_experimental_combinations(emu, oracle_mod, nranks, 
         o[-1].close()
 
 
-# ---- EXPERIMENTAL: float32 late products of the CG (k_symv_f32, cg_caps.cu) ---------------------
+# ---- optional: float32 late products of the CG (k_symv_f32, cg_caps.cu) -------------------------
 
 @pytest.mark.parametrize('sms', [1, 3, 4])
 def test_emulated_float32_product(emu, oracle_mod, sms):

@@ -1089,7 +1089,7 @@ def test_float32_product_kernel(oracle_mod, nt, nph):
 
 
 def test_mixed_precision_cg():
-    """Float32 late products (switch at 1e-6) in the experimental solver: same backward error,
+    """Float32 late products (switch at 1e-6, off by default) in the solver of kind 2: same backward error,
     a good share of the products in float32, a few more iterations at most."""
     from icqsol_b200.mesh.generators import uvSphere
     from icqsol_b200.mesh.polydata import PolyData

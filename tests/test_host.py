@@ -251,7 +251,7 @@ def test_bench_reference_arm_runs():
 
 
 def test_sliver_cap_tiles():
-    """Tiles to merge into the dense cap blocks of the experimental preconditioner: the pole
+    """Tiles to merge into the dense cap blocks of the block preconditioner: the pole
     fan plus the band(s) whose triangles exceed the aspect threshold -- fan + 1 band at
     n_theta = 238 and 318, fan + 2 bands at 448 (what the numpy model needs to converge,
     tools/experiments/pcg_cap_blocks.py), nothing at config C2."""
@@ -365,7 +365,7 @@ def test_bench_json_line_in_emulation(options):
     """bench.py end to end (timed loop, fp64 peak, end-to-end leg through LaplaceSolver, CPU
     baseline, JSON line) on a 320-triangle sphere with the emulated library: every key of the
     bench contract is there and the solve converged -- for the defaults and for the
-    experimental options."""
+    non-default options."""
     import json
     text = _run_emulated(['bench.py', '--workload', 'tiny', '--steps', '1', '--warmup', '1',
                           '--e2e-steps', '1', '--cpu-sample', '120'] + options)
