@@ -58,7 +58,23 @@ UNIT = 'entries/s'
 EXPR_V = '1./sqrt(x**2 + (y-2.)**2 + (z-4.)**2)'   # CMakeLists.txt:487 of the reference
 FLOP_PER_EVAL_G = 12.0
 FLOP_PER_EVAL_GK = 18.0    # + 1/r^3 (2 mul) and two weighted accumulations (2 fma), DESIGN.md
-DEFAULT_BLOCK_TILES = 8    # diagonal blocks of the CG preconditioner, in 128-triangle tiles
+# diagonal blocks of the CG preconditioner, in 128-triangle tiles: (one rank, several ranks).  One
+# rank: blocks of 4 tiles extended by one tile on either side (overlapping blocks are a one-rank
+# feature, include/icqb.h icqb_cg_set_block_extents); several ranks: plain blocks of 8.
+DEFAULT_BLOCK_TILES = (4, 8)
+DEFAULT_BLOCK_OVERLAP = (1, 0)
+
+
+def resolve_blocks(args, world):
+    """(block tiles, overlap tiles) of this run."""
+    many = 0 if world == 1 else 1
+    overlap = DEFAULT_BLOCK_OVERLAP[many] if args.block_overlap is None else args.block_overlap
+    if many:
+        overlap = 0
+    tiles = args.block_tiles
+    if tiles is None:
+        tiles = DEFAULT_BLOCK_TILES[many] if overlap > 0 else DEFAULT_BLOCK_TILES[1]
+    return int(tiles), int(overlap)
 REFERENCE_WORKERS = 16     # host processes of the reference arm (fewer if the box has fewer cores)
 
 
@@ -121,7 +137,8 @@ def bench_config(args, label, n, world):
         'step': ('fused G+K assembly + Poisson product v = G q' if poisson else
                  'fused G+K assembly + dense solve of G sigma = -v (max|v+G sigma| <= 5e-13 max|v|)'),
         'storage': args.storage, 'preconditioner': args.preconditioner,
-        'block_tiles': args.block_tiles, 'assembly_variant': args.assembly_variant,
+        'block_tiles': resolve_blocks(args, world)[0], 'block_overlap_tiles': resolve_blocks(args, world)[1],
+        'assembly_variant': args.assembly_variant,
         'mixed_switch': args.mixed_switch,
         'parallelism': ('folded row blocks balanced by stored tiles, lower storage x{0}' if lower
                         else 'row-block x{0}').format(world),
@@ -422,10 +439,19 @@ def run_b200(args):
     if kind == 2:
         # one dense block per run of sliver tiles, blocks of --block-tiles tiles elsewhere
         cuts = rowPartition.rankCuts(n, world) if (args.storage == 'lower' and world > 1) else None
-        starts, dense_runs = rowPartition.sliverBlockPartition(xyz, tri, blockTiles=args.block_tiles, cuts=cuts)
+        block_tiles, block_overlap = resolve_blocks(args, world)
+        starts, dense_runs = rowPartition.sliverBlockPartition(xyz, tri, blockTiles=block_tiles, cuts=cuts)
+        start_list = [int(t) for t in starts]
         starts = numpy.ascontiguousarray(starts, numpy.int64)
         ctx.check(lib.icqb_cg_set_block_partition(ctx.handle, starts.ctypes.data_as(_lib.c_int64_p),
                                                   len(starts)))
+        if block_overlap > 0:
+            ext0, ext1 = rowPartition.blockExtents(start_list, (n + rowPartition.TILE - 1) // rowPartition.TILE,
+                                                   dense_runs, overlapTiles=block_overlap)
+            e0 = numpy.ascontiguousarray(ext0, numpy.int64)
+            e1 = numpy.ascontiguousarray(ext1, numpy.int64)
+            ctx.check(lib.icqb_cg_set_block_extents(ctx.handle, e0.ctypes.data_as(_lib.c_int64_p),
+                                                    e1.ctypes.data_as(_lib.c_int64_p), len(e0)))
     ctx.check(lib.icqb_set_assembly_variant(ctx.handle, args.assembly_variant))
     ctx.check(lib.icqb_cg_set_mixed_precision(ctx.handle, args.mixed_switch))
     ctx.check(lib.icqb_set_mesh(ctx.handle, xyz.ctypes.data_as(_lib.c_double_p), xyz.shape[0],
@@ -580,7 +606,8 @@ def run_b200(args):
         cls = PoissonSolver if poisson else LaplaceSolver
         solver = cls(pd, float('inf'), 5, computeK=True, device=local,
                      storage=args.storage, preconditioner=args.preconditioner,
-                     blockTiles=args.block_tiles, assemblyVariant=args.assembly_variant,
+                     blockTiles=resolve_blocks(args, world)[0], blockOverlap=resolve_blocks(args, world)[1],
+                     assemblyVariant=args.assembly_variant,
                      mixedPrecision=args.mixed_switch)
         if not poisson:
             solver.setSolverMaxNumberOfIterations(args.max_iters)
@@ -728,8 +755,12 @@ def main():
                     help="CG preconditioner: 'block+caps' (default) = inverse diagonal blocks of "
                          "--block-tiles tiles, with one dense block over every run of sliver tiles "
                          "(DESIGN.md 4.6); 'block' = inverse 128x128 blocks; 'diagonal' = 1/diag")
-    ap.add_argument('--block-tiles', type=int, default=DEFAULT_BLOCK_TILES,
-                    help='with block+caps: 128-triangle tiles per diagonal block')
+    ap.add_argument('--block-tiles', type=int, default=None,
+                    help='with block+caps: 128-triangle tiles per diagonal block (default 4 on one '
+                         'GPU, 8 on several)')
+    ap.add_argument('--block-overlap', type=int, default=None,
+                    help='with block+caps on one GPU: tiles by which every block is extended on either '
+                         'side (overlapping blocks, default 1; 0 = plain blocks)')
     ap.add_argument('--assembly-variant', type=int, default=1, choices=[0, 1],
                     help='arithmetic of the off-diagonal kernel (include/icqb.h, '
                          'icqb_set_assembly_variant): 0 direct, 1 far-field split')

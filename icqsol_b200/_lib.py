@@ -61,6 +61,7 @@ SIGNATURES = [
     ('icqb_cg_set_preconditioner', c_int, [c_void_p, c_int]),
     ('icqb_cg_set_cap_tiles', c_int, [c_void_p, c_int64, c_int64]),
     ('icqb_cg_set_block_partition', c_int, [c_void_p, c_int64_p, c_int64]),
+    ('icqb_cg_set_block_extents', c_int, [c_void_p, c_int64_p, c_int64_p, c_int64]),
     ('icqb_cg_last_stats', c_int, [c_void_p, c_int64_p, c_int64_p]),
     ('icqb_cg_last_blocks', c_int, [c_void_p, c_int64_p, c_int64_p]),
     ('icqb_cg_set_mixed_precision', c_int, [c_void_p, c_double]),

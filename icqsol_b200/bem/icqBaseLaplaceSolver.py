@@ -45,12 +45,14 @@ def leadingDimension(n):
 class BaseLaplaceSolver(BaseSolver):
 
     # defaults of the solver options a caller leaves at None
-    DEFAULTS = {'preconditioner': 'block+caps', 'blockTiles': 8, 'assemblyVariant': 1,
-                'mixedPrecision': 0.}
+    # blockTiles / blockOverlap: (one rank, several ranks) -- overlapping blocks are a
+    # one-rank feature (include/icqb.h, icqb_cg_set_block_extents)
+    DEFAULTS = {'preconditioner': 'block+caps', 'blockTiles': (4, 8), 'blockOverlap': (1, 0),
+                'assemblyVariant': 1, 'mixedPrecision': 0.}
 
     def __init__(self, pdata, max_edge_length, order=5, computeK=False, device=None,
                  storage='lower', preconditioner=None, blockTiles=None, assemblyVariant=None,
-                 directFallback=True, mixedPrecision=None):
+                 directFallback=True, mixedPrecision=None, blockOverlap=None):
         """
         Constructor
         @param pdata polydata (vtkPolyData or stand-in)
@@ -71,7 +73,11 @@ class BaseLaplaceSolver(BaseSolver):
                        default, solvers/icqConjugateGradient.py:19); 'auto' = 'block+caps'
         @param blockTiles with 'block+caps': tiles (of 128 triangles) per diagonal block
                        between the sliver runs (config C2 on a B200: 165 iterations with 1,
-                       91 with 8)
+                       91 with 8); default 4 on one rank (with blockOverlap 1), 8 on several
+        @param blockOverlap with 'block+caps' on ONE rank: tiles by which every block is extended on
+                       either side (symmetric additive Schwarz, icqRowPartition.blockExtents:
+                       config C2 needs 45 iterations with blocks of 4 + 1 + 1 tiles instead of 91
+                       with blocks of 8); default 1 on one rank; ignored on several ranks
         @param mixedPrecision with 'block+caps' and storage='lower' only: relative
                        residual below which the products of the CG stream a float32 copy of
                        the matrix (include/icqb.h, icqb_cg_set_mixed_precision); 0 = off
@@ -94,8 +100,14 @@ class BaseLaplaceSolver(BaseSolver):
         defaults = dict(self.DEFAULTS)
         if preconditioner is None:
             preconditioner = defaults['preconditioner']
+        rankInfo = rowPartition.worldInfo()
+        single = 0 if rankInfo[1] == 1 else 1
+        if blockOverlap is None:
+            blockOverlap = defaults['blockOverlap'][single]
+        if single == 1:
+            blockOverlap = 0
         if blockTiles is None:
-            blockTiles = defaults['blockTiles']
+            blockTiles = defaults['blockTiles'][single] if blockOverlap > 0 else defaults['blockTiles'][1]
         if assemblyVariant is None:
             assemblyVariant = defaults['assemblyVariant']
         if mixedPrecision is None:
@@ -150,9 +162,21 @@ class BaseLaplaceSolver(BaseSolver):
                 if (storage == 'lower' and self.numRanks > 1) else None
             starts, self.denseRuns = rowPartition.sliverBlockPartition(
                 self._xyz, self._tri, blockTiles=int(blockTiles), cuts=cuts, flagged=flagged)
+            self.blockStarts = [int(t) for t in starts]
             starts = numpy.ascontiguousarray(starts, numpy.int64)
             self.ctx.check(self.lib.icqb_cg_set_block_partition(
                 self.ctx.handle, starts.ctypes.data_as(_lib.c_int64_p), len(starts)))
+            self.blockExtents = None
+            if int(blockOverlap) > 0 and self.numRanks == 1:
+                numTiles = (self.numTriangles + rowPartition.TILE - 1) // rowPartition.TILE
+                ext0, ext1 = rowPartition.blockExtents(self.blockStarts, numTiles, self.denseRuns,
+                                                       overlapTiles=int(blockOverlap))
+                self.blockExtents = (ext0, ext1)
+                e0 = numpy.ascontiguousarray(ext0, numpy.int64)
+                e1 = numpy.ascontiguousarray(ext1, numpy.int64)
+                self.ctx.check(self.lib.icqb_cg_set_block_extents(
+                    self.ctx.handle, e0.ctypes.data_as(_lib.c_int64_p),
+                    e1.ctypes.data_as(_lib.c_int64_p), len(e0)))
 
         # one NCCL communicator per process, shared by every solver
         _lib.attachCommunicator(self.ctx, self.rank, self.numRanks, rowPartition.broadcastBytes)

@@ -285,6 +285,54 @@ def sliverBlockPartition(xyz, tri, blockTiles=1, threshold=30., gapTiles=4, maxT
     return (starts or [0]), [r for r in runs if r[1] > 1]
 
 
+def blockExtents(starts, numTiles, denseRuns, overlapTiles=1, maxTiles=64):
+    """Overlapping extents of the diagonal blocks of a partition (icqb_cg_set_block_extents):
+    block q = tile rows [starts[q], starts[q+1]) grows by ``overlapTiles`` tiles on either side
+    (symmetric additive Schwarz: a row in two extents is weighted 1/sqrt(2) in each).  The runs of
+    sliver tiles (``denseRuns`` of sliverBlockPartition) must never be split between blocks --
+    the wrong-sign eigenvectors of diag(A) G live on them and a block that holds
+    only a piece of such a run makes the iteration stall (tools/experiments/pcg_overlap.py) --
+    so a sliver block grows OUTWARDS like the others, but no other block grows into it.
+    An extent never exceeds ``maxTiles`` tiles, never reaches past its neighbours' far ends
+    (a row lies in two extents at most).
+    @return (begins, ends): tile rows, one pair per block"""
+    starts = [int(t) for t in starts]
+    nT = int(numTiles)
+    ov = max(int(overlapTiles), 0)
+    nb = len(starts)
+    ends = starts[1:] + [nT]
+    sliver = [False] * (nT + 1)
+    for (a, m) in denseRuns:
+        for t in range(int(a), min(int(a) + int(m), nT)):
+            sliver[t] = True
+    ext0, ext1 = [], []
+    for q in range(nb):
+        t0, t1 = starts[q], ends[q]
+        # not past the far end of the neighbouring blocks: at most two extents per row
+        lo = starts[q - 1] if q > 0 else 0
+        hi = ends[q + 1] if q + 1 < nb else nT
+        e0, e1 = max(t0 - ov, lo, 0), min(t1 + ov, hi, nT)
+        if not sliver[t0]:
+            while e0 < t0 and sliver[e0]:
+                e0 += 1
+            while e1 > t1 and sliver[e1 - 1]:
+                e1 -= 1
+        while e1 - e0 > int(maxTiles):     # shrink the overlap, never the block
+            if e1 > t1 and (e1 - t1 >= t0 - e0):
+                e1 -= 1
+            elif e0 < t0:
+                e0 += 1
+            else:
+                break
+        ext0.append(e0)
+        ext1.append(e1)
+    # a row may lie in the extents of two CONSECUTIVE blocks only
+    for q in range(2, nb):
+        if ext0[q] < ext1[q - 2]:
+            ext0[q] = min(ext1[q - 2], starts[q])
+    return ext0, ext1
+
+
 def blockPartition(n, blockTiles, headTiles=0, tailTiles=0):
     """First tile row of every diagonal block of the block preconditioner (kind 2): a cap of
     headTiles, blocks of blockTiles, a cap of tailTiles (icqb_cg_set_block_partition)."""

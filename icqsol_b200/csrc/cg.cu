@@ -73,6 +73,33 @@ extern "C" int icqb_cg_set_block_partition(icqb_ctx* ctx, const int64_t* starts,
         if (starts[q] <= starts[q - 1])
             return set_error(ctx, ICQB_EARG, "icqb_cg_set_block_partition: starts must increase");
     ctx->block_starts.assign(starts, starts + nblocks);
+    ctx->block_ext0.clear();   // extents belong to a partition: set them after it
+    ctx->block_ext1.clear();
+    return ICQB_OK;
+}
+
+extern "C" int icqb_cg_set_block_extents(icqb_ctx* ctx, const int64_t* ext_begin, const int64_t* ext_end,
+                                         int64_t nblocks) {
+    if (!ctx) return ICQB_EARG;
+    if (nblocks == 0) {
+        ctx->block_ext0.clear();
+        ctx->block_ext1.clear();
+        return ICQB_OK;
+    }
+    if (nblocks != (int64_t)ctx->block_starts.size() || !ext_begin || !ext_end)
+        return set_error(ctx, ICQB_EARG,
+                         "icqb_cg_set_block_extents: one extent per block of icqb_cg_set_block_partition");
+    for (int64_t q = 0; q < nblocks; ++q) {
+        const int64_t t0 = ctx->block_starts[(size_t)q];
+        if (ext_begin[q] < 0 || ext_begin[q] > t0 || ext_end[q] <= t0 ||
+            (q + 1 < nblocks && ext_end[q] < ctx->block_starts[(size_t)q + 1]))
+            return set_error(ctx, ICQB_EARG, "icqb_cg_set_block_extents: an extent must contain its block");
+        // a row may lie in two extents at most (its own block's and one neighbour's)
+        if (q >= 2 && ext_begin[q] < ext_end[q - 2])
+            return set_error(ctx, ICQB_EARG, "icqb_cg_set_block_extents: extents of blocks q and q-2 overlap");
+    }
+    ctx->block_ext0.assign(ext_begin, ext_begin + nblocks);
+    ctx->block_ext1.assign(ext_end, ext_end + nblocks);
     return ICQB_OK;
 }
 

@@ -96,6 +96,10 @@ struct DenseDesc {
     long long off;     // offset (doubles) of its m x m matrix in the dense buffer
     long long row0;    // first compact row (valid rows of all dense blocks, concatenated)
     long long row0pad; // sum of m over the blocks before this one (position in the panel buffers)
+    // overlapping blocks (one rank): t0 / tiles / m / valid describe the EXTENT; the block proper
+    // is the global rows [core0, core1); urow0 = first row of the extent in the sequence of all
+    // extents, each padded to a multiple of the update kernel's rows per CTA
+    long long core0, core1, urow0;
 };
 
 // dense block of diag(scale) A from the lower storage: tiles J <= I are copied (rows this rank
@@ -854,6 +858,149 @@ __global__ void __launch_bounds__(kUpThreads) k_cg_update_dense(const DenseDesc*
     }
 }
 
+// The same step for OVERLAPPING blocks (icqb_cg_set_block_extents; one rank):
+//     w = sum_q R_q^T D_q A_q^-1 D_q R_q r_new,   D_q = 1 / sqrt(extents that hold the row).
+// CTA = kUpRows consecutive rows of one EXTENT (the extents are laid one after the other, each
+// padded to a multiple of kUpRows: `ctaBlock` gives the block of a CTA).  The staged vector is
+// D r_new over the columns of the extent; a row's result is weighted and ADDED to w, which the
+// host zeroes before the launch -- a row lies in two extents at most, so the sum of its two
+// contributions does not depend on their order and the result is reproducible.  x and r are
+// written, and the residual norms taken, by the CTAs of the block a row belongs to (its core
+// rows); rho = r.w is summed extent by extent as (D r).(A_q^-1 D r).
+// APPLY_ONLY: w = M^-1 r for the given r (set-up and residual replacement): no update, no
+// partials, no closing step -- k_cg_close follows.
+template <bool APPLY_ONLY>
+__global__ void __launch_bounds__(kUpThreads) k_cg_update_overlap(const DenseDesc* desc, const int* ctaBlock,
+                                                                  const double* dense, const double* dcover,
+                                                                  int k, double* x, CgBuf B,
+                                                                  const double* r_old, double* r_new,
+                                                                  double* part) {
+    extern __shared__ __align__(16) double s_r[];   // [m of the largest extent]
+    __shared__ double s_w[kUpRows];
+    __shared__ double s_fin[3 * kUpThreads];
+    __shared__ int s_last;
+    CgState* S = B.state;
+    if (!APPLY_ONLY && S->done) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const DenseDesc D = desc[ctaBlock[blockIdx.x]];
+    const long long lr0 = (long long)blockIdx.x * kUpRows - D.urow0;   // first row of the CTA in its extent
+    const long long g0 = D.t0 * kT, m = D.m, valid = D.valid;
+    const double* inv = dense + D.off;
+    const int lw = 2 * warp;
+    const long long lrA = lr0 + lw, lrB = lrA + 1;
+    const bool active = lrA < valid;                              // warp-uniform
+    const long long rb = lrB < valid ? lrB : lrA;
+    const double* rowA = inv + (active ? lrA : 0) * m;
+    const double* rowB = inv + (active ? rb : 0) * m;
+    const long long c0 = 2 * lane;
+    const bool head = active && (c0 + 7 * 64 < m);               // uniform: m is a multiple of 128
+    double2 va[8], vb[8];
+    if (head) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            va[u] = __ldcs(reinterpret_cast<const double2*>(rowA + c0 + 64 * u));
+            vb[u] = __ldcs(reinterpret_cast<const double2*>(rowB + c0 + 64 * u));
+        }
+    }
+    const double alpha = APPLY_ONLY ? 0.0 : S->rho[k & 1] / *B.pz;
+    for (long long c = tid; c < m; c += kUpThreads) {
+        double v = 0.0;
+        if (c < valid) {
+            const double rn = APPLY_ONLY ? r_old[g0 + c] : fma(-alpha, B.z[g0 + c], r_old[g0 + c]);
+            v = dcover[g0 + c] * rn;
+        }
+        s_r[c] = v;
+    }
+    __syncthreads();
+    // the rows of this CTA that belong to the block itself: x, r, residual norms
+    double ruOwn = 0.0;
+    bool own = false;
+    if (!APPLY_ONLY && tid < kUpRows && lr0 + tid < valid) {
+        const long long i = g0 + lr0 + tid;
+        own = (i >= D.core0 && i < D.core1);
+        if (own) {
+            const double rn = fma(-alpha, B.z[i], r_old[i]);
+            x[i] = fma(alpha, B.p[i], x[i]);
+            r_new[i] = rn;
+            ruOwn = rn / B.s[i];
+        }
+    }
+    if (active) {
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        long long c = c0;
+        if (head) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const double2 xv = *reinterpret_cast<const double2*>(s_r + c0 + 64 * u);
+                acc[0] = fma(va[u].x, xv.x, acc[0]);
+                acc[1] = fma(va[u].y, xv.y, acc[1]);
+                acc[2] = fma(vb[u].x, xv.x, acc[2]);
+                acc[3] = fma(vb[u].y, xv.y, acc[3]);
+            }
+            c += 8 * 64;
+        }
+        up_row_pair(rowA, rowB, s_r, m, c, acc);
+        double ya = acc[0] + acc[1], yb = acc[2] + acc[3];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            ya += __shfl_xor_sync(0xffffffffu, ya, off);
+            yb += __shfl_xor_sync(0xffffffffu, yb, off);
+        }
+        if (lane == 0) {
+            atomicAdd(&B.w[g0 + lrA], dcover[g0 + lrA] * ya);
+            s_w[lw] = ya;
+            if (lrB < valid) {
+                atomicAdd(&B.w[g0 + lrB], dcover[g0 + lrB] * yb);
+                s_w[lw + 1] = yb;
+            }
+        }
+    }
+    if (APPLY_ONLY) return;
+    __syncthreads();
+    if (warp == 0) {
+        double rw = 0.0, r2 = 0.0, rm = 0.0;
+        const long long lr = lr0 + lane;
+        if (lane < kUpRows && lr < valid) rw = s_r[lr] * s_w[lane];   // (D r) . (A_q^-1 D r)
+        if (own) {
+            r2 = ruOwn * ruOwn;
+            rm = fabs(ruOwn);
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            rw += __shfl_xor_sync(0xffffffffu, rw, off);
+            r2 += __shfl_xor_sync(0xffffffffu, r2, off);
+            rm = fmax(rm, __shfl_xor_sync(0xffffffffu, rm, off));
+        }
+        if (lane == 0) {
+            const long long nP = gridDim.x;
+            part[blockIdx.x] = rw;
+            part[nP + blockIdx.x] = r2;
+            part[2 * nP + blockIdx.x] = rm;
+            s_last = take_ticket(&S->ticket_res, gridDim.x) ? 1 : 0;
+        }
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const int nP = (int)gridDim.x;
+    double rho = 0.0, res2 = 0.0, resmax = 0.0;
+    final_reduce3(part, part + nP, part + 2 * nP, nP, s_fin, tid, kUpThreads, &rho, &res2, &resmax);
+    if (tid == 0) {
+        S->rho[(k + 1) & 1] = rho;
+        S->beta = rho / S->rho[k & 1];
+        S->res2 = res2;
+        S->resmax = resmax;
+        S->iters += 1;
+        if ((S->use_max ? resmax : res2) <= S->thr) S->done = 1;
+        if (S->lowp) S->n32 += 1;
+        if (S->switch_thr > 0.0 && resmax <= S->switch_thr) S->lowp = 1;
+        S->skip64 = S->done | S->lowp;
+        S->skip32 = S->done | (S->lowp ^ 1);
+        S->ticket_res = 0;
+        __threadfence();
+    }
+}
+
 }  // namespace
 
 int cg_solve_caps(icqb_ctx* ctx, uint64_t dA_, int64_t n, int64_t ld, int storage,
@@ -900,6 +1047,21 @@ int cg_solve_caps(icqb_ctx* ctx, uint64_t dA_, int64_t n, int64_t ld, int storag
         ranges.push_back({t0, t1});
     }
     const int nAll = (int)ranges.size();
+    // overlapping extents (icqb_cg_set_block_extents): one rank only -- with several ranks every
+    // block is applied by the rank that holds its rows, without overlap
+    bool overlap = (P == 1) && ctx->block_ext0.size() == starts.size() && !ctx->block_starts.empty() &&
+                   ctx->block_starts.size() == starts.size();
+    std::vector<BlockRange> extents = ranges;
+    if (overlap) {
+        bool any = false;
+        for (int bq = 0; bq < nAll; ++bq) {
+            extents[(size_t)bq].t0 = std::min<long long>(ctx->block_ext0[(size_t)bq], ranges[(size_t)bq].t0);
+            extents[(size_t)bq].t1 = std::min<long long>(std::max<long long>(ctx->block_ext1[(size_t)bq],
+                                                                               ranges[(size_t)bq].t1), nT);
+            any = any || extents[(size_t)bq].t0 != ranges[(size_t)bq].t0 || extents[(size_t)bq].t1 != ranges[(size_t)bq].t1;
+        }
+        overlap = any;
+    }
     // Who holds a block?  A block whose tile rows all lie in this rank's rows is OWNED: it is
     // extracted, inverted and applied here only, and its piece of w is all-gathered.  Blocks
     // that straddle a boundary between ranks (none when the host layer aligns the partition with
@@ -945,6 +1107,7 @@ int cg_solve_caps(icqb_ctx* ctx, uint64_t dA_, int64_t n, int64_t ld, int storag
     std::vector<GatherDesc> hgather;
     std::vector<long long> sendLen((size_t)P, 0);
     long long denseDoubles = 0, denseRows = 0, denseRowsPad = 0, kMaxTiles = 0, repDoubles = 0, repOff = 0;
+    long long updRowsPad = 0;
     int nOwn = 0;
     for (int pass = 0; pass < 2; ++pass) {
         for (int bq = 0; bq < nAll; ++bq) {
@@ -962,13 +1125,17 @@ int cg_solve_caps(icqb_ctx* ctx, uint64_t dA_, int64_t n, int64_t ld, int storag
             }
             if ((pass == 0 && !mine) || (pass == 1 && !rep)) continue;
             DenseDesc D;
-            D.t0 = ranges[bq].t0;
-            D.tiles = ranges[bq].t1 - ranges[bq].t0;
+            D.t0 = extents[bq].t0;
+            D.tiles = extents[bq].t1 - extents[bq].t0;
             D.m = D.tiles * kT;
-            D.valid = std::min<long long>(n, ranges[bq].t1 * kT) - D.t0 * kT;
+            D.valid = std::min<long long>(n, extents[bq].t1 * kT) - D.t0 * kT;
             D.off = denseDoubles;
             D.row0 = denseRows;
             D.row0pad = denseRowsPad;
+            D.core0 = ranges[bq].t0 * kT;
+            D.core1 = std::min<long long>(n, ranges[bq].t1 * kT);
+            D.urow0 = updRowsPad;
+            updRowsPad += (D.valid + kUpRows - 1) / kUpRows * kUpRows;
             denseDoubles += D.m * D.m;
             denseRows += D.valid;
             denseRowsPad += D.m;
@@ -1006,8 +1173,10 @@ int cg_solve_caps(icqb_ctx* ctx, uint64_t dA_, int64_t n, int64_t ld, int storag
         }();
         if (off) fusedUpdate = false;
     }
-    const long long nUpd = (denseRows + kUpRows - 1) / kUpRows;
-    const long long updDoubles = fusedUpdate ? 3 * nUpd : 0;
+    if (overlap) fusedUpdate = true;   // (its own kernel; shares the double-buffered residual)
+    const long long nUpd = overlap ? updRowsPad / kUpRows : (denseRows + kUpRows - 1) / kUpRows;
+    // partials of the update kernel; overlapping form: + CTA -> block table, + 1/sqrt(cover) per row
+    const long long updDoubles = fusedUpdate ? 3 * nUpd + (overlap ? (nUpd + 1) / 2 + n + 2 : 0) : 0;
     const long long need = small + denseDoubles + panelDoubles + descDoubles + tileDoubles +
                            gatherDoubles + gdescDoubles + updDoubles + 68;
     int rc = ensure_work(ctx, need);
@@ -1040,6 +1209,21 @@ int cg_solve_caps(icqb_ctx* ctx, uint64_t dA_, int64_t n, int64_t ld, int storag
     double* wrecv = wp; wp += sharded ? (long long)P * slot : 0;
     GatherDesc* dgather = reinterpret_cast<GatherDesc*>(wp); wp += gdescDoubles;
     double* updPart = wp; wp += updDoubles;
+    int* updBlock = reinterpret_cast<int*>(updPart + 3 * nUpd);
+    double* dcover = updPart + 3 * nUpd + (nUpd + 1) / 2 + 1;
+    std::vector<int> hUpdBlock;
+    std::vector<double> hCover;
+    if (overlap) {
+        hUpdBlock.resize((size_t)nUpd);
+        hCover.assign((size_t)n, 0.0);
+        for (int bq = 0; bq < nDense; ++bq) {
+            const DenseDesc& D = hdesc[(size_t)bq];
+            const long long q0 = D.urow0 / kUpRows, q1 = q0 + (D.valid + kUpRows - 1) / kUpRows;
+            for (long long q = q0; q < q1; ++q) hUpdBlock[(size_t)q] = bq;
+            for (long long i = D.t0 * kT; i < D.t0 * kT + D.valid; ++i) hCover[(size_t)i] += 1.0;
+        }
+        for (long long i = 0; i < n; ++i) hCover[(size_t)i] = 1.0 / sqrt(hCover[(size_t)i]);
+    }
     double* rbuf[2] = {B.r, fusedUpdate ? r_alt : B.r};
     // the residual of iteration k lives in rbuf[k & 1] (fused update: double-buffered)
     auto atIter = [&](long long kq) {
@@ -1052,6 +1236,10 @@ int cg_solve_caps(icqb_ctx* ctx, uint64_t dA_, int64_t n, int64_t ld, int storag
         updSmem = sizeof(double) * (size_t)(kMaxTiles * kT);
         ICQB_CUDA(ctx, cudaFuncSetAttribute(k_cg_update_dense, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)updSmem));
+        ICQB_CUDA(ctx, cudaFuncSetAttribute(k_cg_update_overlap<false>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)updSmem));
+        ICQB_CUDA(ctx, cudaFuncSetAttribute(k_cg_update_overlap<true>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)updSmem));
     }
     B.Minv = blocks;
     B.n = n;
@@ -1118,7 +1306,14 @@ int cg_solve_caps(icqb_ctx* ctx, uint64_t dA_, int64_t n, int64_t ld, int storag
     auto precondition = [&](int mode, int kk, int replace, const int* skipFlag) -> int {
         const CgBuf B = atIter(kk);   // (shadows the solver's: the residual buffer of iteration kk)
         const bool needW = (mode != kTrue) || replace;
-        if (needW && denseRows > 0) {
+        if (needW && overlap) {
+            // overlapping blocks: the weighted contributions of the extents are added into a zeroed w
+            int rco = check_cuda(ctx, cudaMemsetAsync(B.w, 0, sizeof(double) * (size_t)n, st), "cudaMemsetAsync w");
+            if (rco != ICQB_OK) return rco;
+            k_cg_update_overlap<true><<<(unsigned)nUpd, kUpThreads, updSmem, st>>>(
+                ddesc, updBlock, dense, dcover, kk, nullptr, B, B.r, nullptr, nullptr);
+            ctx->launches += 1;
+        } else if (needW && denseRows > 0) {
             k_dense_apply<<<(unsigned)((denseRows + 7) / 8), 256, 0, st>>>(ddesc, nDense, denseRows, dense,
                                                                          B.r, B.w, skipFlag);
             ctx->launches += 1;
@@ -1181,7 +1376,14 @@ int cg_solve_caps(icqb_ctx* ctx, uint64_t dA_, int64_t n, int64_t ld, int storag
                 k_cg_dot<<<vgrid, kT, 0, st>>>(B);
                 ctx->launches += 1;
             }
-            if (fusedUpdate) {
+            if (overlap) {
+                r2 = check_cuda(ctx, cudaMemsetAsync(B.w, 0, sizeof(double) * (size_t)n, st), "cudaMemsetAsync w");
+                if (r2 != ICQB_OK) return r2;
+                k_cg_update_overlap<false><<<(unsigned)nUpd, kUpThreads, updSmem, st>>>(
+                    ddesc, updBlock, dense, dcover, kk, x, B, rbuf[kk & 1], rbuf[(kk + 1) & 1], updPart);
+                ctx->launches += 1;
+                r2 = check_cuda(ctx, cudaGetLastError(), "k_cg_update_overlap launch");
+            } else if (fusedUpdate) {
                 k_cg_update_dense<<<(unsigned)nUpd, kUpThreads, updSmem, st>>>(
                     ddesc, nDense, dense, kk, x, B, rbuf[kk & 1], rbuf[(kk + 1) & 1], updPart);
                 ctx->launches += 1;
@@ -1217,6 +1419,11 @@ int cg_solve_caps(icqb_ctx* ctx, uint64_t dA_, int64_t n, int64_t ld, int storag
         // table of the partition: tile -> dense block (every tile belongs to one; blocks of a
         // single tile are dense blocks like the others, so the 128 x 128 set of cg.cu is not built)
         CG_CUDA(cudaMemcpyAsync(dtile, htile.data(), sizeof(int) * (size_t)nT, cudaMemcpyHostToDevice, st));
+        if (overlap) {
+            CG_CUDA(cudaMemcpyAsync(updBlock, hUpdBlock.data(), sizeof(int) * (size_t)nUpd, cudaMemcpyHostToDevice,
+                                    st));
+            CG_CUDA(cudaMemcpyAsync(dcover, hCover.data(), sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, st));
+        }
 
         // tables of the dense blocks, then: extract, all-reduce (replicated ones), block sweep, mirror
         if (sharded)

@@ -159,6 +159,7 @@ struct icqb_ctx {
                             // 2 larger diagonal blocks: block_starts, or caps over cap_head_tiles / cap_tail_tiles
     int64_t cap_head_tiles = 0, cap_tail_tiles = 0;
     std::vector<int64_t> block_starts;   // kind 2: first tile row of every diagonal block
+    std::vector<int64_t> block_ext0, block_ext1;   // kind 2, one rank: overlapping extents [ext0, ext1) of the blocks
     int64_t cg_replacements = 0, cg_products = 0;   // statistics of the last solve
     int64_t cg_bad_blocks = 0, cg_weak_pivots = 0;  // preconditioner blocks replaced by 1/diag, weak pivots
     double mixed_switch = 0.0;     // optional: relative residual below which products use float32 (0 = off)

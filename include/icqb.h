@@ -236,6 +236,18 @@ int icqb_cg_set_cap_tiles(icqb_ctx* ctx, int64_t head_tiles, int64_t tail_tiles)
  * extracted, inverted and applied by the rank that holds their rows.  nblocks = 0 clears the
  * partition (icqb_cg_set_cap_tiles then applies). */
 int icqb_cg_set_block_partition(icqb_ctx* ctx, const int64_t* starts, int64_t nblocks);
+/* Kind 2, one rank: OVERLAPPING blocks.  Block q of the partition is extended to the tile rows
+ * [ext_begin[q], ext_end[q]) (which must contain it; a row may lie in the extents of two
+ * consecutive blocks at most) and the preconditioner becomes the symmetric additive Schwarz
+ * operator  M^-1 = sum_q R_q^T D_q A_q^-1 D_q R_q,  A_q = the diagonal block of diag(rowscale) A
+ * over the extent, D_q = 1/sqrt(number of extents that hold the row).  One tile of overlap on
+ * either side of 4-tile blocks halves the iterations on the UV spheres (config C2: 45 instead of
+ * 91; tools/experiments/pcg_overlap.py) for the same set-up work and 11 % more traffic in the
+ * preconditioner step.  Ignored with several ranks (blocks are then applied by their owners,
+ * without overlap).  Call after icqb_cg_set_block_partition; nblocks = 0 clears the extents.
+ * No reference counterpart (the reference solves by LU). */
+int icqb_cg_set_block_extents(icqb_ctx* ctx, const int64_t* ext_begin, const int64_t* ext_end,
+                              int64_t nblocks);
 /* Statistics of the last icqb_cg_solve_dev: how often the recurrence residual was replaced
  * by the true residual b - A x (0 = the first confirmation passed), and how many matrix
  * products were enqueued (iterations + confirmations + the ones skipped behind the stop

@@ -94,7 +94,7 @@ class Ctx:
         self.check(self.lib.icqb_assemble_lower_dev(self.h, 5, ptr[0], ptr[1], ptr[2]))
         return bufs
 
-    def solve(self, g, storage, kind, caps=None, ld=0, maxit=500, starts=None):
+    def solve(self, g, storage, kind, caps=None, ld=0, maxit=500, starts=None, extents=None):
         n = self.n
         b = dev_array(self.lib, n)
         b[:] = self.rhs()
@@ -103,6 +103,10 @@ class Ctx:
         self.check(self.lib.icqb_cg_set_cap_tiles(self.h, *(caps or (0, 0))))
         st = numpy.asarray(starts or [], numpy.int64)
         self.check(self.lib.icqb_cg_set_block_partition(self.h, lp(st) if len(st) else None, len(st)))
+        if extents is not None:
+            e0 = numpy.asarray(extents[0], numpy.int64)
+            e1 = numpy.asarray(extents[1], numpy.int64)
+            self.check(self.lib.icqb_cg_set_block_extents(self.h, lp(e0), lp(e1), len(e0)))
         it, r2, ri = ctypes.c_int64(0), ctypes.c_double(0.), ctypes.c_double(0.)
         self.check(self.lib.icqb_cg_solve_dev(
             self.h, g.ctypes.data, n, ld, storage, self.lib.icqb_area2_dev(self.h), 0, b.ctypes.data,
@@ -110,19 +114,27 @@ class Ctx:
         return x, it.value, ri.value, b
 
 
-def model_iterations(g, a2, b, cuts):
+def model_iterations(g, a2, b, cuts, extents=None):
     """numpy model of the block-preconditioned CG of csrc/cg.cu with diagonal blocks
-    [cuts[k], cuts[k+1]): iterations to max|r/s| <= 5e-13 max|b|."""
+    [cuts[k], cuts[k+1]): iterations to max|r/s| <= 5e-13 max|b|.  ``extents`` (first rows, end
+    rows): overlapping blocks, weighted 1/sqrt(cover) on both sides (symmetric additive Schwarz)."""
     n = len(b)
     ms = a2[:, None] * g
     ms = 0.5 * (ms + ms.T)
     cuts = [c for c in cuts if c < n] + [n]
-    invs = [numpy.linalg.inv(ms[p:q, p:q]) for p, q in zip(cuts[:-1], cuts[1:])]
+    spans = list(zip(cuts[:-1], cuts[1:]))
+    if extents is not None:
+        spans = [(int(p), min(int(q), n)) for p, q in zip(*extents)]
+    cover = numpy.zeros(n)
+    for p, q in spans:
+        cover[p:q] += 1.
+    d = 1. / numpy.sqrt(cover)
+    invs = [numpy.linalg.inv(ms[p:q, p:q]) for p, q in spans]
 
     def pre(r):
-        out = numpy.empty_like(r)
-        for k, (p, q) in enumerate(zip(cuts[:-1], cuts[1:])):
-            out[p:q] = invs[k].dot(r[p:q])
+        out = numpy.zeros_like(r)
+        for k, (p, q) in enumerate(spans):
+            out[p:q] += d[p:q] * invs[k].dot(d[p:q] * r[p:q])
         return out
     x, r, p, rho_old = numpy.zeros(n), a2 * b, numpy.zeros(n), 1.
     w = pre(r)
@@ -429,6 +441,40 @@ def test_emulated_weak_pivot_in_a_preconditioner_block(emu, oracle_mod, kind, st
         assert bad.value == 1
     else:
         assert bad.value == 0 and weak.value >= 1
+    c.close()
+
+
+@pytest.mark.parametrize('nt,nph,starts,ext,storage', [
+    (20, 11, [0, 1, 2, 3], ([0, 0, 2, 3], [2, 3, 4, 4]), 1),     # single tiles, one tile of overlap
+    (20, 11, [0, 2], ([0, 1], [3, 4]), 1),                       # two blocks of two tiles
+    (20, 11, [0, 2], ([0, 1], [3, 4]), 0),                       # the same from row-block storage
+    (30, 15, [0, 2, 4, 6], ([0, 1, 3, 5], [3, 5, 7, 7]), 1),     # 840 triangles, 7 tile rows (last ragged)
+    (30, 15, [0, 3, 5], ([0, 3, 4], [3, 6, 7]), 1),              # a block that is not extended (sliver-run rule)
+])
+def test_emulated_overlapping_blocks(emu, oracle_mod, nt, nph, starts, ext, storage):
+    """Overlapping preconditioner blocks (icqb_cg_set_block_extents: symmetric additive Schwarz,
+    k_cg_update_overlap): backward error against the oracle's matrix and the iteration count of
+    the numpy model of the same operator."""
+    c = Ctx(emu, nt, nph)
+    n = c.n
+    ref = oracle_mod.green_matrix(c.xyz, c.tri, 5)
+    a2 = oracle_mod.area2(c.xyz, c.tri)
+    if storage == 1:
+        (g,) = c.assemble_lower()
+        ld = 0
+    else:
+        ld = (n + 15) // 16 * 16
+        g = dev_array(emu, (n, ld), 0.)
+        c.check(emu.icqb_set_rows(c.h, 0, n))
+        c.check(emu.icqb_assemble_dev(c.h, 5, g.ctypes.data, 0, ld))
+    x, iters, rinf, b = c.solve(g, storage, 2, ld=ld, starts=starts, extents=ext)
+    assert numpy.abs(b - ref.dot(x)).max() <= 1e-12 * numpy.abs(b).max()
+    rows = ([128 * t for t in ext[0]], [128 * t for t in ext[1]])
+    model = model_iterations(ref, a2, b, [128 * t for t in starts], extents=rows)
+    assert abs(iters - model) <= 1
+    # fewer iterations than the same partition without overlap
+    x0, iters0, _, _ = c.solve(g, storage, 2, ld=ld, starts=starts)
+    assert iters < iters0
     c.close()
 
 

@@ -526,3 +526,38 @@ def test_cell_and_point_data_survive_fan_split_and_refinement():
     s.setSourceFieldName('height')
     proj = s.getSourceArray(s.getSourceArrayIndex())
     assert numpy.abs(proj - (2. * cen[:, 0] + cen[:, 1])).max() < 1e-6
+
+
+def test_block_extents_properties():
+    """icqRowPartition.blockExtents: every extent contains its block, a tile row lies in the
+    extents of two consecutive blocks at most, no block but the sliver block itself reaches into a
+    run of sliver tiles, extents respect maxTiles -- on random partitions."""
+    import random
+    from icqsol_b200.bem import icqRowPartition as rp
+    rng = random.Random(11)
+    for trial in range(300):
+        nT = rng.randint(1, 90)
+        flagged = numpy.zeros(nT, bool)
+        for _ in range(rng.randint(0, 3)):
+            a = rng.randint(0, nT - 1)
+            flagged[a:a + rng.randint(1, 9)] = True
+        k = rng.choice([1, 2, 4, 8])
+        starts, runs = rp.sliverBlockPartition(None, numpy.zeros((nT * 128, 3), int), blockTiles=k, flagged=flagged,
+                                               budgetFraction=1e9)
+        ov = rng.choice([1, 2])
+        maxTiles = rng.choice([64, 12])
+        ext0, ext1 = rp.blockExtents(starts, nT, runs, overlapTiles=ov, maxTiles=maxTiles)
+        ends = list(starts[1:]) + [nT]
+        sliver = numpy.zeros(nT, bool)
+        for a, m in runs:
+            sliver[a:a + m] = True
+        cover = numpy.zeros(nT, int)
+        for q, (t0, t1) in enumerate(zip(starts, ends)):
+            assert ext0[q] <= t0 and ext1[q] >= t1 and 0 <= ext0[q] and ext1[q] <= nT
+            assert ext1[q] - ext0[q] <= max(maxTiles, t1 - t0)
+            cover[ext0[q]:ext1[q]] += 1
+            if q >= 2:
+                assert ext0[q] >= ext1[q - 2]
+            if not sliver[t0]:
+                assert not sliver[ext0[q]:t0].any() and not sliver[t1:ext1[q]].any()
+        assert cover.min() >= 1 and cover.max() <= 2

@@ -143,6 +143,11 @@ static inline int atomicAdd(int* p, int v) {
     *p = old + v;
     return old;
 }
+static inline double atomicAdd(double* p, double v) {
+    const double old = *p;
+    *p = old + v;
+    return old;
+}
 
 // explicitly rounded arithmetic (the build uses -ffp-contract=off)
 static inline double __dmul_rn(double a, double b) { return a * b; }
