@@ -61,11 +61,8 @@ FLOP_PER_EVAL_GK = 18.0    # + 1/r^3 (2 mul) and two weighted accumulations (2 f
 # diagonal blocks of the CG preconditioner, in 128-triangle tiles: (one rank, several ranks).  One
 # rank: blocks of 4 tiles extended by one tile on either side (overlapping blocks are a one-rank
 # feature, include/icqb.h icqb_cg_set_block_extents); several ranks: plain blocks of 8.
-# (Until the overlapping blocks have passed the GPU suite the default stays plain blocks of 8;
-# ICQB_BLOCK_OVERLAP=1 selects 4 + 1 + 1, as in icqBaseLaplaceSolver.DEFAULTS.)
-_OVERLAP = os.environ.get('ICQB_BLOCK_OVERLAP') == '1'
-DEFAULT_BLOCK_TILES = ((4 if _OVERLAP else 8), 8)
-DEFAULT_BLOCK_OVERLAP = ((1 if _OVERLAP else 0), 0)
+DEFAULT_BLOCK_TILES = (4, 8)
+DEFAULT_BLOCK_OVERLAP = (1, 0)
 
 
 def resolve_blocks(args, world):

@@ -47,12 +47,8 @@ class BaseLaplaceSolver(BaseSolver):
     # defaults of the solver options a caller leaves at None
     # blockTiles / blockOverlap: (one rank, several ranks) -- overlapping blocks are a
     # one-rank feature (include/icqb.h, icqb_cg_set_block_extents)
-    # Until the overlapping blocks have passed the GPU suite (tools/gpu_visits/r2_gpu17.sh) the
-    # default stays the configuration validated on hardware, plain blocks of 8 tiles;
-    # ICQB_BLOCK_OVERLAP=1 in the environment selects blocks of 4 tiles + 1 on either side.
-    _OVERLAP = os.environ.get('ICQB_BLOCK_OVERLAP') == '1'
-    DEFAULTS = {'preconditioner': 'block+caps', 'blockTiles': ((4 if _OVERLAP else 8), 8),
-                'blockOverlap': ((1 if _OVERLAP else 0), 0), 'assemblyVariant': 1, 'mixedPrecision': 0.}
+    DEFAULTS = {'preconditioner': 'block+caps', 'blockTiles': (4, 8), 'blockOverlap': (1, 0),
+                'assemblyVariant': 1, 'mixedPrecision': 0.}
 
     def __init__(self, pdata, max_edge_length, order=5, computeK=False, device=None,
                  storage='lower', preconditioner=None, blockTiles=None, assemblyVariant=None,

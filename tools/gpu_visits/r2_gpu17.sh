@@ -5,7 +5,7 @@
 tag=${1:-r2x}
 out=gpurun_out
 mkdir -p $out
-export ICQB_BLOCK_OVERLAP=1
+export ICQB_BLOCK_OVERLAP=1   # (at the time of the visit the overlapping blocks were opt-in; they became the one-rank default after it passed)
 timeout 150 python -m pytest tests -m gpu -q -x > $out/${tag}_pytest.log 2>&1; echo "pytest rc=$?"; tail -n 5 $out/${tag}_pytest.log
 timeout 60 python bench.py --gpus 1 --steps 20 --warmup 5 > $out/${tag}_bench.json 2> $out/${tag}_bench.err; echo "bench rc=$?"
 timeout 60 python bench.py --workload bolt --steps 2 --warmup 1 --e2e-steps 1 --no-cpu-baseline > $out/${tag}_bench_bolt.json 2> $out/${tag}_bench_bolt.err; echo "bolt rc=$?"
