@@ -711,6 +711,22 @@ def run_b200(args):
             'gpu_launches': int(launches),
             'clocks': sampler.summary(),
         }
+        # strong scaling: the one-GPU run of the SAME workload (`--gpus 1` runs config C2, not this
+        # mesh), as measured by this repository on a box of the same pool -- for the reader of the
+        # line; nothing below depends on it
+        if world > 1:
+            try:
+                ref_file = {'bolt': 'r2_bench_n1_bolt_final.json'}.get(wname)
+                if ref_file:
+                    with open(os.path.join(ROOT, 'profiles', ref_file)) as f:
+                        one = json.loads([ln for ln in f if ln.startswith('{')][-1])
+                    if one['config']['triangles'] == n:
+                        line['one_gpu_same_workload'] = {
+                            'ms_per_step': one['ms_per_step'], 'value': one['value'], 'unit': one['unit'],
+                            'speedup_of_this_run': one['ms_per_step'] / ms_per_step,
+                            'source': 'profiles/' + ref_file + ' (bench.py --workload bolt on one B200)'}
+            except Exception:
+                pass
         # `roofline` = the kernel with the larger share of the step
         dom = 'roofline_gemv' if line['roofline_gemv']['share_of_step'] > \
             line['roofline_assembly']['share_of_step'] else 'roofline_assembly'
