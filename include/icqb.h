@@ -241,9 +241,10 @@ int icqb_cg_set_block_partition(icqb_ctx* ctx, const int64_t* starts, int64_t nb
  * consecutive blocks at most) and the preconditioner becomes the symmetric additive Schwarz
  * operator  M^-1 = sum_q R_q^T D_q A_q^-1 D_q R_q,  A_q = the diagonal block of diag(rowscale) A
  * over the extent, D_q = 1/sqrt(number of extents that hold the row).  One tile of overlap on
- * either side of 4-tile blocks halves the iterations on the UV spheres (config C2: 45 instead of
- * 91; tools/experiments/pcg_overlap.py) for the same set-up work and 11 % more traffic in the
- * preconditioner step.  Ignored with several ranks (blocks are then applied by their owners,
+ * either side of 4-tile blocks halves the iterations on the UV spheres (config C2 on a B200: 45
+ * instead of 91, solve 18.3 instead of 32.6 ms; model: tools/experiments/pcg_overlap.py) for the
+ * same set-up work and 11 % more traffic in the preconditioner step.  What the solver classes
+ * select on one rank (icqRowPartition.blockExtents keeps the runs of sliver tiles whole).  Ignored with several ranks (blocks are then applied by their owners,
  * without overlap).  Call after icqb_cg_set_block_partition; nblocks = 0 clears the extents.
  * No reference counterpart (the reference solves by LU). */
 int icqb_cg_set_block_extents(icqb_ctx* ctx, const int64_t* ext_begin, const int64_t* ext_end,
